@@ -1,0 +1,36 @@
+import os
+import sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: test needs a CUDA device (B200)')
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+
+
+def group_scale(golden, prefix, group, Nm):
+    """max |F| over all components and modes of one vector field (E, B, J) or rho:
+    components that vanish by symmetry hold only rounding noise, so parity is
+    measured against the magnitude of the whole field."""
+    names = ['rho'] if group == 'rho' else [group + 'r', group + 't', group + 'z']
+    return max(np.abs(golden['%s%s_m%d' % (prefix, n, m)]).max() for n in names for m in range(Nm))
+
+
+def assert_close(a, b, rel, what='', scale=None):
+    """|a-b| <= rel * (max|a| + max|b|): the tolerance form of the reference's
+    own CPU/GPU parity test (tests/test_cpu_gpu_deposition.py:96-98)."""
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if scale is None:
+        scale = np.abs(a).max() + np.abs(b).max()
+    err = np.abs(a - b).max() if a.size else 0.
+    assert err <= rel * scale + 1e-300, '%s: max err %.3e > %.1e * %.3e' % (what, err, rel, scale)
