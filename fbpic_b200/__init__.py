@@ -1,0 +1,14 @@
+"""
+fbpic_b200 -- B200-native (sm_100a) implementation of FBPIC's per-step PIC hot loop
+behind the reference's own operator surface (Simulation.step / Particles / Fields /
+BoundaryCommunicator).  Host code is Python; every per-step operation runs in
+hand-written CUDA (plus cuFFT for the z-FFT) through the C ABI of
+include/fbpic_b200.h.  There is no CPU fallback.
+"""
+__version__ = '0.1.0'
+
+from .main import Simulation                      # noqa: F401
+from .particles import Particles                  # noqa: F401
+from .fields import Fields, BinomialSmoother      # noqa: F401
+from .boundaries import BoundaryCommunicator      # noqa: F401
+from ._lib import DeviceArray, cuda_available, B200Error   # noqa: F401

@@ -1,0 +1,380 @@
+"""
+`BoundaryCommunicator`: z-slab domain decomposition, guard-cell exchange of the
+fields, particle migration and open-boundary damping, on NCCL instead of
+mpi4py.  Mirrors fbpic/boundaries/boundary_communicator.py:28-1222 for the hot
+path (same constructor arguments, attribute and method names); the gather /
+scatter routines used by the diagnostics are out of scope.
+
+One process drives one GPU.  rank/size come from the launcher's environment
+(RANK, WORLD_SIZE: torchrun) -- the role `mpi4py.MPI.COMM_WORLD` plays in the
+reference (fbpic/utils/mpi.py:10-76).  The NCCL communicator lives inside the C
+library; its 128-byte unique id is broadcast once through torch.distributed
+(gloo), which is host plumbing only.
+
+The slab arithmetic (`decompose_z`, `halo_plan`) is pure Python so that it can
+be tested without a GPU.
+"""
+import ctypes
+import os
+import numpy as np
+from scipy.constants import c
+
+from . import _lib
+from . import host_tables as ht
+from ._lib import DeviceArray, call, ptr_array
+
+
+# ---------------------------------------------------------------------------
+# process group (replaces fbpic/utils/mpi.py)
+# ---------------------------------------------------------------------------
+class ProcessGroup(object):
+    """rank/size of the job and the NCCL communicator between the ranks."""
+
+    def __init__(self):
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.size = int(os.environ.get('WORLD_SIZE', '1'))
+        self._nccl_ready = False
+
+    def init_nccl(self):
+        if self._nccl_ready or self.size == 1:
+            return
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group('gloo')
+        ident = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            call.b2_nccl_unique_id(ident.ctypes.data)
+        t = torch.from_numpy(ident)
+        dist.broadcast(t, src=0)
+        call.b2_nccl_init(_lib.context().handle, ident.ctypes.data, self.rank, self.size)
+        self._nccl_ready = True
+
+
+_world = None
+
+
+def world():
+    global _world
+    if _world is None:
+        _world = ProcessGroup()
+    return _world
+
+
+# ---------------------------------------------------------------------------
+# pure slab arithmetic (testable on CPU)
+# ---------------------------------------------------------------------------
+def decompose_z(Nz_global, size, rank, n_guard, nz_damp, n_inject, with_damp=True, with_guard=True):
+    """(Nz, iz_start) of the local grid of `rank`; iz counted from the first cell of the
+    global physical domain (boundary_communicator.py:399-457: every rank gets
+    int(Nz/size) cells, the last one takes the remainder)."""
+    per = int(Nz_global / size)
+    Nz = per
+    iz = rank * per
+    if rank == size - 1:
+        Nz += Nz_global % size
+    if with_damp:
+        if rank == 0:
+            Nz += nz_damp + n_inject
+            iz -= nz_damp + n_inject
+        if rank == size - 1:
+            Nz += nz_damp + n_inject
+    if with_guard:
+        Nz += 2 * n_guard
+        iz -= n_guard
+    return Nz, iz
+
+
+def halo_plan(Nz, ng, method):
+    """Row ranges of a local [Nz, Nr] array involved in a guard-cell exchange
+    (field_buffer_handling.py:180-188, 270-347; boundaries/cuda_methods.py:56-69, 239-252).
+
+    Returns dict(send_l, send_r, recv_l, recv_r) of (start, stop) row ranges:
+      replace: send the inner `ng` valid rows, overwrite the guard rows;
+      add    : send guard+inner (2*ng rows), ADD into the same 2*ng rows."""
+    if method == 'replace':
+        return dict(send_l=(ng, 2 * ng), send_r=(Nz - 2 * ng, Nz - ng),
+                    recv_l=(0, ng), recv_r=(Nz - ng, Nz))
+    if method == 'add':
+        return dict(send_l=(0, 2 * ng), send_r=(Nz - 2 * ng, Nz),
+                    recv_l=(0, 2 * ng), recv_r=(Nz - 2 * ng, Nz))
+    raise ValueError(method)
+
+
+# ---------------------------------------------------------------------------
+class BoundaryCommunicator(object):
+
+    def __init__(self, Nz, zmin, zmax, Nr, rmax, Nm, dt, v_comoving, use_galilean, boundaries,
+                 n_order, n_guard, n_damp, cdt_over_dr, n_inject=None, exchange_period=None,
+                 use_all_mpi_ranks=True):
+        self.Nm = Nm
+        self._Nr = Nr
+        self._Nz_global_domain = Nz
+        self._zmin_global_domain = zmin
+        self.dz = (zmax - zmin) / self._Nz_global_domain
+        self.dr = rmax / self._Nr
+        if not isinstance(boundaries, dict) or 'z' not in boundaries or 'r' not in boundaries:
+            raise ValueError("The argument `boundaries` should be a dictionary,\n"
+                             "whose keys are 'z' and 'r'.")
+        if boundaries['z'] not in ('periodic', 'open'):
+            raise ValueError("Unrecognized `boundaries['z']`: '%s'" % boundaries['z'])
+        if boundaries['r'] not in ('reflective', 'open'):
+            raise ValueError("Unrecognized `boundaries['r']`: '%s'" % boundaries['r'])
+        if boundaries['r'] == 'open':
+            raise NotImplementedError("boundaries['r']='open' (radial PML) is out of scope of this build")
+        self.use_all_mpi_ranks = use_all_mpi_ranks
+        w = world()
+        if use_all_mpi_ranks and w.size > 1:
+            self.mpi_comm, self.rank, self.size = w, w.rank, w.size
+        else:
+            self.mpi_comm, self.rank, self.size = None, 0, 1
+        self.left_proc, self.right_proc = self.rank - 1, self.rank + 1
+        self.boundaries = boundaries
+        if boundaries['z'] == 'periodic':
+            if self.rank == 0:
+                self.left_proc = self.size - 1
+            if self.rank == self.size - 1:
+                self.right_proc = 0
+        else:
+            if self.rank == 0:
+                self.left_proc = None
+            if self.rank == self.size - 1:
+                self.right_proc = None
+        # guard cells (boundary_communicator.py:225-254)
+        if n_guard is None:
+            if n_order == -1:
+                self.n_guard = 64
+                if self.size != 1:
+                    raise ValueError('When running with domain decomposition, you need to set\n'
+                                     'the argument `n_order` of the `Simulation` object to a\n'
+                                     'positive value (e.g. n_order=32).')
+            else:
+                self.n_guard = ht.stencil_reach(self._Nz_global_domain, self.dz, c * dt, n_order,
+                                                v_comoving, use_galilean) + 1
+        else:
+            self.n_guard = n_guard
+        if boundaries['z'] == 'periodic' and self.size == 1:
+            self.n_guard = 0
+        self.nz_damp, self.nr_damp = n_damp['z'], 0
+        if boundaries['z'] == 'periodic':
+            self.nz_damp, self.n_inject = 0, 0
+        else:
+            self.n_inject = int(self.n_guard / 2) if n_inject is None else n_inject
+        self.use_pml = False
+        # exchange period (boundary_communicator.py:281-304)
+        if exchange_period is None:
+            cells_per_step = 2. * c * dt / self.dz
+            self.exchange_period = int(((self.n_guard / 2) - 3) / cells_per_step)
+            if self.size == 1 and boundaries['z'] == 'periodic':
+                self.exchange_period = 1
+            if self.exchange_period < 1:
+                raise ValueError('Guard region size is too small for chosen timestep.')
+        else:
+            self.exchange_period = exchange_period
+        self.moving_win = None
+        self.left_damp = self.right_damp = None
+        self.d_left_damp = self.d_right_damp = None
+        if (self.nz_damp + self.n_inject) > 0:
+            if self.left_proc is None:
+                self.left_damp = self.generate_damp_array(self.n_guard, self.nz_damp, self.n_inject)
+            if self.right_proc is None:
+                self.right_damp = self.generate_damp_array(self.n_guard, self.nz_damp, self.n_inject)
+        self._halo_buf = {}
+
+    # ---- geometry (boundary_communicator.py:338-512) ----
+    def divide_into_domain(self):
+        zmin, zmax = self.get_zmin_zmax(local=True, with_damp=True, with_guard=True, rank=self.rank)
+        Nz, _ = self.get_Nz_and_iz(local=True, with_damp=True, with_guard=True, rank=self.rank)
+        if Nz < 4 * self.n_guard:
+            raise ValueError('The boundary guard region is larger than the physical domain size. '
+                             'Use fewer ranks or a smaller order of the field solver.')
+        return zmin, zmax, Nz
+
+    def get_Nr(self, with_damp):
+        return self._Nr + (self.nr_damp if with_damp else 0)
+
+    def get_rmax(self, with_damp):
+        return (self._Nr + (self.nr_damp if with_damp else 0)) * self.dr
+
+    def get_Nz_and_iz(self, local, with_damp, with_guard, rank=None):
+        if local:
+            if rank is None:
+                raise ValueError('For a local number of cells, the rank considered is needed.')
+            return decompose_z(self._Nz_global_domain, self.size, rank, self.n_guard, self.nz_damp,
+                               self.n_inject, with_damp, with_guard)
+        Nz, iz = self._Nz_global_domain, 0
+        if with_damp:
+            Nz += 2 * (self.nz_damp + self.n_inject)
+            iz -= self.nz_damp + self.n_inject
+        if with_guard:
+            Nz += 2 * self.n_guard
+            iz -= self.n_guard
+        return Nz, iz
+
+    def get_zmin_zmax(self, local, with_damp, with_guard, rank=None):
+        Nz, iz_start = self.get_Nz_and_iz(local=local, with_damp=with_damp, with_guard=with_guard, rank=rank)
+        zmin = self._zmin_global_domain + iz_start * self.dz
+        return zmin, zmin + Nz * self.dz
+
+    def shift_global_domain_positions(self, z_shift):
+        self._zmin_global_domain += z_shift
+
+    # ---- field guard cells (boundary_communicator.py:556-707) ----
+    def exchange_fields(self, interp, fldtype, method):
+        """Exchange the guard cells of `fldtype` ('E','B','J','rho') with the z-neighbours:
+        'replace' overwrites the local guard rows, 'add' sums guard+inner rows.  Row slabs of
+        a [Nz,Nr] array are contiguous, so slabs go straight from/to the field arrays over NCCL
+        ('add' receives into a scratch slab that one kernel adds in)."""
+        if self.size == 1:
+            return
+        self.mpi_comm.init_nccl()
+        ctx = _lib.context()
+        names = ('rho',) if fldtype == 'rho' else (fldtype + 'r', fldtype + 't', fldtype + 'z')
+        arrays = [getattr(interp[m], n) for m in range(self.Nm) for n in names]
+        Nz, Nr = arrays[0].shape
+        ng = self.n_guard
+        plan = halo_plan(Nz, ng, method)
+        nrow = plan['send_l'][1] - plan['send_l'][0]
+        recv = {}
+        if method == 'add':
+            key = (len(arrays), nrow, Nr)
+            if key not in self._halo_buf:
+                self._halo_buf[key] = (DeviceArray((len(arrays), nrow, Nr), np.complex128),
+                                       DeviceArray((len(arrays), nrow, Nr), np.complex128))
+            recv['l'], recv['r'] = self._halo_buf[key]
+        slab_bytes = nrow * Nr * 16
+        call.b2_nccl_group_start()
+        for i, a in enumerate(arrays):
+            if self.left_proc is not None:
+                call.b2_nccl_send(ctx.handle, a[plan['send_l'][0]:plan['send_l'][1]].ptr, slab_bytes,
+                                  self.left_proc, None)
+                dst = a[plan['recv_l'][0]:plan['recv_l'][1]].ptr if method == 'replace' \
+                    else recv['l'].ptr + i * slab_bytes
+                call.b2_nccl_recv(ctx.handle, dst, slab_bytes, self.left_proc, None)
+            if self.right_proc is not None:
+                call.b2_nccl_send(ctx.handle, a[plan['send_r'][0]:plan['send_r'][1]].ptr, slab_bytes,
+                                  self.right_proc, None)
+                dst = a[plan['recv_r'][0]:plan['recv_r'][1]].ptr if method == 'replace' \
+                    else recv['r'].ptr + i * slab_bytes
+                call.b2_nccl_recv(ctx.handle, dst, slab_bytes, self.right_proc, None)
+        call.b2_nccl_group_end()
+        if method == 'add':
+            for i, a in enumerate(arrays):
+                if self.left_proc is not None:
+                    call.b2_add_rows(ctx.handle, a[plan['recv_l'][0]:plan['recv_l'][1]].ptr,
+                                     recv['l'].ptr + i * slab_bytes, nrow, Nr, None)
+                if self.right_proc is not None:
+                    call.b2_add_rows(ctx.handle, a[plan['recv_r'][0]:plan['recv_r'][1]].ptr,
+                                     recv['r'].ptr + i * slab_bytes, nrow, Nr, None)
+
+    # ---- particles (boundary_communicator.py:710-826) ----
+    def exchange_particles(self, species, fld, time):
+        if self.n_guard == 0:
+            species.shift_periodic(fld.interp[0].zmin, fld.interp[0].zmax)
+        else:
+            self.exchange_particles_aperiodic_subdomain(species, fld, time)
+
+    def exchange_particles_aperiodic_subdomain(self, species, fld, time):
+        """Split the cell-sorted SoA at the guard boundaries (index ranges come from the
+        prefix sum, as remove_particles_gpu does: particle_buffer_handling.py:178-317),
+        send the two outer ranges to the neighbours and rebuild [from-left | kept | from-right]
+        (add_buffers_gpu :424-512).  Particles leaving through an open end are dropped."""
+        from .particles import FLOAT_ATTRS
+        species._need_gpu()
+        ctx = _lib.context()
+        g0 = fld.interp[0]
+        Nz, Nr, ng = g0.Nz, g0.Nr, self.n_guard
+        if not species.sorted:
+            species.sort_particles(fld)
+            species.sorted = True
+        # split indices from the prefix sum (particle_buffer_handling.py:214-236)
+        iz_min = max(ng, 0)
+        iz_max = min(Nz - ng + 1, Nz)
+        ps = species.prefix_sum
+        i_min = int(ps[iz_min * (Nr + 1) - 1:iz_min * (Nr + 1)].get()[0]) if iz_min * (Nr + 1) - 1 >= 0 else 0
+        i_max = int(ps[iz_max * (Nr + 1) - 1:iz_max * (Nr + 1)].get()[0])
+        N = species.Ntot
+        n_send_l = i_min if self.left_proc is not None else 0
+        n_send_r = (N - i_max) if self.right_proc is not None else 0
+        n_stay = i_max - i_min
+        n_recv_l = n_recv_r = 0
+        if self.size > 1:
+            self.mpi_comm.init_nccl()
+            cnt = DeviceArray.from_numpy(np.array([n_send_l, n_send_r, 0, 0], dtype=np.int64))
+            call.b2_nccl_group_start()
+            if self.left_proc is not None:
+                call.b2_nccl_send(ctx.handle, cnt.ptr, 8, self.left_proc, None)
+                call.b2_nccl_recv(ctx.handle, cnt.ptr + 16, 8, self.left_proc, None)
+            if self.right_proc is not None:
+                call.b2_nccl_send(ctx.handle, cnt.ptr + 8, 8, self.right_proc, None)
+                call.b2_nccl_recv(ctx.handle, cnt.ptr + 24, 8, self.right_proc, None)
+            call.b2_nccl_group_end()
+            h = cnt.get()
+            n_recv_l, n_recv_r = int(h[2]), int(h[3])
+        n_new = n_recv_l + n_stay + n_recv_r
+        new = {k: DeviceArray(n_new, np.float64) for k in FLOAT_ATTRS}
+        if self.size > 1:
+            call.b2_nccl_group_start()
+            for k in FLOAT_ATTRS:
+                old = getattr(species, k)
+                if self.left_proc is not None:
+                    if n_send_l:
+                        call.b2_nccl_send(ctx.handle, old.ptr, 8 * n_send_l, self.left_proc, None)
+                    if n_recv_l:
+                        call.b2_nccl_recv(ctx.handle, new[k].ptr, 8 * n_recv_l, self.left_proc, None)
+                if self.right_proc is not None:
+                    if n_send_r:
+                        call.b2_nccl_send(ctx.handle, old.ptr + 8 * i_max, 8 * n_send_r, self.right_proc, None)
+                    if n_recv_r:
+                        call.b2_nccl_recv(ctx.handle, new[k].ptr + 8 * (n_recv_l + n_stay), 8 * n_recv_r,
+                                          self.right_proc, None)
+            call.b2_nccl_group_end()
+        for k in FLOAT_ATTRS:
+            if n_stay:
+                call.b2_memcpy_d2d(new[k].ptr + 8 * n_recv_l, getattr(species, k).ptr + 8 * i_min,
+                                   8 * n_stay, ctx.stream)
+        # periodic images: shift z by the box length (boundary_communicator.py:815-821)
+        Ltot = self._Nz_global_domain * self.dz
+        if self.right_proc == 0 and n_recv_r:
+            self._shift_z(new['z'], n_recv_l + n_stay, n_recv_r, +Ltot)
+        if self.left_proc == self.size - 1 and n_recv_l:
+            self._shift_z(new['z'], 0, n_recv_l, -Ltot)
+        for k in FLOAT_ATTRS:
+            setattr(species, k, new[k])
+        species.Ntot = n_new
+        for k in ('Ex', 'Ey', 'Ez', 'Bx', 'By', 'Bz'):
+            setattr(species, k, DeviceArray(n_new, np.float64))
+        species._alloc_sort_arrays()
+        species.sorted = False
+
+    @staticmethod
+    def _shift_z(z, start, count, dz_shift):
+        """z[start:start+count] += dz_shift for the periodic images received across the ring
+        closure (only the two end ranks, only on particle-exchange steps)."""
+        h = z[start:start + count].get()
+        z[start:start + count].set(h + dz_shift)
+
+    # ---- open-boundary damping (boundary_communicator.py:828-945) ----
+    def generate_damp_array(self, n_guard, nz_damp, n_inject):
+        return ht.damp_array(n_guard, nz_damp, n_inject)
+
+    def damp_EB_open_boundary(self, interp):
+        if self.nz_damp == 0:
+            return
+        nd = self.n_guard + self.nz_damp + self.n_inject
+        left, right = self.left_proc is None, self.right_proc is None
+        if not (left or right):
+            return
+        if self.d_left_damp is None:
+            arr = self.left_damp if self.left_damp is not None else self.right_damp
+            self.d_left_damp = self.d_right_damp = DeviceArray.from_numpy(arr)
+        arrays = [getattr(interp[m], n) for m in range(len(interp))
+                  for n in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz')]
+        call.b2_damp_z(_lib.context().handle, len(arrays), ptr_array(arrays), self.d_left_damp.ptr, nd,
+                       int(left), int(right), interp[0].Nz, interp[0].Nr, None)
+
+    def damp_pml_EB(self, interp):
+        raise NotImplementedError('radial PML is out of scope of this build')
+
+    def move_grids(self, fld, ptcl, dt, time):
+        raise NotImplementedError('moving window: SURVEY 8(f) rank 1, planned next')

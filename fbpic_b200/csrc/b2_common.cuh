@@ -1,0 +1,78 @@
+// b2_common.cuh -- internal helpers shared by the kernels of libfbpic_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <atomic>
+#include "../../include/fbpic_b200.h"
+
+#define B2_C_LIGHT 299792458.0
+
+struct b2_ctx {
+    int device;
+    cudaStream_t stream;
+    // grow-only scratch (sort temp storage, permutation indices, ...)
+    void *scratch[4];
+    size_t scratch_bytes[4];
+    // cuFFT plans keyed by (Nz, Nr)
+    std::map<uint64_t, cufftHandle> fft_plans;
+    void *nccl_comm;
+    int nccl_rank, nccl_size;
+    int sm_count;
+};
+
+extern std::atomic<uint64_t> g_b2_launches;
+extern thread_local char g_b2_err[512];
+
+int b2_fail(int code, const char *what, const char *file, int line);
+
+#define B2_CUDA(call)                                                              \
+    do {                                                                           \
+        cudaError_t _e = (call);                                                   \
+        if (_e != cudaSuccess) return b2_fail((int)_e, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define B2_LAUNCHED()                                                              \
+    do {                                                                           \
+        g_b2_launches.fetch_add(1, std::memory_order_relaxed);                     \
+        cudaError_t _e = cudaPeekAtLastError();                                    \
+        if (_e != cudaSuccess) return b2_fail((int)_e, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+static inline cudaStream_t b2_stream_of(b2_ctx *ctx, void *stream) {
+    return stream ? (cudaStream_t)stream : (ctx ? ctx->stream : (cudaStream_t)0);
+}
+
+int b2_scratch(b2_ctx *ctx, int slot, size_t nbytes, void **ptr);
+
+// pointer bundle passed by value to multi-array kernels
+struct B2Ptrs {
+    void *p[B2_MAX_ARRAYS];
+};
+
+// ---- device helpers -------------------------------------------------------------------
+// (r_cell, z_cell) in cell units and cos/sin of the azimuth: the same arithmetic for the cell
+// key, the gather and the deposition (SURVEY Appendix A notation).
+struct B2Cyl {
+    double r, cs, sn, r_cell, z_cell;
+};
+__device__ __forceinline__ B2Cyl b2_cyl(double xj, double yj, double zj,
+                                        double invdz, double zmin, double invdr, double rmin) {
+    B2Cyl c;
+    // explicit round-to-nearest mul/add (never FMA-contracted): the cell key derived from
+    // r_cell / z_cell must be bit-identical to the CPU formula (cuda_sorting.py:64-72).
+    c.r = sqrt(__dadd_rn(__dmul_rn(xj, xj), __dmul_rn(yj, yj)));
+    if (c.r != 0.) {
+        double invr = 1. / c.r;
+        c.cs = xj * invr;
+        c.sn = yj * invr;
+    } else {
+        c.cs = 1.;
+        c.sn = 0.;
+    }
+    c.r_cell = __dadd_rn(__dmul_rn(invdr, __dsub_rn(c.r, rmin)), -0.5);
+    c.z_cell = __dadd_rn(__dmul_rn(invdz, __dsub_rn(zj, zmin)), -0.5);
+    return c;
+}

@@ -1,0 +1,444 @@
+// b2_particles.cu -- cell keys, stable cell sort + prefix sum, SoA permutation, field gather,
+// Vay push, position push and the fused gather+push kernel.
+#include "b2_common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
+// =====================================================================================
+// cell key (cuda_sorting.py:55-88)
+// =====================================================================================
+__device__ __forceinline__ int b2_cell_of(const B2Cyl &c, int Nz, int Nr) {
+    int ir_upper = (int)ceil(c.r_cell);
+    int iz_upper = (int)ceil(c.z_cell);
+    if (ir_upper > Nr) ir_upper = Nr;
+    if (iz_upper < 0) iz_upper += Nz;
+    else if (iz_upper > Nz - 1) iz_upper -= Nz;
+    return ir_upper + iz_upper * (Nr + 1);
+}
+
+__global__ void k_cell_index(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+                             const double *__restrict__ z, double invdz, double zmin, int Nz,
+                             double invdr, double rmin, int Nr, int32_t *__restrict__ cell_idx) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    B2Cyl c = b2_cyl(x[i], y[i], z[i], invdz, zmin, invdr, rmin);
+    cell_idx[i] = b2_cell_of(c, Nz, Nr);
+}
+
+// =====================================================================================
+// stable sort by cell + inclusive per-cell prefix sum (cuda_sorting.py:91-190)
+// =====================================================================================
+__global__ void k_iota(int64_t n, int32_t *v) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int32_t)i;
+}
+
+// prefix_sum[c] = #particles with key <= c = upper_bound(keys_sorted, c): one thread per cell,
+// cost independent of how the particles are distributed over the cells.
+__global__ void k_prefix_sum(int64_t n, const int32_t *__restrict__ keys_sorted,
+                             int32_t *__restrict__ prefix_sum, int ncells) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    int64_t lo = 0, hi = n;                       // first position whose key is > c
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (__ldg(keys_sorted + mid) <= c) lo = mid + 1;
+        else hi = mid;
+    }
+    prefix_sum[c] = (int32_t)lo;
+}
+
+__global__ void k_finish_sort(int64_t n, const int32_t *__restrict__ keys_sorted,
+                              const int32_t *__restrict__ idx32, int32_t *__restrict__ keys_out,
+                              int64_t *__restrict__ sorted_idx) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys_out[i] = keys_sorted[i];
+    sorted_idx[i] = (int64_t)idx32[i];
+}
+
+struct B2Perm {
+    const double *src[B2_MAX_ARRAYS];
+    double *dst[B2_MAX_ARRAYS];
+};
+template <int NA>
+__global__ void k_permute(int64_t n, const int64_t *__restrict__ sorted_idx, B2Perm a, int n_arrays) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t j = sorted_idx[i];
+    if (NA > 0) {
+#pragma unroll
+        for (int k = 0; k < NA; ++k) a.dst[k][i] = __ldg(a.src[k] + j);
+    } else {
+        for (int k = 0; k < n_arrays; ++k) a.dst[k][i] = __ldg(a.src[k] + j);
+    }
+}
+
+// =====================================================================================
+// gather (gathering/cuda_methods.py:26-354, inline_functions.py:9-187), all modes in one pass
+// =====================================================================================
+struct B2Grids {
+    const double2 *g[6 * B2_MAX_MODES];   // [m][Er,Et,Ez,Br,Bt,Bz]
+};
+
+template <int NM, bool CUBIC>
+__device__ __forceinline__ void b2_gather_one(const B2Cyl &c, const B2Grids &G, double rmax_gather,
+                                              int Nz, int Nr, double F[6]) {
+    double Fc[2][3] = {{0., 0., 0.}, {0., 0., 0.}};   // [E|B][r,t,z]
+    if (c.r < rmax_gather) {
+        if (!CUBIC) {
+            int ir_l = (int)floor(c.r_cell), ir_u = ir_l + 1;
+            int iz_l = (int)floor(c.z_cell), iz_u = iz_l + 1;
+            double Sr_l = ir_u - c.r_cell, Sr_u = c.r_cell - ir_l;
+            double Sz_l = iz_u - c.z_cell, Sz_u = c.z_cell - iz_l;
+            double Sr_g = 0.;
+            if (ir_l < 0) { Sr_g = Sr_l; Sr_l = 0.; ir_l = 0; }
+            if (ir_l > Nr - 1) ir_l = Nr - 1;
+            if (ir_u > Nr - 1) ir_u = Nr - 1;
+            if (iz_l < 0) iz_l += Nz;
+            if (iz_u < 0) iz_u += Nz;
+            if (iz_l > Nz - 1) iz_l -= Nz;
+            if (iz_u > Nz - 1) iz_u -= Nz;
+            const double S_ll = Sz_l * Sr_l, S_lu = Sz_l * Sr_u, S_ul = Sz_u * Sr_l, S_uu = Sz_u * Sr_u;
+            const double S_lg = Sz_l * Sr_g, S_ug = Sz_u * Sr_g;
+            const bool on_axis = (ir_l == 0 && ir_u == 0);
+            const size_t o_ll = (size_t)iz_l * Nr + ir_l, o_lu = (size_t)iz_l * Nr + ir_u;
+            const size_t o_ul = (size_t)iz_u * Nr + ir_l, o_uu = (size_t)iz_u * Nr + ir_u;
+            const size_t o_l0 = (size_t)iz_l * Nr, o_u0 = (size_t)iz_u * Nr;
+            double e_re = 1., e_im = 0.;
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                const double flip = (m & 1) ? -1. : 1.;
+                const double factor = (m == 0) ? 1. : 2.;
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const double2 *a = G.g[6 * m + 3 * f + k];
+                        double2 v;
+                        double re = 0., im = 0.;
+                        v = __ldg(a + o_ll); re += S_ll * v.x; im += S_ll * v.y;
+                        v = __ldg(a + o_lu); re += S_lu * v.x; im += S_lu * v.y;
+                        v = __ldg(a + o_ul); re += S_ul * v.x; im += S_ul * v.y;
+                        v = __ldg(a + o_uu); re += S_uu * v.x; im += S_uu * v.y;
+                        if (on_axis) {
+                            const double sgn = (k == 2) ? flip : -flip;
+                            v = __ldg(a + o_l0); re += sgn * S_lg * v.x; im += sgn * S_lg * v.y;
+                            v = __ldg(a + o_u0); re += sgn * S_ug * v.x; im += sgn * S_ug * v.y;
+                        }
+                        Fc[f][k] += factor * (re * e_re - im * e_im);
+                    }
+                }
+                const double nr = e_re * c.cs + e_im * c.sn, ni = e_im * c.cs - e_re * c.sn;
+                e_re = nr; e_im = ni;
+            }
+        } else {
+            double Sr[4], Sz[4];
+            const int ir_lowest = (int)floor(c.r_cell) - 1;
+            const double rl = c.r_cell - ir_lowest;
+            Sr[0] = -1. / 6. * ((rl - 2.) * (rl - 2.) * (rl - 2.));
+            Sr[1] = 1. / 6. * (3. * ((rl - 1.) * (rl - 1.) * (rl - 1.)) - 6. * ((rl - 1.) * (rl - 1.)) + 4.);
+            Sr[2] = 1. / 6. * (3. * ((2. - rl) * (2. - rl) * (2. - rl)) - 6. * ((2. - rl) * (2. - rl)) + 4.);
+            Sr[3] = -1. / 6. * ((1. - rl) * (1. - rl) * (1. - rl));
+            const int iz_lowest = (int)floor(c.z_cell) - 1;
+            const double zl = c.z_cell - iz_lowest;
+            Sz[0] = -1. / 6. * ((zl - 2.) * (zl - 2.) * (zl - 2.));
+            Sz[1] = 1. / 6. * (3. * ((zl - 1.) * (zl - 1.) * (zl - 1.)) - 6. * ((zl - 1.) * (zl - 1.)) + 4.);
+            Sz[2] = 1. / 6. * (3. * ((2. - zl) * (2. - zl) * (2. - zl)) - 6. * ((2. - zl) * (2. - zl)) + 4.);
+            Sz[3] = -1. / 6. * ((1. - zl) * (1. - zl) * (1. - zl));
+            int irs[4], izs[4];
+            bool neg[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                int ir = ir_lowest + b;
+                neg[b] = (ir < 0);
+                if (ir < 0) ir = -ir - 1;
+                else if (ir > Nr - 1) ir = Nr - 1;
+                irs[b] = ir;
+                int iz = iz_lowest + b;
+                if (iz < 0) iz += Nz;
+                else if (iz > Nz - 1) iz -= Nz;
+                izs[b] = iz;
+            }
+            double e_re = 1., e_im = 0.;
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                const double flip = (m & 1) ? -1. : 1.;
+                const double factor = (m == 0) ? 1. : 2.;
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    double acc[3][2] = {{0., 0.}, {0., 0.}, {0., 0.}};
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const double sr_long = neg[b] ? Sr[b] * flip : Sr[b];
+                        const double sr_perp = neg[b] ? -Sr[b] * flip : Sr[b];
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            const size_t o = (size_t)izs[a] * Nr + irs[b];
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                const double w = Sz[a] * ((k == 2) ? sr_long : sr_perp);
+                                const double2 v = __ldg(G.g[6 * m + 3 * f + k] + o);
+                                acc[k][0] += w * v.x;
+                                acc[k][1] += w * v.y;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) Fc[f][k] += factor * (acc[k][0] * e_re - acc[k][1] * e_im);
+                }
+                const double nr = e_re * c.cs + e_im * c.sn, ni = e_im * c.cs - e_re * c.sn;
+                e_re = nr; e_im = ni;
+            }
+        }
+    }
+    F[0] = c.cs * Fc[0][0] - c.sn * Fc[0][1];
+    F[1] = c.sn * Fc[0][0] + c.cs * Fc[0][1];
+    F[2] = Fc[0][2];
+    F[3] = c.cs * Fc[1][0] - c.sn * Fc[1][1];
+    F[4] = c.sn * Fc[1][0] + c.cs * Fc[1][1];
+    F[5] = Fc[1][2];
+}
+
+template <int NM, bool CUBIC>
+__global__ void __launch_bounds__(256)
+k_gather(int64_t n, const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+         double rmax_gather, double invdz, double zmin, int Nz, double invdr, double rmin, int Nr, B2Grids G,
+         double *__restrict__ Ex, double *__restrict__ Ey, double *__restrict__ Ez,
+         double *__restrict__ Bx, double *__restrict__ By, double *__restrict__ Bz) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    B2Cyl c = b2_cyl(x[i], y[i], z[i], invdz, zmin, invdr, rmin);
+    double F[6];
+    b2_gather_one<NM, CUBIC>(c, G, rmax_gather, Nz, Nr, F);
+    Ex[i] = F[0]; Ey[i] = F[1]; Ez[i] = F[2];
+    Bx[i] = F[3]; By[i] = F[4]; Bz[i] = F[5];
+}
+
+// =====================================================================================
+// Vay pusher (push/inline_functions.py:11-48) and position push (push/cuda_methods.py:17-52)
+// =====================================================================================
+__device__ __forceinline__ void b2_vay(double &ux, double &uy, double &uz, double &inv_gamma,
+                                       const double F[6], double econst, double bconst) {
+    const double taux = bconst * F[3], tauy = bconst * F[4], tauz = bconst * F[5];
+    const double tau2 = taux * taux + tauy * tauy + tauz * tauz;
+    const double uxp = ux + econst * F[0] + inv_gamma * (uy * tauz - uz * tauy);
+    const double uyp = uy + econst * F[1] + inv_gamma * (uz * taux - ux * tauz);
+    const double uzp = uz + econst * F[2] + inv_gamma * (ux * tauy - uy * taux);
+    const double sigma = 1 + uxp * uxp + uyp * uyp + uzp * uzp - tau2;
+    const double utau = uxp * taux + uyp * tauy + uzp * tauz;
+    const double igf = sqrt(2. / (sigma + sqrt(sigma * sigma + 4 * (tau2 + utau * utau))));
+    const double tx = igf * taux, ty = igf * tauy, tz = igf * tauz, ut = igf * utau;
+    const double s = 1. / (1 + tau2 * igf * igf);
+    ux = s * (uxp + tx * ut + uyp * tz - uzp * ty);
+    uy = s * (uyp + ty * ut + uzp * tx - uxp * tz);
+    uz = s * (uzp + tz * ut + uxp * ty - uyp * tx);
+    inv_gamma = igf;
+}
+
+__global__ void k_push_p(int64_t n, double *__restrict__ ux, double *__restrict__ uy, double *__restrict__ uz,
+                         double *__restrict__ inv_gamma, const double *__restrict__ Ex,
+                         const double *__restrict__ Ey, const double *__restrict__ Ez,
+                         const double *__restrict__ Bx, const double *__restrict__ By,
+                         const double *__restrict__ Bz, double econst, double bconst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double F[6] = {Ex[i], Ey[i], Ez[i], Bx[i], By[i], Bz[i]};
+    double a = ux[i], b = uy[i], cz = uz[i], g = inv_gamma[i];
+    b2_vay(a, b, cz, g, F, econst, bconst);
+    ux[i] = a; uy[i] = b; uz[i] = cz; inv_gamma[i] = g;
+}
+
+__global__ void k_push_x(int64_t n, double *__restrict__ x, double *__restrict__ y, double *__restrict__ z,
+                         const double *__restrict__ ux, const double *__restrict__ uy,
+                         const double *__restrict__ uz, const double *__restrict__ inv_gamma,
+                         double chdt, double xp, double yp, double zp) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double g = inv_gamma[i];
+    x[i] += chdt * g * xp * ux[i];
+    y[i] += chdt * g * yp * uy[i];
+    z[i] += chdt * g * zp * uz[i];
+}
+
+// fused gather + push_p + push_x: one read and one write of the particle state per step
+template <int NM, bool CUBIC>
+__global__ void __launch_bounds__(256)
+k_gather_push(int64_t n, double *__restrict__ x, double *__restrict__ y, double *__restrict__ z,
+              double *__restrict__ ux, double *__restrict__ uy, double *__restrict__ uz,
+              double *__restrict__ inv_gamma, double rmax_gather, double invdz, double zmin, int Nz,
+              double invdr, double rmin, int Nr, B2Grids G, double econst, double bconst, double chdt) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double xj = x[i], yj = y[i], zj = z[i];
+    B2Cyl c = b2_cyl(xj, yj, zj, invdz, zmin, invdr, rmin);
+    double F[6];
+    b2_gather_one<NM, CUBIC>(c, G, rmax_gather, Nz, Nr, F);
+    double a = ux[i], b = uy[i], cz = uz[i], g = inv_gamma[i];
+    b2_vay(a, b, cz, g, F, econst, bconst);
+    ux[i] = a; uy[i] = b; uz[i] = cz; inv_gamma[i] = g;
+    x[i] = xj + chdt * g * 1. * a;
+    y[i] = yj + chdt * g * 1. * b;
+    z[i] = zj + chdt * g * 1. * cz;
+}
+
+__global__ void k_shift_periodic(int64_t n, double *__restrict__ z, double zmin, double zmax) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double l_box = zmax - zmin;
+    double zi = z[i];
+    while (zi >= zmax) zi -= l_box;
+    while (zi < zmin) zi += l_box;
+    z[i] = zi;
+}
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+static inline unsigned grid1d(int64_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
+
+template <int NM>
+static void launch_gather(bool cubic, unsigned g, cudaStream_t s, int64_t n, const double *x, const double *y,
+                          const double *z, double rg, double invdz, double zmin, int Nz, double invdr, double rmin,
+                          int Nr, const B2Grids &G, double *Ex, double *Ey, double *Ez, double *Bx, double *By,
+                          double *Bz) {
+    if (cubic) k_gather<NM, true><<<g, 256, 0, s>>>(n, x, y, z, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, Ex, Ey, Ez, Bx, By, Bz);
+    else k_gather<NM, false><<<g, 256, 0, s>>>(n, x, y, z, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, Ex, Ey, Ez, Bx, By, Bz);
+}
+template <int NM>
+static void launch_gather_push(bool cubic, unsigned g, cudaStream_t s, int64_t n, double *x, double *y, double *z,
+                               double *ux, double *uy, double *uz, double *ig, double rg, double invdz, double zmin,
+                               int Nz, double invdr, double rmin, int Nr, const B2Grids &G, double ec, double bc,
+                               double chdt) {
+    if (cubic) k_gather_push<NM, true><<<g, 256, 0, s>>>(n, x, y, z, ux, uy, uz, ig, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt);
+    else k_gather_push<NM, false><<<g, 256, 0, s>>>(n, x, y, z, ux, uy, uz, ig, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt);
+}
+
+extern "C" {
+
+int b2_cell_index(b2_ctx *ctx, int64_t n, const double *x, const double *y, const double *z, double invdz,
+                  double zmin, int Nz, double invdr, double rmin, int Nr, int32_t *cell_idx, void *stream) {
+    if (n <= 0) return 0;
+    k_cell_index<<<grid1d(n, 256), 256, 0, b2_stream_of(ctx, stream)>>>(n, x, y, z, invdz, zmin, Nz, invdr, rmin, Nr, cell_idx);
+    B2_LAUNCHED();
+    return 0;
+}
+
+int b2_sort_cells(b2_ctx *ctx, int64_t n, int32_t *cell_idx, int64_t *sorted_idx, int32_t *prefix_sum,
+                  int Nz, int Nr, void *stream) {
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    const int ncells = Nz * (Nr + 1);
+    if (n <= 0) {
+        B2_CUDA(cudaMemsetAsync(prefix_sum, 0, sizeof(int32_t) * (size_t)ncells, s));
+        return 0;
+    }
+    int end_bit = 1;
+    while ((1LL << end_bit) < (long long)ncells && end_bit < 31) ++end_bit;
+    size_t temp_bytes = 0;
+    int32_t *nul = nullptr;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, nul, nul, nul, nul, (int)n, 0, end_bit, s);
+    // scratch 0: [keys_sorted | idx_in | idx_sorted | cub temp]
+    const size_t na = ((size_t)n * sizeof(int32_t) + 255) & ~(size_t)255;
+    void *base;
+    int rc = b2_scratch(ctx, 0, 3 * na + temp_bytes, &base);
+    if (rc) return rc;
+    int32_t *keys_sorted = (int32_t *)base;
+    int32_t *idx_in = (int32_t *)((char *)base + na);
+    int32_t *idx_sorted = (int32_t *)((char *)base + 2 * na);
+    void *temp = (char *)base + 3 * na;
+    k_iota<<<grid1d(n, 256), 256, 0, s>>>(n, idx_in);
+    B2_LAUNCHED();
+    B2_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const int32_t *)cell_idx, keys_sorted,
+                                            (const int32_t *)idx_in, idx_sorted, (int)n, 0, end_bit, s));
+    g_b2_launches.fetch_add(4);
+    k_finish_sort<<<grid1d(n, 256), 256, 0, s>>>(n, keys_sorted, idx_sorted, cell_idx, sorted_idx);
+    B2_LAUNCHED();
+    k_prefix_sum<<<grid1d(ncells, 256), 256, 0, s>>>(n, keys_sorted, prefix_sum, ncells);
+    B2_LAUNCHED();
+    return 0;
+}
+
+int b2_permute(b2_ctx *ctx, int64_t n, const int64_t *sorted_idx, int n_arrays, const double *const *src,
+               double *const *dst, void *stream) {
+    if (n <= 0 || n_arrays <= 0) return 0;
+    if (n_arrays > B2_MAX_ARRAYS) return b2_fail(-3, "too many arrays", __FILE__, __LINE__);
+    B2Perm a;
+    for (int k = 0; k < n_arrays; ++k) { a.src[k] = src[k]; a.dst[k] = dst[k]; }
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    if (n_arrays == 8) k_permute<8><<<grid1d(n, 256), 256, 0, s>>>(n, sorted_idx, a, n_arrays);
+    else if (n_arrays == 14) k_permute<14><<<grid1d(n, 256), 256, 0, s>>>(n, sorted_idx, a, n_arrays);
+    else k_permute<0><<<grid1d(n, 256), 256, 0, s>>>(n, sorted_idx, a, n_arrays);
+    B2_LAUNCHED();
+    return 0;
+}
+
+int b2_gather(b2_ctx *ctx, int64_t n, const double *x, const double *y, const double *z, double rmax_gather,
+              double invdz, double zmin, int Nz, double invdr, double rmin, int Nr, int Nm,
+              const void *const *grids, int cubic, double *Ex, double *Ey, double *Ez, double *Bx, double *By,
+              double *Bz, void *stream) {
+    if (n <= 0) return 0;
+    if (Nm < 1 || Nm > 4) return b2_fail(-3, "b2_gather: Nm must be in 1..4", __FILE__, __LINE__);
+    B2Grids G;
+    for (int k = 0; k < 6 * Nm; ++k) G.g[k] = (const double2 *)grids[k];
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    unsigned g = grid1d(n, 256);
+#define B2_ARGS cubic != 0, g, s, n, x, y, z, rmax_gather, invdz, zmin, Nz, invdr, rmin, Nr, G, Ex, Ey, Ez, Bx, By, Bz
+    switch (Nm) {
+        case 1: launch_gather<1>(B2_ARGS); break;
+        case 2: launch_gather<2>(B2_ARGS); break;
+        case 3: launch_gather<3>(B2_ARGS); break;
+        default: launch_gather<4>(B2_ARGS); break;
+    }
+#undef B2_ARGS
+    B2_LAUNCHED();
+    return 0;
+}
+
+int b2_push_p(b2_ctx *ctx, int64_t n, double *ux, double *uy, double *uz, double *inv_gamma, const double *Ex,
+              const double *Ey, const double *Ez, const double *Bx, const double *By, const double *Bz, double q,
+              double m, double dt, void *stream) {
+    if (n <= 0) return 0;
+    const double econst = q * dt / (m * B2_C_LIGHT), bconst = 0.5 * q * dt / m;
+    k_push_p<<<grid1d(n, 256), 256, 0, b2_stream_of(ctx, stream)>>>(n, ux, uy, uz, inv_gamma, Ex, Ey, Ez, Bx, By, Bz, econst, bconst);
+    B2_LAUNCHED();
+    return 0;
+}
+
+int b2_push_x(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, const double *ux, const double *uy,
+              const double *uz, const double *inv_gamma, double dt, double xp, double yp, double zp, void *stream) {
+    if (n <= 0) return 0;
+    k_push_x<<<grid1d(n, 256), 256, 0, b2_stream_of(ctx, stream)>>>(n, x, y, z, ux, uy, uz, inv_gamma, B2_C_LIGHT * dt, xp, yp, zp);
+    B2_LAUNCHED();
+    return 0;
+}
+
+int b2_gather_push(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, double *ux, double *uy, double *uz,
+                   double *inv_gamma, double rmax_gather, double invdz, double zmin, int Nz, double invdr,
+                   double rmin, int Nr, int Nm, const void *const *grids, int cubic, double q, double m,
+                   double dt_p, double dt_x, void *stream) {
+    if (n <= 0) return 0;
+    if (Nm < 1 || Nm > 4) return b2_fail(-3, "b2_gather_push: Nm must be in 1..4", __FILE__, __LINE__);
+    B2Grids G;
+    for (int k = 0; k < 6 * Nm; ++k) G.g[k] = (const double2 *)grids[k];
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    unsigned g = grid1d(n, 256);
+    const double ec = q * dt_p / (m * B2_C_LIGHT), bc = 0.5 * q * dt_p / m, chdt = B2_C_LIGHT * dt_x;
+#define B2_ARGS cubic != 0, g, s, n, x, y, z, ux, uy, uz, inv_gamma, rmax_gather, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt
+    switch (Nm) {
+        case 1: launch_gather_push<1>(B2_ARGS); break;
+        case 2: launch_gather_push<2>(B2_ARGS); break;
+        case 3: launch_gather_push<3>(B2_ARGS); break;
+        default: launch_gather_push<4>(B2_ARGS); break;
+    }
+#undef B2_ARGS
+    B2_LAUNCHED();
+    return 0;
+}
+
+int b2_shift_periodic(b2_ctx *ctx, int64_t n, double *z, double zmin, double zmax, void *stream) {
+    if (n <= 0) return 0;
+    k_shift_periodic<<<grid1d(n, 256), 256, 0, b2_stream_of(ctx, stream)>>>(n, z, zmin, zmax);
+    B2_LAUNCHED();
+    return 0;
+}
+
+}  // extern "C"

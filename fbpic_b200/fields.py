@@ -1,0 +1,480 @@
+"""
+`Fields` and its per-mode containers, backed by libfbpic_b200.so.
+
+Mirrors the operator surface of fbpic/fields/fields.py:20-625 (`Fields`),
+interpolation_grid.py:20-306 (`InterpolationGrid`), spectral_grid.py:33-478
+(`SpectralGrid`), spectral_transform/spectral_transformer.py:21-223
+(`SpectralTransformer`), hankel.py:25 (`DHT`), fourier.py:27 (`FFT`) and
+psatd_coefs.py:15 (`PsatdCoeffs`): same class, method and attribute names.
+Arrays are NumPy on the host until `send_fields_to_gpu()`, `DeviceArray`s (HBM)
+afterwards, exactly like the reference swaps NumPy for CuPy arrays.
+
+Not built (out of scope): PML split fields, cross-deposition
+correction, correct_divE.
+"""
+import ctypes
+import numpy as np
+from scipy.constants import mu_0, epsilon_0
+
+from . import _lib
+from . import host_tables as ht
+from ._lib import DeviceArray, call, ptr_array, SpectralMode
+
+INTERP_FIELDS = ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'Jr', 'Jt', 'Jz', 'rho')
+SPECT_FIELDS = ('Ep', 'Em', 'Ez', 'Bp', 'Bm', 'Bz', 'Jp', 'Jm', 'Jz', 'rho_prev', 'rho_next')
+
+
+class BinomialSmoother(object):
+    """Binomial smoother description (fbpic/fields/smoothing.py:10-94)."""
+
+    def __init__(self, n_passes=1, compensator=False):
+        if type(n_passes) is int:
+            self.n_passes = {'z': n_passes, 'r': n_passes}
+        elif type(n_passes) is dict:
+            self.n_passes = n_passes
+        else:
+            raise ValueError('Invalid argument `n_passes`')
+        if type(compensator) is bool:
+            self.compensator = {'z': compensator, 'r': compensator}
+        elif type(compensator) is dict:
+            self.compensator = compensator
+        else:
+            raise ValueError('Invalid argument `compensator`')
+
+    def get_filter_array(self, kz, kr, dz, dr):
+        return ht.binomial_filters(kz, kr, dz, dr, self.n_passes, self.compensator)
+
+
+def _on_gpu(a):
+    return isinstance(a, DeviceArray)
+
+
+def _need_gpu(a):
+    if not _on_gpu(a):
+        raise _lib.B200Error('field data is on the host: call send_fields_to_gpu() '
+                             '(fbpic_b200 has no CPU path)')
+
+
+# =============================================================================
+class InterpolationGrid(object):
+    """Real-space (z, r) grid of one azimuthal mode (interpolation_grid.py:20-306)."""
+
+    def __init__(self, Nz, Nr, m, zmin, zmax, rmax, use_pml=False, use_cuda=True,
+                 use_ruyten_shapes=True, use_modified_volume=True):
+        if use_pml:
+            raise NotImplementedError('radial PML is out of scope of this build (SURVEY 4d)')
+        self.Nz, self.Nr, self.m, self.use_pml = Nz, Nr, m, False
+        dr = rmax / Nr
+        dz = (zmax - zmin) / Nz
+        self.dr, self.dz = dr, dz
+        self.invdr, self.invdz = 1. / dr, 1. / dz
+        self.rmin, self.rmax = 0., rmax
+        self.zmin, self.zmax = zmin, zmax
+        vol = ht.cell_volumes(m, Nr, rmax, dz, use_modified_volume)
+        self.invvol = 1. / vol
+        self.ruyten_linear_coef, self.ruyten_cubic_coef = ht.ruyten_coefs(vol, dr, dz, use_ruyten_shapes)
+        for k in INTERP_FIELDS:
+            setattr(self, k, np.zeros((Nz, Nr), dtype='complex'))
+        self.use_cuda = True
+        self.d_invvol = self.d_ruyten_linear_coef = self.d_ruyten_cubic_coef = None
+
+    @property
+    def z(self):
+        return self.zmin + (0.5 + np.arange(self.Nz)) * self.dz
+
+    @property
+    def r(self):
+        return self.rmin + (0.5 + np.arange(self.Nr)) * self.dr
+
+    def send_fields_to_gpu(self):
+        for k in INTERP_FIELDS:
+            setattr(self, k, _lib.to_device(getattr(self, k)))
+        if self.d_invvol is None:
+            self.d_invvol = DeviceArray.from_numpy(self.invvol)
+            self.d_ruyten_linear_coef = DeviceArray.from_numpy(self.ruyten_linear_coef)
+            self.d_ruyten_cubic_coef = DeviceArray.from_numpy(self.ruyten_cubic_coef)
+
+    def receive_fields_from_gpu(self):
+        for k in INTERP_FIELDS:
+            setattr(self, k, _lib.to_host(getattr(self, k)))
+
+    def _names(self, fieldtype):
+        if fieldtype == 'rho':
+            return ('rho',)
+        if fieldtype in ('E', 'B', 'J'):
+            return (fieldtype + 'r', fieldtype + 't', fieldtype + 'z')
+        raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
+
+    def erase(self, fieldtype):
+        for k in self._names(fieldtype):
+            a = getattr(self, k)
+            _need_gpu(a)
+            a.fill(0)
+
+    def divide_by_volume(self, fieldtype):
+        if fieldtype not in ('rho', 'J'):
+            raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
+        arrs = [getattr(self, k) for k in self._names(fieldtype)]
+        _need_gpu(arrs[0])
+        call.b2_scale_rows_by_r(_lib.context().handle, len(arrs), ptr_array(arrs), self.d_invvol.ptr,
+                                self.Nz, self.Nr, None)
+
+
+# =============================================================================
+class FFT(object):
+    """z-FFT of [Nz, Nr] arrays: cuFFT on the native layout (fourier.py:27-168)."""
+
+    def __init__(self, Nr, Nz, use_cuda=True, nthreads=None):
+        self.Nr, self.Nz = Nr, Nz
+        self.use_cuda = True
+
+    def transform(self, array_in, array_out):
+        _need_gpu(array_in)
+        call.b2_fft_z(_lib.context().handle, array_in.ptr, array_out.ptr, self.Nz, self.Nr, 0, None)
+
+    def inverse_transform(self, array_in, array_out):
+        _need_gpu(array_in)
+        call.b2_fft_z(_lib.context().handle, array_in.ptr, array_out.ptr, self.Nz, self.Nr, 1, None)
+
+
+class DHT(object):
+    """Discrete Hankel transform of order p for mode m (hankel.py:25-243): host-built
+    matrices, fp64 tensor-core GEMM on the device."""
+
+    def __init__(self, p, m, Nr, Nz, rmax, use_cuda=True):
+        self.p, self.m, self.Nr, self.Nz, self.rmax = p, m, Nr, Nz, rmax
+        self.M, self.invM, self.nu = ht.hankel_matrices(p, m, Nr, rmax)
+        self.r = (rmax * 1. / Nr) * (np.arange(Nr) + 0.5)
+        self.use_cuda = True
+        self.d_M = self.d_invM = None
+
+    def get_r(self):
+        return self.r
+
+    def get_nu(self):
+        return self.nu
+
+    def _upload(self):
+        if self.d_M is None:
+            self.d_M = DeviceArray.from_numpy(self.M)
+            self.d_invM = DeviceArray.from_numpy(self.invM)
+
+    def transform(self, F, G):
+        _need_gpu(F)
+        self._upload()
+        call.b2_dht(_lib.context().handle, F.ptr, G.ptr, self.d_M.ptr, None, self.Nz, self.Nr, None)
+
+    def inverse_transform(self, G, F):
+        _need_gpu(G)
+        self._upload()
+        call.b2_dht(_lib.context().handle, G.ptr, F.ptr, self.d_invM.ptr, None, self.Nz, self.Nr, None)
+
+
+class SpectralTransformer(object):
+    """FFT + DHT of one mode (spectral_transformer.py:21-223).  The (r,t)<->(p,m)
+    combinations are fused into the Hankel GEMM (prologue / epilogue)."""
+
+    def __init__(self, Nz, Nr, m, rmax, use_cuda=True):
+        self.use_cuda = True
+        self.Nz, self.Nr, self.m = Nz, Nr, m
+        self.dht0 = DHT(m, m, Nr, Nz, rmax)
+        self.dhtp = DHT(m + 1, m, Nr, Nz, rmax)
+        self.dhtm = DHT(m - 1, m, Nr, Nz, rmax)
+        self.fft = FFT(Nr, Nz)
+        self.spect_buffer_r = self.spect_buffer_t = None
+
+    def _buffers(self):
+        if self.spect_buffer_r is None:
+            self.spect_buffer_r = DeviceArray((self.Nz, self.Nr), np.complex128)
+            self.spect_buffer_t = DeviceArray((self.Nz, self.Nr), np.complex128)
+            self.spect_buffer_p, self.spect_buffer_m = self.spect_buffer_r, self.spect_buffer_t
+            for d in (self.dht0, self.dhtp, self.dhtm):
+                d._upload()
+
+    def spect2interp_scal(self, spect_array, interp_array):
+        self._buffers()
+        self.dht0.inverse_transform(spect_array, self.spect_buffer_r)
+        self.fft.inverse_transform(self.spect_buffer_r, interp_array)
+
+    def spect2interp_vect(self, spect_array_p, spect_array_m, interp_array_r, interp_array_t):
+        self._buffers()
+        _need_gpu(spect_array_p)
+        call.b2_dht_pm_to_rt(_lib.context().handle, spect_array_p.ptr, spect_array_m.ptr,
+                             self.spect_buffer_r.ptr, self.spect_buffer_t.ptr,
+                             self.dhtp.d_invM.ptr, self.dhtm.d_invM.ptr, None, self.Nz, self.Nr, None)
+        self.fft.inverse_transform(self.spect_buffer_r, interp_array_r)
+        self.fft.inverse_transform(self.spect_buffer_t, interp_array_t)
+
+    def interp2spect_scal(self, interp_array, spect_array):
+        self._buffers()
+        self.fft.transform(interp_array, self.spect_buffer_r)
+        self.dht0.transform(self.spect_buffer_r, spect_array)
+
+    def interp2spect_vect(self, interp_array_r, interp_array_t, spect_array_p, spect_array_m):
+        self._buffers()
+        self.fft.transform(interp_array_r, self.spect_buffer_r)
+        self.fft.transform(interp_array_t, self.spect_buffer_t)
+        call.b2_dht_rt_to_pm(_lib.context().handle, self.spect_buffer_r.ptr, self.spect_buffer_t.ptr,
+                             spect_array_p.ptr, spect_array_m.ptr, self.dhtp.d_M.ptr, self.dhtm.d_M.ptr,
+                             None, self.Nz, self.Nr, None)
+
+
+# =============================================================================
+class PsatdCoeffs(object):
+    """PSATD coefficient tables of one mode (psatd_coefs.py:15-177); built on the
+    host from the 1-D kz, kr axes and uploaded once."""
+
+    NAMES_STD = ('C', 'S_w', 'j_coef', 'rho_prev_coef', 'rho_next_coef')
+    NAMES_COM = ('T_eb', 'T_cc', 'T_rho', 'j_corr_coef')
+
+    def __init__(self, kz, kr, m, dt, Nz, Nr, V=None, use_galilean=False, use_cuda=True):
+        kz1 = kz[:, 0] if np.ndim(kz) == 2 else kz
+        kr1 = kr[0, :] if np.ndim(kr) == 2 else kr
+        self.m, self.dt, self.V = m, dt, V
+        t = ht.psatd_coefficients(kz1, kr1, dt, V, use_galilean)
+        for k, v in t.items():
+            setattr(self, k, v)
+        self._device = {}
+
+    def device(self, name):
+        if name not in self._device:
+            a = getattr(self, name)
+            if self.V is not None and name not in ('C', 'S_w'):
+                a = a.astype(np.complex128)       # comoving kernels read complex coefficients
+            self._device[name] = DeviceArray.from_numpy(a)
+        return self._device[name]
+
+
+class SpectralGrid(object):
+    """Spectral (kz, kr) grid of one mode (spectral_grid.py:33-478)."""
+
+    def __init__(self, kz_modified, kr, m, kz_true, dz, dr, current_correction, smoother,
+                 use_pml=False, use_cuda=True):
+        if use_pml:
+            raise NotImplementedError('radial PML is out of scope of this build')
+        if current_correction != 'curl-free':
+            raise NotImplementedError("only current_correction='curl-free' is built (SURVEY 3d)")
+        Nz, Nr = len(kz_modified), len(kr)
+        self.Nz, self.Nr, self.m, self.use_pml = Nz, Nr, m, False
+        for k in SPECT_FIELDS:
+            setattr(self, k, np.zeros((Nz, Nr), dtype='complex'))
+        self.kz, self.kr = np.meshgrid(kz_modified, kr, indexing='ij')
+        self.kz_1d, self.kr_1d = np.ascontiguousarray(kz_modified), np.ascontiguousarray(kr)
+        self.filter_array_z, self.filter_array_r = smoother.get_filter_array(kz_true, kr, dz, dr)
+        self.inv_k2 = ht.inverse_k2(self.kz_1d, self.kr_1d)
+        self.field_shift = np.exp(1.j * kz_true * dz)
+        self.use_cuda = True
+        self.d_kz = self.d_kr = self.d_inv_k2 = self.d_filter_array_z = self.d_filter_array_r = None
+
+    def send_fields_to_gpu(self):
+        for k in SPECT_FIELDS:
+            setattr(self, k, _lib.to_device(getattr(self, k)))
+        if self.d_kz is None:
+            self.d_kz = DeviceArray.from_numpy(self.kz_1d)
+            self.d_kr = DeviceArray.from_numpy(self.kr_1d)
+            self.d_inv_k2 = DeviceArray.from_numpy(self.inv_k2)
+            self.d_filter_array_z = DeviceArray.from_numpy(self.filter_array_z)
+            self.d_filter_array_r = DeviceArray.from_numpy(self.filter_array_r)
+
+    def receive_fields_from_gpu(self):
+        for k in SPECT_FIELDS:
+            setattr(self, k, _lib.to_host(getattr(self, k)))
+
+    def _mode_struct(self, ps):
+        s = SpectralMode()
+        for k in SPECT_FIELDS:
+            a = getattr(self, k)
+            _need_gpu(a)
+            setattr(s, k, a.ptr)
+        s.kz, s.kr, s.inv_k2 = self.d_kz.ptr, self.d_kr.ptr, self.d_inv_k2.ptr
+        for k in PsatdCoeffs.NAMES_STD:
+            setattr(s, k, ps.device(k).ptr)
+        if ps.V is not None:
+            for k in PsatdCoeffs.NAMES_COM:
+                setattr(s, k, ps.device(k).ptr)
+        s.mu_0, s.epsilon_0 = mu_0, epsilon_0
+        return s
+
+    def correct_currents(self, dt, ps, current_correction):
+        if current_correction != 'curl-free':
+            raise NotImplementedError("only current_correction='curl-free' is built")
+        s = self._mode_struct(ps)
+        call.b2_correct_currents(_lib.context().handle, ctypes.byref(s), int(ps.V is not None),
+                                 1. / dt, self.Nz, self.Nr, None)
+
+    def push_eb_with(self, ps, use_true_rho=False):
+        """E, B push; the kernel also performs push_rho (rho_prev <- rho_next, rho_next <- 0),
+        so `push_rho()` below is a no-op marker when called right after it."""
+        assert self.m == ps.m
+        s = self._mode_struct(ps)
+        call.b2_push_eb(_lib.context().handle, ctypes.byref(s), int(ps.V is not None), ps.dt,
+                        0. if ps.V is None else ps.V, int(bool(use_true_rho)), self.Nz, self.Nr, None)
+        self._rho_pushed = True
+
+    def correct_and_push(self, ps, use_true_rho=False):
+        """Fused correct_currents + push_eb + push_rho: one pass over the mode's arrays."""
+        s = self._mode_struct(ps)
+        call.b2_correct_push(_lib.context().handle, ctypes.byref(s), int(ps.V is not None), ps.dt,
+                             0. if ps.V is None else ps.V, int(bool(use_true_rho)), self.Nz, self.Nr, None)
+        self._rho_pushed = True
+
+    def push_rho(self):
+        if getattr(self, '_rho_pushed', False):
+            self._rho_pushed = False
+            return
+        _need_gpu(self.rho_prev)
+        self.rho_prev.copy_from(self.rho_next)
+        self.rho_next.fill(0)
+
+    def filter(self, fieldtype):
+        if fieldtype in ('J', 'E', 'B'):
+            arrs = [getattr(self, fieldtype + c) for c in ('p', 'm', 'z')]
+        elif fieldtype in ('rho_prev', 'rho_next'):
+            arrs = [getattr(self, fieldtype)]
+        else:
+            raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
+        _need_gpu(arrs[0])
+        call.b2_filter(_lib.context().handle, len(arrs), ptr_array(arrs), self.d_filter_array_z.ptr,
+                       self.d_filter_array_r.ptr, self.Nz, self.Nr, None)
+
+
+# =============================================================================
+class Fields(object):
+    """All field data of the simulation (fields.py:20-625)."""
+
+    def __init__(self, Nz, zmax, Nr, rmax, Nm, dt, zmin=0., n_order=-1, v_comoving=None,
+                 use_pml=False, use_galilean=True, current_correction='curl-free', use_cuda=True,
+                 smoother=None, create_threading_buffers=False, use_ruyten_shapes=True,
+                 use_modified_volume=True):
+        if use_pml:
+            raise NotImplementedError('radial PML is out of scope of this build')
+        if current_correction not in ('curl-free', 'cross-deposition'):
+            raise ValueError('Unkown current correction:%s' % current_correction)
+        self.Nz, self.Nr, self.rmax, self.Nm, self.dt = Nz, Nr, rmax, Nm, dt
+        self.n_order, self.v_comoving, self.use_galilean = n_order, v_comoving, use_galilean
+        self.smoother = smoother if smoother is not None else BinomialSmoother(1, False)
+        self.use_cuda, self.use_pml = True, False
+        self.data_is_on_gpu = False
+        self.current_correction = current_correction
+        self.trans = [SpectralTransformer(Nz, Nr, m, rmax) for m in range(Nm)]
+        self.interp = [InterpolationGrid(Nz, Nr, m, zmin, zmax, rmax,
+                                         use_ruyten_shapes=use_ruyten_shapes,
+                                         use_modified_volume=use_modified_volume) for m in range(Nm)]
+        dz = (zmax - zmin) / Nz
+        kz_true = 2 * np.pi * np.fft.fftfreq(Nz, dz)
+        kz_modified = ht.modified_kz(kz_true, n_order, dz)
+        self.spect, self.psatd = [], []
+        for m in range(Nm):
+            kr = 2 * np.pi * self.trans[m].dht0.get_nu()
+            self.spect.append(SpectralGrid(kz_modified, kr, m, kz_true, self.interp[m].dz,
+                                           self.interp[m].dr, current_correction, self.smoother))
+            self.psatd.append(PsatdCoeffs(kz_modified, kr, m, dt, Nz, Nr, V=v_comoving,
+                                          use_galilean=use_galilean))
+        self.exchanged_source = {'J': False, 'rho_prev': False, 'rho_new': False,
+                                 'rho_next_xy': False, 'rho_next_z': False}
+
+    def send_fields_to_gpu(self):
+        for m in range(self.Nm):
+            self.interp[m].send_fields_to_gpu()
+            self.spect[m].send_fields_to_gpu()
+        self.data_is_on_gpu = True
+
+    def receive_fields_from_gpu(self):
+        for m in range(self.Nm):
+            self.interp[m].receive_fields_from_gpu()
+            self.spect[m].receive_fields_from_gpu()
+        self.data_is_on_gpu = False
+
+    # ---- spectral solver ----
+    def push(self, use_true_rho=False, check_exchanges=False):
+        if check_exchanges:
+            assert self.exchanged_source['J'] is True
+            if use_true_rho:
+                assert self.exchanged_source['rho_prev'] is True
+                assert self.exchanged_source['rho_next'] is True
+        for m in range(self.Nm):
+            self.spect[m].push_eb_with(self.psatd[m], use_true_rho)
+            self.spect[m].push_rho()
+
+    def correct_currents(self, check_exchanges=False):
+        if check_exchanges:
+            assert self.exchanged_source['rho_prev'] is False
+            assert self.exchanged_source['rho_next'] is False
+            assert self.exchanged_source['J'] is False
+        for m in range(self.Nm):
+            self.spect[m].correct_currents(self.dt, self.psatd[m], self.current_correction)
+
+    def correct_currents_and_push(self, use_true_rho=False):
+        """Fused Fields.correct_currents() + Fields.push() (single-domain fast path)."""
+        for m in range(self.Nm):
+            self.spect[m].correct_and_push(self.psatd[m], use_true_rho)
+            self.spect[m].push_rho()
+
+    # ---- transforms ----
+    def _vec(self, fieldtype):
+        return fieldtype in ('E', 'B', 'J')
+
+    def interp2spect(self, fieldtype):
+        for m in range(self.Nm):
+            g, s, tr = self.interp[m], self.spect[m], self.trans[m]
+            if self._vec(fieldtype):
+                f = fieldtype
+                tr.interp2spect_scal(getattr(g, f + 'z'), getattr(s, f + 'z'))
+                tr.interp2spect_vect(getattr(g, f + 'r'), getattr(g, f + 't'),
+                                     getattr(s, f + 'p'), getattr(s, f + 'm'))
+            elif fieldtype in ('rho_prev', 'rho_next'):
+                tr.interp2spect_scal(g.rho, getattr(s, fieldtype))
+            else:
+                raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
+
+    def spect2interp(self, fieldtype):
+        for m in range(self.Nm):
+            g, s, tr = self.interp[m], self.spect[m], self.trans[m]
+            if self._vec(fieldtype):
+                f = fieldtype
+                tr.spect2interp_scal(getattr(s, f + 'z'), getattr(g, f + 'z'))
+                tr.spect2interp_vect(getattr(s, f + 'p'), getattr(s, f + 'm'),
+                                     getattr(g, f + 'r'), getattr(g, f + 't'))
+            elif fieldtype in ('rho_prev', 'rho_next'):
+                tr.spect2interp_scal(getattr(s, fieldtype), g.rho)
+            else:
+                raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
+
+    def _partial_pairs(self, m, fieldtype):
+        g, s = self.interp[m], self.spect[m]
+        if self._vec(fieldtype):
+            f = fieldtype
+            return [(getattr(s, f + 'z'), getattr(g, f + 'z')), (getattr(s, f + 'p'), getattr(g, f + 'r')),
+                    (getattr(s, f + 'm'), getattr(g, f + 't'))]
+        if fieldtype in ('rho_prev', 'rho_next'):
+            return [(getattr(s, fieldtype), g.rho)]
+        raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
+
+    def spect2partial_interp(self, fieldtype):
+        """iFFT along z only (fields.py:431-485)."""
+        for m in range(self.Nm):
+            for sp, it in self._partial_pairs(m, fieldtype):
+                self.trans[m].fft.inverse_transform(sp, it)
+
+    def partial_interp2spect(self, fieldtype):
+        """FFT along z only (fields.py:487-537)."""
+        for m in range(self.Nm):
+            for sp, it in self._partial_pairs(m, fieldtype):
+                self.trans[m].fft.transform(it, sp)
+
+    # ---- interpolation-grid ops ----
+    def erase(self, fieldtype):
+        for m in range(self.Nm):
+            self.interp[m].erase(fieldtype)
+
+    def sum_reduce_deposition_array(self, fieldtype):
+        """CPU-thread reduction of the reference (fields.py:566-594): nothing to do on GPU."""
+        return
+
+    def filter_spect(self, fieldtype):
+        for m in range(self.Nm):
+            self.spect[m].filter(fieldtype)
+
+    def divide_by_volume(self, fieldtype):
+        for m in range(self.Nm):
+            self.interp[m].divide_by_volume(fieldtype)

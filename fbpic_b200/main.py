@@ -1,0 +1,279 @@
+"""
+`Simulation`: the PIC cycle driver, same constructor and `step()` contract as
+fbpic/main.py:38-1111, running every per-step operation on the B200 through
+libfbpic_b200.so (no Numba, no CuPy, no CPU fallback).
+
+Hot-path scope: gather / push / deposit / sort, z-FFT + Hankel GEMM,
+current correction + PSATD push, z guard-cell exchange and particle migration.
+Out of scope and therefore rejected loudly: PML (`boundaries['r']='open'`),
+cross-deposition, laser antennas, external fields, diagnostics, checkpoints,
+ionization, moving window (planned next).
+"""
+import numpy as np
+from scipy.constants import m_e, m_p, e, c
+
+from . import _lib
+from .fields import Fields
+from .particles import Particles
+from .boundaries import BoundaryCommunicator
+
+
+class Simulation(object):
+
+    def __init__(self, Nz, zmax, Nr, rmax, Nm, dt,
+                 p_zmin=-np.inf, p_zmax=np.inf, p_rmin=0, p_rmax=np.inf,
+                 p_nz=None, p_nr=None, p_nt=None, n_e=None, zmin=0.,
+                 n_order=-1, dens_func=None, filter_currents=True,
+                 v_comoving=None, use_galilean=True,
+                 initialize_ions=False, use_cuda=True, n_guard=None,
+                 n_damp={'z': 64, 'r': 32}, exchange_period=None,
+                 current_correction='curl-free',
+                 boundaries={'z': 'periodic', 'r': 'reflective'},
+                 gamma_boost=None, use_all_mpi_ranks=True,
+                 particle_shape='linear', verbose_level=0,
+                 smoother=None, use_ruyten_shapes=True, use_modified_volume=True,
+                 fused=True):
+        """Arguments as in fbpic/main.py:51-229.  `use_cuda` is accepted for drop-in
+        compatibility; this implementation only has the GPU path.  `fused=True` lets
+        `step()` use the fused kernels (gather+push, correct+push) -- same arithmetic,
+        fewer passes over HBM; `fused=False` issues one kernel per reference operator."""
+        self.use_cuda = True
+        self.fused = fused
+        if gamma_boost is not None:
+            raise NotImplementedError('gamma_boost conversion is host-side setup outside the hot path; '
+                                      'pass boosted-frame quantities directly')
+        self.boost = None
+        self.v_comoving = v_comoving
+        self.use_galilean = use_galilean if v_comoving is not None else False
+        self.dt = dt
+        cdt_over_dr = c * dt / (rmax / Nr)
+        self.comm = BoundaryCommunicator(Nz, zmin, zmax, Nr, rmax, Nm, dt, self.v_comoving,
+                                         self.use_galilean, boundaries, n_order, n_guard, n_damp,
+                                         cdt_over_dr, None, exchange_period, use_all_mpi_ranks)
+        self.use_pml = False
+        zmin, zmax, Nz = self.comm.divide_into_domain()
+        Nr = self.comm.get_Nr(with_damp=True)
+        rmax = self.comm.get_rmax(with_damp=True)
+        self.fld = Fields(Nz, zmax, Nr, rmax, Nm, dt, n_order=n_order, zmin=zmin,
+                          v_comoving=v_comoving, use_galilean=use_galilean,
+                          current_correction=current_correction, smoother=smoother,
+                          use_ruyten_shapes=use_ruyten_shapes,
+                          use_modified_volume=use_modified_volume)
+        self.grid_shape = self.fld.interp[0].Ez.shape
+        self.particle_shape = particle_shape
+        self.ptcl = []
+        if n_e is not None:
+            self.add_new_species(q=-e, m=m_e, n=n_e, dens_func=dens_func, p_nz=p_nz, p_nr=p_nr, p_nt=p_nt,
+                                 p_zmin=p_zmin, p_zmax=p_zmax, p_rmin=p_rmin, p_rmax=p_rmax)
+            if initialize_ions:
+                self.add_new_species(q=e, m=m_p, n=n_e, dens_func=dens_func, p_nz=p_nz, p_nr=p_nr,
+                                     p_nt=p_nt, p_zmin=p_zmin, p_zmax=p_zmax, p_rmin=p_rmin, p_rmax=p_rmax)
+        self.time = 0.
+        self.iteration = 0
+        self.filter_currents = filter_currents
+        self.external_fields, self.diags, self.checkpoints = [], [], []
+        self.laser_antennas, self.mirrors = [], []
+
+    # ------------------------------------------------------------------ data residency
+    def send_data_to_gpu(self):
+        """fbpic/utils/cuda.py:101-118"""
+        self.fld.send_fields_to_gpu()
+        for species in self.ptcl:
+            species.send_particles_to_gpu()
+
+    def receive_data_from_gpu(self):
+        """fbpic/utils/cuda.py:120-137"""
+        self.fld.receive_fields_from_gpu()
+        for species in self.ptcl:
+            species.receive_particles_from_gpu()
+
+    # ------------------------------------------------------------------ the PIC cycle
+    def step(self, N=1, correct_currents=True, correct_divE=False, use_true_rho=False,
+             move_positions=True, move_momenta=True, show_progress=False, keep_on_gpu=False):
+        """N PIC cycles, call order of fbpic/main.py:346-586.  `keep_on_gpu=True` skips the
+        final device->host copy (the data stays in HBM for the next call)."""
+        ptcl, fld, dt = self.ptcl, self.fld, self.dt
+        if correct_divE:
+            raise NotImplementedError('correct_divE is CPU-only in the reference and out of scope')
+        if self.comm.size > 1 and use_true_rho and correct_currents:
+            raise ValueError('`use_true_rho` cannot be used together with `correct_currents` '
+                             'in multi-proc mode.')
+        if self.external_fields or self.diags or self.checkpoints or self.laser_antennas or self.mirrors:
+            raise NotImplementedError('external fields, diagnostics, checkpoints, antennas and mirrors '
+                                      'are outside the hot path built here')
+        single = (self.comm.size == 1)
+        periodic_single = single and self.comm.n_guard == 0
+        fuse_gp = self.fused and move_positions and move_momenta
+        fuse_cp = self.fused and correct_currents and single
+
+        self.send_data_to_gpu()
+        self.comm.exchange_fields(fld.interp, 'E', 'replace')
+        self.comm.exchange_fields(fld.interp, 'B', 'replace')
+        self.comm.damp_EB_open_boundary(fld.interp)
+        fld.interp2spect('E')
+        fld.interp2spect('B')
+
+        for i_step in range(N):
+            if self.iteration % self.comm.exchange_period == 0 or i_step == 0:
+                for species in ptcl:
+                    self.comm.exchange_particles(species, fld, self.time)
+                self.deposit('rho_prev', exchange=(use_true_rho is True))
+            if i_step == 0:
+                self.deposit('J', exchange=True)
+
+            for species in ptcl:
+                species.keep_fields_sorted = True
+            if fuse_gp:
+                for species in ptcl:
+                    species.gather_and_push(fld.interp, self.comm, 0.5 * dt)
+            else:
+                for species in ptcl:
+                    species.gather(fld.interp, self.comm)
+                if move_momenta:
+                    for species in ptcl:
+                        species.push_p(self.time + 0.5 * dt)
+                if move_positions:
+                    for species in ptcl:
+                        species.push_x(0.5 * dt)
+            if self.use_galilean:
+                self.shift_galilean_boundaries(0.5 * dt)
+            for species in ptcl:
+                species.keep_fields_sorted = False
+
+            self.deposit('J', exchange=(correct_currents is False))
+            if move_positions:
+                for species in ptcl:
+                    species.push_x(0.5 * dt)
+            if self.use_galilean:
+                self.shift_galilean_boundaries(0.5 * dt)
+            self.deposit('rho_next', exchange=(use_true_rho is True))
+
+            if fuse_cp:
+                fld.correct_currents_and_push(use_true_rho)
+                fld.exchanged_source['J'] = True
+            else:
+                if correct_currents:
+                    fld.correct_currents(check_exchanges=(self.comm.size > 1))
+                    if self.comm.size > 1:
+                        fld.spect2partial_interp('J')
+                        self.comm.exchange_fields(fld.interp, 'J', 'add')
+                        fld.partial_interp2spect('J')
+                    fld.exchanged_source['J'] = True
+                fld.push(use_true_rho, check_exchanges=(self.comm.size > 1))
+            if self.comm.moving_win is not None:
+                self.comm.move_grids(fld, ptcl, dt, self.time)
+            self.exchange_and_damp_EB(skip_identity=periodic_single and self.fused)
+            self.time += dt
+            self.iteration += 1
+
+        fld.spect2interp('J')
+        if (not fld.exchanged_source['J']) and (self.comm.size > 1):
+            self.comm.exchange_fields(self.fld.interp, 'J', 'add')
+        fld.spect2interp('rho_prev')
+        if (not fld.exchanged_source['rho_prev']) and (self.comm.size > 1):
+            self.comm.exchange_fields(self.fld.interp, 'rho', 'add')
+        if not keep_on_gpu:
+            self.receive_data_from_gpu()
+        else:
+            _lib.context().sync()
+
+    def deposit(self, fieldtype, exchange=False, update_spectral=True, species_list=None):
+        """fbpic/main.py:588-670"""
+        fld = self.fld
+        if species_list is None:
+            species_list = [s for s in self.ptcl if not s.is_tracer]
+        if fieldtype.startswith('rho'):
+            grid_type = 'rho'
+        elif fieldtype == 'J':
+            grid_type = 'J'
+        else:
+            raise ValueError('Unknown fieldtype: %s' % fieldtype)
+        fld.erase(grid_type)
+        for species in species_list:
+            species.deposit(fld, grid_type)
+        fld.sum_reduce_deposition_array(grid_type)
+        fld.divide_by_volume(grid_type)
+        if exchange and self.comm.size > 1:
+            self.comm.exchange_fields(fld.interp, grid_type, 'add')
+        if update_spectral:
+            fld.interp2spect(fieldtype)
+            if self.filter_currents:
+                fld.filter_spect(fieldtype)
+            fld.exchanged_source[fieldtype] = exchange
+
+    def exchange_and_damp_EB(self, skip_identity=False):
+        """fbpic/main.py:719-769.  On a single periodic domain the iFFT / exchange / FFT round
+        trip is an identity (no neighbour, no damping): `skip_identity` drops those 12 FFTs per
+        mode and goes straight to spect2interp."""
+        fld = self.fld
+        if not skip_identity:
+            fld.spect2partial_interp('E')
+            fld.spect2partial_interp('B')
+            self.comm.exchange_fields(fld.interp, 'E', 'replace')
+            self.comm.exchange_fields(fld.interp, 'B', 'replace')
+            self.comm.damp_EB_open_boundary(fld.interp)
+            fld.partial_interp2spect('E')
+            fld.partial_interp2spect('B')
+        fld.spect2interp('E')
+        fld.spect2interp('B')
+
+    def shift_galilean_boundaries(self, dt):
+        """fbpic/main.py:772-789"""
+        shift_distance = self.v_comoving * dt
+        self.comm.shift_global_domain_positions(shift_distance)
+        for m in range(self.fld.Nm):
+            self.fld.interp[m].zmin += shift_distance
+            self.fld.interp[m].zmax += shift_distance
+
+    # ------------------------------------------------------------------ species
+    def add_new_species(self, q, m, n=None, dens_func=None, p_nz=None, p_nr=None, p_nt=None,
+                        p_zmin=-np.inf, p_zmax=np.inf, p_rmin=0, p_rmax=np.inf,
+                        uz_m=0., ux_m=0., uy_m=0., uz_th=0., ux_th=0., uy_th=0.,
+                        continuous_injection=True, boost_positions_in_dens_func=False, is_tracer=False):
+        """fbpic/main.py:792-1001 (lab frame only)."""
+        if n is not None:
+            for var in (p_nz, p_nr, p_nt):
+                if var is None:
+                    raise ValueError('If the density `n` is passed to `add_new_species`,\n'
+                                     'then the arguments `p_nz`, `p_nr` and `p_nt` need to be passed too.')
+            zmin_local, zmax_local = self.comm.get_zmin_zmax(local=True, rank=self.comm.rank,
+                                                            with_damp=False, with_guard=False)
+            p_zmin = max(zmin_local, p_zmin)
+            p_zmax = min(zmax_local, p_zmax)
+            p_rmax = min(self.comm.get_rmax(with_damp=False), p_rmax)
+            p_zmin, p_zmax, Npz = adapt_to_grid(self.fld.interp[0].z, p_zmin, p_zmax, p_nz)
+            p_rmin, p_rmax, Npr = adapt_to_grid(self.fld.interp[0].r, p_rmin, p_rmax, p_nr)
+            dz_particles = self.comm.dz / p_nz
+        else:
+            n = 0
+            p_zmin = p_zmax = p_rmin = p_rmax = 0
+            Npz = Npr = p_nt = 0
+            continuous_injection = False
+            dz_particles = 0.
+        sp = Particles(q=q, m=m, n=n, dens_func=dens_func, Npz=Npz, zmin=p_zmin, zmax=p_zmax,
+                       Npr=Npr, rmin=p_rmin, rmax=p_rmax, Nptheta=p_nt, dt=self.dt,
+                       particle_shape=self.particle_shape, grid_shape=self.grid_shape,
+                       ux_m=ux_m, uy_m=uy_m, uz_m=uz_m, ux_th=ux_th, uy_th=uy_th, uz_th=uz_th,
+                       continuous_injection=continuous_injection, dz_particles=dz_particles,
+                       is_tracer=is_tracer)
+        self.ptcl.append(sp)
+        return sp
+
+    def set_moving_window(self, v=c, **kw):
+        raise NotImplementedError('moving window: SURVEY 8(f) rank 1, planned next')
+
+
+def adapt_to_grid(x, p_xmin, p_xmax, p_nx, ncells_empty=0):
+    """Snap particle bounds to the grid and count the particles (fbpic/main.py:1056-1111)."""
+    xmin, xmax = x.min(), x.max()
+    dx = x[1] - x[0]
+    if p_xmin < xmin - 0.5 * dx:
+        p_xmin = xmin - 0.5 * dx
+    if p_xmax > xmax + (0.5 - ncells_empty) * dx:
+        p_xmax = xmax + (0.5 - ncells_empty) * dx
+    x_load = x[(x > p_xmin) & (x < p_xmax)]
+    Npx = len(x_load) * p_nx
+    if Npx > 0:
+        p_xmin = x_load.min() - 0.5 * dx
+        p_xmax = x_load.max() + 0.5 * dx
+    return p_xmin, p_xmax, Npx

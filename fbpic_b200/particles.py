@@ -1,0 +1,271 @@
+"""
+`Particles`: the species container of the operator surface, backed by the B200
+kernels of libfbpic_b200.so.  Mirrors fbpic/particles/particles.py:52-1094 for
+the hot path (gather, push_p, push_x, deposit, sort_particles,
+rearrange_particle_arrays, send/receive_particles_*): same method names,
+argument meaning and attribute names (`x..w`, `Ex..Bz`, `cell_idx`,
+`sorted_idx`, `prefix_sum`, `sorted`, `Ntot`, `q`, `m`).
+
+Out of scope here: ionization, Compton scattering, tracking.
+"""
+import ctypes
+import inspect
+import warnings
+import numpy as np
+
+from . import _lib
+from ._lib import DeviceArray, call, ptr_array
+
+FLOAT_ATTRS = ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w')
+FIELD_ATTRS = ('Ex', 'Ey', 'Ez', 'Bx', 'By', 'Bz')
+
+
+def _dens_func_args(dens_func):
+    args = inspect.getfullargspec(dens_func).args
+    if args and args[0] == 'self':
+        args = args[1:]
+    if args not in (['x', 'y', 'z'], ['z', 'r']):
+        raise ValueError("The argument `dens_func` needs to be a function of z, r\n"
+                         "or a function of x, y, z.")
+    return args
+
+
+def generate_evenly_spaced(Npz, zmin, zmax, Npr, rmin, rmax, Nptheta, n, dens_func,
+                           ux_m, uy_m, uz_m, ux_th, uy_th, uz_th):
+    """Host-side particle loader: regular (z, r, theta) lattice, one random azimuthal
+    offset per (z, r) position, weights n*r*dtheta*dr*dz.  Restates
+    fbpic/particles/injection/continuous_injection.py:203-275 (same draw order from
+    np.random, so the same seed gives the same particles as the reference)."""
+    if Npz * Npr * Nptheta <= 0:
+        e = np.empty(0)
+        return 0, e, e.copy(), e.copy(), e.copy(), e.copy(), e.copy(), e.copy(), e.copy()
+    dz = (zmax - zmin) * 1. / Npz
+    dr = (rmax - rmin) * 1. / Npr
+    dtheta = 2 * np.pi / Nptheta
+    z_reg = zmin + dz * (np.arange(Npz) + 0.5)
+    r_reg = rmin + dr * (np.arange(Npr) + 0.5)
+    theta_reg = dtheta * np.arange(Nptheta)
+    zp, rp, thetap = np.meshgrid(z_reg, r_reg, theta_reg, copy=True, indexing='ij')
+    thetap[:, :, :] = thetap + (2 * np.pi * np.random.rand(Npz, Npr))[:, :, np.newaxis]
+    r = rp.flatten()
+    x = r * np.cos(thetap.flatten())
+    y = r * np.sin(thetap.flatten())
+    z = zp.flatten()
+    w = n * r * dtheta * dr * dz
+    if dens_func is not None:
+        if _dens_func_args(dens_func) == ['x', 'y', 'z']:
+            w *= dens_func(x=x, y=y, z=z)
+        else:
+            w *= dens_func(z=z, r=r)
+    if np.any(w < 0):
+        warnings.warn('The specified particle density returned negative densities.\n'
+                      'No particles were generated in areas of negative density.')
+    keep = (w > 0)
+    Ntot = int(keep.sum())
+    x, y, z, w = x[keep], y[keep], z[keep], w[keep]
+    uz = uz_m * np.ones(Ntot) + uz_th * np.random.normal(size=Ntot)
+    ux = ux_m * np.ones(Ntot) + ux_th * np.random.normal(size=Ntot)
+    uy = uy_m * np.ones(Ntot) + uy_th * np.random.normal(size=Ntot)
+    inv_gamma = 1. / np.sqrt(1 + ux**2 + uy**2 + uz**2)
+    return Ntot, x, y, z, ux, uy, uz, inv_gamma, w
+
+
+class Particles(object):
+    """One species.  At the end/start of a PIC cycle the momenta are half a step
+    behind the positions (particles.py:62-63)."""
+
+    def __init__(self, q, m, n, Npz, zmin, zmax, Npr, rmin, rmax, Nptheta, dt,
+                 ux_m=0., uy_m=0., uz_m=0., ux_th=0., uy_th=0., uz_th=0.,
+                 dens_func=None, continuous_injection=True, grid_shape=None,
+                 particle_shape='linear', use_cuda=True, dz_particles=None, is_tracer=False):
+        if particle_shape not in ('linear', 'cubic'):
+            raise ValueError("`particle_shape` should be either 'linear' or 'cubic' "
+                             "but is `%s`" % particle_shape)
+        self.use_cuda = True            # this build only has the GPU path
+        self.data_is_on_gpu = False
+        Ntot, x, y, z, ux, uy, uz, inv_gamma, w = generate_evenly_spaced(
+            Npz, zmin, zmax, Npr, rmin, rmax, Nptheta, n, dens_func,
+            ux_m, uy_m, uz_m, ux_th, uy_th, uz_th)
+        self.Ntot, self.q, self.m, self.dt = Ntot, q, m, dt
+        self.is_tracer = is_tracer
+        self.x, self.y, self.z = x, y, z
+        self.ux, self.uy, self.uz = ux, uy, uz
+        self.inv_gamma, self.w = inv_gamma, w
+        for k in FIELD_ATTRS:
+            setattr(self, k, np.zeros(Ntot))
+        self.continuous_injection = continuous_injection
+        self.injector = None            # moving-window injection: SURVEY 8f rank 1 (next)
+        self.tracker = None
+        self.ionizer = None
+        self.compton_scatterer = None
+        self.n_integer_quantities = 0
+        self.n_float_quantities = 8
+        self.particle_shape = particle_shape
+        self.keep_fields_sorted = False
+        if grid_shape is None:
+            raise ValueError("A `grid_shape` is needed when running on the GPU.\n"
+                             "Please provide it when initializing particles.")
+        self.grid_shape = grid_shape
+        self.cell_idx = None
+        self.sorted_idx = None
+        self.prefix_sum = None
+        self.sorting_buffers = None
+        self.prefix_sum_shift = 0
+        self.sorted = False
+
+    # ------------------------------------------------------------------ device residency
+    def _alloc_sort_arrays(self):
+        Nz, Nr = self.grid_shape
+        self.cell_idx = DeviceArray(self.Ntot, np.int32)
+        self.sorted_idx = DeviceArray(self.Ntot, np.int64)
+        self.prefix_sum = DeviceArray(Nz * (Nr + 1), np.int32)
+        # double buffers for the one-pass SoA permutation (8 state + 6 field arrays)
+        self.sorting_buffers = [DeviceArray(self.Ntot, np.float64) for _ in range(14)]
+
+    def send_particles_to_gpu(self):
+        """particles.py:252-291"""
+        if self.data_is_on_gpu:
+            return
+        for k in FLOAT_ATTRS + FIELD_ATTRS:
+            setattr(self, k, DeviceArray.from_numpy(np.asarray(getattr(self, k), dtype=np.float64)))
+        self._alloc_sort_arrays()
+        self.sorted = False
+        self.data_is_on_gpu = True
+
+    def receive_particles_from_gpu(self):
+        """particles.py:293-333"""
+        if not self.data_is_on_gpu:
+            return
+        for k in FLOAT_ATTRS + FIELD_ATTRS:
+            setattr(self, k, getattr(self, k).get())
+        self.data_is_on_gpu = False
+
+    def _need_gpu(self):
+        if not self.data_is_on_gpu:
+            raise _lib.B200Error('particle data is on the host: call send_particles_to_gpu() '
+                                 '(fbpic_b200 has no CPU path)')
+
+    # ------------------------------------------------------------------ push / gather
+    def push_p(self, t):
+        """Vay momentum push (particles.py:557-636)."""
+        if self.q == 0:
+            return
+        self._need_gpu()
+        ctx = _lib.context()
+        call.b2_push_p(ctx.handle, self.Ntot, self.ux.ptr, self.uy.ptr, self.uz.ptr, self.inv_gamma.ptr,
+                       self.Ex.ptr, self.Ey.ptr, self.Ez.ptr, self.Bx.ptr, self.By.ptr, self.Bz.ptr,
+                       self.q, self.m, self.dt, None)
+
+    def push_x(self, dt, x_push=1., y_push=1., z_push=1.):
+        """Position push (particles.py:639-671)."""
+        self._need_gpu()
+        ctx = _lib.context()
+        call.b2_push_x(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr,
+                       self.ux.ptr, self.uy.ptr, self.uz.ptr, self.inv_gamma.ptr,
+                       dt, x_push, y_push, z_push, None)
+        self.sorted = False
+
+    @staticmethod
+    def _eb_grid_ptrs(grid):
+        return ptr_array([getattr(g, k) for g in grid for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz')])
+
+    def gather(self, grid, comm):
+        """E, B grid -> particles, all azimuthal modes in one pass (particles.py:673-837)."""
+        if self.q == 0:
+            return
+        self._need_gpu()
+        ctx = _lib.context()
+        g0 = grid[0]
+        call.b2_gather(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr,
+                       comm.get_rmax(with_damp=False), g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr,
+                       len(grid), self._eb_grid_ptrs(grid), int(self.particle_shape == 'cubic'),
+                       self.Ex.ptr, self.Ey.ptr, self.Ez.ptr, self.Bx.ptr, self.By.ptr, self.Bz.ptr, None)
+
+    def gather_and_push(self, grid, comm, dt_x):
+        """Fused gather + push_p + push_x(dt_x): the call sequence main.py:470-490 in one
+        kernel (the gathered fields stay in registers; Ex..Bz are not written)."""
+        if self.q == 0:
+            self.push_x(dt_x)
+            return
+        self._need_gpu()
+        ctx = _lib.context()
+        g0 = grid[0]
+        call.b2_gather_push(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr,
+                            self.ux.ptr, self.uy.ptr, self.uz.ptr, self.inv_gamma.ptr,
+                            comm.get_rmax(with_damp=False), g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin,
+                            g0.Nr, len(grid), self._eb_grid_ptrs(grid), int(self.particle_shape == 'cubic'),
+                            self.q, self.m, self.dt, dt_x, None)
+        self.sorted = False
+
+    # ------------------------------------------------------------------ sorting
+    def sort_particles(self, fld):
+        """cell key -> stable sort -> inclusive prefix sum -> permute the SoA
+        (particles.py:1049-1094, cuda_sorting.py)."""
+        self._need_gpu()
+        ctx = _lib.context()
+        g0 = fld.interp[0]
+        if self.cell_idx is None or self.cell_idx.size != self.Ntot:
+            self._alloc_sort_arrays()
+        call.b2_cell_index(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr,
+                           g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, self.cell_idx.ptr, None)
+        call.b2_sort_cells(ctx.handle, self.Ntot, self.cell_idx.ptr, self.sorted_idx.ptr,
+                           self.prefix_sum.ptr, g0.Nz, g0.Nr, None)
+        self.prefix_sum_shift = 0
+        self.rearrange_particle_arrays()
+
+    def rearrange_particle_arrays(self):
+        """One-pass permutation of all SoA attributes, then swap with the spare
+        buffers (particles.py:510-555 does one launch per attribute)."""
+        names = list(FLOAT_ATTRS)
+        if self.keep_fields_sorted:
+            names += list(FIELD_ATTRS)
+        src = [getattr(self, k) for k in names]
+        dst = self.sorting_buffers[:len(names)]
+        call.b2_permute(_lib.context().handle, self.Ntot, self.sorted_idx.ptr, len(names),
+                        ptr_array(src), ptr_array(dst), None)
+        for i, k in enumerate(names):
+            setattr(self, k, dst[i])
+            self.sorting_buffers[i] = src[i]
+
+    # ------------------------------------------------------------------ deposition
+    def deposit(self, fld, fieldtype):
+        """rho or J on the interpolation grid (particles.py:839-985): sorts first if
+        needed, then one launch for all modes."""
+        if self.q == 0:
+            return
+        assert fieldtype in ('rho', 'J')
+        self._need_gpu()
+        if not self.sorted:
+            self.sort_particles(fld=fld)
+            self.sorted = True
+        ctx = _lib.context()
+        grid = fld.interp
+        g0 = grid[0]
+        Nm = len(grid)
+        cubic = (self.particle_shape == 'cubic')
+        attr = 'd_ruyten_cubic_coef' if cubic else 'd_ruyten_linear_coef'
+        r0 = getattr(grid[0], attr)
+        rh = getattr(grid[1 if Nm > 1 else 0], attr)
+        if fieldtype == 'rho':
+            call.b2_deposit_rho(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr, self.w.ptr, self.q,
+                                g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, Nm,
+                                ptr_array([g.rho for g in grid]), self.prefix_sum.ptr, r0.ptr, rh.ptr,
+                                int(cubic), None)
+        else:
+            call.b2_deposit_J(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr, self.w.ptr, self.q,
+                              self.ux.ptr, self.uy.ptr, self.uz.ptr, self.inv_gamma.ptr,
+                              g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, Nm,
+                              ptr_array([getattr(g, k) for g in grid for k in ('Jr', 'Jt', 'Jz')]),
+                              self.prefix_sum.ptr, r0.ptr, rh.ptr, int(cubic), None)
+
+    # ------------------------------------------------------------------ out of scope hooks
+    def handle_elementary_processes(self, t):
+        """No ionization / Compton in this build (out of scope)."""
+        return
+
+    def shift_periodic(self, zmin, zmax):
+        """Single periodic domain: wrap z back into the box
+        (boundaries/particle_buffer_handling.py:514-560)."""
+        self._need_gpu()
+        call.b2_shift_periodic(_lib.context().handle, self.Ntot, self.z.ptr, zmin, zmax, None)
+        self.sorted = False

@@ -1,0 +1,197 @@
+/*
+ * fbpic_b200.h -- C ABI of libfbpic_b200.so: the B200 (sm_100a) implementation of
+ * FBPIC's per-step PIC hot loop.
+ *
+ * This is the drop-in boundary.  It replaces the reference's only
+ * FFI-like seam, `compile_cupy.__getitem__ -> call_kernel` (fbpic/utils/cuda.py:
+ * 434-541), through which every Numba kernel of the reference GPU path is
+ * launched, plus the three library calls of that path (cuBLAS dgemm hankel.py:
+ * 200-203, cuFFT fourier.py:78/121/153, Thrust argsort cuda_sorting.py:114).
+ *
+ * Conventions
+ *   - every pointer named d_* (or documented "device") is a raw device pointer;
+ *     complex128 grids are row-major [Nz][Nr] (z slow, r fast), interleaved re/im;
+ *   - every entry point returns 0 on success, else a cudaError_t / cufftResult /
+ *     ncclResult_t code (b2_error_string() formats the last failure);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the context stream);
+ *   - no global mutable state except inside the opaque b2_ctx (one per GPU);
+ *   - no host fallback: every function needs a CUDA device.
+ * Each declaration cites the reference interface it replaces (file:line relative
+ * to the FBPIC source tree).
+ */
+#ifndef FBPIC_B200_H
+#define FBPIC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2_ctx b2_ctx;
+
+#define B2_MAX_MODES 8      /* azimuthal modes handled by one launch            */
+#define B2_MAX_ARRAYS 32    /* pointers carried by one multi-array launch       */
+
+/* ---- runtime / memory: replaces cupy.asarray/.get and GpuMemoryManager,
+ *      fbpic/utils/cuda.py:101-182 ------------------------------------------ */
+int b2_device_count(int *count);
+int b2_ctx_create(int device, b2_ctx **ctx);
+int b2_ctx_destroy(b2_ctx *ctx);
+void *b2_ctx_stream(b2_ctx *ctx);
+const char *b2_error_string(void);
+const char *b2_version(void);
+int b2_malloc(void **d_ptr, size_t nbytes);
+int b2_free(void *d_ptr);
+int b2_host_alloc(void **h_ptr, size_t nbytes);       /* pinned host memory */
+int b2_host_free(void *h_ptr);
+int b2_memcpy_h2d(void *d_dst, const void *h_src, size_t nbytes, void *stream);
+int b2_memcpy_d2h(void *h_dst, const void *d_src, size_t nbytes, void *stream);
+int b2_memcpy_d2d(void *d_dst, const void *d_src, size_t nbytes, void *stream);
+int b2_memset(void *d_ptr, int value, size_t nbytes, void *stream);
+int b2_stream_sync(void *stream);
+int b2_device_sync(void);
+int b2_event_create(void **event);
+int b2_event_destroy(void *event);
+int b2_event_record(void *event, void *stream);
+int b2_event_elapsed_ms(void *start, void *stop, float *ms);   /* syncs on stop */
+/* number of kernels / library calls this library launched since load */
+uint64_t b2_launch_count(void);
+/* CUDA-graph capture of a sequence of b2_* calls on the context stream */
+int b2_graph_begin(b2_ctx *ctx);
+int b2_graph_end(b2_ctx *ctx, void **graph_exec);
+int b2_graph_launch(b2_ctx *ctx, void *graph_exec);
+int b2_graph_destroy(void *graph_exec);
+
+/* ---- particle sorting: get_cell_idx_per_particle (fbpic/particles/utilities/
+ *      cuda_sorting.py:22-88), sort_particles_per_cell (:91-122, Thrust argsort),
+ *      prefill_prefix_sum + incl_prefix_sum (:125-190), write_sorting_buffer
+ *      (:193-213) / Particles.rearrange_particle_arrays (particles.py:510-555).
+ *      Contract: sorted_idx == stable argsort(cell_idx); prefix_sum[c] = number of
+ *      particles with cell <= c; both bit-exact. ------------------------------- */
+int b2_cell_index(b2_ctx *ctx, int64_t n, const double *d_x, const double *d_y, const double *d_z,
+                  double invdz, double zmin, int Nz, double invdr, double rmin, int Nr,
+                  int32_t *d_cell_idx, void *stream);
+int b2_sort_cells(b2_ctx *ctx, int64_t n, int32_t *d_cell_idx /* in: keys, out: sorted keys */,
+                  int64_t *d_sorted_idx /* out */, int32_t *d_prefix_sum /* out, Nz*(Nr+1) */,
+                  int Nz, int Nr, void *stream);
+int b2_permute(b2_ctx *ctx, int64_t n, const int64_t *d_sorted_idx, int n_arrays,
+               const double *const *d_src /* host array of device pointers */,
+               double *const *d_dst, void *stream);
+
+/* ---- gather + push: gather_field_gpu_{linear,cubic}[_one_mode]
+ *      (fbpic/particles/gathering/cuda_methods.py:26,209; cuda_methods_one_mode.py:46,216),
+ *      push_p_gpu / push_x_gpu (fbpic/particles/push/cuda_methods.py:55,17),
+ *      shift_particles_periodic_cuda (fbpic/boundaries/particle_buffer_handling.py:637).
+ *      d_grids: host array of 6*Nm device pointers ordered [m][Er,Et,Ez,Br,Bt,Bz]. */
+int b2_gather(b2_ctx *ctx, int64_t n, const double *d_x, const double *d_y, const double *d_z,
+              double rmax_gather, double invdz, double zmin, int Nz, double invdr, double rmin, int Nr,
+              int Nm, const void *const *d_grids, int cubic,
+              double *d_Ex, double *d_Ey, double *d_Ez, double *d_Bx, double *d_By, double *d_Bz,
+              void *stream);
+int b2_push_p(b2_ctx *ctx, int64_t n, double *d_ux, double *d_uy, double *d_uz, double *d_inv_gamma,
+              const double *d_Ex, const double *d_Ey, const double *d_Ez,
+              const double *d_Bx, const double *d_By, const double *d_Bz,
+              double q, double m, double dt, void *stream);
+int b2_push_x(b2_ctx *ctx, int64_t n, double *d_x, double *d_y, double *d_z,
+              const double *d_ux, const double *d_uy, const double *d_uz, const double *d_inv_gamma,
+              double dt, double x_push, double y_push, double z_push, void *stream);
+/* fused Particles.gather + push_p + push_x(dt_x) (main.py:470-490): one pass over the SoA */
+int b2_gather_push(b2_ctx *ctx, int64_t n, double *d_x, double *d_y, double *d_z,
+                   double *d_ux, double *d_uy, double *d_uz, double *d_inv_gamma,
+                   double rmax_gather, double invdz, double zmin, int Nz, double invdr, double rmin, int Nr,
+                   int Nm, const void *const *d_grids, int cubic,
+                   double q, double m, double dt_p, double dt_x, void *stream);
+int b2_shift_periodic(b2_ctx *ctx, int64_t n, double *d_z, double zmin, double zmax, void *stream);
+
+/* ---- deposition: deposit_{rho,J}_gpu_{linear,cubic}[_one_mode]
+ *      (fbpic/particles/deposition/cuda_methods.py:28,202,466,751; cuda_methods_one_mode.py)
+ *      with the boundary folds of fbpic/fields/numba_methods.py:410-461.  Particles
+ *      must be cell-sorted (b2_sort_cells + b2_permute); sums are ADDED to the grids
+ *      (raw charge, not yet divided by the cell volume).
+ *      d_grids: host array of device pointers, rho: [m] ; J: [m][Jr,Jt,Jz].
+ *      d_ruyten0 / d_ruyten_hi: Ruyten coefficients (Nr+1) of mode 0 / modes >= 1. */
+int b2_deposit_rho(b2_ctx *ctx, int64_t n, const double *d_x, const double *d_y, const double *d_z,
+                   const double *d_w, double q, double invdz, double zmin, int Nz,
+                   double invdr, double rmin, int Nr, int Nm, void *const *d_grids,
+                   const int32_t *d_prefix_sum, const double *d_ruyten0, const double *d_ruyten_hi,
+                   int cubic, void *stream);
+int b2_deposit_J(b2_ctx *ctx, int64_t n, const double *d_x, const double *d_y, const double *d_z,
+                 const double *d_w, double q, const double *d_ux, const double *d_uy, const double *d_uz,
+                 const double *d_inv_gamma, double invdz, double zmin, int Nz,
+                 double invdr, double rmin, int Nr, int Nm, void *const *d_grids,
+                 const int32_t *d_prefix_sum, const double *d_ruyten0, const double *d_ruyten_hi,
+                 int cubic, void *stream);
+
+/* ---- interpolation-grid element-wise ops: cuda_erase_*, cuda_divide_*_by_volume
+ *      (fbpic/fields/cuda_methods.py:18-117) ---------------------------------- */
+int b2_scale_rows_by_r(b2_ctx *ctx, int n_arrays, void *const *d_arrays, const double *d_invvol,
+                       int Nz, int Nr, void *stream);      /* F[iz,ir] *= invvol[ir] */
+
+/* ---- spectral transforms: FFT.transform / inverse_transform
+ *      (fbpic/fields/spectral_transform/fourier.py:104-168: cuFFT Z2Z along z of a
+ *      [Nz,Nr] array, inverse scaled by 1/Nz) and DHT.transform / inverse_transform
+ *      (hankel.py:182-243: out = in @ M as a real [2Nz,Nr]x[Nr,Nr] product), plus the
+ *      r,t <-> p,m combinations (spectral_transform/cuda_methods.py:120-158). ------ */
+int b2_fft_z(b2_ctx *ctx, const void *d_in, void *d_out, int Nz, int Nr, int inverse, void *stream);
+/* batched: n_arrays independent [Nz,Nr] arrays */
+int b2_fft_z_multi(b2_ctx *ctx, int n_arrays, const void *const *d_in, void *const *d_out,
+                   int Nz, int Nr, int inverse, void *stream);
+/* out[iz,:] = rowscale[iz] * (in[iz,:] @ M)   (rowscale may be NULL); fp64 DMMA */
+int b2_dht(b2_ctx *ctx, const void *d_in, void *d_out, const double *d_M, const double *d_rowscale,
+           int Nz, int Nr, void *stream);
+/* forward vector transform: p=(r-i t)/2, m=(r+i t)/2 ; out_p = p@Mp, out_m = m@Mm, each
+ * row-scaled (spectral_transformer.py:179-223 after the FFTs) */
+int b2_dht_rt_to_pm(b2_ctx *ctx, const void *d_r, const void *d_t, void *d_out_p, void *d_out_m,
+                    const double *d_Mp, const double *d_Mm, const double *d_rowscale,
+                    int Nz, int Nr, void *stream);
+/* inverse vector transform: P = p@iMp, Q = m@iMm ; r = P+Q, t = i(P-Q)
+ * (spectral_transformer.py:111-155 before the inverse FFTs) */
+int b2_dht_pm_to_rt(b2_ctx *ctx, const void *d_p, const void *d_m, void *d_out_r, void *d_out_t,
+                    const double *d_iMp, const double *d_iMm, const double *d_rowscale,
+                    int Nz, int Nr, void *stream);
+int b2_rt_to_pm(b2_ctx *ctx, void *d_r_p, void *d_t_m, int Nz, int Nr, void *stream);   /* in place */
+int b2_pm_to_rt(b2_ctx *ctx, void *d_p_r, void *d_m_t, int Nz, int Nr, void *stream);   /* in place */
+
+/* ---- spectral element-wise kernels: cuda_filter_{scalar,vector} (fields/cuda_methods.py:467,492),
+ *      cuda_correct_currents_curlfree_{standard,comoving} (:121,174),
+ *      cuda_push_eb_{standard,comoving} (:235,334), cuda_push_rho (:443) ----------- */
+int b2_filter(b2_ctx *ctx, int n_arrays, void *const *d_arrays, const double *d_filter_z,
+              const double *d_filter_r, int Nz, int Nr, void *stream);
+typedef struct {
+    void *Ep, *Em, *Ez, *Bp, *Bm, *Bz, *Jp, *Jm, *Jz, *rho_prev, *rho_next;   /* complex [Nz,Nr] */
+    const double *kz;        /* [Nz] modified kz            */
+    const double *kr;        /* [Nr]                        */
+    const double *inv_k2;    /* [Nz,Nr] real                */
+    const double *C, *S_w;   /* [Nz,Nr] real                */
+    const void *j_coef, *rho_prev_coef, *rho_next_coef;  /* real (standard) or complex (comoving) [Nz,Nr] */
+    const void *T_eb, *T_cc, *T_rho, *j_corr_coef;       /* complex [Nz,Nr], comoving only */
+    double mu_0, epsilon_0;  /* the host's scipy.constants values (CODATA release of the installed SciPy) */
+} b2_spectral_mode;
+int b2_correct_currents(b2_ctx *ctx, const b2_spectral_mode *mode, int comoving, double inv_dt,
+                        int Nz, int Nr, void *stream);
+int b2_push_eb(b2_ctx *ctx, const b2_spectral_mode *mode, int comoving, double dt, double V,
+               int use_true_rho, int Nz, int Nr, void *stream);   /* also does push_rho */
+/* fused correct_currents + push_eb + push_rho (fields.py:247-296), one pass */
+int b2_correct_push(b2_ctx *ctx, const b2_spectral_mode *mode, int comoving, double dt, double V,
+                    int use_true_rho, int Nz, int Nr, void *stream);
+
+/* ---- z boundaries: cuda_damp_EB_left/right (fbpic/boundaries/cuda_methods.py:486,562) and the
+ *      halo pack/unpack kernels (:12-483) + BoundaryCommunicator.exchange_domains
+ *      (boundary_communicator.py:674-707, mpi4py Isend/Irecv) -> NCCL send/recv ---- */
+int b2_damp_z(b2_ctx *ctx, int n_arrays, void *const *d_arrays, const double *d_damp, int nd,
+              int left, int right, int Nz, int Nr, void *stream);
+int b2_add_rows(b2_ctx *ctx, void *d_dst, const void *d_src, int nrows, int Nr, void *stream);
+int b2_nccl_unique_id(void *id128);                       /* 128-byte ncclUniqueId */
+int b2_nccl_init(b2_ctx *ctx, const void *id128, int rank, int size);
+int b2_nccl_destroy(b2_ctx *ctx);
+int b2_nccl_group_start(void);
+int b2_nccl_group_end(void);
+int b2_nccl_send(b2_ctx *ctx, const void *d_buf, size_t nbytes, int peer, void *stream);
+int b2_nccl_recv(b2_ctx *ctx, void *d_buf, size_t nbytes, int peer, void *stream);
+int b2_nccl_allreduce_max_f64(b2_ctx *ctx, double *d_buf, size_t count, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,177 @@
+"""GPU parity tests (kernel level): the CUDA path, called through the operator surface /
+C ABI, against (a) the golden vectors generated from the unmodified FBPIC reference and
+(b) the oracle on larger seeded inputs.  Tolerances: indices bit-exact; fp64 results within
+1e-13*(max|a|+max|b|) for deposition (the reference's own CPU/GPU tolerance,
+tests/test_cpu_gpu_deposition.py:96-98), 1e-13 for gather / push."""
+import ctypes
+import numpy as np
+import pytest
+from scipy.constants import c
+
+from conftest import load_golden, assert_close
+from fbpic_b200 import _lib
+from fbpic_b200 import host_tables as ht
+
+pytestmark = pytest.mark.gpu
+
+
+def make_sim(g, shape, Nm):
+    from fbpic_b200 import Simulation
+    Nz, Nr = int(g['Nz']), int(g['Nr'])
+    sim = Simulation(Nz, float(g['zmax']), Nr, float(g['rmax']), Nm, float(g['dt']),
+                     p_zmin=float(g['zmin']), p_zmax=float(g['zmax']), p_rmin=0, p_rmax=float(g['rmax']),
+                     p_nz=1, p_nr=1, p_nt=4, n_e=1.e24, zmin=float(g['zmin']), particle_shape=shape)
+    return sim
+
+
+def set_particles(sp, P):
+    n = len(P['x'])
+    for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w'):
+        setattr(sp, k, np.array(P[k], dtype=np.float64))
+    for k in ('Ex', 'Ey', 'Ez', 'Bx', 'By', 'Bz'):
+        setattr(sp, k, np.zeros(n))
+    sp.Ntot = n
+    sp.data_is_on_gpu = False
+    sp.sorted = False
+
+
+@pytest.mark.parametrize('shape', ['linear', 'cubic'])
+@pytest.mark.parametrize('Nm', [1, 2, 3])
+def test_kernels_vs_reference_golden(shape, Nm):
+    from oracle import oracle as orc
+    g = load_golden('kernels_%s_Nm%d' % (shape, Nm))
+    sim = make_sim(g, shape, Nm)
+    sp = sim.ptcl[0]
+    P = {k: g['p_' + k] for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w')}
+    set_particles(sp, P)
+    sp.q, sp.m = float(g['q']), float(g['m'])
+    Nz, Nr = int(g['Nz']), int(g['Nr'])
+    g0 = sim.fld.interp[0]
+    # ---- sort: bit-exact keys, stable order, prefix sum
+    sim.send_data_to_gpu()
+    sp.sort_particles(sim.fld)
+    cell = orc.cell_index(P['x'], P['y'], P['z'], g0.invdz, g0.zmin, Nz, g0.invdr, 0., Nr)
+    idx, prefix = orc.sort_contract(cell, Nz, Nr)
+    assert np.array_equal(sp.sorted_idx.get(), idx)
+    assert np.array_equal(sp.prefix_sum.get(), prefix)
+    assert np.array_equal(sp.cell_idx.get(), cell[idx])
+    for k in P:
+        assert np.array_equal(getattr(sp, k).get(), P[k][idx]), k
+    sp.sorted = True
+    # ---- deposit rho, J
+    for ft, names in (('rho', ('rho',)), ('J', ('Jr', 'Jt', 'Jz'))):
+        sim.fld.erase(ft)
+        sp.deposit(sim.fld, ft)
+        sim.fld.divide_by_volume(ft)
+        for m in range(Nm):
+            for nme in names:
+                assert_close(getattr(sim.fld.interp[m], nme).get(), g['dep_%s_m%d' % (nme, m)], 1e-13,
+                             'deposit %s m%d' % (nme, m))
+    # ---- gather (original particle order)
+    sim.receive_data_from_gpu()
+    set_particles(sp, P)
+    for m in range(Nm):
+        for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz'):
+            setattr(sim.fld.interp[m], k, g['grid_%s_m%d' % (k, m)].copy())
+    sim.send_data_to_gpu()
+    sp.gather(sim.fld.interp, sim.comm)
+    for k in ('Ex', 'Ey', 'Ez', 'Bx', 'By', 'Bz'):
+        assert_close(getattr(sp, k).get(), g['gath_' + k], 1e-13, 'gather ' + k)
+    # ---- push_p + push_x, separate kernels
+    sp.push_p(0.)
+    sp.push_x(0.5 * sim.dt)
+    for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma'):
+        assert_close(getattr(sp, k).get(), g['push_' + k], 1e-14, 'push ' + k)
+    # ---- fused gather+push gives the same
+    sim.receive_data_from_gpu()
+    set_particles(sp, P)
+    sim.send_data_to_gpu()
+    sp.gather_and_push(sim.fld.interp, sim.comm, 0.5 * sim.dt)
+    for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma'):
+        assert_close(getattr(sp, k).get(), g['push_' + k], 1e-13, 'fused push ' + k)
+
+
+@pytest.mark.parametrize('shape,Nm', [('linear', 2), ('cubic', 2), ('linear', 4)])
+def test_deposit_gather_vs_oracle_large(shape, Nm):
+    """Seeded plasma of ~0.4 M particles on a 96x40 grid: CUDA vs oracle."""
+    from fbpic_b200 import Simulation
+    from oracle import oracle as orc
+    np.random.seed(3)
+    Nz, Nr, zmax, rmax = 96, 40, 30.e-6, 20.e-6
+    dt = zmax / Nz / c
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, p_zmin=0, p_zmax=zmax, p_rmin=0, p_rmax=rmax,
+                     p_nz=2, p_nr=2, p_nt=4 * Nm, n_e=1.e24, particle_shape=shape)
+    sp = sim.ptcl[0]
+    n = sp.Ntot
+    rng = np.random.default_rng(5)
+    sp.ux, sp.uy, sp.uz = rng.normal(size=n) * 0.3, rng.normal(size=n) * 0.3, rng.normal(size=n)
+    sp.inv_gamma = 1. / np.sqrt(1 + sp.ux**2 + sp.uy**2 + sp.uz**2)
+    # perturb positions so that particles are unsorted and cross the axis / the outer edge
+    sp.x += rng.normal(size=n) * 0.3e-6
+    sp.y += rng.normal(size=n) * 0.3e-6
+    sp.z = np.mod(sp.z + rng.normal(size=n) * 0.4e-6, zmax)
+    P = {k: getattr(sp, k).copy() for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w')}
+    g0 = sim.fld.interp[0]
+    cubic = shape == 'cubic'
+    coef = 'ruyten_cubic_coef' if cubic else 'ruyten_linear_coef'
+    sim.send_data_to_gpu()
+    for ft, names in (('rho', ('rho',)), ('J', ('Jr', 'Jt', 'Jz'))):
+        sim.fld.erase(ft)
+        sp.deposit(sim.fld, ft)
+        raw = orc.deposit(ft, P['x'], P['y'], P['z'], P['w'], sp.q, P['ux'], P['uy'], P['uz'], P['inv_gamma'],
+                          g0.invdz, g0.zmin, Nz, g0.invdr, 0., Nr, Nm, cubic,
+                          getattr(sim.fld.interp[0], coef), getattr(sim.fld.interp[1], coef))
+        for m in range(Nm):
+            for k, nme in enumerate(names):
+                assert_close(getattr(sim.fld.interp[m], nme).get(), raw[k, m], 1e-13, '%s m%d' % (nme, m))
+    cell = orc.cell_index(P['x'], P['y'], P['z'], g0.invdz, g0.zmin, Nz, g0.invdr, 0., Nr)
+    idx, prefix = orc.sort_contract(cell, Nz, Nr)
+    assert np.array_equal(sp.sorted_idx.get(), idx)
+    assert np.array_equal(sp.prefix_sum.get(), prefix)
+    # gather from smooth random fields
+    sim.receive_data_from_gpu()
+    grids = []
+    for m in range(Nm):
+        gm = []
+        for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz'):
+            a = (rng.normal(size=(Nz, Nr)) + 1.j * rng.normal(size=(Nz, Nr))) * (1e9 if k[0] == 'E' else 3.)
+            setattr(sim.fld.interp[m], k, a)
+            gm.append(a)
+        grids.append(tuple(gm))
+    sim.send_data_to_gpu()
+    sp.gather(sim.fld.interp, sim.comm)
+    Ps = {k: getattr(sp, k).get() for k in ('x', 'y', 'z')}
+    F = {k: np.zeros(n) for k in ('Ex', 'Ey', 'Ez', 'Bx', 'By', 'Bz')}
+    orc.gather(Ps['x'], Ps['y'], Ps['z'], rmax, g0.invdz, g0.zmin, Nz, g0.invdr, 0., Nr, grids, cubic,
+               F['Ex'], F['Ey'], F['Ez'], F['Bx'], F['By'], F['Bz'])
+    for k in F:
+        assert_close(getattr(sp, k).get(), F[k], 1e-13, 'gather ' + k)
+
+
+@pytest.mark.parametrize('Nz,Nr', [(64, 48), (200, 64), (37, 50), (128, 256)])
+def test_transforms_vs_numpy(Nz, Nr):
+    """FFT + Hankel GEMM (DMMA) round trips and values against NumPy on random data."""
+    from fbpic_b200.fields import SpectralTransformer
+    from fbpic_b200._lib import DeviceArray
+    rng = np.random.default_rng(Nz + Nr)
+    rmax = 30.e-6
+    for m in (0, 1, 2):
+        tr = SpectralTransformer(Nz, Nr, m, rmax)
+        f = rng.normal(size=(Nz, Nr)) + 1.j * rng.normal(size=(Nz, Nr))
+        h = rng.normal(size=(Nz, Nr)) + 1.j * rng.normal(size=(Nz, Nr))
+        d_f, d_h = DeviceArray.from_numpy(f), DeviceArray.from_numpy(h)
+        d_s, d_p, d_m = [DeviceArray((Nz, Nr), np.complex128) for _ in range(3)]
+        tr.interp2spect_scal(d_f, d_s)
+        ref = np.fft.fft(f, axis=0) @ tr.dht0.M
+        assert_close(d_s.get(), ref, 1e-13, 'fwd scal m%d' % m)
+        tr.interp2spect_vect(d_f, d_h, d_p, d_m)
+        fr, ft = np.fft.fft(f, axis=0), np.fft.fft(h, axis=0)
+        assert_close(d_p.get(), (0.5 * (fr - 1.j * ft)) @ tr.dhtp.M, 1e-13, 'fwd p m%d' % m)
+        assert_close(d_m.get(), (0.5 * (fr + 1.j * ft)) @ tr.dhtm.M, 1e-13, 'fwd m m%d' % m)
+        d_r, d_t = DeviceArray((Nz, Nr), np.complex128), DeviceArray((Nz, Nr), np.complex128)
+        tr.spect2interp_vect(d_f, d_h, d_r, d_t)
+        pp, mm = f @ tr.dhtp.invM, h @ tr.dhtm.invM
+        assert_close(d_r.get(), np.fft.ifft(pp + mm, axis=0), 1e-13, 'inv r m%d' % m)
+        assert_close(d_t.get(), np.fft.ifft(1.j * (pp - mm), axis=0), 1e-13, 'inv t m%d' % m)
+        tr.spect2interp_scal(d_s, d_r)
+        assert_close(d_r.get(), f, 1e-11, 'round trip m%d' % m)
