@@ -1,0 +1,347 @@
+"""
+bench.py -- PIC hot-loop throughput of fbpic_b200 on B200 (and of the CPU oracle).
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+
+Workload (BASELINE.json configs[1], SURVEY 8d "C2"): Nz=4096 per GPU, Nr=256, Nm=2, linear
+shapes, uniform electrons 2x2x4 per cell (16.8 M macro-particles per GPU) filling the box,
+a0=4 / w0=5um / 16fs Gaussian laser pulse initialised analytically on the grid, z periodic
+(Nz stays 4096: isolates the hot loop).  N>1: weak scaling, the global grid is N slabs of 4096
+cells (n_order=32, NCCL guard-cell exchange + particle migration).
+One "step" = one full PIC cycle (Simulation.step(1)); metric = particle-updates/s =
+(sum over ranks of macro-particles) * K / (max over ranks of the device time of K steps).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+from scipy.constants import c, e, m_e, epsilon_0
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: Nz (per GPU), Nr, Nm, (p_nz, p_nr, p_nt), dz [m], rmax [m], n_e
+    'C2': dict(Nz=4096, Nr=256, Nm=2, ppc=(2, 2, 4), dz=0.05e-6, rmax=20.e-6 * 256 / 50, n_e=4.e24),
+    'C1': dict(Nz=256, Nr=64, Nm=2, ppc=(2, 2, 4), dz=0.2e-6, rmax=20.e-6, n_e=2.e24),
+    'C4': dict(Nz=2048, Nr=512, Nm=4, ppc=(2, 2, 16), dz=0.05e-6, rmax=40.e-6, n_e=4.e24),
+    'tiny': dict(Nz=128, Nr=32, Nm=2, ppc=(2, 2, 4), dz=0.1e-6, rmax=10.e-6, n_e=4.e24),
+}
+
+
+def laser_fields(z, r, a0=4., w0=5.e-6, ctau=16.e-15 * c, z0=None, lambda0=0.8e-6):
+    """Linearly (x) polarised Gaussian pulse at focus, as mode-1 amplitudes
+    (Er1, Et1, Br1, Bt1) on the (z, r) mesh: Ex = 2 Re[Er1 e^{-i theta}] cos(theta) ..."""
+    k0 = 2 * np.pi / lambda0
+    E0 = a0 * m_e * c**2 * k0 / e
+    if z0 is None:
+        z0 = 0.5 * (z[0] + z[-1])
+    prof = E0 * np.exp(-(z[:, None] - z0)**2 / ctau**2) * np.exp(-r[None, :]**2 / w0**2) \
+        * np.cos(k0 * (z[:, None] - z0))
+    Er1 = 0.5 * prof + 0.j
+    Et1 = -0.5j * prof
+    Br1 = 0.5j * prof / c
+    Bt1 = 0.5 * prof / c + 0.j
+    return Er1, Et1, Br1, Bt1
+
+
+def build_b200_sim(cfg, n_gpus, fused=True, seed=0):
+    from fbpic_b200 import Simulation
+    np.random.seed(seed + int(os.environ.get('RANK', '0')))
+    Nz_g = cfg['Nz'] * n_gpus
+    zmax = Nz_g * cfg['dz']
+    dt = cfg['dz'] / c
+    p_nz, p_nr, p_nt = cfg['ppc']
+    n_order = -1 if n_gpus == 1 else 32
+    sim = Simulation(Nz_g, zmax, cfg['Nr'], cfg['rmax'], cfg['Nm'], dt, p_zmin=0., p_zmax=zmax,
+                     p_rmin=0., p_rmax=cfg['rmax'], p_nz=p_nz, p_nr=p_nr, p_nt=p_nt, n_e=cfg['n_e'],
+                     n_order=n_order, boundaries={'z': 'periodic', 'r': 'reflective'}, fused=fused)
+    g1 = sim.fld.interp[1]
+    Er1, Et1, Br1, Bt1 = laser_fields(g1.z, g1.r, z0=0.5 * zmax if n_gpus == 1 else 0.5 * cfg['Nz'] * cfg['dz'])
+    g1.Er[:, :], g1.Et[:, :], g1.Br[:, :], g1.Bt[:, :] = Er1, Et1, Br1, Bt1
+    return sim
+
+
+def build_oracle_sim(cfg, Nz, nthreads, seed=0):
+    from oracle import oracle as orc
+    from fbpic_b200.particles import generate_evenly_spaced
+    np.random.seed(seed)
+    zmax = Nz * cfg['dz']
+    dt = cfg['dz'] / c
+    p_nz, p_nr, p_nt = cfg['ppc']
+    sim = orc.OracleSim(Nz, zmax, cfg['Nr'], cfg['rmax'], cfg['Nm'], dt, nthreads=nthreads)
+    # particles exactly as Simulation.add_new_species would create them (last two r cells empty)
+    Npz, Npr = Nz * p_nz, cfg['Nr'] * p_nr
+    Ntot, x, y, z, ux, uy, uz, ig, w = generate_evenly_spaced(
+        Npz, 0., zmax, Npr, 0., cfg['rmax'], p_nt, cfg['n_e'], None, 0., 0., 0., 0., 0., 0.)
+    sim.add_species(-e, m_e, x, y, z, ux, uy, uz, ig, w)
+    zz = (0.5 + np.arange(Nz)) * cfg['dz']
+    rr = (0.5 + np.arange(cfg['Nr'])) * (cfg['rmax'] / cfg['Nr'])
+    Er1, Et1, Br1, Bt1 = laser_fields(zz, rr, z0=0.5 * zmax)
+    g1 = sim.interp[1]
+    g1['Er'][:, :], g1['Et'][:, :], g1['Br'][:, :], g1['Bt'][:, :] = Er1, Et1, Br1, Bt1
+    return sim, Ntot
+
+
+# ---------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index=0, period=0.2):
+        super().__init__(daemon=True)
+        self.gpu, self.period, self.samples, self._stop = gpu_index, period, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm = [float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith('active')})
+        return dict(sm_mhz=(float(np.median(sm)) if sm else None), sm_max_mhz=(max(mx) if mx else None),
+                    reasons=reasons, samples=len(self.samples))
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return None
+
+
+def profile_table():
+    from fbpic_b200 import _lib
+    lib = _lib.load()
+    out = {}
+    for s in range(lib.b2_profile_slots()):
+        ms, n = ctypes.c_double(0.), ctypes.c_uint64(0)
+        _lib.call.b2_profile_read(s, ctypes.byref(ms), ctypes.byref(n))
+        if n.value:
+            out[lib.b2_profile_name(s).decode()] = dict(ms=ms.value, launches=int(n.value))
+    return out
+
+
+def time_oracle(cfg, Nz, steps, warmup, nthreads):
+    sim, Ntot = build_oracle_sim(cfg, Nz, nthreads)
+    sim.step(max(warmup, 1))
+    t0 = time.perf_counter()
+    sim.step(steps)
+    dt = time.perf_counter() - t0
+    return Ntot * steps / dt, dt / steps * 1e3, Ntot
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='C2', choices=sorted(CONFIGS))
+    ap.add_argument('--preroll', type=int, default=30, help='untimed setup steps that disorder the plasma')
+    ap.add_argument('--no-fused', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    n_gpus = max(args.gpus, world)
+    metric = 'particle-updates/s (PIC hot loop: gather+push+deposit+sort+spectral solve)'
+    workload = '%s periodic plasma + laser: Nz=%d/GPU Nr=%d Nm=%d ppc=%dx%dx%d linear' % (
+        (args.config, cfg['Nz'], cfg['Nr'], cfg['Nm']) + cfg['ppc'])
+    ncores = os.cpu_count() or 1
+    nthreads = int(os.environ.get('ORACLE_NUM_THREADS', min(ncores, 64)))
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        from oracle import oracle as orc
+        orc.build()
+        Nz_s = min(cfg['Nz'], 1024)          # bounded sample: a z-slab of the same workload
+        steps = max(1, min(args.steps, 10))
+        val, ms, Ntot = time_oracle(cfg, Nz_s, steps, min(args.warmup, 2), nthreads)
+        sample = 'z-slab Nz=%d of the workload (%d particles), %d steps, oracle port (C+OpenMP particle ' \
+                 'kernels, scipy.fft, OpenBLAS dgemm), %d threads' % (Nz_s, Ntot, steps, nthreads)
+        print(json.dumps({
+            'impl': 'reference', 'metric': metric, 'value': val, 'unit': 'particle-updates/s',
+            'n_gpus': 0, 'steps': steps, 'warmup': min(args.warmup, 2), 'ms_per_step': ms,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': {'workload': workload, 'sample': sample},
+            'cpu_baseline': {'value': val, 'unit': 'particle-updates/s', 'cores': nthreads, 'kind': 'port',
+                             'sample': sample},
+            'e2e': {'value': val, 'unit': 'particle-updates/s', 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0}}))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    from fbpic_b200 import _lib
+    from fbpic_b200._lib import call
+    from fbpic_b200.boundaries import world as pg_world
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('gloo')
+    ctx = _lib.context()
+    sim = build_b200_sim(cfg, n_gpus, fused=not args.no_fused)
+    Ntot_local = sum(s.Ntot for s in sim.ptcl)
+    host_state_bytes = sum(getattr(s, k).nbytes for s in sim.ptcl
+                           for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w', 'Ex', 'Ey', 'Ez', 'Bx', 'By', 'Bz')) \
+        + sum(getattr(g, k).nbytes for g in sim.fld.interp for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'Jr', 'Jt', 'Jz', 'rho')) \
+        + sum(getattr(g, k).nbytes for g in sim.fld.spect for k in ('Ep', 'Em', 'Ez', 'Bp', 'Bm', 'Bz', 'Jp', 'Jm', 'Jz', 'rho_prev', 'rho_next'))
+
+    def barrier():
+        call.b2_device_sync()
+        if dist is not None:
+            dist.barrier()
+
+    # setup (untimed): disorder the plasma, then W warm-up steps
+    sim.step(max(args.preroll, 1), keep_on_gpu=True)
+    sim.step(max(args.warmup, 3), keep_on_gpu=True)
+
+    ev0, ev1 = ctypes.c_void_p(), ctypes.c_void_p()
+    call.b2_event_create(ctypes.byref(ev0))
+    call.b2_event_create(ctypes.byref(ev1))
+    sampler = ClockSampler(ctx.device) if rank == 0 else None
+    call.b2_profile_reset()
+    call.b2_profile_enable(1)
+    launches0 = _lib.load().b2_launch_count()
+    barrier()
+    if sampler:
+        sampler.start()
+    call.b2_event_record(ev0, ctx.stream)
+    sim.step(args.steps, keep_on_gpu=True)
+    call.b2_event_record(ev1, ctx.stream)
+    barrier()
+    ms = ctypes.c_float(0.)
+    call.b2_event_elapsed_ms(ev0, ev1, ctypes.byref(ms))
+    clocks = sampler.stop() if sampler else None
+    launches = _lib.load().b2_launch_count() - launches0
+    call.b2_profile_enable(0)
+    prof = profile_table()
+    t_ms, n_tot = ms.value, float(Ntot_local)
+    if dist is not None:
+        import torch
+        t = torch.tensor([t_ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms = float(t[0])
+        nt = torch.tensor([n_tot], dtype=torch.float64)
+        dist.all_reduce(nt, op=dist.ReduceOp.SUM)
+        n_tot = float(nt[0])
+    value = n_tot * args.steps / (t_ms * 1e-3)
+
+    # ---- e2e: the user-facing call with HOST buffers: Simulation.step(K) copies the whole state
+    #      host->device at entry and device->host at exit (main.py:402-403, 579-581) ----
+    e2e = None
+    if not args.no_e2e:
+        sim.receive_data_from_gpu()
+        k_e2e = args.steps
+        barrier()
+        t0 = time.perf_counter()
+        sim.step(k_e2e)                      # H2D of all state, K steps, D2H of all state
+        call.b2_device_sync()
+        t_e2e = time.perf_counter() - t0
+        if dist is not None:
+            import torch
+            t = torch.tensor([t_e2e], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t[0])
+        e2e = {'value': n_tot * k_e2e / t_e2e, 'unit': 'particle-updates/s',
+               'h2d_bytes_per_step': host_state_bytes / k_e2e, 'd2h_bytes_per_step': host_state_bytes / k_e2e,
+               'note': 'Simulation.step(%d) from/to host NumPy arrays: full particle+field state H2D at entry '
+                       'and D2H at exit, as the reference API does; per-step bytes = total/%d' % (k_e2e, k_e2e)}
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel family (device time from CUDA events inside the timed region)
+    peaks = measured_peaks()
+    hbm_peak = (peaks or {}).get('hbm_gbs', 6650.)
+    peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback'
+    cells = cfg['Nz'] * cfg['Nr'] * 16
+    alg = {   # algorithmic bytes per launch
+        'deposit_J': 64 * Ntot_local + 3 * cfg['Nm'] * cells,
+        'deposit_rho': 32 * Ntot_local + cfg['Nm'] * cells,
+        'gather_push': 112 * Ntot_local + 6 * cfg['Nm'] * cells,
+        'permute': (8 + 128) * Ntot_local,
+        'sort': (4 + 12 + 4) * Ntot_local,
+    }
+    top = max(prof.items(), key=lambda kv: kv[1]['ms'])[0] if prof else None
+    roofline = None
+    shares = {k: v['ms'] / t_ms for k, v in prof.items()}
+    if top == 'dht':
+        Nr, Nz = cfg['Nr'], sim.fld.interp[0].Nz
+        # flops per step from the launch mix is awkward to reconstruct; report per-launch average
+        n_l = prof['dht']['launches']
+        flop_step = 0.
+        # every launch handles njobs arrays; count products from the step structure: per mode and step
+        # 5 forward (J:3, rho_prev, rho_next... ) -- computed exactly in DESIGN.md; here measured total:
+        per_mode = (3 + 1 + 1) + 6          # forward products J,rho x2 ; inverse E,B
+        flop_step = cfg['Nm'] * per_mode * 4. * Nz * Nr * Nr
+        ach = flop_step * args.steps / (prof['dht']['ms'] * 1e-3) / 1e12
+        roofline = {'kernel': 'k_dht (Hankel GEMM, fp64 DMMA)', 'bound': 'tensor', 'achieved': ach,
+                    'peak': 37.1, 'unit': 'TFLOP/s', 'frac': ach / 37.1, 'traffic': None,
+                    'peak_source': 'measured DMMA.8x8x4 issue peak on B200 (profiles/r01_microbench.txt); '
+                                   'MEASURED_PEAKS.json has no fp64 entry'}
+    elif top in alg:
+        per_launch_ms = prof[top]['ms'] / prof[top]['launches']
+        ach = alg[top] / (per_launch_ms * 1e-3) / 1e9
+        roofline = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
+                    'frac': ach / hbm_peak, 'traffic': None, 'peak_source': peak_src}
+    kernels = {}
+    for k, v in prof.items():
+        d = dict(ms_per_step=v['ms'] / args.steps, launches_per_step=v['launches'] / args.steps,
+                 share=shares[k])
+        if k in alg:
+            d['GBps'] = alg[k] / (v['ms'] / v['launches'] * 1e-3) / 1e9
+            d['hbm_frac'] = d['GBps'] / hbm_peak
+        kernels[k] = d
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        orc.build()
+        Nz_s = min(cfg['Nz'], 512)
+        val, ms_cpu, n_cpu = time_oracle(cfg, Nz_s, 3, 1, nthreads)
+        cpu_baseline = {'value': val, 'unit': 'particle-updates/s', 'cores': nthreads, 'kind': 'port',
+                        'sample': 'z-slab Nz=%d of the workload (%d particles), 3 steps after 1 warm-up, '
+                                  'oracle port on %d threads of %d logical cores' % (Nz_s, n_cpu, nthreads, ncores)}
+    out = {
+        'metric': metric, 'value': value, 'unit': 'particle-updates/s', 'n_gpus': n_gpus,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': t_ms / args.steps,
+        'pic_steps_per_s': args.steps / (t_ms * 1e-3), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': workload, 'particles_total': n_tot, 'fused': not args.no_fused,
+                   'n_order': -1 if n_gpus == 1 else 32, 'preroll_steps': args.preroll,
+                   'l2': 'inputs larger than L2 (particle state %.1f GB per GPU)' % (Ntot_local * 64 / 1e9)},
+        'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline,
+        'cpu_baseline': cpu_baseline, 'kernels': kernels,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()

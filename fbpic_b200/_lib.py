@@ -51,6 +51,11 @@ _SIGNATURES = {
     'b2_event_record': [P, P],
     'b2_event_elapsed_ms': [P, P, ctypes.POINTER(ctypes.c_float)],
     'b2_launch_count': [],
+    'b2_profile_enable': [c_int],
+    'b2_profile_reset': [],
+    'b2_profile_slots': [],
+    'b2_profile_name': [c_int],
+    'b2_profile_read': [c_int, ctypes.POINTER(c_double), ctypes.POINTER(ctypes.c_uint64)],
     'b2_graph_begin': [P],
     'b2_graph_end': [P, ctypes.POINTER(P)],
     'b2_graph_launch': [P, P],
@@ -65,6 +70,7 @@ _SIGNATURES = {
     'b2_gather_push': [P, c_int64, P, P, P, P, P, P, P, c_double, c_double, c_double, c_int, c_double,
                        c_double, c_int, c_int, P, c_int, c_double, c_double, c_double, c_double, P],
     'b2_shift_periodic': [P, c_int64, P, c_double, c_double, P],
+    'b2_add_scalar': [P, c_int64, P, c_double, P],
     'b2_deposit_rho': [P, c_int64, P, P, P, P, c_double, c_double, c_double, c_int, c_double, c_double,
                        c_int, c_int, P, P, P, P, c_int, P],
     'b2_deposit_J': [P, c_int64, P, P, P, P, c_double, P, P, P, P, c_double, c_double, c_int, c_double,
@@ -92,7 +98,8 @@ _SIGNATURES = {
     'b2_nccl_recv': [P, P, c_size_t, c_int, P],
     'b2_nccl_allreduce_max_f64': [P, P, c_size_t, P],
 }
-_RESTYPES = {'b2_error_string': ctypes.c_char_p, 'b2_version': ctypes.c_char_p,
+_RESTYPES = {'b2_profile_name': ctypes.c_char_p, 'b2_profile_slots': c_int,
+             'b2_error_string': ctypes.c_char_p, 'b2_version': ctypes.c_char_p,
              'b2_ctx_stream': c_void_p, 'b2_launch_count': ctypes.c_uint64}
 EXPORTED = sorted(_SIGNATURES)
 

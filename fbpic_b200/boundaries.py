@@ -351,8 +351,7 @@ class BoundaryCommunicator(object):
     def _shift_z(z, start, count, dz_shift):
         """z[start:start+count] += dz_shift for the periodic images received across the ring
         closure (only the two end ranks, only on particle-exchange steps)."""
-        h = z[start:start + count].get()
-        z[start:start + count].set(h + dz_shift)
+        call.b2_add_scalar(_lib.context().handle, count, z.ptr + 8 * start, dz_shift, None)
 
     # ---- open-boundary damping (boundary_communicator.py:828-945) ----
     def generate_damp_array(self, n_guard, nz_damp, n_inject):

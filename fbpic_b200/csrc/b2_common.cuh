@@ -47,6 +47,19 @@ static inline cudaStream_t b2_stream_of(b2_ctx *ctx, void *stream) {
 
 int b2_scratch(b2_ctx *ctx, int slot, size_t nbytes, void **ptr);
 
+// ---- optional per-kernel-family device timing (CUDA events on the launching stream) ----
+enum B2ProfSlot {
+    B2P_CELL_INDEX = 0, B2P_SORT, B2P_PERMUTE, B2P_GATHER, B2P_PUSH, B2P_GATHER_PUSH, B2P_DEPOSIT_RHO,
+    B2P_DEPOSIT_J, B2P_FFT, B2P_DHT, B2P_SPECTRAL, B2P_ELEMENTWISE, B2P_COMM, B2P_NSLOTS
+};
+extern bool g_b2_prof_on;
+struct B2Prof {
+    int idx;
+    cudaStream_t s;
+    B2Prof(int slot, cudaStream_t stream);
+    ~B2Prof();
+};
+
 // pointer bundle passed by value to multi-array kernels
 struct B2Ptrs {
     void *p[B2_MAX_ARRAYS];

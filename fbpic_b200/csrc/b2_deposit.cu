@@ -230,6 +230,7 @@ static int deposit_any(b2_ctx *ctx, bool is_J, int64_t n, const double *x, const
     const int ng = is_J ? 3 * Nm : Nm;
     for (int k = 0; k < ng; ++k) G.g[k] = (double2 *)grids[k];
     cudaStream_t s = b2_stream_of(ctx, stream);
+    B2Prof prof_(is_J ? B2P_DEPOSIT_J : B2P_DEPOSIT_RHO, s);
     const int ncells = Nz * (Nr + 1);
     switch (Nm) {
         case 1: dispatch_dep<1>(is_J, cubic != 0, DEP_ARGS); break;

@@ -203,6 +203,7 @@ static int launch_dht(b2_ctx *ctx, const DhtJobs &jobs, int njobs, int Nz, int N
         attr_set[NPROD] = true;
     }
     const int ncol = DHT_BN / NPROD;
+    B2Prof prof_(B2P_DHT, s);
     dim3 grid((Nr + ncol - 1) / ncol, (Nz + DHT_BM - 1) / DHT_BM, njobs);
     k_dht<NPROD><<<grid, DHT_THREADS, smem, s>>>(jobs, Nz, Nr);
     B2_LAUNCHED();

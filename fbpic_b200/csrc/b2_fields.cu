@@ -230,6 +230,7 @@ int b2_scale_rows_by_r(b2_ctx *ctx, int na, void *const *arrays, const double *v
     if (na > B2_MAX_ARRAYS) return b2_fail(-3, "too many arrays", __FILE__, __LINE__);
     B2Ptrs A;
     for (int k = 0; k < na; ++k) A.p[k] = arrays[k];
+    B2Prof prof_(B2P_ELEMENTWISE, b2_stream_of(ctx, stream));
     k_scale_r<<<grid2d(Nz, Nr, BLK), BLK, 0, b2_stream_of(ctx, stream)>>>(A, na, v, Nz, Nr);
     B2_LAUNCHED();
     return 0;
@@ -240,6 +241,7 @@ int b2_filter(b2_ctx *ctx, int na, void *const *arrays, const double *fz, const 
     if (na > B2_MAX_ARRAYS) return b2_fail(-3, "too many arrays", __FILE__, __LINE__);
     B2Ptrs A;
     for (int k = 0; k < na; ++k) A.p[k] = arrays[k];
+    B2Prof prof_(B2P_ELEMENTWISE, b2_stream_of(ctx, stream));
     k_filter<<<grid2d(Nz, Nr, BLK), BLK, 0, b2_stream_of(ctx, stream)>>>(A, na, fz, fr, Nz, Nr);
     B2_LAUNCHED();
     return 0;
@@ -261,6 +263,7 @@ int b2_fft_z(b2_ctx *ctx, const void *in, void *out, int Nz, int Nr, int inverse
     int rc = get_plan(ctx, Nz, Nr, &plan);
     if (rc) return rc;
     cudaStream_t s = b2_stream_of(ctx, stream);
+    B2Prof prof_(B2P_FFT, s);
     cufftResult r = cufftSetStream(plan, s);
     if (r != CUFFT_SUCCESS) return b2_fail((int)r, "cufftSetStream failed", __FILE__, __LINE__);
     r = cufftExecZ2Z(plan, (cufftDoubleComplex *)in, (cufftDoubleComplex *)out, inverse ? CUFFT_INVERSE : CUFFT_FORWARD);
@@ -286,6 +289,7 @@ int b2_fft_z_multi(b2_ctx *ctx, int na, const void *const *in, void *const *out,
 static int spectral_launch(b2_ctx *ctx, const b2_spectral_mode *mode, int comoving, bool corr, bool push, double dt,
                            double V, int use_true_rho, int Nz, int Nr, void *stream) {
     cudaStream_t s = b2_stream_of(ctx, stream);
+    B2Prof prof_(B2P_SPECTRAL, s);
     dim3 g = grid2d(Nz, Nr, BLK);
 #define SPEC(CM, A, B) k_spectral<CM, A, B><<<g, BLK, 0, s>>>(*mode, dt, V, use_true_rho, Nz, Nr)
     if (comoving) {

@@ -291,6 +291,11 @@ __global__ void k_shift_periodic(int64_t n, double *__restrict__ z, double zmin,
     z[i] = zi;
 }
 
+__global__ void k_add_scalar(int64_t n, double *__restrict__ v, double a) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) v[i] += a;
+}
+
 // =====================================================================================
 // C ABI
 // =====================================================================================
@@ -318,6 +323,7 @@ extern "C" {
 int b2_cell_index(b2_ctx *ctx, int64_t n, const double *x, const double *y, const double *z, double invdz,
                   double zmin, int Nz, double invdr, double rmin, int Nr, int32_t *cell_idx, void *stream) {
     if (n <= 0) return 0;
+    B2Prof prof_(B2P_CELL_INDEX, b2_stream_of(ctx, stream));
     k_cell_index<<<grid1d(n, 256), 256, 0, b2_stream_of(ctx, stream)>>>(n, x, y, z, invdz, zmin, Nz, invdr, rmin, Nr, cell_idx);
     B2_LAUNCHED();
     return 0;
@@ -331,6 +337,7 @@ int b2_sort_cells(b2_ctx *ctx, int64_t n, int32_t *cell_idx, int64_t *sorted_idx
         B2_CUDA(cudaMemsetAsync(prefix_sum, 0, sizeof(int32_t) * (size_t)ncells, s));
         return 0;
     }
+    B2Prof prof_(B2P_SORT, s);
     int end_bit = 1;
     while ((1LL << end_bit) < (long long)ncells && end_bit < 31) ++end_bit;
     size_t temp_bytes = 0;
@@ -360,6 +367,7 @@ int b2_sort_cells(b2_ctx *ctx, int64_t n, int32_t *cell_idx, int64_t *sorted_idx
 int b2_permute(b2_ctx *ctx, int64_t n, const int64_t *sorted_idx, int n_arrays, const double *const *src,
                double *const *dst, void *stream) {
     if (n <= 0 || n_arrays <= 0) return 0;
+    B2Prof prof_(B2P_PERMUTE, b2_stream_of(ctx, stream));
     if (n_arrays > B2_MAX_ARRAYS) return b2_fail(-3, "too many arrays", __FILE__, __LINE__);
     B2Perm a;
     for (int k = 0; k < n_arrays; ++k) { a.src[k] = src[k]; a.dst[k] = dst[k]; }
@@ -376,6 +384,7 @@ int b2_gather(b2_ctx *ctx, int64_t n, const double *x, const double *y, const do
               const void *const *grids, int cubic, double *Ex, double *Ey, double *Ez, double *Bx, double *By,
               double *Bz, void *stream) {
     if (n <= 0) return 0;
+    B2Prof prof_(B2P_GATHER, b2_stream_of(ctx, stream));
     if (Nm < 1 || Nm > 4) return b2_fail(-3, "b2_gather: Nm must be in 1..4", __FILE__, __LINE__);
     B2Grids G;
     for (int k = 0; k < 6 * Nm; ++k) G.g[k] = (const double2 *)grids[k];
@@ -397,6 +406,7 @@ int b2_push_p(b2_ctx *ctx, int64_t n, double *ux, double *uy, double *uz, double
               const double *Ey, const double *Ez, const double *Bx, const double *By, const double *Bz, double q,
               double m, double dt, void *stream) {
     if (n <= 0) return 0;
+    B2Prof prof_(B2P_PUSH, b2_stream_of(ctx, stream));
     const double econst = q * dt / (m * B2_C_LIGHT), bconst = 0.5 * q * dt / m;
     k_push_p<<<grid1d(n, 256), 256, 0, b2_stream_of(ctx, stream)>>>(n, ux, uy, uz, inv_gamma, Ex, Ey, Ez, Bx, By, Bz, econst, bconst);
     B2_LAUNCHED();
@@ -406,6 +416,7 @@ int b2_push_p(b2_ctx *ctx, int64_t n, double *ux, double *uy, double *uz, double
 int b2_push_x(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, const double *ux, const double *uy,
               const double *uz, const double *inv_gamma, double dt, double xp, double yp, double zp, void *stream) {
     if (n <= 0) return 0;
+    B2Prof prof_(B2P_PUSH, b2_stream_of(ctx, stream));
     k_push_x<<<grid1d(n, 256), 256, 0, b2_stream_of(ctx, stream)>>>(n, x, y, z, ux, uy, uz, inv_gamma, B2_C_LIGHT * dt, xp, yp, zp);
     B2_LAUNCHED();
     return 0;
@@ -416,6 +427,7 @@ int b2_gather_push(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, doub
                    double rmin, int Nr, int Nm, const void *const *grids, int cubic, double q, double m,
                    double dt_p, double dt_x, void *stream) {
     if (n <= 0) return 0;
+    B2Prof prof_(B2P_GATHER_PUSH, b2_stream_of(ctx, stream));
     if (Nm < 1 || Nm > 4) return b2_fail(-3, "b2_gather_push: Nm must be in 1..4", __FILE__, __LINE__);
     B2Grids G;
     for (int k = 0; k < 6 * Nm; ++k) G.g[k] = (const double2 *)grids[k];
@@ -434,8 +446,16 @@ int b2_gather_push(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, doub
     return 0;
 }
 
+int b2_add_scalar(b2_ctx *ctx, int64_t n, double *v, double value, void *stream) {
+    if (n <= 0) return 0;
+    k_add_scalar<<<grid1d(n, 256), 256, 0, b2_stream_of(ctx, stream)>>>(n, v, value);
+    B2_LAUNCHED();
+    return 0;
+}
+
 int b2_shift_periodic(b2_ctx *ctx, int64_t n, double *z, double zmin, double zmax, void *stream) {
     if (n <= 0) return 0;
+    B2Prof prof_(B2P_PUSH, b2_stream_of(ctx, stream));
     k_shift_periodic<<<grid1d(n, 256), 256, 0, b2_stream_of(ctx, stream)>>>(n, z, zmin, zmax);
     B2_LAUNCHED();
     return 0;

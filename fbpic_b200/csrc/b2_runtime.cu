@@ -11,7 +11,49 @@ int b2_fail(int code, const char *what, const char *file, int line) {
     return code ? code : -1;
 }
 
+// ---- profiler -------------------------------------------------------------------------
+#include <vector>
+bool g_b2_prof_on = false;
+struct ProfRec { int slot; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static const char *g_prof_names[B2P_NSLOTS] = {"cell_index", "sort", "permute", "gather", "push", "gather_push",
+    "deposit_rho", "deposit_J", "fft", "dht", "spectral", "elementwise", "comm"};
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+B2Prof::B2Prof(int slot, cudaStream_t stream) : idx(-1), s(stream) {
+    if (!g_b2_prof_on) return;
+    ProfRec r; r.slot = slot; r.a = prof_event(); r.b = prof_event();
+    cudaEventRecord(r.a, s);
+    g_prof_recs.push_back(r);
+    idx = (int)g_prof_recs.size() - 1;
+}
+B2Prof::~B2Prof() { if (idx >= 0) cudaEventRecord(g_prof_recs[idx].b, s); }
+
 extern "C" {
+
+int b2_profile_enable(int on) { g_b2_prof_on = (on != 0); return 0; }
+int b2_profile_reset(void) {
+    for (auto &r : g_prof_recs) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+    g_prof_recs.clear();
+    return 0;
+}
+int b2_profile_slots(void) { return B2P_NSLOTS; }
+const char *b2_profile_name(int slot) { return (slot >= 0 && slot < B2P_NSLOTS) ? g_prof_names[slot] : ""; }
+int b2_profile_read(int slot, double *total_ms, uint64_t *count) {
+    double t = 0.; uint64_t n = 0;
+    for (auto &r : g_prof_recs) {
+        if (r.slot != slot) continue;
+        B2_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        B2_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        t += ms; ++n;
+    }
+    *total_ms = t; *count = n;
+    return 0;
+}
 
 const char *b2_error_string(void) { return g_b2_err; }
 const char *b2_version(void) { return "fbpic_b200 0.1 (sm_100a)"; }

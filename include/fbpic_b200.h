@@ -57,6 +57,13 @@ int b2_event_record(void *event, void *stream);
 int b2_event_elapsed_ms(void *start, void *stop, float *ms);   /* syncs on stop */
 /* number of kernels / library calls this library launched since load */
 uint64_t b2_launch_count(void);
+/* optional per-kernel-family device timing (CUDA events around each launch, on its stream);
+ * used by bench.py to time the dominant kernel inside the timed region */
+int b2_profile_enable(int on);
+int b2_profile_reset(void);
+int b2_profile_slots(void);
+const char *b2_profile_name(int slot);
+int b2_profile_read(int slot, double *total_ms, uint64_t *count);
 /* CUDA-graph capture of a sequence of b2_* calls on the context stream */
 int b2_graph_begin(b2_ctx *ctx);
 int b2_graph_end(b2_ctx *ctx, void **graph_exec);
@@ -103,6 +110,9 @@ int b2_gather_push(b2_ctx *ctx, int64_t n, double *d_x, double *d_y, double *d_z
                    int Nm, const void *const *d_grids, int cubic,
                    double q, double m, double dt_p, double dt_x, void *stream);
 int b2_shift_periodic(b2_ctx *ctx, int64_t n, double *d_z, double zmin, double zmax, void *stream);
+/* v[i] += value : z-shift of the periodic images received across the ring closure
+ * (boundary_communicator.py:815-821) */
+int b2_add_scalar(b2_ctx *ctx, int64_t n, double *d_v, double value, void *stream);
 
 /* ---- deposition: deposit_{rho,J}_gpu_{linear,cubic}[_one_mode]
  *      (fbpic/particles/deposition/cuda_methods.py:28,202,466,751; cuda_methods_one_mode.py)
