@@ -101,10 +101,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu_index=0, period=0.2):
         super().__init__(daemon=True)
-        self.gpu, self.period, self.samples, self._stop = gpu_index, period, [], threading.Event()
+        self.gpu, self.period, self.samples, self._halt = gpu_index, period, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
                                       '--format=csv,noheader,nounits'], capture_output=True, text=True,
@@ -113,10 +113,10 @@ class ClockSampler(threading.Thread):
                     self.samples.append([s.strip() for s in out.split(',')])
             except Exception:
                 pass
-            self._stop.wait(self.period)
+            self._halt.wait(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=3)
         sm = [float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit()]
         mx = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
