@@ -68,7 +68,9 @@ _SIGNATURES = {
     'b2_push_p': [P, c_int64, P, P, P, P, P, P, P, P, P, P, c_double, c_double, c_double, P],
     'b2_push_x': [P, c_int64, P, P, P, P, P, P, P, c_double, c_double, c_double, c_double, P],
     'b2_gather_push': [P, c_int64, P, P, P, P, P, P, P, c_double, c_double, c_double, c_int, c_double,
-                       c_double, c_int, c_int, P, c_int, c_double, c_double, c_double, c_double, P],
+                       c_double, c_int, c_int, P, c_int, c_double, c_double, c_double, c_double, P, c_double, P],
+    'b2_push_x_key': [P, c_int64, P, P, P, P, P, P, P, c_double, c_int, c_double, c_double,
+                      c_double, c_double, c_int, c_double, c_double, c_int, P, P],
     'b2_shift_periodic': [P, c_int64, P, c_double, c_double, P],
     'b2_add_scalar': [P, c_int64, P, c_double, P],
     'b2_deposit_rho': [P, c_int64, P, P, P, P, c_double, c_double, c_double, c_int, c_double, c_double,

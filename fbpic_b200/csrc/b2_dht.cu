@@ -37,7 +37,7 @@ struct DhtJobs {
 };
 
 __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
@@ -73,8 +73,10 @@ k_dht(DhtJobs jobs, int Nz, int Nr) {
             }
 
     const int KT = (Nr + DHT_BK - 1) / DHT_BK;
-    // register staging of the next K chunk
-    double2 ra[NPROD][4];
+    // register staging of the next K chunk: load_tiles only ISSUES the global loads (raw values);
+    // the (r,t)->(p,m) mixing arithmetic happens in store_tiles, after the MMAs of the current
+    // chunk, so that no instruction depending on the loads sits in front of the tensor work.
+    double2 ra[2][4];
     double rb[8];
 
     auto load_tiles = [&](int kt) {
@@ -86,22 +88,8 @@ k_dht(DhtJobs jobs, int Nz, int Nr) {
             const int iz = iz0 + izl, jj = k0 + j;
             const bool ok = (iz < Nz) && (jj < Nr);
             const size_t o = (size_t)iz * Nr + jj;
-            if (NPROD == 1) {
-                double2 v = make_double2(0., 0.);
-                if (ok) {
-                    const double2 a = __ldg(J.in1 + o);
-                    v = make_double2(J.c1.x * a.x - J.c1.y * a.y, J.c1.x * a.y + J.c1.y * a.x);
-                    if (mix) {
-                        const double2 b = __ldg(J.in2 + o);
-                        v.x += J.c2.x * b.x - J.c2.y * b.y;
-                        v.y += J.c2.x * b.y + J.c2.y * b.x;
-                    }
-                }
-                ra[0][qq] = v;
-            } else {
-                ra[0][qq] = ok ? __ldg(J.in1 + o) : make_double2(0., 0.);
-                ra[NPROD - 1][qq] = ok ? __ldg(J.in2 + o) : make_double2(0., 0.);
-            }
+            ra[0][qq] = ok ? __ldg(J.in1 + o) : make_double2(0., 0.);
+            if (NPROD == 2 || mix) ra[1][qq] = ok ? __ldg(J.in2 + o) : make_double2(0., 0.);
         }
 #pragma unroll
         for (int qq = 0; qq < 8; ++qq) {
@@ -124,9 +112,19 @@ k_dht(DhtJobs jobs, int Nz, int Nr) {
         for (int qq = 0; qq < 4; ++qq) {
             const int e = tid + DHT_THREADS * qq;
             const int izl = e >> 4, j = e & 15;
+            if (NPROD == 1) {
+                double2 v = ra[0][qq];
+                if (mix) {
+                    const double2 a = ra[0][qq], b = ra[1][qq];
+                    v.x = J.c1.x * a.x - J.c1.y * a.y + J.c2.x * b.x - J.c2.y * b.y;
+                    v.y = J.c1.x * a.y + J.c1.y * a.x + J.c2.x * b.y + J.c2.y * b.x;
+                }
+                sA[buf * A_ELEMS + izl * DHT_AP + j] = v;
+            } else {
 #pragma unroll
-            for (int p = 0; p < NPROD; ++p)
-                sA[buf * A_ELEMS + (p * DHT_BM + izl) * DHT_AP + j] = ra[p][qq];
+                for (int p = 0; p < NPROD; ++p)
+                    sA[buf * A_ELEMS + (p * DHT_BM + izl) * DHT_AP + j] = ra[p][qq];
+            }
         }
 #pragma unroll
         for (int qq = 0; qq < 8; ++qq) {

@@ -260,13 +260,17 @@ __global__ void k_push_x(int64_t n, double *__restrict__ x, double *__restrict__
     z[i] += chdt * g * zp * uz[i];
 }
 
-// fused gather + push_p + push_x: one read and one write of the particle state per step
+// fused gather + push_p + push_x: one read and one write of the particle state per step.
+// Optionally also emits the cell key of the NEW position (on a grid whose zmin is key_zmin: the
+// Galilean scheme shifts the grid between the push and the deposition), saving the separate
+// get_cell_idx_per_particle pass of the following sort.
 template <int NM, bool CUBIC>
 __global__ void __launch_bounds__(256)
 k_gather_push(int64_t n, double *__restrict__ x, double *__restrict__ y, double *__restrict__ z,
               double *__restrict__ ux, double *__restrict__ uy, double *__restrict__ uz,
               double *__restrict__ inv_gamma, double rmax_gather, double invdz, double zmin, int Nz,
-              double invdr, double rmin, int Nr, B2Grids G, double econst, double bconst, double chdt) {
+              double invdr, double rmin, int Nr, B2Grids G, double econst, double bconst, double chdt,
+              int32_t *__restrict__ cell_idx, double key_zmin) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double xj = x[i], yj = y[i], zj = z[i];
@@ -276,9 +280,34 @@ k_gather_push(int64_t n, double *__restrict__ x, double *__restrict__ y, double 
     double a = ux[i], b = uy[i], cz = uz[i], g = inv_gamma[i];
     b2_vay(a, b, cz, g, F, econst, bconst);
     ux[i] = a; uy[i] = b; uz[i] = cz; inv_gamma[i] = g;
-    x[i] = xj + chdt * g * 1. * a;
-    y[i] = yj + chdt * g * 1. * b;
-    z[i] = zj + chdt * g * 1. * cz;
+    const double xn = xj + chdt * g * 1. * a;
+    const double yn = yj + chdt * g * 1. * b;
+    const double zn = zj + chdt * g * 1. * cz;
+    x[i] = xn; y[i] = yn; z[i] = zn;
+    if (cell_idx) cell_idx[i] = b2_cell_of(b2_cyl(xn, yn, zn, invdz, key_zmin, invdr, rmin), Nz, Nr);
+}
+
+// push_x + optional periodic wrap of z into [wrap_zmin, wrap_zmax) + optional cell key of the new
+// position (push/cuda_methods.py:17-52, particle_buffer_handling.py:637-658, cuda_sorting.py:22-88)
+__global__ void k_push_x_key(int64_t n, double *__restrict__ x, double *__restrict__ y, double *__restrict__ z,
+                             const double *__restrict__ ux, const double *__restrict__ uy,
+                             const double *__restrict__ uz, const double *__restrict__ inv_gamma,
+                             double chdt, int wrap, double wrap_zmin, double wrap_zmax,
+                             double invdz, double key_zmin, int Nz, double invdr, double rmin, int Nr,
+                             int32_t *__restrict__ cell_idx) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double g = inv_gamma[i];
+    const double xn = x[i] + chdt * g * 1. * ux[i];
+    const double yn = y[i] + chdt * g * 1. * uy[i];
+    double zn = z[i] + chdt * g * 1. * uz[i];
+    if (wrap) {
+        const double l_box = wrap_zmax - wrap_zmin;
+        while (zn >= wrap_zmax) zn -= l_box;
+        while (zn < wrap_zmin) zn += l_box;
+    }
+    x[i] = xn; y[i] = yn; z[i] = zn;
+    if (cell_idx) cell_idx[i] = b2_cell_of(b2_cyl(xn, yn, zn, invdz, key_zmin, invdr, rmin), Nz, Nr);
 }
 
 __global__ void k_shift_periodic(int64_t n, double *__restrict__ z, double zmin, double zmax) {
@@ -313,9 +342,9 @@ template <int NM>
 static void launch_gather_push(bool cubic, unsigned g, cudaStream_t s, int64_t n, double *x, double *y, double *z,
                                double *ux, double *uy, double *uz, double *ig, double rg, double invdz, double zmin,
                                int Nz, double invdr, double rmin, int Nr, const B2Grids &G, double ec, double bc,
-                               double chdt) {
-    if (cubic) k_gather_push<NM, true><<<g, 256, 0, s>>>(n, x, y, z, ux, uy, uz, ig, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt);
-    else k_gather_push<NM, false><<<g, 256, 0, s>>>(n, x, y, z, ux, uy, uz, ig, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt);
+                               double chdt, int32_t *cell_idx, double key_zmin) {
+    if (cubic) k_gather_push<NM, true><<<g, 256, 0, s>>>(n, x, y, z, ux, uy, uz, ig, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt, cell_idx, key_zmin);
+    else k_gather_push<NM, false><<<g, 256, 0, s>>>(n, x, y, z, ux, uy, uz, ig, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt, cell_idx, key_zmin);
 }
 
 extern "C" {
@@ -425,7 +454,7 @@ int b2_push_x(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, const dou
 int b2_gather_push(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, double *ux, double *uy, double *uz,
                    double *inv_gamma, double rmax_gather, double invdz, double zmin, int Nz, double invdr,
                    double rmin, int Nr, int Nm, const void *const *grids, int cubic, double q, double m,
-                   double dt_p, double dt_x, void *stream) {
+                   double dt_p, double dt_x, int32_t *cell_idx, double key_zmin, void *stream) {
     if (n <= 0) return 0;
     B2Prof prof_(B2P_GATHER_PUSH, b2_stream_of(ctx, stream));
     if (Nm < 1 || Nm > 4) return b2_fail(-3, "b2_gather_push: Nm must be in 1..4", __FILE__, __LINE__);
@@ -434,7 +463,7 @@ int b2_gather_push(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, doub
     cudaStream_t s = b2_stream_of(ctx, stream);
     unsigned g = grid1d(n, 256);
     const double ec = q * dt_p / (m * B2_C_LIGHT), bc = 0.5 * q * dt_p / m, chdt = B2_C_LIGHT * dt_x;
-#define B2_ARGS cubic != 0, g, s, n, x, y, z, ux, uy, uz, inv_gamma, rmax_gather, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt
+#define B2_ARGS cubic != 0, g, s, n, x, y, z, ux, uy, uz, inv_gamma, rmax_gather, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt, cell_idx, key_zmin
     switch (Nm) {
         case 1: launch_gather_push<1>(B2_ARGS); break;
         case 2: launch_gather_push<2>(B2_ARGS); break;
@@ -442,6 +471,18 @@ int b2_gather_push(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, doub
         default: launch_gather_push<4>(B2_ARGS); break;
     }
 #undef B2_ARGS
+    B2_LAUNCHED();
+    return 0;
+}
+
+int b2_push_x_key(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, const double *ux, const double *uy,
+                  const double *uz, const double *inv_gamma, double dt, int wrap, double wrap_zmin, double wrap_zmax,
+                  double invdz, double key_zmin, int Nz, double invdr, double rmin, int Nr, int32_t *cell_idx,
+                  void *stream) {
+    if (n <= 0) return 0;
+    B2Prof prof_(B2P_PUSH, b2_stream_of(ctx, stream));
+    k_push_x_key<<<grid1d(n, 256), 256, 0, b2_stream_of(ctx, stream)>>>(n, x, y, z, ux, uy, uz, inv_gamma,
+        B2_C_LIGHT * dt, wrap, wrap_zmin, wrap_zmax, invdz, key_zmin, Nz, invdr, rmin, Nr, cell_idx);
     B2_LAUNCHED();
     return 0;
 }

@@ -113,8 +113,14 @@ class Simulation(object):
         fld.interp2spect('E')
         fld.interp2spect('B')
 
+        # Single periodic domain, fused mode: z is wrapped inside the second position push and
+        # rho_prev of step n+1 is (bit for bit) the rho_next that push_rho already moved over, so
+        # the per-step exchange_particles + re-deposition of rho_prev (main.py:435-449, needed in
+        # the reference only because particles may have been added/removed) is done at i_step==0 only.
+        wrap_in_push = self.fused and periodic_single and move_positions
         for i_step in range(N):
-            if self.iteration % self.comm.exchange_period == 0 or i_step == 0:
+            exchange_now = (self.iteration % self.comm.exchange_period == 0 or i_step == 0)
+            if exchange_now and not (wrap_in_push and i_step > 0):
                 for species in ptcl:
                     self.comm.exchange_particles(species, fld, self.time)
                 self.deposit('rho_prev', exchange=(use_true_rho is True))
@@ -123,9 +129,11 @@ class Simulation(object):
 
             for species in ptcl:
                 species.keep_fields_sorted = True
+            gal_shift = self.v_comoving * 0.5 * dt if self.use_galilean else 0.
             if fuse_gp:
                 for species in ptcl:
-                    species.gather_and_push(fld.interp, self.comm, 0.5 * dt)
+                    species.gather_and_push(fld.interp, self.comm, 0.5 * dt,
+                                            key_zmin=fld.interp[0].zmin + gal_shift)
             else:
                 for species in ptcl:
                     species.gather(fld.interp, self.comm)
@@ -142,8 +150,14 @@ class Simulation(object):
 
             self.deposit('J', exchange=(correct_currents is False))
             if move_positions:
-                for species in ptcl:
-                    species.push_x(0.5 * dt)
+                if self.fused:
+                    z0 = fld.interp[0].zmin + gal_shift
+                    wrap = (z0, z0 + (fld.interp[0].zmax - fld.interp[0].zmin)) if wrap_in_push else None
+                    for species in ptcl:
+                        species.push_x_and_key(0.5 * dt, fld, wrap=wrap, key_zmin=z0)
+                else:
+                    for species in ptcl:
+                        species.push_x(0.5 * dt)
             if self.use_galilean:
                 self.shift_galilean_boundaries(0.5 * dt)
             self.deposit('rho_next', exchange=(use_true_rho is True))

@@ -164,6 +164,7 @@ class Particles(object):
                        self.ux.ptr, self.uy.ptr, self.uz.ptr, self.inv_gamma.ptr,
                        dt, x_push, y_push, z_push, None)
         self.sorted = False
+        self._keys_fresh = False
 
     @staticmethod
     def _eb_grid_ptrs(grid):
@@ -181,21 +182,47 @@ class Particles(object):
                        len(grid), self._eb_grid_ptrs(grid), int(self.particle_shape == 'cubic'),
                        self.Ex.ptr, self.Ey.ptr, self.Ez.ptr, self.Bx.ptr, self.By.ptr, self.Bz.ptr, None)
 
-    def gather_and_push(self, grid, comm, dt_x):
+    def gather_and_push(self, grid, comm, dt_x, key_zmin=None):
         """Fused gather + push_p + push_x(dt_x): the call sequence main.py:470-490 in one
-        kernel (the gathered fields stay in registers; Ex..Bz are not written)."""
+        kernel (the gathered fields stay in registers; Ex..Bz are not written).  With
+        `key_zmin` the kernel also emits the cell keys of the new positions for a grid whose
+        left edge is key_zmin, so that the next sort skips its cell-index pass."""
         if self.q == 0:
             self.push_x(dt_x)
             return
         self._need_gpu()
         ctx = _lib.context()
         g0 = grid[0]
+        keys = None
+        if key_zmin is not None:
+            if self.cell_idx is None or self.cell_idx.size != self.Ntot:
+                self._alloc_sort_arrays()
+            keys = self.cell_idx.ptr
         call.b2_gather_push(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr,
                             self.ux.ptr, self.uy.ptr, self.uz.ptr, self.inv_gamma.ptr,
                             comm.get_rmax(with_damp=False), g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin,
                             g0.Nr, len(grid), self._eb_grid_ptrs(grid), int(self.particle_shape == 'cubic'),
-                            self.q, self.m, self.dt, dt_x, None)
+                            self.q, self.m, self.dt, dt_x, keys, 0. if key_zmin is None else key_zmin, None)
         self.sorted = False
+        self._keys_fresh = key_zmin is not None
+
+    def push_x_and_key(self, dt, fld, wrap=None, key_zmin=None):
+        """push_x(dt) fused with the periodic wrap of z into `wrap=(zmin, zmax)` and with the
+        cell-key computation of the following sort (on a grid starting at key_zmin)."""
+        self._need_gpu()
+        g0 = fld.interp[0]
+        keys = None
+        if key_zmin is not None:
+            if self.cell_idx is None or self.cell_idx.size != self.Ntot:
+                self._alloc_sort_arrays()
+            keys = self.cell_idx.ptr
+        wz = wrap if wrap is not None else (0., 0.)
+        call.b2_push_x_key(_lib.context().handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr,
+                           self.ux.ptr, self.uy.ptr, self.uz.ptr, self.inv_gamma.ptr, dt,
+                           int(wrap is not None), wz[0], wz[1], g0.invdz,
+                           0. if key_zmin is None else key_zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, keys, None)
+        self.sorted = False
+        self._keys_fresh = key_zmin is not None
 
     # ------------------------------------------------------------------ sorting
     def sort_particles(self, fld):
@@ -206,8 +233,10 @@ class Particles(object):
         g0 = fld.interp[0]
         if self.cell_idx is None or self.cell_idx.size != self.Ntot:
             self._alloc_sort_arrays()
-        call.b2_cell_index(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr,
-                           g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, self.cell_idx.ptr, None)
+        if not getattr(self, '_keys_fresh', False):
+            call.b2_cell_index(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr,
+                               g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, self.cell_idx.ptr, None)
+        self._keys_fresh = False
         call.b2_sort_cells(ctx.handle, self.Ntot, self.cell_idx.ptr, self.sorted_idx.ptr,
                            self.prefix_sum.ptr, g0.Nz, g0.Nr, None)
         self.prefix_sum_shift = 0
@@ -269,3 +298,4 @@ class Particles(object):
         self._need_gpu()
         call.b2_shift_periodic(_lib.context().handle, self.Ntot, self.z.ptr, zmin, zmax, None)
         self.sorted = False
+        self._keys_fresh = False

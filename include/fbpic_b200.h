@@ -108,7 +108,16 @@ int b2_gather_push(b2_ctx *ctx, int64_t n, double *d_x, double *d_y, double *d_z
                    double *d_ux, double *d_uy, double *d_uz, double *d_inv_gamma,
                    double rmax_gather, double invdz, double zmin, int Nz, double invdr, double rmin, int Nr,
                    int Nm, const void *const *d_grids, int cubic,
-                   double q, double m, double dt_p, double dt_x, void *stream);
+                   double q, double m, double dt_p, double dt_x,
+                   int32_t *d_cell_idx /* NULL, or out: cell key of the new position on a grid starting
+                                          at key_zmin (saves the cell-index pass of the next sort) */,
+                   double key_zmin, void *stream);
+/* push_x(dt) + optional periodic wrap of z into [wrap_zmin, wrap_zmax) + optional cell key */
+int b2_push_x_key(b2_ctx *ctx, int64_t n, double *d_x, double *d_y, double *d_z,
+                  const double *d_ux, const double *d_uy, const double *d_uz, const double *d_inv_gamma,
+                  double dt, int wrap, double wrap_zmin, double wrap_zmax,
+                  double invdz, double key_zmin, int Nz, double invdr, double rmin, int Nr,
+                  int32_t *d_cell_idx, void *stream);
 int b2_shift_periodic(b2_ctx *ctx, int64_t n, double *d_z, double zmin, double zmax, void *stream);
 /* v[i] += value : z-shift of the periodic images received across the ring closure
  * (boundary_communicator.py:815-821) */
