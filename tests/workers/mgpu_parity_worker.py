@@ -1,0 +1,88 @@
+"""N-GPU vs 1-GPU parity of the z-sharded PIC loop (run under torchrun, one rank per GPU).
+Every rank advances its slab with NCCL guard-cell exchange + particle migration; rank 0 also
+advances the same global problem alone on its GPU; the physical regions must agree.
+Prints MGPU_PARITY_OK on success."""
+import os
+import sys
+import numpy as np
+import torch
+import torch.distributed as dist
+from scipy.constants import c, e, m_e
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from fbpic_b200 import Simulation                     # noqa: E402
+from fbpic_b200.particles import generate_evenly_spaced   # noqa: E402
+
+
+def global_particles(Nz, Nr, zmax, rmax, n_e, seed=11):
+    np.random.seed(seed)
+    Ntot, x, y, z, ux, uy, uz, ig, w = generate_evenly_spaced(
+        2 * Nz, 0., zmax, 2 * (Nr - 2), 0., rmax * (Nr - 2) / Nr, 8, n_e, None, 0., 0., 0., 0., 0., 0.)
+    k0 = 2 * np.pi / zmax * 3
+    uz = 0.2 * np.sin(k0 * z) * np.exp(-(x**2 + y**2) / (6.e-6)**2)
+    ux = 0.05 * x / 6.e-6 * np.cos(k0 * z) * np.exp(-(x**2 + y**2) / (6.e-6)**2)
+    uy = 0.05 * y / 6.e-6 * np.cos(k0 * z) * np.exp(-(x**2 + y**2) / (6.e-6)**2)
+    ig = 1. / np.sqrt(1 + ux**2 + uy**2 + uz**2)
+    return dict(x=x, y=y, z=z, ux=ux, uy=uy, uz=uz, inv_gamma=ig, w=w)
+
+
+def set_species(sim, P, zlo, zhi):
+    sp = sim.add_new_species(q=-e, m=m_e)
+    sel = (P['z'] >= zlo) & (P['z'] < zhi)
+    for k, v in P.items():
+        setattr(sp, k, v[sel].copy())
+    sp.Ntot = int(sel.sum())
+    for k in ('Ex', 'Ey', 'Ez', 'Bx', 'By', 'Bz'):
+        setattr(sp, k, np.zeros(sp.Ntot))
+    return sp
+
+
+def main():
+    dist.init_process_group('gloo')
+    rank, size = dist.get_rank(), dist.get_world_size()
+    nsteps = int(os.environ.get('MGPU_STEPS', '24'))
+    shape = os.environ.get('MGPU_SHAPE', 'linear')
+    Nz, Nr, Nm, zmax, rmax, n_e, n_order = 64 * size, 24, 2, 12.8e-6 * size, 12.e-6, 2.e24, 8
+    dt = zmax / Nz / c
+    P = global_particles(Nz, Nr, zmax, rmax, n_e)
+    kw = dict(n_order=n_order, particle_shape=shape, boundaries={'z': 'periodic', 'r': 'reflective'})
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, **kw)
+    assert sim.comm.size == size and sim.comm.n_guard > 0
+    zlo, zhi = sim.comm.get_zmin_zmax(local=True, with_damp=False, with_guard=False, rank=rank)
+    set_species(sim, P, zlo, zhi)
+    sim.step(nsteps)
+    ng = sim.comm.n_guard
+    names = ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'Jr', 'Jt', 'Jz', 'rho')
+    loc = np.stack([getattr(sim.fld.interp[m], k)[ng:sim.fld.interp[m].Nz - ng] for m in range(Nm) for k in names])
+    n_local = sim.ptcl[0].Ntot
+    gathered = [None] * size
+    dist.all_gather_object(gathered, (loc, n_local))
+    ok = True
+    if rank == 0:
+        glob = np.concatenate([g[0] for g in gathered], axis=1)
+        ref = Simulation(Nz, zmax, Nr, rmax, Nm, dt, use_all_mpi_ranks=False, n_guard=ng, **kw)
+        assert ref.comm.size == 1
+        set_species(ref, P, -1., 1.e9)
+        ref.step(nsteps)
+        full = np.stack([getattr(ref.fld.interp[m], k) for m in range(Nm) for k in names])
+        assert sum(g[1] for g in gathered) == ref.ptcl[0].Ntot, 'particle count not conserved'
+        for i, nme in enumerate([k + str(m) for m in range(Nm) for k in names]):
+            grp = slice((i // 10) * 10 + (0 if i % 10 < 3 else 3 if i % 10 < 6 else 6 if i % 10 < 9 else 9),
+                        (i // 10) * 10 + (3 if i % 10 < 3 else 6 if i % 10 < 6 else 9 if i % 10 < 9 else 10))
+            scale = max(np.abs(full[j]).max() for m in range(Nm) for j in range(m * 10 + grp.start % 10, m * 10 + (grp.stop - 1) % 10 + 1))
+            err = np.abs(glob[i] - full[i]).max()
+            if not err <= 1e-9 * scale:
+                ok = False
+                print('MISMATCH %s: err %.3e scale %.3e' % (nme, err, scale))
+        print('max particles/rank', [g[1] for g in gathered])
+    flag = torch.tensor([1 if ok else 0])
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    if rank == 0 and ok:
+        print('MGPU_PARITY_OK size=%d steps=%d' % (size, nsteps))
+    sys.exit(0 if int(flag[0]) else 1)
+
+
+if __name__ == '__main__':
+    main()
