@@ -67,14 +67,15 @@ def main():
         ref.step(nsteps)
         full = np.stack([getattr(ref.fld.interp[m], k) for m in range(Nm) for k in names])
         assert sum(g[1] for g in gathered) == ref.ptcl[0].Ntot, 'particle count not conserved'
-        for i, nme in enumerate([k + str(m) for m in range(Nm) for k in names]):
-            grp = slice((i // 10) * 10 + (0 if i % 10 < 3 else 3 if i % 10 < 6 else 6 if i % 10 < 9 else 9),
-                        (i // 10) * 10 + (3 if i % 10 < 3 else 6 if i % 10 < 6 else 9 if i % 10 < 9 else 10))
-            scale = max(np.abs(full[j]).max() for m in range(Nm) for j in range(m * 10 + grp.start % 10, m * 10 + (grp.stop - 1) % 10 + 1))
-            err = np.abs(glob[i] - full[i]).max()
-            if not err <= 1e-9 * scale:
-                ok = False
-                print('MISMATCH %s: err %.3e scale %.3e' % (nme, err, scale))
+        groups = {'E': (0, 3), 'B': (3, 6), 'J': (6, 9), 'rho': (9, 10)}
+        for gname, (g0, g1) in groups.items():
+            idx = [m * 10 + j for m in range(Nm) for j in range(g0, g1)]
+            scale = max(np.abs(full[i]).max() for i in idx)
+            for i in idx:
+                err = np.abs(glob[i] - full[i]).max()
+                if not err <= 1e-9 * scale:
+                    ok = False
+                    print('MISMATCH %s m%d: err %.3e scale %.3e' % (names[i % 10], i // 10, err, scale))
         print('max particles/rank', [g[1] for g in gathered])
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, src=0)
