@@ -152,7 +152,10 @@ class Simulation(object):
             if move_positions:
                 if self.fused:
                     z0 = fld.interp[0].zmin + gal_shift
-                    wrap = (z0, z0 + (fld.interp[0].zmax - fld.interp[0].zmin)) if wrap_in_push else None
+                    # (no wrap after the last step of this call: the reference leaves x^{n+1} unwrapped until
+                    #  the exchange_particles at the start of the next step, main.py:435-442)
+                    wrap = (z0, z0 + (fld.interp[0].zmax - fld.interp[0].zmin)) \
+                        if (wrap_in_push and i_step < N - 1) else None
                     for species in ptcl:
                         species.push_x_and_key(0.5 * dt, fld, wrap=wrap, key_zmin=z0)
                 else:
