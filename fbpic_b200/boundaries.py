@@ -243,20 +243,27 @@ class BoundaryCommunicator(object):
                                        DeviceArray((len(arrays), nrow, Nr), np.complex128))
             recv['l'], recv['r'] = self._halo_buf[key]
         slab_bytes = nrow * Nr * 16
+        # NCCL pairs the k-th send to a peer with the k-th receive posted for that peer.  What goes
+        # out through my LEFT face arrives at my left neighbour's RIGHT face, so sends are posted
+        # (left, right) and receives (right, left): with 2 ranks on a ring both neighbours are the
+        # same peer and this order is what keeps the two directions apart (the reference uses MPI
+        # tags 1/2 for that, boundary_communicator.py:688-699).
         call.b2_nccl_group_start()
         for i, a in enumerate(arrays):
             if self.left_proc is not None:
                 call.b2_nccl_send(ctx.handle, a[plan['send_l'][0]:plan['send_l'][1]].ptr, slab_bytes,
                                   self.left_proc, None)
-                dst = a[plan['recv_l'][0]:plan['recv_l'][1]].ptr if method == 'replace' \
-                    else recv['l'].ptr + i * slab_bytes
-                call.b2_nccl_recv(ctx.handle, dst, slab_bytes, self.left_proc, None)
             if self.right_proc is not None:
                 call.b2_nccl_send(ctx.handle, a[plan['send_r'][0]:plan['send_r'][1]].ptr, slab_bytes,
                                   self.right_proc, None)
+            if self.right_proc is not None:
                 dst = a[plan['recv_r'][0]:plan['recv_r'][1]].ptr if method == 'replace' \
                     else recv['r'].ptr + i * slab_bytes
                 call.b2_nccl_recv(ctx.handle, dst, slab_bytes, self.right_proc, None)
+            if self.left_proc is not None:
+                dst = a[plan['recv_l'][0]:plan['recv_l'][1]].ptr if method == 'replace' \
+                    else recv['l'].ptr + i * slab_bytes
+                call.b2_nccl_recv(ctx.handle, dst, slab_bytes, self.left_proc, None)
         call.b2_nccl_group_end()
         if method == 'add':
             for i, a in enumerate(arrays):
@@ -301,13 +308,14 @@ class BoundaryCommunicator(object):
         if self.size > 1:
             self.mpi_comm.init_nccl()
             cnt = DeviceArray.from_numpy(np.array([n_send_l, n_send_r, 0, 0], dtype=np.int64))
-            call.b2_nccl_group_start()
+            call.b2_nccl_group_start()       # sends (left, right), receives (right, left): see exchange_fields
             if self.left_proc is not None:
                 call.b2_nccl_send(ctx.handle, cnt.ptr, 8, self.left_proc, None)
-                call.b2_nccl_recv(ctx.handle, cnt.ptr + 16, 8, self.left_proc, None)
             if self.right_proc is not None:
                 call.b2_nccl_send(ctx.handle, cnt.ptr + 8, 8, self.right_proc, None)
                 call.b2_nccl_recv(ctx.handle, cnt.ptr + 24, 8, self.right_proc, None)
+            if self.left_proc is not None:
+                call.b2_nccl_recv(ctx.handle, cnt.ptr + 16, 8, self.left_proc, None)
             call.b2_nccl_group_end()
             h = cnt.get()
             n_recv_l, n_recv_r = int(h[2]), int(h[3])
@@ -317,17 +325,15 @@ class BoundaryCommunicator(object):
             call.b2_nccl_group_start()
             for k in FLOAT_ATTRS:
                 old = getattr(species, k)
-                if self.left_proc is not None:
-                    if n_send_l:
-                        call.b2_nccl_send(ctx.handle, old.ptr, 8 * n_send_l, self.left_proc, None)
-                    if n_recv_l:
-                        call.b2_nccl_recv(ctx.handle, new[k].ptr, 8 * n_recv_l, self.left_proc, None)
-                if self.right_proc is not None:
-                    if n_send_r:
-                        call.b2_nccl_send(ctx.handle, old.ptr + 8 * i_max, 8 * n_send_r, self.right_proc, None)
-                    if n_recv_r:
-                        call.b2_nccl_recv(ctx.handle, new[k].ptr + 8 * (n_recv_l + n_stay), 8 * n_recv_r,
-                                          self.right_proc, None)
+                if self.left_proc is not None and n_send_l:
+                    call.b2_nccl_send(ctx.handle, old.ptr, 8 * n_send_l, self.left_proc, None)
+                if self.right_proc is not None and n_send_r:
+                    call.b2_nccl_send(ctx.handle, old.ptr + 8 * i_max, 8 * n_send_r, self.right_proc, None)
+                if self.right_proc is not None and n_recv_r:
+                    call.b2_nccl_recv(ctx.handle, new[k].ptr + 8 * (n_recv_l + n_stay), 8 * n_recv_r,
+                                      self.right_proc, None)
+                if self.left_proc is not None and n_recv_l:
+                    call.b2_nccl_recv(ctx.handle, new[k].ptr, 8 * n_recv_l, self.left_proc, None)
             call.b2_nccl_group_end()
         for k in FLOAT_ATTRS:
             if n_stay:
