@@ -198,6 +198,7 @@ def context(device=None):
 # ---------------------------------------------------------------------------
 class _Allocation(object):
     def __init__(self, nbytes):
+        context()          # binds this process to its GPU (LOCAL_RANK) BEFORE the first cudaMalloc
         self.ptr = P()
         call.b2_malloc(ctypes.byref(self.ptr), nbytes)
         self.nbytes = nbytes
