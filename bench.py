@@ -199,9 +199,9 @@ def main():
         return
 
     # ------------------------------------------------------------------ B200 arm
+    os.environ['NCCL_DEBUG'] = os.environ.get('B2_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
     from fbpic_b200 import _lib
     from fbpic_b200._lib import call
-    from fbpic_b200.boundaries import world as pg_world
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -288,6 +288,8 @@ def main():
         'gather_push': 112 * Ntot_local + 6 * cfg['Nm'] * cells,
         'permute': (8 + 128) * Ntot_local,
         'sort': (4 + 12 + 4) * Ntot_local,
+        'fft': 2 * cells,
+        'spectral': (11 + 8) * cells + 5 * cells // 2,
     }
     top = max(prof.items(), key=lambda kv: kv[1]['ms'])[0] if prof else None
     roofline = None

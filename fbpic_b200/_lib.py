@@ -28,6 +28,15 @@ class SpectralMode(ctypes.Structure):
                [('mu_0', c_double), ('epsilon_0', c_double)]
 
 
+class DhtJob(ctypes.Structure):
+    """Mirror of `b2_dht_job` (include/fbpic_b200.h)."""
+    _fields_ = [('in1', c_void_p), ('in2', c_void_p), ('out1', c_void_p), ('out2', c_void_p),
+                ('M1', c_void_p), ('M2', c_void_p), ('rowscale', c_void_p), ('kind', c_int)]
+
+
+DHT_SCALAR, DHT_RT_TO_PM, DHT_PM_TO_RT = 0, 1, 2
+
+
 # name -> argtypes; every entry returns int status unless listed in _RESTYPES
 _SIGNATURES = {
     'b2_device_count': [ctypes.POINTER(c_int)],
@@ -83,6 +92,7 @@ _SIGNATURES = {
     'b2_dht': [P, P, P, P, P, c_int, c_int, P],
     'b2_dht_rt_to_pm': [P, P, P, P, P, P, P, P, c_int, c_int, P],
     'b2_dht_pm_to_rt': [P, P, P, P, P, P, P, P, c_int, c_int, P],
+    'b2_dht_batch': [P, c_int, ctypes.POINTER(DhtJob), c_int, c_int, P],
     'b2_rt_to_pm': [P, P, P, c_int, c_int, P],
     'b2_pm_to_rt': [P, P, P, c_int, c_int, P],
     'b2_filter': [P, c_int, P, P, P, c_int, c_int, P],

@@ -14,7 +14,8 @@
 // fp64 only: sm_100a has no tcgen05 f64 kind; the f64 tensor path is mma.sync (DMMA.8x8x4 in SASS,
 // measured 37.1 TFLOP/s peak on B200, profiles/r01_microbench.txt).  Bound: fp64 tensor pipe
 // (AI = Nr/8 flop/B).  Several (array, matrix) jobs are batched in one launch (grid.z) so that the
-// 148 SMs see >1 full wave of CTAs.
+// 148 SMs see >1 full wave of CTAs.  16 warps per CTA (4x4), warp tile 16 iz x 32 columns: 32 fp64
+// accumulators per thread keep the kernel under 128 registers so that 16 warps fit on an SM.
 #include "b2_common.cuh"
 
 #define DHT_BM 64          // iz rows per CTA tile (=128 real rows)
@@ -22,7 +23,7 @@
 #define DHT_BK 16          // K chunk
 #define DHT_AP (DHT_BK + 4)   // A row pitch in complex elements: 20 -> conflict-free LDS.128
 #define DHT_BP (DHT_BN + 4)   // B row pitch in doubles: 132 -> conflict-free LDS.64
-#define DHT_THREADS 256
+#define DHT_THREADS 512
 #define DHT_MAX_JOBS 12
 
 struct DhtJob {
@@ -51,12 +52,12 @@ k_dht(DhtJobs jobs, int Nz, int Nr) {
     constexpr int A_ELEMS = NPROD * DHT_BM * DHT_AP;     // per buffer (double2)
     constexpr int B_ELEMS = DHT_BK * DHT_BP;             // per buffer (double)
     constexpr int NCOL = DHT_BN / NPROD;                 // output columns per product in this CTA
-    constexpr int NI = NCOL / 2 / 8;                     // 8-col MMA blocks per warp per product (8 | 4)
+    constexpr int NI = NCOL / 4 / 8;                     // 8-col MMA blocks per warp per product (4 | 2)
 
     const DhtJob &J = jobs.j[blockIdx.z];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 1, wn = warp & 1;
+    const int wm = warp >> 2, wn = warp & 3;
     const int iz0 = blockIdx.y * DHT_BM;
     const int n0 = blockIdx.x * NCOL;
     const bool mix = (NPROD == 1) && (J.in2 != nullptr);
@@ -76,13 +77,13 @@ k_dht(DhtJobs jobs, int Nz, int Nr) {
     // register staging of the next K chunk: load_tiles only ISSUES the global loads (raw values);
     // the (r,t)->(p,m) mixing arithmetic happens in store_tiles, after the MMAs of the current
     // chunk, so that no instruction depending on the loads sits in front of the tensor work.
-    double2 ra[2][4];
-    double rb[8];
+    double2 ra[2][2];
+    double rb[4];
 
     auto load_tiles = [&](int kt) {
         const int k0 = kt * DHT_BK;
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
+        for (int qq = 0; qq < 2; ++qq) {
             const int e = tid + DHT_THREADS * qq;
             const int izl = e >> 4, j = e & 15;
             const int iz = iz0 + izl, jj = k0 + j;
@@ -92,7 +93,7 @@ k_dht(DhtJobs jobs, int Nz, int Nr) {
             if (NPROD == 2 || mix) ra[1][qq] = ok ? __ldg(J.in2 + o) : make_double2(0., 0.);
         }
 #pragma unroll
-        for (int qq = 0; qq < 8; ++qq) {
+        for (int qq = 0; qq < 4; ++qq) {
             const int e = tid + DHT_THREADS * qq;
             const int k = e / DHT_BN, c = e % DHT_BN;          // c: column within the 128-wide B tile
             const int kk = k0 + k;
@@ -109,7 +110,7 @@ k_dht(DhtJobs jobs, int Nz, int Nr) {
     };
     auto store_tiles = [&](int buf) {
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
+        for (int qq = 0; qq < 2; ++qq) {
             const int e = tid + DHT_THREADS * qq;
             const int izl = e >> 4, j = e & 15;
             if (NPROD == 1) {
@@ -127,7 +128,7 @@ k_dht(DhtJobs jobs, int Nz, int Nr) {
             }
         }
 #pragma unroll
-        for (int qq = 0; qq < 8; ++qq) {
+        for (int qq = 0; qq < 4; ++qq) {
             const int e = tid + DHT_THREADS * qq;
             const int k = e / DHT_BN, c = e % DHT_BN;
             sB[buf * B_ELEMS + k * DHT_BP + c] = rb[qq];
@@ -154,7 +155,7 @@ k_dht(DhtJobs jobs, int Nz, int Nr) {
             for (int p = 0; p < NPROD; ++p)
 #pragma unroll
                 for (int n = 0; n < NI; ++n) {
-                    const double b = B[(k4 * 4 + t) * DHT_BP + p * NCOL + wn * (NCOL / 2) + n * 8 + g];
+                    const double b = B[(k4 * 4 + t) * DHT_BP + p * NCOL + wn * (NCOL / 4) + n * 8 + g];
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         dmma(acc[p][i][n][0][0], acc[p][i][n][0][1], a[p][i].x, b);
@@ -176,7 +177,7 @@ k_dht(DhtJobs jobs, int Nz, int Nr) {
         for (int n = 0; n < NI; ++n) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int col = n0 + wn * (NCOL / 2) + n * 8 + 2 * t + h;
+                const int col = n0 + wn * (NCOL / 4) + n * 8 + 2 * t + h;
                 if (col >= Nr) continue;
                 const size_t o = (size_t)iz * Nr + col;
                 if (NPROD == 1) {
@@ -210,6 +211,44 @@ static int launch_dht(b2_ctx *ctx, const DhtJobs &jobs, int njobs, int Nz, int N
 }
 
 extern "C" {
+
+// Batched transforms: one launch per kernel flavour for the whole list (all modes / components).
+int b2_dht_batch(b2_ctx *ctx, int njobs, const b2_dht_job *jobs, int Nz, int Nr, void *stream) {
+    DhtJobs j1, j2;
+    int n1 = 0, n2 = 0;
+    for (int k = 0; k < njobs; ++k) {
+        const b2_dht_job &u = jobs[k];
+        if (u.kind == B2_DHT_SCALAR) {
+            if (n1 >= DHT_MAX_JOBS) return b2_fail(-3, "b2_dht_batch: too many jobs", __FILE__, __LINE__);
+            DhtJob &j = j1.j[n1++];
+            j.in1 = (const double2 *)u.in1; j.in2 = nullptr; j.out1 = (double2 *)u.out1; j.out2 = nullptr;
+            j.M1 = u.M1; j.M2 = nullptr; j.rowscale = u.rowscale;
+            j.c1 = make_double2(1., 0.); j.c2 = make_double2(0., 0.);
+        } else if (u.kind == B2_DHT_RT_TO_PM) {
+            if (n1 + 2 > DHT_MAX_JOBS) return b2_fail(-3, "b2_dht_batch: too many jobs", __FILE__, __LINE__);
+            for (int h = 0; h < 2; ++h) {
+                DhtJob &j = j1.j[n1++];
+                j.in1 = (const double2 *)u.in1; j.in2 = (const double2 *)u.in2;
+                j.out1 = (double2 *)(h == 0 ? u.out1 : u.out2); j.out2 = nullptr;
+                j.M1 = (h == 0 ? u.M1 : u.M2); j.M2 = nullptr; j.rowscale = u.rowscale;
+                j.c1 = make_double2(0.5, 0.); j.c2 = make_double2(0., h == 0 ? -0.5 : 0.5);
+            }
+        } else if (u.kind == B2_DHT_PM_TO_RT) {
+            if (n2 >= DHT_MAX_JOBS) return b2_fail(-3, "b2_dht_batch: too many jobs", __FILE__, __LINE__);
+            DhtJob &j = j2.j[n2++];
+            j.in1 = (const double2 *)u.in1; j.in2 = (const double2 *)u.in2;
+            j.out1 = (double2 *)u.out1; j.out2 = (double2 *)u.out2;
+            j.M1 = u.M1; j.M2 = u.M2; j.rowscale = u.rowscale;
+            j.c1 = make_double2(1., 0.); j.c2 = make_double2(1., 0.);
+        } else {
+            return b2_fail(-3, "b2_dht_batch: unknown job kind", __FILE__, __LINE__);
+        }
+    }
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    if (n1) { int rc = launch_dht<1>(ctx, j1, n1, Nz, Nr, s); if (rc) return rc; }
+    if (n2) { int rc = launch_dht<2>(ctx, j2, n2, Nz, Nr, s); if (rc) return rc; }
+    return 0;
+}
 
 int b2_dht(b2_ctx *ctx, const void *in, void *out, const double *M, const double *rowscale, int Nz, int Nr,
            void *stream) {

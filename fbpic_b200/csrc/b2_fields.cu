@@ -269,7 +269,7 @@ int b2_fft_z(b2_ctx *ctx, const void *in, void *out, int Nz, int Nr, int inverse
     r = cufftExecZ2Z(plan, (cufftDoubleComplex *)in, (cufftDoubleComplex *)out, inverse ? CUFFT_INVERSE : CUFFT_FORWARD);
     if (r != CUFFT_SUCCESS) return b2_fail((int)r, "cufftExecZ2Z failed", __FILE__, __LINE__);
     g_b2_launches.fetch_add(1);
-    if (inverse) {
+    if (inverse == 1) {      // inverse == 2: raw inverse (the 1/Nz factor is folded into the Hankel matrices)
         const size_t n = (size_t)Nz * Nr;
         k_scale<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((double2 *)out, 1. / Nz, n);
         B2_LAUNCHED();

@@ -2,6 +2,9 @@
 // Vay push, position push and the fused gather+push kernel.
 #include "b2_common.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <climits>
+
+static inline unsigned grid1d(int64_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 
 // =====================================================================================
 // cell key (cuda_sorting.py:55-88)
@@ -287,6 +290,138 @@ k_gather_push(int64_t n, double *__restrict__ x, double *__restrict__ y, double 
     if (cell_idx) cell_idx[i] = b2_cell_of(b2_cyl(xn, yn, zn, invdz, key_zmin, invdr, rmin), Nz, Nr);
 }
 
+// ---- tiled variant (linear shapes) -------------------------------------------------------------
+// When the particles are cell-sorted, the 128 particles of a CTA touch a handful of neighbouring
+// cells.  The CTA finds the bounding box of its stencils (integer min/max in shared memory), stages
+// that (rows x cols) tile of all 6*NM field arrays in shared memory with coalesced 16-byte loads, and
+// every thread then gathers from shared memory: ~50 dependent global loads per particle become a few
+// coalesced tile loads per thread.  A CTA whose bounding box does not fit (unsorted particles, or a
+// z-row boundary of the sorted order) falls back to global loads; results are identical either way.
+#define GP_TPB 128
+#define GP_TILE_CELLS 96
+
+template <int NM>
+__global__ void __launch_bounds__(GP_TPB, 5)
+k_gather_push_tiled(int64_t n, double *__restrict__ x, double *__restrict__ y, double *__restrict__ z,
+                    double *__restrict__ ux, double *__restrict__ uy, double *__restrict__ uz,
+                    double *__restrict__ inv_gamma, double rmax_gather, double invdz, double zmin, int Nz,
+                    double invdr, double rmin, int Nr, B2Grids G, double econst, double bconst, double chdt,
+                    int32_t *__restrict__ cell_idx, double key_zmin) {
+    __shared__ double2 tile[6 * NM][GP_TILE_CELLS];
+    __shared__ int s_box[4];     // min iz_l (unwrapped), max iz_u (unwrapped), min ir, max ir (clamped)
+    const int tid = threadIdx.x;
+    const int64_t i = blockIdx.x * (int64_t)GP_TPB + tid;
+    if (tid == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MIN; s_box[2] = INT_MAX; s_box[3] = INT_MIN; }
+    __syncthreads();
+    const bool in_range = i < n;
+    double xj = 0., yj = 0., zj = 0.;
+    if (in_range) { xj = x[i]; yj = y[i]; zj = z[i]; }
+    const B2Cyl c = b2_cyl(xj, yj, zj, invdz, zmin, invdr, rmin);
+    const bool active = in_range && (c.r < rmax_gather);
+    // stencil indices and weights exactly as gather_field_gpu_linear (gathering/cuda_methods.py:109-160)
+    int ir_l = (int)floor(c.r_cell), ir_u = ir_l + 1;
+    const int iz_l0 = (int)floor(c.z_cell);              // unwrapped, in [-1, Nz-1] for in-box particles
+    double Sr_l = ir_u - c.r_cell, Sr_u = c.r_cell - ir_l;
+    const double Sz_l = (iz_l0 + 1) - c.z_cell, Sz_u = c.z_cell - iz_l0;
+    double Sr_g = 0.;
+    if (ir_l < 0) { Sr_g = Sr_l; Sr_l = 0.; ir_l = 0; }
+    if (ir_l > Nr - 1) ir_l = Nr - 1;
+    if (ir_u > Nr - 1) ir_u = Nr - 1;
+    if (active) {
+        atomicMin(&s_box[0], iz_l0); atomicMax(&s_box[1], iz_l0 + 1);
+        atomicMin(&s_box[2], ir_l);  atomicMax(&s_box[3], ir_u);
+    }
+    __syncthreads();
+    const int z0 = s_box[0], r0 = s_box[2];
+    const int nrow = s_box[1] - z0 + 1, ncol = s_box[3] - r0 + 1;
+    const bool any_active = s_box[1] >= z0;
+    const bool use_tile = any_active && nrow > 0 && ncol > 0 && nrow <= 4 && (nrow * ncol <= GP_TILE_CELLS)
+                          && z0 >= -1 && s_box[1] <= Nz;
+    if (use_tile) {
+        const int ncell = nrow * ncol;
+        for (int e = tid; e < ncell * 6 * NM; e += GP_TPB) {
+            const int a = e / ncell, cell = e - a * ncell;
+            const int row = cell / ncol, col = cell - row * ncol;
+            int iz = z0 + row;
+            if (iz < 0) iz += Nz;
+            if (iz > Nz - 1) iz -= Nz;
+            tile[a][cell] = __ldg(G.g[a] + (size_t)iz * Nr + r0 + col);
+        }
+    }
+    __syncthreads();
+    if (!in_range) return;
+
+    double Fc[2][3] = {{0., 0., 0.}, {0., 0., 0.}};
+    if (active) {
+        int iz_l = iz_l0, iz_u = iz_l0 + 1;
+        if (iz_l < 0) iz_l += Nz;
+        if (iz_u < 0) iz_u += Nz;
+        if (iz_l > Nz - 1) iz_l -= Nz;
+        if (iz_u > Nz - 1) iz_u -= Nz;
+        const double S_ll = Sz_l * Sr_l, S_lu = Sz_l * Sr_u, S_ul = Sz_u * Sr_l, S_uu = Sz_u * Sr_u;
+        const double S_lg = Sz_l * Sr_g, S_ug = Sz_u * Sr_g;
+        const bool on_axis = (ir_l == 0 && ir_u == 0);
+        // tile-relative cell offsets (used when use_tile) and global offsets (fallback)
+        const int t_ll = (iz_l0 - z0) * ncol + (ir_l - r0), t_lu = (iz_l0 - z0) * ncol + (ir_u - r0);
+        const int t_ul = t_ll + ncol, t_uu = t_lu + ncol;
+        const int t_l0 = (iz_l0 - z0) * ncol - r0, t_u0 = t_l0 + ncol;    // column 0 (only if on_axis: r0 == 0)
+        const size_t o_ll = (size_t)iz_l * Nr + ir_l, o_lu = (size_t)iz_l * Nr + ir_u;
+        const size_t o_ul = (size_t)iz_u * Nr + ir_l, o_uu = (size_t)iz_u * Nr + ir_u;
+        const size_t o_l0 = (size_t)iz_l * Nr, o_u0 = (size_t)iz_u * Nr;
+        double e_re = 1., e_im = 0.;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            const double flip = (m & 1) ? -1. : 1.;
+            const double factor = (m == 0) ? 1. : 2.;
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int a = 6 * m + 3 * f + k;
+                    double2 v_ll, v_lu, v_ul, v_uu;
+                    if (use_tile) {
+                        v_ll = tile[a][t_ll]; v_lu = tile[a][t_lu]; v_ul = tile[a][t_ul]; v_uu = tile[a][t_uu];
+                    } else {
+                        const double2 *g = G.g[a];
+                        v_ll = __ldg(g + o_ll); v_lu = __ldg(g + o_lu); v_ul = __ldg(g + o_ul); v_uu = __ldg(g + o_uu);
+                    }
+                    double re = 0., im = 0.;
+                    re += S_ll * v_ll.x; im += S_ll * v_ll.y;
+                    re += S_lu * v_lu.x; im += S_lu * v_lu.y;
+                    re += S_ul * v_ul.x; im += S_ul * v_ul.y;
+                    re += S_uu * v_uu.x; im += S_uu * v_uu.y;
+                    if (on_axis) {
+                        const double sgn = (k == 2) ? flip : -flip;
+                        double2 v_l0, v_u0;
+                        if (use_tile) { v_l0 = tile[a][t_l0]; v_u0 = tile[a][t_u0]; }
+                        else { v_l0 = __ldg(G.g[a] + o_l0); v_u0 = __ldg(G.g[a] + o_u0); }
+                        re += sgn * S_lg * v_l0.x; im += sgn * S_lg * v_l0.y;
+                        re += sgn * S_ug * v_u0.x; im += sgn * S_ug * v_u0.y;
+                    }
+                    Fc[f][k] += factor * (re * e_re - im * e_im);
+                }
+            }
+            const double nr = e_re * c.cs + e_im * c.sn, ni = e_im * c.cs - e_re * c.sn;
+            e_re = nr; e_im = ni;
+        }
+    }
+    double F[6];
+    F[0] = c.cs * Fc[0][0] - c.sn * Fc[0][1];
+    F[1] = c.sn * Fc[0][0] + c.cs * Fc[0][1];
+    F[2] = Fc[0][2];
+    F[3] = c.cs * Fc[1][0] - c.sn * Fc[1][1];
+    F[4] = c.sn * Fc[1][0] + c.cs * Fc[1][1];
+    F[5] = Fc[1][2];
+    double a = ux[i], b = uy[i], cz = uz[i], g = inv_gamma[i];
+    b2_vay(a, b, cz, g, F, econst, bconst);
+    ux[i] = a; uy[i] = b; uz[i] = cz; inv_gamma[i] = g;
+    const double xn = xj + chdt * g * 1. * a;
+    const double yn = yj + chdt * g * 1. * b;
+    const double zn = zj + chdt * g * 1. * cz;
+    x[i] = xn; y[i] = yn; z[i] = zn;
+    if (cell_idx) cell_idx[i] = b2_cell_of(b2_cyl(xn, yn, zn, invdz, key_zmin, invdr, rmin), Nz, Nr);
+}
+
 // push_x + optional periodic wrap of z into [wrap_zmin, wrap_zmax) + optional cell key of the new
 // position (push/cuda_methods.py:17-52, particle_buffer_handling.py:637-658, cuda_sorting.py:22-88)
 __global__ void k_push_x_key(int64_t n, double *__restrict__ x, double *__restrict__ y, double *__restrict__ z,
@@ -328,7 +463,6 @@ __global__ void k_add_scalar(int64_t n, double *__restrict__ v, double a) {
 // =====================================================================================
 // C ABI
 // =====================================================================================
-static inline unsigned grid1d(int64_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 
 template <int NM>
 static void launch_gather(bool cubic, unsigned g, cudaStream_t s, int64_t n, const double *x, const double *y,
@@ -344,7 +478,7 @@ static void launch_gather_push(bool cubic, unsigned g, cudaStream_t s, int64_t n
                                int Nz, double invdr, double rmin, int Nr, const B2Grids &G, double ec, double bc,
                                double chdt, int32_t *cell_idx, double key_zmin) {
     if (cubic) k_gather_push<NM, true><<<g, 256, 0, s>>>(n, x, y, z, ux, uy, uz, ig, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt, cell_idx, key_zmin);
-    else k_gather_push<NM, false><<<g, 256, 0, s>>>(n, x, y, z, ux, uy, uz, ig, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt, cell_idx, key_zmin);
+    else k_gather_push_tiled<NM><<<grid1d(n, GP_TPB), GP_TPB, 0, s>>>(n, x, y, z, ux, uy, uz, ig, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt, cell_idx, key_zmin);
 }
 
 extern "C" {

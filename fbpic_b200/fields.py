@@ -18,7 +18,7 @@ from scipy.constants import mu_0, epsilon_0
 
 from . import _lib
 from . import host_tables as ht
-from ._lib import DeviceArray, call, ptr_array, SpectralMode
+from ._lib import DeviceArray, call, ptr_array, SpectralMode, DhtJob
 
 INTERP_FIELDS = ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'Jr', 'Jt', 'Jz', 'rho')
 SPECT_FIELDS = ('Ep', 'Em', 'Ez', 'Bp', 'Bm', 'Bz', 'Jp', 'Jm', 'Jz', 'rho_prev', 'rho_next')
@@ -461,6 +461,74 @@ class Fields(object):
         for m in range(self.Nm):
             for sp, it in self._partial_pairs(m, fieldtype):
                 self.trans[m].fft.transform(it, sp)
+
+    # ---- fused transforms (single-domain fast path of Simulation.step) ----
+    def _fused_tables(self, filter_currents):
+        """Device copies of the Hankel matrices with the neighbouring element-wise passes folded in:
+        forward (deposited sources): diag(invvol) . M . diag(filter_r)  -- divide_by_volume
+        (interpolation_grid.py:271) and the radial half of filter_spect (spectral_grid.py:423) cost
+        nothing; the z half of the filter is the row scale of the GEMM epilogue;
+        inverse (E, B): invM / Nz -- the normalisation pass of the inverse FFT (fourier.py:157)."""
+        key = bool(filter_currents)
+        if getattr(self, '_fused_key', None) == key:
+            return self._fused
+        out = []
+        for m in range(self.Nm):
+            tr, g, sp = self.trans[m], self.interp[m], self.spect[m]
+            fr = sp.filter_array_r if filter_currents else np.ones(self.Nr)
+            fwd = lambda M: DeviceArray.from_numpy(g.invvol[:, None] * M * fr[None, :])
+            inv = lambda M: DeviceArray.from_numpy(M / self.Nz)
+            tr._buffers()
+            bufs = [DeviceArray((self.Nz, self.Nr), np.complex128) for _ in range(6)]
+            out.append(dict(F0=fwd(tr.dht0.M), Fp=fwd(tr.dhtp.M), Fm=fwd(tr.dhtm.M),
+                            I0=inv(tr.dht0.invM), Ip=inv(tr.dhtp.invM), Im=inv(tr.dhtm.invM),
+                            fz=(sp.d_filter_array_z if filter_currents else None), buf=bufs))
+        self._fused, self._fused_key = out, key
+        return out
+
+    def fused_deposit2spect(self, fieldtype, filter_currents=True):
+        """divide_by_volume + interp2spect + filter_spect of a freshly deposited source
+        (main.py:640,657,666-668) as 1 (rho) or 3 (J) FFTs per mode + ONE batched Hankel launch."""
+        T = self._fused_tables(filter_currents)
+        ctx = _lib.context()
+        jobs = []
+        for m in range(self.Nm):
+            g, s, t = self.interp[m], self.spect[m], T[m]
+            fz = t['fz'].ptr if t['fz'] is not None else None
+            if fieldtype == 'J':
+                for a, b in ((g.Jz, t['buf'][0]), (g.Jr, t['buf'][1]), (g.Jt, t['buf'][2])):
+                    call.b2_fft_z(ctx.handle, a.ptr, b.ptr, self.Nz, self.Nr, 0, None)
+                jobs.append(DhtJob(t['buf'][0].ptr, None, s.Jz.ptr, None, t['F0'].ptr, None, fz, _lib.DHT_SCALAR))
+                jobs.append(DhtJob(t['buf'][1].ptr, t['buf'][2].ptr, s.Jp.ptr, s.Jm.ptr, t['Fp'].ptr, t['Fm'].ptr,
+                                   fz, _lib.DHT_RT_TO_PM))
+            elif fieldtype in ('rho_prev', 'rho_next'):
+                call.b2_fft_z(ctx.handle, g.rho.ptr, t['buf'][0].ptr, self.Nz, self.Nr, 0, None)
+                jobs.append(DhtJob(t['buf'][0].ptr, None, getattr(s, fieldtype).ptr, None, t['F0'].ptr, None,
+                                   fz, _lib.DHT_SCALAR))
+            else:
+                raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
+        arr = (DhtJob * len(jobs))(*jobs)
+        call.b2_dht_batch(ctx.handle, len(jobs), arr, self.Nz, self.Nr, None)
+
+    def fused_spect2interp_EB(self):
+        """spect2interp('E') + spect2interp('B') (main.py:768-769): batched inverse Hankel
+        transforms of all modes (1/Nz folded in), then the 6*Nm unscaled inverse FFTs."""
+        T = self._fused_tables(getattr(self, '_fused_key', True))
+        ctx = _lib.context()
+        jobs, ffts = [], []
+        for m in range(self.Nm):
+            g, s, t = self.interp[m], self.spect[m], T[m]
+            for f, o in (('E', 0), ('B', 3)):
+                bz, br, bt = t['buf'][o], t['buf'][o + 1], t['buf'][o + 2]
+                jobs.append(DhtJob(getattr(s, f + 'z').ptr, None, bz.ptr, None, t['I0'].ptr, None, None,
+                                   _lib.DHT_SCALAR))
+                jobs.append(DhtJob(getattr(s, f + 'p').ptr, getattr(s, f + 'm').ptr, br.ptr, bt.ptr,
+                                   t['Ip'].ptr, t['Im'].ptr, None, _lib.DHT_PM_TO_RT))
+                ffts += [(bz, getattr(g, f + 'z')), (br, getattr(g, f + 'r')), (bt, getattr(g, f + 't'))]
+        arr = (DhtJob * len(jobs))(*jobs)
+        call.b2_dht_batch(ctx.handle, len(jobs), arr, self.Nz, self.Nr, None)
+        for a, b in ffts:
+            call.b2_fft_z(ctx.handle, a.ptr, b.ptr, self.Nz, self.Nr, 2, None)
 
     # ---- interpolation-grid ops ----
     def erase(self, fieldtype):

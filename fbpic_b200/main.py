@@ -209,6 +209,11 @@ class Simulation(object):
         for species in species_list:
             species.deposit(fld, grid_type)
         fld.sum_reduce_deposition_array(grid_type)
+        if self.fused and self.comm.size == 1 and update_spectral:
+            # divide_by_volume, the transforms and the filter as FFTs + one batched Hankel launch
+            fld.fused_deposit2spect(fieldtype, self.filter_currents)
+            fld.exchanged_source[fieldtype] = exchange
+            return
         fld.divide_by_volume(grid_type)
         if exchange and self.comm.size > 1:
             self.comm.exchange_fields(fld.interp, grid_type, 'add')
@@ -231,8 +236,11 @@ class Simulation(object):
             self.comm.damp_EB_open_boundary(fld.interp)
             fld.partial_interp2spect('E')
             fld.partial_interp2spect('B')
-        fld.spect2interp('E')
-        fld.spect2interp('B')
+        if self.fused:
+            fld.fused_spect2interp_EB()
+        else:
+            fld.spect2interp('E')
+            fld.spect2interp('B')
 
     def shift_galilean_boundaries(self, dt):
         """fbpic/main.py:772-789"""

@@ -152,6 +152,7 @@ int b2_scale_rows_by_r(b2_ctx *ctx, int n_arrays, void *const *d_arrays, const d
  *      [Nz,Nr] array, inverse scaled by 1/Nz) and DHT.transform / inverse_transform
  *      (hankel.py:182-243: out = in @ M as a real [2Nz,Nr]x[Nr,Nr] product), plus the
  *      r,t <-> p,m combinations (spectral_transform/cuda_methods.py:120-158). ------ */
+/* inverse: 0 forward, 1 inverse scaled by 1/Nz (NumPy ifft convention), 2 inverse unscaled */
 int b2_fft_z(b2_ctx *ctx, const void *d_in, void *d_out, int Nz, int Nr, int inverse, void *stream);
 /* batched: n_arrays independent [Nz,Nr] arrays */
 int b2_fft_z_multi(b2_ctx *ctx, int n_arrays, const void *const *d_in, void *const *d_out,
@@ -169,6 +170,16 @@ int b2_dht_rt_to_pm(b2_ctx *ctx, const void *d_r, const void *d_t, void *d_out_p
 int b2_dht_pm_to_rt(b2_ctx *ctx, const void *d_p, const void *d_m, void *d_out_r, void *d_out_t,
                     const double *d_iMp, const double *d_iMm, const double *d_rowscale,
                     int Nz, int Nr, void *stream);
+/* batched form: the whole list (all modes / components of a field) in one launch per flavour */
+enum { B2_DHT_SCALAR = 0, B2_DHT_RT_TO_PM = 1, B2_DHT_PM_TO_RT = 2 };
+typedef struct {
+    const void *in1, *in2;      /* SCALAR: in1 ; RT_TO_PM: r, t ; PM_TO_RT: p, m          */
+    void *out1, *out2;          /* SCALAR: out1 ; RT_TO_PM: p, m ; PM_TO_RT: r, t         */
+    const double *M1, *M2;      /* SCALAR: M1 ; vector kinds: the +/- order matrices      */
+    const double *rowscale;     /* NULL or [Nz]                                           */
+    int kind;
+} b2_dht_job;
+int b2_dht_batch(b2_ctx *ctx, int njobs, const b2_dht_job *jobs, int Nz, int Nr, void *stream);
 int b2_rt_to_pm(b2_ctx *ctx, void *d_r_p, void *d_t_m, int Nz, int Nr, void *stream);   /* in place */
 int b2_pm_to_rt(b2_ctx *ctx, void *d_p_r, void *d_m_t, int Nz, int Nr, void *stream);   /* in place */
 
