@@ -18,6 +18,10 @@ struct b2_ctx {
     size_t scratch_bytes[4];
     // cuFFT plans keyed by (Nz, Nr)
     std::map<uint64_t, cufftHandle> fft_plans;
+    // result of the last b2_sort_cells on this context (lives in scratch slot 0)
+    const int32_t *last_idx32;
+    const int32_t *last_keys_sorted;
+    int64_t last_sort_n;
     void *nccl_comm;
     int nccl_rank, nccl_size;
     int sm_count;

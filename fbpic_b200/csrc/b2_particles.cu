@@ -64,10 +64,11 @@ struct B2Perm {
     double *dst[B2_MAX_ARRAYS];
 };
 template <int NA>
-__global__ void k_permute(int64_t n, const int64_t *__restrict__ sorted_idx, B2Perm a, int n_arrays) {
+__global__ void k_permute(int64_t n, const int64_t *__restrict__ sorted_idx, const int32_t *__restrict__ idx32,
+                          B2Perm a, int n_arrays) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int64_t j = sorted_idx[i];
+    int64_t j = sorted_idx ? sorted_idx[i] : (int64_t)idx32[i];
     if (NA > 0) {
 #pragma unroll
         for (int k = 0; k < NA; ++k) a.dst[k][i] = __ldg(a.src[k] + j);
@@ -520,8 +521,11 @@ int b2_sort_cells(b2_ctx *ctx, int64_t n, int32_t *cell_idx, int64_t *sorted_idx
     B2_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const int32_t *)cell_idx, keys_sorted,
                                             (const int32_t *)idx_in, idx_sorted, (int)n, 0, end_bit, s));
     g_b2_launches.fetch_add(4);
-    k_finish_sort<<<grid1d(n, 256), 256, 0, s>>>(n, keys_sorted, idx_sorted, cell_idx, sorted_idx);
-    B2_LAUNCHED();
+    ctx->last_idx32 = idx_sorted; ctx->last_keys_sorted = keys_sorted; ctx->last_sort_n = n;
+    if (sorted_idx) {     // materialise the API-visible int64 permutation and the sorted keys
+        k_finish_sort<<<grid1d(n, 256), 256, 0, s>>>(n, keys_sorted, idx_sorted, cell_idx, sorted_idx);
+        B2_LAUNCHED();
+    }
     k_prefix_sum<<<grid1d(ncells, 256), 256, 0, s>>>(n, keys_sorted, prefix_sum, ncells);
     B2_LAUNCHED();
     return 0;
@@ -535,9 +539,15 @@ int b2_permute(b2_ctx *ctx, int64_t n, const int64_t *sorted_idx, int n_arrays, 
     B2Perm a;
     for (int k = 0; k < n_arrays; ++k) { a.src[k] = src[k]; a.dst[k] = dst[k]; }
     cudaStream_t s = b2_stream_of(ctx, stream);
-    if (n_arrays == 8) k_permute<8><<<grid1d(n, 256), 256, 0, s>>>(n, sorted_idx, a, n_arrays);
-    else if (n_arrays == 14) k_permute<14><<<grid1d(n, 256), 256, 0, s>>>(n, sorted_idx, a, n_arrays);
-    else k_permute<0><<<grid1d(n, 256), 256, 0, s>>>(n, sorted_idx, a, n_arrays);
+    const int32_t *i32 = nullptr;
+    if (!sorted_idx) {
+        if (!ctx->last_idx32 || ctx->last_sort_n != n)
+            return b2_fail(-4, "b2_permute: no sorted_idx given and no matching sort in this context", __FILE__, __LINE__);
+        i32 = ctx->last_idx32;
+    }
+    if (n_arrays == 8) k_permute<8><<<grid1d(n, 256), 256, 0, s>>>(n, sorted_idx, i32, a, n_arrays);
+    else if (n_arrays == 14) k_permute<14><<<grid1d(n, 256), 256, 0, s>>>(n, sorted_idx, i32, a, n_arrays);
+    else k_permute<0><<<grid1d(n, 256), 256, 0, s>>>(n, sorted_idx, i32, a, n_arrays);
     B2_LAUNCHED();
     return 0;
 }

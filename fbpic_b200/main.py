@@ -156,8 +156,11 @@ class Simulation(object):
                     #  the exchange_particles at the start of the next step, main.py:435-442)
                     wrap = (z0, z0 + (fld.interp[0].zmax - fld.interp[0].zmin)) \
                         if (wrap_in_push and i_step < N - 1) else None
+                    # cubic shapes re-sort for the rho deposition and use the keys; linear shapes
+                    # deposit rho with the displaced kernel (no sort, no keys)
+                    kz0 = z0 if self.particle_shape == 'cubic' else None
                     for species in ptcl:
-                        species.push_x_and_key(0.5 * dt, fld, wrap=wrap, key_zmin=z0)
+                        species.push_x_and_key(0.5 * dt, fld, wrap=wrap, key_zmin=kz0)
                 else:
                     for species in ptcl:
                         species.push_x(0.5 * dt)
@@ -207,7 +210,10 @@ class Simulation(object):
             raise ValueError('Unknown fieldtype: %s' % fieldtype)
         fld.erase(grid_type)
         for species in species_list:
-            species.deposit(fld, grid_type)
+            if self.fused:
+                species.deposit_fused(fld, grid_type)
+            else:
+                species.deposit(fld, grid_type)
         fld.sum_reduce_deposition_array(grid_type)
         if self.fused and self.comm.size == 1 and update_spectral:
             # divide_by_volume, the transforms and the filter as FFTs + one batched Hankel launch

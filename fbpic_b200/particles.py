@@ -121,6 +121,8 @@ class Particles(object):
         self.prefix_sum = DeviceArray(Nz * (Nr + 1), np.int32)
         # double buffers for the one-pass SoA permutation (8 state + 6 field arrays)
         self.sorting_buffers = [DeviceArray(self.Ntot, np.float64) for _ in range(14)]
+        self._order_matches_prefix = False
+        self._keys_fresh = False
 
     def send_particles_to_gpu(self):
         """particles.py:252-291"""
@@ -241,6 +243,7 @@ class Particles(object):
                            self.prefix_sum.ptr, g0.Nz, g0.Nr, None)
         self.prefix_sum_shift = 0
         self.rearrange_particle_arrays()
+        self._order_matches_prefix = True
 
     def rearrange_particle_arrays(self):
         """One-pass permutation of all SoA attributes, then swap with the spare
@@ -257,6 +260,56 @@ class Particles(object):
             self.sorting_buffers[i] = src[i]
 
     # ------------------------------------------------------------------ deposition
+    def deposit_fused(self, fld, fieldtype):
+        """Fast path used by Simulation.step(fused=True); same sums as deposit().
+        * not sorted: cell sort (keys possibly already emitted by the push kernel), then ONE
+          kernel that applies the permutation to the SoA and deposits (`b2_deposit_permute`);
+        * rho, linear shapes, arrays still in the order of the last sort (particles moved by about
+          a cell since): `b2_deposit_rho_displaced`, no re-sort -- the second sort of the PIC cycle
+          (particles.py:866-871 sorts before every deposit) disappears.
+        The API-visible `cell_idx` / `sorted_idx` are refreshed only by sort_particles()."""
+        if self.q == 0:
+            return
+        assert fieldtype in ('rho', 'J')
+        self._need_gpu()
+        ctx = _lib.context()
+        grid = fld.interp
+        g0, Nm = grid[0], len(grid)
+        cubic = (self.particle_shape == 'cubic')
+        attr = 'd_ruyten_cubic_coef' if cubic else 'd_ruyten_linear_coef'
+        r0, rh = getattr(grid[0], attr), getattr(grid[1 if Nm > 1 else 0], attr)
+        if fieldtype == 'rho':
+            grids = ptr_array([g.rho for g in grid])
+        else:
+            grids = ptr_array([getattr(g, k) for g in grid for k in ('Jr', 'Jt', 'Jz')])
+        if self.sorted:
+            return self.deposit(fld, fieldtype)
+        if fieldtype == 'rho' and not cubic and getattr(self, '_order_matches_prefix', False):
+            call.b2_deposit_rho_displaced(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr, self.w.ptr,
+                                          self.q, g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, Nm, grids,
+                                          self.prefix_sum.ptr, r0.ptr, rh.ptr, None)
+            return
+        if self.cell_idx is None or self.cell_idx.size != self.Ntot:
+            self._alloc_sort_arrays()
+        if not getattr(self, '_keys_fresh', False):
+            call.b2_cell_index(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr,
+                               g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, self.cell_idx.ptr, None)
+        self._keys_fresh = False
+        call.b2_sort_cells(ctx.handle, self.Ntot, self.cell_idx.ptr, None, self.prefix_sum.ptr,
+                           g0.Nz, g0.Nr, None)
+        self.prefix_sum_shift = 0
+        names = ('x', 'y', 'z', 'w', 'ux', 'uy', 'uz', 'inv_gamma')
+        src = [getattr(self, k) for k in names]
+        dst = self.sorting_buffers[:8]
+        call.b2_deposit_permute(ctx.handle, int(fieldtype == 'J'), self.Ntot, ptr_array(src), ptr_array(dst),
+                                self.q, g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, Nm, grids,
+                                self.prefix_sum.ptr, r0.ptr, rh.ptr, int(cubic), None)
+        for i, k in enumerate(names):
+            setattr(self, k, dst[i])
+            self.sorting_buffers[i] = src[i]
+        self.sorted = True
+        self._order_matches_prefix = True
+
     def deposit(self, fld, fieldtype):
         """rho or J on the interpolation grid (particles.py:839-985): sorts first if
         needed, then one launch for all modes."""

@@ -79,6 +79,9 @@ int b2_graph_destroy(void *graph_exec);
 int b2_cell_index(b2_ctx *ctx, int64_t n, const double *d_x, const double *d_y, const double *d_z,
                   double invdz, double zmin, int Nz, double invdr, double rmin, int Nr,
                   int32_t *d_cell_idx, void *stream);
+/* d_sorted_idx may be NULL: the permutation then stays inside the context (32-bit) for the
+ * immediately following b2_permute(.., NULL, ..) / b2_deposit_permute, and d_cell_idx keeps the
+ * unsorted keys */
 int b2_sort_cells(b2_ctx *ctx, int64_t n, int32_t *d_cell_idx /* in: keys, out: sorted keys */,
                   int64_t *d_sorted_idx /* out */, int32_t *d_prefix_sum /* out, Nz*(Nr+1) */,
                   int Nz, int Nr, void *stream);
@@ -141,6 +144,22 @@ int b2_deposit_J(b2_ctx *ctx, int64_t n, const double *d_x, const double *d_y, c
                  double invdr, double rmin, int Nr, int Nm, void *const *d_grids,
                  const int32_t *d_prefix_sum, const double *d_ruyten0, const double *d_ruyten_hi,
                  int cubic, void *stream);
+
+/* deposition fused with the SoA permutation of the sort that just ran on this context
+ * (b2_sort_cells(.., d_sorted_idx=NULL, ..)): reads the 8 UNSORTED attribute arrays through the
+ * permutation, writes the 8 sorted arrays and deposits (what: 0 rho, 1 J) in the same pass.
+ * d_src8/d_dst8: host arrays of 8 device pointers ordered x,y,z,w,ux,uy,uz,inv_gamma. */
+int b2_deposit_permute(b2_ctx *ctx, int what, int64_t n, const double *const *d_src8, double *const *d_dst8,
+                       double q, double invdz, double zmin, int Nz, double invdr, double rmin, int Nr, int Nm,
+                       void *const *d_grids, const int32_t *d_prefix_sum, const double *d_ruyten0,
+                       const double *d_ruyten_hi, int cubic, void *stream);
+/* rho deposition (linear shapes) for particles that were cell-sorted half a step ago and have
+ * moved by about one cell at most since (d_prefix_sum is the OLD sort's): no re-sort needed */
+int b2_deposit_rho_displaced(b2_ctx *ctx, int64_t n, const double *d_x, const double *d_y, const double *d_z,
+                             const double *d_w, double q, double invdz, double zmin, int Nz,
+                             double invdr, double rmin, int Nr, int Nm, void *const *d_grids,
+                             const int32_t *d_prefix_sum, const double *d_ruyten0, const double *d_ruyten_hi,
+                             void *stream);
 
 /* ---- interpolation-grid element-wise ops: cuda_erase_*, cuda_divide_*_by_volume
  *      (fbpic/fields/cuda_methods.py:18-117) ---------------------------------- */

@@ -177,3 +177,66 @@ def test_transforms_vs_numpy(Nz, Nr):
         assert_close(d_r.get(), np.fft.ifft(d_s.get() @ tr.dht0.invM, axis=0), 1e-13, 'inv scal m%d' % m)
         if m == 0:      # the order-0 matrices of mode 0 are exact inverses of each other
             assert_close(d_r.get(), f, 1e-11, 'round trip m%d' % m)
+
+
+@pytest.mark.parametrize('shape,Nm', [('linear', 2), ('linear', 3), ('cubic', 2)])
+def test_fused_deposition_paths_vs_oracle(shape, Nm):
+    """deposit_fused(): sort + (permutation fused into the deposition kernel) for J, and the
+    displaced rho deposition on particles that moved since the sort (incl. a few that moved by
+    several cells and take the per-particle fallback), all against the oracle."""
+    from fbpic_b200 import Simulation
+    from oracle import oracle as orc
+    np.random.seed(4)
+    Nz, Nr, zmax, rmax = 80, 36, 24.e-6, 18.e-6
+    dt = zmax / Nz / c
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, p_zmin=0, p_zmax=zmax, p_rmin=0, p_rmax=rmax,
+                     p_nz=2, p_nr=2, p_nt=4 * Nm, n_e=1.e24, particle_shape=shape)
+    sp = sim.ptcl[0]
+    n = sp.Ntot
+    rng = np.random.default_rng(9)
+    sp.ux, sp.uy, sp.uz = rng.normal(size=n) * 0.3, rng.normal(size=n) * 0.3, rng.normal(size=n)
+    sp.inv_gamma = 1. / np.sqrt(1 + sp.ux**2 + sp.uy**2 + sp.uz**2)
+    sp.x += rng.normal(size=n) * 0.4e-6
+    sp.y += rng.normal(size=n) * 0.4e-6
+    sp.z = np.mod(sp.z + rng.normal(size=n) * 0.5e-6, zmax)
+    g0 = sim.fld.interp[0]
+    cubic = shape == 'cubic'
+    coef = 'ruyten_cubic_coef' if cubic else 'ruyten_linear_coef'
+    r0, rh = getattr(sim.fld.interp[0], coef), getattr(sim.fld.interp[1], coef)
+    P = {k: getattr(sp, k).copy() for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w')}
+
+    def oracle_dep(what, Q):
+        return orc.deposit(what, Q['x'], Q['y'], Q['z'], Q['w'], sp.q, Q['ux'], Q['uy'], Q['uz'], Q['inv_gamma'],
+                           g0.invdz, g0.zmin, Nz, g0.invdr, 0., Nr, Nm, cubic, r0, rh)
+
+    sim.send_data_to_gpu()
+    # J: sort + fused permute/deposit
+    sim.fld.erase('J')
+    sp.deposit_fused(sim.fld, 'J')
+    raw = oracle_dep('J', P)
+    for m in range(Nm):
+        for k, nme in enumerate(('Jr', 'Jt', 'Jz')):
+            assert_close(getattr(sim.fld.interp[m], nme).get(), raw[k, m], 1e-13, 'fused %s m%d' % (nme, m))
+    cell = orc.cell_index(P['x'], P['y'], P['z'], g0.invdz, g0.zmin, Nz, g0.invdr, 0., Nr)
+    idx, prefix = orc.sort_contract(cell, Nz, Nr)
+    assert np.array_equal(sp.prefix_sum.get(), prefix)
+    for k in P:
+        assert np.array_equal(getattr(sp, k).get(), P[k][idx]), k     # SoA permuted by the same kernel
+    # move the particles (most by < 1 cell, a few by several cells), keep the array order
+    Q = {k: P[k][idx].copy() for k in P}
+    dz, dr = zmax / Nz, rmax / Nr
+    Q['x'] += rng.uniform(-0.45, 0.45, n) * dr
+    Q['y'] += rng.uniform(-0.45, 0.45, n) * dr
+    Q['z'] += rng.uniform(-0.9, 0.9, n) * dz
+    far = rng.choice(n, 200, replace=False)
+    Q['z'][far] += rng.uniform(-6, 6, 200) * dz
+    Q['x'][far] += rng.uniform(-4, 4, 200) * dr
+    Q['z'] = np.mod(Q['z'], zmax)
+    for k in ('x', 'y', 'z'):
+        getattr(sp, k).set(Q[k])
+    sp.sorted = False
+    sim.fld.erase('rho')
+    sp.deposit_fused(sim.fld, 'rho')
+    raw = oracle_dep('rho', Q)
+    for m in range(Nm):
+        assert_close(sim.fld.interp[m].rho.get(), raw[0, m], 1e-13, 'displaced/fused rho m%d' % m)
