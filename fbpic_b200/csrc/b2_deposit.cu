@@ -19,9 +19,9 @@
 //   PERMUTE   : the chunk is gathered through the sort permutation (idx32) from the UNSORTED
 //               attribute arrays and also written back, coalesced, to the sorted arrays: the
 //               permutation pass and the deposition share one read of the particle data.
-//   DISPLACED : (rho, linear) the particles were sorted half a step ago and have moved by at most one
-//               cell since: each thread keeps a 4x4-point footprint around its (old) cell and adds
-//               every particle at its own offset; farther particles fall back to per-particle REDs.
+//   DISPLACED : (rho, linear) the particles were sorted half a step ago and have moved a little since:
+//               a particle that is still in the cell it was sorted into goes into the cell's register
+//               sums, one that crossed a cell boundary issues its own 4 x (2Nm-1) REDs.
 //               Saves the second sort of the PIC cycle (particles.py:866-871 sorts before every
 //               deposit; main.py:511,528).
 //
@@ -86,7 +86,7 @@ k_deposit(B2DepPtrs P, const int32_t *__restrict__ idx32, double q,
     constexpr int NATTR = PERMUTE ? 8 : NNEED;          // attributes staged (PERMUTE moves all 8)
     constexpr int NVM = 2 * NM - 1;                     // real values per component
     constexpr int NV = NC * NVM;
-    constexpr int FP = DISPLACED ? 4 : NPT;             // register footprint (points per dimension)
+    constexpr int FP = NPT;                             // register footprint (points per dimension)
     static_assert(!DISPLACED || (!IS_J && NPT == 2 && NC == 1), "DISPLACED: rho, linear only");
     __shared__ double sm[2][NATTR][DEP_CHUNK];
 
@@ -208,21 +208,19 @@ k_deposit(B2DepPtrs P, const int32_t *__restrict__ idx32, double q,
                     if (dz > Nz / 2) dz -= Nz; else if (dz < -(Nz / 2)) dz += Nz;
                     double sz[2], sr0[2], sr1[2];
                     lin_shapes(c, __ldg(ruyten0 + irp), __ldg(ruyten_hi + irp), sz, sr0, sr1);
-                    const int code = (dz + 1) * 3 + (dr + 1);
-                    if (dz >= -1 && dz <= 1 && dr >= -1 && dr <= 1) {
-                        switch (code) {
-                            case 0: add_footprint<NM, NVM, 0, 0>(acc, sz, sr0, sr1, V); break;
-                            case 1: add_footprint<NM, NVM, 0, 1>(acc, sz, sr0, sr1, V); break;
-                            case 2: add_footprint<NM, NVM, 0, 2>(acc, sz, sr0, sr1, V); break;
-                            case 3: add_footprint<NM, NVM, 1, 0>(acc, sz, sr0, sr1, V); break;
-                            case 4: add_footprint<NM, NVM, 1, 1>(acc, sz, sr0, sr1, V); break;
-                            case 5: add_footprint<NM, NVM, 1, 2>(acc, sz, sr0, sr1, V); break;
-                            case 6: add_footprint<NM, NVM, 2, 0>(acc, sz, sr0, sr1, V); break;
-                            case 7: add_footprint<NM, NVM, 2, 1>(acc, sz, sr0, sr1, V); break;
-                            default: add_footprint<NM, NVM, 2, 2>(acc, sz, sr0, sr1, V); break;
-                        }
+                    if (dz == 0 && dr == 0) {
+                        // still in the cell it was sorted into: register sums, as in the sorted kernel
+#pragma unroll
+                        for (int a = 0; a < 2; ++a)
+#pragma unroll
+                            for (int b = 0; b < 2; ++b) {
+                                const double w0 = sz[a] * sr0[b], w1 = sz[a] * sr1[b];
+                                acc[a][b][0] += w0 * V[0];
+#pragma unroll
+                                for (int v = 1; v < NVM; ++v) acc[a][b][v] += w1 * V[v];
+                            }
                     } else {
-                        // moved by more than one cell since the sort: per-particle REDs (rare)
+                        // left its cell since the sort: per-particle REDs (fp64 REDG is cheap on B200)
 #pragma unroll
                         for (int b = 0; b < 2; ++b) {
                             int ir = irp - 1 + b;
@@ -290,7 +288,7 @@ k_deposit(B2DepPtrs P, const int32_t *__restrict__ idx32, double q,
     if (!valid || e == s) return;
 
     // ---- flush: one RED per (stencil point, component, real value) of this cell ----
-    constexpr int OFF = DISPLACED ? 2 : NPT / 2;        // footprint origin relative to (iz_u, ir_u)
+    constexpr int OFF = NPT / 2;                        // footprint origin relative to (iz_u, ir_u)
 #pragma unroll
     for (int b = 0; b < FP; ++b) {
         int ir = ir_u - OFF + b;
