@@ -1,0 +1,348 @@
+// b2_deposit_mma.cu -- charge / current deposition as a tensor-core segmented reduction.
+//
+// Replaces deposit_{rho,J}_gpu_{linear,cubic}[_one_mode] (fbpic/particles/deposition/cuda_methods.py:
+// 28,202,466,751; cuda_methods_one_mode.py: one thread per cell, TPB 8, serial loop over the cell's
+// particles, one pass per mode) and, in the PERMUTE flavour, write_sorting_buffer /
+// rearrange_particle_arrays (cuda_sorting.py:193-213, particles.py:510-555).
+//
+// Every particle contributes  grid[point] += S[point] * V[value]  with NPT^2 stencil points and
+// NV = ncomp*(2Nm-1) real values; all particles of a run of equal cell key hit the same points, so the
+// sum over a run is a small matrix product  C[point,value] = sum_p S[p,point] * V[p,value]  -- a GEMM
+// with K = particles of the run.  The kernel therefore works in two fully parallel phases per CTA
+// (256 consecutive particles of the array):
+//   A  thread-per-particle: coalesced load (or gather through the sort permutation + coalesced
+//      write-back of the sorted SoA when PERMUTE), cylindrical coordinates, shape factors with the
+//      Ruyten correction, per-mode phases -> S (two weight classes: m=0 / m>=1 use different Ruyten
+//      coefficients) and V "packets" in shared memory, plus the particle's cell key;
+//   B  each warp takes 32 particles, walks the runs of equal key and reduces every run on the fp64
+//      tensor cores (mma.sync m8n8k4: rows = points x class, columns = values, K = 4 particles per
+//      step, out-of-run particles masked), then flushes the useful entries of the 8x8 accumulator
+//      tiles with one red.global.add.f64 each.
+// No thread owns a cell: load balance does not depend on the density profile, the kernel is correct
+// for ANY particle order (runs just get shorter when the array is less sorted), so the same kernel
+// serves sorted particles, particles that moved since their last sort (the second deposition of the
+// PIC cycle needs no second sort) and unsorted ones.
+//
+// Boundary folds follow fbpic/fields/numba_methods.py:410-461 / cuda_methods.py:167-177,670-691:
+// z periodic; points below the axis fold to -(1+ir) with the flip sign (-1)^m (rho, Jz) or -(-1)^m
+// (Jr, Jt) (particle_shapes.py:33-36,76-79); points beyond Nr-1 clamp to Nr-1.
+#include "b2_common.cuh"
+
+#define DM_TPB 256          // particles per CTA = threads per CTA
+
+struct B2DmGrids {
+    double2 *g[3 * B2_MAX_MODES];   // rho: [m] ; J: [m][Jr,Jt,Jz]
+};
+struct B2DmPtrs {
+    const double *src[8];           // x,y,z,w,ux,uy,uz,inv_gamma
+    double *dst[8];                 // PERMUTE: sorted destination arrays
+};
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int NM, bool IS_J, int NPT, bool PERMUTE>
+__global__ void __launch_bounds__(DM_TPB)
+k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, double q,
+              double invdz, double zmin, int Nz, double invdr, double rmin, int Nr, B2DmGrids G,
+              const double *__restrict__ ruyten0, const double *__restrict__ ruyten_hi) {
+    constexpr int NCOMP = IS_J ? 3 : 1;
+    constexpr int NP = NPT * NPT;                      // stencil points
+    constexpr int NROW = 2 * NP;                       // (point, weight class)
+    constexpr int MT = NROW / 8;                       // 8-row MMA tiles: 1 (linear), 4 (cubic)
+    constexpr int NVT = NCOMP * (2 * NM - 1);          // real values per particle
+    constexpr int NT = (NVT + 7) / 8;                  // 8-column MMA tiles
+    extern __shared__ __align__(16) unsigned char dm_smem[];
+    double *sW = (double *)dm_smem;                    // [MT][DM_TPB][8]
+    double *sV = sW + MT * DM_TPB * 8;                 // [NT][DM_TPB][8]
+    int *sK = (int *)(sV + NT * DM_TPB * 8);           // [DM_TPB] cell key (-1: no particle)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q0 = blockIdx.x * (int64_t)DM_TPB;
+    const int64_t i = q0 + tid;
+
+    // ------------------------------------------------------------------ phase A
+    {
+        int key = -1;
+        double S[NROW];
+        double V[NT * 8];
+#pragma unroll
+        for (int r = 0; r < NROW; ++r) S[r] = 0.;
+#pragma unroll
+        for (int v = 0; v < NT * 8; ++v) V[v] = 0.;
+        if (i < n) {
+            const size_t j = PERMUTE ? (size_t)__ldg(idx32 + i) : (size_t)i;
+            double at[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) at[k] = (PERMUTE || IS_J || k < 4) ? __ldg(P.src[k] + j) : 0.;
+            if (PERMUTE) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) P.dst[k][i] = at[k];
+            }
+            const B2Cyl c = b2_cyl(at[0], at[1], at[2], invdz, zmin, invdr, rmin);
+            int iru = (int)ceil(c.r_cell), izu = (int)ceil(c.z_cell);
+            if (iru > Nr) iru = Nr;
+            if (izu < 0) izu += Nz; else if (izu > Nz - 1) izu -= Nz;
+            key = iru + izu * (Nr + 1);
+            const double beta0 = __ldg(ruyten0 + iru), beta_hi = __ldg(ruyten_hi + iru);
+            // shape factors (particle_shapes.py:17-80); the flip sign is applied at flush time
+            double sz[NPT], sr0[NPT], sr1[NPT];
+            if (NPT == 2) {
+                sz[0] = ceil(c.z_cell) - c.z_cell;
+                sz[1] = 1. - sz[0];
+                const double u = c.r_cell - (ceil(c.r_cell) - 1.);
+                const double base = 1. - u, t = (1. - u) * u;
+                sr0[0] = base + beta0 * t;   sr0[1] = 1. - sr0[0];
+                sr1[0] = base + beta_hi * t; sr1[1] = 1. - sr1[0];
+            } else {
+                const double uz_ = c.z_cell - (ceil(c.z_cell) - 2.) - 1.;
+                const double vz = 1. - uz_;
+                sz[0] = (1. / 6.) * (vz * vz * vz);
+                sz[1] = (1. / 6.) * (3. * (uz_ * uz_ * uz_) - 6. * (uz_ * uz_) + 4.);
+                sz[NPT - 2] = (1. / 6.) * (3. * (vz * vz * vz) - 6. * (vz * vz) + 4.);
+                sz[NPT - 1] = (1. / 6.) * (uz_ * uz_ * uz_);
+                const double u = c.r_cell - (ceil(c.r_cell) - 2.) - 1.;
+                const double v = 1. - u, t = (1. - u) * u;
+                const double s0 = (1. / 6.) * (v * v * v);
+                const double s1 = (1. / 6.) * (3. * (u * u * u) - 6. * (u * u) + 4.);
+                const double s2 = (1. / 6.) * (3. * (v * v * v) - 6. * (v * v) + 4.);
+                const double s3 = (1. / 6.) * (u * u * u);
+                sr0[0] = s0; sr0[1] = s1 + beta0 * t;   sr0[NPT - 2] = s2 - beta0 * t;   sr0[NPT - 1] = s3;
+                sr1[0] = s0; sr1[1] = s1 + beta_hi * t; sr1[NPT - 2] = s2 - beta_hi * t; sr1[NPT - 1] = s3;
+            }
+#pragma unroll
+            for (int a = 0; a < NPT; ++a)
+#pragma unroll
+                for (int b = 0; b < NPT; ++b) {
+                    S[a * NPT + b] = sz[a] * sr0[b];
+                    S[NP + a * NPT + b] = sz[a] * sr1[b];
+                }
+            // values: [m=0 of every component | (Re, Im) of m=1..NM-1 of every component]
+            const double wj = q * at[3];
+            double v0[NCOMP];
+            if (!IS_J) {
+                v0[0] = wj;
+            } else {
+                const double f = wj * B2_C_LIGHT * at[7];
+                v0[0] = f * (c.cs * at[4] + c.sn * at[5]);
+                v0[NCOMP > 1 ? 1 : 0] = f * (c.cs * at[5] - c.sn * at[4]);
+                v0[NCOMP > 2 ? 2 : 0] = f * at[6];
+            }
+#pragma unroll
+            for (int k = 0; k < NCOMP; ++k) {
+                V[k] = v0[k];
+                double re = v0[k], im = 0.;
+#pragma unroll
+                for (int m = 1; m < NM; ++m) {
+                    const double nre = c.cs * re - c.sn * im, nim = c.cs * im + c.sn * re;
+                    re = nre; im = nim;
+                    V[NCOMP + (k * (NM - 1) + (m - 1)) * 2] = re;
+                    V[NCOMP + (k * (NM - 1) + (m - 1)) * 2 + 1] = im;
+                }
+            }
+        }
+        sK[tid] = key;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) sW[(mt * DM_TPB + tid) * 8 + r] = S[mt * 8 + r];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int v = 0; v < 8; ++v) sV[(nt * DM_TPB + tid) * 8 + v] = V[nt * 8 + v];
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ phase B
+    const int g = lane >> 2, t = lane & 3;
+    const int lo_w = warp * 32, hi_w = lo_w + 32;            // this warp's particles (CTA-local)
+    int pos = lo_w;
+    while (pos < hi_w) {
+        const int key = sK[pos];
+        // end of the run of equal keys starting at pos (within the warp's slice)
+        const int kk = (lo_w + lane >= pos) ? sK[lo_w + lane] : key;
+        const unsigned diff = __ballot_sync(0xffffffffu, kk != key);
+        const int end = diff ? (lo_w + __ffs(diff) - 1) : hi_w;
+        if (key >= 0) {
+            double acc[MT][NT][2];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.;
+            for (int k0 = pos & ~3; k0 < end; k0 += 4) {
+                const int p = k0 + t;
+                const bool in = (p >= pos) && (p < end);
+                double a[MT], b[NT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) a[mt] = in ? sW[(mt * DM_TPB + p) * 8 + g] : 0.;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) b[nt] = in ? sV[(nt * DM_TPB + p) * 8 + g] : 0.;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+            }
+            // ---- flush: this lane holds C[row = mt*8+g][col = nt*8 + 2t + {0,1}] ----
+            const int iz_u = key / (Nr + 1), ir_u = key - iz_u * (Nr + 1);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int row = mt * 8 + g;
+                const int cls = row / NP, pt = row - cls * NP;
+                const int a_ = pt / NPT, b_ = pt - a_ * NPT;
+                int iz = iz_u - NPT / 2 + a_;
+                if (iz < 0) iz += Nz;
+                if (iz > Nz - 1) iz -= Nz;
+                int ir = ir_u - NPT / 2 + b_;
+                const bool below = ir < 0;
+                if (below) ir = -(1 + ir);
+                if (ir > Nr - 1) ir = Nr - 1;
+                const size_t o = (size_t)iz * Nr + ir;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = nt * 8 + 2 * t + h;
+                        if (col >= NVT) continue;
+                        int comp, m, part;
+                        if (col < NCOMP) { comp = col; m = 0; part = 0; }
+                        else {
+                            const int d = col - NCOMP;
+                            part = d & 1;
+                            const int km = d >> 1;
+                            comp = km / (NM > 1 ? NM - 1 : 1);
+                            m = km - comp * (NM > 1 ? NM - 1 : 1) + 1;
+                        }
+                        if ((m > 0) != (cls == 1)) continue;          // weight class of this value
+                        const double v = acc[mt][nt][h];
+                        if (v == 0.) continue;
+                        double sgn = 1.;
+                        if (below) {
+                            sgn = (m & 1) ? -1. : 1.;
+                            if (IS_J && comp < 2) sgn = -sgn;
+                        }
+                        double *p = (double *)(G.g[IS_J ? (3 * m + comp) : m] + o);
+                        atomicAdd(p + part, sgn * v);
+                    }
+            }
+        }
+        pos = end;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct DmArgs {
+    int64_t n;
+    B2DmPtrs P;
+    const int32_t *idx32;
+    double q, invdz, zmin, invdr, rmin;
+    int Nz, Nr;
+    B2DmGrids G;
+    const double *r0, *rh;
+};
+
+template <int NM, bool IS_J, int NPT, bool PERMUTE>
+static int launch_dm(cudaStream_t s, const DmArgs &A) {
+    constexpr int NCOMP = IS_J ? 3 : 1;
+    constexpr int MT = 2 * NPT * NPT / 8, NT = (NCOMP * (2 * NM - 1) + 7) / 8;
+    const size_t smem = sizeof(double) * 8 * DM_TPB * (MT + NT) + sizeof(int) * DM_TPB;
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        B2_CUDA(cudaFuncSetAttribute(k_deposit_mma<NM, IS_J, NPT, PERMUTE>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    unsigned grid = (unsigned)((A.n + DM_TPB - 1) / DM_TPB);
+    k_deposit_mma<NM, IS_J, NPT, PERMUTE><<<grid, DM_TPB, smem, s>>>(
+        A.n, A.P, A.idx32, A.q, A.invdz, A.zmin, A.Nz, A.invdr, A.rmin, A.Nr, A.G, A.r0, A.rh);
+    return 0;
+}
+
+template <int NM>
+static int dispatch_dm(bool is_J, bool cubic, bool permute, cudaStream_t s, const DmArgs &A) {
+#define DM_GO(J, NPT) (permute ? launch_dm<NM, J, NPT, true>(s, A) : launch_dm<NM, J, NPT, false>(s, A))
+    if (!is_J) return cubic ? DM_GO(false, 4) : DM_GO(false, 2);
+    return cubic ? DM_GO(true, 4) : DM_GO(true, 2);
+#undef DM_GO
+}
+
+int b2_deposit_mma(b2_ctx *ctx, bool is_J, int64_t n, const double *const *src8, double *const *dst8,
+                   const int32_t *idx32, double q, double invdz, double zmin, int Nz, double invdr, double rmin,
+                   int Nr, int Nm, void *const *grids, const double *r0, const double *rh, int cubic,
+                   void *stream) {
+    if (n <= 0) return 0;
+    if (Nm < 1 || Nm > 4) return b2_fail(-3, "deposit: Nm must be in 1..4", __FILE__, __LINE__);
+    DmArgs A;
+    const bool permute = (dst8 != nullptr);
+    A.n = n;
+    for (int k = 0; k < 8; ++k) {
+        A.P.src[k] = (k < (is_J || permute ? 8 : 4)) ? src8[k] : nullptr;
+        A.P.dst[k] = permute ? dst8[k] : nullptr;
+    }
+    A.idx32 = idx32;
+    A.q = q; A.invdz = invdz; A.zmin = zmin; A.invdr = invdr; A.rmin = rmin; A.Nz = Nz; A.Nr = Nr;
+    const int ng = is_J ? 3 * Nm : Nm;
+    for (int k = 0; k < ng; ++k) A.G.g[k] = (double2 *)grids[k];
+    A.r0 = r0; A.rh = rh;
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    B2Prof prof_(is_J ? B2P_DEPOSIT_J : B2P_DEPOSIT_RHO, s);
+    int rc;
+    switch (Nm) {
+        case 1: rc = dispatch_dm<1>(is_J, cubic != 0, permute, s, A); break;
+        case 2: rc = dispatch_dm<2>(is_J, cubic != 0, permute, s, A); break;
+        case 3: rc = dispatch_dm<3>(is_J, cubic != 0, permute, s, A); break;
+        default: rc = dispatch_dm<4>(is_J, cubic != 0, permute, s, A); break;
+    }
+    if (rc) return rc;
+    B2_LAUNCHED();
+    return 0;
+}
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int b2_deposit_rho(b2_ctx *ctx, int64_t n, const double *x, const double *y, const double *z, const double *w,
+                   double q, double invdz, double zmin, int Nz, double invdr, double rmin, int Nr, int Nm,
+                   void *const *grids, const int32_t *prefix, const double *r0, const double *rh, int cubic,
+                   void *stream) {
+    (void)prefix;   // kept in the signature for the reference's call shape; the runs are found on the fly
+    const double *src[8] = {x, y, z, w, nullptr, nullptr, nullptr, nullptr};
+    return b2_deposit_mma(ctx, false, n, src, nullptr, nullptr, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm, grids,
+                          r0, rh, cubic, stream);
+}
+
+int b2_deposit_J(b2_ctx *ctx, int64_t n, const double *x, const double *y, const double *z, const double *w,
+                 double q, const double *ux, const double *uy, const double *uz, const double *ig, double invdz,
+                 double zmin, int Nz, double invdr, double rmin, int Nr, int Nm, void *const *grids,
+                 const int32_t *prefix, const double *r0, const double *rh, int cubic, void *stream) {
+    (void)prefix;
+    const double *src[8] = {x, y, z, w, ux, uy, uz, ig};
+    return b2_deposit_mma(ctx, true, n, src, nullptr, nullptr, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm, grids,
+                          r0, rh, cubic, stream);
+}
+
+int b2_deposit_permute(b2_ctx *ctx, int what, int64_t n, const double *const *src8, double *const *dst8,
+                       double q, double invdz, double zmin, int Nz, double invdr, double rmin, int Nr, int Nm,
+                       void *const *grids, const int32_t *prefix, const double *r0, const double *rh, int cubic,
+                       void *stream) {
+    (void)prefix;
+    if (!ctx->last_idx32 || ctx->last_sort_n != n)
+        return b2_fail(-4, "b2_deposit_permute: no matching b2_sort_cells result in this context", __FILE__, __LINE__);
+    return b2_deposit_mma(ctx, what != 0, n, src8, dst8, ctx->last_idx32, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm,
+                          grids, r0, rh, cubic, stream);
+}
+
+int b2_deposit_rho_displaced(b2_ctx *ctx, int64_t n, const double *x, const double *y, const double *z,
+                             const double *w, double q, double invdz, double zmin, int Nz, double invdr, double rmin,
+                             int Nr, int Nm, void *const *grids, const int32_t *prefix, const double *r0,
+                             const double *rh, void *stream) {
+    (void)prefix;
+    const double *src[8] = {x, y, z, w, nullptr, nullptr, nullptr, nullptr};
+    return b2_deposit_mma(ctx, false, n, src, nullptr, nullptr, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm, grids,
+                          r0, rh, 0, stream);
+}
+
+}  // extern "C"

@@ -14,16 +14,17 @@
 // fp64 only: sm_100a has no tcgen05 f64 kind; the f64 tensor path is mma.sync (DMMA.8x8x4 in SASS,
 // measured 37.1 TFLOP/s peak on B200, profiles/r01_microbench.txt).  Bound: fp64 tensor pipe
 // (AI = Nr/8 flop/B).  Several (array, matrix) jobs are batched in one launch (grid.z) so that the
-// 148 SMs see >1 full wave of CTAs.  16 warps per CTA (4x4), warp tile 16 iz x 32 columns: 32 fp64
-// accumulators per thread keep the kernel under 128 registers so that 16 warps fit on an SM.
+// 148 SMs see >1 full wave of CTAs.  8 warps per CTA (2x4), warp tile 16 iz x 32 columns: 32 fp64
+// accumulators per thread keep the kernel under 128 registers, so two CTAs share an SM and one CTA's
+// prologue / epilogue overlaps the other's tensor work.
 #include "b2_common.cuh"
 
-#define DHT_BM 64          // iz rows per CTA tile (=128 real rows)
+#define DHT_BM 32          // iz rows per CTA tile (=64 real rows)
 #define DHT_BN 128         // output columns per CTA tile (NPROD=1) ; 64 per product (NPROD=2)
 #define DHT_BK 16          // K chunk
 #define DHT_AP (DHT_BK + 4)   // A row pitch in complex elements: 20 -> conflict-free LDS.128
 #define DHT_BP (DHT_BN + 4)   // B row pitch in doubles: 132 -> conflict-free LDS.64
-#define DHT_THREADS 512
+#define DHT_THREADS 256
 #define DHT_MAX_JOBS 12
 
 struct DhtJob {
@@ -43,7 +44,7 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
 }
 
 template <int NPROD>
-__global__ void __launch_bounds__(DHT_THREADS, 1)
+__global__ void __launch_bounds__(DHT_THREADS, 2)
 k_dht(DhtJobs jobs, int Nz, int Nr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: A[2 buf][NPROD][BM][AP] double2 | B[2 buf][BK][BP] double
@@ -78,7 +79,7 @@ k_dht(DhtJobs jobs, int Nz, int Nr) {
     // the (r,t)->(p,m) mixing arithmetic happens in store_tiles, after the MMAs of the current
     // chunk, so that no instruction depending on the loads sits in front of the tensor work.
     double2 ra[2][2];
-    double rb[4];
+    double rb[8];
 
     auto load_tiles = [&](int kt) {
         const int k0 = kt * DHT_BK;
@@ -93,7 +94,7 @@ k_dht(DhtJobs jobs, int Nz, int Nr) {
             if (NPROD == 2 || mix) ra[1][qq] = ok ? __ldg(J.in2 + o) : make_double2(0., 0.);
         }
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
+        for (int qq = 0; qq < 8; ++qq) {
             const int e = tid + DHT_THREADS * qq;
             const int k = e / DHT_BN, c = e % DHT_BN;          // c: column within the 128-wide B tile
             const int kk = k0 + k;
@@ -128,7 +129,7 @@ k_dht(DhtJobs jobs, int Nz, int Nr) {
             }
         }
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
+        for (int qq = 0; qq < 8; ++qq) {
             const int e = tid + DHT_THREADS * qq;
             const int k = e / DHT_BN, c = e % DHT_BN;
             sB[buf * B_ELEMS + k * DHT_BP + c] = rb[qq];

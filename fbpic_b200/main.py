@@ -156,9 +156,7 @@ class Simulation(object):
                     #  the exchange_particles at the start of the next step, main.py:435-442)
                     wrap = (z0, z0 + (fld.interp[0].zmax - fld.interp[0].zmin)) \
                         if (wrap_in_push and i_step < N - 1) else None
-                    # cubic shapes re-sort for the rho deposition and use the keys; linear shapes
-                    # deposit rho with the displaced kernel (no sort, no keys)
-                    kz0 = z0 if self.particle_shape == 'cubic' else None
+                    kz0 = None          # rho is deposited without a re-sort: no keys needed here
                     for species in ptcl:
                         species.push_x_and_key(0.5 * dt, fld, wrap=wrap, key_zmin=kz0)
                 else:

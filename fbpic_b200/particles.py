@@ -264,9 +264,10 @@ class Particles(object):
         """Fast path used by Simulation.step(fused=True); same sums as deposit().
         * not sorted: cell sort (keys possibly already emitted by the push kernel), then ONE
           kernel that applies the permutation to the SoA and deposits (`b2_deposit_permute`);
-        * rho, linear shapes, arrays still in the order of the last sort (particles moved by about
-          a cell since): `b2_deposit_rho_displaced`, no re-sort -- the second sort of the PIC cycle
-          (particles.py:866-871 sorts before every deposit) disappears.
+        * rho with the arrays still in the order of the last sort (particles moved by about a cell
+          since): deposited as they lie, no re-sort -- the deposition kernel reduces runs of equal
+          cell key, whatever the order; the second sort of the PIC cycle (particles.py:866-871 sorts
+          before every deposit) disappears.
         The API-visible `cell_idx` / `sorted_idx` are refreshed only by sort_particles()."""
         if self.q == 0:
             return
@@ -284,10 +285,12 @@ class Particles(object):
             grids = ptr_array([getattr(g, k) for g in grid for k in ('Jr', 'Jt', 'Jz')])
         if self.sorted:
             return self.deposit(fld, fieldtype)
-        if fieldtype == 'rho' and not cubic and getattr(self, '_order_matches_prefix', False):
-            call.b2_deposit_rho_displaced(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr, self.w.ptr,
-                                          self.q, g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, Nm, grids,
-                                          self.prefix_sum.ptr, r0.ptr, rh.ptr, None)
+        if fieldtype == 'rho' and getattr(self, '_order_matches_prefix', False):
+            # the arrays are still in the order of the last sort and the particles moved by about a
+            # cell since: the run-based deposition kernel needs no re-sort
+            call.b2_deposit_rho(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr, self.w.ptr,
+                                self.q, g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, Nm, grids,
+                                self.prefix_sum.ptr, r0.ptr, rh.ptr, int(cubic), None)
             return
         if self.cell_idx is None or self.cell_idx.size != self.Ntot:
             self._alloc_sort_arrays()
