@@ -17,6 +17,9 @@ import argparse
 import ctypes
 import json
 import os
+# host-thread hygiene for the CPU legs, before NumPy/OpenBLAS load (oversubscription costs 25x)
+os.environ.setdefault('OMP_WAIT_POLICY', 'passive')
+os.environ.setdefault('OPENBLAS_NUM_THREADS', str(min(os.cpu_count() or 1, 32)))
 import subprocess
 import sys
 import threading
@@ -184,6 +187,7 @@ def main():
         orc.build()
         Nz_s = min(cfg['Nz'], 1024)          # bounded sample: a z-slab of the same workload
         steps = max(1, min(args.steps, 10))
+        nthreads = int(os.environ.get('ORACLE_NUM_THREADS', min(ncores, 32)))
         val, ms, Ntot = time_oracle(cfg, Nz_s, steps, min(args.warmup, 2), nthreads)
         sample = 'z-slab Nz=%d of the workload (%d particles), %d steps, oracle port (C+OpenMP particle ' \
                  'kernels, scipy.fft, OpenBLAS dgemm), %d threads' % (Nz_s, Ntot, steps, nthreads)
@@ -260,6 +264,7 @@ def main():
     if not args.no_e2e:
         sim.receive_data_from_gpu()
         k_e2e = args.steps
+        sim.step(1)                          # untimed: the first round trip allocates the page-locked buffers
         barrier()
         t0 = time.perf_counter()
         sim.step(k_e2e)                      # H2D of all state, K steps, D2H of all state
@@ -327,10 +332,14 @@ def main():
         from oracle import oracle as orc
         orc.build()
         Nz_s = min(cfg['Nz'], 512)
-        val, ms_cpu, n_cpu = time_oracle(cfg, Nz_s, 3, 1, nthreads)
-        cpu_baseline = {'value': val, 'unit': 'particle-updates/s', 'cores': nthreads, 'kind': 'port',
-                        'sample': 'z-slab Nz=%d of the workload (%d particles), 3 steps after 1 warm-up, '
-                                  'oracle port on %d threads of %d logical cores' % (Nz_s, n_cpu, nthreads, ncores)}
+        best = None
+        for nt in sorted({min(ncores, t) for t in (16, 32, 64)}):
+            val, ms_cpu, n_cpu = time_oracle(cfg, Nz_s, 2, 1, nt)
+            if best is None or val > best[0]:
+                best = (val, nt, n_cpu)
+        cpu_baseline = {'value': best[0], 'unit': 'particle-updates/s', 'cores': best[1], 'kind': 'port',
+                        'sample': 'z-slab Nz=%d of the workload (%d particles), 2 steps after 1 warm-up, oracle '
+                                  'port, best of 16/32/64 threads on %d logical cores' % (Nz_s, best[2], ncores)}
     out = {
         'metric': metric, 'value': value, 'unit': 'particle-updates/s', 'n_gpus': n_gpus,
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': t_ms / args.steps,

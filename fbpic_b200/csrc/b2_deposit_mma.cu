@@ -29,6 +29,7 @@
 #include "b2_common.cuh"
 
 #define DM_TPB 256          // particles per CTA = threads per CTA
+#define DM_PITCH (DM_TPB + 4)
 
 struct B2DmGrids {
     double2 *g[3 * B2_MAX_MODES];   // rho: [m] ; J: [m][Jr,Jt,Jz]
@@ -55,9 +56,14 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, double q
     constexpr int NVT = NCOMP * (2 * NM - 1);          // real values per particle
     constexpr int NT = (NVT + 7) / 8;                  // 8-column MMA tiles
     extern __shared__ __align__(16) unsigned char dm_smem[];
-    double *sW = (double *)dm_smem;                    // [MT][DM_TPB][8]
-    double *sV = sW + MT * DM_TPB * 8;                 // [NT][DM_TPB][8]
-    int *sK = (int *)(sV + NT * DM_TPB * 8);           // [DM_TPB] cell key (-1: no particle)
+    // packets, transposed and padded: element (tile, row r, particle p) at (tile*8 + r)*DM_PITCH + p.
+    // Phase A writes rows with consecutive threads (conflict-free); phase B reads fragment element
+    // (r = lane/4, p = k0 + lane%4): DM_PITCH % 16 == 4 makes the 16 lanes of a half-warp hit 16
+    // different 8-byte banks.
+    double *sW = (double *)dm_smem;                    // [MT*8][DM_PITCH]
+    double *sV = sW + MT * 8 * DM_PITCH;               // [NT*8][DM_PITCH]
+    int *sK = (int *)(sV + NT * 8 * DM_PITCH);         // [DM_TPB] cell key (-1: no particle)
+    int *sIz = sK + DM_TPB, *sIr = sIz + DM_TPB;       // [DM_TPB] upper cell indices of the particle
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q0 = blockIdx.x * (int64_t)DM_TPB;
@@ -65,7 +71,7 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, double q
 
     // ------------------------------------------------------------------ phase A
     {
-        int key = -1;
+        int key = -1, kiz = 0, kir = 0;
         double S[NROW];
         double V[NT * 8];
 #pragma unroll
@@ -85,7 +91,7 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, double q
             int iru = (int)ceil(c.r_cell), izu = (int)ceil(c.z_cell);
             if (iru > Nr) iru = Nr;
             if (izu < 0) izu += Nz; else if (izu > Nz - 1) izu -= Nz;
-            key = iru + izu * (Nr + 1);
+            key = iru + izu * (Nr + 1); kiz = izu; kir = iru;
             const double beta0 = __ldg(ruyten0 + iru), beta_hi = __ldg(ruyten_hi + iru);
             // shape factors (particle_shapes.py:17-80); the flip sign is applied at flush time
             double sz[NPT], sr0[NPT], sr1[NPT];
@@ -143,20 +149,49 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, double q
                 }
             }
         }
-        sK[tid] = key;
+        sK[tid] = key; sIz[tid] = kiz; sIr[tid] = kir;
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
+        for (int r = 0; r < MT * 8; ++r) sW[r * DM_PITCH + tid] = S[r];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) sW[(mt * DM_TPB + tid) * 8 + r] = S[mt * 8 + r];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int v = 0; v < 8; ++v) sV[(nt * DM_TPB + tid) * 8 + v] = V[nt * 8 + v];
+        for (int v = 0; v < NT * 8; ++v) sV[v * DM_PITCH + tid] = V[v];
     }
     __syncthreads();
 
     // ------------------------------------------------------------------ phase B
     const int g = lane >> 2, t = lane & 3;
+    // lane constants of the flush: this lane holds C[row = mt*8+g][col = nt*8 + 2t + h]
+    int f_a[MT], f_b[MT];                     // stencil offsets of the row's point
+    double *f_ptr[MT][NT][2];                 // grid base (+re/im part) of the column's value, null: unused
+    double f_flip[MT][NT][2];                 // sign applied when the point lies below the axis
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int row = mt * 8 + g;
+        const int cls = row / NP, pt = row - cls * NP;
+        f_a[mt] = pt / NPT - NPT / 2;
+        f_b[mt] = pt % NPT - NPT / 2;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = nt * 8 + 2 * t + h;
+                int comp = 0, m = 0, part = 0;
+                bool ok = col < NVT;
+                if (col >= NCOMP) {
+                    const int d = col - NCOMP;
+                    part = d & 1;
+                    const int km = d >> 1;
+                    comp = km / (NM > 1 ? NM - 1 : 1);
+                    m = km - comp * (NM > 1 ? NM - 1 : 1) + 1;
+                } else {
+                    comp = col;
+                }
+                ok = ok && ((m > 0) == (cls == 1));        // weight class of this value
+                double sgn = (m & 1) ? -1. : 1.;
+                if (IS_J && comp < 2) sgn = -sgn;
+                f_flip[mt][nt][h] = sgn;
+                f_ptr[mt][nt][h] = ok ? ((double *)G.g[IS_J ? (3 * m + comp) : m] + part) : nullptr;
+            }
+    }
     const int lo_w = warp * 32, hi_w = lo_w + 32;            // this warp's particles (CTA-local)
     int pos = lo_w;
     while (pos < hi_w) {
@@ -176,54 +211,33 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, double q
                 const bool in = (p >= pos) && (p < end);
                 double a[MT], b[NT];
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) a[mt] = in ? sW[(mt * DM_TPB + p) * 8 + g] : 0.;
+                for (int mt = 0; mt < MT; ++mt) a[mt] = in ? sW[(mt * 8 + g) * DM_PITCH + p] : 0.;
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) b[nt] = in ? sV[(nt * DM_TPB + p) * 8 + g] : 0.;
+                for (int nt = 0; nt < NT; ++nt) b[nt] = in ? sV[(nt * 8 + g) * DM_PITCH + p] : 0.;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
             }
-            // ---- flush: this lane holds C[row = mt*8+g][col = nt*8 + 2t + {0,1}] ----
-            const int iz_u = key / (Nr + 1), ir_u = key - iz_u * (Nr + 1);
+            // ---- flush the useful entries with one RED each ----
+            const int iz_u = sIz[pos], ir_u = sIr[pos];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                const int row = mt * 8 + g;
-                const int cls = row / NP, pt = row - cls * NP;
-                const int a_ = pt / NPT, b_ = pt - a_ * NPT;
-                int iz = iz_u - NPT / 2 + a_;
+                int iz = iz_u + f_a[mt];
                 if (iz < 0) iz += Nz;
                 if (iz > Nz - 1) iz -= Nz;
-                int ir = ir_u - NPT / 2 + b_;
+                int ir = ir_u + f_b[mt];
                 const bool below = ir < 0;
                 if (below) ir = -(1 + ir);
                 if (ir > Nr - 1) ir = Nr - 1;
-                const size_t o = (size_t)iz * Nr + ir;
+                const size_t o = 2 * ((size_t)iz * Nr + ir);
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int col = nt * 8 + 2 * t + h;
-                        if (col >= NVT) continue;
-                        int comp, m, part;
-                        if (col < NCOMP) { comp = col; m = 0; part = 0; }
-                        else {
-                            const int d = col - NCOMP;
-                            part = d & 1;
-                            const int km = d >> 1;
-                            comp = km / (NM > 1 ? NM - 1 : 1);
-                            m = km - comp * (NM > 1 ? NM - 1 : 1) + 1;
-                        }
-                        if ((m > 0) != (cls == 1)) continue;          // weight class of this value
                         const double v = acc[mt][nt][h];
-                        if (v == 0.) continue;
-                        double sgn = 1.;
-                        if (below) {
-                            sgn = (m & 1) ? -1. : 1.;
-                            if (IS_J && comp < 2) sgn = -sgn;
-                        }
-                        double *p = (double *)(G.g[IS_J ? (3 * m + comp) : m] + o);
-                        atomicAdd(p + part, sgn * v);
+                        if (f_ptr[mt][nt][h] != nullptr && v != 0.)
+                            atomicAdd(f_ptr[mt][nt][h] + o, below ? f_flip[mt][nt][h] * v : v);
                     }
             }
         }
@@ -246,7 +260,7 @@ template <int NM, bool IS_J, int NPT, bool PERMUTE>
 static int launch_dm(cudaStream_t s, const DmArgs &A) {
     constexpr int NCOMP = IS_J ? 3 : 1;
     constexpr int MT = 2 * NPT * NPT / 8, NT = (NCOMP * (2 * NM - 1) + 7) / 8;
-    const size_t smem = sizeof(double) * 8 * DM_TPB * (MT + NT) + sizeof(int) * DM_TPB;
+    const size_t smem = sizeof(double) * 8 * DM_PITCH * (MT + NT) + sizeof(int) * 3 * DM_TPB;
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
         B2_CUDA(cudaFuncSetAttribute(k_deposit_mma<NM, IS_J, NPT, PERMUTE>,

@@ -302,7 +302,7 @@ k_gather_push(int64_t n, double *__restrict__ x, double *__restrict__ y, double 
 #define GP_TILE_CELLS 96
 
 template <int NM>
-__global__ void __launch_bounds__(GP_TPB, 5)
+__global__ void __launch_bounds__(GP_TPB, 6)
 k_gather_push_tiled(int64_t n, double *__restrict__ x, double *__restrict__ y, double *__restrict__ z,
                     double *__restrict__ ux, double *__restrict__ uy, double *__restrict__ uz,
                     double *__restrict__ inv_gamma, double rmax_gather, double invdz, double zmin, int Nz,
@@ -338,16 +338,15 @@ k_gather_push_tiled(int64_t n, double *__restrict__ x, double *__restrict__ y, d
     const bool any_active = s_box[1] >= z0;
     const bool use_tile = any_active && nrow > 0 && ncol > 0 && nrow <= 4 && (nrow * ncol <= GP_TILE_CELLS)
                           && z0 >= -1 && s_box[1] <= Nz;
-    if (use_tile) {
-        const int ncell = nrow * ncol;
-        for (int e = tid; e < ncell * 6 * NM; e += GP_TPB) {
-            const int a = e / ncell, cell = e - a * ncell;
-            const int row = cell / ncol, col = cell - row * ncol;
-            int iz = z0 + row;
-            if (iz < 0) iz += Nz;
-            if (iz > Nz - 1) iz -= Nz;
-            tile[a][cell] = __ldg(G.g[a] + (size_t)iz * Nr + r0 + col);
-        }
+    if (use_tile && tid < nrow * ncol) {
+        // one thread per tile cell (GP_TILE_CELLS <= GP_TPB), 6*NM coalesced 16-byte loads each
+        const int row = tid / ncol, col = tid - row * ncol;
+        int iz = z0 + row;
+        if (iz < 0) iz += Nz;
+        if (iz > Nz - 1) iz -= Nz;
+        const size_t o = (size_t)iz * Nr + r0 + col;
+#pragma unroll
+        for (int a = 0; a < 6 * NM; ++a) tile[a][tid] = __ldg(G.g[a] + o);
     }
     __syncthreads();
     if (!in_range) return;

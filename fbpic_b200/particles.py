@@ -139,7 +139,7 @@ class Particles(object):
         if not self.data_is_on_gpu:
             return
         for k in FLOAT_ATTRS + FIELD_ATTRS:
-            setattr(self, k, getattr(self, k).get())
+            setattr(self, k, _lib.to_host(getattr(self, k)))
         self.data_is_on_gpu = False
 
     def _need_gpu(self):

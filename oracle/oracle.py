@@ -107,6 +107,9 @@ def gather(x, y, z, rmax_gather, invdz, zmin, Nz, invdr, rmin, Nr, grids, cubic,
                      _p(Ex), _p(Ey), _p(Ez), _p(Bx), _p(By), _p(Bz))
 
 
+_DEP_BUFFERS = {}
+
+
 def deposit(what, x, y, z, w, q, ux, uy, uz, inv_gamma, invdz, zmin, Nz, invdr, rmin, Nr, Nm,
             cubic, beta0, beta_hi, nthreads=None):
     """Deposit 'rho' or 'J'; returns raw (not volume-divided) complex sums,
@@ -114,7 +117,15 @@ def deposit(what, x, y, z, w, q, ux, uy, uz, inv_gamma, invdz, zmin, Nz, invdr, 
     as in fbpic/fields/numba_methods.py:410-461."""
     nthreads = nthreads or nthreads_default()
     ncomp = 3 if what == 'J' else 1
-    glob = np.zeros((nthreads, ncomp, Nm, Nz + 4, Nr + 4), dtype=np.complex128)
+    # the per-thread guarded copies persist between calls and are erased in parallel, like
+    # Fields.rho_global / J*_global + numba_erase_threading_buffer (fields.py:205-218, 539-564)
+    shape = (nthreads, ncomp, Nm, Nz + 4, Nr + 4)
+    glob = _DEP_BUFFERS.get(shape)
+    if glob is None:
+        _DEP_BUFFERS.clear()
+        glob = _DEP_BUFFERS.setdefault(shape, np.zeros(shape, dtype=np.complex128))
+    else:
+        lib().orc_zero(_p(glob), _l(glob.size * 2))
     dummy = x
     lib().orc_deposit(_i(1 if what == 'J' else 0), _l(len(x)), _p(x), _p(y), _p(z), _p(w), _d(q),
                       _p(ux if what == 'J' else dummy), _p(uy if what == 'J' else dummy),

@@ -39,6 +39,13 @@ void orc_set_threads(int n) {
 #endif
 }
 
+/* parallel memset of the per-thread deposition copies (numba_erase_threading_buffer,
+ * fbpic/fields/numba_methods.py:390-407) */
+void orc_zero(double *a, int64_t n) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) a[i] = 0.;
+}
+
 /* ---- cell key: fbpic/particles/utilities/cuda_sorting.py:55-88 ---- */
 void orc_cell_index(int64_t n, const double *x, const double *y, const double *z,
                     double invdz, double zmin, int Nz, double invdr, double rmin, int Nr,
