@@ -57,7 +57,7 @@ def laser_fields(z, r, a0=4., w0=5.e-6, ctau=16.e-15 * c, z0=None, lambda0=0.8e-
     return Er1, Et1, Br1, Bt1
 
 
-def build_b200_sim(cfg, n_gpus, fused=True, seed=0):
+def build_b200_sim(cfg, n_gpus, fused=True, seed=0, sort_period=1):
     from fbpic_b200 import Simulation
     np.random.seed(seed + int(os.environ.get('RANK', '0')))
     Nz_g = cfg['Nz'] * n_gpus
@@ -67,7 +67,8 @@ def build_b200_sim(cfg, n_gpus, fused=True, seed=0):
     n_order = -1 if n_gpus == 1 else 32
     sim = Simulation(Nz_g, zmax, cfg['Nr'], cfg['rmax'], cfg['Nm'], dt, p_zmin=0., p_zmax=zmax,
                      p_rmin=0., p_rmax=cfg['rmax'], p_nz=p_nz, p_nr=p_nr, p_nt=p_nt, n_e=cfg['n_e'],
-                     n_order=n_order, boundaries={'z': 'periodic', 'r': 'reflective'}, fused=fused)
+                     n_order=n_order, boundaries={'z': 'periodic', 'r': 'reflective'}, fused=fused,
+                     sort_period=sort_period)
     g1 = sim.fld.interp[1]
     Er1, Et1, Br1, Bt1 = laser_fields(g1.z, g1.r, z0=0.5 * zmax if n_gpus == 1 else 0.5 * cfg['Nz'] * cfg['dz'])
     g1.Er[:, :], g1.Et[:, :], g1.Br[:, :], g1.Bt[:, :] = Er1, Et1, Br1, Bt1
@@ -102,7 +103,7 @@ class ClockSampler(threading.Thread):
         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
         'clocks_event_reasons.sw_power_cap'
 
-    def __init__(self, gpu_index=0, period=0.2):
+    def __init__(self, gpu_index=0, period=0.05):
         super().__init__(daemon=True)
         self.gpu, self.period, self.samples, self._halt = gpu_index, period, [], threading.Event()
 
@@ -160,12 +161,13 @@ def time_oracle(cfg, Nz, steps, warmup, nthreads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default='C2', choices=sorted(CONFIGS))
     ap.add_argument('--preroll', type=int, default=30, help='untimed setup steps that disorder the plasma')
     ap.add_argument('--no-fused', action='store_true')
+    ap.add_argument('--sort-period', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
@@ -211,7 +213,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('gloo')
     ctx = _lib.context()
-    sim = build_b200_sim(cfg, n_gpus, fused=not args.no_fused)
+    sim = build_b200_sim(cfg, n_gpus, fused=not args.no_fused, sort_period=args.sort_period)
     Ntot_local = sum(s.Ntot for s in sim.ptcl)
     host_state_bytes = sum(getattr(s, k).nbytes for s in sim.ptcl
                            for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w', 'Ex', 'Ey', 'Ez', 'Bx', 'By', 'Bz')) \
@@ -234,6 +236,7 @@ def main():
     call.b2_profile_reset()
     call.b2_profile_enable(1)
     launches0 = _lib.load().b2_launch_count()
+    flops0 = _lib.load().b2_dht_flops()
     barrier()
     if sampler:
         sampler.start()
@@ -245,6 +248,7 @@ def main():
     call.b2_event_elapsed_ms(ev0, ev1, ctypes.byref(ms))
     clocks = sampler.stop() if sampler else None
     launches = _lib.load().b2_launch_count() - launches0
+    dht_flops = _lib.load().b2_dht_flops() - flops0
     call.b2_profile_enable(0)
     prof = profile_table()
     t_ms, n_tot = ms.value, float(Ntot_local)
@@ -300,14 +304,8 @@ def main():
     roofline = None
     shares = {k: v['ms'] / t_ms for k, v in prof.items()}
     if top == 'dht':
-        Nr, Nz = cfg['Nr'], sim.fld.interp[0].Nz
-        # flops per step from the launch mix is awkward to reconstruct; report per-launch average
-        n_l = prof['dht']['launches']
-        flop_step = 0.
-        # every launch handles njobs arrays; count products from the step structure: per mode and step
-        # 5 forward (J:3, rho_prev, rho_next... ) -- computed exactly in DESIGN.md; here measured total:
-        per_mode = (3 + 1 + 1) + 6          # forward products J,rho x2 ; inverse E,B
-        flop_step = cfg['Nm'] * per_mode * 4. * Nz * Nr * Nr
+        # flops counted by the library for the launches of the timed region (4*Nz*Nr^2 per array)
+        flop_step = dht_flops / args.steps
         ach = flop_step * args.steps / (prof['dht']['ms'] * 1e-3) / 1e12
         roofline = {'kernel': 'k_dht (Hankel GEMM, fp64 DMMA)', 'bound': 'tensor', 'achieved': ach,
                     'peak': 37.1, 'unit': 'TFLOP/s', 'frac': ach / 37.1, 'traffic': None,
@@ -346,7 +344,7 @@ def main():
         'pic_steps_per_s': args.steps / (t_ms * 1e-3), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload, 'particles_total': n_tot, 'fused': not args.no_fused,
-                   'n_order': -1 if n_gpus == 1 else 32, 'preroll_steps': args.preroll,
+                   'n_order': -1 if n_gpus == 1 else 32, 'preroll_steps': args.preroll, 'sort_period': args.sort_period,
                    'l2': 'inputs larger than L2 (particle state %.1f GB per GPU)' % (Ntot_local * 64 / 1e9)},
         'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline,
         'cpu_baseline': cpu_baseline, 'kernels': kernels,

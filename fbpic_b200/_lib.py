@@ -97,6 +97,7 @@ _SIGNATURES = {
     'b2_dht_rt_to_pm': [P, P, P, P, P, P, P, P, c_int, c_int, P],
     'b2_dht_pm_to_rt': [P, P, P, P, P, P, P, P, c_int, c_int, P],
     'b2_dht_batch': [P, c_int, ctypes.POINTER(DhtJob), c_int, c_int, P],
+    'b2_dht_flops': [],
     'b2_rt_to_pm': [P, P, P, c_int, c_int, P],
     'b2_pm_to_rt': [P, P, P, c_int, c_int, P],
     'b2_filter': [P, c_int, P, P, P, c_int, c_int, P],
@@ -114,7 +115,7 @@ _SIGNATURES = {
     'b2_nccl_recv': [P, P, c_size_t, c_int, P],
     'b2_nccl_allreduce_max_f64': [P, P, c_size_t, P],
 }
-_RESTYPES = {'b2_profile_name': ctypes.c_char_p, 'b2_profile_slots': c_int,
+_RESTYPES = {'b2_dht_flops': c_double, 'b2_profile_name': ctypes.c_char_p, 'b2_profile_slots': c_int,
              'b2_error_string': ctypes.c_char_p, 'b2_version': ctypes.c_char_p,
              'b2_ctx_stream': c_void_p, 'b2_launch_count': ctypes.c_uint64}
 EXPORTED = sorted(_SIGNATURES)

@@ -194,6 +194,8 @@ k_dht(DhtJobs jobs, int Nz, int Nr) {
     }
 }
 
+static double g_dht_flops = 0.;
+
 template <int NPROD>
 static int launch_dht(b2_ctx *ctx, const DhtJobs &jobs, int njobs, int Nz, int Nr, cudaStream_t s) {
     const size_t smem = sizeof(double2) * 2 * NPROD * DHT_BM * DHT_AP + sizeof(double) * 2 * DHT_BK * DHT_BP;
@@ -204,6 +206,7 @@ static int launch_dht(b2_ctx *ctx, const DhtJobs &jobs, int njobs, int Nz, int N
     }
     const int ncol = DHT_BN / NPROD;
     B2Prof prof_(B2P_DHT, s);
+    g_dht_flops += (double)njobs * NPROD * 4. * Nz * (double)Nr * Nr;   // real flops issued (2 planes x 2*Nz*Nr*Nr)
     dim3 grid((Nr + ncol - 1) / ncol, (Nz + DHT_BM - 1) / DHT_BM, njobs);
     k_dht<NPROD><<<grid, DHT_THREADS, smem, s>>>(jobs, Nz, Nr);
     B2_LAUNCHED();
@@ -212,6 +215,8 @@ static int launch_dht(b2_ctx *ctx, const DhtJobs &jobs, int njobs, int Nz, int N
 }
 
 extern "C" {
+
+double b2_dht_flops(void) { return g_dht_flops; }
 
 // Batched transforms: one launch per kernel flavour for the whole list (all modes / components).
 int b2_dht_batch(b2_ctx *ctx, int njobs, const b2_dht_job *jobs, int Nz, int Nr, void *stream) {

@@ -310,6 +310,7 @@ k_gather_push_tiled(int64_t n, double *__restrict__ x, double *__restrict__ y, d
                     int32_t *__restrict__ cell_idx, double key_zmin) {
     __shared__ double2 tile[6 * NM][GP_TILE_CELLS];
     __shared__ int s_box[4];     // min iz_l (unwrapped), max iz_u (unwrapped), min ir, max ir (clamped)
+    __shared__ int s_anchor[2];
     const int tid = threadIdx.x;
     const int64_t i = blockIdx.x * (int64_t)GP_TPB + tid;
     if (tid == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MIN; s_box[2] = INT_MAX; s_box[3] = INT_MIN; }
@@ -328,17 +329,23 @@ k_gather_push_tiled(int64_t n, double *__restrict__ x, double *__restrict__ y, d
     if (ir_l < 0) { Sr_g = Sr_l; Sr_l = 0.; ir_l = 0; }
     if (ir_l > Nr - 1) ir_l = Nr - 1;
     if (ir_u > Nr - 1) ir_u = Nr - 1;
-    if (active) {
+    // bounding box of the stencils of the particles that lie NEAR the CTA's first particle (sorted
+    // particles all do); a stray particle (moved far since the last sort) gathers from global memory
+    // on its own instead of blowing up the tile for the whole CTA
+    if (tid == 0) { s_anchor[0] = iz_l0; s_anchor[1] = ir_l; }
+    __syncthreads();
+    const bool near = active && abs(iz_l0 - s_anchor[0]) <= 2 && ir_l >= s_anchor[1] - 8 && ir_u <= s_anchor[1] + 40;
+    if (near) {
         atomicMin(&s_box[0], iz_l0); atomicMax(&s_box[1], iz_l0 + 1);
         atomicMin(&s_box[2], ir_l);  atomicMax(&s_box[3], ir_u);
     }
     __syncthreads();
     const int z0 = s_box[0], r0 = s_box[2];
     const int nrow = s_box[1] - z0 + 1, ncol = s_box[3] - r0 + 1;
-    const bool any_active = s_box[1] >= z0;
-    const bool use_tile = any_active && nrow > 0 && ncol > 0 && nrow <= 4 && (nrow * ncol <= GP_TILE_CELLS)
-                          && z0 >= -1 && s_box[1] <= Nz;
-    if (use_tile && tid < nrow * ncol) {
+    const bool tile_ok = (s_box[1] >= z0) && nrow > 0 && ncol > 0 && (nrow * ncol <= GP_TILE_CELLS)
+                         && z0 >= -1 && s_box[1] <= Nz;
+    const bool use_tile = tile_ok && near;          // per thread
+    if (tile_ok && tid < nrow * ncol) {
         // one thread per tile cell (GP_TILE_CELLS <= GP_TPB), 6*NM coalesced 16-byte loads each
         const int row = tid / ncol, col = tid - row * ncol;
         int iz = z0 + row;

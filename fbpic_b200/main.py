@@ -32,13 +32,17 @@ class Simulation(object):
                  gamma_boost=None, use_all_mpi_ranks=True,
                  particle_shape='linear', verbose_level=0,
                  smoother=None, use_ruyten_shapes=True, use_modified_volume=True,
-                 fused=True):
+                 fused=True, sort_period=1):
         """Arguments as in fbpic/main.py:51-229.  `use_cuda` is accepted for drop-in
         compatibility; this implementation only has the GPU path.  `fused=True` lets
         `step()` use the fused kernels (gather+push, correct+push) -- same arithmetic,
-        fewer passes over HBM; `fused=False` issues one kernel per reference operator."""
+        fewer passes over HBM; `fused=False` issues one kernel per reference operator.
+        `sort_period` (fused mode): the particle arrays are re-sorted by cell every sort_period-th
+        step instead of before every deposition; the deposition and gather kernels are correct for
+        any particle order, sorting only restores memory locality."""
         self.use_cuda = True
         self.fused = fused
+        self.sort_period = max(int(sort_period), 1)
         if gamma_boost is not None:
             raise NotImplementedError('gamma_boost conversion is host-side setup outside the hot path; '
                                       'pass boosted-frame quantities directly')
@@ -132,8 +136,10 @@ class Simulation(object):
             gal_shift = self.v_comoving * 0.5 * dt if self.use_galilean else 0.
             if fuse_gp:
                 for species in ptcl:
+                    will_sort = (not getattr(species, '_order_matches_prefix', False)) or \
+                        species._j_since_sort >= self.sort_period - 1
                     species.gather_and_push(fld.interp, self.comm, 0.5 * dt,
-                                            key_zmin=fld.interp[0].zmin + gal_shift)
+                                            key_zmin=(fld.interp[0].zmin + gal_shift) if will_sort else None)
             else:
                 for species in ptcl:
                     species.gather(fld.interp, self.comm)
@@ -285,6 +291,7 @@ class Simulation(object):
                        ux_m=ux_m, uy_m=uy_m, uz_m=uz_m, ux_th=ux_th, uy_th=uy_th, uz_th=uz_th,
                        continuous_injection=continuous_injection, dz_particles=dz_particles,
                        is_tracer=is_tracer)
+        sp.sort_period = self.sort_period
         self.ptcl.append(sp)
         return sp
 

@@ -123,6 +123,7 @@ class Particles(object):
         self.sorting_buffers = [DeviceArray(self.Ntot, np.float64) for _ in range(14)]
         self._order_matches_prefix = False
         self._keys_fresh = False
+        self._j_since_sort = 0
 
     def send_particles_to_gpu(self):
         """particles.py:252-291"""
@@ -292,12 +293,24 @@ class Particles(object):
                                 self.q, g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, Nm, grids,
                                 self.prefix_sum.ptr, r0.ptr, rh.ptr, int(cubic), None)
             return
+        if fieldtype == 'J' and getattr(self, '_order_matches_prefix', False) \
+                and self._j_since_sort < getattr(self, 'sort_period', 1) - 1:
+            # re-sorting is only a locality optimisation for the run-based kernels: with
+            # sort_period > 1 the arrays are re-sorted every sort_period-th current deposition
+            self._j_since_sort += 1
+            self._keys_fresh = False
+            call.b2_deposit_J(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr, self.w.ptr, self.q,
+                              self.ux.ptr, self.uy.ptr, self.uz.ptr, self.inv_gamma.ptr,
+                              g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, Nm, grids,
+                              self.prefix_sum.ptr, r0.ptr, rh.ptr, int(cubic), None)
+            return
         if self.cell_idx is None or self.cell_idx.size != self.Ntot:
             self._alloc_sort_arrays()
         if not getattr(self, '_keys_fresh', False):
             call.b2_cell_index(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr,
                                g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, self.cell_idx.ptr, None)
         self._keys_fresh = False
+        self._j_since_sort = 0
         call.b2_sort_cells(ctx.handle, self.Ntot, self.cell_idx.ptr, None, self.prefix_sum.ptr,
                            g0.Nz, g0.Nr, None)
         self.prefix_sum_shift = 0

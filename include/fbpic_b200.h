@@ -198,6 +198,8 @@ typedef struct {
     const double *rowscale;     /* NULL or [Nz]                                           */
     int kind;
 } b2_dht_job;
+/* fp64 flops issued by the Hankel GEMMs since load (4*Nz*Nr^2 per transformed array) */
+double b2_dht_flops(void);
 int b2_dht_batch(b2_ctx *ctx, int njobs, const b2_dht_job *jobs, int Nz, int Nr, void *stream);
 int b2_rt_to_pm(b2_ctx *ctx, void *d_r_p, void *d_t_m, int Nz, int Nr, void *stream);   /* in place */
 int b2_pm_to_rt(b2_ctx *ctx, void *d_p_r, void *d_m_t, int Nz, int Nr, void *stream);   /* in place */

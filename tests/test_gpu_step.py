@@ -30,12 +30,18 @@ def build_sim(g, tag, fused):
     return sim
 
 
-@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('fused', [False, True, 3])
 @pytest.mark.parametrize('tag', TAGS)
 def test_step_vs_reference_golden(tag, fused):
+    """fused: False = one kernel per reference operator; True = fused kernels; 3 = fused with the
+    particle arrays re-sorted only every 3rd step (sort_period=3)."""
     g = load_golden('step_' + tag)
     Nm = int(g['Nm'])
-    sim = build_sim(g, tag, fused)
+    sim = build_sim(g, tag, bool(fused))
+    if fused == 3:
+        sim.sort_period = 3
+        for sp in sim.ptcl:
+            sp.sort_period = 3
     sim.step(int(g['nsteps']))
     assert abs(sim.fld.interp[0].zmin - float(g['zmin_end'])) <= 1e-12 * abs(float(g['zmax']))
     for i, sp in enumerate(sim.ptcl):
