@@ -90,6 +90,8 @@ _SIGNATURES = {
                            c_int, c_int, P, P, P, P, c_int, P],
     'b2_deposit_rho_displaced': [P, c_int64, P, P, P, P, c_double, c_double, c_double, c_int, c_double, c_double,
                                  c_int, c_int, P, P, P, P, P],
+    'b2_push_deposit_rho': [P, c_int64, P, P, P, P, P, P, P, P, c_double, c_int, c_double, c_double, c_double,
+                            c_double, c_double, c_int, c_double, c_double, c_int, c_int, P, P, P, c_int, P],
     'b2_scale_rows_by_r': [P, c_int, P, P, c_int, c_int, P],
     'b2_fft_z': [P, P, P, c_int, c_int, c_int, P],
     'b2_fft_z_multi': [P, c_int, P, P, c_int, c_int, c_int, P],

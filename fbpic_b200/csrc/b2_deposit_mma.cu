@@ -44,9 +44,18 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
         : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-template <int NM, bool IS_J, int NPT, bool PERMUTE>
+// PUSH (rho only): the second half position push of the PIC cycle (push_x_gpu, push/cuda_methods.py:
+// 17-52) and the periodic wrap are applied first and written back; the charge is deposited at the new
+// position -- one pass over the particle data instead of two (main.py:519,528).
+struct B2DmPush {
+    double chdt;            // c*dt of the push
+    int wrap;               // wrap z into [wrap_zmin, wrap_zmax)
+    double wrap_zmin, wrap_zmax;
+};
+
+template <int NM, bool IS_J, int NPT, bool PERMUTE, bool PUSH>
 __global__ void __launch_bounds__(DM_TPB)
-k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, double q,
+k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush push, double q,
               double invdz, double zmin, int Nz, double invdr, double rmin, int Nr, B2DmGrids G,
               const double *__restrict__ ruyten0, const double *__restrict__ ruyten_hi) {
     constexpr int NCOMP = IS_J ? 3 : 1;
@@ -82,7 +91,21 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, double q
             const size_t j = PERMUTE ? (size_t)__ldg(idx32 + i) : (size_t)i;
             double at[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) at[k] = (PERMUTE || IS_J || k < 4) ? __ldg(P.src[k] + j) : 0.;
+            for (int k = 0; k < 8; ++k) at[k] = (PERMUTE || IS_J || PUSH || k < 4) ? __ldg(P.src[k] + j) : 0.;
+            if (PUSH) {
+                const double f = push.chdt * at[7];
+                at[0] += f * 1. * at[4];
+                at[1] += f * 1. * at[5];
+                at[2] += f * 1. * at[6];
+                if (push.wrap) {
+                    const double l_box = push.wrap_zmax - push.wrap_zmin;
+                    while (at[2] >= push.wrap_zmax) at[2] -= l_box;
+                    while (at[2] < push.wrap_zmin) at[2] += l_box;
+                }
+                if (!PERMUTE) {
+                    P.dst[0][i] = at[0]; P.dst[1][i] = at[1]; P.dst[2][i] = at[2];
+                }
+            }
             if (PERMUTE) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) P.dst[k][i] = at[k];
@@ -254,45 +277,50 @@ struct DmArgs {
     int Nz, Nr;
     B2DmGrids G;
     const double *r0, *rh;
+    B2DmPush push;
+    bool do_push;
 };
 
-template <int NM, bool IS_J, int NPT, bool PERMUTE>
+template <int NM, bool IS_J, int NPT, bool PERMUTE, bool PUSH>
 static int launch_dm(cudaStream_t s, const DmArgs &A) {
     constexpr int NCOMP = IS_J ? 3 : 1;
     constexpr int MT = 2 * NPT * NPT / 8, NT = (NCOMP * (2 * NM - 1) + 7) / 8;
     const size_t smem = sizeof(double) * 8 * DM_PITCH * (MT + NT) + sizeof(int) * 3 * DM_TPB;
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
-        B2_CUDA(cudaFuncSetAttribute(k_deposit_mma<NM, IS_J, NPT, PERMUTE>,
+        B2_CUDA(cudaFuncSetAttribute(k_deposit_mma<NM, IS_J, NPT, PERMUTE, PUSH>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     unsigned grid = (unsigned)((A.n + DM_TPB - 1) / DM_TPB);
-    k_deposit_mma<NM, IS_J, NPT, PERMUTE><<<grid, DM_TPB, smem, s>>>(
-        A.n, A.P, A.idx32, A.q, A.invdz, A.zmin, A.Nz, A.invdr, A.rmin, A.Nr, A.G, A.r0, A.rh);
+    k_deposit_mma<NM, IS_J, NPT, PERMUTE, PUSH><<<grid, DM_TPB, smem, s>>>(
+        A.n, A.P, A.idx32, A.push, A.q, A.invdz, A.zmin, A.Nz, A.invdr, A.rmin, A.Nr, A.G, A.r0, A.rh);
     return 0;
 }
 
 template <int NM>
 static int dispatch_dm(bool is_J, bool cubic, bool permute, cudaStream_t s, const DmArgs &A) {
-#define DM_GO(J, NPT) (permute ? launch_dm<NM, J, NPT, true>(s, A) : launch_dm<NM, J, NPT, false>(s, A))
+#define DM_GO(J, NPT) (permute ? launch_dm<NM, J, NPT, true, false>(s, A) : launch_dm<NM, J, NPT, false, false>(s, A))
+    if (!is_J && A.do_push) return cubic ? launch_dm<NM, false, 4, false, true>(s, A) : launch_dm<NM, false, 2, false, true>(s, A);
     if (!is_J) return cubic ? DM_GO(false, 4) : DM_GO(false, 2);
     return cubic ? DM_GO(true, 4) : DM_GO(true, 2);
 #undef DM_GO
 }
 
 int b2_deposit_mma(b2_ctx *ctx, bool is_J, int64_t n, const double *const *src8, double *const *dst8,
-                   const int32_t *idx32, double q, double invdz, double zmin, int Nz, double invdr, double rmin,
+                   const int32_t *idx32, const B2DmPush *push, double q, double invdz, double zmin, int Nz, double invdr, double rmin,
                    int Nr, int Nm, void *const *grids, const double *r0, const double *rh, int cubic,
                    void *stream) {
     if (n <= 0) return 0;
     if (Nm < 1 || Nm > 4) return b2_fail(-3, "deposit: Nm must be in 1..4", __FILE__, __LINE__);
     DmArgs A;
-    const bool permute = (dst8 != nullptr);
+    const bool permute = (dst8 != nullptr) && (push == nullptr);
     A.n = n;
+    A.do_push = (push != nullptr);
+    if (push) A.push = *push; else { A.push.chdt = 0.; A.push.wrap = 0; A.push.wrap_zmin = A.push.wrap_zmax = 0.; }
     for (int k = 0; k < 8; ++k) {
-        A.P.src[k] = (k < (is_J || permute ? 8 : 4)) ? src8[k] : nullptr;
-        A.P.dst[k] = permute ? dst8[k] : nullptr;
+        A.P.src[k] = (k < (is_J || permute || push ? 8 : 4)) ? src8[k] : nullptr;
+        A.P.dst[k] = (permute || push) ? dst8[k] : nullptr;
     }
     A.idx32 = idx32;
     A.q = q; A.invdz = invdz; A.zmin = zmin; A.invdr = invdr; A.rmin = rmin; A.Nz = Nz; A.Nr = Nr;
@@ -324,7 +352,7 @@ int b2_deposit_rho(b2_ctx *ctx, int64_t n, const double *x, const double *y, con
                    void *stream) {
     (void)prefix;   // kept in the signature for the reference's call shape; the runs are found on the fly
     const double *src[8] = {x, y, z, w, nullptr, nullptr, nullptr, nullptr};
-    return b2_deposit_mma(ctx, false, n, src, nullptr, nullptr, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm, grids,
+    return b2_deposit_mma(ctx, false, n, src, nullptr, nullptr, nullptr, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm, grids,
                           r0, rh, cubic, stream);
 }
 
@@ -334,7 +362,7 @@ int b2_deposit_J(b2_ctx *ctx, int64_t n, const double *x, const double *y, const
                  const int32_t *prefix, const double *r0, const double *rh, int cubic, void *stream) {
     (void)prefix;
     const double *src[8] = {x, y, z, w, ux, uy, uz, ig};
-    return b2_deposit_mma(ctx, true, n, src, nullptr, nullptr, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm, grids,
+    return b2_deposit_mma(ctx, true, n, src, nullptr, nullptr, nullptr, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm, grids,
                           r0, rh, cubic, stream);
 }
 
@@ -345,7 +373,7 @@ int b2_deposit_permute(b2_ctx *ctx, int what, int64_t n, const double *const *sr
     (void)prefix;
     if (!ctx->last_idx32 || ctx->last_sort_n != n)
         return b2_fail(-4, "b2_deposit_permute: no matching b2_sort_cells result in this context", __FILE__, __LINE__);
-    return b2_deposit_mma(ctx, what != 0, n, src8, dst8, ctx->last_idx32, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm,
+    return b2_deposit_mma(ctx, what != 0, n, src8, dst8, ctx->last_idx32, nullptr, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm,
                           grids, r0, rh, cubic, stream);
 }
 
@@ -355,8 +383,21 @@ int b2_deposit_rho_displaced(b2_ctx *ctx, int64_t n, const double *x, const doub
                              const double *rh, void *stream) {
     (void)prefix;
     const double *src[8] = {x, y, z, w, nullptr, nullptr, nullptr, nullptr};
-    return b2_deposit_mma(ctx, false, n, src, nullptr, nullptr, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm, grids,
+    return b2_deposit_mma(ctx, false, n, src, nullptr, nullptr, nullptr, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm, grids,
                           r0, rh, 0, stream);
+}
+
+int b2_push_deposit_rho(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, const double *w,
+                        const double *ux, const double *uy, const double *uz, const double *ig, double dt,
+                        int wrap, double wrap_zmin, double wrap_zmax, double q, double invdz, double zmin, int Nz,
+                        double invdr, double rmin, int Nr, int Nm, void *const *grids, const double *r0,
+                        const double *rh, int cubic, void *stream) {
+    const double *src[8] = {x, y, z, w, ux, uy, uz, ig};
+    double *dst[8] = {x, y, z, nullptr, nullptr, nullptr, nullptr, nullptr};
+    B2DmPush push;
+    push.chdt = B2_C_LIGHT * dt; push.wrap = wrap; push.wrap_zmin = wrap_zmin; push.wrap_zmax = wrap_zmax;
+    return b2_deposit_mma(ctx, false, n, src, dst, nullptr, &push, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm, grids,
+                          r0, rh, cubic, stream);
 }
 
 }  // extern "C"

@@ -155,7 +155,18 @@ class Simulation(object):
                 species.keep_fields_sorted = False
 
             self.deposit('J', exchange=(correct_currents is False))
-            if move_positions:
+            # fused mode: the second half push rides inside the rho deposition kernel when every
+            # species deposits and already has sort locality
+            fuse_pr = self.fused and move_positions and single and len(ptcl) > 0 and \
+                all((sp.q != 0) and (not sp.is_tracer) and getattr(sp, '_order_matches_prefix', False)
+                    for sp in ptcl)
+            if fuse_pr:
+                if self.use_galilean:
+                    self.shift_galilean_boundaries(0.5 * dt)
+                z0 = fld.interp[0].zmin
+                wrap = (z0, fld.interp[0].zmax) if (wrap_in_push and i_step < N - 1) else None
+                self.deposit('rho_next', exchange=(use_true_rho is True), push=(0.5 * dt, wrap))
+            elif move_positions:
                 if self.fused:
                     z0 = fld.interp[0].zmin + gal_shift
                     # (no wrap after the last step of this call: the reference leaves x^{n+1} unwrapped until
@@ -168,9 +179,10 @@ class Simulation(object):
                 else:
                     for species in ptcl:
                         species.push_x(0.5 * dt)
-            if self.use_galilean:
-                self.shift_galilean_boundaries(0.5 * dt)
-            self.deposit('rho_next', exchange=(use_true_rho is True))
+            if not fuse_pr:
+                if self.use_galilean:
+                    self.shift_galilean_boundaries(0.5 * dt)
+                self.deposit('rho_next', exchange=(use_true_rho is True))
 
             if fuse_cp:
                 fld.correct_currents_and_push(use_true_rho)
@@ -201,7 +213,7 @@ class Simulation(object):
         else:
             _lib.context().sync()
 
-    def deposit(self, fieldtype, exchange=False, update_spectral=True, species_list=None):
+    def deposit(self, fieldtype, exchange=False, update_spectral=True, species_list=None, push=None):
         """fbpic/main.py:588-670"""
         fld = self.fld
         if species_list is None:
@@ -215,7 +227,7 @@ class Simulation(object):
         fld.erase(grid_type)
         for species in species_list:
             if self.fused:
-                species.deposit_fused(fld, grid_type)
+                species.deposit_fused(fld, grid_type, push=push)
             else:
                 species.deposit(fld, grid_type)
         fld.sum_reduce_deposition_array(grid_type)

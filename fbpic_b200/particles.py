@@ -261,7 +261,7 @@ class Particles(object):
             self.sorting_buffers[i] = src[i]
 
     # ------------------------------------------------------------------ deposition
-    def deposit_fused(self, fld, fieldtype):
+    def deposit_fused(self, fld, fieldtype, push=None):
         """Fast path used by Simulation.step(fused=True); same sums as deposit().
         * not sorted: cell sort (keys possibly already emitted by the push kernel), then ONE
           kernel that applies the permutation to the SoA and deposits (`b2_deposit_permute`);
@@ -284,6 +284,19 @@ class Particles(object):
             grids = ptr_array([g.rho for g in grid])
         else:
             grids = ptr_array([getattr(g, k) for g in grid for k in ('Jr', 'Jt', 'Jz')])
+        if push is not None:
+            # second half position push + periodic wrap + rho deposition at the new position,
+            # one pass (main.py:519 and :528); push = (dt, wrap interval or None)
+            assert fieldtype == 'rho'
+            dt_x, wrap = push
+            wz = wrap if wrap is not None else (0., 0.)
+            call.b2_push_deposit_rho(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr, self.w.ptr,
+                                     self.ux.ptr, self.uy.ptr, self.uz.ptr, self.inv_gamma.ptr, dt_x,
+                                     int(wrap is not None), wz[0], wz[1], self.q, g0.invdz, g0.zmin, g0.Nz,
+                                     g0.invdr, g0.rmin, g0.Nr, Nm, grids, r0.ptr, rh.ptr, int(cubic), None)
+            self.sorted = False
+            self._keys_fresh = False
+            return
         if self.sorted:
             return self.deposit(fld, fieldtype)
         if fieldtype == 'rho' and getattr(self, '_order_matches_prefix', False):

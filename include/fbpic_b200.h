@@ -161,6 +161,16 @@ int b2_deposit_rho_displaced(b2_ctx *ctx, int64_t n, const double *d_x, const do
                              const int32_t *d_prefix_sum, const double *d_ruyten0, const double *d_ruyten_hi,
                              void *stream);
 
+/* push_x(dt) (+ optional periodic wrap of z) fused with the rho deposition at the NEW position
+ * (main.py:519 + 528 in one pass; the grid may have moved in between: zmin is the grid of the
+ * deposition) */
+int b2_push_deposit_rho(b2_ctx *ctx, int64_t n, double *d_x, double *d_y, double *d_z, const double *d_w,
+                        const double *d_ux, const double *d_uy, const double *d_uz, const double *d_inv_gamma,
+                        double dt, int wrap, double wrap_zmin, double wrap_zmax, double q,
+                        double invdz, double zmin, int Nz, double invdr, double rmin, int Nr, int Nm,
+                        void *const *d_grids, const double *d_ruyten0, const double *d_ruyten_hi, int cubic,
+                        void *stream);
+
 /* ---- interpolation-grid element-wise ops: cuda_erase_*, cuda_divide_*_by_volume
  *      (fbpic/fields/cuda_methods.py:18-117) ---------------------------------- */
 int b2_scale_rows_by_r(b2_ctx *ctx, int n_arrays, void *const *d_arrays, const double *d_invvol,
