@@ -65,10 +65,25 @@ def build_b200_sim(cfg, n_gpus, fused=True, seed=0, sort_period=1):
     dt = cfg['dz'] / c
     p_nz, p_nr, p_nt = cfg['ppc']
     n_order = -1 if n_gpus == 1 else 32
+    n_guard = None
+    if n_gpus > 1:
+        # guard width: the stencil reach of n_order=32 (boundary_communicator.py:243-250), rounded up
+        # until the local grid length Nz/N + 2*n_guard has no prime factor above 13 (cuFFT otherwise
+        # runs Bluestein: 4096+2*63 = 2*2111, 13x slower).  A wider guard region is always valid.
+        from fbpic_b200.host_tables import stencil_reach
+        n_guard = stencil_reach(Nz_g, cfg['dz'], cfg['dz'], n_order, None, False) + 1
+
+        def smooth(n):
+            for p in (2, 3, 5, 7, 11, 13):
+                while n % p == 0:
+                    n //= p
+            return n == 1
+        while not smooth(cfg['Nz'] + 2 * n_guard):
+            n_guard += 1
     sim = Simulation(Nz_g, zmax, cfg['Nr'], cfg['rmax'], cfg['Nm'], dt, p_zmin=0., p_zmax=zmax,
                      p_rmin=0., p_rmax=cfg['rmax'], p_nz=p_nz, p_nr=p_nr, p_nt=p_nt, n_e=cfg['n_e'],
-                     n_order=n_order, boundaries={'z': 'periodic', 'r': 'reflective'}, fused=fused,
-                     sort_period=sort_period)
+                     n_order=n_order, n_guard=n_guard, boundaries={'z': 'periodic', 'r': 'reflective'},
+                     fused=fused, sort_period=sort_period)
     g1 = sim.fld.interp[1]
     Er1, Et1, Br1, Bt1 = laser_fields(g1.z, g1.r, z0=0.5 * zmax if n_gpus == 1 else 0.5 * cfg['Nz'] * cfg['dz'])
     g1.Er[:, :], g1.Et[:, :], g1.Br[:, :], g1.Bt[:, :] = Er1, Et1, Br1, Bt1
@@ -344,7 +359,7 @@ def main():
         'pic_steps_per_s': args.steps / (t_ms * 1e-3), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload, 'particles_total': n_tot, 'fused': not args.no_fused,
-                   'n_order': -1 if n_gpus == 1 else 32, 'preroll_steps': args.preroll, 'sort_period': args.sort_period,
+                   'n_order': -1 if n_gpus == 1 else 32, 'n_guard': sim.comm.n_guard, 'preroll_steps': args.preroll, 'sort_period': args.sort_period,
                    'l2': 'inputs larger than L2 (particle state %.1f GB per GPU)' % (Ntot_local * 64 / 1e9)},
         'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline,
         'cpu_baseline': cpu_baseline, 'kernels': kernels,

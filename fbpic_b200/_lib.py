@@ -113,6 +113,8 @@ _SIGNATURES = {
     'b2_nccl_destroy': [P],
     'b2_nccl_group_start': [],
     'b2_nccl_group_end': [],
+    'b2_comm_begin': [P],
+    'b2_comm_end': [P],
     'b2_nccl_send': [P, P, c_size_t, c_int, P],
     'b2_nccl_recv': [P, P, c_size_t, c_int, P],
     'b2_nccl_allreduce_max_f64': [P, P, c_size_t, P],
@@ -295,7 +297,17 @@ class DeviceArray(object):
         return d
 
     def view(self, shape, dtype=None, byte_offset=0):
-        return DeviceArray(shape, dtype or self.dtype, base=self.base, offset=self.offset + byte_offset)
+        v = DeviceArray(shape, dtype or self.dtype, base=self.base, offset=self.offset + byte_offset)
+        if v.offset + v.nbytes > self.base.nbytes:
+            raise B200Error('DeviceArray.view: %d bytes at offset %d exceed the %d-byte allocation'
+                            % (v.nbytes, v.offset, self.base.nbytes))
+        return v
+
+    @property
+    def capacity(self):
+        """Number of elements of this dtype that fit between this view's start and the end of the
+        underlying allocation (per-particle arrays are allocated with headroom)."""
+        return (self.base.nbytes - self.offset) // self.dtype.itemsize
 
     def __getitem__(self, key):
         """Row-range view: a[i0:i1] along the first axis (contiguous)."""

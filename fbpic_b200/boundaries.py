@@ -248,7 +248,7 @@ class BoundaryCommunicator(object):
         # (left, right) and receives (right, left): with 2 ranks on a ring both neighbours are the
         # same peer and this order is what keeps the two directions apart (the reference uses MPI
         # tags 1/2 for that, boundary_communicator.py:688-699).
-        call.b2_nccl_group_start()
+        call.b2_comm_begin(ctx.handle)
         for i, a in enumerate(arrays):
             if self.left_proc is not None:
                 call.b2_nccl_send(ctx.handle, a[plan['send_l'][0]:plan['send_l'][1]].ptr, slab_bytes,
@@ -264,7 +264,7 @@ class BoundaryCommunicator(object):
                 dst = a[plan['recv_l'][0]:plan['recv_l'][1]].ptr if method == 'replace' \
                     else recv['l'].ptr + i * slab_bytes
                 call.b2_nccl_recv(ctx.handle, dst, slab_bytes, self.left_proc, None)
-        call.b2_nccl_group_end()
+        call.b2_comm_end(ctx.handle)
         if method == 'add':
             for i, a in enumerate(arrays):
                 if self.left_proc is not None:
@@ -320,7 +320,7 @@ class BoundaryCommunicator(object):
             h = cnt.get()
             n_recv_l, n_recv_r = int(h[2]), int(h[3])
         n_new = n_recv_l + n_stay + n_recv_r
-        new = {k: DeviceArray(n_new, np.float64) for k in FLOAT_ATTRS}
+        new = species.exchange_buffers(n_new)       # spare sort buffers: no allocation in steady state
         if self.size > 1:
             call.b2_nccl_group_start()
             for k in FLOAT_ATTRS:
@@ -345,13 +345,7 @@ class BoundaryCommunicator(object):
             self._shift_z(new['z'], n_recv_l + n_stay, n_recv_r, +Ltot)
         if self.left_proc == self.size - 1 and n_recv_l:
             self._shift_z(new['z'], 0, n_recv_l, -Ltot)
-        for k in FLOAT_ATTRS:
-            setattr(species, k, new[k])
-        species.Ntot = n_new
-        for k in ('Ex', 'Ey', 'Ez', 'Bx', 'By', 'Bz'):
-            setattr(species, k, DeviceArray(n_new, np.float64))
-        species._alloc_sort_arrays()
-        species.sorted = False
+        species.resize_device_arrays(new, n_new)
 
     @staticmethod
     def _shift_z(z, start, count, dz_shift):

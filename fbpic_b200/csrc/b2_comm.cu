@@ -45,6 +45,22 @@ int b2_nccl_destroy(b2_ctx *ctx) {
 int b2_nccl_group_start(void) { B2_NCCL(ncclGroupStart()); return 0; }
 int b2_nccl_group_end(void) { B2_NCCL(ncclGroupEnd()); return 0; }
 
+// group start/end bracketed by profiler events on the context stream (slot "comm")
+static B2Prof *g_comm_prof = nullptr;
+int b2_comm_begin(b2_ctx *ctx) {
+    if (g_comm_prof) { delete g_comm_prof; g_comm_prof = nullptr; }
+    g_comm_prof = new B2Prof(B2P_COMM, ctx->stream);
+    B2_NCCL(ncclGroupStart());
+    return 0;
+}
+int b2_comm_end(b2_ctx *ctx) {
+    (void)ctx;
+    ncclResult_t r = ncclGroupEnd();
+    if (g_comm_prof) { delete g_comm_prof; g_comm_prof = nullptr; }
+    if (r != ncclSuccess) return b2_fail((int)r, ncclGetErrorString(r), __FILE__, __LINE__);
+    return 0;
+}
+
 int b2_nccl_send(b2_ctx *ctx, const void *buf, size_t nbytes, int peer, void *stream) {
     B2_NCCL(ncclSend(buf, nbytes, ncclChar, peer, (ncclComm_t)ctx->nccl_comm, b2_stream_of(ctx, stream)));
     g_b2_launches.fetch_add(1);

@@ -231,7 +231,7 @@ class Simulation(object):
             else:
                 species.deposit(fld, grid_type)
         fld.sum_reduce_deposition_array(grid_type)
-        if self.fused and self.comm.size == 1 and update_spectral:
+        if self.fused and update_spectral and not (exchange and self.comm.size > 1):
             # divide_by_volume, the transforms and the filter as FFTs + one batched Hankel launch
             fld.fused_deposit2spect(fieldtype, self.filter_currents)
             fld.exchanged_source[fieldtype] = exchange

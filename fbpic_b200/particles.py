@@ -114,13 +114,23 @@ class Particles(object):
         self.sorted = False
 
     # ------------------------------------------------------------------ device residency
+    HEADROOM = 1.08     # per-particle device arrays are allocated with room for migration
+
+    def _capacity_for(self, n):
+        return int(n * self.HEADROOM) + 4096
+
     def _alloc_sort_arrays(self):
+        """(Re)allocate the sort work arrays.  All per-particle arrays share one capacity so that
+        particle exchange can reuse them without touching the allocator."""
         Nz, Nr = self.grid_shape
-        self.cell_idx = DeviceArray(self.Ntot, np.int32)
-        self.sorted_idx = DeviceArray(self.Ntot, np.int64)
-        self.prefix_sum = DeviceArray(Nz * (Nr + 1), np.int32)
+        cap = max(getattr(self, '_capacity', 0), self._capacity_for(self.Ntot))
+        self._capacity = cap
+        self.cell_idx = DeviceArray(cap, np.int32).view((self.Ntot,))
+        self.sorted_idx = DeviceArray(cap, np.int64).view((self.Ntot,))
+        if self.prefix_sum is None or self.prefix_sum.size != Nz * (Nr + 1):
+            self.prefix_sum = DeviceArray(Nz * (Nr + 1), np.int32)
         # double buffers for the one-pass SoA permutation (8 state + 6 field arrays)
-        self.sorting_buffers = [DeviceArray(self.Ntot, np.float64) for _ in range(14)]
+        self.sorting_buffers = [DeviceArray(cap, np.float64).view((self.Ntot,)) for _ in range(14)]
         self._order_matches_prefix = False
         self._keys_fresh = False
         self._j_since_sort = 0
@@ -129,8 +139,11 @@ class Particles(object):
         """particles.py:252-291"""
         if self.data_is_on_gpu:
             return
+        self._capacity = self._capacity_for(self.Ntot)
         for k in FLOAT_ATTRS + FIELD_ATTRS:
-            setattr(self, k, DeviceArray.from_numpy(np.asarray(getattr(self, k), dtype=np.float64)))
+            d = DeviceArray(self._capacity, np.float64).view((self.Ntot,))
+            d.set(np.asarray(getattr(self, k), dtype=np.float64))
+            setattr(self, k, d)
         self._alloc_sort_arrays()
         self.sorted = False
         self.data_is_on_gpu = True
@@ -142,6 +155,43 @@ class Particles(object):
         for k in FLOAT_ATTRS + FIELD_ATTRS:
             setattr(self, k, _lib.to_host(getattr(self, k)))
         self.data_is_on_gpu = False
+
+    def resize_device_arrays(self, new_arrays, n_new):
+        """Adopt `new_arrays` (dict of the 8 state arrays, length n_new, built in the spare sort
+        buffers) after a particle exchange; every other per-particle array is re-viewed at the new
+        length.  Falls back to fresh allocations when n_new exceeds the capacity."""
+        old = [getattr(self, k) for k in FLOAT_ATTRS]
+        if n_new <= self._capacity:
+            for k in FLOAT_ATTRS:
+                setattr(self, k, new_arrays[k])
+            spare = [a.view((n_new,)) for a in old] + [b.view((n_new,)) for b in self.sorting_buffers[8:]]
+            self.sorting_buffers = spare
+            for k in FIELD_ATTRS:
+                setattr(self, k, getattr(self, k).view((n_new,)))
+            self.cell_idx = self.cell_idx.view((n_new,))
+            self.sorted_idx = self.sorted_idx.view((n_new,))
+            self.Ntot = n_new
+        else:
+            self.Ntot = n_new
+            self._capacity = self._capacity_for(n_new)
+            for k in FLOAT_ATTRS:
+                d = DeviceArray(self._capacity, np.float64).view((n_new,))
+                d.copy_from(new_arrays[k])
+                setattr(self, k, d)
+            for k in FIELD_ATTRS:
+                setattr(self, k, DeviceArray(self._capacity, np.float64).view((n_new,)))
+            self._alloc_sort_arrays()
+        self._order_matches_prefix = False
+        self._keys_fresh = False
+        self._j_since_sort = 0
+        self.sorted = False
+
+    def exchange_buffers(self, n_new):
+        """Destination arrays (length n_new) for a particle exchange: the spare sort buffers when
+        they are large enough, else temporary allocations."""
+        if n_new <= self._capacity:
+            return {k: self.sorting_buffers[i].view((n_new,)) for i, k in enumerate(FLOAT_ATTRS)}
+        return {k: DeviceArray(n_new, np.float64) for k in FLOAT_ATTRS}
 
     def _need_gpu(self):
         if not self.data_is_on_gpu:

@@ -248,6 +248,9 @@ int b2_nccl_init(b2_ctx *ctx, const void *id128, int rank, int size);
 int b2_nccl_destroy(b2_ctx *ctx);
 int b2_nccl_group_start(void);
 int b2_nccl_group_end(void);
+/* group start / end bracketed by profiler events (slot "comm") on the context stream */
+int b2_comm_begin(b2_ctx *ctx);
+int b2_comm_end(b2_ctx *ctx);
 int b2_nccl_send(b2_ctx *ctx, const void *d_buf, size_t nbytes, int peer, void *stream);
 int b2_nccl_recv(b2_ctx *ctx, void *d_buf, size_t nbytes, int peer, void *stream);
 int b2_nccl_allreduce_max_f64(b2_ctx *ctx, double *d_buf, size_t count, void *stream);
