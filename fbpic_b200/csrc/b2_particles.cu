@@ -302,7 +302,7 @@ k_gather_push(int64_t n, double *__restrict__ x, double *__restrict__ y, double 
 #define GP_TILE_CELLS 96
 
 template <int NM>
-__global__ void __launch_bounds__(GP_TPB, 6)
+__global__ void __launch_bounds__(GP_TPB, 8)
 k_gather_push_tiled(int64_t n, double *__restrict__ x, double *__restrict__ y, double *__restrict__ z,
                     double *__restrict__ ux, double *__restrict__ uy, double *__restrict__ uz,
                     double *__restrict__ inv_gamma, double rmax_gather, double invdz, double zmin, int Nz,

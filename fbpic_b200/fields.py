@@ -530,6 +530,31 @@ class Fields(object):
         for a, b in ffts:
             call.b2_fft_z(ctx.handle, a.ptr, b.ptr, self.Nz, self.Nr, 2, None)
 
+    def fused_partial2interp_EB(self):
+        """After the guard-cell exchange of exchange_and_damp_EB (main.py:741-747) the interpolation
+        arrays hold E, B in (z, kr) space.  The inverse Hankel transform commutes with the z-FFT, so
+        the real-space fields follow directly from those arrays -- iDHT only, (p,m)->(r,t) in the
+        epilogue -- instead of spect2interp's iDHT + inverse FFT of the spectral arrays
+        (main.py:768-769): 6*Nm FFTs less per step.  Call AFTER partial_interp2spect."""
+        T = self._fused_tables(getattr(self, '_fused_key', True))
+        ctx = _lib.context()
+        jobs, swaps = [], []
+        for m in range(self.Nm):
+            g, tr, t = self.interp[m], self.trans[m], T[m]
+            for f, o in (('E', 0), ('B', 3)):
+                bz, br, bt = t['buf'][o], t['buf'][o + 1], t['buf'][o + 2]
+                jobs.append(DhtJob(getattr(g, f + 'z').ptr, None, bz.ptr, None, tr.dht0.d_invM.ptr, None, None,
+                                   _lib.DHT_SCALAR))
+                jobs.append(DhtJob(getattr(g, f + 'r').ptr, getattr(g, f + 't').ptr, br.ptr, bt.ptr,
+                                   tr.dhtp.d_invM.ptr, tr.dhtm.d_invM.ptr, None, _lib.DHT_PM_TO_RT))
+                swaps += [(f + 'z', o), (f + 'r', o + 1), (f + 't', o + 2)]
+            for name, o in swaps[-6:]:
+                old = getattr(g, name)
+                setattr(g, name, t['buf'][o])        # pointer swap: the result becomes the field array
+                t['buf'][o] = old
+        arr = (DhtJob * len(jobs))(*jobs)
+        call.b2_dht_batch(ctx.handle, len(jobs), arr, self.Nz, self.Nr, None)
+
     # ---- interpolation-grid ops ----
     def erase(self, fieldtype):
         for m in range(self.Nm):

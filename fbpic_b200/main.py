@@ -258,6 +258,10 @@ class Simulation(object):
             self.comm.damp_EB_open_boundary(fld.interp)
             fld.partial_interp2spect('E')
             fld.partial_interp2spect('B')
+            if self.fused:
+                # the exchanged (z, kr) arrays go straight to real space: inverse Hankel only
+                fld.fused_partial2interp_EB()
+                return
         if self.fused:
             fld.fused_spect2interp_EB()
         else:
