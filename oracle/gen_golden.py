@@ -167,16 +167,19 @@ def impart_momenta(sp, epsilon, k0, w0, wp):
     sp.inv_gamma[:] = 1. / np.sqrt(1 + sp.ux**2 + sp.uy**2 + sp.uz**2)
 
 
-def gen_step(tag, shape, Nm, n_order, v_comoving, use_galilean, nsteps=3, ions=False):
+def gen_step(tag, shape, Nm, n_order, v_comoving, use_galilean, nsteps=3, ions=False, open_z=False):
     np.random.seed(0)
     Nz, Nr, zmax, rmax = 24, 12, 12.e-6, 8.e-6
     dt = zmax / Nz / c
     n_e = 2.e24
-    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, p_zmin=0, p_zmax=zmax, p_rmin=0, p_rmax=rmax,
+    pz0, pz1 = (0.25 * zmax, 0.75 * zmax) if open_z else (0, zmax)
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, p_zmin=pz0, p_zmax=pz1, p_rmin=0, p_rmax=rmax,
                      p_nz=2, p_nr=2, p_nt=4 * max(Nm - 1, 1), n_e=n_e, n_order=n_order,
                      particle_shape=shape, v_comoving=v_comoving, use_galilean=use_galilean,
-                     initialize_ions=ions, verbose_level=0, n_guard=(None if n_order == -1 else 8),
-                     boundaries={'z': 'periodic', 'r': 'reflective'})
+                     initialize_ions=ions, verbose_level=0,
+                     n_guard=(16 if open_z else (None if n_order == -1 else 8)),
+                     n_damp={'z': 16, 'r': 32},
+                     boundaries={'z': ('open' if open_z else 'periodic'), 'r': 'reflective'})
     k0 = 2 * np.pi / zmax * 2
     wp = np.sqrt(n_e * e**2 / (m_e * 8.8541878128e-12))
     impart_momenta(sim.ptcl[0], 0.05, k0, 3.e-6, wp)
@@ -188,7 +191,8 @@ def gen_step(tag, shape, Nm, n_order, v_comoving, use_galilean, nsteps=3, ions=F
             sp.inv_gamma[:] = 1. / np.sqrt(1 + sp.ux**2 + sp.uy**2 + sp.uz**2)
     out = dict(Nz=Nz, Nr=Nr, Nm=Nm, zmax=zmax, rmax=rmax, dt=dt, n_order=n_order, nsteps=nsteps,
                v_comoving=(0. if v_comoving is None else v_comoving),
-               has_v=(v_comoving is not None), use_galilean=use_galilean, n_species=len(sim.ptcl))
+               has_v=(v_comoving is not None), use_galilean=use_galilean, n_species=len(sim.ptcl),
+               open_z=open_z, Nz_local=sim.fld.interp[0].Nz)
     for i, sp in enumerate(sim.ptcl):
         out.update({'s%d_in_%s' % (i, k): v for k, v in ptcl_arrays(sp).items()})
         out['s%d_q' % i], out['s%d_m' % i] = sp.q, sp.m
@@ -202,6 +206,9 @@ def gen_step(tag, shape, Nm, n_order, v_comoving, use_galilean, nsteps=3, ions=F
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    if '--only-open' in sys.argv:
+        gen_step('linear_open', 'linear', 2, -1, None, False, nsteps=5, open_z=True)
+        sys.exit(0)
     gen_tables()
     for shape in ('linear', 'cubic'):
         for Nm in (1, 2, 3):
@@ -211,3 +218,4 @@ if __name__ == '__main__':
     gen_step('linear_Nm3_order8', 'linear', 3, 8, None, False)
     gen_step('linear_galilean', 'linear', 2, 16, -0.995 * c, True, ions=True)
     gen_step('linear_comoving', 'linear', 2, 16, -0.995 * c, False, ions=True)
+    gen_step('linear_open', 'linear', 2, -1, None, False, nsteps=5, open_z=True)

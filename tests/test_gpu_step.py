@@ -7,7 +7,7 @@ from conftest import load_golden, assert_close, group_scale
 
 pytestmark = pytest.mark.gpu
 
-TAGS = ['linear_std', 'cubic_std', 'linear_Nm3_order8', 'linear_galilean', 'linear_comoving']
+TAGS = ['linear_std', 'cubic_std', 'linear_Nm3_order8', 'linear_galilean', 'linear_comoving', 'linear_open']
 
 
 def build_sim(g, tag, fused):
@@ -16,10 +16,14 @@ def build_sim(g, tag, fused):
     Nz, Nr, Nm = int(g['Nz']), int(g['Nr']), int(g['Nm'])
     V = float(g['v_comoving']) if bool(g['has_v']) else None
     n_order = int(g['n_order'])
+    open_z = bool(g['open_z']) if 'open_z' in g else False
     sim = Simulation(Nz, float(g['zmax']), Nr, float(g['rmax']), Nm, float(g['dt']),
                      n_order=n_order, v_comoving=V, use_galilean=bool(g['use_galilean']),
                      particle_shape=('cubic' if 'cubic' in tag else 'linear'),
-                     n_guard=(None if n_order == -1 else 8), fused=fused)
+                     n_guard=(16 if open_z else (None if n_order == -1 else 8)), n_damp={'z': 16, 'r': 32},
+                     boundaries={'z': ('open' if open_z else 'periodic'), 'r': 'reflective'}, fused=fused)
+    if open_z:      # open z: guard + damp + injection cells around the physical box, sin^2 damping of E, B
+        assert sim.fld.interp[0].Nz == int(g['Nz_local'])
     for i in range(int(g['n_species'])):
         sp = sim.add_new_species(q=float(g['s%d_q' % i]), m=float(g['s%d_m' % i]))
         for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w'):
