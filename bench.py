@@ -331,6 +331,13 @@ def main():
         ach = alg[top] / (per_launch_ms * 1e-3) / 1e9
         roofline = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
                     'frac': ach / hbm_peak, 'traffic': None, 'peak_source': peak_src}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+    except Exception:
+        traffic = {}
+    if roofline is not None and args.config == 'C2' and n_gpus == 1:
+        roofline['traffic'] = (traffic.get(top) or {}).get('bytes_per_launch')
+        roofline['traffic_source'] = 'ncu --set full capture of this kernel (profiles/r01_ncu_final.txt), per launch'
     kernels = {}
     for k, v in prof.items():
         d = dict(ms_per_step=v['ms'] / args.steps, launches_per_step=v['launches'] / args.steps,
