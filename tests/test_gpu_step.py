@@ -61,3 +61,31 @@ def test_step_vs_reference_golden(tag, fused):
             sc = group_scale(g, 'out_', 'rho' if k == 'rho' else k[0], Nm)
             assert_close(getattr(sim.fld.interp[m], k), g['out_%s_m%d' % (k, m)], 1e-9,
                          '%s %s m%d' % (tag, k, m), scale=sc)
+
+
+@pytest.mark.parametrize('shape', ['linear', 'cubic'])
+def test_step_Nm4_vs_oracle(shape):
+    """High-mode case (BASELINE configs[3]: Nm=4): 4 PIC cycles, CUDA vs the oracle."""
+    from fbpic_b200 import Simulation
+    from oracle import oracle as orc
+    from scipy.constants import c
+    np.random.seed(2)
+    Nz, Nr, Nm, zmax, rmax = 40, 20, 4, 16.e-6, 10.e-6
+    dt = zmax / Nz / c
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, p_zmin=0, p_zmax=zmax, p_rmin=0, p_rmax=rmax,
+                     p_nz=2, p_nr=2, p_nt=16, n_e=2.e24, particle_shape=shape)
+    sp = sim.ptcl[0]
+    k0 = 2 * np.pi / zmax * 2
+    g = np.exp(-(sp.x**2 + sp.y**2) / (3.e-6)**2)
+    sp.uz = 0.05 * np.sin(k0 * sp.z) * g * (1 + sp.x / 3.e-6 + (sp.x**2 - sp.y**2) / (3.e-6)**2)
+    sp.ux = 0.02 * np.cos(k0 * sp.z) * g * sp.y / 3.e-6
+    sp.inv_gamma = 1. / np.sqrt(1 + sp.ux**2 + sp.uy**2 + sp.uz**2)
+    ref = orc.OracleSim(Nz, zmax, Nr, rmax, Nm, dt, particle_shape=shape, nthreads=2)
+    ref.add_species(sp.q, sp.m, sp.x, sp.y, sp.z, sp.ux, sp.uy, sp.uz, sp.inv_gamma, sp.w)
+    sim.step(4)
+    ref.step(4)
+    for grp, names in (('E', ('Er', 'Et', 'Ez')), ('B', ('Br', 'Bt', 'Bz')), ('J', ('Jr', 'Jt', 'Jz')), ('rho', ('rho',))):
+        scale = max(np.abs(ref.interp[m][k]).max() for m in range(Nm) for k in names)
+        for m in range(Nm):
+            for k in names:
+                assert_close(getattr(sim.fld.interp[m], k), ref.interp[m][k], 1e-9, '%s m%d' % (k, m), scale=scale)
