@@ -43,7 +43,10 @@ def main():
     rank, size = dist.get_rank(), dist.get_world_size()
     nsteps = int(os.environ.get('MGPU_STEPS', '24'))
     shape = os.environ.get('MGPU_SHAPE', 'linear')
-    Nz, Nr, Nm, zmax, rmax, n_e, n_order = 64 * size, 24, 2, 12.8e-6 * size, 12.e-6, 2.e24, 8
+    # 96 physical cells per rank + 2*32 guard cells: every local box (160 cells) is smaller than the
+    # global one, so the decomposition is non-trivial already with 2 ranks
+    nzr = int(os.environ.get('MGPU_NZ_PER_RANK', '96'))
+    Nz, Nr, Nm, zmax, rmax, n_e, n_order = nzr * size, 24, 2, 0.2e-6 * nzr * size, 12.e-6, 2.e24, 8
     dt = zmax / Nz / c
     P = global_particles(Nz, Nr, zmax, rmax, n_e)
     kw = dict(n_order=n_order, particle_shape=shape, boundaries={'z': 'periodic', 'r': 'reflective'})
@@ -75,7 +78,11 @@ def main():
                 err = np.abs(glob[i] - full[i]).max()
                 if not err <= 1e-9 * scale:
                     ok = False
-                    print('MISMATCH %s m%d: err %.3e scale %.3e' % (names[i % 10], i // 10, err, scale))
+                    d = np.abs(glob[i] - full[i])
+                    rows = np.argsort(d.max(axis=1))[::-1][:6]
+                    print('MISMATCH %s m%d: err %.3e scale %.3e  worst z-rows %s (row err %s)  mean-row err %.2e'
+                          % (names[i % 10], i // 10, err, scale, rows.tolist(),
+                             ['%.1e' % v for v in d.max(axis=1)[rows]], d.max(axis=1).mean()))
         print('max particles/rank', [g[1] for g in gathered])
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, src=0)
