@@ -1,6 +1,17 @@
 """N-GPU vs 1-GPU parity of the z-sharded PIC loop (run under torchrun, one rank per GPU).
 Every rank advances its slab with NCCL guard-cell exchange + particle migration; rank 0 also
 advances the same global problem alone on its GPU; the physical regions must agree.
+
+Two passes:
+  * correct_currents=False: every operation of the cycle is local in z up to the stencil reach
+    (finite-order PSATD), so the sharded run must reproduce the single-domain one to rounding
+    (1e-9 of the field maximum).  Exercises E/B 'replace' and J 'add' guard exchanges and the
+    particle migration.
+  * correct_currents=True: the curl-free current correction is a global operation in z
+    ("`curl-free` is faster but less local", fbpic/main.py:179-182); each slab applies it on its own
+    periodic box, exactly as the reference does per MPI rank, so sharded and single-domain runs
+    differ by the truncated tail of its Green's function (~1e-5 here).  Checked to 5e-4; exercises
+    the spect2partial_interp / exchange / partial_interp2spect path of main.py:536-538.
 Prints MGPU_PARITY_OK on success."""
 import os
 import sys
@@ -38,8 +49,7 @@ def set_species(sim, P, zlo, zhi):
     return sp
 
 
-def main():
-    dist.init_process_group('gloo')
+def run_case(correct, tol):
     rank, size = dist.get_rank(), dist.get_world_size()
     nsteps = int(os.environ.get('MGPU_STEPS', '24'))
     shape = os.environ.get('MGPU_SHAPE', 'linear')
@@ -54,7 +64,7 @@ def main():
     assert sim.comm.size == size and sim.comm.n_guard > 0
     zlo, zhi = sim.comm.get_zmin_zmax(local=True, with_damp=False, with_guard=False, rank=rank)
     set_species(sim, P, zlo, zhi)
-    sim.step(nsteps)
+    sim.step(nsteps, correct_currents=correct)
     ng = sim.comm.n_guard
     names = ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'Jr', 'Jt', 'Jz', 'rho')
     loc = np.stack([getattr(sim.fld.interp[m], k)[ng:sim.fld.interp[m].Nz - ng] for m in range(Nm) for k in names])
@@ -67,7 +77,7 @@ def main():
         ref = Simulation(Nz, zmax, Nr, rmax, Nm, dt, use_all_mpi_ranks=False, n_guard=ng, **kw)
         assert ref.comm.size == 1
         set_species(ref, P, -1., 1.e9)
-        ref.step(nsteps)
+        ref.step(nsteps, correct_currents=correct)
         full = np.stack([getattr(ref.fld.interp[m], k) for m in range(Nm) for k in names])
         assert sum(g[1] for g in gathered) == ref.ptcl[0].Ntot, 'particle count not conserved'
         groups = {'E': (0, 3), 'B': (3, 6), 'J': (6, 9), 'rho': (9, 10)}
@@ -76,7 +86,7 @@ def main():
             scale = max(np.abs(full[i]).max() for i in idx)
             for i in idx:
                 err = np.abs(glob[i] - full[i]).max()
-                if not err <= 1e-9 * scale:
+                if not err <= tol * scale:
                     ok = False
                     d = np.abs(glob[i] - full[i])
                     rows = np.argsort(d.max(axis=1))[::-1][:6]
@@ -87,9 +97,16 @@ def main():
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, src=0)
     dist.barrier()
-    if rank == 0 and ok:
-        print('MGPU_PARITY_OK size=%d steps=%d' % (size, nsteps))
-    sys.exit(0 if int(flag[0]) else 1)
+    return bool(int(flag[0]))
+
+
+def main():
+    dist.init_process_group('gloo')
+    ok = run_case(False, 1e-9)
+    ok = run_case(True, 5e-4) and ok
+    if dist.get_rank() == 0 and ok:
+        print('MGPU_PARITY_OK size=%d' % dist.get_world_size())
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == '__main__':
