@@ -307,8 +307,10 @@ def main():
     peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback'
     cells = cfg['Nz'] * cfg['Nr'] * 16
     alg = {   # algorithmic bytes per launch
-        'deposit_J': 64 * Ntot_local + 3 * cfg['Nm'] * cells,
-        'deposit_rho': 32 * Ntot_local + cfg['Nm'] * cells,
+        # J: + (4+64+64-64) B/particle on the steps where the SoA permutation rides along;
+        # rho: the second position push is fused in (reads 64, writes 24 B/particle)
+        'deposit_J': (64 + 68 / max(args.sort_period, 1)) * Ntot_local + 3 * cfg['Nm'] * cells,
+        'deposit_rho': 88 * Ntot_local + cfg['Nm'] * cells,
         'gather_push': 112 * Ntot_local + 6 * cfg['Nm'] * cells,
         'permute': (8 + 128) * Ntot_local,
         'sort': (4 + 12 + 4) * Ntot_local,
