@@ -82,6 +82,8 @@ _SIGNATURES = {
                       c_double, c_double, c_int, c_double, c_double, c_int, P, P],
     'b2_shift_periodic': [P, c_int64, P, c_double, c_double, P],
     'b2_add_scalar': [P, c_int64, P, c_double, P],
+    'b2_exchange_classify': [P, c_int64, P, c_double, c_double, ctypes.POINTER(c_int64), P],
+    'b2_exchange_scatter': [P, c_int64, P, c_double, c_double, c_int, P, P, P, P, P],
     'b2_deposit_rho': [P, c_int64, P, P, P, P, c_double, c_double, c_double, c_int, c_double, c_double,
                        c_int, c_int, P, P, P, P, c_int, P],
     'b2_deposit_J': [P, c_int64, P, P, P, P, c_double, P, P, P, P, c_double, c_double, c_int, c_double,
@@ -107,6 +109,7 @@ _SIGNATURES = {
     'b2_push_eb': [P, ctypes.POINTER(SpectralMode), c_int, c_double, c_double, c_int, c_int, c_int, P],
     'b2_correct_push': [P, ctypes.POINTER(SpectralMode), c_int, c_double, c_double, c_int, c_int, c_int, P],
     'b2_damp_z': [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    'b2_shift_spect': [P, c_int, P, P, c_int, c_int, c_int, P],
     'b2_add_rows': [P, P, P, c_int, c_int, P],
     'b2_nccl_unique_id': [P],
     'b2_nccl_init': [P, P, c_int, c_int],

@@ -282,28 +282,26 @@ class BoundaryCommunicator(object):
             self.exchange_particles_aperiodic_subdomain(species, fld, time)
 
     def exchange_particles_aperiodic_subdomain(self, species, fld, time):
-        """Split the cell-sorted SoA at the guard boundaries (index ranges come from the
-        prefix sum, as remove_particles_gpu does: particle_buffer_handling.py:178-317),
-        send the two outer ranges to the neighbours and rebuild [from-left | kept | from-right]
-        (add_buffers_gpu :424-512).  Particles leaving through an open end are dropped."""
+        """Particles that left the physical part of the slab go to the z-neighbours (or are dropped
+        at an open end), the others stay; received ones are placed before (from the left) and after
+        (from the right) the kept block, new plasma injected by a moving window counts as received
+        from the right (boundary_communicator.py:750-826).  Selection rule and ordering are those of
+        the reference CPU path (remove_particles_cpu / add_buffers_cpu,
+        particle_buffer_handling.py:58-175, 424-512): left if z < zmin + n_guard*dz, right if
+        z > zmax - n_guard*dz, a stable 3-way partition of the SoA done on the device."""
         from .particles import FLOAT_ATTRS
         species._need_gpu()
         ctx = _lib.context()
         g0 = fld.interp[0]
-        Nz, Nr, ng = g0.Nz, g0.Nr, self.n_guard
-        if not species.sorted:
-            species.sort_particles(fld)
-            species.sorted = True
-        # split indices from the prefix sum (particle_buffer_handling.py:214-236)
-        iz_min = max(ng, 0)
-        iz_max = min(Nz - ng + 1, Nz)
-        ps = species.prefix_sum
-        i_min = int(ps[iz_min * (Nr + 1) - 1:iz_min * (Nr + 1)].get()[0]) if iz_min * (Nr + 1) - 1 >= 0 else 0
-        i_max = int(ps[iz_max * (Nr + 1) - 1:iz_max * (Nr + 1)].get()[0])
+        ng = self.n_guard
+        zlo = g0.zmin + ng * g0.dz
+        zhi = g0.zmax - ng * g0.dz
         N = species.Ntot
-        n_send_l = i_min if self.left_proc is not None else 0
-        n_send_r = (N - i_max) if self.right_proc is not None else 0
-        n_stay = i_max - i_min
+        counts = (ctypes.c_int64 * 3)()
+        call.b2_exchange_classify(ctx.handle, N, species.z.ptr, zlo, zhi, counts, None)
+        n_stay, n_left, n_right = int(counts[0]), int(counts[1]), int(counts[2])
+        n_send_l = n_left if self.left_proc is not None else 0
+        n_send_r = n_right if self.right_proc is not None else 0
         n_recv_l = n_recv_r = 0
         if self.size > 1:
             self.mpi_comm.init_nccl()
@@ -319,26 +317,38 @@ class BoundaryCommunicator(object):
             call.b2_nccl_group_end()
             h = cnt.get()
             n_recv_l, n_recv_r = int(h[2]), int(h[3])
+        injected = None
+        if (self.moving_win is not None) and (self.rank == self.size - 1) and species.continuous_injection:
+            # new plasma entering through the right edge (boundary_communicator.py:803-810)
+            injected = species.generate_continuously_injected_particles(time)
+            n_recv_r = injected.shape[1]
         n_new = n_recv_l + n_stay + n_recv_r
         new = species.exchange_buffers(n_new)       # spare sort buffers: no allocation in steady state
+        send_l = self._send_buffer('l', 8 * n_send_l)
+        send_r = self._send_buffer('r', 8 * n_send_r)
+        src = [getattr(species, k) for k in FLOAT_ATTRS]
+        stay = [new[k].ptr + 8 * n_recv_l for k in FLOAT_ATTRS]
+        left = [send_l.ptr + 8 * n_send_l * i for i in range(8)] if n_send_l else None
+        right = [send_r.ptr + 8 * n_send_r * i for i in range(8)] if n_send_r else None
+        if N:
+            call.b2_exchange_scatter(ctx.handle, N, species.z.ptr, zlo, zhi, 8, ptr_array(src), ptr_array(stay),
+                                     ptr_array(left) if left else None, ptr_array(right) if right else None, None)
         if self.size > 1:
             call.b2_nccl_group_start()
-            for k in FLOAT_ATTRS:
-                old = getattr(species, k)
+            for i, k in enumerate(FLOAT_ATTRS):
                 if self.left_proc is not None and n_send_l:
-                    call.b2_nccl_send(ctx.handle, old.ptr, 8 * n_send_l, self.left_proc, None)
+                    call.b2_nccl_send(ctx.handle, left[i], 8 * n_send_l, self.left_proc, None)
                 if self.right_proc is not None and n_send_r:
-                    call.b2_nccl_send(ctx.handle, old.ptr + 8 * i_max, 8 * n_send_r, self.right_proc, None)
-                if self.right_proc is not None and n_recv_r:
+                    call.b2_nccl_send(ctx.handle, right[i], 8 * n_send_r, self.right_proc, None)
+                if self.right_proc is not None and n_recv_r and injected is None:
                     call.b2_nccl_recv(ctx.handle, new[k].ptr + 8 * (n_recv_l + n_stay), 8 * n_recv_r,
                                       self.right_proc, None)
                 if self.left_proc is not None and n_recv_l:
                     call.b2_nccl_recv(ctx.handle, new[k].ptr, 8 * n_recv_l, self.left_proc, None)
             call.b2_nccl_group_end()
-        for k in FLOAT_ATTRS:
-            if n_stay:
-                call.b2_memcpy_d2d(new[k].ptr + 8 * n_recv_l, getattr(species, k).ptr + 8 * i_min,
-                                   8 * n_stay, ctx.stream)
+        if injected is not None and n_recv_r:
+            for i, k in enumerate(FLOAT_ATTRS):
+                new[k].view((n_recv_r,), byte_offset=8 * (n_recv_l + n_stay)).set(injected[i])
         # periodic images: shift z by the box length (boundary_communicator.py:815-821)
         Ltot = self._Nz_global_domain * self.dz
         if self.right_proc == 0 and n_recv_r:
@@ -346,6 +356,14 @@ class BoundaryCommunicator(object):
         if self.left_proc == self.size - 1 and n_recv_l:
             self._shift_z(new['z'], 0, n_recv_l, -Ltot)
         species.resize_device_arrays(new, n_new)
+
+    def _send_buffer(self, side, n_doubles):
+        """Grow-only device staging buffer for the particles leaving through one face."""
+        buf = self._halo_buf.get(('ptcl', side))
+        if buf is None or buf.size < max(n_doubles, 1):
+            buf = DeviceArray(max(int(n_doubles * 1.5), 1 << 16), np.float64)
+            self._halo_buf[('ptcl', side)] = buf
+        return buf
 
     @staticmethod
     def _shift_z(z, start, count, dz_shift):
@@ -376,4 +394,15 @@ class BoundaryCommunicator(object):
         raise NotImplementedError('radial PML is out of scope of this build')
 
     def move_grids(self, fld, ptcl, dt, time):
-        raise NotImplementedError('moving window: SURVEY 8(f) rank 1, planned next')
+        """boundary_communicator.py:531-553"""
+        self.moving_win.move_grids(fld, ptcl, self, time)
+
+    def bcast_int(self, value):
+        """Rank 0's integer on every rank (the n_move broadcast of moving_window.py:97)."""
+        if self.size == 1:
+            return value
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([0 if value is None else int(value)], dtype=torch.int64)
+        dist.broadcast(t, src=0)
+        return int(t[0])

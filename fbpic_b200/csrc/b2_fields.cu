@@ -199,6 +199,20 @@ __global__ void k_damp_z(B2Ptrs A, int na, const double *__restrict__ damp, int 
         if (right) { const size_t o = (size_t)(Nz - 1 - id) * Nr + ir; a[o] = rmul(d, a[o]); }
     }
 }
+// moving window: F[iz,:] *= shift[iz]^n_move (shift = exp(i kz dz)), power by repeated product as
+// shift_spect_array_gpu does (fbpic/boundaries/moving_window.py:205-278)
+__global__ void k_shift_spect(B2Ptrs A, int na, const double2 *__restrict__ shift, int n_move, int Nz, int Nr) {
+    B2_2D_INDEX
+    const double2 sft = shift[iz];
+    double2 pw = make_double2(1., 0.);
+    const int n = n_move < 0 ? -n_move : n_move;
+    for (int i = 0; i < n; ++i) pw = cmul(pw, sft);
+    if (n_move < 0) pw.y = -pw.y;
+    for (int k = 0; k < na; ++k) {
+        double2 *a = (double2 *)A.p[k];
+        a[o] = cmul(a[o], pw);
+    }
+}
 __global__ void k_add(double2 *__restrict__ dst, const double2 *__restrict__ src, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) dst[i] = cadd(dst[i], src[i]);
@@ -322,6 +336,18 @@ int b2_damp_z(b2_ctx *ctx, int na, void *const *arrays, const double *damp, int 
     B2Ptrs A;
     for (int k = 0; k < na; ++k) A.p[k] = arrays[k];
     k_damp_z<<<grid2d(nd, Nr, BLK), BLK, 0, b2_stream_of(ctx, stream)>>>(A, na, damp, nd, left, right, Nz, Nr);
+    B2_LAUNCHED();
+    return 0;
+}
+
+int b2_shift_spect(b2_ctx *ctx, int na, void *const *arrays, const void *shift, int n_move, int Nz, int Nr,
+                   void *stream) {
+    if (na > B2_MAX_ARRAYS) return b2_fail(-3, "too many arrays", __FILE__, __LINE__);
+    if (n_move == 0) return 0;
+    B2Ptrs A;
+    for (int k = 0; k < na; ++k) A.p[k] = arrays[k];
+    B2Prof prof_(B2P_ELEMENTWISE, b2_stream_of(ctx, stream));
+    k_shift_spect<<<grid2d(Nz, Nr, BLK), BLK, 0, b2_stream_of(ctx, stream)>>>(A, na, (const double2 *)shift, n_move, Nz, Nr);
     B2_LAUNCHED();
     return 0;
 }

@@ -2,6 +2,7 @@
 // Vay push, position push and the fused gather+push kernel.
 #include "b2_common.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <climits>
 
 static inline unsigned grid1d(int64_t n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
@@ -468,6 +469,41 @@ __global__ void k_add_scalar(int64_t n, double *__restrict__ v, double a) {
 }
 
 // =====================================================================================
+// particle exchange: 3-way stable partition by z (remove_particles_cpu semantics,
+// fbpic/boundaries/particle_buffer_handling.py:58-175: left if z < zlo, right if z > zhi, the rest
+// stays, relative order preserved)
+// =====================================================================================
+__global__ void k_classify_z(int64_t n, const double *__restrict__ z, double zlo, double zhi,
+                             int32_t *__restrict__ f_stay, int32_t *__restrict__ f_left,
+                             int32_t *__restrict__ f_right) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double zi = z[i];
+    const int l = zi < zlo, r = zi > zhi;
+    f_left[i] = l; f_right[i] = r; f_stay[i] = !(l || r);
+}
+struct B2Part {
+    const double *src[B2_MAX_ARRAYS];
+    double *stay[B2_MAX_ARRAYS], *left[B2_MAX_ARRAYS], *right[B2_MAX_ARRAYS];
+};
+// after the exclusive scans p_* hold the destination index inside each class; the class of i is
+// recovered from the scans themselves (p[i+1] - p[i], or the known total for the last element)
+__global__ void k_partition_scatter(int64_t n, const int32_t *__restrict__ p_stay,
+                                    const int32_t *__restrict__ p_left, const int32_t *__restrict__ p_right,
+                                    const double *__restrict__ z, double zlo, double zhi, B2Part a, int n_arrays) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double zi = z[i];
+    const int l = zi < zlo, r = zi > zhi;
+    for (int k = 0; k < n_arrays; ++k) {
+        const double v = a.src[k][i];
+        if (l) { if (a.left[k]) a.left[k][p_left[i]] = v; }
+        else if (r) { if (a.right[k]) a.right[k][p_right[i]] = v; }
+        else a.stay[k][p_stay[i]] = v;
+    }
+}
+
+// =====================================================================================
 // C ABI
 // =====================================================================================
 
@@ -633,6 +669,57 @@ int b2_push_x_key(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, const
     B2Prof prof_(B2P_PUSH, b2_stream_of(ctx, stream));
     k_push_x_key<<<grid1d(n, 256), 256, 0, b2_stream_of(ctx, stream)>>>(n, x, y, z, ux, uy, uz, inv_gamma,
         B2_C_LIGHT * dt, wrap, wrap_zmin, wrap_zmax, invdz, key_zmin, Nz, invdr, rmin, Nr, cell_idx);
+    B2_LAUNCHED();
+    return 0;
+}
+
+int b2_exchange_classify(b2_ctx *ctx, int64_t n, const double *z, double zlo, double zhi, int64_t *h_counts3,
+                         void *stream) {
+    h_counts3[0] = h_counts3[1] = h_counts3[2] = 0;
+    if (n <= 0) return 0;
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    // scratch 1: [f_stay | f_left | f_right | cub temp]; the flags are scanned in place
+    const size_t na = ((size_t)(n + 1) * sizeof(int32_t) + 255) & ~(size_t)255;
+    size_t temp_bytes = 0;
+    int32_t *nul = nullptr;
+    cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, nul, nul, (int)n, s);
+    void *base;
+    int rc = b2_scratch(ctx, 1, 3 * na + temp_bytes + 64, &base);
+    if (rc) return rc;
+    int32_t *f[3] = {(int32_t *)base, (int32_t *)((char *)base + na), (int32_t *)((char *)base + 2 * na)};
+    void *temp = (char *)base + 3 * na;
+    int32_t last_flag[3], last_pos[3];
+    k_classify_z<<<grid1d(n, 256), 256, 0, s>>>(n, z, zlo, zhi, f[0], f[1], f[2]);
+    B2_LAUNCHED();
+    for (int k = 0; k < 3; ++k)
+        B2_CUDA(cudaMemcpyAsync(&last_flag[k], f[k] + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    for (int k = 0; k < 3; ++k) {
+        B2_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, f[k], f[k], (int)n, s));
+        B2_CUDA(cudaMemcpyAsync(&last_pos[k], f[k] + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    g_b2_launches.fetch_add(3);
+    B2_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < 3; ++k) h_counts3[k] = (int64_t)last_pos[k] + last_flag[k];
+    ctx->part_n = n;
+    return 0;
+}
+
+int b2_exchange_scatter(b2_ctx *ctx, int64_t n, const double *z, double zlo, double zhi, int n_arrays,
+                        const double *const *src, double *const *stay, double *const *left, double *const *right,
+                        void *stream) {
+    if (n <= 0) return 0;
+    if (ctx->part_n != n || !ctx->scratch[1])
+        return b2_fail(-4, "b2_exchange_scatter: call b2_exchange_classify first", __FILE__, __LINE__);
+    if (n_arrays > B2_MAX_ARRAYS) return b2_fail(-3, "too many arrays", __FILE__, __LINE__);
+    const size_t na = ((size_t)(n + 1) * sizeof(int32_t) + 255) & ~(size_t)255;
+    char *base = (char *)ctx->scratch[1];
+    B2Part a;
+    for (int k = 0; k < n_arrays; ++k) {
+        a.src[k] = src[k]; a.stay[k] = stay[k];
+        a.left[k] = left ? left[k] : nullptr; a.right[k] = right ? right[k] : nullptr;
+    }
+    k_partition_scatter<<<grid1d(n, 256), 256, 0, b2_stream_of(ctx, stream)>>>(
+        n, (const int32_t *)base, (const int32_t *)(base + na), (const int32_t *)(base + 2 * na), z, zlo, zhi, a, n_arrays);
     B2_LAUNCHED();
     return 0;
 }

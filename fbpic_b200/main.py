@@ -7,7 +7,7 @@ Hot-path scope: gather / push / deposit / sort, z-FFT + Hankel GEMM,
 current correction + PSATD push, z guard-cell exchange and particle migration.
 Out of scope and therefore rejected loudly: PML (`boundaries['r']='open'`),
 cross-deposition, laser antennas, external fields, diagnostics, checkpoints,
-ionization, moving window (planned next).
+ionization.  The moving window with continuous injection is built.
 """
 import numpy as np
 from scipy.constants import m_e, m_p, e, c
@@ -105,6 +105,12 @@ class Simulation(object):
         if self.external_fields or self.diags or self.checkpoints or self.laser_antennas or self.mirrors:
             raise NotImplementedError('external fields, diagnostics, checkpoints, antennas and mirrors '
                                       'are outside the hot path built here')
+        if self.comm.moving_win is not None:          # main.py:390-395
+            for species in self.ptcl:
+                if species.continuous_injection and species.injector is not None:
+                    z_host = species.z.get() if species.data_is_on_gpu else species.z
+                    species.injector.initialize_injection_positions(
+                        self.comm, self.comm.moving_win.v, z_host, self.dt)
         single = (self.comm.size == 1)
         periodic_single = single and self.comm.n_guard == 0
         fuse_gp = self.fused and move_positions and move_momenta
@@ -312,7 +318,9 @@ class Simulation(object):
         return sp
 
     def set_moving_window(self, v=c, **kw):
-        raise NotImplementedError('moving window: SURVEY 8(f) rank 1, planned next')
+        """fbpic/main.py:1004-1032 (the deprecated keyword arguments are accepted and ignored)."""
+        from .moving_window import MovingWindow
+        self.comm.moving_win = MovingWindow(self.comm, self.dt, v, self.time)
 
 
 def adapt_to_grid(x, p_xmin, p_xmax, p_nx, ncells_empty=0):

@@ -70,6 +70,66 @@ def generate_evenly_spaced(Npz, zmin, zmax, Npr, rmin, rmax, Nptheta, n, dens_fu
     return Ntot, x, y, z, ux, uy, uz, inv_gamma, w
 
 
+class ContinuousInjector(object):
+    """Book-keeping of the plasma that enters through the right edge of a moving window
+    (fbpic/particles/injection/continuous_injection.py:13-200); host side, runs once per particle
+    exchange."""
+
+    def __init__(self, Npz, zmin, zmax, dz_particles, Npr, rmin, rmax, Nptheta, n, dens_func,
+                 ux_m, uy_m, uz_m, ux_th, uy_th, uz_th):
+        self.Npr, self.rmin, self.rmax, self.Nptheta, self.n = Npr, rmin, rmax, Nptheta, n
+        self.dens_func = dens_func
+        self.ux_m, self.uy_m, self.uz_m = ux_m, uy_m, uz_m
+        self.ux_th, self.uy_th, self.uz_th = ux_th, uy_th, uz_th
+        self.dz_particles = (zmax - zmin) / Npz if Npz != 0 else dz_particles
+        c_light = 299792458.
+        self.v_end_plasma = c_light * uz_m / np.sqrt(1 + ux_m**2 + uy_m**2 + uz_m**2)
+        self.nz_inject = self.z_inject = self.z_end_plasma = None
+
+    def initialize_injection_positions(self, comm, v_moving_window, species_z, dt):
+        if comm.rank != comm.size - 1 or self.z_inject is not None:
+            return
+        _, zmax_damp = comm.get_zmin_zmax(local=False, with_damp=True, with_guard=False)
+        self.z_inject = zmax_damp + (3 - comm.n_inject) * comm.dz \
+            + comm.exchange_period * dt * (v_moving_window - self.v_end_plasma)
+        self.nz_inject = 0
+        if len(species_z) > 0:
+            self.z_end_plasma = species_z.max() + 0.5 * self.dz_particles
+        else:
+            _, self.z_end_plasma = comm.get_zmin_zmax(local=False, with_damp=False, with_guard=False)
+        if self.dz_particles is None:
+            raise ValueError('The simulation uses continuous injection of particles, but was unable to\n'
+                             'calculate the spacing between particles: pass `dz_particles`.')
+
+    def reset_injection_positions(self):
+        self.nz_inject = self.z_inject = self.z_end_plasma = None
+
+    def increment_injection_positions(self, v_moving_window, duration):
+        self.z_inject += v_moving_window * duration
+        self.z_end_plasma += self.v_end_plasma * duration
+        nz_new = int((self.z_inject - self.z_end_plasma) / self.dz_particles)
+        self.nz_inject += nz_new
+        self.z_end_plasma += nz_new * self.dz_particles
+
+    def generate_particles(self, time):
+        dens_func = None
+        if self.dens_func is not None:
+            user, v = self.dens_func, self.v_end_plasma
+            if _dens_func_args(user) == ['z', 'r']:
+                def dens_func(z, r):
+                    return user(z - v * time, r)
+            else:
+                def dens_func(x, y, z):
+                    return user(x, y, z - v * time)
+        zmax = self.z_end_plasma
+        zmin = self.z_end_plasma - self.nz_inject * self.dz_particles
+        out = generate_evenly_spaced(self.nz_inject, zmin, zmax, self.Npr, self.rmin, self.rmax, self.Nptheta,
+                                     self.n, dens_func, self.ux_m, self.uy_m, self.uz_m,
+                                     self.ux_th, self.uy_th, self.uz_th)
+        self.nz_inject = 0
+        return out
+
+
 class Particles(object):
     """One species.  At the end/start of a PIC cycle the momenta are half a step
     behind the positions (particles.py:62-63)."""
@@ -94,7 +154,9 @@ class Particles(object):
         for k in FIELD_ATTRS:
             setattr(self, k, np.zeros(Ntot))
         self.continuous_injection = continuous_injection
-        self.injector = None            # moving-window injection: SURVEY 8f rank 1 (next)
+        self.injector = ContinuousInjector(Npz, zmin, zmax, dz_particles, Npr, rmin, rmax, Nptheta, n,
+                                           dens_func, ux_m, uy_m, uz_m, ux_th, uy_th, uz_th) \
+            if continuous_injection else None
         self.tracker = None
         self.ionizer = None
         self.compton_scatterer = None
@@ -192,6 +254,13 @@ class Particles(object):
         if n_new <= self._capacity:
             return {k: self.sorting_buffers[i].view((n_new,)) for i, k in enumerate(FLOAT_ATTRS)}
         return {k: DeviceArray(n_new, np.float64) for k in FLOAT_ATTRS}
+
+    def generate_continuously_injected_particles(self, time):
+        """Float buffer (8, N) of the particles entering through the right edge
+        (particles.py:335-374; no tracker / ionizer quantities in this build)."""
+        assert self.continuous_injection is True
+        Ntot, x, y, z, ux, uy, uz, inv_gamma, w = self.injector.generate_particles(time)
+        return np.ascontiguousarray(np.stack((x, y, z, ux, uy, uz, inv_gamma, w)))
 
     def _need_gpu(self):
         if not self.data_is_on_gpu:

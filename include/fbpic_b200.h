@@ -122,6 +122,15 @@ int b2_push_x_key(b2_ctx *ctx, int64_t n, double *d_x, double *d_y, double *d_z,
                   double invdz, double key_zmin, int Nz, double invdr, double rmin, int Nr,
                   int32_t *d_cell_idx, void *stream);
 int b2_shift_periodic(b2_ctx *ctx, int64_t n, double *d_z, double zmin, double zmax, void *stream);
+/* particle exchange (remove_particles_cpu / add_buffers, fbpic/boundaries/particle_buffer_handling.py:
+ * 58-175, 424-512): stable 3-way partition of the SoA by z -- left if z < zlo, right if z > zhi.
+ * classify returns the class sizes {stay, left, right} on the host (synchronises); scatter then
+ * writes every attribute to the three destinations (left/right may be NULL: particles dropped). */
+int b2_exchange_classify(b2_ctx *ctx, int64_t n, const double *d_z, double zlo, double zhi,
+                         int64_t *h_counts3, void *stream);
+int b2_exchange_scatter(b2_ctx *ctx, int64_t n, const double *d_z, double zlo, double zhi, int n_arrays,
+                        const double *const *d_src, double *const *d_stay, double *const *d_left,
+                        double *const *d_right, void *stream);
 /* v[i] += value : z-shift of the periodic images received across the ring closure
  * (boundary_communicator.py:815-821) */
 int b2_add_scalar(b2_ctx *ctx, int64_t n, double *d_v, double value, void *stream);
@@ -242,6 +251,10 @@ int b2_correct_push(b2_ctx *ctx, const b2_spectral_mode *mode, int comoving, dou
  *      (boundary_communicator.py:674-707, mpi4py Isend/Irecv) -> NCCL send/recv ---- */
 int b2_damp_z(b2_ctx *ctx, int n_arrays, void *const *d_arrays, const double *d_damp, int nd,
               int left, int right, int Nz, int Nr, void *stream);
+/* moving window: F[iz,:] *= shift[iz]^n_move for every listed spectral array
+ * (shift_spect_array_gpu, fbpic/boundaries/moving_window.py:244-278); d_shift: complex128[Nz] */
+int b2_shift_spect(b2_ctx *ctx, int n_arrays, void *const *d_arrays, const void *d_shift, int n_move,
+                   int Nz, int Nr, void *stream);
 int b2_add_rows(b2_ctx *ctx, void *d_dst, const void *d_src, int nrows, int Nr, void *stream);
 int b2_nccl_unique_id(void *id128);                       /* 128-byte ncclUniqueId */
 int b2_nccl_init(b2_ctx *ctx, const void *id128, int rank, int size);

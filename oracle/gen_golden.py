@@ -204,8 +204,43 @@ def gen_step(tag, shape, Nm, n_order, v_comoving, use_galilean, nsteps=3, ions=F
     save('step_' + tag, **out)
 
 
+def window_dens(z, r):
+    """density ramp used by the moving-window fixture (restated identically in tests/test_gpu_step.py)"""
+    return np.clip((z - 5.e-6) / 3.e-6, 0., 1.)
+
+
+def gen_window(nsteps=26):
+    """Open-z box with a moving window (v = c) and continuous plasma injection."""
+    np.random.seed(5)
+    Nz, Nr, Nm, zmax, rmax = 40, 12, 2, 20.e-6, 8.e-6
+    dt = zmax / Nz / c
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, p_zmin=5.e-6, p_zmax=30.e-6, p_rmin=0, p_rmax=6.e-6,
+                     p_nz=2, p_nr=2, p_nt=4, n_e=1.e24, dens_func=window_dens, n_order=-1,
+                     n_guard=16, n_damp={'z': 16, 'r': 32}, verbose_level=0,
+                     boundaries={'z': 'open', 'r': 'reflective'})
+    sim.set_moving_window(v=c)
+    g1 = sim.fld.interp[1]
+    zz, rr = np.meshgrid(g1.z, g1.r, indexing='ij')
+    prof = 2.e11 * np.exp(-(zz - 12.e-6)**2 / (3.e-6)**2) * np.exp(-rr**2 / (3.e-6)**2) * np.cos(2 * np.pi * (zz - 12.e-6) / 2.e-6)
+    g1.Er[:, :], g1.Et[:, :] = 0.5 * prof, -0.5j * prof
+    g1.Br[:, :], g1.Bt[:, :] = 0.5j * prof / c, 0.5 * prof / c
+    out = dict(Nz=Nz, Nr=Nr, Nm=Nm, zmax=zmax, rmax=rmax, dt=dt, nsteps=nsteps, Nz_local=sim.fld.interp[0].Nz)
+    sp = sim.ptcl[0]
+    out.update({'s0_in_%s' % k: v for k, v in ptcl_arrays(sp).items()})
+    out.update({'in_' + k: v for k, v in field_arrays(sim, ('E', 'B')).items()})
+    np.random.seed(7)
+    sim.step(nsteps, show_progress=False)
+    out.update({'s0_out_%s' % k: v for k, v in ptcl_arrays(sp).items()})
+    out.update({'out_' + k: v for k, v in field_arrays(sim).items()})
+    out['zmin_end'] = sim.fld.interp[0].zmin
+    save('step_moving_window', **out)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    if '--only-window' in sys.argv:
+        gen_window()
+        sys.exit(0)
     if '--only-open' in sys.argv:
         gen_step('linear_open', 'linear', 2, -1, None, False, nsteps=5, open_z=True)
         sys.exit(0)
@@ -219,3 +254,4 @@ if __name__ == '__main__':
     gen_step('linear_galilean', 'linear', 2, 16, -0.995 * c, True, ions=True)
     gen_step('linear_comoving', 'linear', 2, 16, -0.995 * c, False, ions=True)
     gen_step('linear_open', 'linear', 2, -1, None, False, nsteps=5, open_z=True)
+    gen_window()

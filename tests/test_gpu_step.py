@@ -89,3 +89,50 @@ def test_step_Nm4_vs_oracle(shape):
         for m in range(Nm):
             for k in names:
                 assert_close(getattr(sim.fld.interp[m], k), ref.interp[m][k], 1e-9, '%s m%d' % (k, m), scale=scale)
+
+
+def _window_dens(z, r):
+    return np.clip((z - 5.e-6) / 3.e-6, 0., 1.)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+def test_moving_window_vs_reference_golden(fused):
+    """Open-z box, moving window at c, continuous plasma injection, 26 cycles (the window moves and
+    injects several times): grids shifted in spectral space, particles dropped at the left edge and
+    injected at the right one -- against the unmodified reference (fbpic/boundaries/moving_window.py,
+    particles/injection/continuous_injection.py) run on the same inputs."""
+    from fbpic_b200 import Simulation
+    from scipy.constants import c
+    g = load_golden('step_moving_window')
+    Nz, Nr, Nm = int(g['Nz']), int(g['Nr']), int(g['Nm'])
+    np.random.seed(5)       # the azimuthal offsets of the particle loader come from np.random (gen_golden.py)
+    sim = Simulation(Nz, float(g['zmax']), Nr, float(g['rmax']), Nm, float(g['dt']),
+                     p_zmin=5.e-6, p_zmax=30.e-6, p_rmin=0, p_rmax=6.e-6, p_nz=2, p_nr=2, p_nt=4, n_e=1.e24,
+                     dens_func=_window_dens, n_order=-1, n_guard=16, n_damp={'z': 16, 'r': 32},
+                     boundaries={'z': 'open', 'r': 'reflective'}, fused=fused)
+    sim.set_moving_window(v=c)
+    assert sim.fld.interp[0].Nz == int(g['Nz_local'])
+    sp = sim.ptcl[0]
+    # the initial plasma comes out of the same generator as the reference's
+    assert sp.Ntot == len(g['s0_in_x'])
+    for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w'):
+        assert_close(getattr(sp, k), g['s0_in_' + k], 1e-14, 'initial ' + k)
+        setattr(sp, k, g['s0_in_' + k].copy())
+    for m in range(Nm):
+        for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz'):
+            getattr(sim.fld.interp[m], k)[:, :] = g['in_%s_m%d' % (k, m)]
+    np.random.seed(7)       # ... and so do those of the continuously injected plasma
+    sim.step(int(g['nsteps']))
+    assert abs(sim.fld.interp[0].zmin - float(g['zmin_end'])) <= 1e-12 * abs(float(g['zmax']))
+    names = ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w')
+    ref = np.stack([g['s0_out_' + k] for k in names])
+    got = np.stack([getattr(sp, k) for k in names])
+    assert got.shape == ref.shape, 'particle count after drop + injection: %s vs %s' % (got.shape, ref.shape)
+    ro, go = np.lexsort((ref[2], ref[1], ref[0], ref[7])), np.lexsort((got[2], got[1], got[0], got[7]))
+    for j, k in enumerate(names):
+        assert_close(got[j][go], ref[j][ro], 1e-9, 'window %s' % k)
+    for m in range(Nm):
+        for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'Jr', 'Jt', 'Jz', 'rho'):
+            sc = group_scale(g, 'out_', 'rho' if k == 'rho' else k[0], Nm)
+            assert_close(getattr(sim.fld.interp[m], k), g['out_%s_m%d' % (k, m)], 1e-9,
+                         'window %s m%d' % (k, m), scale=sc)
