@@ -100,10 +100,99 @@ def run_case(correct, tol):
     return bool(int(flag[0]))
 
 
+def window_dens(z, r):
+    return np.clip((z - 4.e-6) / 3.e-6, 0., 1.)
+
+
+def run_window_case(tol):
+    """Open z, moving window at c, plasma injected at the right edge by the last rank, particles
+    dropped at the left edge by rank 0, migration in between (correct_currents=False: local in z)."""
+    rank, size = dist.get_rank(), dist.get_world_size()
+    nsteps = int(os.environ.get('MGPU_WINDOW_STEPS', '40'))
+    nzr = int(os.environ.get('MGPU_NZ_PER_RANK', '96'))
+    Nz, Nr, Nm, rmax, n_order = nzr * size, 16, 2, 8.e-6, 8
+    zmax = 0.25e-6 * Nz
+    dt = zmax / Nz / c
+    kw = dict(p_zmin=4.e-6, p_zmax=1., p_rmin=0, p_rmax=6.e-6, p_nz=2, p_nr=2, p_nt=4, n_e=1.e24,
+              dens_func=window_dens, n_order=n_order, n_damp={'z': 32, 'r': 32},
+              boundaries={'z': 'open', 'r': 'reflective'})
+
+    def launch(sim):
+        sim.set_moving_window(v=c)
+        g1 = sim.fld.interp[1]
+        zz, rr = np.meshgrid(g1.z, g1.r, indexing='ij')
+        z0 = 0.6 * zmax
+        prof = 3.e11 * np.exp(-(zz - z0)**2 / (2.e-6)**2) * np.exp(-rr**2 / (3.e-6)**2) * np.cos(2 * np.pi * (zz - z0) / 1.e-6)
+        g1.Er[:, :], g1.Et[:, :] = 0.5 * prof, -0.5j * prof
+        g1.Br[:, :], g1.Bt[:, :] = 0.5j * prof / c, 0.5 * prof / c
+        np.random.seed(3)
+        sim.step(nsteps, correct_currents=False)
+
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, **kw)
+    assert sim.comm.size == size
+    ng = sim.comm.n_guard
+    # the loader draws its azimuthal offsets from np.random: build the global plasma once (host
+    # only, same seed on every rank) and give every slab the particles of its physical range
+    np.random.seed(21)
+    ref = Simulation(Nz, zmax, Nr, rmax, Nm, dt, use_all_mpi_ranks=False, n_guard=ng, **kw)
+    zlo, zhi = sim.comm.get_zmin_zmax(local=True, with_damp=False, with_guard=False, rank=rank)
+    sp, rp = sim.ptcl[0], ref.ptcl[0]
+    sel = (rp.z >= zlo) & (rp.z < zhi)
+    for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w'):
+        setattr(sp, k, getattr(rp, k)[sel].copy())
+    sp.Ntot = int(sel.sum())
+    for k in ('Ex', 'Ey', 'Ez', 'Bx', 'By', 'Bz'):
+        setattr(sp, k, np.zeros(sp.Ntot))
+    launch(sim)
+    names = ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'rho')
+    loc = np.stack([getattr(sim.fld.interp[m], k)[ng:sim.fld.interp[m].Nz - ng] for m in range(Nm) for k in names])
+    sp = sim.ptcl[0]
+    part = np.stack([getattr(sp, k) for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'w')])
+    gathered = [None] * size
+    dist.all_gather_object(gathered, (loc, part))
+    ok = True
+    if rank == 0:
+        glob = np.concatenate([g[0] for g in gathered], axis=1)
+        launch(ref)
+        full = np.stack([getattr(ref.fld.interp[m], k)[ng:ref.fld.interp[m].Nz - ng] for m in range(Nm) for k in names])
+        assert abs(ref.fld.interp[0].zmin - sim.fld.interp[0].zmin) < 1e-12
+        for gname, (g0, g1) in {'E': (0, 3), 'B': (3, 6), 'rho': (6, 7)}.items():
+            idx = [m * 7 + j for m in range(Nm) for j in range(g0, g1)]
+            scale = max(np.abs(full[i]).max() for i in idx)
+            for i in idx:
+                err = np.abs(glob[i] - full[i]).max()
+                if not err <= tol * scale:
+                    ok = False
+                    print('WINDOW MISMATCH %s m%d: err %.3e scale %.3e' % (names[i % 7], i // 7, err, scale))
+        allp = np.concatenate([g[1] for g in gathered], axis=1)
+        refp = np.stack([getattr(ref.ptcl[0], k) for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'w')])
+        print('window: particles/rank', [g[1].shape[1] for g in gathered], 'single', refp.shape[1])
+        if allp.shape != refp.shape:
+            ok = False
+            print('WINDOW MISMATCH particle count %s vs %s' % (allp.shape, refp.shape))
+        else:
+            # particle sets compared by nearest neighbour in normalised phase space (sorting on
+            # the coordinates is not stable against rounding noise between equal keys)
+            from scipy.spatial import cKDTree
+            sc = np.abs(refp).max(axis=1, keepdims=True) + 1e-300
+            d, j = cKDTree((refp / sc).T).query((allp / sc).T)
+            if len(np.unique(j)) != len(j) or d.max() > 1e-7:
+                ok = False
+                print('WINDOW MISMATCH particles: max phase-space distance %.3e, %d unmatched'
+                      % (d.max(), len(j) - len(np.unique(j))))
+            else:
+                print('window: particle sets agree, max normalised distance %.2e' % d.max())
+    flag = torch.tensor([1 if ok else 0])
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    return bool(int(flag[0]))
+
+
 def main():
     dist.init_process_group('gloo')
     ok = run_case(False, 1e-9)
     ok = run_case(True, 5e-4) and ok
+    ok = run_window_case(1e-8) and ok
     if dist.get_rank() == 0 and ok:
         print('MGPU_PARITY_OK size=%d' % dist.get_world_size())
     sys.exit(0 if ok else 1)
