@@ -57,35 +57,33 @@ def laser_fields(z, r, a0=4., w0=5.e-6, ctau=16.e-15 * c, z0=None, lambda0=0.8e-
     return Er1, Et1, Br1, Bt1
 
 
-def build_b200_sim(cfg, n_gpus, fused=True, seed=0, sort_period=1):
+def build_b200_sim(cfg, n_gpus, fused=True, seed=0, sort_period=1, full_slab=False):
     from fbpic_b200 import Simulation
     np.random.seed(seed + int(os.environ.get('RANK', '0')))
-    Nz_g = cfg['Nz'] * n_gpus
-    zmax = Nz_g * cfg['dz']
     dt = cfg['dz'] / c
     p_nz, p_nr, p_nt = cfg['ppc']
     n_order = -1 if n_gpus == 1 else 32
     n_guard = None
+    nz_phys = cfg['Nz']
     if n_gpus > 1:
-        # guard width: the stencil reach of n_order=32 (boundary_communicator.py:243-250), rounded up
-        # until the local grid length Nz/N + 2*n_guard has no prime factor above 13 (cuFFT otherwise
-        # runs Bluestein: 4096+2*63 = 2*2111, 13x slower).  A wider guard region is always valid.
+        # z-slabs: every rank works on a LOCAL periodic box = physical cells + 2*n_guard guard cells and
+        # FFTs that length.  Guard width = stencil reach of n_order=32 (boundary_communicator.py:243-250),
+        # rounded up to a multiple of 8.  Default: the local box keeps the single-GPU length cfg['Nz']
+        # (4096 = one-kernel cuFFT; 4096 physical + 2*64 = 4224 costs 2.5x per transform), i.e. each
+        # GPU owns cfg['Nz'] - 2*n_guard physical cells; --full-slab keeps cfg['Nz'] physical cells.
         from fbpic_b200.host_tables import stencil_reach
-        n_guard = stencil_reach(Nz_g, cfg['dz'], cfg['dz'], n_order, None, False) + 1
-
-        def smooth(n):
-            for p in (2, 3, 5, 7, 11, 13):
-                while n % p == 0:
-                    n //= p
-            return n == 1
-        while not smooth(cfg['Nz'] + 2 * n_guard):
-            n_guard += 1
+        n_guard = stencil_reach(cfg['Nz'] * n_gpus, cfg['dz'], cfg['dz'], n_order, None, False) + 1
+        n_guard = (n_guard + 7) // 8 * 8
+        if not full_slab:
+            nz_phys = cfg['Nz'] - 2 * n_guard
+    Nz_g = nz_phys * n_gpus
+    zmax = Nz_g * cfg['dz']
     sim = Simulation(Nz_g, zmax, cfg['Nr'], cfg['rmax'], cfg['Nm'], dt, p_zmin=0., p_zmax=zmax,
                      p_rmin=0., p_rmax=cfg['rmax'], p_nz=p_nz, p_nr=p_nr, p_nt=p_nt, n_e=cfg['n_e'],
                      n_order=n_order, n_guard=n_guard, boundaries={'z': 'periodic', 'r': 'reflective'},
                      fused=fused, sort_period=sort_period)
     g1 = sim.fld.interp[1]
-    Er1, Et1, Br1, Bt1 = laser_fields(g1.z, g1.r, z0=0.5 * zmax if n_gpus == 1 else 0.5 * cfg['Nz'] * cfg['dz'])
+    Er1, Et1, Br1, Bt1 = laser_fields(g1.z, g1.r, z0=0.5 * zmax if n_gpus == 1 else 0.5 * nz_phys * cfg['dz'])
     g1.Er[:, :], g1.Et[:, :], g1.Br[:, :], g1.Bt[:, :] = Er1, Et1, Br1, Bt1
     return sim
 
@@ -185,6 +183,9 @@ def main():
     ap.add_argument('--sort-period', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--full-slab', action='store_true',
+                    help='N>1: Nz physical cells per GPU plus guards (local FFT length Nz+2*n_guard) instead '
+                         'of a local box of Nz cells including the guards')
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get('RANK', '0'))
@@ -228,7 +229,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('gloo')
     ctx = _lib.context()
-    sim = build_b200_sim(cfg, n_gpus, fused=not args.no_fused, sort_period=args.sort_period)
+    sim = build_b200_sim(cfg, n_gpus, fused=not args.no_fused, sort_period=args.sort_period,
+                         full_slab=args.full_slab)
+    nz_local = sim.fld.interp[0].Nz
+    if n_gpus > 1:
+        workload += ' | z-slabs: %d physical + 2x%d guard = %d local cells per GPU, n_order=32' % (
+            nz_local - 2 * sim.comm.n_guard, sim.comm.n_guard, nz_local)
     Ntot_local = sum(s.Ntot for s in sim.ptcl)
     host_state_bytes = sum(getattr(s, k).nbytes for s in sim.ptcl
                            for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w', 'Ex', 'Ey', 'Ez', 'Bx', 'By', 'Bz')) \
@@ -305,7 +311,7 @@ def main():
     peaks = measured_peaks()
     hbm_peak = (peaks or {}).get('hbm_gbs', 6650.)
     peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback'
-    cells = cfg['Nz'] * cfg['Nr'] * 16
+    cells = nz_local * cfg['Nr'] * 16
     alg = {   # algorithmic bytes per launch
         # J: + (4+64+64-64) B/particle on the steps where the SoA permutation rides along;
         # rho: the second position push is fused in (reads 64, writes 24 B/particle)

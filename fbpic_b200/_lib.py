@@ -111,6 +111,7 @@ _SIGNATURES = {
     'b2_damp_z': [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P],
     'b2_shift_spect': [P, c_int, P, P, c_int, c_int, c_int, P],
     'b2_add_rows': [P, P, P, c_int, c_int, P],
+    'b2_halo_stage': [P, c_int, c_int, P, c_int, c_int, c_int, P, P],
     'b2_nccl_unique_id': [P],
     'b2_nccl_init': [P, P, c_int, c_int],
     'b2_nccl_destroy': [P],

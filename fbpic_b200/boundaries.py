@@ -222,57 +222,52 @@ class BoundaryCommunicator(object):
     # ---- field guard cells (boundary_communicator.py:556-707) ----
     def exchange_fields(self, interp, fldtype, method):
         """Exchange the guard cells of `fldtype` ('E','B','J','rho') with the z-neighbours:
-        'replace' overwrites the local guard rows, 'add' sums guard+inner rows.  Row slabs of
-        a [Nz,Nr] array are contiguous, so slabs go straight from/to the field arrays over NCCL
-        ('add' receives into a scratch slab that one kernel adds in)."""
+        'replace' overwrites the local guard rows, 'add' sums guard+inner rows."""
         if self.size == 1:
             return
         self.mpi_comm.init_nccl()
         ctx = _lib.context()
-        names = ('rho',) if fldtype == 'rho' else (fldtype + 'r', fldtype + 't', fldtype + 'z')
+        if fldtype == 'EB':         # fused step: E and B in one NCCL group (same data as 'E' then 'B')
+            names = ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz')
+        else:
+            names = ('rho',) if fldtype == 'rho' else (fldtype + 'r', fldtype + 't', fldtype + 'z')
         arrays = [getattr(interp[m], n) for m in range(self.Nm) for n in names]
         Nz, Nr = arrays[0].shape
         ng = self.n_guard
         plan = halo_plan(Nz, ng, method)
         nrow = plan['send_l'][1] - plan['send_l'][0]
-        recv = {}
-        if method == 'add':
-            key = (len(arrays), nrow, Nr)
-            if key not in self._halo_buf:
-                self._halo_buf[key] = (DeviceArray((len(arrays), nrow, Nr), np.complex128),
-                                       DeviceArray((len(arrays), nrow, Nr), np.complex128))
-            recv['l'], recv['r'] = self._halo_buf[key]
-        slab_bytes = nrow * Nr * 16
+        na = len(arrays)
+        key = ('fld', na, nrow, Nr)
+        if key not in self._halo_buf:
+            self._halo_buf[key] = [DeviceArray((na, nrow, Nr), np.complex128) for _ in range(4)]
+        send_l, send_r, recv_l, recv_r = self._halo_buf[key]
+        nbytes = na * nrow * Nr * 16
+        ptrs = ptr_array(arrays)
+        # one staging kernel per face packs the slabs of all the arrays (rows are contiguous), ONE NCCL
+        # message per neighbour and direction, one kernel per face replaces / adds the received rows
+        if self.left_proc is not None:
+            call.b2_halo_stage(ctx.handle, 0, na, ptrs, plan['send_l'][0], nrow, Nr, send_l.ptr, None)
+        if self.right_proc is not None:
+            call.b2_halo_stage(ctx.handle, 0, na, ptrs, plan['send_r'][0], nrow, Nr, send_r.ptr, None)
         # NCCL pairs the k-th send to a peer with the k-th receive posted for that peer.  What goes
         # out through my LEFT face arrives at my left neighbour's RIGHT face, so sends are posted
         # (left, right) and receives (right, left): with 2 ranks on a ring both neighbours are the
         # same peer and this order is what keeps the two directions apart (the reference uses MPI
         # tags 1/2 for that, boundary_communicator.py:688-699).
         call.b2_comm_begin(ctx.handle)
-        for i, a in enumerate(arrays):
-            if self.left_proc is not None:
-                call.b2_nccl_send(ctx.handle, a[plan['send_l'][0]:plan['send_l'][1]].ptr, slab_bytes,
-                                  self.left_proc, None)
-            if self.right_proc is not None:
-                call.b2_nccl_send(ctx.handle, a[plan['send_r'][0]:plan['send_r'][1]].ptr, slab_bytes,
-                                  self.right_proc, None)
-            if self.right_proc is not None:
-                dst = a[plan['recv_r'][0]:plan['recv_r'][1]].ptr if method == 'replace' \
-                    else recv['r'].ptr + i * slab_bytes
-                call.b2_nccl_recv(ctx.handle, dst, slab_bytes, self.right_proc, None)
-            if self.left_proc is not None:
-                dst = a[plan['recv_l'][0]:plan['recv_l'][1]].ptr if method == 'replace' \
-                    else recv['l'].ptr + i * slab_bytes
-                call.b2_nccl_recv(ctx.handle, dst, slab_bytes, self.left_proc, None)
+        if self.left_proc is not None:
+            call.b2_nccl_send(ctx.handle, send_l.ptr, nbytes, self.left_proc, None)
+        if self.right_proc is not None:
+            call.b2_nccl_send(ctx.handle, send_r.ptr, nbytes, self.right_proc, None)
+            call.b2_nccl_recv(ctx.handle, recv_r.ptr, nbytes, self.right_proc, None)
+        if self.left_proc is not None:
+            call.b2_nccl_recv(ctx.handle, recv_l.ptr, nbytes, self.left_proc, None)
         call.b2_comm_end(ctx.handle)
-        if method == 'add':
-            for i, a in enumerate(arrays):
-                if self.left_proc is not None:
-                    call.b2_add_rows(ctx.handle, a[plan['recv_l'][0]:plan['recv_l'][1]].ptr,
-                                     recv['l'].ptr + i * slab_bytes, nrow, Nr, None)
-                if self.right_proc is not None:
-                    call.b2_add_rows(ctx.handle, a[plan['recv_r'][0]:plan['recv_r'][1]].ptr,
-                                     recv['r'].ptr + i * slab_bytes, nrow, Nr, None)
+        mode = 1 if method == 'replace' else 2
+        if self.left_proc is not None:
+            call.b2_halo_stage(ctx.handle, mode, na, ptrs, plan['recv_l'][0], nrow, Nr, recv_l.ptr, None)
+        if self.right_proc is not None:
+            call.b2_halo_stage(ctx.handle, mode, na, ptrs, plan['recv_r'][0], nrow, Nr, recv_r.ptr, None)
 
     # ---- particles (boundary_communicator.py:710-826) ----
     def exchange_particles(self, species, fld, time):

@@ -9,6 +9,7 @@
 #include "../../include/fbpic_b200.h"
 
 #define B2_C_LIGHT 299792458.0
+#define B2_FFT_MAX_LANES 8
 
 struct b2_ctx {
     int device;
@@ -16,8 +17,12 @@ struct b2_ctx {
     // grow-only scratch (sort temp storage, permutation indices, ...)
     void *scratch[4];
     size_t scratch_bytes[4];
-    // cuFFT plans keyed by (Nz, Nr)
+    // cuFFT plans keyed by (Nz, Nr, lane): one plan (and work area) per concurrent lane
     std::map<uint64_t, cufftHandle> fft_plans;
+    // fork/join lanes of b2_fft_z_multi: independent latency-bound transforms overlap
+    cudaStream_t fft_lane[B2_FFT_MAX_LANES];
+    cudaEvent_t fft_fork, fft_join[B2_FFT_MAX_LANES];
+    int fft_lanes;             // 0 = not initialised yet
     // result of the last b2_sort_cells on this context (lives in scratch slot 0)
     const int32_t *last_idx32;
     const int32_t *last_keys_sorted;

@@ -218,9 +218,22 @@ __global__ void k_add(double2 *__restrict__ dst, const double2 *__restrict__ src
     if (i < n) dst[i] = cadd(dst[i], src[i]);
 }
 
+// Guard-cell staging: slab `a` of packed = rows [row0, row0+nrow) of array a (contiguous, n = nrow*Nr
+// elements).  MODE 0: pack (array -> packed), 1: unpack (packed -> array), 2: unpack-add.
+template <int MODE>
+__global__ void k_halo(B2Ptrs A, double2 *__restrict__ packed, size_t off, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double2 *arr = (double2 *)A.p[blockIdx.y] + off;
+    double2 *pk = packed + blockIdx.y * n;
+    if (MODE == 0) pk[i] = arr[i];
+    else if (MODE == 1) arr[i] = pk[i];
+    else arr[i] = cadd(arr[i], pk[i]);
+}
+
 // ==============================================================================================
-static int get_plan(b2_ctx *ctx, int Nz, int Nr, cufftHandle *plan) {
-    const uint64_t key = ((uint64_t)Nz << 32) | (uint32_t)Nr;
+static int get_plan(b2_ctx *ctx, int Nz, int Nr, int lane, cufftHandle *plan) {
+    const uint64_t key = ((uint64_t)lane << 56) | ((uint64_t)Nz << 28) | (uint32_t)Nr;
     auto it = ctx->fft_plans.find(key);
     if (it == ctx->fft_plans.end()) {
         cufftHandle h;
@@ -234,6 +247,39 @@ static int get_plan(b2_ctx *ctx, int Nz, int Nr, cufftHandle *plan) {
         *plan = h;
     } else {
         *plan = it->second;
+    }
+    return 0;
+}
+
+// lane 0 is the caller's stream; lanes 1.. are context-owned non-blocking streams
+static int fft_lanes_init(b2_ctx *ctx) {
+    if (ctx->fft_lanes) return 0;
+    int lanes = 4;
+    if (const char *e = getenv("B2_FFT_LANES")) lanes = atoi(e);
+    if (lanes < 1) lanes = 1;
+    if (lanes > B2_FFT_MAX_LANES) lanes = B2_FFT_MAX_LANES;
+    B2_CUDA(cudaEventCreateWithFlags(&ctx->fft_fork, cudaEventDisableTiming));
+    for (int k = 1; k < lanes; ++k) {
+        B2_CUDA(cudaStreamCreateWithFlags(&ctx->fft_lane[k], cudaStreamNonBlocking));
+        B2_CUDA(cudaEventCreateWithFlags(&ctx->fft_join[k], cudaEventDisableTiming));
+    }
+    ctx->fft_lanes = lanes;
+    return 0;
+}
+
+static int fft_exec(b2_ctx *ctx, int lane, cudaStream_t s, const void *in, void *out, int Nz, int Nr, int inverse) {
+    cufftHandle plan;
+    int rc = get_plan(ctx, Nz, Nr, lane, &plan);
+    if (rc) return rc;
+    cufftResult r = cufftSetStream(plan, s);
+    if (r != CUFFT_SUCCESS) return b2_fail((int)r, "cufftSetStream failed", __FILE__, __LINE__);
+    r = cufftExecZ2Z(plan, (cufftDoubleComplex *)in, (cufftDoubleComplex *)out, inverse ? CUFFT_INVERSE : CUFFT_FORWARD);
+    if (r != CUFFT_SUCCESS) return b2_fail((int)r, "cufftExecZ2Z failed", __FILE__, __LINE__);
+    g_b2_launches.fetch_add(1);
+    if (inverse == 1) {      // inverse == 2: raw inverse (the 1/Nz factor is folded into the Hankel matrices)
+        const size_t n = (size_t)Nz * Nr;
+        k_scale<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((double2 *)out, 1. / Nz, n);
+        B2_LAUNCHED();
     }
     return 0;
 }
@@ -273,29 +319,34 @@ int b2_pm_to_rt(b2_ctx *ctx, void *p, void *m, int Nz, int Nr, void *stream) {
 }
 
 int b2_fft_z(b2_ctx *ctx, const void *in, void *out, int Nz, int Nr, int inverse, void *stream) {
-    cufftHandle plan;
-    int rc = get_plan(ctx, Nz, Nr, &plan);
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    B2Prof prof_(B2P_FFT, s);
+    return fft_exec(ctx, 0, s, in, out, Nz, Nr, inverse);
+}
+
+// The transforms of one call are independent and each of them is too small to fill the GPU
+// (one 4096 x 256 Z2Z = 128 CTAs): they are spread over `B2_FFT_LANES` (default 4) streams forked from
+// and joined back into the caller's stream with events, so the caller still sees stream order.
+int b2_fft_z_multi(b2_ctx *ctx, int na, const void *const *in, void *const *out, int Nz, int Nr, int inverse,
+                   void *stream) {
+    if (na <= 0) return 0;
+    int rc = fft_lanes_init(ctx);
     if (rc) return rc;
     cudaStream_t s = b2_stream_of(ctx, stream);
     B2Prof prof_(B2P_FFT, s);
-    cufftResult r = cufftSetStream(plan, s);
-    if (r != CUFFT_SUCCESS) return b2_fail((int)r, "cufftSetStream failed", __FILE__, __LINE__);
-    r = cufftExecZ2Z(plan, (cufftDoubleComplex *)in, (cufftDoubleComplex *)out, inverse ? CUFFT_INVERSE : CUFFT_FORWARD);
-    if (r != CUFFT_SUCCESS) return b2_fail((int)r, "cufftExecZ2Z failed", __FILE__, __LINE__);
-    g_b2_launches.fetch_add(1);
-    if (inverse == 1) {      // inverse == 2: raw inverse (the 1/Nz factor is folded into the Hankel matrices)
-        const size_t n = (size_t)Nz * Nr;
-        k_scale<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((double2 *)out, 1. / Nz, n);
-        B2_LAUNCHED();
+    const int lanes = ctx->fft_lanes < na ? ctx->fft_lanes : na;
+    if (lanes > 1) {
+        B2_CUDA(cudaEventRecord(ctx->fft_fork, s));
+        for (int l = 1; l < lanes; ++l) B2_CUDA(cudaStreamWaitEvent(ctx->fft_lane[l], ctx->fft_fork, 0));
     }
-    return 0;
-}
-
-int b2_fft_z_multi(b2_ctx *ctx, int na, const void *const *in, void *const *out, int Nz, int Nr, int inverse,
-                   void *stream) {
     for (int k = 0; k < na; ++k) {
-        int rc = b2_fft_z(ctx, in[k], out[k], Nz, Nr, inverse, stream);
+        const int l = k % lanes;
+        rc = fft_exec(ctx, l, l ? ctx->fft_lane[l] : s, in[k], out[k], Nz, Nr, inverse);
         if (rc) return rc;
+    }
+    for (int l = 1; l < lanes; ++l) {
+        B2_CUDA(cudaEventRecord(ctx->fft_join[l], ctx->fft_lane[l]));
+        B2_CUDA(cudaStreamWaitEvent(s, ctx->fft_join[l], 0));
     }
     return 0;
 }
@@ -348,6 +399,23 @@ int b2_shift_spect(b2_ctx *ctx, int na, void *const *arrays, const void *shift, 
     for (int k = 0; k < na; ++k) A.p[k] = arrays[k];
     B2Prof prof_(B2P_ELEMENTWISE, b2_stream_of(ctx, stream));
     k_shift_spect<<<grid2d(Nz, Nr, BLK), BLK, 0, b2_stream_of(ctx, stream)>>>(A, na, (const double2 *)shift, n_move, Nz, Nr);
+    B2_LAUNCHED();
+    return 0;
+}
+
+int b2_halo_stage(b2_ctx *ctx, int mode, int na, void *const *arrays, int row0, int nrow, int Nr, void *packed,
+                  void *stream) {
+    if (na <= 0 || nrow <= 0) return 0;
+    if (na > B2_MAX_ARRAYS) return b2_fail(-3, "too many arrays", __FILE__, __LINE__);
+    if (mode < 0 || mode > 2) return b2_fail(-3, "b2_halo_stage: mode must be 0 (pack), 1 (unpack), 2 (unpack-add)", __FILE__, __LINE__);
+    B2Ptrs A;
+    for (int k = 0; k < na; ++k) A.p[k] = arrays[k];
+    const size_t n = (size_t)nrow * Nr, off = (size_t)row0 * Nr;
+    dim3 g((unsigned)((n + 255) / 256), na);
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    if (mode == 0) k_halo<0><<<g, 256, 0, s>>>(A, (double2 *)packed, off, n);
+    else if (mode == 1) k_halo<1><<<g, 256, 0, s>>>(A, (double2 *)packed, off, n);
+    else k_halo<2><<<g, 256, 0, s>>>(A, (double2 *)packed, off, n);
     B2_LAUNCHED();
     return 0;
 }

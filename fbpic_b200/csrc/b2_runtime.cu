@@ -88,6 +88,11 @@ int b2_ctx_destroy(b2_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->fft_plans) cufftDestroy(kv.second);
+    for (int l = 1; l < ctx->fft_lanes; ++l) {
+        cudaStreamDestroy(ctx->fft_lane[l]);
+        cudaEventDestroy(ctx->fft_join[l]);
+    }
+    if (ctx->fft_lanes) cudaEventDestroy(ctx->fft_fork);
     for (int i = 0; i < 4; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

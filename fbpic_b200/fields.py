@@ -442,6 +442,8 @@ class Fields(object):
 
     def _partial_pairs(self, m, fieldtype):
         g, s = self.interp[m], self.spect[m]
+        if fieldtype == 'EB':       # both at once (fused step): same arrays as 'E' then 'B'
+            return self._partial_pairs(m, 'E') + self._partial_pairs(m, 'B')
         if self._vec(fieldtype):
             f = fieldtype
             return [(getattr(s, f + 'z'), getattr(g, f + 'z')), (getattr(s, f + 'p'), getattr(g, f + 'r')),
@@ -450,17 +452,20 @@ class Fields(object):
             return [(getattr(s, fieldtype), g.rho)]
         raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
 
+    def _fft_many(self, pairs, inverse):
+        """z-FFTs of independent arrays in one call (spread over concurrent lanes by the library)."""
+        if not pairs:
+            return
+        call.b2_fft_z_multi(_lib.context().handle, len(pairs), ptr_array([a for a, _ in pairs]),
+                            ptr_array([b for _, b in pairs]), self.Nz, self.Nr, inverse, None)
+
     def spect2partial_interp(self, fieldtype):
         """iFFT along z only (fields.py:431-485)."""
-        for m in range(self.Nm):
-            for sp, it in self._partial_pairs(m, fieldtype):
-                self.trans[m].fft.inverse_transform(sp, it)
+        self._fft_many([(sp, it) for m in range(self.Nm) for sp, it in self._partial_pairs(m, fieldtype)], 1)
 
     def partial_interp2spect(self, fieldtype):
         """FFT along z only (fields.py:487-537)."""
-        for m in range(self.Nm):
-            for sp, it in self._partial_pairs(m, fieldtype):
-                self.trans[m].fft.transform(it, sp)
+        self._fft_many([(it, sp) for m in range(self.Nm) for sp, it in self._partial_pairs(m, fieldtype)], 0)
 
     # ---- fused transforms (single-domain fast path of Simulation.step) ----
     def _fused_tables(self, filter_currents):
@@ -491,22 +496,22 @@ class Fields(object):
         (main.py:640,657,666-668) as 1 (rho) or 3 (J) FFTs per mode + ONE batched Hankel launch."""
         T = self._fused_tables(filter_currents)
         ctx = _lib.context()
-        jobs = []
+        jobs, ffts = [], []
         for m in range(self.Nm):
             g, s, t = self.interp[m], self.spect[m], T[m]
             fz = t['fz'].ptr if t['fz'] is not None else None
             if fieldtype == 'J':
-                for a, b in ((g.Jz, t['buf'][0]), (g.Jr, t['buf'][1]), (g.Jt, t['buf'][2])):
-                    call.b2_fft_z(ctx.handle, a.ptr, b.ptr, self.Nz, self.Nr, 0, None)
+                ffts += [(g.Jz, t['buf'][0]), (g.Jr, t['buf'][1]), (g.Jt, t['buf'][2])]
                 jobs.append(DhtJob(t['buf'][0].ptr, None, s.Jz.ptr, None, t['F0'].ptr, None, fz, _lib.DHT_SCALAR))
                 jobs.append(DhtJob(t['buf'][1].ptr, t['buf'][2].ptr, s.Jp.ptr, s.Jm.ptr, t['Fp'].ptr, t['Fm'].ptr,
                                    fz, _lib.DHT_RT_TO_PM))
             elif fieldtype in ('rho_prev', 'rho_next'):
-                call.b2_fft_z(ctx.handle, g.rho.ptr, t['buf'][0].ptr, self.Nz, self.Nr, 0, None)
+                ffts.append((g.rho, t['buf'][0]))
                 jobs.append(DhtJob(t['buf'][0].ptr, None, getattr(s, fieldtype).ptr, None, t['F0'].ptr, None,
                                    fz, _lib.DHT_SCALAR))
             else:
                 raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
+        self._fft_many(ffts, 0)
         arr = (DhtJob * len(jobs))(*jobs)
         call.b2_dht_batch(ctx.handle, len(jobs), arr, self.Nz, self.Nr, None)
 
@@ -527,8 +532,7 @@ class Fields(object):
                 ffts += [(bz, getattr(g, f + 'z')), (br, getattr(g, f + 'r')), (bt, getattr(g, f + 't'))]
         arr = (DhtJob * len(jobs))(*jobs)
         call.b2_dht_batch(ctx.handle, len(jobs), arr, self.Nz, self.Nr, None)
-        for a, b in ffts:
-            call.b2_fft_z(ctx.handle, a.ptr, b.ptr, self.Nz, self.Nr, 2, None)
+        self._fft_many(ffts, 2)
 
     def fused_partial2interp_EB(self):
         """After the guard-cell exchange of exchange_and_damp_EB (main.py:741-747) the interpolation

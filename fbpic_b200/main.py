@@ -163,7 +163,7 @@ class Simulation(object):
             self.deposit('J', exchange=(correct_currents is False))
             # fused mode: the second half push rides inside the rho deposition kernel when every
             # species deposits and already has sort locality
-            fuse_pr = self.fused and move_positions and single and len(ptcl) > 0 and \
+            fuse_pr = self.fused and move_positions and len(ptcl) > 0 and \
                 all((sp.q != 0) and (not sp.is_tracer) and getattr(sp, '_order_matches_prefix', False)
                     for sp in ptcl)
             if fuse_pr:
@@ -257,6 +257,15 @@ class Simulation(object):
         mode and goes straight to spect2interp."""
         fld = self.fld
         if not skip_identity:
+            if self.fused:
+                # E and B together: one batch of concurrent z-FFTs each way, one NCCL group
+                fld.spect2partial_interp('EB')
+                self.comm.exchange_fields(fld.interp, 'EB', 'replace')
+                self.comm.damp_EB_open_boundary(fld.interp)
+                fld.partial_interp2spect('EB')
+                # the exchanged (z, kr) arrays go straight to real space: inverse Hankel only
+                fld.fused_partial2interp_EB()
+                return
             fld.spect2partial_interp('E')
             fld.spect2partial_interp('B')
             self.comm.exchange_fields(fld.interp, 'E', 'replace')
@@ -264,10 +273,6 @@ class Simulation(object):
             self.comm.damp_EB_open_boundary(fld.interp)
             fld.partial_interp2spect('E')
             fld.partial_interp2spect('B')
-            if self.fused:
-                # the exchanged (z, kr) arrays go straight to real space: inverse Hankel only
-                fld.fused_partial2interp_EB()
-                return
         if self.fused:
             fld.fused_spect2interp_EB()
         else:

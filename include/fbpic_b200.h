@@ -256,6 +256,12 @@ int b2_damp_z(b2_ctx *ctx, int n_arrays, void *const *d_arrays, const double *d_
 int b2_shift_spect(b2_ctx *ctx, int n_arrays, void *const *d_arrays, const void *d_shift, int n_move,
                    int Nz, int Nr, void *stream);
 int b2_add_rows(b2_ctx *ctx, void *d_dst, const void *d_src, int nrows, int Nr, void *stream);
+/* Guard-cell staging for the z-slab exchange (replaces the copy_vec_to_gpu_buffer / replace_vec_from_gpu_buffer
+ * / add_vec_from_gpu_buffer kernels of fbpic/boundaries/cuda_methods.py:21-253): rows [row0, row0+nrow) of the
+ * n_arrays [Nz][Nr] complex arrays <-> one contiguous buffer [n_arrays][nrow][Nr].
+ * mode 0: pack, 1: unpack (replace), 2: unpack and add. */
+int b2_halo_stage(b2_ctx *ctx, int mode, int n_arrays, void *const *d_arrays, int row0, int nrow, int Nr,
+                  void *d_packed, void *stream);
 int b2_nccl_unique_id(void *id128);                       /* 128-byte ncclUniqueId */
 int b2_nccl_init(b2_ctx *ctx, const void *id128, int rank, int size);
 int b2_nccl_destroy(b2_ctx *ctx);
