@@ -30,6 +30,7 @@
 
 #define DM_TPB 256          // particles per CTA = threads per CTA
 #define DM_PITCH (DM_TPB + 4)
+#define DM_IR_BITS 12       // packed run identity: ir_u <= Nr < 2^12, iz_u < 2^19
 
 struct B2DmGrids {
     double2 *g[3 * B2_MAX_MODES];   // rho: [m] ; J: [m][Jr,Jt,Jz]
@@ -54,7 +55,7 @@ struct B2DmPush {
 };
 
 template <int NM, bool IS_J, int NPT, bool PERMUTE, bool PUSH>
-__global__ void __launch_bounds__(DM_TPB)
+__global__ void __launch_bounds__(DM_TPB, (NPT == 2 && NM <= 2) ? 6 : 1)
 k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush push, double q,
               double invdz, double zmin, int Nz, double invdr, double rmin, int Nr, B2DmGrids G,
               const double *__restrict__ ruyten0, const double *__restrict__ ruyten_hi) {
@@ -70,9 +71,9 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush
     // (r = lane/4, p = k0 + lane%4): DM_PITCH % 16 == 4 makes the 16 lanes of a half-warp hit 16
     // different 8-byte banks.
     double *sW = (double *)dm_smem;                    // [MT*8][DM_PITCH]
-    double *sV = sW + MT * 8 * DM_PITCH;               // [NT*8][DM_PITCH]
-    int *sK = (int *)(sV + NT * 8 * DM_PITCH);         // [DM_TPB] cell key (-1: no particle)
-    int *sIz = sK + DM_TPB, *sIr = sIz + DM_TPB;       // [DM_TPB] upper cell indices of the particle
+    double *sV = sW + MT * 8 * DM_PITCH;               // [NVT][DM_PITCH]: only the rows that carry a value
+    // [DM_TPB] run identity = packed upper cell indices (iz_u << DM_IR_BITS | ir_u), -1: no particle
+    int *sK = (int *)(sV + NVT * DM_PITCH);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q0 = blockIdx.x * (int64_t)DM_TPB;
@@ -80,7 +81,7 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush
 
     // ------------------------------------------------------------------ phase A
     {
-        int key = -1, kiz = 0, kir = 0;
+        int key = -1;
         double S[NROW];
         double V[NT * 8];
 #pragma unroll
@@ -114,7 +115,7 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush
             int iru = (int)ceil(c.r_cell), izu = (int)ceil(c.z_cell);
             if (iru > Nr) iru = Nr;
             if (izu < 0) izu += Nz; else if (izu > Nz - 1) izu -= Nz;
-            key = iru + izu * (Nr + 1); kiz = izu; kir = iru;
+            key = (izu << DM_IR_BITS) | iru;
             const double beta0 = __ldg(ruyten0 + iru), beta_hi = __ldg(ruyten_hi + iru);
             // shape factors (particle_shapes.py:17-80); the flip sign is applied at flush time
             double sz[NPT], sr0[NPT], sr1[NPT];
@@ -172,11 +173,11 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush
                 }
             }
         }
-        sK[tid] = key; sIz[tid] = kiz; sIr[tid] = kir;
+        sK[tid] = key;
 #pragma unroll
         for (int r = 0; r < MT * 8; ++r) sW[r * DM_PITCH + tid] = S[r];
 #pragma unroll
-        for (int v = 0; v < NT * 8; ++v) sV[v * DM_PITCH + tid] = V[v];
+        for (int v = 0; v < NVT; ++v) sV[v * DM_PITCH + tid] = V[v];
     }
     __syncthreads();
 
@@ -236,14 +237,15 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) a[mt] = in ? sW[(mt * 8 + g) * DM_PITCH + p] : 0.;
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) b[nt] = in ? sV[(nt * 8 + g) * DM_PITCH + p] : 0.;
+                for (int nt = 0; nt < NT; ++nt)
+                    b[nt] = (in && nt * 8 + g < NVT) ? sV[(nt * 8 + g) * DM_PITCH + p] : 0.;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
             }
             // ---- flush the useful entries with one RED each ----
-            const int iz_u = sIz[pos], ir_u = sIr[pos];
+            const int iz_u = key >> DM_IR_BITS, ir_u = key & ((1 << DM_IR_BITS) - 1);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 int iz = iz_u + f_a[mt];
@@ -284,8 +286,8 @@ struct DmArgs {
 template <int NM, bool IS_J, int NPT, bool PERMUTE, bool PUSH>
 static int launch_dm(cudaStream_t s, const DmArgs &A) {
     constexpr int NCOMP = IS_J ? 3 : 1;
-    constexpr int MT = 2 * NPT * NPT / 8, NT = (NCOMP * (2 * NM - 1) + 7) / 8;
-    const size_t smem = sizeof(double) * 8 * DM_PITCH * (MT + NT) + sizeof(int) * 3 * DM_TPB;
+    constexpr int MT = 2 * NPT * NPT / 8, NVT = NCOMP * (2 * NM - 1);
+    const size_t smem = sizeof(double) * DM_PITCH * (8 * MT + NVT) + sizeof(int) * DM_TPB;
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
         B2_CUDA(cudaFuncSetAttribute(k_deposit_mma<NM, IS_J, NPT, PERMUTE, PUSH>,
@@ -313,6 +315,8 @@ int b2_deposit_mma(b2_ctx *ctx, bool is_J, int64_t n, const double *const *src8,
                    void *stream) {
     if (n <= 0) return 0;
     if (Nm < 1 || Nm > 4) return b2_fail(-3, "deposit: Nm must be in 1..4", __FILE__, __LINE__);
+    if (Nr >= (1 << DM_IR_BITS) || Nz >= (1 << (31 - DM_IR_BITS)))
+        return b2_fail(-3, "deposit: grid too large for the packed run key (Nr < 4096, Nz < 524288)", __FILE__, __LINE__);
     DmArgs A;
     const bool permute = (dst8 != nullptr) && (push == nullptr);
     A.n = n;

@@ -314,11 +314,11 @@ k_gather_push_tiled(int64_t n, double *__restrict__ x, double *__restrict__ y, d
     __shared__ int s_anchor[2];
     const int tid = threadIdx.x;
     const int64_t i = blockIdx.x * (int64_t)GP_TPB + tid;
-    if (tid == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MIN; s_box[2] = INT_MAX; s_box[3] = INT_MIN; }
-    __syncthreads();
     const bool in_range = i < n;
     double xj = 0., yj = 0., zj = 0.;
-    if (in_range) { xj = x[i]; yj = y[i]; zj = z[i]; }
+    if (in_range) {
+        xj = x[i]; yj = y[i]; zj = z[i];
+    }
     const B2Cyl c = b2_cyl(xj, yj, zj, invdz, zmin, invdr, rmin);
     const bool active = in_range && (c.r < rmax_gather);
     // stencil indices and weights exactly as gather_field_gpu_linear (gathering/cuda_methods.py:109-160)
@@ -333,7 +333,10 @@ k_gather_push_tiled(int64_t n, double *__restrict__ x, double *__restrict__ y, d
     // bounding box of the stencils of the particles that lie NEAR the CTA's first particle (sorted
     // particles all do); a stray particle (moved far since the last sort) gathers from global memory
     // on its own instead of blowing up the tile for the whole CTA
-    if (tid == 0) { s_anchor[0] = iz_l0; s_anchor[1] = ir_l; }
+    if (tid == 0) {
+        s_box[0] = INT_MAX; s_box[1] = INT_MIN; s_box[2] = INT_MAX; s_box[3] = INT_MIN;
+        s_anchor[0] = iz_l0; s_anchor[1] = ir_l;
+    }
     __syncthreads();
     const bool near = active && abs(iz_l0 - s_anchor[0]) <= 2 && ir_l >= s_anchor[1] - 8 && ir_u <= s_anchor[1] + 40;
     if (near) {
