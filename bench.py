@@ -7,8 +7,10 @@ bench.py -- PIC hot-loop throughput of fbpic_b200 on B200 (and of the CPU oracle
 Workload (BASELINE.json configs[1], SURVEY 8d "C2"): Nz=4096 per GPU, Nr=256, Nm=2, linear
 shapes, uniform electrons 2x2x4 per cell (16.8 M macro-particles per GPU) filling the box,
 a0=4 / w0=5um / 16fs Gaussian laser pulse initialised analytically on the grid, z periodic
-(Nz stays 4096: isolates the hot loop).  N>1: weak scaling, the global grid is N slabs of 4096
-cells (n_order=32, NCCL guard-cell exchange + particle migration).
+(Nz stays 4096: isolates the hot loop).  N>1: weak scaling over z-slabs (n_order=32, NCCL guard-cell
+exchange + particle migration): every GPU works on a local periodic box of 4096 cells = 3968 physical
+cells + 2x64 guard cells, so the local z-FFT keeps the single-GPU length (`--full-slab`: 4096 physical
+cells + guards = 4224 local cells per GPU); the particle count in `value` is the real one.
 One "step" = one full PIC cycle (Simulation.step(1)); metric = particle-updates/s =
 (sum over ranks of macro-particles) * K / (max over ranks of the device time of K steps).
 Prints ONE JSON line (rank 0).
@@ -111,23 +113,54 @@ def build_oracle_sim(cfg, Nz, nthreads, seed=0):
 
 # ---------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML every 5 ms (the same counters
+    nvidia-smi prints as clocks.sm / clocks_event_reasons.*); falls back to polling nvidia-smi."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
         'clocks_event_reasons.sw_power_cap'
 
-    def __init__(self, gpu_index=0, period=0.05):
+    def __init__(self, gpu_index=0, period=0.005):
         super().__init__(daemon=True)
-        self.gpu, self.period, self.samples, self._halt = gpu_index, period, [], threading.Event()
+        self.gpu, self.period, self._halt = gpu_index, period, threading.Event()
+        self.sm, self.reasons, self.sm_max, self.source = [], set(), None, 'nvml'
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[gpu_index]) if vis and vis.split(',')[gpu_index].isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.masks = {'hw_slowdown': pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                          'hw_thermal_slowdown': pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                          'sw_thermal_slowdown': pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                          'sw_power_cap': pynvml.nvmlClocksThrottleReasonSwPowerCap}
+        except Exception:
+            self.nv, self.source, self.period = None, 'nvidia-smi', 0.05
+
+    def _sample(self):
+        if self.nv is not None:
+            self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.reasons.update(n for n, m in self.masks.items() if r & m)
+            return
+        out = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                              '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                             timeout=5).stdout.strip()
+        if out:
+            f = [v.strip() for v in out.split(',')]
+            if f[0].replace('.', '').isdigit():
+                self.sm.append(float(f[0]))
+            if f[1].replace('.', '').isdigit():
+                self.sm_max = max(self.sm_max or 0., float(f[1]))
+            names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+            self.reasons.update(n for n, v in zip(names, f[3:7]) if v.lower().startswith('active'))
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(',')])
+                self._sample()
             except Exception:
                 pass
             self._halt.wait(self.period)
@@ -135,12 +168,35 @@ class ClockSampler(threading.Thread):
     def stop(self):
         self._halt.set()
         self.join(timeout=3)
-        sm = [float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
-        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith('active')})
-        return dict(sm_mhz=(float(np.median(sm)) if sm else None), sm_max_mhz=(max(mx) if mx else None),
-                    reasons=reasons, samples=len(self.samples))
+        return dict(sm_mhz=(float(np.median(self.sm)) if self.sm else None),
+                    sm_min_mhz=(min(self.sm) if self.sm else None), sm_max_mhz=self.sm_max,
+                    reasons=sorted(self.reasons), samples=len(self.sm), source=self.source)
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI
+    function), before any host buffer is allocated: page-locked staging buffers and the H2D/D2H copies of the
+    e2e leg then stay on the GPU's socket.  Returns a description (None if nothing was changed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = int(vis.split(',')[device_index]) if vis and vis.split(',')[device_index].isdigit() else device_index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = '/sys/bus/pci/devices/%s/local_cpulist' % bus.lower()[-12:]
+        txt = open(path).read().strip()
+        cpus = set()
+        for part in txt.split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return 'cpus %s (NUMA node of GPU %s)' % (txt, bus)
+    except Exception:
+        pass
+    return None
 
 
 def measured_peaks():
@@ -229,6 +285,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('gloo')
     ctx = _lib.context()
+    affinity = bind_to_gpu_numa(ctx.device)
     sim = build_b200_sim(cfg, n_gpus, fused=not args.no_fused, sort_period=args.sort_period,
                          full_slab=args.full_slab)
     nz_local = sim.fld.interp[0].Nz
@@ -300,7 +357,8 @@ def main():
             t = torch.tensor([t_e2e], dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t_e2e = float(t[0])
-        e2e = {'value': n_tot * k_e2e / t_e2e, 'unit': 'particle-updates/s',
+        e2e = {'value': n_tot * k_e2e / t_e2e, 'unit': 'particle-updates/s', 'wall_s': t_e2e,
+               'split_s': {k: round(v, 4) for k, v in sim.last_step_timing.items()},
                'h2d_bytes_per_step': host_state_bytes / k_e2e, 'd2h_bytes_per_step': host_state_bytes / k_e2e,
                'note': 'Simulation.step(%d) from/to host NumPy arrays: full particle+field state H2D at entry '
                        'and D2H at exit, as the reference API does; per-step bytes = total/%d' % (k_e2e, k_e2e)}
@@ -373,7 +431,7 @@ def main():
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': t_ms / args.steps,
         'pic_steps_per_s': args.steps / (t_ms * 1e-3), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': workload, 'particles_total': n_tot, 'fused': not args.no_fused,
+        'config': {'workload': workload, 'particles_total': n_tot, 'host_affinity': affinity, 'fused': not args.no_fused,
                    'n_order': -1 if n_gpus == 1 else 32, 'n_guard': sim.comm.n_guard, 'preroll_steps': args.preroll, 'sort_period': args.sort_period,
                    'l2': 'inputs larger than L2 (particle state %.1f GB per GPU)' % (Ntot_local * 64 / 1e9)},
         'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline,

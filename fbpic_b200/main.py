@@ -116,7 +116,10 @@ class Simulation(object):
         fuse_gp = self.fused and move_positions and move_momenta
         fuse_cp = self.fused and correct_currents and single
 
+        import time as _time
+        t_start = _time.perf_counter()
         self.send_data_to_gpu()
+        t_sent = _time.perf_counter()
         self.comm.exchange_fields(fld.interp, 'E', 'replace')
         self.comm.exchange_fields(fld.interp, 'B', 'replace')
         self.comm.damp_EB_open_boundary(fld.interp)
@@ -214,10 +217,13 @@ class Simulation(object):
         fld.spect2interp('rho_prev')
         if (not fld.exchanged_source['rho_prev']) and (self.comm.size > 1):
             self.comm.exchange_fields(self.fld.interp, 'rho', 'add')
+        _lib.context().sync()
+        t_done = _time.perf_counter()
         if not keep_on_gpu:
             self.receive_data_from_gpu()
-        else:
-            _lib.context().sync()
+        # wall-clock split of this call: host->device copy, the N cycles (device-synchronised), device->host copy
+        self.last_step_timing = dict(h2d_s=t_sent - t_start, cycles_s=t_done - t_sent,
+                                     d2h_s=_time.perf_counter() - t_done)
 
     def deposit(self, fieldtype, exchange=False, update_spectral=True, species_list=None, push=None):
         """fbpic/main.py:588-670"""
