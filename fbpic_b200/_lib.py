@@ -35,6 +35,7 @@ class DhtJob(ctypes.Structure):
 
 
 DHT_SCALAR, DHT_RT_TO_PM, DHT_PM_TO_RT = 0, 1, 2
+MAX_ARRAYS = 32             # B2_MAX_ARRAYS (include/fbpic_b200.h): pointers carried by one multi-array launch
 
 
 # name -> argtypes; every entry returns int status unless listed in _RESTYPES
@@ -122,6 +123,11 @@ _SIGNATURES = {
     'b2_nccl_send': [P, P, c_size_t, c_int, P],
     'b2_nccl_recv': [P, P, c_size_t, c_int, P],
     'b2_nccl_allreduce_max_f64': [P, P, c_size_t, P],
+    'b2_push_eb_pml': [P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, P],
+    'b2_damp_pml': [P, P, P, P, P, P, P, P, c_int, c_int, c_int, P],
+    'b2_correct_currents_cross': [P, ctypes.POINTER(SpectralMode), P, P, c_int, c_double, c_int, c_int, P],
+    'b2_antenna_particles': [P, c_int64, P, P, P, P, P, P, P, c_double, P, P, P, P, P, P],
+    'b2_axpy': [P, c_int64, c_double, P, P, P],
 }
 _RESTYPES = {'b2_dht_flops': c_double, 'b2_profile_name': ctypes.c_char_p, 'b2_profile_slots': c_int,
              'b2_error_string': ctypes.c_char_p, 'b2_version': ctypes.c_char_p,

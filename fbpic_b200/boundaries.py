@@ -120,8 +120,6 @@ class BoundaryCommunicator(object):
             raise ValueError("Unrecognized `boundaries['z']`: '%s'" % boundaries['z'])
         if boundaries['r'] not in ('reflective', 'open'):
             raise ValueError("Unrecognized `boundaries['r']`: '%s'" % boundaries['r'])
-        if boundaries['r'] == 'open':
-            raise NotImplementedError("boundaries['r']='open' (radial PML) is out of scope of this build")
         self.use_all_mpi_ranks = use_all_mpi_ranks
         w = world()
         if use_all_mpi_ranks and w.size > 1:
@@ -155,12 +153,17 @@ class BoundaryCommunicator(object):
             self.n_guard = n_guard
         if boundaries['z'] == 'periodic' and self.size == 1:
             self.n_guard = 0
-        self.nz_damp, self.nr_damp = n_damp['z'], 0
+        self.nz_damp, self.nr_damp = n_damp['z'], n_damp['r']
         if boundaries['z'] == 'periodic':
             self.nz_damp, self.n_inject = 0, 0
         else:
             self.n_inject = int(self.n_guard / 2) if n_inject is None else n_inject
-        self.use_pml = False
+        # radial PML (boundary_communicator.py:272-278, 332-335; pml_damping.py:23-44, 86-108)
+        if boundaries['r'] == 'reflective':
+            self.nr_damp = 0
+        self.use_pml = (boundaries['r'] == 'open')
+        self.pml_damp_array = ht.pml_damp_array(self.nr_damp, cdt_over_dr) if self.use_pml else None
+        self.d_pml_damp_array = None
         # exchange period (boundary_communicator.py:281-304)
         if exchange_period is None:
             cells_per_step = 2. * c * dt / self.dz
@@ -231,7 +234,19 @@ class BoundaryCommunicator(object):
             names = ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz')
         else:
             names = ('rho',) if fldtype == 'rho' else (fldtype + 'r', fldtype + 't', fldtype + 'z')
+        if self.use_pml and fldtype in ('E', 'B', 'EB'):
+            # the split PML components travel with their field (boundary_communicator.py:621-627)
+            names = names + tuple(f + c + '_pml' for f in fldtype for c in 'rt')
         arrays = [getattr(interp[m], n) for m in range(self.Nm) for n in names]
+        if len(arrays) > _lib.MAX_ARRAYS:
+            # more slabs than one staging launch carries: exchange them in chunks
+            for i in range(0, len(arrays), _lib.MAX_ARRAYS):
+                self._exchange_arrays(arrays[i:i + _lib.MAX_ARRAYS], method)
+            return
+        self._exchange_arrays(arrays, method)
+
+    def _exchange_arrays(self, arrays, method):
+        ctx = _lib.context()
         Nz, Nr = arrays[0].shape
         ng = self.n_guard
         plan = halo_plan(Nz, ng, method)
@@ -380,13 +395,23 @@ class BoundaryCommunicator(object):
         if self.d_left_damp is None:
             arr = self.left_damp if self.left_damp is not None else self.right_damp
             self.d_left_damp = self.d_right_damp = DeviceArray.from_numpy(arr)
-        arrays = [getattr(interp[m], n) for m in range(len(interp))
-                  for n in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz')]
-        call.b2_damp_z(_lib.context().handle, len(arrays), ptr_array(arrays), self.d_left_damp.ptr, nd,
-                       int(left), int(right), interp[0].Nz, interp[0].Nr, None)
+        names = ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz')
+        if interp[0].use_pml:       # boundary_communicator.py:856-860, 893-897
+            names = names + ('Er_pml', 'Et_pml', 'Br_pml', 'Bt_pml')
+        for m in range(len(interp)):
+            arrays = [getattr(interp[m], n) for n in names]
+            call.b2_damp_z(_lib.context().handle, len(arrays), ptr_array(arrays), self.d_left_damp.ptr, nd,
+                           int(left), int(right), interp[0].Nz, interp[0].Nr, None)
 
     def damp_pml_EB(self, interp):
-        raise NotImplementedError('radial PML is out of scope of this build')
+        """Anisotropic damping of E, B in the last nr_damp radial cells (pml_damping.py:46-83)."""
+        if not self.use_pml:
+            return
+        if self.d_pml_damp_array is None:
+            self.d_pml_damp_array = DeviceArray.from_numpy(self.pml_damp_array)
+        for g in interp:
+            call.b2_damp_pml(_lib.context().handle, g.Et.ptr, g.Et_pml.ptr, g.Ez.ptr, g.Bt.ptr, g.Bt_pml.ptr,
+                             g.Bz.ptr, self.d_pml_damp_array.ptr, self.nr_damp, g.Nz, g.Nr, None)
 
     def move_grids(self, fld, ptcl, dt, time):
         """boundary_communicator.py:531-553"""

@@ -1,0 +1,157 @@
+// b2_ext_kernels.cuh -- kernels of the solver variants around the hot loop: radial PML,
+// cross-deposition current correction, laser-antenna virtual particles.  All of them are HBM-bound
+// streaming passes: 2-D (iz, ir) grids with ir fastest (one 16-B double2 per access, coalesced) or
+// 1-D particle loops.  This header holds ONLY the __global__ bodies (no launches, no runtime calls) so
+// that tests/hostemu can compile the very same source for the CPU and check it without a GPU.
+#pragma once
+
+#ifndef B2_C_LIGHT
+#define B2_C_LIGHT 299792458.0
+#endif
+
+namespace b2ext {
+
+static __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+static __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+static __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+static __device__ __forceinline__ double2 rmul(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
+static __device__ __forceinline__ double2 imul(double2 a) { return make_double2(-a.y, a.x); }      // i*a
+static __device__ __forceinline__ double2 nimul(double2 a) { return make_double2(a.y, -a.x); }     // -i*a
+
+#define B2X_2D_INDEX                                                  \
+    const int ir = blockIdx.x * blockDim.x + threadIdx.x;             \
+    const int iz = blockIdx.y * blockDim.y + threadIdx.y;             \
+    if (ir >= Nr || iz >= Nz) return;                                 \
+    const size_t o = (size_t)iz * Nr + ir;
+
+// ---- PML split components in spectral space ------------------------------------------------------
+// cuda_push_eb_pml_standard / cuda_push_eb_pml_comoving (fbpic/fields/cuda_methods.py:305-331, 415-440;
+// CPU twins fbpic/fields/numba_methods.py:189-214, 358-383):
+//   E{p,m}_pml <- [T_eb] C E{p,m}_pml + c^2 [T_eb] S_w (-i kr/2 Bz)
+//   B{p,m}_pml <- [T_eb] C B{p,m}_pml -     [T_eb] S_w (-i kr/2 Ez)
+// Ez, Bz are the values BEFORE the regular push of the same step (spectral_grid.py:343-366 launches this
+// kernel first).  T_eb == nullptr selects the standard PSATD.
+template <bool COMOVING>
+__global__ void k_push_eb_pml(double2 *__restrict__ Ep_pml, double2 *__restrict__ Em_pml,
+                              double2 *__restrict__ Bp_pml, double2 *__restrict__ Bm_pml,
+                              const double2 *__restrict__ Ez, const double2 *__restrict__ Bz,
+                              const double *__restrict__ C, const double *__restrict__ S_w,
+                              const double2 *__restrict__ T_eb, const double *__restrict__ kr, int Nz, int Nr) {
+    B2X_2D_INDEX
+    const double c2 = B2_C_LIGHT * B2_C_LIGHT;
+    const double hk = 0.5 * kr[ir];
+    double2 TC = make_double2(C[o], 0.), TS = make_double2(S_w[o], 0.);
+    if (COMOVING) {
+        const double2 t = T_eb[o];
+        TC = rmul(C[o], t);
+        TS = rmul(S_w[o], t);
+    }
+    const double2 sE = rmul(c2 * hk, nimul(Bz[o]));     // c^2 (-i kr/2 Bz)
+    const double2 sB = rmul(hk, nimul(Ez[o]));          //     (-i kr/2 Ez)
+    const double2 dE = cmul(TS, sE), dB = cmul(TS, sB);
+    Ep_pml[o] = cadd(cmul(TC, Ep_pml[o]), dE);
+    Em_pml[o] = cadd(cmul(TC, Em_pml[o]), dE);
+    Bp_pml[o] = csub(cmul(TC, Bp_pml[o]), dB);
+    Bm_pml[o] = csub(cmul(TC, Bm_pml[o]), dB);
+}
+
+// ---- anisotropic damping in the last n_pml radial cells -----------------------------------------
+// cuda_damp_pml_EB (fbpic/boundaries/pml_damping.py:111-154): the PML part of Et, Bt is damped
+// (F -= F_pml; F_pml *= d; F += F_pml), Ez and Bz are damped entirely.  Grid: (i_pml, iz).
+__global__ void k_damp_pml(double2 *__restrict__ Et, double2 *__restrict__ Et_pml, double2 *__restrict__ Ez,
+                           double2 *__restrict__ Bt, double2 *__restrict__ Bt_pml, double2 *__restrict__ Bz,
+                           const double *__restrict__ damp, int n_pml, int Nz, int Nr) {
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    const int iz = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ip >= n_pml || iz >= Nz) return;
+    const double d = damp[ip];
+    const size_t o = (size_t)iz * Nr + (size_t)(Nr - n_pml + ip);
+    double2 e = Et[o], ep = Et_pml[o], b = Bt[o], bp = Bt_pml[o];
+    e = csub(e, ep);
+    b = csub(b, bp);
+    ep = rmul(d, ep);
+    bp = rmul(d, bp);
+    Et_pml[o] = ep;
+    Bt_pml[o] = bp;
+    Et[o] = cadd(e, ep);
+    Bt[o] = cadd(b, bp);
+    Ez[o] = rmul(d, Ez[o]);
+    Bz[o] = rmul(d, Bz[o]);
+}
+
+// ---- cross-deposition current correction ---------------------------------------------------------
+// cuda_correct_currents_crossdeposition_standard / _comoving (fbpic/fields/cuda_methods.py:144-171,
+// 200-232; CPU twins fbpic/fields/numba_methods.py:88-116, 243-275):
+//   Dz  = i kz Jz        + 1/2 a (rho_next - b rho_next_xy + rho_next_z  - b rho_prev)
+//   Dxy = kr (Jp - Jm)   + 1/2 a (rho_next + b rho_next_xy - rho_next_z  - b rho_prev)
+//   standard: a = 1/dt, b = 1 ; comoving: a = T_cc j_corr_coef, b = T_eb
+//   Jp -= Dxy/(2 kr), Jm += Dxy/(2 kr)  (kr != 0) ;  Jz += i Dz / kz  (kz != 0)
+// (the standard formula of the reference is the b = 1 case with the xy / z terms written in the other
+// order: same value.)
+template <bool COMOVING>
+__global__ void k_correct_cross(const double2 *__restrict__ rho_prev, const double2 *__restrict__ rho_next,
+                                const double2 *__restrict__ rho_next_z, const double2 *__restrict__ rho_next_xy,
+                                double2 *__restrict__ Jp, double2 *__restrict__ Jm, double2 *__restrict__ Jz,
+                                const double *__restrict__ kz_, const double *__restrict__ kr_,
+                                const double2 *__restrict__ T_cc, const double2 *__restrict__ j_corr_coef,
+                                const double2 *__restrict__ T_eb, double inv_dt, int Nz, int Nr) {
+    B2X_2D_INDEX
+    const double kz = kz_[iz], kr = kr_[ir];
+    const double2 rp = rho_prev[o], rn = rho_next[o], rz = rho_next_z[o], rxy = rho_next_xy[o];
+    double2 tz, txy;      // the rho combinations of Dz and Dxy, times a/2
+    if (COMOVING) {
+        const double2 a = rmul(0.5, cmul(T_cc[o], j_corr_coef[o]));
+        const double2 b = T_eb[o];
+        const double2 bxy = cmul(b, rxy), bp = cmul(b, rp);
+        tz = cmul(a, csub(cadd(csub(rn, bxy), rz), bp));
+        txy = cmul(a, csub(csub(cadd(rn, bxy), rz), bp));
+    } else {
+        tz = rmul(0.5 * inv_dt, csub(cadd(csub(rn, rxy), rz), rp));
+        txy = rmul(0.5 * inv_dt, csub(cadd(csub(rn, rz), rxy), rp));
+    }
+    const double2 jp = Jp[o], jm = Jm[o], jz = Jz[o];
+    const double2 Dz = cadd(rmul(kz, imul(jz)), tz);
+    const double2 Dxy = cadd(rmul(kr, csub(jp, jm)), txy);
+    if (kr != 0.) {
+        const double inv_kr = 1. / kr;
+        Jp[o] = cadd(jp, rmul(-0.5 * inv_kr, Dxy));
+        Jm[o] = cadd(jm, rmul(0.5 * inv_kr, Dxy));
+    }
+    if (kz != 0.) {
+        const double inv_kz = 1. / kz;
+        Jz[o] = cadd(jz, rmul(inv_kz, imul(Dz)));
+    }
+}
+
+// ---- laser antenna: virtual particles -------------------------------------------------------------
+// LaserAntenna.deposit_virtual_particles_gpu (fbpic/lpa_utils/laser/antenna_injection.py:357-391):
+// positions x = baseline + sign*excursion and normalised momenta u = v/c (sign*v for x, y) of the
+// positive (sign = +1) or negative (sign = -1) copy of the antenna particles; inv_gamma is 1 for them.
+// The result feeds the regular deposition kernel (order-independent, linear shapes).
+__global__ void k_antenna_particles(long long n, const double *__restrict__ bx, const double *__restrict__ by,
+                                    const double *__restrict__ ex, const double *__restrict__ ey,
+                                    const double *__restrict__ vx, const double *__restrict__ vy,
+                                    const double *__restrict__ vz, double sign,
+                                    double *__restrict__ x, double *__restrict__ y, double *__restrict__ ux,
+                                    double *__restrict__ uy, double *__restrict__ uz) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double inv_c = 1. / B2_C_LIGHT;
+    x[i] = bx[i] + sign * ex[i];
+    y[i] = by[i] + sign * ey[i];
+    ux[i] = sign * vx[i] * inv_c;
+    uy[i] = sign * vy[i] * inv_c;
+    uz[i] = vz[i] * inv_c;
+}
+
+// y[i] += a * x[i]   (LaserAntenna.push_x, antenna_injection.py:196-218; rounded product then rounded
+// sum like the cupy expression `y += (dt*push) * x`)
+__global__ void k_axpy(long long n, double a, const double *__restrict__ x, double *__restrict__ y) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    y[i] = __dadd_rn(y[i], __dmul_rn(a, x[i]));
+}
+
+}  // namespace b2ext

@@ -9,8 +9,8 @@ psatd_coefs.py:15 (`PsatdCoeffs`): same class, method and attribute names.
 Arrays are NumPy on the host until `send_fields_to_gpu()`, `DeviceArray`s (HBM)
 afterwards, exactly like the reference swaps NumPy for CuPy arrays.
 
-Not built (out of scope): PML split fields, cross-deposition
-correction, correct_divE.
+Radial PML split fields (`use_pml`) and the cross-deposition current correction
+ are built; correct_divE (CPU-only in the reference) is not.
 """
 import ctypes
 import numpy as np
@@ -22,6 +22,10 @@ from ._lib import DeviceArray, call, ptr_array, SpectralMode, DhtJob
 
 INTERP_FIELDS = ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'Jr', 'Jt', 'Jz', 'rho')
 SPECT_FIELDS = ('Ep', 'Em', 'Ez', 'Bp', 'Bm', 'Bz', 'Jp', 'Jm', 'Jz', 'rho_prev', 'rho_next')
+RHO_TYPES = ('rho_prev', 'rho_next', 'rho_next_z', 'rho_next_xy')  # fields.py:361
+PML_INTERP_FIELDS = ('Er_pml', 'Et_pml', 'Br_pml', 'Bt_pml')        # interpolation_grid.py:152-156
+PML_SPECT_FIELDS = ('Ep_pml', 'Em_pml', 'Bp_pml', 'Bm_pml')         # spectral_grid.py:102-106
+CROSS_SPECT_FIELDS = ('rho_next_z', 'rho_next_xy')                  # spectral_grid.py:97-99
 
 
 class BinomialSmoother(object):
@@ -61,9 +65,8 @@ class InterpolationGrid(object):
 
     def __init__(self, Nz, Nr, m, zmin, zmax, rmax, use_pml=False, use_cuda=True,
                  use_ruyten_shapes=True, use_modified_volume=True):
-        if use_pml:
-            raise NotImplementedError('radial PML is out of scope of this build (SURVEY 4d)')
-        self.Nz, self.Nr, self.m, self.use_pml = Nz, Nr, m, False
+        self.Nz, self.Nr, self.m, self.use_pml = Nz, Nr, m, bool(use_pml)
+        self._fields = INTERP_FIELDS + (PML_INTERP_FIELDS if self.use_pml else ())
         dr = rmax / Nr
         dz = (zmax - zmin) / Nz
         self.dr, self.dz = dr, dz
@@ -73,7 +76,7 @@ class InterpolationGrid(object):
         vol = ht.cell_volumes(m, Nr, rmax, dz, use_modified_volume)
         self.invvol = 1. / vol
         self.ruyten_linear_coef, self.ruyten_cubic_coef = ht.ruyten_coefs(vol, dr, dz, use_ruyten_shapes)
-        for k in INTERP_FIELDS:
+        for k in self._fields:
             setattr(self, k, np.zeros((Nz, Nr), dtype='complex'))
         self.use_cuda = True
         self.d_invvol = self.d_ruyten_linear_coef = self.d_ruyten_cubic_coef = None
@@ -87,7 +90,7 @@ class InterpolationGrid(object):
         return self.rmin + (0.5 + np.arange(self.Nr)) * self.dr
 
     def send_fields_to_gpu(self):
-        for k in INTERP_FIELDS:
+        for k in self._fields:
             setattr(self, k, _lib.to_device(getattr(self, k)))
         if self.d_invvol is None:
             self.d_invvol = DeviceArray.from_numpy(self.invvol)
@@ -95,7 +98,7 @@ class InterpolationGrid(object):
             self.d_ruyten_cubic_coef = DeviceArray.from_numpy(self.ruyten_cubic_coef)
 
     def receive_fields_from_gpu(self):
-        for k in INTERP_FIELDS:
+        for k in self._fields:
             setattr(self, k, _lib.to_host(getattr(self, k)))
 
     def _names(self, fieldtype):
@@ -250,13 +253,13 @@ class SpectralGrid(object):
 
     def __init__(self, kz_modified, kr, m, kz_true, dz, dr, current_correction, smoother,
                  use_pml=False, use_cuda=True):
-        if use_pml:
-            raise NotImplementedError('radial PML is out of scope of this build')
-        if current_correction != 'curl-free':
-            raise NotImplementedError("only current_correction='curl-free' is built (SURVEY 3d)")
+        if current_correction not in ('curl-free', 'cross-deposition'):
+            raise ValueError('Unkown current correction:%s' % current_correction)
         Nz, Nr = len(kz_modified), len(kr)
-        self.Nz, self.Nr, self.m, self.use_pml = Nz, Nr, m, False
-        for k in SPECT_FIELDS:
+        self.Nz, self.Nr, self.m, self.use_pml = Nz, Nr, m, bool(use_pml)
+        self._fields = SPECT_FIELDS + (PML_SPECT_FIELDS if self.use_pml else ()) + \
+            (CROSS_SPECT_FIELDS if current_correction == 'cross-deposition' else ())
+        for k in self._fields:
             setattr(self, k, np.zeros((Nz, Nr), dtype='complex'))
         self.kz, self.kr = np.meshgrid(kz_modified, kr, indexing='ij')
         self.kz_1d, self.kr_1d = np.ascontiguousarray(kz_modified), np.ascontiguousarray(kr)
@@ -267,7 +270,7 @@ class SpectralGrid(object):
         self.d_kz = self.d_kr = self.d_inv_k2 = self.d_filter_array_z = self.d_filter_array_r = None
 
     def send_fields_to_gpu(self):
-        for k in SPECT_FIELDS:
+        for k in self._fields:
             setattr(self, k, _lib.to_device(getattr(self, k)))
         if self.d_kz is None:
             self.d_kz = DeviceArray.from_numpy(self.kz_1d)
@@ -277,7 +280,7 @@ class SpectralGrid(object):
             self.d_filter_array_r = DeviceArray.from_numpy(self.filter_array_r)
 
     def receive_fields_from_gpu(self):
-        for k in SPECT_FIELDS:
+        for k in self._fields:
             setattr(self, k, _lib.to_host(getattr(self, k)))
 
     def _mode_struct(self, ps):
@@ -296,16 +299,34 @@ class SpectralGrid(object):
         return s
 
     def correct_currents(self, dt, ps, current_correction):
-        if current_correction != 'curl-free':
-            raise NotImplementedError("only current_correction='curl-free' is built")
+        """spectral_grid.py:198-296"""
         s = self._mode_struct(ps)
-        call.b2_correct_currents(_lib.context().handle, ctypes.byref(s), int(ps.V is not None),
-                                 1. / dt, self.Nz, self.Nr, None)
+        if current_correction == 'curl-free':
+            call.b2_correct_currents(_lib.context().handle, ctypes.byref(s), int(ps.V is not None),
+                                     1. / dt, self.Nz, self.Nr, None)
+        elif current_correction == 'cross-deposition':
+            _need_gpu(self.rho_next_z)
+            call.b2_correct_currents_cross(_lib.context().handle, ctypes.byref(s), self.rho_next_z.ptr,
+                                           self.rho_next_xy.ptr, int(ps.V is not None), 1. / dt,
+                                           self.Nz, self.Nr, None)
+        else:
+            raise ValueError('Unkown current correction:%s' % current_correction)
+
+    def push_eb_pml_with(self, ps):
+        """Split PML components (spectral_grid.py:343-348, 358-363); reads the Ez, Bz of BEFORE the
+        regular push, so it is issued first."""
+        _need_gpu(self.Ep_pml)
+        call.b2_push_eb_pml(_lib.context().handle, self.Ep_pml.ptr, self.Em_pml.ptr, self.Bp_pml.ptr,
+                            self.Bm_pml.ptr, self.Ez.ptr, self.Bz.ptr, ps.device('C').ptr, ps.device('S_w').ptr,
+                            ps.device('T_eb').ptr if ps.V is not None else None, self.d_kr.ptr,
+                            self.Nz, self.Nr, None)
 
     def push_eb_with(self, ps, use_true_rho=False):
         """E, B push; the kernel also performs push_rho (rho_prev <- rho_next, rho_next <- 0),
         so `push_rho()` below is a no-op marker when called right after it."""
         assert self.m == ps.m
+        if self.use_pml:
+            self.push_eb_pml_with(ps)
         s = self._mode_struct(ps)
         call.b2_push_eb(_lib.context().handle, ctypes.byref(s), int(ps.V is not None), ps.dt,
                         0. if ps.V is None else ps.V, int(bool(use_true_rho)), self.Nz, self.Nr, None)
@@ -313,6 +334,8 @@ class SpectralGrid(object):
 
     def correct_and_push(self, ps, use_true_rho=False):
         """Fused correct_currents + push_eb + push_rho: one pass over the mode's arrays."""
+        if self.use_pml:
+            self.push_eb_pml_with(ps)
         s = self._mode_struct(ps)
         call.b2_correct_push(_lib.context().handle, ctypes.byref(s), int(ps.V is not None), ps.dt,
                              0. if ps.V is None else ps.V, int(bool(use_true_rho)), self.Nz, self.Nr, None)
@@ -329,7 +352,7 @@ class SpectralGrid(object):
     def filter(self, fieldtype):
         if fieldtype in ('J', 'E', 'B'):
             arrs = [getattr(self, fieldtype + c) for c in ('p', 'm', 'z')]
-        elif fieldtype in ('rho_prev', 'rho_next'):
+        elif fieldtype in RHO_TYPES:
             arrs = [getattr(self, fieldtype)]
         else:
             raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
@@ -346,18 +369,16 @@ class Fields(object):
                  use_pml=False, use_galilean=True, current_correction='curl-free', use_cuda=True,
                  smoother=None, create_threading_buffers=False, use_ruyten_shapes=True,
                  use_modified_volume=True):
-        if use_pml:
-            raise NotImplementedError('radial PML is out of scope of this build')
         if current_correction not in ('curl-free', 'cross-deposition'):
             raise ValueError('Unkown current correction:%s' % current_correction)
         self.Nz, self.Nr, self.rmax, self.Nm, self.dt = Nz, Nr, rmax, Nm, dt
         self.n_order, self.v_comoving, self.use_galilean = n_order, v_comoving, use_galilean
         self.smoother = smoother if smoother is not None else BinomialSmoother(1, False)
-        self.use_cuda, self.use_pml = True, False
+        self.use_cuda, self.use_pml = True, bool(use_pml)
         self.data_is_on_gpu = False
         self.current_correction = current_correction
         self.trans = [SpectralTransformer(Nz, Nr, m, rmax) for m in range(Nm)]
-        self.interp = [InterpolationGrid(Nz, Nr, m, zmin, zmax, rmax,
+        self.interp = [InterpolationGrid(Nz, Nr, m, zmin, zmax, rmax, use_pml=use_pml,
                                          use_ruyten_shapes=use_ruyten_shapes,
                                          use_modified_volume=use_modified_volume) for m in range(Nm)]
         dz = (zmax - zmin) / Nz
@@ -367,7 +388,8 @@ class Fields(object):
         for m in range(Nm):
             kr = 2 * np.pi * self.trans[m].dht0.get_nu()
             self.spect.append(SpectralGrid(kz_modified, kr, m, kz_true, self.interp[m].dz,
-                                           self.interp[m].dr, current_correction, self.smoother))
+                                           self.interp[m].dr, current_correction, self.smoother,
+                                           use_pml=use_pml))
             self.psatd.append(PsatdCoeffs(kz_modified, kr, m, dt, Nz, Nr, V=v_comoving,
                                           use_galilean=use_galilean))
         self.exchanged_source = {'J': False, 'rho_prev': False, 'rho_new': False,
@@ -401,6 +423,9 @@ class Fields(object):
             assert self.exchanged_source['rho_prev'] is False
             assert self.exchanged_source['rho_next'] is False
             assert self.exchanged_source['J'] is False
+            if self.current_correction == 'cross-deposition':
+                assert self.exchanged_source['rho_next_xy'] is False
+                assert self.exchanged_source['rho_next_z'] is False
         for m in range(self.Nm):
             self.spect[m].correct_currents(self.dt, self.psatd[m], self.current_correction)
 
@@ -422,8 +447,12 @@ class Fields(object):
                 tr.interp2spect_scal(getattr(g, f + 'z'), getattr(s, f + 'z'))
                 tr.interp2spect_vect(getattr(g, f + 'r'), getattr(g, f + 't'),
                                      getattr(s, f + 'p'), getattr(s, f + 'm'))
-            elif fieldtype in ('rho_prev', 'rho_next'):
+            elif fieldtype in RHO_TYPES:
                 tr.interp2spect_scal(g.rho, getattr(s, fieldtype))
+            elif fieldtype in ('E_pml', 'B_pml'):          # fields.py:341-352
+                f = fieldtype[0]
+                tr.interp2spect_vect(getattr(g, f + 'r_pml'), getattr(g, f + 't_pml'),
+                                     getattr(s, f + 'p_pml'), getattr(s, f + 'm_pml'))
             else:
                 raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
 
@@ -435,8 +464,12 @@ class Fields(object):
                 tr.spect2interp_scal(getattr(s, f + 'z'), getattr(g, f + 'z'))
                 tr.spect2interp_vect(getattr(s, f + 'p'), getattr(s, f + 'm'),
                                      getattr(g, f + 'r'), getattr(g, f + 't'))
-            elif fieldtype in ('rho_prev', 'rho_next'):
+            elif fieldtype in RHO_TYPES:
                 tr.spect2interp_scal(getattr(s, fieldtype), g.rho)
+            elif fieldtype in ('E_pml', 'B_pml'):          # fields.py:398-409
+                f = fieldtype[0]
+                tr.spect2interp_vect(getattr(s, f + 'p_pml'), getattr(s, f + 'm_pml'),
+                                     getattr(g, f + 'r_pml'), getattr(g, f + 't_pml'))
             else:
                 raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
 
@@ -448,7 +481,7 @@ class Fields(object):
             f = fieldtype
             return [(getattr(s, f + 'z'), getattr(g, f + 'z')), (getattr(s, f + 'p'), getattr(g, f + 'r')),
                     (getattr(s, f + 'm'), getattr(g, f + 't'))]
-        if fieldtype in ('rho_prev', 'rho_next'):
+        if fieldtype in RHO_TYPES:
             return [(getattr(s, fieldtype), g.rho)]
         raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
 
@@ -505,7 +538,7 @@ class Fields(object):
                 jobs.append(DhtJob(t['buf'][0].ptr, None, s.Jz.ptr, None, t['F0'].ptr, None, fz, _lib.DHT_SCALAR))
                 jobs.append(DhtJob(t['buf'][1].ptr, t['buf'][2].ptr, s.Jp.ptr, s.Jm.ptr, t['Fp'].ptr, t['Fm'].ptr,
                                    fz, _lib.DHT_RT_TO_PM))
-            elif fieldtype in ('rho_prev', 'rho_next'):
+            elif fieldtype in RHO_TYPES:
                 ffts.append((g.rho, t['buf'][0]))
                 jobs.append(DhtJob(t['buf'][0].ptr, None, getattr(s, fieldtype).ptr, None, t['F0'].ptr, None,
                                    fz, _lib.DHT_SCALAR))

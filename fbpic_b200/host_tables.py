@@ -250,3 +250,9 @@ def damp_array(n_guard, nz_damp, n_inject):
     d = np.where(i < edge + nz_damp / 2.,
                  np.sin((i - edge) * np.pi / (2 * nz_damp / 2.))**2, 1.)
     return np.where(i < edge, 0., d)
+
+
+def pml_damp_array(n_pml, cdt_over_dr):
+    """Radial PML damping profile (fbpic/boundaries/pml_damping.py:86-108)."""
+    x_pml = np.arange(n_pml) * 1. / n_pml
+    return np.exp(-4. * cdt_over_dr * x_pml**2)

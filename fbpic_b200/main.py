@@ -5,9 +5,9 @@ libfbpic_b200.so (no Numba, no CuPy, no CPU fallback).
 
 Hot-path scope: gather / push / deposit / sort, z-FFT + Hankel GEMM,
 current correction + PSATD push, z guard-cell exchange and particle migration.
-Out of scope and therefore rejected loudly: PML (`boundaries['r']='open'`),
-cross-deposition, laser antennas, external fields, diagnostics, checkpoints,
-ionization.  The moving window with continuous injection is built.
+Widened per SURVEY 8f: moving window with continuous injection (rank 1), radial PML
+(`boundaries['r']='open'`) and the cross-deposition current correction (rank 4).
+Out of scope and therefore rejected loudly: diagnostics, checkpoints, ionization.
 """
 import numpy as np
 from scipy.constants import m_e, m_p, e, c
@@ -54,12 +54,12 @@ class Simulation(object):
         self.comm = BoundaryCommunicator(Nz, zmin, zmax, Nr, rmax, Nm, dt, self.v_comoving,
                                          self.use_galilean, boundaries, n_order, n_guard, n_damp,
                                          cdt_over_dr, None, exchange_period, use_all_mpi_ranks)
-        self.use_pml = False
+        self.use_pml = self.comm.use_pml
         zmin, zmax, Nz = self.comm.divide_into_domain()
         Nr = self.comm.get_Nr(with_damp=True)
         rmax = self.comm.get_rmax(with_damp=True)
         self.fld = Fields(Nz, zmax, Nr, rmax, Nm, dt, n_order=n_order, zmin=zmin,
-                          v_comoving=v_comoving, use_galilean=use_galilean,
+                          v_comoving=v_comoving, use_pml=self.use_pml, use_galilean=use_galilean,
                           current_correction=current_correction, smoother=smoother,
                           use_ruyten_shapes=use_ruyten_shapes,
                           use_modified_volume=use_modified_volume)
@@ -114,7 +114,7 @@ class Simulation(object):
         single = (self.comm.size == 1)
         periodic_single = single and self.comm.n_guard == 0
         fuse_gp = self.fused and move_positions and move_momenta
-        fuse_cp = self.fused and correct_currents and single
+        fuse_cp = self.fused and correct_currents and single and fld.current_correction == 'curl-free'
 
         import time as _time
         t_start = _time.perf_counter()
@@ -125,6 +125,9 @@ class Simulation(object):
         self.comm.damp_EB_open_boundary(fld.interp)
         fld.interp2spect('E')
         fld.interp2spect('B')
+        if self.use_pml:                              # main.py:413-415
+            fld.interp2spect('E_pml')
+            fld.interp2spect('B_pml')
 
         # Single periodic domain, fused mode: z is wrapped inside the second position push and
         # rho_prev of step n+1 is (bit for bit) the rho_next that push_rho already moved over, so
@@ -164,9 +167,12 @@ class Simulation(object):
                 species.keep_fields_sorted = False
 
             self.deposit('J', exchange=(correct_currents is False))
+            cross = correct_currents and fld.current_correction == 'cross-deposition'
+            if cross:                                 # main.py:512-514
+                self.cross_deposit(move_positions)
             # fused mode: the second half push rides inside the rho deposition kernel when every
             # species deposits and already has sort locality
-            fuse_pr = self.fused and move_positions and len(ptcl) > 0 and \
+            fuse_pr = self.fused and move_positions and len(ptcl) > 0 and (not cross) and \
                 all((sp.q != 0) and (not sp.is_tracer) and getattr(sp, '_order_matches_prefix', False)
                     for sp in ptcl)
             if fuse_pr:
@@ -207,7 +213,7 @@ class Simulation(object):
                 fld.push(use_true_rho, check_exchanges=(self.comm.size > 1))
             if self.comm.moving_win is not None:
                 self.comm.move_grids(fld, ptcl, dt, self.time)
-            self.exchange_and_damp_EB(skip_identity=periodic_single and self.fused)
+            self.exchange_and_damp_EB(skip_identity=periodic_single and self.fused and not self.use_pml)
             self.time += dt
             self.iteration += 1
 
@@ -262,6 +268,17 @@ class Simulation(object):
         trip is an identity (no neighbour, no damping): `skip_identity` drops those 12 FFTs per
         mode and goes straight to spect2interp."""
         fld = self.fld
+        if self.use_pml:
+            # exchange / damp act in z AND r: full transforms both ways (main.py:732-761)
+            for ft in ('E', 'B', 'E_pml', 'B_pml'):
+                fld.spect2interp(ft)
+            self.comm.exchange_fields(fld.interp, 'E', 'replace')
+            self.comm.exchange_fields(fld.interp, 'B', 'replace')
+            self.comm.damp_EB_open_boundary(fld.interp)
+            self.comm.damp_pml_EB(fld.interp)
+            for ft in ('E', 'B', 'E_pml', 'B_pml'):
+                fld.interp2spect(ft)
+            return
         if not skip_identity:
             if self.fused:
                 # E and B together: one batch of concurrent z-FFTs each way, one NCCL group
@@ -284,6 +301,19 @@ class Simulation(object):
         else:
             fld.spect2interp('E')
             fld.spect2interp('B')
+
+    def cross_deposit(self, move_positions):
+        """fbpic/main.py:672-717: with the particles at time n+1/2, deposit rho at (z[n], x[n+1]) and at
+        (z[n+1], x[n]) for the cross-deposition current correction."""
+        dt = self.dt
+        for frac, sx, sz, ft in ((0.5, 1., -1., 'rho_next_xy'), (1., -1., 1., 'rho_next_z'), (0.5, 1., -1., None)):
+            if move_positions:
+                for species in self.ptcl:
+                    species.push_x(frac * dt, x_push=sx, y_push=sx, z_push=sz)
+            if self.use_galilean:
+                self.shift_galilean_boundaries(sz * frac * dt)
+            if ft is not None:
+                self.deposit(ft)
 
     def shift_galilean_boundaries(self, dt):
         """fbpic/main.py:772-789"""

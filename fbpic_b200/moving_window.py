@@ -54,6 +54,8 @@ class MovingWindow(object):
         signature defaults to shift_currents=True -- its docstring says False -- so the J returned
         at the end of step() is the shifted one.)"""
         names = ['Ep', 'Em', 'Ez', 'Bp', 'Bm', 'Bz']
+        if grid.use_pml:        # moving_window.py:172-176
+            names += ['Ep_pml', 'Em_pml', 'Bp_pml', 'Bm_pml']
         if shift_rho:
             names.append('rho_prev')
         if shift_currents:

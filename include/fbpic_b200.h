@@ -274,6 +274,35 @@ int b2_nccl_send(b2_ctx *ctx, const void *d_buf, size_t nbytes, int peer, void *
 int b2_nccl_recv(b2_ctx *ctx, void *d_buf, size_t nbytes, int peer, void *stream);
 int b2_nccl_allreduce_max_f64(b2_ctx *ctx, double *d_buf, size_t count, void *stream);
 
+/* ---- solver variants around the hot loop ----------------------------- */
+/* radial PML, spectral push of the split components: cuda_push_eb_pml_standard / _comoving
+ * (fbpic/fields/cuda_methods.py:305,415; dispatch spectral_grid.py:343-366).  Must run BEFORE the
+ * regular E,B push of the step (it reads the old Ez, Bz).  d_T_eb: complex [Nz,Nr] (comoving / Galilean)
+ * or NULL (standard PSATD); d_C, d_S_w: real [Nz,Nr]; d_kr: [Nr]. */
+int b2_push_eb_pml(b2_ctx *ctx, void *d_Ep_pml, void *d_Em_pml, void *d_Bp_pml, void *d_Bm_pml,
+                   const void *d_Ez, const void *d_Bz, const double *d_C, const double *d_S_w,
+                   const void *d_T_eb, const double *d_kr, int Nz, int Nr, void *stream);
+/* radial PML, anisotropic damping of the last n_pml radial cells in real space: cuda_damp_pml_EB
+ * (fbpic/boundaries/pml_damping.py:111-154); d_damp: [n_pml] */
+int b2_damp_pml(b2_ctx *ctx, void *d_Et, void *d_Et_pml, void *d_Ez, void *d_Bt, void *d_Bt_pml, void *d_Bz,
+                const double *d_damp, int n_pml, int Nz, int Nr, void *stream);
+/* cross-deposition current correction: cuda_correct_currents_crossdeposition_standard / _comoving
+ * (fbpic/fields/cuda_methods.py:144,200; dispatch spectral_grid.py:231-258).  Uses Jp,Jm,Jz,rho_prev,
+ * rho_next,kz,kr (and T_cc, j_corr_coef, T_eb when comoving) of `mode`. */
+int b2_correct_currents_cross(b2_ctx *ctx, const b2_spectral_mode *mode, const void *d_rho_next_z,
+                              const void *d_rho_next_xy, int comoving, double inv_dt, int Nz, int Nr,
+                              void *stream);
+/* laser antenna (fbpic/lpa_utils/laser/antenna_injection.py:357-391): positions and normalised momenta of
+ * the positive (sign=+1) / negative (sign=-1) copy of the virtual particles, to be handed to
+ * b2_deposit_rho / b2_deposit_J (linear shapes, inv_gamma = 1):
+ *   x = bx + sign*ex, y = by + sign*ey, ux = sign*vx/c, uy = sign*vy/c, uz = vz/c */
+int b2_antenna_particles(b2_ctx *ctx, int64_t n, const double *d_bx, const double *d_by, const double *d_ex,
+                         const double *d_ey, const double *d_vx, const double *d_vy, const double *d_vz,
+                         double sign, double *d_x, double *d_y, double *d_ux, double *d_uy, double *d_uz,
+                         void *stream);
+/* y += a*x (LaserAntenna.push_x, antenna_injection.py:196-218) */
+int b2_axpy(b2_ctx *ctx, int64_t n, double a, const double *d_x, double *d_y, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -188,9 +188,23 @@ class OracleSim(object):
     FIELDS_I = ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'Jr', 'Jt', 'Jz', 'rho')
     FIELDS_S = ('Ep', 'Em', 'Ez', 'Bp', 'Bm', 'Bz', 'Jp', 'Jm', 'Jz', 'rho_prev', 'rho_next')
 
+    PML_I = ('Er_pml', 'Et_pml', 'Br_pml', 'Bt_pml')
+    PML_S = ('Ep_pml', 'Em_pml', 'Bp_pml', 'Bm_pml')
+
     def __init__(self, Nz, zmax, Nr, rmax, Nm, dt, zmin=0., n_order=-1,
                  v_comoving=None, use_galilean=True, particle_shape='linear',
-                 filter_currents=True, nthreads=None):
+                 filter_currents=True, nthreads=None, nr_damp=0,
+                 current_correction='curl-free'):
+        # radial PML (boundaries['r']='open'): the grid is enlarged by nr_damp cells
+        # (main.py:293-294, boundary_communicator.py:371-397); particles are only gathered
+        # inside the physical radius (particles.py:700-704)
+        self.nr_damp = nr_damp
+        self.use_pml = nr_damp > 0
+        self.rmax_gather = rmax
+        rmax = (Nr + nr_damp) * (rmax / Nr)
+        Nr = Nr + nr_damp
+        self.cdt_over_dr = c * dt / (rmax / Nr)
+        self.current_correction = current_correction
         self.Nz, self.Nr, self.Nm, self.dt = Nz, Nr, Nm, dt
         self.zmin, self.zmax, self.rmax = zmin, zmax, rmax
         self.dz = (zmax - zmin) / Nz
@@ -217,8 +231,13 @@ class OracleSim(object):
             self.ruyten.append(ht.ruyten_coefs(vol, self.dr, self.dz))
             self.filt.append(ht.binomial_filters(kz_true, kr, self.dz, self.dr))
             self.inv_k2.append(ht.inverse_k2(self.kz, kr))
-            self.interp.append({k: np.zeros((Nz, Nr), dtype=np.complex128) for k in self.FIELDS_I})
-            self.spect.append({k: np.zeros((Nz, Nr), dtype=np.complex128) for k in self.FIELDS_S})
+            names_i = self.FIELDS_I + (self.PML_I if self.use_pml else ())
+            names_s = self.FIELDS_S + (self.PML_S if self.use_pml else ()) + \
+                (('rho_next_z', 'rho_next_xy') if current_correction == 'cross-deposition' else ())
+            self.interp.append({k: np.zeros((Nz, Nr), dtype=np.complex128) for k in names_i})
+            self.spect.append({k: np.zeros((Nz, Nr), dtype=np.complex128) for k in names_s})
+        # pml_damping.py:86-108
+        self.pml_damp = np.exp(-4. * self.cdt_over_dr * (np.arange(nr_damp) * 1. / max(nr_damp, 1))**2)
         self.species = []
 
     # -- species: dict of SoA arrays + q, m
@@ -237,7 +256,7 @@ class OracleSim(object):
         if sp['q'] == 0:
             return
         grids = [tuple(g[k] for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz')) for g in self.interp]
-        gather(sp['x'], sp['y'], sp['z'], self.rmax, self.invdz, self.zmin, self.Nz,
+        gather(sp['x'], sp['y'], sp['z'], self.rmax_gather, self.invdz, self.zmin, self.Nz,
                self.invdr, 0., self.Nr, grids, self.cubic,
                sp['Ex'], sp['Ey'], sp['Ez'], sp['Bx'], sp['By'], sp['Bz'])
 
@@ -247,8 +266,9 @@ class OracleSim(object):
         push_p(sp['ux'], sp['uy'], sp['uz'], sp['inv_gamma'], sp['Ex'], sp['Ey'], sp['Ez'],
                sp['Bx'], sp['By'], sp['Bz'], sp['q'], sp['m'], self.dt)
 
-    def push_x(self, sp, dt):
-        push_x(sp['x'], sp['y'], sp['z'], sp['ux'], sp['uy'], sp['uz'], sp['inv_gamma'], dt)
+    def push_x(self, sp, dt, x_push=1., y_push=1., z_push=1.):
+        push_x(sp['x'], sp['y'], sp['z'], sp['ux'], sp['uy'], sp['uz'], sp['inv_gamma'], dt,
+               x_push, y_push, z_push)
 
     def deposit_interp(self, what):
         """erase + deposit all species + fold + divide by volume (main.py:628-657)."""
@@ -296,6 +316,9 @@ class OracleSim(object):
             if ft in ('E', 'B'):
                 s[ft + 'z'][:, :] = tr.interp2spect_scal(g[ft + 'z'])
                 s[ft + 'p'][:, :], s[ft + 'm'][:, :] = tr.interp2spect_vect(g[ft + 'r'], g[ft + 't'])
+            elif ft in ('E_pml', 'B_pml'):        # fields.py:341-352
+                f = ft[0]
+                s[f + 'p_pml'][:, :], s[f + 'm_pml'][:, :] = tr.interp2spect_vect(g[f + 'r_pml'], g[f + 't_pml'])
             else:
                 raise ValueError(ft)
 
@@ -307,11 +330,72 @@ class OracleSim(object):
                 g[ft + 'r'][:, :], g[ft + 't'][:, :] = tr.spect2interp_vect(s[ft + 'p'], s[ft + 'm'])
             elif ft in ('rho_prev', 'rho_next'):
                 g['rho'][:, :] = tr.spect2interp_scal(s[ft])
+            elif ft in ('E_pml', 'B_pml'):        # fields.py:398-409
+                f = ft[0]
+                g[f + 'r_pml'][:, :], g[f + 't_pml'][:, :] = tr.spect2interp_vect(s[f + 'p_pml'], s[f + 'm_pml'])
             else:
                 raise ValueError(ft)
 
+    def damp_pml_EB(self):
+        """pml_damping.py:46-83 (CPU branch)"""
+        n, d = self.nr_damp, self.pml_damp[np.newaxis, :]
+        for g in self.interp:
+            g['Et'][:, -n:] -= g['Et_pml'][:, -n:]
+            g['Bt'][:, -n:] -= g['Bt_pml'][:, -n:]
+            g['Et_pml'][:, -n:] *= d
+            g['Bt_pml'][:, -n:] *= d
+            g['Et'][:, -n:] += g['Et_pml'][:, -n:]
+            g['Bt'][:, -n:] += g['Bt_pml'][:, -n:]
+            g['Bz'][:, -n:] *= d
+            g['Ez'][:, -n:] *= d
+
+    def correct_currents_cross(self):
+        """numba_methods.py:88-116 (standard), :243-275 (comoving)."""
+        inv_dt = 1. / self.dt
+        for m in range(self.Nm):
+            s, t = self.spect[m], self.coef[m]
+            kz = np.broadcast_to(self.kz[:, None], (self.Nz, self.Nr))
+            kr = np.broadcast_to(self.kr[m][None, :], (self.Nz, self.Nr))
+            rn, rp, rz, rxy = s['rho_next'], s['rho_prev'], s['rho_next_z'], s['rho_next_xy']
+            if self.v_comoving is None:
+                Dz = 1.j * kz * s['Jz'] + 0.5 * inv_dt * (rn - rxy + rz - rp)
+                Dxy = kr * (s['Jp'] - s['Jm']) + 0.5 * inv_dt * (rn - rz + rxy - rp)
+            else:
+                a, b = 0.5 * t['T_cc'] * t['j_corr_coef'], t['T_eb']
+                Dz = 1.j * kz * s['Jz'] + a * (rn - b * rxy + rz - b * rp)
+                Dxy = kr * (s['Jp'] - s['Jm']) + a * (rn + b * rxy - rz - b * rp)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                dxy = np.where(kr != 0, 0.5 * Dxy / kr, 0.)
+                dz = np.where(kz != 0, 1.j * Dz / kz, 0.)
+            s['Jp'] -= dxy
+            s['Jm'] += dxy
+            s['Jz'] += dz
+
+    def cross_deposit(self, move_positions):
+        """main.py:672-717"""
+        dt = self.dt
+        if move_positions:
+            for sp in self.species:
+                self.push_x(sp, 0.5 * dt, 1., 1., -1.)
+        if self.use_galilean:
+            self.shift_galilean(-0.5 * dt)
+        self.deposit('rho_next_xy')
+        if move_positions:
+            for sp in self.species:
+                self.push_x(sp, dt, -1., -1., 1.)
+        if self.use_galilean:
+            self.shift_galilean(dt)
+        self.deposit('rho_next_z')
+        if move_positions:
+            for sp in self.species:
+                self.push_x(sp, 0.5 * dt, 1., 1., -1.)
+        if self.use_galilean:
+            self.shift_galilean(-0.5 * dt)
+
     def correct_currents(self):
         """numba_methods.py:64-86 (standard), :217-241 (comoving)."""
+        if self.current_correction == 'cross-deposition':
+            return self.correct_currents_cross()
         inv_dt = 1. / self.dt
         for m in range(self.Nm):
             s, t = self.spect[m], self.coef[m]
@@ -338,6 +422,13 @@ class OracleSim(object):
             Bp, Bm, Bz = s['Bp'], s['Bm'], s['Bz']
             Jp, Jm, Jz = s['Jp'], s['Jm'], s['Jz']
             std = self.v_comoving is None
+            if self.use_pml:
+                # split components first, from the old Ez, Bz (numba_methods.py:189-214, 358-383)
+                Tp = 1. if std else t['T_eb']
+                for f in ('Ep_pml', 'Em_pml'):
+                    s[f][:, :] = Tp * C * s[f] + c2 * Tp * S_w * (-1.j * 0.5 * kr * Bz)
+                for f in ('Bp_pml', 'Bm_pml'):
+                    s[f][:, :] = Tp * C * s[f] - Tp * S_w * (-1.j * 0.5 * kr * Ez)
             if use_true_rho:
                 rho_diff = t['rho_next_coef'] * s['rho_next'] - t['rho_prev_coef'] * s['rho_prev']
             else:
@@ -379,6 +470,9 @@ class OracleSim(object):
         dt = self.dt
         self.interp2spect('E')
         self.interp2spect('B')
+        if self.use_pml:
+            self.interp2spect('E_pml')
+            self.interp2spect('B_pml')
         for i_step in range(N):
             # single periodic domain: exchange_period == 1 (boundary_communicator.py:283-286)
             for sp in self.species:
@@ -397,6 +491,8 @@ class OracleSim(object):
             if self.use_galilean:
                 self.shift_galilean(0.5 * dt)
             self.deposit('J')
+            if correct_currents and self.current_correction == 'cross-deposition':
+                self.cross_deposit(move_positions)
             if move_positions:
                 for sp in self.species:
                     self.push_x(sp, 0.5 * dt)
@@ -410,6 +506,13 @@ class OracleSim(object):
             # round trip is an identity; only the final spect2interp remains.
             self.spect2interp('E')
             self.spect2interp('B')
+            if self.use_pml:
+                # full transforms both ways around the radial damping (main.py:732-761)
+                self.spect2interp('E_pml')
+                self.spect2interp('B_pml')
+                self.damp_pml_EB()
+                for ft in ('E', 'B', 'E_pml', 'B_pml'):
+                    self.interp2spect(ft)
             self.time += dt
             self.iteration += 1
         self.spect2interp('J')

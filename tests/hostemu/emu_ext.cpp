@@ -1,0 +1,63 @@
+// tests/hostemu/emu_ext.cpp -- TEST INFRASTRUCTURE.  Runs the kernel bodies of
+// fbpic_b200/csrc/b2_ext_kernels.cuh on the CPU with the launch geometry of b2_ext.cu, so that their
+// index arithmetic and formulas can be checked against NumPy / reference fixtures in the GPU-less
+// build container.  Never loaded by the product (fbpic_b200/_lib.py only knows libfbpic_b200.so).
+#include "cuda_shim.h"
+#include "../../fbpic_b200/csrc/b2_ext_kernels.cuh"
+
+static emu_dim3 grid2d(int Nz, int Nr, emu_dim3 b) { return emu_dim3((Nr + b.x - 1) / b.x, (Nz + b.y - 1) / b.y); }
+
+extern "C" {
+
+int emu_push_eb_pml(void *Ep, void *Em, void *Bp, void *Bm, const void *Ez, const void *Bz, const double *C,
+                    const double *S_w, const void *T_eb, const double *kr, int Nz, int Nr) {
+    emu_dim3 blk(64, 4);
+    if (T_eb)
+        EMU_LAUNCH(grid2d(Nz, Nr, blk), blk, b2ext::k_push_eb_pml<true>, (double2 *)Ep, (double2 *)Em, (double2 *)Bp,
+                   (double2 *)Bm, (const double2 *)Ez, (const double2 *)Bz, C, S_w, (const double2 *)T_eb, kr, Nz, Nr);
+    else
+        EMU_LAUNCH(grid2d(Nz, Nr, blk), blk, b2ext::k_push_eb_pml<false>, (double2 *)Ep, (double2 *)Em, (double2 *)Bp,
+                   (double2 *)Bm, (const double2 *)Ez, (const double2 *)Bz, C, S_w, (const double2 *)nullptr, kr, Nz, Nr);
+    return 0;
+}
+
+int emu_damp_pml(void *Et, void *Et_pml, void *Ez, void *Bt, void *Bt_pml, void *Bz, const double *damp, int n_pml,
+                 int Nz, int Nr) {
+    emu_dim3 blk(32, 8);
+    EMU_LAUNCH(grid2d(Nz, n_pml, blk), blk, b2ext::k_damp_pml, (double2 *)Et, (double2 *)Et_pml, (double2 *)Ez,
+               (double2 *)Bt, (double2 *)Bt_pml, (double2 *)Bz, damp, n_pml, Nz, Nr);
+    return 0;
+}
+
+int emu_correct_currents_cross(const void *rho_prev, const void *rho_next, const void *rho_next_z,
+                               const void *rho_next_xy, void *Jp, void *Jm, void *Jz, const double *kz,
+                               const double *kr, const void *T_cc, const void *j_corr_coef, const void *T_eb,
+                               int comoving, double inv_dt, int Nz, int Nr) {
+    emu_dim3 blk(64, 4);
+    if (comoving)
+        EMU_LAUNCH(grid2d(Nz, Nr, blk), blk, b2ext::k_correct_cross<true>, (const double2 *)rho_prev,
+                   (const double2 *)rho_next, (const double2 *)rho_next_z, (const double2 *)rho_next_xy, (double2 *)Jp,
+                   (double2 *)Jm, (double2 *)Jz, kz, kr, (const double2 *)T_cc, (const double2 *)j_corr_coef,
+                   (const double2 *)T_eb, inv_dt, Nz, Nr);
+    else
+        EMU_LAUNCH(grid2d(Nz, Nr, blk), blk, b2ext::k_correct_cross<false>, (const double2 *)rho_prev,
+                   (const double2 *)rho_next, (const double2 *)rho_next_z, (const double2 *)rho_next_xy, (double2 *)Jp,
+                   (double2 *)Jm, (double2 *)Jz, kz, kr, (const double2 *)nullptr, (const double2 *)nullptr,
+                   (const double2 *)nullptr, inv_dt, Nz, Nr);
+    return 0;
+}
+
+int emu_antenna_particles(long long n, const double *bx, const double *by, const double *ex, const double *ey,
+                          const double *vx, const double *vy, const double *vz, double sign, double *x, double *y,
+                          double *ux, double *uy, double *uz) {
+    EMU_LAUNCH(emu_dim3((unsigned)((n + 255) / 256)), emu_dim3(256), b2ext::k_antenna_particles, n, bx, by, ex, ey, vx,
+               vy, vz, sign, x, y, ux, uy, uz);
+    return 0;
+}
+
+int emu_axpy(long long n, double a, const double *x, double *y) {
+    EMU_LAUNCH(emu_dim3((unsigned)((n + 255) / 256)), emu_dim3(256), b2ext::k_axpy, n, a, x, y);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+"""CPU tests of the kernel SOURCE of fbpic_b200/csrc/b2_ext_kernels.cuh (radial PML, cross-deposition,
+laser-antenna helpers): tests/hostemu compiles the very same __global__ bodies with g++ (a launch becomes
+nested loops over blockIdx/threadIdx, same launch geometry as b2_ext.cu) and the results are compared with
+the NumPy statements of the reference formulas.  This checks index arithmetic and formulas in the GPU-less
+build container; the `-m gpu` tests check the compiled sm_100a kernels through the C ABI."""
+import ctypes
+import os
+import subprocess
+import numpy as np
+import pytest
+from scipy.constants import c
+
+from conftest import ROOT, assert_close
+
+EMU_DIR = os.path.join(ROOT, 'tests', 'hostemu')
+
+
+@pytest.fixture(scope='module')
+def emu():
+    so = os.path.join(EMU_DIR, 'libemu_ext.so')
+    srcs = [os.path.join(EMU_DIR, 'emu_ext.cpp'), os.path.join(EMU_DIR, 'cuda_shim.h'),
+            os.path.join(ROOT, 'fbpic_b200', 'csrc', 'b2_ext_kernels.cuh')]
+    if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(['g++', '-O1', '-ffp-contract=off', '-shared', '-fPIC', '-o', so, srcs[0]])
+    return ctypes.CDLL(so)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _cplx(rng, shape):
+    return (rng.normal(size=shape) + 1.j * rng.normal(size=shape)).astype(np.complex128)
+
+
+@pytest.mark.parametrize('comoving', [False, True])
+@pytest.mark.parametrize('shape', [(5, 7), (9, 130)])
+def test_emu_push_eb_pml(emu, comoving, shape):
+    rng = np.random.default_rng(3)
+    Nz, Nr = shape
+    Ep, Em, Bp, Bm, Ez, Bz = [_cplx(rng, shape) for _ in range(6)]
+    C, S_w = rng.normal(size=shape), rng.normal(size=shape) * 1e-9
+    T = _cplx(rng, shape) if comoving else None
+    kr = rng.normal(size=Nr) * 1e5
+    Tn = T if comoving else 1.
+    # fbpic/fields/numba_methods.py:189-214 (standard), :358-383 (comoving)
+    ref = [Tn * C * Ep + c**2 * Tn * S_w * (-1.j * 0.5 * kr[None, :] * Bz),
+           Tn * C * Em + c**2 * Tn * S_w * (-1.j * 0.5 * kr[None, :] * Bz),
+           Tn * C * Bp - Tn * S_w * (-1.j * 0.5 * kr[None, :] * Ez),
+           Tn * C * Bm - Tn * S_w * (-1.j * 0.5 * kr[None, :] * Ez)]
+    Ez0, Bz0 = Ez.copy(), Bz.copy()
+    emu.emu_push_eb_pml(_p(Ep), _p(Em), _p(Bp), _p(Bm), _p(Ez), _p(Bz), _p(C), _p(S_w),
+                        _p(T) if comoving else None, _p(kr), Nz, Nr)
+    for got, want, name in zip((Ep, Em, Bp, Bm), ref, ('Ep_pml', 'Em_pml', 'Bp_pml', 'Bm_pml')):
+        assert_close(got, want, 1e-14, name)
+    assert np.array_equal(Ez, Ez0) and np.array_equal(Bz, Bz0)
+
+
+@pytest.mark.parametrize('shape,n_pml', [((6, 9), 4), ((33, 70), 33), ((3, 5), 5)])
+def test_emu_damp_pml(emu, shape, n_pml):
+    rng = np.random.default_rng(4)
+    Nz, Nr = shape
+    Et, Etp, Ez, Bt, Btp, Bz = [_cplx(rng, shape) for _ in range(6)]
+    damp = np.exp(-4. * 0.7 * (np.arange(n_pml) / n_pml)**2)
+    want = [a.copy() for a in (Et, Etp, Ez, Bt, Btp, Bz)]
+    wEt, wEtp, wEz, wBt, wBtp, wBz = want
+    d = damp[None, :]                               # pml_damping.py:66-83
+    wEt[:, -n_pml:] -= wEtp[:, -n_pml:]
+    wBt[:, -n_pml:] -= wBtp[:, -n_pml:]
+    wEtp[:, -n_pml:] *= d
+    wBtp[:, -n_pml:] *= d
+    wEt[:, -n_pml:] += wEtp[:, -n_pml:]
+    wBt[:, -n_pml:] += wBtp[:, -n_pml:]
+    wBz[:, -n_pml:] *= d
+    wEz[:, -n_pml:] *= d
+    emu.emu_damp_pml(_p(Et), _p(Etp), _p(Ez), _p(Bt), _p(Btp), _p(Bz), _p(damp), n_pml, Nz, Nr)
+    for got, w, name in zip((Et, Etp, Ez, Bt, Btp, Bz), want, ('Et', 'Et_pml', 'Ez', 'Bt', 'Bt_pml', 'Bz')):
+        assert np.array_equal(got, w), name
+
+
+@pytest.mark.parametrize('comoving', [False, True])
+def test_emu_correct_currents_cross(emu, comoving):
+    rng = np.random.default_rng(5)
+    Nz, Nr = 10, 67
+    rp, rn, rz, rxy, Jp, Jm, Jz = [_cplx(rng, (Nz, Nr)) for _ in range(7)]
+    kz1, kr1 = rng.normal(size=Nz) * 1e5, np.abs(rng.normal(size=Nr)) * 1e5
+    kz1[0] = 0.
+    kr1[3] = 0.
+    Tcc, jcc, Teb = [_cplx(rng, (Nz, Nr)) for _ in range(3)]
+    inv_dt = 3.e14
+    kz, kr = np.broadcast_to(kz1[:, None], (Nz, Nr)), np.broadcast_to(kr1[None, :], (Nz, Nr))
+    if comoving:      # numba_methods.py:243-275
+        Dz = 1.j * kz * Jz + 0.5 * Tcc * jcc * (rn - Teb * rxy + rz - Teb * rp)
+        Dxy = kr * (Jp - Jm) + 0.5 * Tcc * jcc * (rn + Teb * rxy - rz - Teb * rp)
+    else:             # numba_methods.py:88-116
+        Dz = 1.j * kz * Jz + 0.5 * inv_dt * (rn - rxy + rz - rp)
+        Dxy = kr * (Jp - Jm) + 0.5 * inv_dt * (rn - rz + rxy - rp)
+    wJp, wJm, wJz = Jp.copy(), Jm.copy(), Jz.copy()
+    nzr, nzz = kr != 0, kz != 0
+    wJp[nzr] += -0.5 * Dxy[nzr] / kr[nzr]
+    wJm[nzr] += 0.5 * Dxy[nzr] / kr[nzr]
+    wJz[nzz] += 1.j * Dz[nzz] / kz[nzz]
+    emu.emu_correct_currents_cross(_p(rp), _p(rn), _p(rz), _p(rxy), _p(Jp), _p(Jm), _p(Jz), _p(kz1), _p(kr1),
+                                   _p(Tcc), _p(jcc), _p(Teb), int(comoving), ctypes.c_double(inv_dt), Nz, Nr)
+    for got, w, name in zip((Jp, Jm, Jz), (wJp, wJm, wJz), ('Jp', 'Jm', 'Jz')):
+        assert_close(got, w, 1e-14, name)
+    assert np.array_equal(Jz[0], wJz[0]) and np.array_equal(Jp[:, 3], wJp[:, 3])      # untouched where k == 0
+
+
+def test_emu_antenna_helpers(emu):
+    rng = np.random.default_rng(6)
+    n = 700
+    bx, by, ex, ey, vx, vy, vz = [rng.normal(size=n) for _ in range(7)]
+    for sign in (1., -1.):
+        x, y, ux, uy, uz = [np.full(n, np.nan) for _ in range(5)]
+        emu.emu_antenna_particles(ctypes.c_longlong(n), _p(bx), _p(by), _p(ex), _p(ey), _p(vx), _p(vy), _p(vz),
+                                  ctypes.c_double(sign), _p(x), _p(y), _p(ux), _p(uy), _p(uz))
+        # antenna_injection.py:360-361, 373-374, 411-413
+        assert np.array_equal(x, bx + sign * ex) and np.array_equal(y, by + sign * ey)
+        assert_close(ux, sign * vx / c, 1e-15, 'ux')
+        assert_close(uy, sign * vy / c, 1e-15, 'uy')
+        assert_close(uz, vz / c, 1e-15, 'uz')
+    y0 = by.copy()
+    emu.emu_axpy(ctypes.c_longlong(n), ctypes.c_double(0.37), _p(vx), _p(by))
+    assert np.array_equal(by, y0 + 0.37 * vx)

@@ -116,3 +116,48 @@ def test_oracle_step_vs_reference(tag):
         for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'Jr', 'Jt', 'Jz', 'rho'):
             sc = group_scale(g, 'out_', 'rho' if k == 'rho' else k[0], Nm)
             assert_close(sim.interp[m][k], g['out_%s_m%d' % (k, m)], 1e-10, '%s %s m%d' % (tag, k, m), scale=sc)
+
+
+def _oracle_from_step_golden(g, **kw):
+    Nz, Nr, Nm = int(g['Nz']), int(g['Nr']), int(g['Nm'])
+    V = float(g['v_comoving']) if bool(g['has_v']) else None
+    sim = orc.OracleSim(Nz, float(g['zmax']), Nr, float(g['rmax']), Nm, float(g['dt']),
+                        n_order=int(g['n_order']), v_comoving=V, use_galilean=bool(g['use_galilean']),
+                        nthreads=2, **kw)
+    sim.add_species(float(g['s0_q']), float(g['s0_m']),
+                    *[g['s0_in_%s' % k] for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w')])
+    return sim
+
+
+def _check_step_outputs(sim, g, tag, names, ptol=1e-11, ftol=1e-10):
+    for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma'):
+        assert_close(sim.species[0][k], g['s0_out_%s' % k], ptol, '%s %s' % (tag, k))
+    for m in range(sim.Nm):
+        for k in names:
+            grp = 'rho' if k == 'rho' else k[0]
+            sc = group_scale(g, 'out_', grp, sim.Nm)
+            assert_close(sim.interp[m][k], g['out_%s_m%d' % (k, m)], ftol, '%s %s m%d' % (tag, k, m), scale=sc)
+
+
+@pytest.mark.parametrize('tag', ['std', 'galilean'])
+def test_oracle_cross_deposition_vs_reference(tag):
+    """current_correction='cross-deposition' (main.py:512-514, 672-717; numba_methods.py:88-116, 243-275)"""
+    g = load_golden('step_cross_' + tag)
+    sim = _oracle_from_step_golden(g, current_correction='cross-deposition')
+    sim.step(int(g['nsteps']))
+    assert abs(sim.zmin - float(g['zmin_end'])) <= 1e-12 * abs(float(g['zmax']))
+    _check_step_outputs(sim, g, 'cross ' + tag, ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'Jr', 'Jt', 'Jz', 'rho'))
+
+
+def test_oracle_pml_vs_reference():
+    """boundaries['r']='open': split PML components, their spectral push and the radial damping
+    (main.py:410-415, 732-761; numba_methods.py:189-214; pml_damping.py:46-83), z periodic."""
+    g = load_golden('step_pml_periodic')
+    sim = _oracle_from_step_golden(g, nr_damp=int(g['nr_damp']))
+    assert sim.Nr == int(g['Nr_local'])
+    for m in range(sim.Nm):
+        for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz'):
+            sim.interp[m][k][:, :] = g['in_%s_m%d' % (k, m)]
+    sim.step(int(g['nsteps']))
+    _check_step_outputs(sim, g, 'pml', ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'Jr', 'Jt', 'Jz', 'rho',
+                                        'Er_pml', 'Et_pml', 'Br_pml', 'Bt_pml'))
