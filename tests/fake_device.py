@@ -25,12 +25,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU_DIR = os.path.join(ROOT, 'tests', 'hostemu')
 
 
-def _emu():
+def build_emu():
+    """Compile (if stale) and load tests/hostemu/libemu_ext.so: the kernel source of b2_ext_kernels.cuh for the CPU."""
     so = os.path.join(EMU_DIR, 'libemu_ext.so')
     srcs = [os.path.join(EMU_DIR, 'emu_ext.cpp'), os.path.join(EMU_DIR, 'cuda_shim.h'),
             os.path.join(ROOT, 'fbpic_b200', 'csrc', 'b2_ext_kernels.cuh')]
     if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(['g++', '-O1', '-ffp-contract=off', '-shared', '-fPIC', '-o', so, srcs[0]])
+        # the namespace is renamed and references are bound inside the library (-Bsymbolic): libfbpic_b200.so
+        # is loaded RTLD_GLOBAL and exports host launch stubs with the same mangled kernel names
+        subprocess.check_call(['g++', '-O1', '-ffp-contract=off', '-Db2ext=b2ext_hostemu', '-shared', '-fPIC',
+                               '-Wl,-Bsymbolic', '-o', so, srcs[0]])
     return ctypes.CDLL(so)
 
 
@@ -69,7 +73,7 @@ class FakeLib(object):
         self._part = None
         self.launches = 0
         self.calls = []
-        self.emu = _emu()
+        self.emu = build_emu()
 
     def __getattr__(self, name):
         raise AttributeError('fake device: %s is not emulated' % name)

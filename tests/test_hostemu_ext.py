@@ -4,25 +4,17 @@ nested loops over blockIdx/threadIdx, same launch geometry as b2_ext.cu) and the
 the NumPy statements of the reference formulas.  This checks index arithmetic and formulas in the GPU-less
 build container; the `-m gpu` tests check the compiled sm_100a kernels through the C ABI."""
 import ctypes
-import os
-import subprocess
 import numpy as np
 import pytest
 from scipy.constants import c
 
-from conftest import ROOT, assert_close
-
-EMU_DIR = os.path.join(ROOT, 'tests', 'hostemu')
+from conftest import assert_close
 
 
 @pytest.fixture(scope='module')
 def emu():
-    so = os.path.join(EMU_DIR, 'libemu_ext.so')
-    srcs = [os.path.join(EMU_DIR, 'emu_ext.cpp'), os.path.join(EMU_DIR, 'cuda_shim.h'),
-            os.path.join(ROOT, 'fbpic_b200', 'csrc', 'b2_ext_kernels.cuh')]
-    if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(['g++', '-O1', '-ffp-contract=off', '-shared', '-fPIC', '-o', so, srcs[0]])
-    return ctypes.CDLL(so)
+    from fake_device import build_emu
+    return build_emu()
 
 
 def _p(a):
