@@ -5,9 +5,11 @@ libfbpic_b200.so (no Numba, no CuPy, no CPU fallback).
 
 Hot-path scope: gather / push / deposit / sort, z-FFT + Hankel GEMM,
 current correction + PSATD push, z guard-cell exchange and particle migration.
-Widened per SURVEY 8f: moving window with continuous injection (rank 1), radial PML
-(`boundaries['r']='open'`) and the cross-deposition current correction (rank 4).
-Out of scope and therefore rejected loudly: diagnostics, checkpoints, ionization.
+Widened per SURVEY 8f: moving window with continuous injection (rank 1), laser antennas
+(rank 2), radial PML (`boundaries['r']='open'`) and the cross-deposition current correction
+(rank 4); plus mirrors, external fields and the boosted-frame conversion of the set-up
+(`gamma_boost`).  Out of scope and therefore rejected loudly: diagnostics, checkpoints,
+ionization.
 """
 import numpy as np
 from scipy.constants import m_e, m_p, e, c
@@ -43,12 +45,14 @@ class Simulation(object):
         self.use_cuda = True
         self.fused = fused
         self.sort_period = max(int(sort_period), 1)
-        if gamma_boost is not None:
-            raise NotImplementedError('gamma_boost conversion is host-side setup outside the hot path; '
-                                      'pass boosted-frame quantities directly')
-        self.boost = None
         self.v_comoving = v_comoving
         self.use_galilean = use_galilean if v_comoving is not None else False
+        if gamma_boost is not None:                   # main.py:275-280
+            from .lpa_utils.boosted_frame import BoostConverter
+            self.boost = BoostConverter(gamma_boost)
+            zmin, zmax, dt = self.boost.copropag_length([zmin, zmax, dt])
+        else:
+            self.boost = None
         self.dt = dt
         cdt_over_dr = c * dt / (rmax / Nr)
         self.comm = BoundaryCommunicator(Nz, zmin, zmax, Nr, rmax, Nm, dt, self.v_comoving,
@@ -102,9 +106,8 @@ class Simulation(object):
         if self.comm.size > 1 and use_true_rho and correct_currents:
             raise ValueError('`use_true_rho` cannot be used together with `correct_currents` '
                              'in multi-proc mode.')
-        if self.external_fields or self.diags or self.checkpoints or self.laser_antennas or self.mirrors:
-            raise NotImplementedError('external fields, diagnostics, checkpoints, antennas and mirrors '
-                                      'are outside the hot path built here')
+        if self.diags or self.checkpoints:
+            raise NotImplementedError('diagnostics and checkpoints are outside the hot path built here')
         if self.comm.moving_win is not None:          # main.py:390-395
             for species in self.ptcl:
                 if species.continuous_injection and species.injector is not None:
@@ -113,7 +116,8 @@ class Simulation(object):
                         self.comm, self.comm.moving_win.v, z_host, self.dt)
         single = (self.comm.size == 1)
         periodic_single = single and self.comm.n_guard == 0
-        fuse_gp = self.fused and move_positions and move_momenta
+        # external fields act on the gathered E, B of the particles: they need the unfused gather
+        fuse_gp = self.fused and move_positions and move_momenta and not self.external_fields
         fuse_cp = self.fused and correct_currents and single and fld.current_correction == 'curl-free'
 
         import time as _time
@@ -133,12 +137,14 @@ class Simulation(object):
         # rho_prev of step n+1 is (bit for bit) the rho_next that push_rho already moved over, so
         # the per-step exchange_particles + re-deposition of rho_prev (main.py:435-449, needed in
         # the reference only because particles may have been added/removed) is done at i_step==0 only.
-        wrap_in_push = self.fused and periodic_single and move_positions
+        wrap_in_push = self.fused and periodic_single and move_positions and not self.laser_antennas
         for i_step in range(N):
             exchange_now = (self.iteration % self.comm.exchange_period == 0 or i_step == 0)
             if exchange_now and not (wrap_in_push and i_step > 0):
                 for species in ptcl:
                     self.comm.exchange_particles(species, fld, self.time)
+                for antenna in self.laser_antennas:       # main.py:443-444
+                    antenna.update_current_rank(self.comm)
                 self.deposit('rho_prev', exchange=(use_true_rho is True))
             if i_step == 0:
                 self.deposit('J', exchange=True)
@@ -155,12 +161,17 @@ class Simulation(object):
             else:
                 for species in ptcl:
                     species.gather(fld.interp, self.comm)
+                for ext_field in self.external_fields:    # main.py:472-473
+                    ext_field.apply_expression(self.ptcl, self.time)
                 if move_momenta:
                     for species in ptcl:
                         species.push_p(self.time + 0.5 * dt)
                 if move_positions:
                     for species in ptcl:
                         species.push_x(0.5 * dt)
+            for antenna in self.laser_antennas:           # main.py:491-494
+                antenna.update_v(self.time + 0.5 * dt, dt)
+                antenna.push_x(0.5 * dt)
             if self.use_galilean:
                 self.shift_galilean_boundaries(0.5 * dt)
             for species in ptcl:
@@ -175,6 +186,8 @@ class Simulation(object):
             fuse_pr = self.fused and move_positions and len(ptcl) > 0 and (not cross) and \
                 all((sp.q != 0) and (not sp.is_tracer) and getattr(sp, '_order_matches_prefix', False)
                     for sp in ptcl)
+            for antenna in self.laser_antennas:           # main.py:520-522
+                antenna.push_x(0.5 * dt)
             if fuse_pr:
                 if self.use_galilean:
                     self.shift_galilean_boundaries(0.5 * dt)
@@ -213,7 +226,8 @@ class Simulation(object):
                 fld.push(use_true_rho, check_exchanges=(self.comm.size > 1))
             if self.comm.moving_win is not None:
                 self.comm.move_grids(fld, ptcl, dt, self.time)
-            self.exchange_and_damp_EB(skip_identity=periodic_single and self.fused and not self.use_pml)
+            self.exchange_and_damp_EB(skip_identity=(periodic_single and self.fused and not self.use_pml
+                                                     and not self.mirrors))
             self.time += dt
             self.iteration += 1
 
@@ -234,8 +248,11 @@ class Simulation(object):
     def deposit(self, fieldtype, exchange=False, update_spectral=True, species_list=None, push=None):
         """fbpic/main.py:588-670"""
         fld = self.fld
-        if species_list is None:
+        if species_list is None:            # everything deposits (main.py:618-624)
             species_list = [s for s in self.ptcl if not s.is_tracer]
+            antennas_list = self.laser_antennas
+        else:
+            antennas_list = []
         if fieldtype.startswith('rho'):
             grid_type = 'rho'
         elif fieldtype == 'J':
@@ -248,6 +265,8 @@ class Simulation(object):
                 species.deposit_fused(fld, grid_type, push=push)
             else:
                 species.deposit(fld, grid_type)
+        for antenna in antennas_list:       # main.py:634-636, 651-653
+            antenna.deposit(fld, grid_type)
         fld.sum_reduce_deposition_array(grid_type)
         if self.fused and update_spectral and not (exchange and self.comm.size > 1):
             # divide_by_volume, the transforms and the filter as FFTs + one batched Hankel launch
@@ -276,6 +295,8 @@ class Simulation(object):
             self.comm.exchange_fields(fld.interp, 'B', 'replace')
             self.comm.damp_EB_open_boundary(fld.interp)
             self.comm.damp_pml_EB(fld.interp)
+            for mirror in self.mirrors:
+                mirror.set_fields_to_zero(fld.interp, self.comm, self.time)
             for ft in ('E', 'B', 'E_pml', 'B_pml'):
                 fld.interp2spect(ft)
             return
@@ -285,6 +306,8 @@ class Simulation(object):
                 fld.spect2partial_interp('EB')
                 self.comm.exchange_fields(fld.interp, 'EB', 'replace')
                 self.comm.damp_EB_open_boundary(fld.interp)
+                for mirror in self.mirrors:           # main.py:751-753 (rows in z: valid in (z, kr) space)
+                    mirror.set_fields_to_zero(fld.interp, self.comm, self.time)
                 fld.partial_interp2spect('EB')
                 # the exchanged (z, kr) arrays go straight to real space: inverse Hankel only
                 fld.fused_partial2interp_EB()
@@ -294,6 +317,8 @@ class Simulation(object):
             self.comm.exchange_fields(fld.interp, 'E', 'replace')
             self.comm.exchange_fields(fld.interp, 'B', 'replace')
             self.comm.damp_EB_open_boundary(fld.interp)
+            for mirror in self.mirrors:
+                mirror.set_fields_to_zero(fld.interp, self.comm, self.time)
             fld.partial_interp2spect('E')
             fld.partial_interp2spect('B')
         if self.fused:
@@ -310,6 +335,8 @@ class Simulation(object):
             if move_positions:
                 for species in self.ptcl:
                     species.push_x(frac * dt, x_push=sx, y_push=sx, z_push=sz)
+            for antenna in self.laser_antennas:
+                antenna.push_x(frac * dt, x_push=sx, y_push=sx, z_push=sz)
             if self.use_galilean:
                 self.shift_galilean_boundaries(sz * frac * dt)
             if ft is not None:
@@ -328,12 +355,33 @@ class Simulation(object):
                         p_zmin=-np.inf, p_zmax=np.inf, p_rmin=0, p_rmax=np.inf,
                         uz_m=0., ux_m=0., uy_m=0., uz_th=0., ux_th=0., uy_th=0.,
                         continuous_injection=True, boost_positions_in_dens_func=False, is_tracer=False):
-        """fbpic/main.py:792-1001 (lab frame only)."""
+        """fbpic/main.py:792-1001.  With `gamma_boost`, positions, density and momenta are given in the
+        lab frame and converted to the boosted frame here (main.py:909-950)."""
         if n is not None:
             for var in (p_nz, p_nr, p_nt):
                 if var is None:
                     raise ValueError('If the density `n` is passed to `add_new_species`,\n'
                                      'then the arguments `p_nz`, `p_nr` and `p_nt` need to be passed too.')
+            if self.boost is not None:
+                gamma_m = np.sqrt(1. + uz_m**2 + ux_m**2 + uy_m**2)
+                beta_m_lab = uz_m / gamma_m
+                p_zmin, p_zmax = self.boost.copropag_length([p_zmin, p_zmax], beta_object=beta_m_lab)
+                n, = self.boost.copropag_density([n], beta_object=beta_m_lab)
+                # approximate transform of the longitudinal thermal spread (perturbation of the Lorentz
+                # transform of uz), then of the mean momentum
+                if uz_m == 0:
+                    uz_th = self.boost.gamma0 * uz_th
+                else:
+                    uz_th = self.boost.gamma0 * (1. - self.boost.beta0 * beta_m_lab) * uz_th
+                uz_m = self.boost.gamma0 * (uz_m - self.boost.beta0 * gamma_m)
+                if boost_positions_in_dens_func and (dens_func is not None):
+                    from .particles import _dens_func_args
+                    coef = self.boost.gamma0 * (1 - beta_m_lab * self.boost.beta0)
+                    lab_dens_func = dens_func
+                    if _dens_func_args(lab_dens_func) == ['z', 'r']:
+                        dens_func = lambda z, r: lab_dens_func(coef * z, r)      # noqa: E731
+                    else:
+                        dens_func = lambda x, y, z: lab_dens_func(x, y, coef * z)  # noqa: E731
             zmin_local, zmax_local = self.comm.get_zmin_zmax(local=True, rank=self.comm.rank,
                                                             with_damp=False, with_guard=False)
             p_zmin = max(zmin_local, p_zmin)

@@ -98,7 +98,83 @@ def gen_cross(tag, v_comoving, use_galilean, nsteps=3):
     save('step_cross_' + tag, **out)
 
 
+def gen_laser_profiles():
+    """E_field of the analytic profiles on random points (laser_profiles.py)."""
+    from fbpic.lpa_utils.laser import GaussianLaser, LaguerreGaussLaser
+    rng = np.random.default_rng(21)
+    n = 400
+    x, y = rng.normal(size=n) * 6.e-6, rng.normal(size=n) * 6.e-6
+    z = rng.uniform(-20.e-6, 40.e-6, n)
+    t = 13.e-15
+    out = dict(x=x, y=y, z=z, t=t)
+    profs = {
+        'gauss': GaussianLaser(a0=2., waist=5.e-6, tau=20.e-15, z0=10.e-6, zf=30.e-6, theta_pol=0.3,
+                               lambda0=0.8e-6, cep_phase=0.4, phi2_chirp=150.e-30),
+        'gauss_bw': GaussianLaser(a0=1., waist=4.e-6, tau=15.e-15, z0=5.e-6, propagation_direction=-1),
+        'lg11': LaguerreGaussLaser(1, 1, a0=1.5, waist=6.e-6, tau=18.e-15, z0=8.e-6, zf=-5.e-6, theta_pol=1.1,
+                                   cep_phase=0.2, theta0=0.5),
+        'lg20': LaguerreGaussLaser(2, 0, a0=0.7, waist=5.e-6, tau=25.e-15, z0=0.),
+    }
+    for k, p in profs.items():
+        out[k + '_Ex'], out[k + '_Ey'] = p.E_field(x, y, z, t)
+    s = profs['gauss'] + profs['lg11']
+    out['sum_Ex'], out['sum_Ey'] = s.E_field(x, y, z, t)
+    save('laser_profiles', **out)
+
+
+def gen_laser_direct(tag, gamma_boost=None, lg=False, pml=False):
+    """add_laser_pulse(method='direct') on an open-z box: the fields put on the grid
+    (direct_injection.py:12-217)."""
+    from fbpic.lpa_utils.laser import add_laser_pulse, GaussianLaser, LaguerreGaussLaser
+    Nz, Nr, Nm, zmax, rmax = 48, 16, 2, 24.e-6, 16.e-6
+    zmin = 0.
+    dt = (zmax - zmin) / Nz / c
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, zmin=zmin, n_order=-1, n_guard=12, n_damp={'z': 12, 'r': 6},
+                     gamma_boost=gamma_boost, verbose_level=0,
+                     boundaries={'z': 'open', 'r': ('open' if pml else 'reflective')})
+    if lg:
+        prof = LaguerreGaussLaser(0, 1, a0=1., waist=4.e-6, tau=8.e-15, z0=12.e-6, zf=20.e-6, theta_pol=0.4)
+    else:
+        prof = GaussianLaser(a0=2., waist=4.e-6, tau=8.e-15, z0=12.e-6, zf=25.e-6, theta_pol=0.7,
+                             lambda0=1.6e-6, cep_phase=0.3)
+    add_laser_pulse(sim, prof, gamma_boost=gamma_boost)
+    out = dict(Nz=Nz, Nr=Nr, Nm=Nm, zmax=zmax, rmax=rmax, zmin=zmin, dt=dt, lg=lg, pml=pml,
+               gamma_boost=(0. if gamma_boost is None else gamma_boost), Nz_local=sim.fld.interp[0].Nz)
+    out.update({'out_' + k: v for k, v in field_arrays(sim, ('E', 'B')).items()})
+    save('laser_direct_' + tag, **out)
+
+
+def gen_laser_antenna(tag, gamma_boost=None, v_antenna=0., nsteps=24, cross=False):
+    """A laser emitted by an antenna into an empty open-z box (antenna_injection.py:24-442):
+    fields after nsteps and the state of the antenna."""
+    from fbpic.lpa_utils.laser import add_laser_pulse, GaussianLaser
+    Nz, Nr, Nm, zmax, rmax = 48, 12, 2, 24.e-6, 12.e-6
+    dt = zmax / Nz / c
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, zmin=0., n_order=-1, n_guard=12, n_damp={'z': 12, 'r': 6},
+                     gamma_boost=gamma_boost, verbose_level=0,
+                     current_correction=('cross-deposition' if cross else 'curl-free'),
+                     boundaries={'z': 'open', 'r': 'reflective'})
+    prof = GaussianLaser(a0=1., waist=3.e-6, tau=6.e-15, z0=-4.e-6, zf=10.e-6, theta_pol=0.5, lambda0=1.6e-6)
+    add_laser_pulse(sim, prof, gamma_boost=gamma_boost, method='antenna', z0_antenna=6.e-6, v_antenna=v_antenna)
+    sim.step(nsteps, show_progress=False)
+    ant = sim.laser_antennas[0]
+    out = dict(Nz=Nz, Nr=Nr, Nm=Nm, zmax=zmax, rmax=rmax, dt=dt, nsteps=nsteps, cross=cross,
+               gamma_boost=(0. if gamma_boost is None else gamma_boost), v_antenna=v_antenna,
+               Nz_local=sim.fld.interp[0].Nz, excursion_x=ant.excursion_x, excursion_y=ant.excursion_y,
+               baseline_z=ant.baseline_z, vx=ant.vx, vy=ant.vy, w=ant.w, mobility_coef=ant.mobility_coef,
+               zmin_end=sim.fld.interp[0].zmin)
+    out.update({'out_' + k: v for k, v in field_arrays(sim).items()})
+    save('laser_antenna_' + tag, **out)
+
+
 GENERATORS = {
+    'laser_profiles': gen_laser_profiles,
+    'laser_direct_gauss': lambda: gen_laser_direct('gauss'),
+    'laser_direct_lg_pml': lambda: gen_laser_direct('lg_pml', lg=True, pml=True),
+    'laser_direct_boost': lambda: gen_laser_direct('boost', gamma_boost=3.),
+    'laser_antenna_lab': lambda: gen_laser_antenna('lab'),
+    'laser_antenna_moving': lambda: gen_laser_antenna('moving', v_antenna=0.2 * c, cross=True, nsteps=16),
+    'laser_antenna_boost': lambda: gen_laser_antenna('boost', gamma_boost=2.),
     'pml_periodic': lambda: gen_pml('periodic', False),
     'pml_open': lambda: gen_pml('open', True),
     'pml_galilean': lambda: gen_pml('galilean', True, v_comoving=0.999 * c, use_galilean=True),

@@ -11,6 +11,7 @@ import pytest
 import fake_device
 import test_gpu_step
 import test_gpu_widen
+import test_gpu_laser
 
 
 @pytest.fixture
@@ -43,3 +44,14 @@ def test_pml_flow(fake, tag, fused):
 @pytest.mark.parametrize('tag', ['std', 'galilean'])
 def test_cross_deposition_flow(fake, tag, fused):
     test_gpu_widen.test_cross_deposition_step_vs_reference_golden(tag, fused)
+
+
+@pytest.mark.parametrize('tag', ['gauss', 'lg_pml', 'boost'])
+def test_add_laser_direct_flow(fake, tag):
+    test_gpu_laser.test_add_laser_direct_vs_reference_golden(tag)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('tag', ['lab', 'moving', 'boost'])
+def test_laser_antenna_flow(fake, tag, fused):
+    test_gpu_laser.test_laser_antenna_vs_reference_golden(tag, fused)

@@ -1,0 +1,59 @@
+"""CPU tests of the host-side set-up utilities (fbpic_b200/lpa_utils): laser profiles and the boosted-frame
+converter against values produced by the unmodified reference (oracle/gen_golden_ext.py)."""
+import numpy as np
+from scipy.constants import c
+
+from conftest import load_golden, assert_close
+
+
+def test_laser_profiles_vs_reference():
+    from fbpic_b200.lpa_utils.laser import GaussianLaser, LaguerreGaussLaser
+    g = load_golden('laser_profiles')
+    x, y, z, t = g['x'], g['y'], g['z'], float(g['t'])
+    profs = {
+        'gauss': GaussianLaser(a0=2., waist=5.e-6, tau=20.e-15, z0=10.e-6, zf=30.e-6, theta_pol=0.3,
+                               lambda0=0.8e-6, cep_phase=0.4, phi2_chirp=150.e-30),
+        'gauss_bw': GaussianLaser(a0=1., waist=4.e-6, tau=15.e-15, z0=5.e-6, propagation_direction=-1),
+        'lg11': LaguerreGaussLaser(1, 1, a0=1.5, waist=6.e-6, tau=18.e-15, z0=8.e-6, zf=-5.e-6, theta_pol=1.1,
+                                   cep_phase=0.2, theta0=0.5),
+        'lg20': LaguerreGaussLaser(2, 0, a0=0.7, waist=5.e-6, tau=25.e-15, z0=0.),
+    }
+    for k, p in profs.items():
+        Ex, Ey = p.E_field(x, y, z, t)
+        assert_close(Ex, g[k + '_Ex'], 1e-13, k + ' Ex')
+        assert_close(Ey, g[k + '_Ey'], 1e-13, k + ' Ey')
+    Ex, Ey = (profs['gauss'] + profs['lg11']).E_field(x, y, z, t)
+    assert_close(Ex, g['sum_Ex'], 1e-13, 'sum Ex')
+    assert_close(Ey, g['sum_Ey'], 1e-13, 'sum Ey')
+
+
+def test_boost_converter():
+    """Lorentz identities of fbpic/lpa_utils/boosted_frame.py."""
+    from fbpic_b200.lpa_utils.boosted_frame import BoostConverter
+    b = BoostConverter(10.)
+    assert abs(b.beta0 - np.sqrt(1 - 0.01)) < 1e-15
+    L, = b.static_length([2.])
+    assert L == 2. / 10.
+    Lc, = b.copropag_length([1.], beta_object=1.)
+    assert abs(Lc - 1. / (10. * (1 - b.beta0))) < 1e-12 * Lc
+    n1, = b.static_density([3.])
+    n2, = b.copropag_density([3.], beta_object=0.5)
+    assert n1 == 30. and abs(n2 - 3. * 10. * (1 - 0.5 * b.beta0)) < 1e-13
+    v, = b.velocity([c])
+    assert abs(v - c) < 1e-14 * c / (1 - b.beta0)   # light stays light (cancellation in 1 - beta0)
+    v0, = b.velocity([0.])
+    assert abs(v0 + b.beta0 * c) < 1e-7           # a lab-frame object at rest moves backwards
+    uz, = b.longitudinal_momentum([0.])
+    assert abs(uz + 10. * b.beta0) < 1e-13
+    gm, = b.gamma([1.])
+    assert abs(gm - 10.) < 1e-13
+    k, = b.wavenumber([1.])
+    assert abs(k - 1. / (10. * (1 + b.beta0))) < 1e-15
+    # a particle at rest at z: after the boost it sits at z/gamma0 at t' = 0 and moves with -beta0 c
+    x, y, z = np.zeros(3), np.zeros(3), np.array([1., 2., 3.])
+    u0 = np.zeros(3)
+    nx, ny, nz, nux, nuy, nuz, nig = b.boost_particle_arrays(x, y, z, u0, u0, u0, np.ones(3))
+    assert np.allclose(nz, z / 10., rtol=1e-12) and np.allclose(nuz, -10. * b.beta0) and np.allclose(nig, 0.1)
+    T = b.interaction_time(1.e-3, 50.e-6, c)
+    Li, lw, vw = 1.e-3 / 10., 50.e-6 / (10. * (1 - b.beta0)), c
+    assert abs(T - (Li + lw) / (vw + b.beta0 * c)) < 1e-12 * T
