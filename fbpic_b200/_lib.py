@@ -128,6 +128,10 @@ _SIGNATURES = {
     'b2_correct_currents_cross': [P, ctypes.POINTER(SpectralMode), P, P, c_int, c_double, c_int, c_int, P],
     'b2_antenna_particles': [P, c_int64, P, P, P, P, P, P, P, c_double, P, P, P, P, P, P],
     'b2_axpy': [P, c_int64, c_double, P, P, P],
+    'b2_external_field_compile': [ctypes.c_char_p, ctypes.POINTER(P)],
+    'b2_external_field_cubin_size': [P, ctypes.POINTER(c_size_t)],
+    'b2_external_field_apply': [P, P, c_int64, P, P, P, P, c_double, c_double, c_double, c_double, c_double, P],
+    'b2_external_field_free': [P],
 }
 _RESTYPES = {'b2_dht_flops': c_double, 'b2_profile_name': ctypes.c_char_p, 'b2_profile_slots': c_int,
              'b2_error_string': ctypes.c_char_p, 'b2_version': ctypes.c_char_p,

@@ -41,7 +41,7 @@ def build(force=False, verbose=False):
             raise RuntimeError('nvcc failed on %s:\n%s' % (src, out))
         if verbose and out.strip():
             print(out)
-    cmd = [NVCC, '-shared', '-o', SO] + objs + ['-lcufft', '-lnccl', '-lcudart']
+    cmd = [NVCC, '-shared', '-o', SO] + objs + ['-lcufft', '-lnccl', '-lcudart', '-ldl']
     subprocess.check_call(cmd)
     return SO
 

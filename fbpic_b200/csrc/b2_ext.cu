@@ -82,3 +82,142 @@ int b2_axpy(b2_ctx *ctx, int64_t n, double a, const double *x, double *y, void *
 }
 
 }  // extern "C"
+
+// =================================================================================================
+// External fields: user-supplied element-wise expression F' = f(F, x, y, z, t, amplitude, length_scale)
+// applied to a gathered field of the particles after the gather (ExternalField.apply_expression,
+// fbpic/lpa_utils/external_fields.py:183-215).  The reference JIT-compiles the user's Python function
+// with Numba (`cuda.jit(func, device=True)` + `compile_cupy`, :134-147); here the expression arrives as
+// CUDA C (translated from the Python function by the host layer), is compiled once by NVRTC to an
+// sm_100a cubin and loaded through the runtime's library API.  For boosted-frame runs the kernel
+// evaluates the lab-frame expression at zlab = g (z + b c t), tlab = g (t + b z / c) (:118-126).
+// =================================================================================================
+#include <nvrtc.h>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+// NVRTC is bound at first use (dlopen), not at link time: the hot path of the library must load on a
+// machine without the NVRTC runtime.
+struct B2Nvrtc {
+    decltype(&nvrtcCreateProgram) create;
+    decltype(&nvrtcCompileProgram) compile;
+    decltype(&nvrtcGetProgramLogSize) log_size;
+    decltype(&nvrtcGetProgramLog) log;
+    decltype(&nvrtcGetCUBINSize) cubin_size;
+    decltype(&nvrtcGetCUBIN) cubin;
+    decltype(&nvrtcDestroyProgram) destroy;
+    decltype(&nvrtcGetErrorString) error_string;
+    bool ok;
+};
+static B2Nvrtc *b2_nvrtc() {
+    static B2Nvrtc api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        api.ok = false;
+        void *h = nullptr;
+        const char *names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
+        for (int k = 0; k < 3 && !h; ++k) h = dlopen(names[k], RTLD_NOW | RTLD_LOCAL);
+        if (h) {
+#define B2_SYM(field, name) api.field = (decltype(api.field))dlsym(h, #name)
+            B2_SYM(create, nvrtcCreateProgram); B2_SYM(compile, nvrtcCompileProgram);
+            B2_SYM(log_size, nvrtcGetProgramLogSize); B2_SYM(log, nvrtcGetProgramLog);
+            B2_SYM(cubin_size, nvrtcGetCUBINSize); B2_SYM(cubin, nvrtcGetCUBIN);
+            B2_SYM(destroy, nvrtcDestroyProgram); B2_SYM(error_string, nvrtcGetErrorString);
+#undef B2_SYM
+            api.ok = api.create && api.compile && api.log_size && api.log && api.cubin_size && api.cubin &&
+                     api.destroy && api.error_string;
+        }
+    }
+    return &api;
+}
+
+struct B2ExtField {
+    std::vector<char> cubin;
+    cudaLibrary_t lib;
+    cudaKernel_t kernel;
+    bool loaded;
+};
+
+static const char *kExtFieldPrologue =
+    "extern \"C\" __global__ void b2_external_field(long long n_, double *F_, const double *x_, const double *y_,\n"
+    "        const double *z_, double t_, double amplitude, double length_scale, double gamma_b_, double beta_b_) {\n"
+    "    const long long i_ = blockIdx.x * (long long)blockDim.x + threadIdx.x;\n"
+    "    if (i_ >= n_) return;\n"
+    "    const double c_ = 299792458.0;\n"
+    "    const double F = F_[i_], x = x_[i_], y = y_[i_];\n"
+    "    const double z = gamma_b_ * (z_[i_] + beta_b_ * c_ * t_);\n"
+    "    const double t = gamma_b_ * (t_ + beta_b_ * (1. / c_) * z_[i_]);\n"
+    "    (void)F; (void)x; (void)y; (void)z; (void)t; (void)amplitude; (void)length_scale;\n";
+
+extern "C" {
+
+int b2_external_field_compile(const char *cuda_body, void **handle) {
+    if (!cuda_body || !handle) return b2_fail(-3, "b2_external_field_compile: null argument", __FILE__, __LINE__);
+    std::string src(kExtFieldPrologue);
+    src += cuda_body;            // statements ending with `F_[i_] = <expression>;`
+    src += "\n}\n";
+    B2Nvrtc *rt = b2_nvrtc();
+    if (!rt->ok) return b2_fail(-5, "external fields need the NVRTC runtime (libnvrtc.so.12), which could not be loaded", __FILE__, __LINE__);
+    nvrtcProgram prog;
+    nvrtcResult r = rt->create(&prog, src.c_str(), "b2_external_field.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) return b2_fail((int)r, rt->error_string(r), __FILE__, __LINE__);
+    // -fmad=false: products and sums are rounded separately, like the NumPy / Numba-CPU evaluation
+    const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-fmad=false"};
+    r = rt->compile(prog, 3, opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t ls = 0;
+        rt->log_size(prog, &ls);
+        std::string log(ls ? ls : 1, '\0');
+        if (ls) rt->log(prog, &log[0]);
+        rt->destroy(&prog);
+        snprintf(g_b2_err, sizeof(g_b2_err), "external field expression does not compile: %.400s", log.c_str());
+        return (int)r;
+    }
+    size_t nb = 0;
+    rt->cubin_size(prog, &nb);
+    B2ExtField *h = new B2ExtField();
+    h->cubin.resize(nb);
+    rt->cubin(prog, h->cubin.data());
+    rt->destroy(&prog);
+    h->loaded = false;
+    *handle = h;
+    return 0;
+}
+
+int b2_external_field_cubin_size(void *handle, size_t *nbytes) {
+    if (!handle || !nbytes) return b2_fail(-3, "b2_external_field_cubin_size: null argument", __FILE__, __LINE__);
+    *nbytes = ((B2ExtField *)handle)->cubin.size();
+    return 0;
+}
+
+int b2_external_field_apply(b2_ctx *ctx, void *handle, int64_t n, double *F, const double *x, const double *y,
+                            const double *z, double t, double amplitude, double length_scale, double gamma_boost,
+                            double beta_boost, void *stream) {
+    if (!handle) return b2_fail(-3, "b2_external_field_apply: null handle", __FILE__, __LINE__);
+    if (n <= 0) return 0;
+    B2ExtField *h = (B2ExtField *)handle;
+    if (!h->loaded) {
+        B2_CUDA(cudaLibraryLoadData(&h->lib, h->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+        B2_CUDA(cudaLibraryGetKernel(&h->kernel, h->lib, "b2_external_field"));
+        h->loaded = true;
+    }
+    long long nn = (long long)n;
+    void *args[] = {&nn, &F, &x, &y, &z, &t, &amplitude, &length_scale, &gamma_boost, &beta_boost};
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    B2Prof prof_(B2P_PUSH, s);
+    B2_CUDA(cudaLaunchKernel((const void *)h->kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), args, 0, s));
+    B2_LAUNCHED();
+    return 0;
+}
+
+int b2_external_field_free(void *handle) {
+    if (!handle) return 0;
+    B2ExtField *h = (B2ExtField *)handle;
+    if (h->loaded) cudaLibraryUnload(h->lib);
+    delete h;
+    return 0;
+}
+
+}  // extern "C"

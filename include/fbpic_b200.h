@@ -302,6 +302,18 @@ int b2_antenna_particles(b2_ctx *ctx, int64_t n, const double *d_bx, const doubl
                          void *stream);
 /* y += a*x (LaserAntenna.push_x, antenna_injection.py:196-218) */
 int b2_axpy(b2_ctx *ctx, int64_t n, double a, const double *d_x, double *d_y, void *stream);
+/* external fields (ExternalField, fbpic/lpa_utils/external_fields.py:13-215): the reference turns the user's
+ * Python function into a GPU kernel with Numba (:134-147); here its body arrives as CUDA C statements over
+ * the scalars F, x, y, z, t, amplitude, length_scale that end with `F_[i_] = <expr>;`, is compiled once by
+ * NVRTC to an sm_100a cubin (no GPU needed for this step) and applied element-wise to one gathered field of
+ * a species.  gamma_boost/beta_boost: the expression is evaluated at the lab-frame (z, t) of the particle
+ * (:118-126); pass 1, 0 in the lab frame. */
+int b2_external_field_compile(const char *cuda_body, void **handle);
+int b2_external_field_cubin_size(void *handle, size_t *nbytes);
+int b2_external_field_apply(b2_ctx *ctx, void *handle, int64_t n, double *d_F, const double *d_x,
+                            const double *d_y, const double *d_z, double t, double amplitude,
+                            double length_scale, double gamma_boost, double beta_boost, void *stream);
+int b2_external_field_free(void *handle);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,7 @@ oracle/ref_shim) and only in the build container:
 
 Test infrastructure.
 """
+import math
 import os
 import sys
 import numpy as np
@@ -167,7 +168,46 @@ def gen_laser_antenna(tag, gamma_boost=None, v_antenna=0., nsteps=24, cross=Fals
     save('laser_antenna_' + tag, **out)
 
 
+def undulator_field(F, x, y, z, t, amplitude, length_scale):
+    return F + amplitude * math.cos(2 * np.pi * z / length_scale)
+
+
+def focusing_field(F, x, y, z, t, amplitude, length_scale):
+    k = 2 * math.pi / length_scale
+    if z > 2.e-6:
+        g = math.exp(-(x**2 + y**2) / length_scale**2)
+    else:
+        g = 0.
+    return F - amplitude * k * x * g * math.sin(k * (z - 299792458. * t))
+
+
+def gen_external(tag, gamma_boost=None, nsteps=4):
+    """Plasma electrons in external fields (external_fields.py:13-215, main.py:472-473)."""
+    from fbpic.lpa_utils.external_fields import ExternalField
+    np.random.seed(3)
+    Nz, Nr, Nm, zmax, rmax = 24, 12, 2, 12.e-6, 8.e-6
+    dt = zmax / Nz / c
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, p_zmin=0, p_zmax=zmax, p_rmin=0, p_rmax=rmax,
+                     p_nz=2, p_nr=2, p_nt=4, n_e=1.e23, n_order=-1, gamma_boost=gamma_boost, verbose_level=0,
+                     boundaries={'z': 'periodic', 'r': 'reflective'})
+    sim.external_fields = [
+        ExternalField(undulator_field, 'By', 40., 5.e-6, gamma_boost=gamma_boost),
+        ExternalField(focusing_field, 'Ex', 3.e10, 4.e-6, species=sim.ptcl[0], gamma_boost=gamma_boost)]
+    out = dict(Nz=Nz, Nr=Nr, Nm=Nm, zmax=zmax, rmax=rmax, dt=dt, nsteps=nsteps,
+               gamma_boost=(0. if gamma_boost is None else gamma_boost))
+    sp = sim.ptcl[0]
+    out.update({'s0_in_%s' % k: v for k, v in ptcl_arrays(sp).items()})
+    out['s0_q'], out['s0_m'] = sp.q, sp.m
+    sim.step(nsteps, show_progress=False)
+    out.update({'s0_out_%s' % k: v for k, v in ptcl_arrays(sp).items()})
+    out.update({'out_' + k: v for k, v in field_arrays(sim).items()})
+    out['zmin_end'] = sim.fld.interp[0].zmin
+    save('step_external_' + tag, **out)
+
+
 GENERATORS = {
+    'external_lab': lambda: gen_external('lab'),
+    'external_boost': lambda: gen_external('boost', gamma_boost=4.),
     'laser_profiles': gen_laser_profiles,
     'laser_direct_gauss': lambda: gen_laser_direct('gauss'),
     'laser_direct_lg_pml': lambda: gen_laser_direct('lg_pml', lg=True, pml=True),

@@ -430,10 +430,59 @@ class FakeLib(object):
         return self.emu.emu_antenna_particles(ctypes.c_longlong(n), *[V(_addr(p)) for p in (bx, by, ex, ey, vx, vy, vz)],
                                               ctypes.c_double(sign), *[V(_addr(p)) for p in (x, y, ux, uy, uz)])
 
+    # external fields: the CUDA C body produced by fbpic_b200.lpa_utils.external_fields, compiled for the host
+    def b2_external_field_compile(self, body, handle):
+        import hashlib
+        import tempfile
+        body = body.decode() if isinstance(body, bytes) else body
+        src = HOST_EXT_FIELD_TEMPLATE % body
+        d = os.path.join(tempfile.gettempdir(), 'b2_fake_extfield')
+        os.makedirs(d, exist_ok=True)
+        base = os.path.join(d, hashlib.sha1(src.encode()).hexdigest())
+        if not os.path.exists(base + '.so'):
+            with open(base + '.cpp', 'w') as f:
+                f.write(src)
+            subprocess.check_call(['g++', '-O1', '-ffp-contract=off', '-std=c++17', '-shared', '-fPIC',
+                                   '-o', base + '.so', base + '.cpp'])
+        self._ext = getattr(self, '_ext', {})
+        key = len(self._ext) + 1
+        self._ext[key] = ctypes.CDLL(base + '.so')
+        handle._obj.value = key
+        return 0
+
+    def b2_external_field_apply(self, ctx, handle, n, F, x, y, z, t, amplitude, length_scale, gamma_b, beta_b,
+                                stream):
+        lib = self._ext[_addr(handle)]
+        V, D = ctypes.c_void_p, ctypes.c_double
+        lib.apply(ctypes.c_longlong(n), V(_addr(F)), V(_addr(x)), V(_addr(y)), V(_addr(z)), D(t), D(amplitude),
+                  D(length_scale), D(gamma_b), D(beta_b))
+        return 0
+
+    def b2_external_field_free(self, handle):
+        return 0
+
     def b2_axpy(self, ctx, n, a, x, y, stream):
         return self.emu.emu_axpy(ctypes.c_longlong(n), ctypes.c_double(a), ctypes.c_void_p(_addr(x)),
                                  ctypes.c_void_p(_addr(y)))
 
+
+HOST_EXT_FIELD_TEMPLATE = r'''
+#include <cmath>
+using namespace std;
+static void one(long long i_, double *F_, const double *x_, const double *y_, const double *z_, double t_,
+                double amplitude, double length_scale, double gamma_b_, double beta_b_) {
+    const double c_ = 299792458.0;
+    const double F = F_[i_], x = x_[i_], y = y_[i_];
+    const double z = gamma_b_ * (z_[i_] + beta_b_ * c_ * t_);
+    const double t = gamma_b_ * (t_ + beta_b_ * (1. / c_) * z_[i_]);
+    (void)F; (void)x; (void)y; (void)z; (void)t; (void)amplitude; (void)length_scale;
+%s
+}
+extern "C" void apply(long long n, double *F_, const double *x_, const double *y_, const double *z_, double t_,
+                      double amplitude, double length_scale, double gamma_b_, double beta_b_) {
+    for (long long i = 0; i < n; ++i) one(i, F_, x_, y_, z_, t_, amplitude, length_scale, gamma_b_, beta_b_);
+}
+'''
 
 _KEEP = []      # fakes (and the host blocks they own) stay alive for the whole pytest process
 

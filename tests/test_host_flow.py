@@ -12,6 +12,7 @@ import fake_device
 import test_gpu_step
 import test_gpu_widen
 import test_gpu_laser
+import test_gpu_external
 
 
 @pytest.fixture
@@ -55,3 +56,13 @@ def test_add_laser_direct_flow(fake, tag):
 @pytest.mark.parametrize('tag', ['lab', 'moving', 'boost'])
 def test_laser_antenna_flow(fake, tag, fused):
     test_gpu_laser.test_laser_antenna_vs_reference_golden(tag, fused)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('tag', ['lab', 'boost'])
+def test_external_fields_flow(fake, tag, fused):
+    test_gpu_external.test_external_fields_step_vs_reference_golden(tag, fused)
+
+
+def test_external_field_string_flow(fake):
+    test_gpu_external.test_external_field_string_expression()
