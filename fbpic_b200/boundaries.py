@@ -417,6 +417,47 @@ class BoundaryCommunicator(object):
         """boundary_communicator.py:531-553"""
         self.moving_win.move_grids(fld, ptcl, self, time)
 
+    # ---- global <-> local grid arrays on the host (boundary_communicator.py:1011-1130); used by the one-off
+    #      set-up routines (laser injection, bunch space charge), never inside the PIC cycle ----
+    def _host_group(self):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group('gloo')
+        return dist
+
+    def allreduce_sum(self, values):
+        """Sum of a short list of floats over the ranks (mpi_comm.allreduce in the reference)."""
+        if self.size == 1:
+            return list(values)
+        import torch
+        t = torch.tensor(list(values), dtype=torch.float64)
+        self._host_group().all_reduce(t)
+        return [float(v) for v in t]
+
+    def gather_grid_array(self, array, root=0, with_damp=False):
+        """Global array (no guard cells; damp cells if with_damp) assembled from the local host arrays.
+        Unlike the reference (root only) every rank receives it: the set-up solves that use it run
+        redundantly on every GPU instead of on rank 0 + scatter."""
+        Nr = self.get_Nr(with_damp=with_damp)
+        Nz_local, iz_dom = self.get_Nz_and_iz(local=True, with_damp=with_damp, with_guard=False, rank=self.rank)
+        _, iz_arr = self.get_Nz_and_iz(local=True, with_damp=True, with_guard=True, rank=self.rank)
+        i0 = iz_dom - iz_arr
+        local = np.ascontiguousarray(array[i0:i0 + Nz_local, :Nr])
+        if self.size == 1:
+            return local.copy()
+        parts = [None] * self.size
+        self._host_group().all_gather_object(parts, local)
+        return np.concatenate(parts, axis=0)
+
+    def scatter_grid_array(self, array, root=0, with_damp=False):
+        """The local part (no guard cells) of a global array that every rank holds."""
+        Nz_global, iz_glob = self.get_Nz_and_iz(local=False, with_damp=with_damp, with_guard=False)
+        Nr = self.get_Nr(with_damp=with_damp)
+        assert array.shape == (Nz_global, Nr)
+        Nz_local, iz_dom = self.get_Nz_and_iz(local=True, with_damp=with_damp, with_guard=False, rank=self.rank)
+        i0 = iz_dom - iz_glob
+        return np.array(array[i0:i0 + Nz_local], dtype=np.complex128)
+
     def bcast_int(self, value):
         """Rank 0's integer on every rank (the n_move broadcast of moving_window.py:97)."""
         if self.size == 1:

@@ -205,7 +205,33 @@ def gen_external(tag, gamma_boost=None, nsteps=4):
     save('step_external_' + tag, **out)
 
 
+def gen_bunch(tag, gaussian=False, gamma_boost=None):
+    """Relativistic bunch + its space-charge field on the grid (bunch.py:18-1007)."""
+    from fbpic.lpa_utils.bunch import add_particle_bunch, add_particle_bunch_gaussian
+    from fbpic.lpa_utils.boosted_frame import BoostConverter
+    np.random.seed(17)
+    Nz, Nr, Nm, zmax, rmax = 40, 16, 2, 20.e-6, 16.e-6
+    dt = zmax / Nz / c
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, zmin=0., n_order=-1, n_guard=12, n_damp={'z': 10, 'r': 6},
+                     gamma_boost=gamma_boost, verbose_level=0, boundaries={'z': 'open', 'r': 'reflective'})
+    boost = BoostConverter(gamma_boost) if gamma_boost is not None else None
+    if gaussian:
+        sp = add_particle_bunch_gaussian(sim, -e, m_e, sig_r=2.e-6, sig_z=1.5e-6, n_emit=1.e-6, gamma0=200.,
+                                         sig_gamma=2., n_physical_particles=1.e8, n_macroparticles=2000,
+                                         tf=10.e-15, zf=10.e-6, boost=boost, symmetrize=True)
+    else:
+        sp = add_particle_bunch(sim, -e, m_e, 100., 1.e23, 6.e-6, 12.e-6, 0., 5.e-6, boost=boost)
+    out = dict(Nz=Nz, Nr=Nr, Nm=Nm, zmax=zmax, rmax=rmax, dt=dt, gaussian=gaussian,
+               gamma_boost=(0. if gamma_boost is None else gamma_boost))
+    out.update({'s0_%s' % k: v for k, v in ptcl_arrays(sp).items()})
+    out.update({'out_' + k: v for k, v in field_arrays(sim, ('E', 'B')).items()})
+    save('bunch_' + tag, **out)
+
+
 GENERATORS = {
+    'bunch_uniform': lambda: gen_bunch('uniform'),
+    'bunch_gaussian': lambda: gen_bunch('gaussian', gaussian=True),
+    'bunch_gaussian_boost': lambda: gen_bunch('gaussian_boost', gaussian=True, gamma_boost=5.),
     'external_lab': lambda: gen_external('lab'),
     'external_boost': lambda: gen_external('boost', gamma_boost=4.),
     'laser_profiles': gen_laser_profiles,

@@ -41,3 +41,14 @@ def test_halo_exchange_world_size_2_gloo():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert 'GLOO_HALO_OK' in out.stdout
+
+
+def test_gather_scatter_world_size_2_gloo():
+    """gather_grid_array / scatter_grid_array / allreduce_sum of the set-up routines, 2 ranks over gloo."""
+    env = dict(os.environ, OMP_NUM_THREADS='1')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', '29633',
+           os.path.join(ROOT, 'tests', 'workers', 'gloo_gather_worker.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert 'GLOO_GATHER_OK' in out.stdout

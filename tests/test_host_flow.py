@@ -13,6 +13,7 @@ import test_gpu_step
 import test_gpu_widen
 import test_gpu_laser
 import test_gpu_external
+import test_gpu_bunch
 
 
 @pytest.fixture
@@ -66,3 +67,8 @@ def test_external_fields_flow(fake, tag, fused):
 
 def test_external_field_string_flow(fake):
     test_gpu_external.test_external_field_string_expression()
+
+
+@pytest.mark.parametrize('tag', ['uniform', 'gaussian', 'gaussian_boost'])
+def test_bunch_space_charge_flow(fake, tag):
+    test_gpu_bunch.test_bunch_space_charge_vs_reference_golden(tag)
