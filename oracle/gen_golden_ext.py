@@ -228,7 +228,34 @@ def gen_bunch(tag, gaussian=False, gamma_boost=None):
     save('bunch_' + tag, **out)
 
 
+def gen_script(tag):
+    """The scaled-down documented input scripts of tests/script_cases.py, run by the reference."""
+    import types
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'tests'))
+    import script_cases
+    from fbpic.lpa_utils.laser import add_laser_pulse, GaussianLaser
+    from fbpic.lpa_utils.bunch import add_particle_bunch
+    from fbpic.lpa_utils.boosted_frame import BoostConverter
+    ns = types.SimpleNamespace(Simulation=Simulation, add_laser_pulse=add_laser_pulse, GaussianLaser=GaussianLaser,
+                               add_particle_bunch=add_particle_bunch, BoostConverter=BoostConverter)
+    np.random.seed(31)
+    sim, species, nsteps = script_cases.CASES[tag](ns, verbose_level=0)
+    out = dict(nsteps=nsteps, Nm=sim.fld.Nm, Nz_local=sim.fld.interp[0].Nz, dt=sim.dt,
+               species=np.array(sorted(species)))
+    out.update({'%s_n_in' % name: sp.Ntot for name, sp in species.items()})
+    np.random.seed(32)
+    sim.step(nsteps, show_progress=False)
+    for name, sp in species.items():
+        out.update({'%s_out_%s' % (name, k): v for k, v in ptcl_arrays(sp).items()})
+    out.update({'out_' + k: v for k, v in field_arrays(sim).items()})
+    out['zmin_end'] = sim.fld.interp[0].zmin
+    out['time_end'] = sim.time
+    save('script_' + tag, **out)
+
+
 GENERATORS = {
+    'script_lwfa': lambda: gen_script('lwfa'),
+    'script_boosted': lambda: gen_script('boosted'),
     'bunch_uniform': lambda: gen_bunch('uniform'),
     'bunch_gaussian': lambda: gen_bunch('gaussian', gaussian=True),
     'bunch_gaussian_boost': lambda: gen_bunch('gaussian_boost', gaussian=True, gamma_boost=5.),

@@ -14,6 +14,7 @@ import test_gpu_widen
 import test_gpu_laser
 import test_gpu_external
 import test_gpu_bunch
+import test_gpu_scripts
 
 
 @pytest.fixture
@@ -72,3 +73,9 @@ def test_external_field_string_flow(fake):
 @pytest.mark.parametrize('tag', ['uniform', 'gaussian', 'gaussian_boost'])
 def test_bunch_space_charge_flow(fake, tag):
     test_gpu_bunch.test_bunch_space_charge_vs_reference_golden(tag)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('tag', ['lwfa', 'boosted'])
+def test_example_script_flow(fake, tag, fused):
+    test_gpu_scripts.test_example_script_vs_reference_golden(tag, fused)
