@@ -47,3 +47,40 @@ def test_no_cpu_fallback():
         sim.step(1)
     with pytest.raises(B200Error):
         sim.ptcl[0].push_x(1.e-16)
+
+
+def header_prototypes():
+    """name -> number of parameters, parsed from the declarations of include/fbpic_b200.h"""
+    txt = open(os.path.join(ROOT, 'include', 'fbpic_b200.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    out = {}
+    for m in re.finditer(r'\b(b2_[A-Za-z0-9_]+)\s*\(([^;{]*?)\)\s*;', txt, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ('', 'void') else len(args.split(','))
+    return out
+
+
+def test_ctypes_argument_counts_match_header():
+    """Every ctypes signature has as many arguments as the C prototype it binds, and pointer / integer /
+    floating-point arguments sit at the same positions."""
+    protos = header_prototypes()
+    assert sorted(protos) == sorted(_lib.EXPORTED)
+    txt = re.sub(r'/\*.*?\*/', '', open(os.path.join(ROOT, 'include', 'fbpic_b200.h')).read(), flags=re.S)
+    for name, argtypes in _lib._SIGNATURES.items():
+        assert len(argtypes) == protos[name], (name, len(argtypes), protos[name])
+        m = re.search(r'\b%s\s*\(([^;{]*?)\)\s*;' % name, txt, flags=re.S)
+        params = [p.strip() for p in m.group(1).split(',')] if protos[name] else []
+        for i, (p, t) in enumerate(zip(params, argtypes)):
+            is_ptr = '*' in p
+            is_dbl = (not is_ptr) and p.startswith('double')
+            if is_ptr:
+                ok = t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, 'contents') or 'LP_' in t.__name__
+            elif is_dbl:
+                ok = t is ctypes.c_double
+            elif p.startswith('int64_t'):
+                ok = t is ctypes.c_int64
+            elif p.startswith('size_t'):
+                ok = t is ctypes.c_size_t
+            else:
+                ok = t is ctypes.c_int
+            assert ok, '%s: argument %d (%s) is bound as %s' % (name, i, p, t.__name__)
