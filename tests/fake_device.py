@@ -406,6 +406,81 @@ class FakeLib(object):
         _grid(dst, nrows, Nr)[:, :] += _grid(src, nrows, Nr)
         return 0
 
+    # ---------------------------------------------------------------- z-slab exchange: gloo stands in for NCCL
+    def b2_halo_stage(self, ctx, mode, na, arrays, row0, nrow, Nr, packed, stream):
+        if na <= 0 or nrow <= 0:
+            return 0
+        pk = _arr(packed, na * nrow * Nr, np.complex128).reshape(na, nrow, Nr)
+        for k, a in enumerate(_ptrs(arrays, na)):
+            rows = _arr(a + 16 * row0 * Nr, nrow * Nr, np.complex128).reshape(nrow, Nr)
+            if mode == 0:
+                pk[k] = rows
+            elif mode == 1:
+                rows[:, :] = pk[k]
+            else:
+                rows[:, :] += pk[k]
+        return 0
+
+    def b2_nccl_unique_id(self, ident):
+        ctypes.memset(_addr(ident), 0, 128)
+        return 0
+
+    def b2_nccl_init(self, ctx, ident, rank, size):
+        self._rank, self._size, self._group = rank, size, None
+        return 0
+
+    def b2_nccl_destroy(self, ctx):
+        return 0
+
+    def b2_nccl_group_start(self):
+        self._group = []
+        return 0
+
+    def b2_comm_begin(self, ctx):
+        return self.b2_nccl_group_start()
+
+    def _p2p(self, kind, buf, nbytes, peer):
+        op = (kind, _addr(buf), int(nbytes), int(peer))
+        if getattr(self, '_group', None) is not None:
+            self._group.append(op)
+        else:
+            self._run_ops([op])
+        return 0
+
+    def b2_nccl_send(self, ctx, buf, nbytes, peer, stream):
+        return self._p2p('send', buf, nbytes, peer)
+
+    def b2_nccl_recv(self, ctx, buf, nbytes, peer, stream):
+        return self._p2p('recv', buf, nbytes, peer)
+
+    def _run_ops(self, ops):
+        # NCCL pairs the k-th send to a peer with the k-th receive posted for that peer: same rule, as tags
+        import torch
+        import torch.distributed as dist
+        reqs, keep, count = [], [], {}
+        for kind, addr, nbytes, peer in ops:
+            if nbytes == 0:
+                continue
+            k = count.get((kind, peer), 0)
+            count[(kind, peer)] = k + 1
+            t = torch.from_numpy(_arr(addr, nbytes, np.uint8))
+            if kind == 'send':
+                t = t.clone()
+                reqs.append(dist.isend(t, peer, tag=k))
+            else:
+                reqs.append(dist.irecv(t, peer, tag=k))
+            keep.append(t)
+        for r in reqs:
+            r.wait()
+
+    def b2_nccl_group_end(self):
+        ops, self._group = self._group or [], None
+        self._run_ops(ops)
+        return 0
+
+    def b2_comm_end(self, ctx):
+        return self.b2_nccl_group_end()
+
     # ---------------------------------------------------------------- solver variants: the real kernel
     # source of fbpic_b200/csrc/b2_ext_kernels.cuh, compiled for the host by tests/hostemu
     def b2_push_eb_pml(self, ctx, Ep, Em, Bp, Bm, Ez, Bz, C, S_w, T_eb, kr, Nz, Nr, stream):
@@ -485,6 +560,17 @@ extern "C" void apply(long long n, double *F_, const double *x_, const double *y
 '''
 
 _KEEP = []      # fakes (and the host blocks they own) stay alive for the whole pytest process
+
+
+def install_global():
+    """Install the fake for the lifetime of the process (multi-rank worker scripts of tests/workers run with
+    `--fake-device` under torchrun + gloo in the GPU-less container)."""
+    from fbpic_b200 import _lib
+    fake = FakeLib()
+    _KEEP.append(fake)
+    _lib._lib, _lib._ctx = fake, None
+    _lib.call.__dict__.clear()
+    return fake
 
 
 def install(monkeypatch):

@@ -6,7 +6,12 @@ cross-deposition / antenna flows, particle exchange and injection on one rank.  
 the CUDA kernels (the `-m gpu` tests do, through the real library).  The test bodies are the GPU tests
 themselves, imported from their modules."""
 import gc
+import os
+import subprocess
+import sys
 import pytest
+
+from conftest import ROOT
 
 import fake_device
 import test_gpu_step
@@ -79,3 +84,28 @@ def test_bunch_space_charge_flow(fake, tag):
 @pytest.mark.parametrize('tag', ['lwfa', 'boosted'])
 def test_example_script_flow(fake, tag, fused):
     test_gpu_scripts.test_example_script_vs_reference_golden(tag, fused)
+
+
+def test_two_rank_flow_gloo():
+    """The 2-rank parity worker of tests/test_gpu_multi.py (periodic slabs with and without the current
+    correction, open z + moving window + injection + migration) on the CPU: fake device + gloo."""
+    env = dict(os.environ, OMP_NUM_THREADS='2', ORACLE_NUM_THREADS='2', MGPU_NZ_PER_RANK='64', MGPU_STEPS='10',
+               MGPU_WINDOW_STEPS='24')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', '29647',
+           os.path.join(ROOT, 'tests', 'workers', 'mgpu_parity_worker.py'), '--fake-device']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0 and 'MGPU_PARITY_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize('Nm', [2, 4])
+def test_two_rank_pml_antenna_flow_gloo(Nm):
+    """2 ranks, open z + radial PML + laser antenna + moving window with injection vs the single domain
+    (Nm = 4: the E/B + PML guard exchange exceeds one staging launch and is chunked)."""
+    env = dict(os.environ, OMP_NUM_THREADS='2', ORACLE_NUM_THREADS='2', MGPU_NZ_PER_RANK='64',
+               MGPU_WINDOW_STEPS='24', MGPU_EXTRA='1', MGPU_NM=str(Nm))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', str(29649 + Nm),
+           os.path.join(ROOT, 'tests', 'workers', 'mgpu_parity_worker.py'), '--fake-device']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0 and 'MGPU_EXTRA_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

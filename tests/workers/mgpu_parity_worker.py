@@ -22,6 +22,12 @@ from scipy.constants import c, e, m_e
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+if '--fake-device' in sys.argv:
+    # CPU run of the multi-rank HOST logic (tests/test_host_flow.py): the fake library of tests/fake_device.py
+    # stands in for libfbpic_b200.so and gloo for NCCL.  Never set in the GPU tests.
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import fake_device
+    fake_device.install_global()
 from fbpic_b200 import Simulation                     # noqa: E402
 from fbpic_b200.particles import generate_evenly_spaced   # noqa: E402
 
@@ -188,8 +194,83 @@ def run_window_case(tol):
     return bool(int(flag[0]))
 
 
+def run_pml_antenna_case(tol):
+    """Open z + radial PML + a laser antenna sitting in the first slab + moving window with plasma
+    injection (correct_currents=False: local in z).  The PML split components travel with E, B in the guard
+    exchange (boundary_communicator.py:621-627); the antenna deposits on the rank that holds it
+    (antenna_injection.py:171-194).  Nm = MGPU_NM (4: more slabs than one staging launch carries, the
+    exchange is chunked)."""
+    from fbpic_b200.lpa_utils.laser import add_laser_pulse, GaussianLaser
+    rank, size = dist.get_rank(), dist.get_world_size()
+    nsteps = int(os.environ.get('MGPU_WINDOW_STEPS', '40'))
+    nzr = int(os.environ.get('MGPU_NZ_PER_RANK', '96'))
+    Nm = int(os.environ.get('MGPU_NM', '2'))
+    Nz, Nr, rmax, n_order = nzr * size, 12, 6.e-6, 8
+    zmax = 0.25e-6 * Nz
+    dt = zmax / Nz / c
+    kw = dict(p_zmin=0.6 * zmax, p_zmax=1., p_rmin=0, p_rmax=5.e-6, p_nz=2, p_nr=2, p_nt=4, n_e=1.e24,
+              n_order=n_order, n_damp={'z': 32, 'r': 6}, boundaries={'z': 'open', 'r': 'open'})
+
+    def launch(sim):
+        prof = GaussianLaser(a0=1., waist=2.5e-6, tau=4.e-15, z0=0.1 * zmax - 3.e-6, zf=0.5 * zmax,
+                             theta_pol=0.3, lambda0=1.e-6)
+        add_laser_pulse(sim, prof, method='antenna', z0_antenna=0.1 * zmax)
+        sim.set_moving_window(v=0.5 * c)
+        np.random.seed(3)
+        sim.step(nsteps, correct_currents=False)
+
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, **kw)
+    assert sim.comm.size == size and sim.use_pml
+    ng = sim.comm.n_guard
+    np.random.seed(21)
+    ref = Simulation(Nz, zmax, Nr, rmax, Nm, dt, use_all_mpi_ranks=False, n_guard=ng, **kw)
+    zlo, zhi = sim.comm.get_zmin_zmax(local=True, with_damp=False, with_guard=False, rank=rank)
+    sp, rp = sim.ptcl[0], ref.ptcl[0]
+    sel = (rp.z >= zlo) & (rp.z < zhi)
+    for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w'):
+        setattr(sp, k, getattr(rp, k)[sel].copy())
+    sp.Ntot = int(sel.sum())
+    for k in ('Ex', 'Ey', 'Ez', 'Bx', 'By', 'Bz'):
+        setattr(sp, k, np.zeros(sp.Ntot))
+    launch(sim)
+    names = ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'Er_pml', 'Et_pml', 'Br_pml', 'Bt_pml', 'rho')
+    nn = len(names)
+    loc = np.stack([getattr(sim.fld.interp[m], k)[ng:sim.fld.interp[m].Nz - ng] for m in range(Nm) for k in names])
+    gathered = [None] * size
+    dist.all_gather_object(gathered, (loc, sim.ptcl[0].Ntot))
+    ok = True
+    if rank == 0:
+        glob = np.concatenate([g[0] for g in gathered], axis=1)
+        launch(ref)
+        full = np.stack([getattr(ref.fld.interp[m], k)[ng:ref.fld.interp[m].Nz - ng] for m in range(Nm) for k in names])
+        assert abs(ref.fld.interp[0].zmin - sim.fld.interp[0].zmin) < 1e-12
+        # PML components are compared on the scale of their parent field
+        for gname, cols in {'E': (0, 1, 2, 6, 7), 'B': (3, 4, 5, 8, 9), 'rho': (10,)}.items():
+            idx = [m * nn + j for m in range(Nm) for j in cols]
+            scale = max(np.abs(full[i]).max() for i in idx)
+            assert scale > 0, gname
+            for i in idx:
+                err = np.abs(glob[i] - full[i]).max()
+                if not err <= tol * scale:
+                    ok = False
+                    print('PML/ANTENNA MISMATCH %s m%d: err %.3e scale %.3e' % (names[i % nn], i // nn, err, scale))
+        if sum(g[1] for g in gathered) != ref.ptcl[0].Ntot:
+            ok = False
+            print('PML/ANTENNA MISMATCH particle count', [g[1] for g in gathered], ref.ptcl[0].Ntot)
+        print('pml+antenna: particles/rank', [g[1] for g in gathered], 'single', ref.ptcl[0].Ntot)
+    flag = torch.tensor([1 if ok else 0])
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    return bool(int(flag[0]))
+
+
 def main():
     dist.init_process_group('gloo')
+    if os.environ.get('MGPU_EXTRA') == '1':
+        ok = run_pml_antenna_case(1e-8)
+        if dist.get_rank() == 0 and ok:
+            print('MGPU_EXTRA_OK size=%d' % dist.get_world_size())
+        sys.exit(0 if ok else 1)
     ok = run_case(False, 1e-9)
     ok = run_case(True, 5e-4) and ok
     ok = run_window_case(1e-8) and ok
