@@ -2,7 +2,8 @@
 Laser initialisation and emission, same entry points as `fbpic.lpa_utils.laser`
 (fbpic/lpa_utils/laser/{laser.py, laser_profiles.py, direct_injection.py, antenna_injection.py}):
 
-* laser profiles (`GaussianLaser`, `LaguerreGaussLaser`, sums with `+`): analytic E(x, y, z, t), NumPy;
+* laser profiles (`GaussianLaser`, `LaguerreGaussLaser`, `DonutLikeLaguerreGaussLaser`, `FlattenedGaussianLaser`,
+  `FewCycleLaser`, sums with `+`): analytic E(x, y, z, t), NumPy (`FromLasyFileLaser` needs h5py: not built);
 * `add_laser_pulse(sim, profile, method='direct')`: the profile is sampled on the global grid, Ez and B
   follow from div E = 0 and Faraday's law in spectral space.  The transforms of that one-off set-up run on
   the GPU (cuFFT + DMMA Hankel kernels of the hot path) -- the reference does them on the CPU even in GPU
@@ -15,7 +16,7 @@ Laser initialisation and emission, same entry points as `fbpic.lpa_utils.laser`
 import numpy as np
 from math import factorial
 from scipy.constants import c, m_e, e, epsilon_0, physical_constants
-from scipy.special import genlaguerre
+from scipy.special import genlaguerre, binom
 
 from .. import _lib
 from .._lib import DeviceArray, call, ptr_array
@@ -129,6 +130,88 @@ class LaguerreGaussLaser(_ParaxialLaser):
         prof = np.exp(-r2 / (self.w0**2 * d) - 1.j * (2 * self.p + self.m) * psi) / d \
             * np.sqrt(s2)**self.m * self.laguerre_pm(s2) * np.cos(self.m * (theta - self.theta0))
         return prof * self.scaled_amplitude
+
+
+class DonutLikeLaguerreGaussLaser(_ParaxialLaser):
+    """Laguerre-Gauss mode (p, m) with the helical phase exp(-i m theta): a donut-like intensity profile
+    (laser_profiles.py:448-584, transverse_laser_profiles.py:312-432)."""
+
+    def __init__(self, p, m, a0, waist, tau, z0, zf=None, theta_pol=0., lambda0=0.8e-6, cep_phase=0.,
+                 propagation_direction=1):
+        _ParaxialLaser.__init__(self, a0, waist, tau, z0, zf, theta_pol, lambda0, cep_phase, 0.,
+                                propagation_direction)
+        self.p, self.m = p, m
+        self.scaled_amplitude = np.sqrt(factorial(p) / factorial(abs(m) + p))
+        self.laguerre_pm = genlaguerre(p, abs(m))
+
+    def transverse(self, x, y, z):
+        d = self._diffract(z)
+        w = self.w0 * abs(d)
+        psi = np.angle(d)
+        r2 = x**2 + y**2
+        s2 = 2 * r2 / w**2
+        theta = np.angle(x + 1.j * y)
+        arg = -1.j * self.m * theta - r2 / (self.w0**2 * d) - 1.j * (2 * self.p + abs(self.m)) * psi
+        return np.exp(arg) / d * np.sqrt(s2)**abs(self.m) * self.laguerre_pm(s2) * self.scaled_amplitude
+
+
+class FlattenedGaussianLaser(_ParaxialLaser):
+    """Flat-top-like intensity far from focus (a Gaussian times a polynomial of order N there), built as a
+    sum of N+1 Laguerre-Gauss modes of waist w0 sqrt(N+1) (laser_profiles.py:587-710,
+    transverse_laser_profiles.py:434-565)."""
+
+    def __init__(self, a0, w0, tau, z0, N=6, zf=None, theta_pol=0., lambda0=0.8e-6, cep_phase=0.,
+                 propagation_direction=1):
+        self.N = int(round(N))
+        w_foc = w0 * (self.N + 1)**.5
+        _ParaxialLaser.__init__(self, a0, w_foc, tau, z0, zf, theta_pol, lambda0, cep_phase, 0.,
+                                propagation_direction)
+        self.w_foc = w_foc
+        self.cn = np.empty(self.N + 1)
+        for n in range(self.N + 1):
+            mv = np.arange(n, self.N + 1)
+            self.cn[n] = np.sum((1. / 2)**mv * binom(mv, n)) / (self.N + 1)
+
+    def transverse(self, x, y, z):
+        d = self._diffract(z)
+        w = self.w_foc * np.abs(d)
+        psi = np.angle(d)
+        r2 = x**2 + y**2
+        s2 = 2 * r2 / w**2
+        total = np.zeros_like(x, dtype=np.complex128)
+        L_prev, L = 0., 1.                       # three-term recurrence of the Laguerre polynomials
+        for n in range(self.N + 1):
+            if n == 1:
+                L_prev, L = L, 1. - s2
+            elif n > 1:
+                L_prev, L = L, (((2 * n - 1) - s2) * L - (n - 1) * L_prev) / n
+            total += self.cn[n] * np.exp(-(2j * n) * psi) * L
+        return total * np.exp(-r2 / (self.w_foc**2 * d)) / d
+
+
+class FewCycleLaser(LaserProfile):
+    """Ultra-short, tightly focused pulse: an exact solution of the paraxial equation with a Poisson-like
+    spectrum, valid down to a few cycles (laser_profiles.py:713-838)."""
+
+    def __init__(self, a0, waist, tau_fwhm, z0, zf=None, theta_pol=0., lambda0=0.8e-6, cep_phase=0.,
+                 propagation_direction=1):
+        from scipy.optimize import fsolve
+        LaserProfile.__init__(self, propagation_direction, gpu_capable=True)
+        self.k0 = 2 * np.pi / lambda0
+        E0 = a0 * m_e * c**2 * self.k0 / e
+        self.zr = 0.5 * self.k0 * waist**2
+        self.zf = z0 if zf is None else zf
+        self.z0, self.w0, self.cep_phase = z0, waist, cep_phase
+        self.E0x, self.E0y = E0 * np.cos(theta_pol), E0 * np.sin(theta_pol)
+        w_tau = c * self.k0 * tau_fwhm          # the Poisson parameter s follows from the FWHM duration
+        self.s = fsolve(lambda s: s * (2 * (4**(1 / (s + 1)) - 1))**.5 - w_tau, 1.)[0]
+
+    def E_field(self, x, y, z, t):
+        d = self.propag_direction
+        inv_q = 1. / (d * (z - self.zf) + 1.j * self.zr)
+        arg = 1. + 1.j * self.k0 / self.s * (d * (z - self.z0) - c * t + 0.5 * (x**2 + y**2) * inv_q)
+        prof = np.exp(1.j * self.cep_phase) * 1.j * self.zr * inv_q * arg**(-self.s - 1)
+        return (self.E0x * prof).real, (self.E0y * prof).real
 
 
 # =============================================================================

@@ -7,7 +7,8 @@ from conftest import load_golden, assert_close
 
 
 def test_laser_profiles_vs_reference():
-    from fbpic_b200.lpa_utils.laser import GaussianLaser, LaguerreGaussLaser
+    from fbpic_b200.lpa_utils.laser import GaussianLaser, LaguerreGaussLaser, DonutLikeLaguerreGaussLaser, \
+        FlattenedGaussianLaser, FewCycleLaser
     g = load_golden('laser_profiles')
     x, y, z, t = g['x'], g['y'], g['z'], float(g['t'])
     profs = {
@@ -17,6 +18,14 @@ def test_laser_profiles_vs_reference():
         'lg11': LaguerreGaussLaser(1, 1, a0=1.5, waist=6.e-6, tau=18.e-15, z0=8.e-6, zf=-5.e-6, theta_pol=1.1,
                                    cep_phase=0.2, theta0=0.5),
         'lg20': LaguerreGaussLaser(2, 0, a0=0.7, waist=5.e-6, tau=25.e-15, z0=0.),
+        'donut12': DonutLikeLaguerreGaussLaser(1, 2, a0=1.2, waist=6.e-6, tau=18.e-15, z0=8.e-6, zf=20.e-6,
+                                               theta_pol=0.6, cep_phase=0.1),
+        'donut0m1': DonutLikeLaguerreGaussLaser(0, -1, a0=1., waist=5.e-6, tau=12.e-15, z0=3.e-6,
+                                                propagation_direction=-1),
+        'flat': FlattenedGaussianLaser(a0=1.3, w0=5.e-6, tau=20.e-15, z0=5.e-6, N=5, zf=60.e-6, theta_pol=0.2,
+                                       cep_phase=0.3),
+        'fewcycle': FewCycleLaser(a0=2., waist=3.e-6, tau_fwhm=5.e-15, z0=10.e-6, zf=14.e-6, theta_pol=0.9,
+                                  cep_phase=0.7),
     }
     for k, p in profs.items():
         Ex, Ey = p.E_field(x, y, z, t)

@@ -208,7 +208,7 @@ def run_pml_antenna_case(tol):
     Nz, Nr, rmax, n_order = nzr * size, 12, 6.e-6, 8
     zmax = 0.25e-6 * Nz
     dt = zmax / Nz / c
-    kw = dict(p_zmin=0.6 * zmax, p_zmax=1., p_rmin=0, p_rmax=5.e-6, p_nz=2, p_nr=2, p_nt=4, n_e=1.e24,
+    kw = dict(p_zmin=0.45 * zmax, p_zmax=1., p_rmin=0, p_rmax=5.e-6, p_nz=2, p_nr=2, p_nt=4, n_e=1.e24,
               n_order=n_order, n_damp={'z': 32, 'r': 6}, boundaries={'z': 'open', 'r': 'open'})
 
     def launch(sim):
