@@ -449,6 +449,22 @@ class BoundaryCommunicator(object):
         self._host_group().all_gather_object(parts, local)
         return np.concatenate(parts, axis=0)
 
+    def gather_grid(self, grid, root=0):
+        """A global InterpolationGrid (physical domain only: no guard, damp or PML cells) holding the host
+        data of the local grids of all ranks (boundary_communicator.py:964-1009); available on every rank."""
+        from .fields import InterpolationGrid, INTERP_FIELDS
+        Nz_g, _ = self.get_Nz_and_iz(local=False, with_guard=False, with_damp=False)
+        zmin_g, zmax_g = self.get_zmin_zmax(local=False, with_guard=False, with_damp=False)
+        out = InterpolationGrid(Nz_g, self.get_Nr(with_damp=False), grid.m, zmin_g, zmax_g,
+                                self.get_rmax(with_damp=False))
+        for k in INTERP_FIELDS:
+            a = getattr(grid, k)
+            if hasattr(a, 'ptr'):
+                raise _lib.B200Error('gather_grid acts on the host copy of the fields: call it after step() or '
+                                     'receive_data_from_gpu()')
+            setattr(out, k, self.gather_grid_array(a, root))
+        return out
+
     def scatter_grid_array(self, array, root=0, with_damp=False):
         """The local part (no guard cells) of a global array that every rank holds."""
         Nz_global, iz_glob = self.get_Nz_and_iz(local=False, with_damp=with_damp, with_guard=False)

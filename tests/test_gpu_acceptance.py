@@ -1,0 +1,155 @@
+"""The reference's physics acceptance tests of the hot path, restated for the B200 implementation
+with the reference's own parameters and pass criteria (its test files cannot be imported here: they import
+`fbpic`):
+  * tests/test_uniform_rho_deposition.py -- deposition + Ruyten shapes + cell volumes: a uniform plasma gives a
+    uniform charge density; a neutral plasma whose electrons are shifted by 1 % of a cell stays neutral;
+  * tests/test_boosted.py -- numerical Cherenkov instability of a relativistically flowing plasma: the
+    Galilean and comoving PSATD schemes are stable where the standard one is not;
+  * tests/test_continuous_injection.py -- moving window + continuous injection reproduce the prescribed
+    density profile (lab frame with / without plasma at t = 0, boosted frame with a Cartesian dens_func).
+(tests/test_periodic_plasma_wave.py is restated in test_gpu_plasma_wave.py.)"""
+import numpy as np
+import pytest
+from scipy.constants import c, e, m_e
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------ test_uniform_rho_deposition.py
+U = dict(Nz=250, zmax=20.e-6, Nr=50, rmax=20.e-6, Nm=2, p_nr=8, p_nz=1, p_nt=4, p_rmax=10.e-6, n=9.e24,
+         frac_shift=0.01)
+
+
+def _deposit_rho(sim):
+    """the reference's kernel-level call pattern (test_uniform_rho_deposition.py:61-66)"""
+    sim.send_data_to_gpu()
+    sim.fld.erase('rho')
+    for species in sim.ptcl:
+        species.deposit(sim.fld, 'rho')
+    sim.fld.sum_reduce_deposition_array('rho')
+    sim.fld.divide_by_volume('rho')
+    sim.receive_data_from_gpu()
+
+
+@pytest.mark.parametrize('shape', ['linear', 'cubic'])
+def test_uniform_electron_plasma(shape):
+    from fbpic_b200 import Simulation
+    u = U
+    sim = Simulation(u['Nz'], u['zmax'], u['Nr'], u['rmax'], u['Nm'], u['zmax'] / u['Nz'] / c, 0, u['zmax'], 0,
+                     u['p_rmax'], u['p_nz'], u['p_nr'], u['p_nt'], u['n'], initialize_ions=False,
+                     particle_shape=shape)
+    _deposit_rho(sim)
+    Nrmax = int(u['Nr'] * u['p_rmax'] * 1. / u['rmax'])
+    assert np.allclose(-u['n'] * e, sim.fld.interp[0].rho[:, :Nrmax - 2], 2.e-3)
+    assert np.allclose(0, sim.fld.interp[0].rho[:, Nrmax + 2:], 1.e-10)
+    assert np.allclose(0, sim.fld.interp[1].rho[:, :], 1.e-10)
+
+
+@pytest.mark.parametrize('shape', ['linear', 'cubic'])
+def test_neutral_plasma_shifted(shape):
+    from fbpic_b200 import Simulation
+    u = U
+    sim = Simulation(u['Nz'], u['zmax'], u['Nr'], u['rmax'], u['Nm'], u['zmax'] / u['Nz'] / c, 0, u['zmax'], 0,
+                     u['p_rmax'], u['p_nz'], u['p_nr'], u['p_nt'], u['n'], initialize_ions=True,
+                     particle_shape=shape)
+    sim.ptcl[0].x += u['frac_shift'] * u['rmax'] / u['Nr']
+    _deposit_rho(sim)
+    Nrmax = int(u['Nr'] * u['p_rmax'] * 1. / u['rmax'])
+    ne = u['n'] * e
+    assert np.allclose(0, sim.fld.interp[0].rho[:, :Nrmax - 2], atol=ne * 1.e-3)
+    assert np.allclose(0, sim.fld.interp[1].rho[:, :Nrmax - 2], atol=ne * 1.e-3)
+    assert np.allclose(0, sim.fld.interp[0].rho[:, Nrmax + 2:], 1.e-10)
+    assert np.allclose(0, sim.fld.interp[1].rho[:, Nrmax + 2:], atol=ne * 1.e-10)
+
+
+# ------------------------------------------------------------------ test_boosted.py
+def test_cherenkov_instability():
+    """test_boosted.py:76-142: gamma = 130 plasma on a periodic 40 x 20 grid, 600 cycles; the growth rate of
+    RMS(Er) over the last 30 cycles is more than 3.5x smaller with the Galilean / comoving schemes."""
+    from fbpic_b200 import Simulation
+    Nz, zmax, zmin, Nr, rmax, Nm, N_step = 40, 7.86, -7.86, 20, 7.86, 2, 600
+    dt = (zmax - zmin) / Nz / c
+    gamma_boost = 130.
+    uz_m = np.sqrt(gamma_boost**2 - 1)
+    n_e = gamma_boost / (4 * 3.14 * 2.81e-15)
+
+    def er_rms(sim):
+        return np.sqrt(np.average(abs(sim.fld.interp[0].Er)**2 + abs(sim.fld.interp[1].Er)**2))
+
+    slope = {}
+    for scheme in ('standard', 'galilean', 'pseudo-galilean'):
+        v_comoving = 0. if scheme == 'standard' else 0.9999 * c
+        np.random.seed(0)
+        sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, zmin, zmax, 0., rmax, 2, 2, 4, n_e, zmin=zmin,
+                         initialize_ions=True, v_comoving=v_comoving, use_galilean=(scheme == 'galilean'),
+                         boundaries={'z': 'periodic', 'r': 'reflective'})
+        for sp in sim.ptcl:
+            sp.uz[:] = uz_m
+            sp.inv_gamma[:] = 1. / np.sqrt(1 + sp.uz**2)
+        rms = [er_rms(sim)]
+        for i in range(int(N_step / 30)):
+            sim.step(30, show_progress=False)
+            rms.append(er_rms(sim))
+        assert np.all(np.isfinite(rms))
+        slope[scheme] = np.log(rms[-1]) - np.log(rms[-2])
+    assert slope['standard'] > 3.5 * slope['galilean']
+    assert slope['standard'] > 3.5 * slope['pseudo-galilean']
+
+
+# ------------------------------------------------------------------ test_continuous_injection.py
+CI = dict(Nz=100, Nr=50, Nm=2, zmin=-10.e-6, zmax=5.e-6, rmax=20.e-6, n=1.e24, ramp0=7.e-6)
+
+
+def _run_continuous_injection(gamma_boost, ramp, p_zmin, cartesian=False, N_check=2):
+    from fbpic_b200 import Simulation
+    u = CI
+    Nz, zmin, zmax, rmax, n = u['Nz'], u['zmin'], u['zmax'], u['rmax'], u['n']
+    dt = (zmax - zmin) / Nz / c
+    smooth_r = rmax * 0.5
+
+    def dens_func_cylindrical(z, r):
+        dens = np.ones_like(z)
+        dens = np.where(r > rmax - smooth_r, np.cos(0.5 * np.pi * (r - smooth_r) / smooth_r)**2, dens)
+        dens = np.where(z < p_zmin, 0., dens)
+        dens = np.where((z >= p_zmin) & (z < p_zmin + ramp), (z - p_zmin) / ramp * dens, dens)
+        return dens
+
+    if cartesian:
+        def dens_func(x, y, z):
+            return dens_func_cylindrical(z, (x**2 + y**2)**.5)
+    else:
+        dens_func = dens_func_cylindrical
+    np.random.seed(0)
+    sim = Simulation(Nz, zmax, u['Nr'], rmax, u['Nm'], dt, p_zmin, 1e6, 0, rmax, 2, 2, 4, 0.5 * n,
+                     dens_func=dens_func, initialize_ions=False, zmin=zmin, gamma_boost=gamma_boost,
+                     boundaries={'z': 'open', 'r': 'reflective'})
+    uth = 0.0001
+    sim.add_new_species(-e, m_e, 0.5 * n, dens_func, 4, 4, 8, p_zmin, 1e6, 0, rmax, ux_th=uth, uy_th=uth, uz_th=uth)
+    sim.set_moving_window(v=c)
+    N_step = int(Nz / N_check / 2)
+    for i in range(N_check):
+        sim.step(N_step, move_momenta=False)
+        g = sim.comm.gather_grid(sim.fld.interp[0])
+        z, r = np.meshgrid(g.z, g.r, indexing='ij')
+        if gamma_boost is None:
+            rho_expected = -n * e * dens_func_cylindrical(z, r)
+        else:
+            shift = np.sqrt(1. - 1. / gamma_boost**2) * c * sim.time
+            rho_expected = -gamma_boost * n * e * dens_func_cylindrical(z + shift, r)
+        # within 1 % of the expected value (test_continuous_injection.py:160-165)
+        assert np.allclose(g.rho.real, rho_expected, atol=1.e-2 * abs(rho_expected).max())
+        assert np.allclose(g.rho.imag, 0., atol=1.e-2 * abs(rho_expected).max())
+
+
+def test_labframe_with_preexisting_plasma():
+    _run_continuous_injection(None, CI['ramp0'], 0.e-6)
+
+
+def test_boosted_with_preexisting_plasma():
+    gamma_boost = 15.
+    _run_continuous_injection(gamma_boost, 2 * gamma_boost * CI['ramp0'], 0.e-6, cartesian=True)
+
+
+def test_labframe_without_preexisting_plasma():
+    dz = (CI['zmax'] - CI['zmin']) / CI['Nz']
+    _run_continuous_injection(None, CI['ramp0'], CI['zmax'] + 2 * dz)

@@ -20,6 +20,7 @@ import test_gpu_laser
 import test_gpu_external
 import test_gpu_bunch
 import test_gpu_scripts
+import test_gpu_acceptance
 
 
 @pytest.fixture
@@ -109,3 +110,20 @@ def test_two_rank_pml_antenna_flow_gloo(Nm):
            os.path.join(ROOT, 'tests', 'workers', 'mgpu_parity_worker.py'), '--fake-device']
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0 and 'MGPU_EXTRA_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+# ---- the reference's physics acceptance tests (restated in test_gpu_acceptance.py), host flow on the CPU
+@pytest.mark.parametrize('shape', ['linear', 'cubic'])
+def test_uniform_rho_flow(fake, shape):
+    test_gpu_acceptance.test_uniform_electron_plasma(shape)
+    test_gpu_acceptance.test_neutral_plasma_shifted(shape)
+
+
+def test_cherenkov_instability_flow(fake):
+    test_gpu_acceptance.test_cherenkov_instability()
+
+
+@pytest.mark.parametrize('case', ['labframe_with_preexisting_plasma', 'boosted_with_preexisting_plasma',
+                                  'labframe_without_preexisting_plasma'])
+def test_continuous_injection_flow(fake, case):
+    getattr(test_gpu_acceptance, 'test_' + case)()
