@@ -153,3 +153,76 @@ def test_boosted_with_preexisting_plasma():
 def test_labframe_without_preexisting_plasma():
     dz = (CI['zmax'] - CI['zmin']) / CI['Nz']
     _run_continuous_injection(None, CI['ramp0'], CI['zmax'] + 2 * dz)
+
+
+# ------------------------------------------------------------------ test_laser.py
+L = dict(Nz=400, zmin=-10.e-6, zmax=10.e-6, Nr=25, Lr=20.e-6, w0=4.e-6, ctau=5.e-6, k0=2 * np.pi / 0.8e-6, E0=1.,
+         L_prop=30.e-6, zf=25.e-6, N_diag=10, rtol=1.e-4)
+
+
+def _propagate_pulse(m, dt, boundaries, v_window=0, use_galilean=False, v_comoving=0):
+    """test_laser.py:128-262: a laser pulse (m = 1: Gaussian, linearly polarised; m = 0: annular, polarised along
+    theta; m = 2: donut-like Laguerre-Gauss) propagates in vacuum over 30 microns towards its focus; waist and
+    amplitude, fitted on the longitudinally averaged Er of mode m, follow Gaussian-beam theory."""
+    from scipy.optimize import curve_fit
+    from fbpic_b200 import Simulation
+    from fbpic_b200.lpa_utils.laser import add_laser_pulse, GaussianLaser, LaguerreGaussLaser, \
+        DonutLikeLaguerreGaussLaser
+    u = L
+    w0, ctau, k0, E0, zf = u['w0'], u['ctau'], u['k0'], u['E0'], u['zf']
+    sim = Simulation(u['Nz'], u['zmax'], u['Nr'], u['Lr'], m + 1, dt, n_order=-1, zmin=u['zmin'],
+                     boundaries=boundaries, v_comoving=v_comoving, exchange_period=1, use_galilean=use_galilean)
+    sim.ptcl = []
+    if v_window != 0:
+        sim.set_moving_window(v=v_window)
+    z0 = (u['zmax'] + u['zmin']) / 2
+    a0, tau, lambda0 = E0 * e / (m_e * c**2 * k0), ctau / c, 2 * np.pi / k0
+    if m == 0:
+        profile = LaguerreGaussLaser(0, 1, 0.5 * a0, w0, tau, z0, zf=zf, lambda0=lambda0, theta_pol=0., theta0=0.) \
+            + LaguerreGaussLaser(0, 1, 0.5 * a0, w0, tau, z0, zf=zf, lambda0=lambda0, theta_pol=np.pi / 2,
+                                 theta0=np.pi / 2)
+    elif m == 1:
+        profile = GaussianLaser(a0=a0, waist=w0, tau=tau, lambda0=lambda0, z0=z0, zf=zf)
+    else:
+        profile = DonutLikeLaguerreGaussLaser(0, -1, a0=a0, waist=w0, tau=tau, lambda0=lambda0, z0=z0, zf=zf)
+    add_laser_pulse(sim, profile)
+
+    def fit_fields(fld):
+        dz = fld.interp[0].dz
+        prof = np.sqrt(dz * (abs(fld.interp[m].Er)**2).sum(axis=0)) * 2.**(3. / 4) / (np.pi**(1. / 4) * ctau**(1. / 2))
+        r = fld.interp[m].r
+        if m == 1:
+            f = lambda r, w, E: E * np.exp(-r**2 / w**2)                    # noqa: E731
+        else:
+            f = lambda r, w, E: E * (r / w) * np.exp(-r**2 / w**2)          # noqa: E731
+        res = curve_fit(f, r, prof, p0=np.array([w0, E0]))[0]
+        if m > 0:
+            res[1] = 2 * res[1]
+        return res
+
+    N_diag = u['N_diag']
+    w, E = np.zeros(N_diag), np.zeros(N_diag)
+    N_step = int(round(int(round(u['L_prop'] / (c * dt))) / N_diag))
+    for it in range(N_diag):
+        w[it], E[it] = fit_fields(sim.fld)
+        sim.step(N_step, show_progress=False)
+    z_prop = c * dt * N_step * np.arange(N_diag)
+    ZR = 0.5 * k0 * w0**2
+    assert np.allclose(w, w0 * np.sqrt(1 + (z_prop - zf)**2 / ZR**2), rtol=u['rtol'])
+    assert np.allclose(E, E0 / (1 + (z_prop - zf)**2 / ZR**2)**(1. / 2), rtol=5.e-3)
+
+
+@pytest.mark.parametrize('m', [0, 1, 2])
+def test_laser_periodic(m):
+    _propagate_pulse(m, L['L_prop'] * 1. / c / L['N_diag'], {'z': 'periodic', 'r': 'reflective'})
+
+
+@pytest.mark.parametrize('m', [0, 1, 2])
+def test_laser_moving_window(m):
+    _propagate_pulse(m, (L['zmax'] - L['zmin']) * 1. / c / L['Nz'], {'z': 'open', 'r': 'reflective'}, v_window=c)
+
+
+@pytest.mark.parametrize('m', [0, 1, 2])
+def test_laser_galilean(m):
+    _propagate_pulse(m, L['L_prop'] * 1. / c / L['N_diag'], {'z': 'open', 'r': 'reflective'}, use_galilean=True,
+                     v_comoving=0.999 * c)

@@ -127,3 +127,9 @@ def test_cherenkov_instability_flow(fake):
                                   'labframe_without_preexisting_plasma'])
 def test_continuous_injection_flow(fake, case):
     getattr(test_gpu_acceptance, 'test_' + case)()
+
+
+@pytest.mark.parametrize('variant', ['periodic', 'moving_window', 'galilean'])
+def test_laser_propagation_flow(fake, variant):
+    """mode 1 (Gaussian beam) of each variant; the other modes run in the GPU suite"""
+    getattr(test_gpu_acceptance, 'test_laser_' + variant)(1)
