@@ -226,3 +226,61 @@ def test_laser_moving_window(m):
 def test_laser_galilean(m):
     _propagate_pulse(m, L['L_prop'] * 1. / c / L['N_diag'], {'z': 'open', 'r': 'reflective'}, use_galilean=True,
                      v_comoving=0.999 * c)
+
+
+# ------------------------------------------------------------------ test_linear_wakefield.py
+W = dict(Nz=800, zmax=40.e-6, Nr=120, rmax=60.e-6, N_step=1500, p_zmin=39.e-6, p_zmax=41.e-6, p_rmax=55.e-6,
+         n_e=8.e24, a0=0.01, w0=20.e-6, ctau=6.e-6, z0=22.e-6)
+
+
+@pytest.mark.parametrize('Nm', [1, 2, 3])
+def test_linear_wakefield(Nm):
+    """test_linear_wakefield.py:56-160: a weak laser (a0 = 0.01; annular / Gaussian / Laguerre-Gauss for
+    Nm = 1 / 2 / 3) drives a linear wake in a plasma entering the moving window; Ez and Er behind the pulse
+    agree with the analytic linear-theory integrals to 8 % / 11 % of their maximum."""
+    from scipy.constants import epsilon_0
+    from scipy.integrate import quad
+    from fbpic_b200 import Simulation
+    from fbpic_b200.lpa_utils.laser import add_laser_pulse, GaussianLaser, LaguerreGaussLaser
+    u = W
+    a0, w0, ctau, z0 = u['a0'], u['w0'], u['ctau'], u['z0']
+    tau = ctau / c
+    dt = u['zmax'] / u['Nz'] / c
+    kp = 1. / c * np.sqrt(u['n_e'] * e**2 / (m_e * epsilon_0))
+    np.random.seed(0)
+    sim = Simulation(u['Nz'], u['zmax'], u['Nr'], u['rmax'], Nm, dt, u['p_zmin'], u['p_zmax'], 0., u['p_rmax'],
+                     2, 2, 2 * Nm, u['n_e'], boundaries={'z': 'open', 'r': 'reflective'})
+    if Nm == 1:
+        profile = LaguerreGaussLaser(0, 1, a0=a0, waist=w0, tau=tau, z0=z0, theta_pol=np.pi / 2, theta0=0.) \
+            + LaguerreGaussLaser(0, 1, a0=a0, waist=w0, tau=tau, z0=z0, theta_pol=0., theta0=-np.pi / 2)
+    elif Nm == 2:
+        profile = GaussianLaser(a0=a0, waist=w0, tau=tau, z0=z0, theta_pol=np.pi / 2)
+    else:
+        profile = LaguerreGaussLaser(0, 1, a0=a0, waist=w0, tau=tau, z0=z0, theta_pol=np.pi / 2)
+    add_laser_pulse(sim, profile)
+    sim.set_moving_window(v=c)
+    sim.step(u['N_step'], correct_currents=(sim.comm.size == 1))
+    grids = [sim.comm.gather_grid(sim.fld.interp[m]) for m in range(Nm)]
+    z, r, t = grids[0].z, grids[0].r, sim.time
+    Ez_sim = grids[0].Ez.real.copy()
+    Er_sim = grids[0].Er.real.copy()
+    for m in range(1, Nm):
+        Ez_sim += 2 * grids[m].Ez.real
+        Er_sim += 2 * grids[m].Er.real
+    # analytic solution: longitudinal integrals of the ponderomotive drive times the transverse profile of f^2
+    env = lambda xi0: np.exp(-2 * (xi0 - z0)**2 / ctau**2)          # noqa: E731
+    zw = z.max()
+    long_z = np.array([quad(lambda x0, xi: np.cos(kp * (xi - x0)) * env(x0), zi - c * t, zw - c * t,
+                            args=(zi - c * t,), limit=30)[0] for zi in z])
+    long_r = np.array([quad(lambda x0, xi: np.sin(kp * (xi - x0)) * env(x0), zi - c * t, zw - c * t,
+                            args=(zi - c * t,), limit=200)[0] for zi in z])
+    if Nm in (1, 3):
+        tz = 4 * (r / w0)**2 * np.exp(-2 * r**2 / w0**2)
+        tr = 8 * (r / w0**2) * (1 - 2 * r**2 / w0**2) * np.exp(-2 * r**2 / w0**2)
+    else:
+        tz = np.exp(-2 * r**2 / w0**2)
+        tr = -4 * r / w0**2 * np.exp(-2 * r**2 / w0**2)
+    Ez_an = m_e * c**2 * kp**2 * a0**2 / (4. * e) * tz[np.newaxis, :] * long_z[:, np.newaxis]
+    Er_an = m_e * c**2 * kp * a0**2 / (4. * e) * tr[np.newaxis, :] * long_r[:, np.newaxis]
+    assert np.allclose(Ez_sim, Ez_an, atol=0.08 * abs(Ez_an).max())
+    assert np.allclose(Er_sim, Er_an, atol=0.11 * abs(Er_an).max())
