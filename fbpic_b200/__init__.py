@@ -7,7 +7,7 @@ include/fbpic_b200.h.  There is no CPU fallback.
 """
 __version__ = '0.1.0'
 
-from .main import Simulation                      # noqa: F401
+from .main import Simulation, GpuMemoryManager    # noqa: F401
 from .particles import Particles                  # noqa: F401
 from .fields import Fields, BinomialSmoother      # noqa: F401
 from .boundaries import BoundaryCommunicator      # noqa: F401

@@ -412,6 +412,35 @@ class Simulation(object):
         self.comm.moving_win = MovingWindow(self.comm, self.dt, v, self.time)
 
 
+    def reverse_time(self):
+        """Reverse the propagation direction of waves and particles: B and the momenta change sign
+        (fbpic/main.py:1034-1053).  Acts on the host copy of the data."""
+        if self.fld.data_is_on_gpu or any(sp.data_is_on_gpu for sp in self.ptcl):
+            raise _lib.B200Error('reverse_time acts on the host copy of the data: call receive_data_from_gpu() first')
+        for m in range(self.fld.Nm):
+            for k in ('Bp', 'Bm', 'Bz'):
+                getattr(self.fld.spect[m], k)[...] *= -1
+            for k in ('Br', 'Bt', 'Bz'):
+                getattr(self.fld.interp[m], k)[...] *= -1
+        for species in self.ptcl:
+            for k in ('ux', 'uy', 'uz'):
+                setattr(species, k, -np.asarray(getattr(species, k)))
+
+
+class GpuMemoryManager(object):
+    """`with GpuMemoryManager(sim):` -- fields and particles live in HBM inside the block and come back as
+    NumPy arrays at its end (fbpic/utils/cuda.py:139-182)."""
+
+    def __init__(self, sim):
+        self.sim = sim
+
+    def __enter__(self):
+        self.sim.send_data_to_gpu()
+
+    def __exit__(self, type, value, traceback):
+        self.sim.receive_data_from_gpu()
+
+
 def adapt_to_grid(x, p_xmin, p_xmax, p_nx, ncells_empty=0):
     """Snap particle bounds to the grid and count the particles (fbpic/main.py:1056-1111)."""
     xmin, xmax = x.min(), x.max()

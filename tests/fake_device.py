@@ -17,7 +17,6 @@ import os
 import subprocess
 import numpy as np
 import scipy.fft as sfft
-from scipy.constants import c
 
 from oracle import oracle as orc
 

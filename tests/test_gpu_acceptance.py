@@ -22,13 +22,13 @@ U = dict(Nz=250, zmax=20.e-6, Nr=50, rmax=20.e-6, Nm=2, p_nr=8, p_nz=1, p_nt=4, 
 
 def _deposit_rho(sim):
     """the reference's kernel-level call pattern (test_uniform_rho_deposition.py:61-66)"""
-    sim.send_data_to_gpu()
-    sim.fld.erase('rho')
-    for species in sim.ptcl:
-        species.deposit(sim.fld, 'rho')
-    sim.fld.sum_reduce_deposition_array('rho')
-    sim.fld.divide_by_volume('rho')
-    sim.receive_data_from_gpu()
+    from fbpic_b200 import GpuMemoryManager
+    with GpuMemoryManager(sim):
+        sim.fld.erase('rho')
+        for species in sim.ptcl:
+            species.deposit(sim.fld, 'rho')
+        sim.fld.sum_reduce_deposition_array('rho')
+        sim.fld.divide_by_volume('rho')
 
 
 @pytest.mark.parametrize('shape', ['linear', 'cubic'])

@@ -2,7 +2,6 @@
 unmodified reference (oracle/gen_golden_ext.py): `add_laser_pulse` direct injection (profile sampled on the
 grid, Ez / B built in spectral space with the device transforms) and the laser antenna (virtual particles
 deposited by the regular deposition kernel every step)."""
-import numpy as np
 import pytest
 
 from conftest import load_golden, assert_close, group_scale
