@@ -34,3 +34,8 @@ def assert_close(a, b, rel, what='', scale=None):
         scale = np.abs(a).max() + np.abs(b).max()
     err = np.abs(a - b).max() if a.size else 0.
     assert err <= rel * scale + 1e-300, '%s: max err %.3e > %.1e * %.3e' % (what, err, rel, scale)
+
+
+# Test files are collected in alphabetical order and the driver runs `pytest -x`: the hardware-proven GPU tests
+# (test_gpu_kernels / multi / plasma_wave / step) therefore come first, the tests of the SURVEY 8f widening
+# (test_gpu_w1 .. w7, ordered from kernel-level goldens to whole-script and analytic acceptance runs) after them.

@@ -15,12 +15,12 @@ from conftest import ROOT
 
 import fake_device
 import test_gpu_step
-import test_gpu_widen
-import test_gpu_laser
-import test_gpu_external
-import test_gpu_bunch
-import test_gpu_scripts
-import test_gpu_acceptance
+import test_gpu_w1_pml_cross
+import test_gpu_w2_laser
+import test_gpu_w5_external
+import test_gpu_w3_bunch
+import test_gpu_w4_scripts
+import test_gpu_w6_acceptance
 
 
 @pytest.fixture
@@ -46,45 +46,45 @@ def test_moving_window_flow(fake, fused):
 @pytest.mark.parametrize('fused', [False, True])
 @pytest.mark.parametrize('tag', ['periodic', 'open', 'galilean', 'window'])
 def test_pml_flow(fake, tag, fused):
-    test_gpu_widen.test_pml_step_vs_reference_golden(tag, fused)
+    test_gpu_w1_pml_cross.test_pml_step_vs_reference_golden(tag, fused)
 
 
 @pytest.mark.parametrize('fused', [False, True])
 @pytest.mark.parametrize('tag', ['std', 'galilean'])
 def test_cross_deposition_flow(fake, tag, fused):
-    test_gpu_widen.test_cross_deposition_step_vs_reference_golden(tag, fused)
+    test_gpu_w1_pml_cross.test_cross_deposition_step_vs_reference_golden(tag, fused)
 
 
 @pytest.mark.parametrize('tag', ['gauss', 'lg_pml', 'boost'])
 def test_add_laser_direct_flow(fake, tag):
-    test_gpu_laser.test_add_laser_direct_vs_reference_golden(tag)
+    test_gpu_w2_laser.test_add_laser_direct_vs_reference_golden(tag)
 
 
 @pytest.mark.parametrize('fused', [False, True])
 @pytest.mark.parametrize('tag', ['lab', 'moving', 'boost'])
 def test_laser_antenna_flow(fake, tag, fused):
-    test_gpu_laser.test_laser_antenna_vs_reference_golden(tag, fused)
+    test_gpu_w2_laser.test_laser_antenna_vs_reference_golden(tag, fused)
 
 
 @pytest.mark.parametrize('fused', [False, True])
 @pytest.mark.parametrize('tag', ['lab', 'boost'])
 def test_external_fields_flow(fake, tag, fused):
-    test_gpu_external.test_external_fields_step_vs_reference_golden(tag, fused)
+    test_gpu_w5_external.test_external_fields_step_vs_reference_golden(tag, fused)
 
 
 def test_external_field_string_flow(fake):
-    test_gpu_external.test_external_field_string_expression()
+    test_gpu_w5_external.test_external_field_string_expression()
 
 
 @pytest.mark.parametrize('tag', ['uniform', 'gaussian', 'gaussian_boost'])
 def test_bunch_space_charge_flow(fake, tag):
-    test_gpu_bunch.test_bunch_space_charge_vs_reference_golden(tag)
+    test_gpu_w3_bunch.test_bunch_space_charge_vs_reference_golden(tag)
 
 
 @pytest.mark.parametrize('fused', [False, True])
 @pytest.mark.parametrize('tag', ['lwfa', 'boosted'])
 def test_example_script_flow(fake, tag, fused):
-    test_gpu_scripts.test_example_script_vs_reference_golden(tag, fused)
+    test_gpu_w4_scripts.test_example_script_vs_reference_golden(tag, fused)
 
 
 def test_two_rank_flow_gloo():
@@ -112,24 +112,24 @@ def test_two_rank_pml_antenna_flow_gloo(Nm):
     assert out.returncode == 0 and 'MGPU_EXTRA_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
-# ---- the reference's physics acceptance tests (restated in test_gpu_acceptance.py), host flow on the CPU
+# ---- the reference's physics acceptance tests (restated in test_gpu_w6_acceptance.py), host flow on the CPU
 @pytest.mark.parametrize('shape', ['linear', 'cubic'])
 def test_uniform_rho_flow(fake, shape):
-    test_gpu_acceptance.test_uniform_electron_plasma(shape)
-    test_gpu_acceptance.test_neutral_plasma_shifted(shape)
+    test_gpu_w6_acceptance.test_uniform_electron_plasma(shape)
+    test_gpu_w6_acceptance.test_neutral_plasma_shifted(shape)
 
 
 def test_cherenkov_instability_flow(fake):
-    test_gpu_acceptance.test_cherenkov_instability()
+    test_gpu_w6_acceptance.test_cherenkov_instability()
 
 
 @pytest.mark.parametrize('case', ['labframe_with_preexisting_plasma', 'boosted_with_preexisting_plasma',
                                   'labframe_without_preexisting_plasma'])
 def test_continuous_injection_flow(fake, case):
-    getattr(test_gpu_acceptance, 'test_' + case)()
+    getattr(test_gpu_w6_acceptance, 'test_' + case)()
 
 
 @pytest.mark.parametrize('variant', ['periodic', 'moving_window', 'galilean'])
 def test_laser_propagation_flow(fake, variant):
     """mode 1 (Gaussian beam) of each variant; the other modes run in the GPU suite"""
-    getattr(test_gpu_acceptance, 'test_laser_' + variant)(1)
+    getattr(test_gpu_w6_acceptance, 'test_laser_' + variant)(1)
