@@ -8,8 +8,8 @@ current correction + PSATD push, z guard-cell exchange and particle migration.
 Widened per SURVEY 8f: moving window with continuous injection (rank 1), laser antennas
 (rank 2), radial PML (`boundaries['r']='open'`) and the cross-deposition current correction
 (rank 4); plus mirrors, external fields and the boosted-frame conversion of the set-up
-(`gamma_boost`).  Out of scope and therefore rejected loudly: diagnostics, checkpoints,
-ionization.
+(`gamma_boost`), and the `sim.diags` / `sim.checkpoints` hooks (fbpic_b200/diags.py).  Out of scope
+and therefore rejected loudly: ionization, Compton scattering, particle tracking.
 """
 import numpy as np
 from scipy.constants import m_e, m_p, e, c
@@ -106,8 +106,6 @@ class Simulation(object):
         if self.comm.size > 1 and use_true_rho and correct_currents:
             raise ValueError('`use_true_rho` cannot be used together with `correct_currents` '
                              'in multi-proc mode.')
-        if self.diags or self.checkpoints:
-            raise NotImplementedError('diagnostics and checkpoints are outside the hot path built here')
         if self.comm.moving_win is not None:          # main.py:390-395
             for species in self.ptcl:
                 if species.continuous_injection and species.injector is not None:
@@ -116,8 +114,9 @@ class Simulation(object):
                         self.comm, self.comm.moving_win.v, z_host, self.dt)
         single = (self.comm.size == 1)
         periodic_single = single and self.comm.n_guard == 0
-        # external fields act on the gathered E, B of the particles: they need the unfused gather
-        fuse_gp = self.fused and move_positions and move_momenta and not self.external_fields
+        # external fields act on the gathered E, B of the particles and diagnostics may output them: both need
+        # the unfused gather
+        fuse_gp = self.fused and move_positions and move_momenta and not self.external_fields and not self.diags
         fuse_cp = self.fused and correct_currents and single and fld.current_correction == 'curl-free'
 
         import time as _time
@@ -163,6 +162,9 @@ class Simulation(object):
                     species.gather(fld.interp, self.comm)
                 for ext_field in self.external_fields:    # main.py:472-473
                     ext_field.apply_expression(self.ptcl, self.time)
+                # (E, B, rho, x are defined at time n ; J, p at time n-1/2: main.py:474-481)
+                for diag in self.diags:
+                    diag.write(self.iteration)
                 if move_momenta:
                     for species in ptcl:
                         species.push_p(self.time + 0.5 * dt)
@@ -230,6 +232,8 @@ class Simulation(object):
                                                      and not self.mirrors))
             self.time += dt
             self.iteration += 1
+            for checkpoint in self.checkpoints:       # main.py:563-565
+                checkpoint.write(self.iteration)
 
         fld.spect2interp('J')
         if (not fld.exchanged_source['J']) and (self.comm.size > 1):

@@ -1,0 +1,122 @@
+"""GPU tests of the diagnostics / checkpoint hooks of `Simulation.step()` (fbpic_b200/diags.py; the reference's
+openpmd_diag writes openPMD/HDF5 through h5py, which is not available here, so these are self-consistency
+tests): a field / particle diagnostic written during a step holds the data the simulation itself reports for
+that iteration, and a run restarted from a checkpoint continues like the uninterrupted one."""
+import numpy as np
+import pytest
+from scipy.constants import c
+
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+# slightly faster than one cell per step: the window position never sits a rounding error below a cell boundary,
+# so the cell count moved per step does not depend on the sub-cell offset that a restart (here as in the
+# reference, which re-creates the MovingWindow at the grid position) does not carry over
+V_WINDOW = c * (1 + 1.e-6)
+
+
+def _sim(fused, window, **kw):
+    from fbpic_b200 import Simulation
+    Nz, Nr, Nm, zmax, rmax = 32, 12, 2, 16.e-6, 8.e-6
+    np.random.seed(4)
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, zmax / Nz / c, p_zmin=2.e-6, p_zmax=40.e-6, p_rmin=0, p_rmax=6.e-6,
+                     p_nz=2, p_nr=2, p_nt=4, n_e=2.e24, n_order=-1, n_guard=12, n_damp={'z': 12, 'r': 4},
+                     boundaries={'z': 'open', 'r': 'reflective'}, fused=fused, **kw)
+    sp = sim.ptcl[0]
+    # the plasma near the right edge stays exactly at rest during the test (no signal reaches it in 7 cycles): the
+    # continuous injector, re-initialised from the particle positions after a restart, then continues the same lattice
+    inner = sp.z < 10.e-6
+    sp.uz = inner * 0.3 * np.sin(2 * np.pi * sp.z / 8.e-6) * np.exp(-(sp.x**2 + sp.y**2) / (3.e-6)**2)
+    sp.ux = inner * 0.05 * sp.x / 3.e-6 * np.cos(2 * np.pi * sp.z / 8.e-6)
+    sp.inv_gamma = 1. / np.sqrt(1 + sp.ux**2 + sp.uy**2 + sp.uz**2)
+    if window:
+        sim.set_moving_window(v=V_WINDOW)
+    return sim
+
+
+def _modes(d, Nm):
+    """openPMD thetaMode dataset [2 Nm - 1, Nr, Nz] -> list of complex [Nz, Nr] arrays"""
+    return [d[0].T + 0.j] + [0.5 * (d[2 * m - 1] + 1.j * d[2 * m]).T for m in range(1, Nm)]
+
+
+@pytest.mark.parametrize('fused', [False, True])
+def test_diagnostics_hold_the_state_of_their_iteration(fused, tmp_path):
+    from fbpic_b200.diags import FieldDiagnostic, ParticleDiagnostic
+    sim = _sim(fused, window=True)
+    sp = sim.ptcl[0]
+    sim.diags = [FieldDiagnostic(period=5, fldobject=sim.fld, comm=sim.comm, write_dir=str(tmp_path)),
+                 ParticleDiagnostic(period=5, species={'electrons': sp}, comm=sim.comm, select={'uz': [0.05, None]},
+                                    particle_data=['position', 'momentum', 'weighting', 'gamma'],
+                                    write_dir=str(tmp_path))]
+    sim.step(5)                                   # writes iteration 0; the state now is that of iteration 5
+    ref = {k: [sim.comm.gather_grid_array(getattr(sim.fld.interp[m], k)) for m in range(2)]
+           for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'rho')}
+    part = {k: np.array(getattr(sp, k)) for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'w', 'inv_gamma')}
+    zmin_phys, _ = sim.comm.get_zmin_zmax(local=False, with_damp=False, with_guard=False)
+    sim.step(1)                                   # iteration 5 is due at the start of this cycle
+    f = np.load(str(tmp_path / 'npz' / 'fields00000005.npz'))
+    assert int(f['meta/iteration']) == 5 and abs(float(f['meta/zmin']) - zmin_phys) < 1e-12
+    assert f['fields/E/r'].shape == (3, 12, 32)
+    for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz'):
+        got = _modes(f['fields/%s/%s' % (k[0], k[1])], 2)
+        scale = max(np.abs(ref[k[0] + c_][m]).max() for c_ in 'rtz' for m in range(2)) + 1e-300
+        for m in range(2):
+            assert_close(got[m], ref[k][m] if m else ref[k][m].real, 1e-13, 'diag %s m%d' % (k, m), scale=scale)
+    got = _modes(f['fields/rho'], 2)
+    scale = max(np.abs(ref['rho'][m]).max() for m in range(2))
+    for m in range(2):          # re-deposited after a re-sort: summation order differs
+        assert_close(got[m], ref['rho'][m] if m else ref['rho'][m].real, 1e-11, 'diag rho m%d' % m, scale=scale)
+    assert np.all(np.isfinite(f['fields/J/z']))
+    p = np.load(str(tmp_path / 'npz' / 'particles00000005.npz'))
+    sel = part['uz'] > 0.05
+    assert sel.sum() > 0 and len(p['particles/electrons/position/x']) == sel.sum()
+    order_ref = np.lexsort((part['z'][sel], part['x'][sel]))
+    order_got = np.lexsort((p['particles/electrons/position/z'], p['particles/electrons/position/x']))
+    for key, k in (('position/x', 'x'), ('position/z', 'z'), ('momentum/z', 'uz'), ('weighting', 'w')):
+        assert_close(p['particles/electrons/' + key][order_got], part[k][sel][order_ref], 1e-14, 'diag ' + k)
+    assert_close(p['particles/electrons/gamma'][order_got], 1. / part['inv_gamma'][sel][order_ref], 1e-14, 'gamma')
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('window', [False, True])
+def test_restart_from_checkpoint_continues_the_run(fused, window, tmp_path):
+    from fbpic_b200.diags import set_periodic_checkpoint, restart_from_checkpoint
+    a = _sim(fused, window)
+    set_periodic_checkpoint(a, 4, checkpoint_dir=str(tmp_path))
+    a.step(4)                                     # checkpoint of iteration 4
+    np.random.seed(77)                            # the azimuths of the injected plasma are drawn from np.random
+    a.step(3)
+    np.random.seed(9)
+    b = _sim(fused, False)
+    restart_from_checkpoint(b, checkpoint_dir=str(tmp_path))
+    assert b.iteration == 4 and abs(b.time - 4 * b.dt) < 1e-20
+    if window:      # as in the reference's lwfa_script.py: restart first, then attach the moving window
+        b.set_moving_window(v=V_WINDOW)
+    np.random.seed(77)
+    b.step(3)
+    assert b.iteration == a.iteration and abs(b.fld.interp[0].zmin - a.fld.interp[0].zmin) < 1e-12
+    sa, sb = a.ptcl[0], b.ptcl[0]
+    assert sa.Ntot == sb.Ntot
+    # With the moving window the restarted run re-initialises the continuous injector (as the reference does), so
+    # the plasma slices can enter in different batches and draw different azimuths from np.random: the axisymmetric
+    # quantities (r, z, momenta along z, weights; mode-0 fields) are the ones a restart must reproduce.
+    pa = dict(r=np.hypot(sa.x, sa.y), z=np.array(sa.z), uz=np.array(sa.uz), w=np.array(sa.w))
+    pb = dict(r=np.hypot(sb.x, sb.y), z=np.array(sb.z), uz=np.array(sb.uz), w=np.array(sb.w))
+    # several particles share one (z, r) (different azimuths): sort on coordinates rounded far above the rounding
+    # noise and far below the lattice spacing, then on uz
+    order = lambda p: np.lexsort((p['uz'], np.round(p['r'] / 1.e-13), np.round(p['z'] / 1.e-13)))      # noqa: E731
+    oa, ob = order(pa), order(pb)
+    for k in pa:
+        assert_close(pb[k][ob], pa[k][oa], 1e-10, 'restart ' + k)
+    if not window:
+        oa, ob = np.lexsort((sa.z, sa.y, sa.x, sa.w)), np.lexsort((sb.z, sb.y, sb.x, sb.w))
+        for k in ('x', 'y', 'ux', 'uy'):
+            assert_close(np.array(getattr(sb, k))[ob], np.array(getattr(sa, k))[oa], 1e-10, 'restart ' + k)
+    for m in range(1 if window else 2):
+        for grp in ('E', 'B'):
+            scale = max(np.abs(getattr(a.fld.interp[mm], grp + c_)).max() for c_ in 'rtz' for mm in range(2))
+            for c_ in 'rtz':
+                assert_close(getattr(b.fld.interp[m], grp + c_), getattr(a.fld.interp[m], grp + c_), 1e-9,
+                             'restart %s%s m%d' % (grp, c_, m), scale=scale)

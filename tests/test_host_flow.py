@@ -21,6 +21,7 @@ import test_gpu_w5_external
 import test_gpu_w3_bunch
 import test_gpu_w4_scripts
 import test_gpu_w6_acceptance
+import test_gpu_w8_diags
 
 
 @pytest.fixture
@@ -133,3 +134,14 @@ def test_continuous_injection_flow(fake, case):
 def test_laser_propagation_flow(fake, variant):
     """mode 1 (Gaussian beam) of each variant; the other modes run in the GPU suite"""
     getattr(test_gpu_w6_acceptance, 'test_laser_' + variant)(1)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+def test_diagnostics_flow(fake, fused, tmp_path):
+    test_gpu_w8_diags.test_diagnostics_hold_the_state_of_their_iteration(fused, tmp_path)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('window', [False, True])
+def test_restart_flow(fake, fused, window, tmp_path):
+    test_gpu_w8_diags.test_restart_from_checkpoint_continues_the_run(fused, window, tmp_path)
