@@ -1,0 +1,142 @@
+"""GPU tests of the C-ABI entry points of b2_ext.cu one by one (radial PML push / damping, cross-deposition
+correction, antenna helpers, NVRTC external field), on random data against the NumPy statements of the reference
+formulas -- the device-side twin of tests/test_hostemu_ext.py (same formulas, same shapes: non-multiples of the
+block size, k = 0 lines).  Runs before the whole-step tests of the widening so that a failure is localised."""
+import ctypes
+import numpy as np
+import pytest
+from scipy.constants import c
+
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _cplx(rng, shape):
+    return (rng.normal(size=shape) + 1.j * rng.normal(size=shape)).astype(np.complex128)
+
+
+def _dev(*arrays):
+    from fbpic_b200._lib import DeviceArray
+    return [DeviceArray.from_numpy(a) for a in arrays]
+
+
+@pytest.mark.parametrize('comoving', [False, True])
+@pytest.mark.parametrize('shape', [(5, 7), (9, 130), (257, 64)])
+def test_push_eb_pml(comoving, shape):
+    from fbpic_b200 import _lib
+    rng = np.random.default_rng(3)
+    Nz, Nr = shape
+    Ep, Em, Bp, Bm, Ez, Bz = [_cplx(rng, shape) for _ in range(6)]
+    C, S_w = rng.normal(size=shape), rng.normal(size=shape) * 1e-9
+    T = _cplx(rng, shape)
+    kr = rng.normal(size=Nr) * 1e5
+    Tn = T if comoving else 1.
+    ref = [Tn * C * Ep + c**2 * Tn * S_w * (-1.j * 0.5 * kr[None, :] * Bz),        # numba_methods.py:189-214, 358-383
+           Tn * C * Em + c**2 * Tn * S_w * (-1.j * 0.5 * kr[None, :] * Bz),
+           Tn * C * Bp - Tn * S_w * (-1.j * 0.5 * kr[None, :] * Ez),
+           Tn * C * Bm - Tn * S_w * (-1.j * 0.5 * kr[None, :] * Ez)]
+    d = _dev(Ep, Em, Bp, Bm, Ez, Bz, C, S_w, T, kr)
+    _lib.call.b2_push_eb_pml(_lib.context().handle, d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, d[4].ptr, d[5].ptr,
+                             d[6].ptr, d[7].ptr, d[8].ptr if comoving else None, d[9].ptr, Nz, Nr, None)
+    for got, want, name in zip(d[:4], ref, ('Ep_pml', 'Em_pml', 'Bp_pml', 'Bm_pml')):
+        assert_close(got.get(), want, 1e-14, name)
+    assert np.array_equal(d[4].get(), Ez) and np.array_equal(d[5].get(), Bz)
+
+
+@pytest.mark.parametrize('shape,n_pml', [((6, 9), 4), ((33, 70), 33), ((3, 5), 5), ((300, 96), 32)])
+def test_damp_pml(shape, n_pml):
+    from fbpic_b200 import _lib
+    rng = np.random.default_rng(4)
+    Nz, Nr = shape
+    arrs = [_cplx(rng, shape) for _ in range(6)]
+    damp = np.exp(-4. * 0.7 * (np.arange(n_pml) / n_pml)**2)
+    wEt, wEtp, wEz, wBt, wBtp, wBz = [a.copy() for a in arrs]
+    dd = damp[None, :]                               # pml_damping.py:66-83
+    wEt[:, -n_pml:] -= wEtp[:, -n_pml:]
+    wBt[:, -n_pml:] -= wBtp[:, -n_pml:]
+    wEtp[:, -n_pml:] *= dd
+    wBtp[:, -n_pml:] *= dd
+    wEt[:, -n_pml:] += wEtp[:, -n_pml:]
+    wBt[:, -n_pml:] += wBtp[:, -n_pml:]
+    wBz[:, -n_pml:] *= dd
+    wEz[:, -n_pml:] *= dd
+    d = _dev(*arrs, damp)
+    _lib.call.b2_damp_pml(_lib.context().handle, *[a.ptr for a in d[:6]], d[6].ptr, n_pml, Nz, Nr, None)
+    for got, w, name in zip(d[:6], (wEt, wEtp, wEz, wBt, wBtp, wBz), ('Et', 'Et_pml', 'Ez', 'Bt', 'Bt_pml', 'Bz')):
+        assert_close(got.get(), w, 1e-15, name)
+
+
+@pytest.mark.parametrize('comoving', [False, True])
+def test_correct_currents_cross(comoving):
+    from fbpic_b200 import _lib
+    from fbpic_b200._lib import SpectralMode
+    rng = np.random.default_rng(5)
+    Nz, Nr = 10, 67
+    rp, rn, rz, rxy, Jp, Jm, Jz = [_cplx(rng, (Nz, Nr)) for _ in range(7)]
+    kz1, kr1 = rng.normal(size=Nz) * 1e5, np.abs(rng.normal(size=Nr)) * 1e5
+    kz1[0] = 0.
+    kr1[3] = 0.
+    Tcc, jcc, Teb = [_cplx(rng, (Nz, Nr)) for _ in range(3)]
+    inv_dt = 3.e14
+    kz, kr = np.broadcast_to(kz1[:, None], (Nz, Nr)), np.broadcast_to(kr1[None, :], (Nz, Nr))
+    if comoving:      # numba_methods.py:243-275
+        Dz = 1.j * kz * Jz + 0.5 * Tcc * jcc * (rn - Teb * rxy + rz - Teb * rp)
+        Dxy = kr * (Jp - Jm) + 0.5 * Tcc * jcc * (rn + Teb * rxy - rz - Teb * rp)
+    else:             # numba_methods.py:88-116
+        Dz = 1.j * kz * Jz + 0.5 * inv_dt * (rn - rxy + rz - rp)
+        Dxy = kr * (Jp - Jm) + 0.5 * inv_dt * (rn - rz + rxy - rp)
+    wJp, wJm, wJz = Jp.copy(), Jm.copy(), Jz.copy()
+    nzr, nzz = kr != 0, kz != 0
+    wJp[nzr] += -0.5 * Dxy[nzr] / kr[nzr]
+    wJm[nzr] += 0.5 * Dxy[nzr] / kr[nzr]
+    wJz[nzz] += 1.j * Dz[nzz] / kz[nzz]
+    d = dict(zip(('rho_prev', 'rho_next', 'rz', 'rxy', 'Jp', 'Jm', 'Jz', 'kz', 'kr', 'T_cc', 'j_corr_coef', 'T_eb'),
+                 _dev(rp, rn, rz, rxy, Jp, Jm, Jz, kz1, kr1, Tcc, jcc, Teb)))
+    s = SpectralMode()
+    for k in ('rho_prev', 'rho_next', 'Jp', 'Jm', 'Jz', 'kz', 'kr', 'T_cc', 'j_corr_coef', 'T_eb'):
+        setattr(s, k, d[k].ptr)
+    _lib.call.b2_correct_currents_cross(_lib.context().handle, ctypes.byref(s), d['rz'].ptr, d['rxy'].ptr,
+                                        int(comoving), inv_dt, Nz, Nr, None)
+    for k, w in (('Jp', wJp), ('Jm', wJm), ('Jz', wJz)):
+        assert_close(d[k].get(), w, 1e-14, k)
+    assert np.array_equal(d['Jz'].get()[0], wJz[0]) and np.array_equal(d['Jp'].get()[:, 3], wJp[:, 3])
+
+
+def test_antenna_helpers():
+    from fbpic_b200 import _lib
+    from fbpic_b200._lib import DeviceArray
+    rng = np.random.default_rng(6)
+    n = 700
+    host = [rng.normal(size=n) for _ in range(7)]
+    bx, by, ex, ey, vx, vy, vz = host
+    d = _dev(*host)
+    out = [DeviceArray(n, np.float64) for _ in range(5)]
+    for sign in (1., -1.):
+        _lib.call.b2_antenna_particles(_lib.context().handle, n, *[a.ptr for a in d], sign, *[a.ptr for a in out], None)
+        x, y, ux, uy, uz = [a.get() for a in out]
+        assert np.array_equal(x, bx + sign * ex) and np.array_equal(y, by + sign * ey)     # antenna_injection.py:360-361
+        assert_close(ux, sign * vx / c, 1e-15, 'ux')
+        assert_close(uy, sign * vy / c, 1e-15, 'uy')
+        assert_close(uz, vz / c, 1e-15, 'uz')
+    _lib.call.b2_axpy(_lib.context().handle, n, 0.37, d[4].ptr, d[1].ptr, None)
+    assert np.array_equal(d[1].get(), by + 0.37 * vx)
+
+
+def test_external_field_jit():
+    """NVRTC -> cubin -> cudaLibraryLoadData -> launch, lab frame and boosted (z, t) arguments."""
+    from fbpic_b200 import _lib
+    rng = np.random.default_rng(7)
+    n = 1000
+    F, x, y, z = rng.normal(size=n), rng.normal(size=n) * 1e-6, rng.normal(size=n) * 1e-6, rng.uniform(0, 2e-5, n)
+    h = ctypes.c_void_p()
+    _lib.call.b2_external_field_compile(b'    F_[i_] = F + amplitude * cos(z / length_scale) * x - t * 1.e9 * y;',
+                                        ctypes.byref(h))
+    for g, b in ((1., 0.), (3., np.sqrt(1 - 1 / 9.))):
+        d = _dev(F, x, y, z)
+        t, amp, L = 5.e-15, 2.5, 3.e-6
+        _lib.call.b2_external_field_apply(_lib.context().handle, h, n, d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, t, amp, L,
+                                          g, b, None)
+        zl, tl = g * (z + b * c * t), g * (t + b * (1. / c) * z)
+        assert_close(d[0].get(), F + amp * np.cos(zl / L) * x - tl * 1.e9 * y, 1e-14, 'external field g=%g' % g)
+    _lib.call.b2_external_field_free(h)

@@ -15,6 +15,7 @@ from conftest import ROOT
 
 import fake_device
 import test_gpu_step
+import test_gpu_w0_ext_kernels
 import test_gpu_w1_pml_cross
 import test_gpu_w2_laser
 import test_gpu_w5_external
@@ -145,3 +146,14 @@ def test_diagnostics_flow(fake, fused, tmp_path):
 @pytest.mark.parametrize('window', [False, True])
 def test_restart_flow(fake, fused, window, tmp_path):
     test_gpu_w8_diags.test_restart_from_checkpoint_continues_the_run(fused, window, tmp_path)
+
+
+def test_ext_kernel_tests_flow(fake):
+    """the device-side kernel tests of b2_ext.cu, run here against the host-compiled kernel source"""
+    k = test_gpu_w0_ext_kernels
+    for comoving in (False, True):
+        k.test_push_eb_pml(comoving, (9, 130))
+        k.test_correct_currents_cross(comoving)
+    k.test_damp_pml((33, 70), 33)
+    k.test_antenna_helpers()
+    k.test_external_field_jit()
