@@ -279,6 +279,10 @@ def pinned_empty(shape, dtype):
     return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
+# bytes moved by DeviceArray.set / .get since import (bench.py reports the per-call deltas)
+TRANSFERRED = {'h2d': 0, 'd2h': 0}
+
+
 class DeviceArray(object):
     """A C-contiguous array in HBM (or a view into one).  Mirrors the little of the
     cupy.ndarray interface that the reference's operator surface relies on:
@@ -342,6 +346,7 @@ class DeviceArray(object):
         ctx = context()
         call.b2_memcpy_h2d(self.ptr, a.ctypes.data, self.nbytes, ctx.stream)
         call.b2_stream_sync(ctx.stream)
+        TRANSFERRED['h2d'] += self.nbytes
 
     def get(self, pinned=False):
         out = pinned_empty(self.shape, self.dtype) if (pinned and self.nbytes >= (1 << 16)) \
@@ -349,6 +354,7 @@ class DeviceArray(object):
         ctx = context()
         call.b2_memcpy_d2h(out.ctypes.data, self.ptr, self.nbytes, ctx.stream)
         call.b2_stream_sync(ctx.stream)
+        TRANSFERRED['d2h'] += self.nbytes
         return out
 
     def fill(self, value):

@@ -119,7 +119,13 @@ class Simulation(object):
         fuse_gp = self.fused and move_positions and move_momenta and not self.external_fields and not self.diags
         fuse_cp = self.fused and correct_currents and single and fld.current_correction == 'curl-free'
 
+        for species in ptcl:
+            if not species.data_is_on_gpu:
+                species.fields_resident_only = bool(fuse_gp)
+            elif not fuse_gp:
+                species.fields_resident_only = False      # an unfused gather will write them: read them back
         import time as _time
+        bytes0 = dict(_lib.TRANSFERRED)
         t_start = _time.perf_counter()
         self.send_data_to_gpu()
         t_sent = _time.perf_counter()
@@ -248,6 +254,8 @@ class Simulation(object):
         # wall-clock split of this call: host->device copy, the N cycles (device-synchronised), device->host copy
         self.last_step_timing = dict(h2d_s=t_sent - t_start, cycles_s=t_done - t_sent,
                                      d2h_s=_time.perf_counter() - t_done)
+        # bytes copied host->device / device->host by this call (counted from the arrays actually copied)
+        self.last_step_bytes = {k: _lib.TRANSFERRED[k] - bytes0[k] for k in bytes0}
 
     def deposit(self, fieldtype, exchange=False, update_spectral=True, species_list=None, push=None):
         """fbpic/main.py:588-670"""

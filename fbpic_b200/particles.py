@@ -174,6 +174,10 @@ class Particles(object):
         self.sorting_buffers = None
         self.prefix_sum_shift = 0
         self.sorted = False
+        # set by Simulation.step() when the fused gather+push is used: Ex..Bz are then neither uploaded nor
+        # read back (they are never written on the device), which removes 6 of the 14 per-particle arrays from
+        # the host<->device copies of a step() call
+        self.fields_resident_only = False
 
     # ------------------------------------------------------------------ device residency
     HEADROOM = 1.08     # per-particle device arrays are allocated with room for migration
@@ -204,7 +208,10 @@ class Particles(object):
         self._capacity = self._capacity_for(self.Ntot)
         for k in FLOAT_ATTRS + FIELD_ATTRS:
             d = DeviceArray(self._capacity, np.float64).view((self.Ntot,))
-            d.set(np.asarray(getattr(self, k), dtype=np.float64))
+            if k in FIELD_ATTRS and self.fields_resident_only:
+                d.fill(0)       # gathered fields never leave the device in this mode: nothing to upload
+            else:
+                d.set(np.asarray(getattr(self, k), dtype=np.float64))
             setattr(self, k, d)
         self._alloc_sort_arrays()
         self.sorted = False
@@ -214,8 +221,12 @@ class Particles(object):
         """particles.py:293-333"""
         if not self.data_is_on_gpu:
             return
-        for k in FLOAT_ATTRS + FIELD_ATTRS:
+        for k in FLOAT_ATTRS:
             setattr(self, k, _lib.to_host(getattr(self, k)))
+        for k in FIELD_ATTRS:
+            # fused gather+push keeps the gathered fields in registers: the device arrays still hold the zeros
+            # they were created with, so the host gets zeros without a copy
+            setattr(self, k, np.zeros(self.Ntot) if self.fields_resident_only else _lib.to_host(getattr(self, k)))
         self.data_is_on_gpu = False
 
     def resize_device_arrays(self, new_arrays, n_new):

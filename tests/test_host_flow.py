@@ -157,3 +157,27 @@ def test_ext_kernel_tests_flow(fake):
     k.test_damp_pml((33, 70), 33)
     k.test_antenna_helpers()
     k.test_external_field_jit()
+
+
+@pytest.mark.parametrize('fused', [False, True])
+def test_transfer_accounting(fake, fused):
+    """Bytes copied by a step() call: the fused step neither uploads nor reads back the 6 gathered-field arrays
+    of the particles (they stay in registers); the unfused one moves them and returns the gathered fields."""
+    import numpy as np
+    from scipy.constants import c
+    from fbpic_b200 import Simulation
+    np.random.seed(0)
+    zmax, rmax = 16.e-6, 8.e-6
+    sim = Simulation(32, zmax, 12, rmax, 2, zmax / 32 / c, p_zmin=0, p_zmax=zmax, p_rmin=0, p_rmax=rmax,
+                     p_nz=2, p_nr=2, p_nt=4, n_e=1.e24, fused=fused)
+    sp = sim.ptcl[0]
+    sp.uz = 0.1 * np.sin(2 * np.pi * sp.z / zmax)
+    sp.inv_gamma = 1. / np.sqrt(1 + sp.uz**2)
+    sim.step(2)
+    grids = sum(getattr(g, k).nbytes for g in sim.fld.interp for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'Jr', 'Jt', 'Jz', 'rho')) \
+        + sum(getattr(g, k).nbytes for g in sim.fld.spect for k in ('Ep', 'Em', 'Ez', 'Bp', 'Bm', 'Bz', 'Jp', 'Jm', 'Jz', 'rho_prev', 'rho_next'))
+    n_arrays = 8 if fused else 14
+    assert sim.last_step_bytes['d2h'] == n_arrays * 8 * sp.Ntot + grids
+    assert sim.last_step_bytes['h2d'] >= n_arrays * 8 * sp.Ntot + grids            # + the one-off table uploads
+    assert sim.last_step_bytes['h2d'] < (n_arrays + 1) * 8 * sp.Ntot + 4 * grids
+    assert len(sp.Ez) == sp.Ntot and (np.any(sp.Ez != 0) != fused)
