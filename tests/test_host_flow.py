@@ -181,3 +181,13 @@ def test_transfer_accounting(fake, fused):
     assert sim.last_step_bytes['h2d'] >= n_arrays * 8 * sp.Ntot + grids            # + the one-off table uploads
     assert sim.last_step_bytes['h2d'] < (n_arrays + 1) * 8 * sp.Ntot + 4 * grids
     assert len(sp.Ez) == sp.Ntot and (np.any(sp.Ez != 0) != fused)
+
+
+def test_two_rank_diagnostics_flow_gloo():
+    """Diagnostics of a 2-rank run (gathered over the ranks) equal those of the single-domain run."""
+    env = dict(os.environ, OMP_NUM_THREADS='2', ORACLE_NUM_THREADS='2', MGPU_NZ_PER_RANK='64', MGPU_EXTRA='2')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', '29659',
+           os.path.join(ROOT, 'tests', 'workers', 'mgpu_parity_worker.py'), '--fake-device']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0 and 'MGPU_DIAG_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -264,8 +264,67 @@ def run_pml_antenna_case(tol):
     return bool(int(flag[0]))
 
 
+def run_diag_case(tol):
+    """Field / particle diagnostics of a sharded run (gathered over the ranks, written by rank 0) against those of
+    the single-domain run: same files (fbpic_b200/diags.py; gathering rules of field_diag.py:192-212)."""
+    import tempfile
+    from fbpic_b200.diags import FieldDiagnostic, ParticleDiagnostic
+    rank, size = dist.get_rank(), dist.get_world_size()
+    nzr = int(os.environ.get('MGPU_NZ_PER_RANK', '96'))
+    Nz, Nr, Nm, zmax, rmax, n_e, n_order = nzr * size, 16, 2, 0.2e-6 * nzr * size, 8.e-6, 2.e24, 8
+    dt = zmax / Nz / c
+    P = global_particles(Nz, Nr, zmax, rmax, n_e)
+    kw = dict(n_order=n_order, boundaries={'z': 'periodic', 'r': 'reflective'})
+    dirs = [tempfile.mkdtemp() if rank == 0 else None, tempfile.mkdtemp() if rank == 0 else None]
+    dist.broadcast_object_list(dirs, src=0)
+
+    def run(sim, zlo, zhi, d):
+        sp = set_species(sim, P, zlo, zhi)
+        sim.diags = [FieldDiagnostic(period=3, fldobject=sim.fld, comm=sim.comm, fieldtypes=['E', 'B', 'rho'], write_dir=d),
+                     ParticleDiagnostic(period=3, species={'e': sp}, comm=sim.comm, select={'uz': [0.05, None]},
+                                        write_dir=d)]
+        sim.step(5, correct_currents=False)
+
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, **kw)
+    zlo, zhi = sim.comm.get_zmin_zmax(local=True, with_damp=False, with_guard=False, rank=rank)
+    run(sim, zlo, zhi, dirs[0])
+    ok = True
+    if rank == 0:
+        ref = Simulation(Nz, zmax, Nr, rmax, Nm, dt, use_all_mpi_ranks=False, n_guard=sim.comm.n_guard, **kw)
+        run(ref, -1., 1.e9, dirs[1])
+        for it in (0, 3):
+            a = np.load(os.path.join(dirs[0], 'npz', 'fields%08d.npz' % it))
+            b = np.load(os.path.join(dirs[1], 'npz', 'fields%08d.npz' % it))
+            for grp in ('E', 'B'):
+                scale = max(np.abs(b['fields/%s/%s' % (grp, k)]).max() for k in 'rtz') + 1e-300
+                for k in 'rtz':
+                    key = 'fields/%s/%s' % (grp, k)
+                    if a[key].shape != b[key].shape or not np.abs(a[key] - b[key]).max() <= tol * scale:
+                        ok = False
+                        print('DIAG MISMATCH', it, key, a[key].shape, b[key].shape)
+            if not np.abs(a['fields/rho'] - b['fields/rho']).max() <= tol * np.abs(b['fields/rho']).max():
+                ok = False
+                print('DIAG MISMATCH rho', it)
+            pa = np.load(os.path.join(dirs[0], 'npz', 'particles%08d.npz' % it))
+            pb = np.load(os.path.join(dirs[1], 'npz', 'particles%08d.npz' % it))
+            za, zb = np.sort(pa['particles/e/position/z']), np.sort(pb['particles/e/position/z'])
+            if za.shape != zb.shape or (len(za) and np.abs(za - zb).max() > 1e-9 * zmax):
+                ok = False
+                print('DIAG MISMATCH particles', it, za.shape, zb.shape)
+        print('diag: selected particles at iteration 3:', len(za))
+    flag = torch.tensor([1 if ok else 0])
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    return bool(int(flag[0]))
+
+
 def main():
     dist.init_process_group('gloo')
+    if os.environ.get('MGPU_EXTRA') == '2':
+        ok = run_diag_case(1e-9)
+        if dist.get_rank() == 0 and ok:
+            print('MGPU_DIAG_OK size=%d' % dist.get_world_size())
+        sys.exit(0 if ok else 1)
     if os.environ.get('MGPU_EXTRA') == '1':
         ok = run_pml_antenna_case(1e-8)
         if dist.get_rank() == 0 and ok:
