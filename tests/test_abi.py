@@ -84,3 +84,35 @@ def test_ctypes_argument_counts_match_header():
             else:
                 ok = t is ctypes.c_int
             assert ok, '%s: argument %d (%s) is bound as %s' % (name, i, p, t.__name__)
+
+
+def test_product_never_reaches_the_checkers():
+    """The oracle (oracle/), the fake device and the kernel-source emulation (tests/) are test infrastructure:
+    no module of the product imports or loads them, and bench.py touches the oracle only in its cpu_baseline /
+    --impl reference legs."""
+    import ast
+    pkg = os.path.join(ROOT, 'fbpic_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith('.py'):
+                continue
+            tree = ast.parse(open(os.path.join(dirpath, f)).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom) and node.level == 0:
+                    names = [node.module or '']
+                for n in names:
+                    top = n.split('.')[0]
+                    assert top not in ('oracle', 'tests', 'fake_device', 'conftest'), (f, n)
+            src = open(os.path.join(dirpath, f)).read()
+            assert 'liboracle' not in src and 'libemu_ext' not in src, f
+    bench = open(os.path.join(ROOT, 'bench.py')).read()
+    uses = [m.start() for m in re.finditer(r'from oracle import|import oracle', bench)]
+    assert uses, 'bench.py is expected to time the oracle as the CPU baseline'
+    for pos in uses:
+        ctx = bench[max(0, pos - 1500):pos]
+        assert ('def time_oracle' in ctx) or ('def build_oracle_sim' in ctx) or ("args.impl == 'reference'" in ctx) \
+            or ('cpu_baseline = None' in ctx), \
+            'bench.py imports the oracle outside the cpu_baseline / reference legs'
