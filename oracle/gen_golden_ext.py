@@ -262,7 +262,33 @@ def gen_script(tag):
     save('script_' + tag, **out)
 
 
+def gen_tables_variants():
+    """Host tables for the non-default options: smoother passes / compensator, Ruyten shapes and modified
+    volumes switched off (smoothing.py:57-94, interpolation_grid.py:88-138)."""
+    from fbpic.fields.smoothing import BinomialSmoother
+    Nr, Nz, rmax, dz = 12, 16, 15.e-6, 0.4e-6
+    dt = dz / c
+    out = dict(Nr=Nr, Nz=Nz, rmax=rmax, dz=dz, dt=dt)
+    cases = {'p2': dict(n_passes=2, compensator=False), 'p1c': dict(n_passes=1, compensator=True),
+             'mixed': dict(n_passes={'z': 3, 'r': 1}, compensator={'z': True, 'r': False})}
+    for tag, kw in cases.items():
+        sim = Simulation(Nz, Nz * dz, Nr, rmax, 2, dt, zmin=0., smoother=BinomialSmoother(**kw), verbose_level=0)
+        for m in range(2):
+            out['%s_fz_m%d' % (tag, m)] = sim.fld.spect[m].filter_array_z
+            out['%s_fr_m%d' % (tag, m)] = sim.fld.spect[m].filter_array_r
+    for tag, kw in {'noruyten': dict(use_ruyten_shapes=False), 'novol': dict(use_modified_volume=False),
+                    'neither': dict(use_ruyten_shapes=False, use_modified_volume=False)}.items():
+        sim = Simulation(Nz, Nz * dz, Nr, rmax, 3, dt, zmin=0., verbose_level=0, **kw)
+        for m in range(3):
+            g = sim.fld.interp[m]
+            out['%s_invvol_m%d' % (tag, m)] = g.invvol
+            out['%s_lin_m%d' % (tag, m)] = g.ruyten_linear_coef
+            out['%s_cub_m%d' % (tag, m)] = g.ruyten_cubic_coef
+    save('tables_variants', **out)
+
+
 GENERATORS = {
+    'tables_variants': gen_tables_variants,
     'script_lwfa': lambda: gen_script('lwfa'),
     'script_boosted': lambda: gen_script('boosted'),
     'bunch_uniform': lambda: gen_bunch('uniform'),

@@ -66,3 +66,26 @@ def test_boost_converter():
     T = b.interaction_time(1.e-3, 50.e-6, c)
     Li, lw, vw = 1.e-3 / 10., 50.e-6 / (10. * (1 - b.beta0)), c
     assert abs(T - (Li + lw) / (vw + b.beta0 * c)) < 1e-12 * T
+
+
+def test_host_tables_option_variants_bit_exact():
+    """Smoother passes / compensator, use_ruyten_shapes=False, use_modified_volume=False: the host tables of
+    `Simulation` equal the reference's bit for bit (smoothing.py:57-94, interpolation_grid.py:88-138)."""
+    from fbpic_b200 import Simulation, BinomialSmoother
+    g = load_golden('tables_variants')
+    Nr, Nz, rmax, dz, dt = int(g['Nr']), int(g['Nz']), float(g['rmax']), float(g['dz']), float(g['dt'])
+    cases = {'p2': dict(n_passes=2, compensator=False), 'p1c': dict(n_passes=1, compensator=True),
+             'mixed': dict(n_passes={'z': 3, 'r': 1}, compensator={'z': True, 'r': False})}
+    for tag, kw in cases.items():
+        sim = Simulation(Nz, Nz * dz, Nr, rmax, 2, dt, zmin=0., smoother=BinomialSmoother(**kw))
+        for m in range(2):
+            assert np.array_equal(sim.fld.spect[m].filter_array_z, g['%s_fz_m%d' % (tag, m)]), (tag, m)
+            assert np.array_equal(sim.fld.spect[m].filter_array_r, g['%s_fr_m%d' % (tag, m)]), (tag, m)
+    for tag, kw in {'noruyten': dict(use_ruyten_shapes=False), 'novol': dict(use_modified_volume=False),
+                    'neither': dict(use_ruyten_shapes=False, use_modified_volume=False)}.items():
+        sim = Simulation(Nz, Nz * dz, Nr, rmax, 3, dt, zmin=0., **kw)
+        for m in range(3):
+            gr = sim.fld.interp[m]
+            assert np.array_equal(gr.invvol, g['%s_invvol_m%d' % (tag, m)]), (tag, m)
+            assert np.array_equal(gr.ruyten_linear_coef, g['%s_lin_m%d' % (tag, m)]), (tag, m)
+            assert np.array_equal(gr.ruyten_cubic_coef, g['%s_cub_m%d' % (tag, m)]), (tag, m)
