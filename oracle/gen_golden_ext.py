@@ -287,6 +287,51 @@ def gen_tables_variants():
     save('tables_variants', **out)
 
 
+STEP_OPTIONS = {
+    'true_rho': dict(step=dict(use_true_rho=True), sim=dict(initialize_ions=True)),
+    'true_rho_galilean': dict(step=dict(use_true_rho=True),
+                              sim=dict(initialize_ions=True, v_comoving=-0.995 * c, use_galilean=True, n_order=16,
+                                       n_guard=8)),
+    'no_correction': dict(step=dict(correct_currents=False), sim=dict()),
+    'no_filter': dict(step=dict(), sim=dict(filter_currents=False)),
+    'no_push_x': dict(step=dict(move_positions=False), sim=dict()),
+    'no_push_p': dict(step=dict(move_momenta=False), sim=dict()),
+    'cubic_true_rho_nm3': dict(step=dict(use_true_rho=True), sim=dict(initialize_ions=True, particle_shape='cubic'),
+                               Nm=3),
+}
+
+
+def gen_step_options(tag, nsteps=3):
+    """Periodic plasma wave advanced with the non-default options of Simulation / step() (main.py:346-586)."""
+    opt = STEP_OPTIONS[tag]
+    np.random.seed(0)
+    Nz, Nr, Nm, zmax, rmax = 24, 12, opt.get('Nm', 2), 12.e-6, 8.e-6
+    dt = zmax / Nz / c
+    n_e = 2.e24
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, p_zmin=0, p_zmax=zmax, p_rmin=0, p_rmax=rmax, p_nz=2, p_nr=2,
+                     p_nt=4 * max(Nm - 1, 1), n_e=n_e, verbose_level=0, boundaries={'z': 'periodic', 'r': 'reflective'},
+                     **opt['sim'])
+    k0 = 2 * np.pi / zmax * 2
+    wp = np.sqrt(n_e * e**2 / (m_e * 8.8541878128e-12))
+    impart_momenta(sim.ptcl[0], 0.05, k0, 3.e-6, wp)
+    V = opt['sim'].get('v_comoving')
+    if V is not None:
+        g = 1. / np.sqrt(1 - (V / c)**2)
+        for sp in sim.ptcl:
+            sp.uz += -np.sqrt(g**2 - 1)
+            sp.inv_gamma[:] = 1. / np.sqrt(1 + sp.ux**2 + sp.uy**2 + sp.uz**2)
+    out = dict(Nz=Nz, Nr=Nr, Nm=Nm, zmax=zmax, rmax=rmax, dt=dt, nsteps=nsteps, n_species=len(sim.ptcl))
+    for i, sp in enumerate(sim.ptcl):
+        out.update({'s%d_in_%s' % (i, k): v for k, v in ptcl_arrays(sp).items()})
+        out['s%d_q' % i], out['s%d_m' % i] = sp.q, sp.m
+    sim.step(nsteps, show_progress=False, **opt['step'])
+    for i, sp in enumerate(sim.ptcl):
+        out.update({'s%d_out_%s' % (i, k): v for k, v in ptcl_arrays(sp).items()})
+    out.update({'out_' + k: v for k, v in field_arrays(sim).items()})
+    out['zmin_end'] = sim.fld.interp[0].zmin
+    save('step_opt_' + tag, **out)
+
+
 GENERATORS = {
     'tables_variants': gen_tables_variants,
     'script_lwfa': lambda: gen_script('lwfa'),
@@ -310,6 +355,9 @@ GENERATORS = {
     'cross_std': lambda: gen_cross('std', None, False),
     'cross_galilean': lambda: gen_cross('galilean', -0.995 * c, True),
 }
+
+for _tag in STEP_OPTIONS:
+    GENERATORS['step_opt_' + _tag] = (lambda t: (lambda: gen_step_options(t)))(_tag)
 
 if __name__ == '__main__':
     only = sys.argv[sys.argv.index('--only') + 1] if '--only' in sys.argv else None

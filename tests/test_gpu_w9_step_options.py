@@ -1,0 +1,54 @@
+"""GPU parity of the non-default options of `Simulation` / `step()` (use_true_rho with neutralising ions, standard
+and Galilean; correct_currents=False; filter_currents=False; move_positions=False; move_momenta=False; cubic shapes
+with three modes) against golden outputs of the unmodified reference (oracle/gen_golden_ext.py)."""
+import numpy as np
+import pytest
+from scipy.constants import c
+
+from conftest import load_golden, assert_close, group_scale
+
+pytestmark = pytest.mark.gpu
+
+OPTIONS = {
+    'true_rho': dict(step=dict(use_true_rho=True), sim=dict()),
+    'true_rho_galilean': dict(step=dict(use_true_rho=True),
+                              sim=dict(v_comoving=-0.995 * c, use_galilean=True, n_order=16, n_guard=8)),
+    'no_correction': dict(step=dict(correct_currents=False), sim=dict()),
+    'no_filter': dict(step=dict(), sim=dict(filter_currents=False)),
+    'no_push_x': dict(step=dict(move_positions=False), sim=dict()),
+    'no_push_p': dict(step=dict(move_momenta=False), sim=dict()),
+    'cubic_true_rho_nm3': dict(step=dict(use_true_rho=True), sim=dict(particle_shape='cubic')),
+}
+STATE = ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w')
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('tag', sorted(OPTIONS))
+def test_step_options_vs_reference_golden(tag, fused):
+    from fbpic_b200 import Simulation
+    g = load_golden('step_opt_' + tag)
+    opt = OPTIONS[tag]
+    Nm = int(g['Nm'])
+    sim = Simulation(int(g['Nz']), float(g['zmax']), int(g['Nr']), float(g['rmax']), Nm, float(g['dt']),
+                     boundaries={'z': 'periodic', 'r': 'reflective'}, fused=fused, **opt['sim'])
+    for i in range(int(g['n_species'])):
+        sp = sim.add_new_species(q=float(g['s%d_q' % i]), m=float(g['s%d_m' % i]))
+        for k in STATE:
+            setattr(sp, k, g['s%d_in_%s' % (i, k)].copy())
+        sp.Ntot = len(sp.x)
+        for k in ('Ex', 'Ey', 'Ez', 'Bx', 'By', 'Bz'):
+            setattr(sp, k, np.zeros(sp.Ntot))
+    sim.step(int(g['nsteps']), **opt['step'])
+    assert abs(sim.fld.interp[0].zmin - float(g['zmin_end'])) <= 1e-12 * float(g['zmax'])
+    for i, sp in enumerate(sim.ptcl):
+        ref = np.stack([g['s%d_out_%s' % (i, k)] for k in STATE])
+        got = np.stack([getattr(sp, k) for k in STATE])
+        assert got.shape == ref.shape
+        ro, go = np.lexsort((ref[2], ref[0], ref[7])), np.lexsort((got[2], got[0], got[7]))
+        for j, k in enumerate(STATE[:7]):
+            assert_close(got[j][go], ref[j][ro], 1e-10, '%s species %d %s' % (tag, i, k))
+    for m in range(Nm):
+        for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz', 'Jr', 'Jt', 'Jz', 'rho'):
+            sc = group_scale(g, 'out_', 'rho' if k == 'rho' else k[0], Nm)
+            assert_close(getattr(sim.fld.interp[m], k), g['out_%s_m%d' % (k, m)], 1e-9,
+                         '%s %s m%d' % (tag, k, m), scale=sc)

@@ -23,6 +23,7 @@ import test_gpu_w3_bunch
 import test_gpu_w4_scripts
 import test_gpu_w6_acceptance
 import test_gpu_w8_diags
+import test_gpu_w9_step_options
 
 
 @pytest.fixture
@@ -191,3 +192,9 @@ def test_two_rank_diagnostics_flow_gloo():
            os.path.join(ROOT, 'tests', 'workers', 'mgpu_parity_worker.py'), '--fake-device']
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0 and 'MGPU_DIAG_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('tag', sorted(test_gpu_w9_step_options.OPTIONS))
+def test_step_options_flow(fake, tag, fused):
+    test_gpu_w9_step_options.test_step_options_vs_reference_golden(tag, fused)
