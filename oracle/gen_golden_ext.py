@@ -332,7 +332,29 @@ def gen_step_options(tag, nsteps=3):
     save('step_opt_' + tag, **out)
 
 
+def gen_mirror(tag, pml=False, gamma_boost=None, nsteps=30):
+    """A laser pulse reflected by a Mirror (mirrors.py:10-94; main.py:751-753)."""
+    from fbpic.lpa_utils.laser import add_laser_pulse, GaussianLaser
+    from fbpic.lpa_utils.mirrors import Mirror
+    Nz, Nr, Nm, zmax, rmax = 48, 12, 2, 24.e-6, 12.e-6
+    dt = zmax / Nz / c
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, zmin=0., n_order=-1, n_guard=12, n_damp={'z': 12, 'r': 6},
+                     gamma_boost=gamma_boost, verbose_level=0,
+                     boundaries={'z': 'open', 'r': ('open' if pml else 'reflective')})
+    add_laser_pulse(sim, GaussianLaser(a0=1., waist=4.e-6, tau=6.e-15, z0=8.e-6, lambda0=1.6e-6, theta_pol=0.4),
+                    gamma_boost=gamma_boost)
+    sim.mirrors = [Mirror(16.e-6, 17.5e-6, gamma_boost=gamma_boost, m=('all' if not pml else [1]))]
+    sim.step(nsteps, show_progress=False)
+    out = dict(Nz=Nz, Nr=Nr, Nm=Nm, zmax=zmax, rmax=rmax, dt=dt, nsteps=nsteps, pml=pml,
+               gamma_boost=(0. if gamma_boost is None else gamma_boost))
+    out.update({'out_' + k: v for k, v in field_arrays(sim, ('E', 'B')).items()})
+    save('mirror_' + tag, **out)
+
+
 GENERATORS = {
+    'mirror_lab': lambda: gen_mirror('lab'),
+    'mirror_pml': lambda: gen_mirror('pml', pml=True),
+    'mirror_boost': lambda: gen_mirror('boost', gamma_boost=2., nsteps=40),
     'tables_variants': gen_tables_variants,
     'script_lwfa': lambda: gen_script('lwfa'),
     'script_boosted': lambda: gen_script('boosted'),

@@ -68,3 +68,25 @@ def test_laser_antenna_vs_reference_golden(tag, fused):
             sc = group_scale(g, 'out_', 'rho' if k == 'rho' else k[0], Nm)
             assert_close(getattr(sim.fld.interp[m], k), g['out_%s_m%d' % (k, m)], 1e-9,
                          'antenna %s %s m%d' % (tag, k, m), scale=sc)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('tag', ['lab', 'pml', 'boost'])
+def test_mirror_vs_reference_golden(tag, fused):
+    """mirrors.py:10-94: a Gaussian pulse runs into a mirror (E, B zeroed in a slab every cycle) and is reflected;
+    'pml': radial PML, only mode 1 is zeroed; 'boost': mirror position given in the lab frame, gamma_boost = 2."""
+    from fbpic_b200.lpa_utils.laser import add_laser_pulse, GaussianLaser
+    from fbpic_b200.lpa_utils.mirrors import Mirror
+    g = load_golden('mirror_' + tag)
+    gb = float(g['gamma_boost']) or None
+    pml = bool(g['pml'])
+    sim = _sim(g, boundaries={'z': 'open', 'r': ('open' if pml else 'reflective')}, fused=fused)
+    add_laser_pulse(sim, GaussianLaser(a0=1., waist=4.e-6, tau=6.e-15, z0=8.e-6, lambda0=1.6e-6, theta_pol=0.4),
+                    gamma_boost=gb)
+    sim.mirrors = [Mirror(16.e-6, 17.5e-6, gamma_boost=gb, m=('all' if not pml else [1]))]
+    sim.step(int(g['nsteps']))
+    Nm = sim.fld.Nm
+    for m in range(Nm):
+        for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz'):
+            assert_close(getattr(sim.fld.interp[m], k), g['out_%s_m%d' % (k, m)], 1e-9,
+                         'mirror %s %s m%d' % (tag, k, m), scale=group_scale(g, 'out_', k[0], Nm))

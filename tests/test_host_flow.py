@@ -198,3 +198,9 @@ def test_two_rank_diagnostics_flow_gloo():
 @pytest.mark.parametrize('tag', sorted(test_gpu_w9_step_options.OPTIONS))
 def test_step_options_flow(fake, tag, fused):
     test_gpu_w9_step_options.test_step_options_vs_reference_golden(tag, fused)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('tag', ['lab', 'pml', 'boost'])
+def test_mirror_flow(fake, tag, fused):
+    test_gpu_w2_laser.test_mirror_vs_reference_golden(tag, fused)
