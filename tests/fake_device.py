@@ -558,6 +558,39 @@ extern "C" void apply(long long n, double *F_, const double *x_, const double *y
 }
 '''
 
+class CheckedFake(object):
+    """What the product sees: every call is first put through the ctypes conversion rules of the real binding
+    (`fbpic_b200._lib._SIGNATURES`: number of arguments, integers where the C prototype has integers, pointers or
+    None where it has pointers), then forwarded to the fake.  A call that ctypes would reject fails here too."""
+
+    def __init__(self, fake):
+        self._fake = fake
+
+    def __getattr__(self, name):
+        from fbpic_b200 import _lib
+        target = getattr(self._fake, name)
+        argtypes = _lib._SIGNATURES.get(name)
+        if argtypes is None:
+            return target
+
+        def checked(*args):
+            if len(args) != len(argtypes):
+                raise TypeError('%s: %d arguments given, the C prototype has %d' % (name, len(args), len(argtypes)))
+            for i, (a, t) in enumerate(zip(args, argtypes)):
+                try:
+                    if t in (ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_double, ctypes.c_void_p,
+                             ctypes.c_char_p):
+                        t.from_param(a)
+                    elif a is not None and not isinstance(a, (ctypes.Array, ctypes.Structure)) \
+                            and not hasattr(a, '_obj'):
+                        t.from_param(a)
+                except (TypeError, ctypes.ArgumentError) as exc:
+                    raise TypeError('%s: argument %d (%r) is not convertible to %s: %s'
+                                    % (name, i, a, t.__name__, exc))
+            return target(*args)
+        return checked
+
+
 _KEEP = []      # fakes (and the host blocks they own) stay alive for the whole pytest process
 
 
@@ -567,7 +600,7 @@ def install_global():
     from fbpic_b200 import _lib
     fake = FakeLib()
     _KEEP.append(fake)
-    _lib._lib, _lib._ctx = fake, None
+    _lib._lib, _lib._ctx = CheckedFake(fake), None
     _lib.call.__dict__.clear()
     return fake
 
@@ -579,7 +612,7 @@ def install(monkeypatch):
     from fbpic_b200 import _lib
     fake = FakeLib()
     _KEEP.append(fake)
-    monkeypatch.setattr(_lib, '_lib', fake)
+    monkeypatch.setattr(_lib, '_lib', CheckedFake(fake))
     monkeypatch.setattr(_lib, '_ctx', None)
     monkeypatch.setattr(_lib, '_PINNED_FREE', {})
     _lib.call.__dict__.clear()
