@@ -62,6 +62,17 @@ int b2_correct_currents_cross(b2_ctx *ctx, const b2_spectral_mode *M, const void
     return 0;
 }
 
+int b2_correct_divE(b2_ctx *ctx, const b2_spectral_mode *M, int Nz, int Nr, void *stream) {
+    if (Nz <= 0 || Nr <= 0) return 0;
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    B2Prof prof_(B2P_SPECTRAL, s);
+    b2ext::k_correct_divE<<<x_grid2d(Nz, Nr, XBLK), XBLK, 0, s>>>((double2 *)M->Ep, (double2 *)M->Em, (double2 *)M->Ez,
+                                                                (const double2 *)M->rho_prev, M->kz, M->kr, M->inv_k2,
+                                                                1. / M->epsilon_0, Nz, Nr);
+    B2_LAUNCHED();
+    return 0;
+}
+
 int b2_antenna_particles(b2_ctx *ctx, int64_t n, const double *bx, const double *by, const double *ex,
                          const double *ey, const double *vx, const double *vy, const double *vz, double sign,
                          double *x, double *y, double *ux, double *uy, double *uz, void *stream) {

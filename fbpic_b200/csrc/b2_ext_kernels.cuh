@@ -125,6 +125,23 @@ __global__ void k_correct_cross(const double2 *__restrict__ rho_prev, const doub
     }
 }
 
+// ---- div E correction ---------------------------------------------------------------------------------
+// SpectralGrid.correct_divE (fbpic/fields/spectral_grid.py:299-314; NumPy only in the reference, also in GPU
+// runs):  F = -inv_k2 (-rho_prev/eps0 + i kz Ez + kr (Ep - Em));  Ep += kr F/2; Em -= kr F/2; Ez -= i kz F
+__global__ void k_correct_divE(double2 *__restrict__ Ep, double2 *__restrict__ Em, double2 *__restrict__ Ez,
+                               const double2 *__restrict__ rho_prev, const double *__restrict__ kz_,
+                               const double *__restrict__ kr_, const double *__restrict__ inv_k2,
+                               double inv_eps0, int Nz, int Nr) {
+    B2X_2D_INDEX
+    const double kz = kz_[iz], kr = kr_[ir];
+    const double2 ep = Ep[o], em = Em[o], ez = Ez[o];
+    const double2 div = cadd(cadd(rmul(-inv_eps0, rho_prev[o]), rmul(kz, imul(ez))), rmul(kr, csub(ep, em)));
+    const double2 F = rmul(-inv_k2[o], div);
+    Ep[o] = cadd(ep, rmul(0.5 * kr, F));
+    Em[o] = cadd(em, rmul(-0.5 * kr, F));
+    Ez[o] = cadd(ez, rmul(kz, nimul(F)));
+}
+
 // ---- laser antenna: virtual particles -------------------------------------------------------------
 // LaserAntenna.deposit_virtual_particles_gpu (fbpic/lpa_utils/laser/antenna_injection.py:357-391):
 // positions x = baseline + sign*excursion and normalised momenta u = v/c (sign*v for x, y) of the

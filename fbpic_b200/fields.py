@@ -10,7 +10,7 @@ Arrays are NumPy on the host until `send_fields_to_gpu()`, `DeviceArray`s (HBM)
 afterwards, exactly like the reference swaps NumPy for CuPy arrays.
 
 Radial PML split fields (`use_pml`) and the cross-deposition current correction
- are built; correct_divE (CPU-only in the reference) is not.
+ are built, and so is correct_divE (NumPy-only in the reference, a device kernel here).
 """
 import ctypes
 import numpy as np
@@ -312,6 +312,11 @@ class SpectralGrid(object):
         else:
             raise ValueError('Unkown current correction:%s' % current_correction)
 
+    def correct_divE(self, ps):
+        """E <- E - grad-like correction such that div E = rho_prev/eps0 (spectral_grid.py:299-314)"""
+        s = self._mode_struct(ps)
+        call.b2_correct_divE(_lib.context().handle, ctypes.byref(s), self.Nz, self.Nr, None)
+
     def push_eb_pml_with(self, ps):
         """Split PML components (spectral_grid.py:343-348, 358-363); reads the Ez, Bz of BEFORE the
         regular push, so it is issued first."""
@@ -428,6 +433,11 @@ class Fields(object):
                 assert self.exchanged_source['rho_next_z'] is False
         for m in range(self.Nm):
             self.spect[m].correct_currents(self.dt, self.psatd[m], self.current_correction)
+
+    def correct_divE(self):
+        """fields.py:298-311 (the reference runs this one with NumPy; here it is a device kernel)"""
+        for m in range(self.Nm):
+            self.spect[m].correct_divE(self.psatd[m])
 
     def correct_currents_and_push(self, use_true_rho=False):
         """Fused Fields.correct_currents() + Fields.push() (single-domain fast path)."""

@@ -101,8 +101,8 @@ class Simulation(object):
         """N PIC cycles, call order of fbpic/main.py:346-586.  `keep_on_gpu=True` skips the
         final device->host copy (the data stays in HBM for the next call)."""
         ptcl, fld, dt = self.ptcl, self.fld, self.dt
-        if correct_divE:
-            raise NotImplementedError('correct_divE is CPU-only in the reference and out of scope')
+        if self.comm.size > 1 and correct_divE:
+            raise ValueError('correct_divE cannot be used in multi-proc mode.')
         if self.comm.size > 1 and use_true_rho and correct_currents:
             raise ValueError('`use_true_rho` cannot be used together with `correct_currents` '
                              'in multi-proc mode.')
@@ -232,6 +232,8 @@ class Simulation(object):
                         fld.partial_interp2spect('J')
                     fld.exchanged_source['J'] = True
                 fld.push(use_true_rho, check_exchanges=(self.comm.size > 1))
+            if correct_divE:                          # main.py:543-544
+                fld.correct_divE()
             if self.comm.moving_win is not None:
                 self.comm.move_grids(fld, ptcl, dt, self.time)
             self.exchange_and_damp_EB(skip_identity=(periodic_single and self.fused and not self.use_pml

@@ -292,6 +292,9 @@ int b2_damp_pml(b2_ctx *ctx, void *d_Et, void *d_Et_pml, void *d_Ez, void *d_Bt,
 int b2_correct_currents_cross(b2_ctx *ctx, const b2_spectral_mode *mode, const void *d_rho_next_z,
                               const void *d_rho_next_xy, int comoving, double inv_dt, int Nz, int Nr,
                               void *stream);
+/* div E correction in spectral space: SpectralGrid.correct_divE (fbpic/fields/spectral_grid.py:299-314, NumPy
+ * only in the reference); uses Ep, Em, Ez, rho_prev, kz, kr, inv_k2, epsilon_0 of `mode` */
+int b2_correct_divE(b2_ctx *ctx, const b2_spectral_mode *mode, int Nz, int Nr, void *stream);
 /* laser antenna (fbpic/lpa_utils/laser/antenna_injection.py:357-391): positions and normalised momenta of
  * the positive (sign=+1) / negative (sign=-1) copy of the virtual particles, to be handed to
  * b2_deposit_rho / b2_deposit_J (linear shapes, inv_gamma = 1):

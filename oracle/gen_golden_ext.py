@@ -293,6 +293,7 @@ STEP_OPTIONS = {
                               sim=dict(initialize_ions=True, v_comoving=-0.995 * c, use_galilean=True, n_order=16,
                                        n_guard=8)),
     'no_correction': dict(step=dict(correct_currents=False), sim=dict()),
+    'correct_divE': dict(step=dict(correct_divE=True, correct_currents=False), sim=dict(initialize_ions=True)),
     'no_filter': dict(step=dict(), sim=dict(filter_currents=False)),
     'no_push_x': dict(step=dict(move_positions=False), sim=dict()),
     'no_push_p': dict(step=dict(move_momenta=False), sim=dict()),

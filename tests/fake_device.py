@@ -499,6 +499,11 @@ class FakeLib(object):
             V(M.rho_prev), V(M.rho_next), V(_addr(rho_next_z)), V(_addr(rho_next_xy)), V(M.Jp), V(M.Jm), V(M.Jz),
             V(M.kz), V(M.kr), V(M.T_cc), V(M.j_corr_coef), V(M.T_eb), int(comoving), ctypes.c_double(inv_dt), Nz, Nr)
 
+    def b2_correct_divE(self, ctx, mode, Nz, Nr, stream):
+        M, V = mode._obj, ctypes.c_void_p
+        return self.emu.emu_correct_divE(V(M.Ep), V(M.Em), V(M.Ez), V(M.rho_prev), V(M.kz), V(M.kr), V(M.inv_k2),
+                                         ctypes.c_double(1. / M.epsilon_0), Nz, Nr)
+
     def b2_antenna_particles(self, ctx, n, bx, by, ex, ey, vx, vy, vz, sign, x, y, ux, uy, uz, stream):
         V = ctypes.c_void_p
         return self.emu.emu_antenna_particles(ctypes.c_longlong(n), *[V(_addr(p)) for p in (bx, by, ex, ey, vx, vy, vz)],

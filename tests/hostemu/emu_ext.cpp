@@ -47,6 +47,14 @@ int emu_correct_currents_cross(const void *rho_prev, const void *rho_next, const
     return 0;
 }
 
+int emu_correct_divE(void *Ep, void *Em, void *Ez, const void *rho_prev, const double *kz, const double *kr,
+                     const double *inv_k2, double inv_eps0, int Nz, int Nr) {
+    emu_dim3 blk(64, 4);
+    EMU_LAUNCH(grid2d(Nz, Nr, blk), blk, b2ext::k_correct_divE, (double2 *)Ep, (double2 *)Em, (double2 *)Ez,
+               (const double2 *)rho_prev, kz, kr, inv_k2, inv_eps0, Nz, Nr);
+    return 0;
+}
+
 int emu_antenna_particles(long long n, const double *bx, const double *by, const double *ex, const double *ey,
                           const double *vx, const double *vy, const double *vz, double sign, double *x, double *y,
                           double *ux, double *uy, double *uz) {

@@ -103,6 +103,28 @@ def test_correct_currents_cross(comoving):
     assert np.array_equal(d['Jz'].get()[0], wJz[0]) and np.array_equal(d['Jp'].get()[:, 3], wJp[:, 3])
 
 
+def test_correct_divE():
+    from scipy.constants import epsilon_0, mu_0
+    from fbpic_b200 import _lib
+    from fbpic_b200._lib import SpectralMode
+    rng = np.random.default_rng(9)
+    Nz, Nr = 11, 70
+    Ep, Em, Ez, rho = [_cplx(rng, (Nz, Nr)) for _ in range(4)]
+    kz1, kr1 = rng.normal(size=Nz) * 1e5, np.abs(rng.normal(size=Nr)) * 1e5
+    kz, kr = kz1[:, None], kr1[None, :]
+    inv_k2 = np.ascontiguousarray(1. / (kz**2 + kr**2))
+    F = -inv_k2 * (-rho / epsilon_0 + 1.j * kz * Ez + kr * (Ep - Em))        # spectral_grid.py:299-314
+    want = dict(Ep=Ep + 0.5 * kr * F, Em=Em - 0.5 * kr * F, Ez=Ez - 1.j * kz * F)
+    d = dict(zip(('Ep', 'Em', 'Ez', 'rho_prev', 'kz', 'kr', 'inv_k2'), _dev(Ep, Em, Ez, rho, kz1, kr1, inv_k2)))
+    s = SpectralMode()
+    for k, v in d.items():
+        setattr(s, k, v.ptr)
+    s.mu_0, s.epsilon_0 = mu_0, epsilon_0
+    _lib.call.b2_correct_divE(_lib.context().handle, ctypes.byref(s), Nz, Nr, None)
+    for k, w in want.items():
+        assert_close(d[k].get(), w, 1e-14, k)
+
+
 def test_antenna_helpers():
     from fbpic_b200 import _lib
     from fbpic_b200._lib import DeviceArray

@@ -1,5 +1,5 @@
 """GPU parity of the non-default options of `Simulation` / `step()` (use_true_rho with neutralising ions, standard
-and Galilean; correct_currents=False; filter_currents=False; move_positions=False; move_momenta=False; cubic shapes
+and Galilean; correct_currents=False; filter_currents=False; move_positions=False; move_momenta=False; correct_divE; cubic shapes
 with three modes) against golden outputs of the unmodified reference (oracle/gen_golden_ext.py)."""
 import numpy as np
 import pytest
@@ -14,6 +14,7 @@ OPTIONS = {
     'true_rho_galilean': dict(step=dict(use_true_rho=True),
                               sim=dict(v_comoving=-0.995 * c, use_galilean=True, n_order=16, n_guard=8)),
     'no_correction': dict(step=dict(correct_currents=False), sim=dict()),
+    'correct_divE': dict(step=dict(correct_divE=True, correct_currents=False), sim=dict()),
     'no_filter': dict(step=dict(), sim=dict(filter_currents=False)),
     'no_push_x': dict(step=dict(move_positions=False), sim=dict()),
     'no_push_p': dict(step=dict(move_momenta=False), sim=dict()),

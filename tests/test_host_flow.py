@@ -156,6 +156,7 @@ def test_ext_kernel_tests_flow(fake):
         k.test_push_eb_pml(comoving, (9, 130))
         k.test_correct_currents_cross(comoving)
     k.test_damp_pml((33, 70), 33)
+    k.test_correct_divE()
     k.test_antenna_helpers()
     k.test_external_field_jit()
 

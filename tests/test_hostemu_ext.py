@@ -115,3 +115,19 @@ def test_emu_antenna_helpers(emu):
     y0 = by.copy()
     emu.emu_axpy(ctypes.c_longlong(n), ctypes.c_double(0.37), _p(vx), _p(by))
     assert np.array_equal(by, y0 + 0.37 * vx)
+
+
+def test_emu_correct_divE(emu):
+    from scipy.constants import epsilon_0
+    rng = np.random.default_rng(9)
+    Nz, Nr = 11, 70
+    Ep, Em, Ez, rho = [_cplx(rng, (Nz, Nr)) for _ in range(4)]
+    kz1, kr1 = rng.normal(size=Nz) * 1e5, np.abs(rng.normal(size=Nr)) * 1e5
+    kz, kr = kz1[:, None], kr1[None, :]
+    inv_k2 = 1. / (kz**2 + kr**2)
+    F = -inv_k2 * (-rho / epsilon_0 + 1.j * kz * Ez + kr * (Ep - Em))        # spectral_grid.py:299-314
+    want = [Ep + 0.5 * kr * F, Em - 0.5 * kr * F, Ez - 1.j * kz * F]
+    emu.emu_correct_divE(_p(Ep), _p(Em), _p(Ez), _p(rho), _p(kz1), _p(kr1), _p(np.ascontiguousarray(inv_k2)),
+                         ctypes.c_double(1. / epsilon_0), Nz, Nr)
+    for got, w, name in zip((Ep, Em, Ez), want, ('Ep', 'Em', 'Ez')):
+        assert_close(got, w, 1e-14, name)
