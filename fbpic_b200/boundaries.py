@@ -365,7 +365,41 @@ class BoundaryCommunicator(object):
             self._shift_z(new['z'], n_recv_l + n_stay, n_recv_r, +Ltot)
         if self.left_proc == self.size - 1 and n_recv_l:
             self._shift_z(new['z'], 0, n_recv_l, -Ltot)
+        if species.tracker is not None:
+            self._exchange_ids(species, N, zlo, zhi, n_new, n_stay, n_send_l, n_send_r, n_recv_l, n_recv_r,
+                               injected is not None)
         species.resize_device_arrays(new, n_new)
+
+    def _exchange_ids(self, species, N, zlo, zhi, n_new, n_stay, n_send_l, n_send_r, n_recv_l, n_recv_r, injected):
+        """The tracked ids take the same 3-way partition as the float attributes (the classification of
+        b2_exchange_classify is still valid: one more b2_exchange_scatter with the id array), travel to the
+        neighbours in a message of their own, and new ids are drawn for injected plasma
+        (particle_buffer_handling.py:117-167, 409-411; particles.py:367-368)."""
+        ctx, t = _lib.context(), species.tracker
+        cap = max(species._capacity, species._capacity_for(n_new))
+        dest = t.spare.view((n_new,)) if t.spare.capacity >= n_new else DeviceArray(cap, np.uint64).view((n_new,))
+        id_l = DeviceArray(max(n_send_l, 1), np.uint64)
+        id_r = DeviceArray(max(n_send_r, 1), np.uint64)
+        if N:
+            call.b2_exchange_scatter(ctx.handle, N, species.z.ptr, zlo, zhi, 1, ptr_array([t.id]),
+                                     ptr_array([dest.ptr + 8 * n_recv_l]), ptr_array([id_l]) if n_send_l else None,
+                                     ptr_array([id_r]) if n_send_r else None, None)
+        if self.size > 1:
+            call.b2_nccl_group_start()
+            if self.left_proc is not None and n_send_l:
+                call.b2_nccl_send(ctx.handle, id_l.ptr, 8 * n_send_l, self.left_proc, None)
+            if self.right_proc is not None and n_send_r:
+                call.b2_nccl_send(ctx.handle, id_r.ptr, 8 * n_send_r, self.right_proc, None)
+            if self.right_proc is not None and n_recv_r and not injected:
+                call.b2_nccl_recv(ctx.handle, dest.ptr + 8 * (n_recv_l + n_stay), 8 * n_recv_r, self.right_proc, None)
+            if self.left_proc is not None and n_recv_l:
+                call.b2_nccl_recv(ctx.handle, dest.ptr, 8 * n_recv_l, self.left_proc, None)
+            call.b2_nccl_group_end()
+        if injected and n_recv_r:
+            dest.view((n_recv_r,), byte_offset=8 * (n_recv_l + n_stay)).set(t.generate_new_ids(n_recv_r))
+        old = t.id
+        t.id = dest
+        t.spare = old.view((n_new,)) if old.capacity >= n_new else DeviceArray(cap, np.uint64).view((n_new,))
 
     def _send_buffer(self, side, n_doubles):
         """Grow-only device staging buffer for the particles leaving through one face."""
@@ -432,6 +466,15 @@ class BoundaryCommunicator(object):
         import torch
         t = torch.tensor(list(values), dtype=torch.float64)
         self._host_group().all_reduce(t)
+        return [float(v) for v in t]
+
+    def allreduce_max(self, values):
+        if self.size == 1:
+            return list(values)
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor(list(values), dtype=torch.float64)
+        self._host_group().all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(v) for v in t]
 
     def gather_grid_array(self, array, root=0, with_damp=False):

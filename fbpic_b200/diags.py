@@ -131,7 +131,7 @@ class FieldDiagnostic(NpzDiagnostic):
 
 
 _QUANTITIES = {'position': ('x', 'y', 'z'), 'momentum': ('ux', 'uy', 'uz'), 'weighting': ('w',),
-               'gamma': ('gamma',), 'E': ('Ex', 'Ey', 'Ez'), 'B': ('Bx', 'By', 'Bz')}
+               'gamma': ('gamma',), 'E': ('Ex', 'Ey', 'Ez'), 'B': ('Bx', 'By', 'Bz'), 'id': ('id',)}
 
 
 class ParticleDiagnostic(NpzDiagnostic):
@@ -150,11 +150,18 @@ class ParticleDiagnostic(NpzDiagnostic):
                 raise ValueError("Invalid string in particle_data: %s" % q)
         self.species_dict, self.particle_data, self.select = dict(species), list(particle_data), select
         self.dt = dt
+        # tracked species get their ids written as well (particle_diag.py:111-116)
+        if 'id' not in self.particle_data and any(sp.tracker is not None for sp in self.species_dict.values()):
+            self.particle_data.append('id')
 
     @staticmethod
     def _attr(sp, name):
         if name == 'gamma':
             return 1. / _host(sp.inv_gamma)
+        if name == 'id':
+            if sp.tracker is None:
+                raise ValueError('The species is not tracked: call `species.track(sim.comm)` first.')
+            return _host(sp.tracker.id)
         return _host(getattr(sp, name))
 
     def write_npz(self, iteration):
@@ -171,7 +178,8 @@ class ParticleDiagnostic(NpzDiagnostic):
                     if hi is not None:
                         keep &= (v < hi)
             data = {}
-            for q in self.particle_data:
+            quantities = [q for q in self.particle_data if not (q == 'id' and sp.tracker is None)]
+            for q in quantities:
                 for comp in _QUANTITIES[q]:
                     data[comp] = self._attr(sp, comp)[:n][keep]
             if self.comm is not None and self.comm.size > 1:
@@ -180,7 +188,7 @@ class ParticleDiagnostic(NpzDiagnostic):
                 data = {k: np.concatenate([p[k] for p in parts]) for k in data}
             grp = 'particles/%s/' % name
             out[grp + 'charge'], out[grp + 'mass'] = sp.q, sp.m
-            for q in self.particle_data:
+            for q in quantities:
                 for comp in _QUANTITIES[q]:
                     key = q if len(_QUANTITIES[q]) == 1 else '%s/%s' % (q, comp[-1])
                     out[grp + key] = data[comp]
@@ -256,6 +264,8 @@ def restart_from_checkpoint(sim, iteration=None, checkpoint_dir='./checkpoints')
                               ('uy', 'momentum/y'), ('uz', 'momentum/z'), ('w', 'weighting')):
                 setattr(sp, attr, np.ascontiguousarray(p[grp + key], dtype=np.float64))
             sp.Ntot = len(sp.x)
+            if sp.tracker is not None:
+                sp.tracker.overwrite_ids(p[grp + 'id'], comm)
             sp.inv_gamma = 1. / np.sqrt(1 + sp.ux**2 + sp.uy**2 + sp.uz**2)
             for k in FIELD_ATTRS:
                 setattr(sp, k, np.zeros(sp.Ntot))

@@ -9,7 +9,7 @@ Widened per SURVEY 8f: moving window with continuous injection (rank 1), laser a
 (rank 2), radial PML (`boundaries['r']='open'`) and the cross-deposition current correction
 (rank 4); plus mirrors, external fields and the boosted-frame conversion of the set-up
 (`gamma_boost`), and the `sim.diags` / `sim.checkpoints` hooks (fbpic_b200/diags.py).  Out of scope
-and therefore rejected loudly: ionization, Compton scattering, particle tracking.
+and therefore rejected loudly: ionization, Compton scattering.
 """
 import numpy as np
 from scipy.constants import m_e, m_p, e, c

@@ -130,6 +130,50 @@ class ContinuousInjector(object):
         return out
 
 
+class ParticleTracker(object):
+    """Unique integer ids of the macroparticles, for tracking in post-processing
+    (fbpic/particles/tracking/tracking.py:15-130): rank r hands out r, r + size, r + 2 size, ...
+    On the device the ids are one more 8-byte array that follows the particles through the cell sort and the
+    particle exchange (moved bit for bit by the same permutation / partition kernels as the float attributes)."""
+
+    def __init__(self, comm_size, comm_rank, N):
+        self.next_attributed_id = comm_rank
+        self.id_step = comm_size
+        self.id = self.generate_new_ids(N)
+        self.spare = None
+
+    def generate_new_ids(self, N):
+        stop = self.next_attributed_id + N * self.id_step
+        ids = np.arange(start=self.next_attributed_id, stop=stop, step=self.id_step, dtype=np.uint64)
+        self.next_attributed_id = stop
+        return ids
+
+    def overwrite_ids(self, pid, comm):
+        """tracking.py:92-118"""
+        self.id = np.array(pid, dtype=np.uint64)
+        local_max = int(pid.max()) if len(pid) > 0 else 0
+        global_max = int(max(comm.allreduce_max([float(local_max)])))
+        n = int((global_max - comm.rank) / self.id_step) + 1
+        self.next_attributed_id = comm.rank + n * self.id_step
+
+    def send_to_gpu(self, capacity):
+        n = len(self.id)
+        d = DeviceArray(capacity, np.uint64).view((n,))
+        d.set(self.id)
+        self.id = d
+        self.spare = DeviceArray(capacity, np.uint64).view((n,))
+
+    def receive_from_gpu(self):
+        self.id = self.id.get()
+        self.spare = None
+
+    def swap(self, n=None):
+        """the spare buffer (just filled by a permutation / partition) becomes the id array"""
+        self.id, self.spare = self.spare, self.id
+        if n is not None:
+            self.id, self.spare = self.id.view((n,)), self.spare.view((n,))
+
+
 class Particles(object):
     """One species.  At the end/start of a PIC cycle the momenta are half a step
     behind the positions (particles.py:62-63)."""
@@ -179,6 +223,14 @@ class Particles(object):
         # the host<->device copies of a step() call
         self.fields_resident_only = False
 
+    def track(self, comm):
+        """Activate particle tracking: a unique id per macroparticle, written by the particle diagnostics
+        (fbpic/particles/particles.py:376-392)."""
+        if self.data_is_on_gpu:
+            raise _lib.B200Error('track() acts on the host copy of the particles: call it before step()')
+        self.tracker = ParticleTracker(comm.size, comm.rank, self.Ntot)
+        self.n_integer_quantities += 1
+
     # ------------------------------------------------------------------ device residency
     HEADROOM = 1.08     # per-particle device arrays are allocated with room for migration
 
@@ -213,6 +265,8 @@ class Particles(object):
             else:
                 d.set(np.asarray(getattr(self, k), dtype=np.float64))
             setattr(self, k, d)
+        if self.tracker is not None:
+            self.tracker.send_to_gpu(self._capacity)
         self._alloc_sort_arrays()
         self.sorted = False
         self.data_is_on_gpu = True
@@ -227,6 +281,8 @@ class Particles(object):
             # fused gather+push keeps the gathered fields in registers: the device arrays still hold the zeros
             # they were created with, so the host gets zeros without a copy
             setattr(self, k, np.zeros(self.Ntot) if self.fields_resident_only else _lib.to_host(getattr(self, k)))
+        if self.tracker is not None:
+            self.tracker.receive_from_gpu()
         self.data_is_on_gpu = False
 
     def resize_device_arrays(self, new_arrays, n_new):
@@ -389,6 +445,17 @@ class Particles(object):
         for i, k in enumerate(names):
             setattr(self, k, dst[i])
             self.sorting_buffers[i] = src[i]
+        self._permute_ids(self.sorted_idx.ptr)
+
+    def _permute_ids(self, sorted_idx_ptr):
+        """The tracked ids follow the sort (particles.py:541-542); sorted_idx_ptr None: the permutation of the
+        last b2_sort_cells on this context."""
+        if self.tracker is None:
+            return
+        t = self.tracker
+        call.b2_permute(_lib.context().handle, self.Ntot, sorted_idx_ptr, 1, ptr_array([t.id]), ptr_array([t.spare]),
+                        None)
+        t.swap()
 
     # ------------------------------------------------------------------ deposition
     def deposit_fused(self, fld, fieldtype, push=None):
@@ -466,6 +533,7 @@ class Particles(object):
         for i, k in enumerate(names):
             setattr(self, k, dst[i])
             self.sorting_buffers[i] = src[i]
+        self._permute_ids(None)
         self.sorted = True
         self._order_matches_prefix = True
 

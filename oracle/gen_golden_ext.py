@@ -352,7 +352,31 @@ def gen_mirror(tag, pml=False, gamma_boost=None, nsteps=30):
     save('mirror_' + tag, **out)
 
 
+def gen_tracking(nsteps=20):
+    """Tracked electrons in a moving window with continuous injection: ids follow the particles and new ids are
+    drawn for the injected plasma (tracking.py:15-130; particles.py:367-368, 376-392)."""
+    np.random.seed(5)
+    Nz, Nr, Nm, zmax, rmax = 32, 10, 2, 16.e-6, 8.e-6
+    dt = zmax / Nz / c
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, p_zmin=4.e-6, p_zmax=60.e-6, p_rmin=0, p_rmax=6.e-6, p_nz=2, p_nr=2,
+                     p_nt=4, n_e=1.e24, n_order=-1, n_guard=12, n_damp={'z': 12, 'r': 4}, verbose_level=0,
+                     boundaries={'z': 'open', 'r': 'reflective'})
+    sp = sim.ptcl[0]
+    sp.uz[:] = 0.4 * np.sin(2 * np.pi * sp.z / 8.e-6) * (sp.z < 10.e-6)
+    sp.inv_gamma[:] = 1. / np.sqrt(1 + sp.uz**2)
+    sp.track(sim.comm)
+    sim.set_moving_window(v=c)
+    out = dict(Nz=Nz, Nr=Nr, Nm=Nm, zmax=zmax, rmax=rmax, dt=dt, nsteps=nsteps, n_in=sp.Ntot, id_in=sp.tracker.id.copy())
+    out.update({'in_%s' % k: v for k, v in ptcl_arrays(sp).items()})
+    np.random.seed(6)
+    sim.step(nsteps, show_progress=False)
+    out.update({'out_%s' % k: v for k, v in ptcl_arrays(sp).items()})
+    out['id_out'] = sp.tracker.id.copy()
+    save('tracking_window', **out)
+
+
 GENERATORS = {
+    'tracking_window': gen_tracking,
     'mirror_lab': lambda: gen_mirror('lab'),
     'mirror_pml': lambda: gen_mirror('pml', pml=True),
     'mirror_boost': lambda: gen_mirror('boost', gamma_boost=2., nsteps=40),

@@ -120,3 +120,33 @@ def test_restart_from_checkpoint_continues_the_run(fused, window, tmp_path):
             for c_ in 'rtz':
                 assert_close(getattr(b.fld.interp[m], grp + c_), getattr(a.fld.interp[m], grp + c_), 1e-9,
                              'restart %s%s m%d' % (grp, c_, m), scale=scale)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+def test_tracked_ids_follow_the_particles(fused):
+    """Particle tracking (tracking.py:15-130) against the unmodified reference on the same inputs: after 20 cycles
+    with a moving window (particles dropped at the left edge, plasma injected at the right one, several cell
+    sorts) every id still labels the same particle, and the injected particles got the same new ids."""
+    from fbpic_b200 import Simulation
+    from conftest import load_golden
+    g = load_golden('tracking_window')
+    np.random.seed(5)
+    sim = Simulation(int(g['Nz']), float(g['zmax']), int(g['Nr']), float(g['rmax']), int(g['Nm']), float(g['dt']),
+                     p_zmin=4.e-6, p_zmax=60.e-6, p_rmin=0, p_rmax=6.e-6, p_nz=2, p_nr=2, p_nt=4, n_e=1.e24, n_order=-1,
+                     n_guard=12, n_damp={'z': 12, 'r': 4}, boundaries={'z': 'open', 'r': 'reflective'}, fused=fused)
+    sp = sim.ptcl[0]
+    assert sp.Ntot == int(g['n_in'])
+    sp.uz[:] = 0.4 * np.sin(2 * np.pi * sp.z / 8.e-6) * (sp.z < 10.e-6)
+    sp.inv_gamma[:] = 1. / np.sqrt(1 + sp.uz**2)
+    sp.track(sim.comm)
+    assert np.array_equal(sp.tracker.id, g['id_in'])
+    sim.set_moving_window(v=c)
+    np.random.seed(6)
+    sim.step(int(g['nsteps']))
+    ids = np.asarray(sp.tracker.id)
+    assert ids.dtype == np.uint64 and len(ids) == sp.Ntot == len(g['id_out'])
+    assert len(np.unique(ids)) == len(ids)
+    assert np.array_equal(np.sort(ids), np.sort(g['id_out']))
+    o, ro = np.argsort(ids), np.argsort(g['id_out'])
+    for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w'):
+        assert_close(np.asarray(getattr(sp, k))[o], g['out_' + k][ro], 1e-10, 'tracked ' + k)

@@ -205,3 +205,8 @@ def test_step_options_flow(fake, tag, fused):
 @pytest.mark.parametrize('tag', ['lab', 'pml', 'boost'])
 def test_mirror_flow(fake, tag, fused):
     test_gpu_w2_laser.test_mirror_vs_reference_golden(tag, fused)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+def test_tracking_flow(fake, fused):
+    test_gpu_w8_diags.test_tracked_ids_follow_the_particles(fused)

@@ -274,21 +274,43 @@ def run_diag_case(tol):
     Nz, Nr, Nm, zmax, rmax, n_e, n_order = nzr * size, 16, 2, 0.2e-6 * nzr * size, 8.e-6, 2.e24, 8
     dt = zmax / Nz / c
     P = global_particles(Nz, Nr, zmax, rmax, n_e)
+    P['uz'] = P['uz'] + 0.3          # a drift, so that particles cross the slab boundaries (and the ring closure)
+    P['inv_gamma'] = 1. / np.sqrt(1 + P['ux']**2 + P['uy']**2 + P['uz']**2)
     kw = dict(n_order=n_order, boundaries={'z': 'periodic', 'r': 'reflective'})
     dirs = [tempfile.mkdtemp() if rank == 0 else None, tempfile.mkdtemp() if rank == 0 else None]
     dist.broadcast_object_list(dirs, src=0)
 
     def run(sim, zlo, zhi, d):
         sp = set_species(sim, P, zlo, zhi)
+        sp.track(sim.comm)
+        sim.id_w_before = (np.array(sp.tracker.id), np.array(sp.w), np.array(sp.x))
         sim.diags = [FieldDiagnostic(period=3, fldobject=sim.fld, comm=sim.comm, fieldtypes=['E', 'B', 'rho'], write_dir=d),
                      ParticleDiagnostic(period=3, species={'e': sp}, comm=sim.comm, select={'uz': [0.05, None]},
                                         write_dir=d)]
         sim.step(5, correct_currents=False)
+        sim.step(1, correct_currents=False)      # a new call starts with a particle exchange: migration happens
 
     sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, **kw)
     zlo, zhi = sim.comm.get_zmin_zmax(local=True, with_damp=False, with_guard=False, rank=rank)
     run(sim, zlo, zhi, dirs[0])
     ok = True
+    # tracked ids migrate with their particles: every id is still unique over the ranks and labels a particle
+    # with the weight (never modified by the cycle) it had at the start
+    sp = sim.ptcl[0]
+    both = [None] * size
+    dist.all_gather_object(both, (sim.id_w_before[0], sim.id_w_before[1], np.array(sp.tracker.id), np.array(sp.w)))
+    if rank == 0:
+        id0, w0 = np.concatenate([b[0] for b in both]), np.concatenate([b[1] for b in both])
+        id1, w1 = np.concatenate([b[2] for b in both]), np.concatenate([b[3] for b in both])
+        moved = sum(len(np.setdiff1d(b[2], b[0])) for b in both)
+        if len(np.unique(id1)) != len(id1) or not np.array_equal(np.sort(id0), np.sort(id1)) \
+                or not np.array_equal(w0[np.argsort(id0)], w1[np.argsort(id1)]):
+            ok = False
+            print('DIAG MISMATCH tracked ids')
+        print('diag: %d tracked particles, %d changed rank' % (len(id1), moved))
+        if moved == 0:
+            ok = False
+            print('DIAG MISMATCH: no particle migrated, the id exchange was not exercised')
     if rank == 0:
         ref = Simulation(Nz, zmax, Nr, rmax, Nm, dt, use_all_mpi_ranks=False, n_guard=sim.comm.n_guard, **kw)
         run(ref, -1., 1.e9, dirs[1])
@@ -307,10 +329,12 @@ def run_diag_case(tol):
                 print('DIAG MISMATCH rho', it)
             pa = np.load(os.path.join(dirs[0], 'npz', 'particles%08d.npz' % it))
             pb = np.load(os.path.join(dirs[1], 'npz', 'particles%08d.npz' % it))
-            za, zb = np.sort(pa['particles/e/position/z']), np.sort(pb['particles/e/position/z'])
+            # (the two runs wrap / migrate their particles at different iterations: compare modulo the box length)
+            za, zb = np.sort(pa['particles/e/position/z'] % zmax), np.sort(pb['particles/e/position/z'] % zmax)
             if za.shape != zb.shape or (len(za) and np.abs(za - zb).max() > 1e-9 * zmax):
                 ok = False
-                print('DIAG MISMATCH particles', it, za.shape, zb.shape)
+                print('DIAG MISMATCH particles', it, za.shape, zb.shape, np.abs(za - zb).max() if za.shape == zb.shape else '',
+                      za.min(), zb.min(), za.max(), zb.max())
         print('diag: selected particles at iteration 3:', len(za))
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, src=0)
