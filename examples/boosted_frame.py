@@ -10,7 +10,8 @@ import numpy as np
 from scipy.constants import c, e, m_e, m_p
 
 from fbpic_b200 import Simulation
-from fbpic_b200.lpa_utils.laser import add_laser_pulse, GaussianLaser
+from fbpic_b200.lpa_utils.laser import add_laser_pulse
+from fbpic_b200.lpa_utils.laser.laser_profiles import GaussianLaser
 from fbpic_b200.lpa_utils.bunch import add_particle_bunch
 from fbpic_b200.lpa_utils.boosted_frame import BoostConverter
 from fbpic_b200.diags import FieldDiagnostic, ParticleDiagnostic

@@ -9,7 +9,8 @@ import numpy as np
 from scipy.constants import c, e, m_e
 
 from fbpic_b200 import Simulation
-from fbpic_b200.lpa_utils.laser import add_laser_pulse, GaussianLaser
+from fbpic_b200.lpa_utils.laser import add_laser_pulse
+from fbpic_b200.lpa_utils.laser.laser_profiles import GaussianLaser
 from fbpic_b200.diags import FieldDiagnostic, ParticleDiagnostic, set_periodic_checkpoint
 
 ap = argparse.ArgumentParser()

@@ -18,9 +18,9 @@ from math import factorial
 from scipy.constants import c, m_e, e, epsilon_0, physical_constants
 from scipy.special import genlaguerre, binom
 
-from .. import _lib
-from .._lib import DeviceArray, call, ptr_array
-from .boosted_frame import BoostConverter
+from ... import _lib
+from ..._lib import DeviceArray, call, ptr_array
+from ..boosted_frame import BoostConverter
 
 r_e = physical_constants['classical electron radius'][0]
 
@@ -301,7 +301,7 @@ def add_laser_direct(sim, laser_profile, boost):
     the reference gathers from the ranks (direct_injection.py:45-75) -- runs the forward transform, the
     spectral construction of Ez and B and the inverse transforms of that global grid on its own GPU and adds
     its slab (direct_injection.py:85-101): no communication."""
-    from ..fields import Fields
+    from ...fields import Fields
     comm, fld = sim.comm, sim.fld
     if fld.data_is_on_gpu:
         raise _lib.B200Error('add_laser_pulse(method="direct") acts on the host copy of the fields: call it '
