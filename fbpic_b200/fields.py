@@ -602,6 +602,76 @@ class Fields(object):
         arr = (DhtJob * len(jobs))(*jobs)
         call.b2_dht_batch(ctx.handle, len(jobs), arr, self.Nz, self.Nr, None)
 
+    def _dht_batch(self, jobs):
+        """b2_dht_batch on a job list of any length: one launch per kernel flavour carries at most MAX_DHT_JOBS
+        products (a scalar job is 1, an (r,t)->(p,m) job 2 products of the single-product kernel; a (p,m)->(r,t)
+        job is 1 product pair of the other kernel), longer lists are split."""
+        ctx = _lib.context()
+        chunk, n1, n2 = [], 0, 0
+
+        def flush():
+            if chunk:
+                arr = (DhtJob * len(chunk))(*chunk)
+                call.b2_dht_batch(ctx.handle, len(chunk), arr, self.Nz, self.Nr, None)
+
+        for j in jobs:
+            c1 = {_lib.DHT_SCALAR: 1, _lib.DHT_RT_TO_PM: 2}.get(j.kind, 0)
+            c2 = 1 if j.kind == _lib.DHT_PM_TO_RT else 0
+            if n1 + c1 > _lib.MAX_DHT_JOBS or n2 + c2 > _lib.MAX_DHT_JOBS:
+                flush()
+                chunk, n1, n2 = [], 0, 0
+            chunk.append(j)
+            n1, n2 = n1 + c1, n2 + c2
+        flush()
+
+    def _pml_buffers(self):
+        if getattr(self, '_pml_buf', None) is None:
+            self._pml_buf = [[DeviceArray((self.Nz, self.Nr), np.complex128) for _ in range(4)] for m in range(self.Nm)]
+        return self._pml_buf
+
+    def fused_spect2interp_EB_pml(self):
+        """spect2interp of 'E', 'B', 'E_pml', 'B_pml' (main.py:732-737) as batched inverse Hankel launches of all modes
+        (1/Nz folded into the matrices) followed by one multi-lane call of unscaled inverse FFTs."""
+        T = self._fused_tables(getattr(self, '_fused_key', True))
+        P = self._pml_buffers()
+        jobs, ffts = [], []
+        for m in range(self.Nm):
+            g, s, t = self.interp[m], self.spect[m], T[m]
+            for f, o in (('E', 0), ('B', 3)):
+                bz, br, bt = t['buf'][o], t['buf'][o + 1], t['buf'][o + 2]
+                pr, pt = P[m][0 if f == 'E' else 2], P[m][1 if f == 'E' else 3]
+                jobs.append(DhtJob(getattr(s, f + 'z').ptr, None, bz.ptr, None, t['I0'].ptr, None, None, _lib.DHT_SCALAR))
+                jobs.append(DhtJob(getattr(s, f + 'p').ptr, getattr(s, f + 'm').ptr, br.ptr, bt.ptr,
+                                   t['Ip'].ptr, t['Im'].ptr, None, _lib.DHT_PM_TO_RT))
+                jobs.append(DhtJob(getattr(s, f + 'p_pml').ptr, getattr(s, f + 'm_pml').ptr, pr.ptr, pt.ptr,
+                                   t['Ip'].ptr, t['Im'].ptr, None, _lib.DHT_PM_TO_RT))
+                ffts += [(bz, getattr(g, f + 'z')), (br, getattr(g, f + 'r')), (bt, getattr(g, f + 't')),
+                         (pr, getattr(g, f + 'r_pml')), (pt, getattr(g, f + 't_pml'))]
+        self._dht_batch(jobs)
+        self._fft_many(ffts, 2)
+
+    def fused_interp2spect_EB_pml(self):
+        """interp2spect of 'E', 'B', 'E_pml', 'B_pml' (main.py:757-761): one multi-lane call of forward FFTs, then
+        batched forward Hankel launches with the (r,t)->(p,m) combination in their prologue."""
+        T = self._fused_tables(getattr(self, '_fused_key', True))
+        P = self._pml_buffers()
+        jobs, ffts = [], []
+        for m in range(self.Nm):
+            g, s, t, tr = self.interp[m], self.spect[m], T[m], self.trans[m]
+            for f, o in (('E', 0), ('B', 3)):
+                bz, br, bt = t['buf'][o], t['buf'][o + 1], t['buf'][o + 2]
+                pr, pt = P[m][0 if f == 'E' else 2], P[m][1 if f == 'E' else 3]
+                ffts += [(getattr(g, f + 'z'), bz), (getattr(g, f + 'r'), br), (getattr(g, f + 't'), bt),
+                         (getattr(g, f + 'r_pml'), pr), (getattr(g, f + 't_pml'), pt)]
+                jobs.append(DhtJob(bz.ptr, None, getattr(s, f + 'z').ptr, None, tr.dht0.d_M.ptr, None, None,
+                                   _lib.DHT_SCALAR))
+                jobs.append(DhtJob(br.ptr, bt.ptr, getattr(s, f + 'p').ptr, getattr(s, f + 'm').ptr,
+                                   tr.dhtp.d_M.ptr, tr.dhtm.d_M.ptr, None, _lib.DHT_RT_TO_PM))
+                jobs.append(DhtJob(pr.ptr, pt.ptr, getattr(s, f + 'p_pml').ptr, getattr(s, f + 'm_pml').ptr,
+                                   tr.dhtp.d_M.ptr, tr.dhtm.d_M.ptr, None, _lib.DHT_RT_TO_PM))
+        self._fft_many(ffts, 0)
+        self._dht_batch(jobs)
+
     # ---- interpolation-grid ops ----
     def erase(self, fieldtype):
         for m in range(self.Nm):
