@@ -8,7 +8,6 @@ argument meaning and attribute names (`x..w`, `Ex..Bz`, `cell_idx`,
 
 Out of scope here: ionization, Compton scattering, tracking.
 """
-import ctypes
 import inspect
 import warnings
 import numpy as np

@@ -3,7 +3,6 @@ exchange plan, including a world_size-2 run over gloo."""
 import os
 import subprocess
 import sys
-import numpy as np
 import pytest
 
 from conftest import ROOT
