@@ -210,3 +210,18 @@ def test_mirror_flow(fake, tag, fused):
 @pytest.mark.parametrize('fused', [False, True])
 def test_tracking_flow(fake, fused):
     test_gpu_w8_diags.test_tracked_ids_follow_the_particles(fused)
+
+
+def test_fullsize_property_tests_flow(fake, monkeypatch):
+    """The property tests of the full-size GPU suite, on a small grid (their logic, not their size)."""
+    import test_gpu_x_fullsize_properties as t
+    monkeypatch.setattr(t, 'NZ', 48)
+    monkeypatch.setattr(t, 'NR', 24)
+    t.test_sort_contract_full_size()
+    for shape in ('linear', 'cubic'):
+        t.test_deposition_conserves_charge_and_is_linear(shape)
+        t.test_gather_reproduces_uniform_fields(shape)
+    t.test_push_invariants()
+    t.test_transform_round_trips()
+    for fused in (False, True):
+        t.test_cold_plasma_is_a_fixed_point_of_the_cycle(fused)
