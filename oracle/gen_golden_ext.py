@@ -297,6 +297,9 @@ STEP_OPTIONS = {
     'no_filter': dict(step=dict(), sim=dict(filter_currents=False)),
     'no_push_x': dict(step=dict(move_positions=False), sim=dict()),
     'no_push_p': dict(step=dict(move_momenta=False), sim=dict()),
+    'nm1': dict(step=dict(), sim=dict(), Nm=1),
+    'nm1_cubic_galilean': dict(step=dict(), sim=dict(particle_shape='cubic', v_comoving=-0.995 * c, use_galilean=True,
+                                                     n_order=16, n_guard=8), Nm=1),
     'cubic_true_rho_nm3': dict(step=dict(use_true_rho=True), sim=dict(initialize_ions=True, particle_shape='cubic'),
                                Nm=3),
 }

@@ -1,5 +1,5 @@
 """GPU parity of the non-default options of `Simulation` / `step()` (use_true_rho with neutralising ions, standard
-and Galilean; correct_currents=False; filter_currents=False; move_positions=False; move_momenta=False; correct_divE; cubic shapes
+and Galilean; correct_currents=False; filter_currents=False; move_positions=False; move_momenta=False; correct_divE; a single azimuthal mode; cubic shapes
 with three modes) against golden outputs of the unmodified reference (oracle/gen_golden_ext.py)."""
 import numpy as np
 import pytest
@@ -18,6 +18,9 @@ OPTIONS = {
     'no_filter': dict(step=dict(), sim=dict(filter_currents=False)),
     'no_push_x': dict(step=dict(move_positions=False), sim=dict()),
     'no_push_p': dict(step=dict(move_momenta=False), sim=dict()),
+    'nm1': dict(step=dict(), sim=dict()),
+    'nm1_cubic_galilean': dict(step=dict(), sim=dict(particle_shape='cubic', v_comoving=-0.995 * c, use_galilean=True,
+                                                     n_order=16, n_guard=8)),
     'cubic_true_rho_nm3': dict(step=dict(use_true_rho=True), sim=dict(particle_shape='cubic')),
 }
 STATE = ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w')
