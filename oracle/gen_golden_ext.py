@@ -378,7 +378,32 @@ def gen_tracking(nsteps=20):
     save('tracking_window', **out)
 
 
+def gen_species_mix(nsteps=4):
+    """Several species at once: thermal electrons, heavier positive ions with another sampling, a tracer species
+    (pushed, never deposited) and a neutral one (q = 0: neither gathered nor pushed in momentum)
+    (main.py:792-1001; particles.py:557-560, 690-693, 860-864)."""
+    from scipy.constants import m_p
+    np.random.seed(8)
+    Nz, Nr, Nm, zmax, rmax = 24, 12, 2, 12.e-6, 8.e-6
+    dt = zmax / Nz / c
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, verbose_level=0, boundaries={'z': 'periodic', 'r': 'reflective'})
+    kw = dict(p_zmin=0, p_zmax=zmax, p_rmin=0, p_rmax=rmax)
+    sim.add_new_species(q=-e, m=m_e, n=2.e24, p_nz=2, p_nr=2, p_nt=4, ux_th=0.02, uy_th=0.01, uz_th=0.05, uz_m=0.1, **kw)
+    sim.add_new_species(q=2 * e, m=4 * m_p, n=1.e24, p_nz=1, p_nr=2, p_nt=6, **kw)
+    sim.add_new_species(q=-e, m=m_e, n=1.e20, p_nz=1, p_nr=1, p_nt=4, is_tracer=True, ux_m=0.3, **kw)
+    sim.add_new_species(q=0., m=m_e, n=1.e24, p_nz=1, p_nr=1, p_nt=4, uz_m=2., uy_th=0.1, **kw)
+    out = dict(Nz=Nz, Nr=Nr, Nm=Nm, zmax=zmax, rmax=rmax, dt=dt, nsteps=nsteps, n_species=len(sim.ptcl))
+    for i, sp in enumerate(sim.ptcl):
+        out.update({'s%d_in_%s' % (i, k): v for k, v in ptcl_arrays(sp).items()})
+    sim.step(nsteps, show_progress=False)
+    for i, sp in enumerate(sim.ptcl):
+        out.update({'s%d_out_%s' % (i, k): v for k, v in ptcl_arrays(sp).items()})
+    out.update({'out_' + k: v for k, v in field_arrays(sim).items()})
+    save('step_species_mix', **out)
+
+
 GENERATORS = {
+    'species_mix': gen_species_mix,
     'tracking_window': gen_tracking,
     'mirror_lab': lambda: gen_mirror('lab'),
     'mirror_pml': lambda: gen_mirror('pml', pml=True),

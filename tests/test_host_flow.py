@@ -225,3 +225,8 @@ def test_fullsize_property_tests_flow(fake, monkeypatch):
     t.test_transform_round_trips()
     for fused in (False, True):
         t.test_cold_plasma_is_a_fixed_point_of_the_cycle(fused)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+def test_species_mix_flow(fake, fused):
+    test_gpu_w9_step_options.test_species_mix_vs_reference_golden(fused)
