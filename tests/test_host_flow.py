@@ -230,3 +230,16 @@ def test_fullsize_property_tests_flow(fake, monkeypatch):
 @pytest.mark.parametrize('fused', [False, True])
 def test_species_mix_flow(fake, fused):
     test_gpu_w9_step_options.test_species_mix_vs_reference_golden(fused)
+
+
+def test_kernel_level_operator_flow(fake):
+    """The operator-level GPU tests of test_gpu_kernels.py / the Nm = 4 step (kernel results are the oracle's own here:
+    what this run checks is the host side of the operator calls -- argument order, array swaps, sort-state flags)."""
+    import test_gpu_kernels as K
+    for shape in ('linear', 'cubic'):
+        for Nm in (1, 2, 3):
+            K.test_kernels_vs_reference_golden(shape, Nm)
+        K.test_deposit_gather_vs_oracle_large(shape, 2)
+        K.test_fused_deposition_paths_vs_oracle(shape, 2)
+        test_gpu_step.test_step_Nm4_vs_oracle(shape)
+    K.test_transforms_vs_numpy(48, 20)
