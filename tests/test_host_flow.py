@@ -243,3 +243,15 @@ def test_kernel_level_operator_flow(fake):
         K.test_fused_deposition_paths_vs_oracle(shape, 2)
         test_gpu_step.test_step_Nm4_vs_oracle(shape)
     K.test_transforms_vs_numpy(48, 20)
+
+
+def test_config_shape_tests_flow(fake, monkeypatch):
+    """The BASELINE-shape parity tests on reduced sizes (their host logic; the oracle checks itself here)."""
+    import test_gpu_x_config_shapes as t
+    monkeypatch.setattr(t, 'SCALE', 0.125)
+    for fused in (False, True):
+        t.test_c2_shape(fused)
+        t.test_c5_shape(fused)
+    t.test_c4_shape(True)
+    t.test_transforms_at_config_sizes(256, 256)
+    t.test_mode3_transforms_512()
