@@ -546,6 +546,9 @@ int b2_sort_cells(b2_ctx *ctx, int64_t n, int32_t *cell_idx, int64_t *sorted_idx
         B2_CUDA(cudaMemsetAsync(prefix_sum, 0, sizeof(int32_t) * (size_t)ncells, s));
         return 0;
     }
+    // 32-bit particle indices (CUB num_items, the idx32 permutation, the int32 prefix sums): one species on one
+    // GPU may hold up to 2^31 - 1 macroparticles (137 GB of SoA state -- more than fits next to the sort buffers)
+    if (n > (int64_t)INT32_MAX) return b2_fail(-3, "b2_sort_cells: more than 2^31-1 particles in one species on one GPU", __FILE__, __LINE__);
     B2Prof prof_(B2P_SORT, s);
     int end_bit = 1;
     while ((1LL << end_bit) < (long long)ncells && end_bit < 31) ++end_bit;
@@ -680,6 +683,7 @@ int b2_exchange_classify(b2_ctx *ctx, int64_t n, const double *z, double zlo, do
                          void *stream) {
     h_counts3[0] = h_counts3[1] = h_counts3[2] = 0;
     if (n <= 0) return 0;
+    if (n > (int64_t)INT32_MAX) return b2_fail(-3, "b2_exchange_classify: more than 2^31-1 particles in one species on one GPU", __FILE__, __LINE__);
     cudaStream_t s = b2_stream_of(ctx, stream);
     // scratch 1: [f_stay | f_left | f_right | cub temp]; the flags are scanned in place
     const size_t na = ((size_t)(n + 1) * sizeof(int32_t) + 255) & ~(size_t)255;
