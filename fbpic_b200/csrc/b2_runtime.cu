@@ -66,19 +66,21 @@ int b2_device_count(int *count) {
 
 int b2_ctx_create(int device, b2_ctx **out) {
     B2_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B2_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return b2_fail(-2, "fbpic_b200 needs an sm_100a (B200) device", __FILE__, __LINE__);
+    cudaStream_t stream;
+    B2_CUDA(cudaStreamCreate(&stream));
     b2_ctx *ctx = new b2_ctx();
     ctx->device = device;
-    B2_CUDA(cudaStreamCreate(&ctx->stream));
+    ctx->stream = stream;
     for (int i = 0; i < 4; ++i) { ctx->scratch[i] = nullptr; ctx->scratch_bytes[i] = 0; }
     ctx->last_idx32 = nullptr; ctx->last_keys_sorted = nullptr; ctx->last_sort_n = -1; ctx->part_n = -1;
     ctx->nccl_comm = nullptr;
     ctx->nccl_rank = 0;
     ctx->nccl_size = 1;
-    cudaDeviceProp prop;
-    B2_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
-    if (prop.major < 10)
-        return b2_fail(-2, "fbpic_b200 needs an sm_100a (B200) device", __FILE__, __LINE__);
     *out = ctx;
     return 0;
 }
