@@ -130,6 +130,40 @@ class FakeLib(object):
     def b2_stream_sync(self, stream):
         return 0
 
+    # events and the per-kernel profiler: host clock, no per-kernel records
+    def b2_event_create(self, p):
+        p._obj.value = len(self.calls) + 1
+        self.calls.append(0.)
+        return 0
+
+    def b2_event_destroy(self, e):
+        return 0
+
+    def b2_event_record(self, e, stream):
+        import time
+        self.calls[_addr(e) - 1] = time.perf_counter()
+        return 0
+
+    def b2_event_elapsed_ms(self, a, b, ms):
+        ms._obj.value = 1e3 * (self.calls[_addr(b) - 1] - self.calls[_addr(a) - 1])
+        return 0
+
+    def b2_profile_enable(self, on):
+        return 0
+
+    def b2_profile_reset(self):
+        return 0
+
+    def b2_profile_slots(self):
+        return 0
+
+    def b2_profile_name(self, slot):
+        return b''
+
+    def b2_profile_read(self, slot, total_ms, count):
+        total_ms._obj.value, count._obj.value = 0., 0
+        return 0
+
     def b2_device_sync(self):
         return 0
 

@@ -255,3 +255,22 @@ def test_config_shape_tests_flow(fake, monkeypatch):
     t.test_c4_shape(True)
     t.test_transforms_at_config_sizes(256, 256)
     t.test_mode3_transforms_512()
+
+
+def test_bench_flow(fake, monkeypatch, capsys):
+    """bench.py end to end on its `tiny` configuration (host flow: set-up, timed region bracketing, e2e leg with the
+    byte accounting, JSON line with every key of the contract)."""
+    import json
+    import bench
+    monkeypatch.setattr(sys, 'argv', ['bench.py', '--config', 'tiny', '--steps', '3', '--warmup', '3', '--preroll', '2',
+                                      '--no-cpu-baseline'])
+    bench.main()
+    line = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith('{')][-1]
+    d = json.loads(line)
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+              'vs_baseline', 'dtype', 'data', 'config', 'gpu_launches', 'clocks', 'e2e', 'roofline', 'cpu_baseline'):
+        assert k in d, k
+    assert d['steps'] == 3 and d['n_gpus'] == 1 and d['dtype'] == 'f64' and d['config']['workload'].startswith('tiny')
+    assert d['e2e']['value'] > 0 and 'error' not in d['e2e']
+    n = d['config']['particles_total']
+    assert 8 * 8 * n / 3 < d['e2e']['h2d_bytes_per_step'] < 14 * 8 * n / 3       # 8 particle arrays + the grids
