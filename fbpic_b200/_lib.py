@@ -128,6 +128,7 @@ _SIGNATURES = {
     'b2_damp_pml': [P, P, P, P, P, P, P, P, c_int, c_int, c_int, P],
     'b2_correct_currents_cross': [P, ctypes.POINTER(SpectralMode), P, P, c_int, c_double, c_int, c_int, P],
     'b2_correct_divE': [P, ctypes.POINTER(SpectralMode), c_int, c_int, P],
+    'b2_push_p_after_plane': [P, c_int64, P, c_double, P, P, P, P, P, P, P, P, P, P, c_double, c_double, c_double, P],
     'b2_antenna_particles': [P, c_int64, P, P, P, P, P, P, P, c_double, P, P, P, P, P, P],
     'b2_axpy': [P, c_int64, c_double, P, P, P],
     'b2_external_field_compile': [ctypes.c_char_p, ctypes.POINTER(P)],

@@ -73,6 +73,19 @@ int b2_correct_divE(b2_ctx *ctx, const b2_spectral_mode *M, int Nz, int Nr, void
     return 0;
 }
 
+int b2_push_p_after_plane(b2_ctx *ctx, int64_t n, const double *z, double z_plane, double *ux, double *uy, double *uz,
+                          double *inv_gamma, const double *Ex, const double *Ey, const double *Ez, const double *Bx,
+                          const double *By, const double *Bz, double q, double m, double dt, void *stream) {
+    if (n <= 0) return 0;
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    B2Prof prof_(B2P_PUSH, s);
+    const double econst = q * dt / (m * B2_C_LIGHT), bconst = 0.5 * q * dt / m;
+    b2ext::k_push_p_after_plane<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((long long)n, z, z_plane, ux, uy, uz,
+                                                                           inv_gamma, Ex, Ey, Ez, Bx, By, Bz, econst, bconst);
+    B2_LAUNCHED();
+    return 0;
+}
+
 int b2_antenna_particles(b2_ctx *ctx, int64_t n, const double *bx, const double *by, const double *ex,
                          const double *ey, const double *vx, const double *vy, const double *vz, double sign,
                          double *x, double *y, double *ux, double *uy, double *uz, void *stream) {

@@ -142,6 +142,36 @@ __global__ void k_correct_divE(double2 *__restrict__ Ep, double2 *__restrict__ E
     Ez[o] = cadd(ez, rmul(kz, nimul(F)));
 }
 
+// ---- momentum push beyond a plane -----------------------------------------------------------------------
+// push_p_after_plane_gpu (fbpic/particles/push/cuda_methods.py:103-132): the Vay push
+// (push/inline_functions.py:11-48) for the particles with z > z_plane; the others keep their momentum (ballistic
+// motion of an injected bunch before it reaches the plasma, injection/ballistic_before_plane.py:10-61).
+__global__ void k_push_p_after_plane(long long n, const double *__restrict__ z, double z_plane,
+                                     double *__restrict__ ux, double *__restrict__ uy, double *__restrict__ uz,
+                                     double *__restrict__ inv_gamma, const double *__restrict__ Ex,
+                                     const double *__restrict__ Ey, const double *__restrict__ Ez,
+                                     const double *__restrict__ Bx, const double *__restrict__ By,
+                                     const double *__restrict__ Bz, double econst, double bconst) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n || !(z[i] > z_plane)) return;
+    const double tx = bconst * Bx[i], ty = bconst * By[i], tz = bconst * Bz[i];
+    const double t2 = tx * tx + ty * ty + tz * tz;
+    const double ig0 = inv_gamma[i], u0x = ux[i], u0y = uy[i], u0z = uz[i];
+    // half electric kick + full magnetic term with the old velocity
+    const double px = u0x + econst * Ex[i] + ig0 * (u0y * tz - u0z * ty);
+    const double py = u0y + econst * Ey[i] + ig0 * (u0z * tx - u0x * tz);
+    const double pz = u0z + econst * Ez[i] + ig0 * (u0x * ty - u0y * tx);
+    const double sigma = 1 + px * px + py * py + pz * pz - t2;
+    const double pt = px * tx + py * ty + pz * tz;
+    const double ig = sqrt(2. / (sigma + sqrt(sigma * sigma + 4 * (t2 + pt * pt))));
+    const double sx = ig * tx, sy = ig * ty, sz = ig * tz, st = ig * pt;
+    const double s = 1. / (1 + t2 * ig * ig);
+    ux[i] = s * (px + sx * st + py * sz - pz * sy);
+    uy[i] = s * (py + sy * st + pz * sx - px * sz);
+    uz[i] = s * (pz + sz * st + px * sy - py * sx);
+    inv_gamma[i] = ig;
+}
+
 // ---- laser antenna: virtual particles -------------------------------------------------------------
 // LaserAntenna.deposit_virtual_particles_gpu (fbpic/lpa_utils/laser/antenna_injection.py:357-391):
 // positions x = baseline + sign*excursion and normalised momenta u = v/c (sign*v for x, y) of the

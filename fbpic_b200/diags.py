@@ -269,5 +269,5 @@ def restart_from_checkpoint(sim, iteration=None, checkpoint_dir='./checkpoints')
             sp.inv_gamma = 1. / np.sqrt(1 + sp.ux**2 + sp.uy**2 + sp.uz**2)
             for k in FIELD_ATTRS:
                 setattr(sp, k, np.zeros(sp.Ntot))
-            if sp.injector is not None:
+            if hasattr(sp.injector, 'reset_injection_positions'):
                 sp.injector.reset_injection_positions()

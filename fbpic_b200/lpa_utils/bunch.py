@@ -7,25 +7,25 @@ Relativistic particle bunches and their initial space-charge field, same entry p
 The bunch charge and current are deposited by the regular deposition kernel; the Poisson-like solve for the
 field of a bunch of Lorentz factor gamma is done in spectral space -- forward and inverse transforms on the
 GPU (cuFFT + DMMA Hankel), the element-wise spectral formula on the host arrays of this one-off set-up (the
-reference runs all of it on the CPU, bunch.py:886-915).  Not built: `z_injection_plane` (ballistic motion
-before a plane needs the `push_p_after_plane` pusher variants, SURVEY 2a out of scope) and openPMD input (h5py).
+reference runs all of it on the CPU, bunch.py:886-915).  Not built: openPMD input (h5py).
 """
 import warnings
 import numpy as np
 from scipy.constants import c, e, m_e, epsilon_0, mu_0
 
 
-def _no_injection_plane(z_injection_plane):
+def _set_injection_plane(ptcl_bunch, z_injection_plane, boost):
+    """bunch.py:117-119: ballistic motion before the plane z_injection_plane (lab frame)"""
     if z_injection_plane is not None:
-        raise NotImplementedError('`z_injection_plane` (ballistic motion before a plane) is not built: it needs '
-                                  'the push_p_after_plane pusher variants (out of scope of the hot path)')
+        from ..particles import BallisticBeforePlane
+        assert ptcl_bunch.injector is None      # don't overwrite a previous injector
+        ptcl_bunch.injector = BallisticBeforePlane(z_injection_plane, boost)
 
 
 def add_particle_bunch(sim, q, m, gamma0, n, p_zmin, p_zmax, p_rmin, p_rmax, p_nr=2, p_nz=2, p_nt=4,
                        dens_func=None, boost=None, direction='forward', z_injection_plane=None,
                        initialize_self_field=True, boost_positions_in_dens_func=False):
     """Uniform (or dens_func-shaped) mono-energetic bunch of Lorentz factor gamma0 (bunch.py:18-123)."""
-    _no_injection_plane(z_injection_plane)
     uz_m = (gamma0**2 - 1.)**0.5
     if direction == 'backward':
         uz_m *= -1.
@@ -33,6 +33,7 @@ def add_particle_bunch(sim, q, m, gamma0, n, p_zmin, p_zmax, p_rmin, p_rmax, p_n
                                      p_rmin=p_rmin, p_rmax=p_rmax, continuous_injection=False,
                                      dens_func=dens_func, uz_m=uz_m,
                                      boost_positions_in_dens_func=boost_positions_in_dens_func)
+    _set_injection_plane(ptcl_bunch, z_injection_plane, boost)
     if initialize_self_field:
         get_space_charge_fields(sim, ptcl_bunch, direction=direction)
     return ptcl_bunch
@@ -104,7 +105,6 @@ def add_particle_bunch_from_arrays(sim, q, m, x, y, z, ux, uy, uz, w, boost=None
     """Bunch from arrays given in the lab frame (bunch.py:456-547); with `boost` they are Lorentz-transformed
     and propagated to t' = 0.  Particles outside the local physical domain are dropped."""
     from ..particles import FIELD_ATTRS
-    _no_injection_plane(z_injection_plane)
     inv_gamma = 1. / np.sqrt(1. + ux**2 + uy**2 + uz**2)
     if boost is not None:
         x, y, z, ux, uy, uz, inv_gamma = boost.boost_particle_arrays(x, y, z, ux, uy, uz, inv_gamma)
@@ -117,6 +117,7 @@ def add_particle_bunch_from_arrays(sim, q, m, x, y, z, ux, uy, uz, w, boost=None
     ptcl_bunch.Ntot = int(sel.sum())
     for k in FIELD_ATTRS:
         setattr(ptcl_bunch, k, np.zeros(ptcl_bunch.Ntot))
+    _set_injection_plane(ptcl_bunch, z_injection_plane, boost)
     if initialize_self_field:
         get_space_charge_fields(sim, ptcl_bunch, direction=direction)
     return ptcl_bunch

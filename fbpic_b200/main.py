@@ -121,7 +121,7 @@ class Simulation(object):
 
         for species in ptcl:
             if not species.data_is_on_gpu:
-                species.fields_resident_only = bool(fuse_gp)
+                species.fields_resident_only = bool(fuse_gp) and not species.ballistic_before_plane
             elif not fuse_gp:
                 species.fields_resident_only = False      # an unfused gather will write them: read them back
         import time as _time
@@ -159,6 +159,12 @@ class Simulation(object):
             gal_shift = self.v_comoving * 0.5 * dt if self.use_galilean else 0.
             if fuse_gp:
                 for species in ptcl:
+                    if species.ballistic_before_plane:
+                        # the fused kernel pushes every particle: this species takes the three-kernel route
+                        species.gather(fld.interp, self.comm)
+                        species.push_p(self.time + 0.5 * dt)
+                        species.push_x(0.5 * dt)
+                        continue
                     will_sort = (not getattr(species, '_order_matches_prefix', False)) or \
                         species._j_since_sort >= self.sort_period - 1
                     species.gather_and_push(fld.interp, self.comm, 0.5 * dt,

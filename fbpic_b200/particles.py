@@ -129,6 +129,20 @@ class ContinuousInjector(object):
         return out
 
 
+class BallisticBeforePlane(object):
+    """Injection "through a plane": the particles of the species move ballistically until they cross the plane
+    z = z_plane_lab (fixed in the lab frame), e.g. the plasma entrance for a bunch initialised in vacuum in a
+    boosted-frame run (fbpic/particles/injection/ballistic_before_plane.py:10-61)."""
+
+    def __init__(self, z_plane_lab, boost):
+        self.z_plane_lab = z_plane_lab
+        self.inv_gamma_boost = 1. / boost.gamma0 if boost is not None else 1.
+        self.beta_boost = boost.beta0 if boost is not None else 0.
+
+    def get_current_plane_position(self, t):
+        return self.inv_gamma_boost * self.z_plane_lab - self.beta_boost * 299792458. * t
+
+
 class ParticleTracker(object):
     """Unique integer ids of the macroparticles, for tracking in post-processing
     (fbpic/particles/tracking/tracking.py:15-130): rank r hands out r, r + size, r + 2 size, ...
@@ -221,6 +235,10 @@ class Particles(object):
         # read back (they are never written on the device), which removes 6 of the 14 per-particle arrays from
         # the host<->device copies of a step() call
         self.fields_resident_only = False
+
+    @property
+    def ballistic_before_plane(self):
+        return isinstance(self.injector, BallisticBeforePlane)
 
     def track(self, comm):
         """Activate particle tracking: a unique id per macroparticle, written by the particle diagnostics
@@ -340,6 +358,12 @@ class Particles(object):
             return
         self._need_gpu()
         ctx = _lib.context()
+        if isinstance(self.injector, BallisticBeforePlane):       # particles.py:577-578, 599-606
+            call.b2_push_p_after_plane(ctx.handle, self.Ntot, self.z.ptr, self.injector.get_current_plane_position(t),
+                                       self.ux.ptr, self.uy.ptr, self.uz.ptr, self.inv_gamma.ptr,
+                                       self.Ex.ptr, self.Ey.ptr, self.Ez.ptr, self.Bx.ptr, self.By.ptr, self.Bz.ptr,
+                                       self.q, self.m, self.dt, None)
+            return
         call.b2_push_p(ctx.handle, self.Ntot, self.ux.ptr, self.uy.ptr, self.uz.ptr, self.inv_gamma.ptr,
                        self.Ex.ptr, self.Ey.ptr, self.Ez.ptr, self.Bx.ptr, self.By.ptr, self.Bz.ptr,
                        self.q, self.m, self.dt, None)

@@ -295,6 +295,12 @@ int b2_correct_currents_cross(b2_ctx *ctx, const b2_spectral_mode *mode, const v
 /* div E correction in spectral space: SpectralGrid.correct_divE (fbpic/fields/spectral_grid.py:299-314, NumPy
  * only in the reference); uses Ep, Em, Ez, rho_prev, kz, kr, inv_k2, epsilon_0 of `mode` */
 int b2_correct_divE(b2_ctx *ctx, const b2_spectral_mode *mode, int Nz, int Nr, void *stream);
+/* momentum push only for the particles beyond z_plane: push_p_after_plane_gpu
+ * (fbpic/particles/push/cuda_methods.py:103-132); the others move ballistically */
+int b2_push_p_after_plane(b2_ctx *ctx, int64_t n, const double *d_z, double z_plane, double *d_ux, double *d_uy,
+                          double *d_uz, double *d_inv_gamma, const double *d_Ex, const double *d_Ey,
+                          const double *d_Ez, const double *d_Bx, const double *d_By, const double *d_Bz,
+                          double q, double m, double dt, void *stream);
 /* laser antenna (fbpic/lpa_utils/laser/antenna_injection.py:357-391): positions and normalised momenta of
  * the positive (sign=+1) / negative (sign=-1) copy of the virtual particles, to be handed to
  * b2_deposit_rho / b2_deposit_J (linear shapes, inv_gamma = 1):

@@ -402,7 +402,32 @@ def gen_species_mix(nsteps=4):
     save('step_species_mix', **out)
 
 
+def gen_bunch_plane(tag, gamma_boost=None, nsteps=8):
+    """A Gaussian bunch with z_injection_plane: particles before the plane move ballistically, the others feel the
+    bunch's own field (bunch.py:117-119; push/numba_methods.py push_p_after_plane; ballistic_before_plane.py)."""
+    from fbpic.lpa_utils.bunch import add_particle_bunch_gaussian
+    from fbpic.lpa_utils.boosted_frame import BoostConverter
+    np.random.seed(19)
+    Nz, Nr, Nm, zmax, rmax = 40, 16, 2, 20.e-6, 16.e-6
+    dt = zmax / Nz / c
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, zmin=0., n_order=-1, n_guard=12, n_damp={'z': 10, 'r': 6},
+                     gamma_boost=gamma_boost, verbose_level=0, boundaries={'z': 'open', 'r': 'reflective'})
+    boost = BoostConverter(gamma_boost) if gamma_boost is not None else None
+    sp = add_particle_bunch_gaussian(sim, -e, m_e, sig_r=2.e-6, sig_z=1.5e-6, n_emit=1.e-6, gamma0=8., sig_gamma=0.5,
+                                     n_physical_particles=5.e9, n_macroparticles=1200, zf=9.e-6, boost=boost,
+                                     z_injection_plane=10.e-6)
+    out = dict(Nz=Nz, Nr=Nr, Nm=Nm, zmax=zmax, rmax=rmax, dt=dt, nsteps=nsteps,
+               gamma_boost=(0. if gamma_boost is None else gamma_boost))
+    out.update({'in_%s' % k: v for k, v in ptcl_arrays(sp).items()})
+    sim.step(nsteps, show_progress=False)
+    out.update({'out_%s' % k: v for k, v in ptcl_arrays(sp).items()})
+    out.update({'out_' + k: v for k, v in field_arrays(sim).items()})
+    save('bunch_plane_' + tag, **out)
+
+
 GENERATORS = {
+    'bunch_plane_lab': lambda: gen_bunch_plane('lab'),
+    'bunch_plane_boost': lambda: gen_bunch_plane('boost', gamma_boost=3.),
     'species_mix': gen_species_mix,
     'tracking_window': gen_tracking,
     'mirror_lab': lambda: gen_mirror('lab'),

@@ -541,6 +541,13 @@ class FakeLib(object):
         return self.emu.emu_correct_divE(V(M.Ep), V(M.Em), V(M.Ez), V(M.rho_prev), V(M.kz), V(M.kr), V(M.inv_k2),
                                          ctypes.c_double(1. / M.epsilon_0), Nz, Nr)
 
+    def b2_push_p_after_plane(self, ctx, n, z, z_plane, ux, uy, uz, ig, Ex, Ey, Ez, Bx, By, Bz, q, m, dt, stream):
+        V, D = ctypes.c_void_p, ctypes.c_double
+        c = 299792458.
+        return self.emu.emu_push_p_after_plane(ctypes.c_longlong(n), V(_addr(z)), D(z_plane),
+                                               *[V(_addr(p)) for p in (ux, uy, uz, ig, Ex, Ey, Ez, Bx, By, Bz)],
+                                               D(q * dt / (m * c)), D(0.5 * q * dt / m))
+
     def b2_antenna_particles(self, ctx, n, bx, by, ex, ey, vx, vy, vz, sign, x, y, ux, uy, uz, stream):
         V = ctypes.c_void_p
         return self.emu.emu_antenna_particles(ctypes.c_longlong(n), *[V(_addr(p)) for p in (bx, by, ex, ey, vx, vy, vz)],

@@ -55,6 +55,14 @@ int emu_correct_divE(void *Ep, void *Em, void *Ez, const void *rho_prev, const d
     return 0;
 }
 
+int emu_push_p_after_plane(long long n, const double *z, double z_plane, double *ux, double *uy, double *uz,
+                           double *ig, const double *Ex, const double *Ey, const double *Ez, const double *Bx,
+                           const double *By, const double *Bz, double econst, double bconst) {
+    EMU_LAUNCH(emu_dim3((unsigned)((n + 255) / 256)), emu_dim3(256), b2ext::k_push_p_after_plane, n, z, z_plane, ux, uy,
+               uz, ig, Ex, Ey, Ez, Bx, By, Bz, econst, bconst);
+    return 0;
+}
+
 int emu_antenna_particles(long long n, const double *bx, const double *by, const double *ex, const double *ey,
                           const double *vx, const double *vy, const double *vz, double sign, double *x, double *y,
                           double *ux, double *uy, double *uz) {

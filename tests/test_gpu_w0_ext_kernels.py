@@ -162,3 +162,33 @@ def test_external_field_jit():
         zl, tl = g * (z + b * c * t), g * (t + b * (1. / c) * z)
         assert_close(d[0].get(), F + amp * np.cos(zl / L) * x - tl * 1.e9 * y, 1e-14, 'external field g=%g' % g)
     _lib.call.b2_external_field_free(h)
+
+
+def test_push_p_after_plane():
+    """b2_push_p_after_plane against the oracle's Vay push masked to z > z_plane (push_p_after_plane_numba)."""
+    from oracle import oracle as orc
+    from scipy.constants import e, m_e
+    from fbpic_b200 import _lib
+    rng = np.random.default_rng(21)
+    n = 900
+    z = rng.uniform(-1., 1., n)
+    z[:3] = 0.2
+    u0 = [rng.normal(size=n) * 3. for _ in range(3)]
+    ig0 = 1. / np.sqrt(1. + u0[0]**2 + u0[1]**2 + u0[2]**2)
+    E = [rng.normal(size=n) * 1.e11 for _ in range(3)]
+    B = [rng.normal(size=n) * 300. for _ in range(3)]
+    q, m, dt = -e, m_e, 3.e-16
+    want = [a.copy() for a in u0] + [ig0.copy()]
+    orc.push_p(*want, *E, *B, q, m, dt)
+    keep = z <= 0.2
+    for w, a in zip(want, u0 + [ig0]):
+        w[keep] = a[keep]
+    dz, = _dev(z)
+    du = _dev(*u0, ig0)
+    df = _dev(*E, *B)
+    _lib.call.b2_push_p_after_plane(_lib.context().handle, n, dz.ptr, 0.2, *[a.ptr for a in du],
+                                    *[a.ptr for a in df], q, m, dt, None)
+    for g, w, a, name in zip(du, want, u0 + [ig0], ('ux', 'uy', 'uz', 'inv_gamma')):
+        g = g.get()
+        assert np.array_equal(g[keep], a[keep]), name
+        assert_close(g, w, 1e-14, name)

@@ -158,6 +158,7 @@ def test_ext_kernel_tests_flow(fake):
     k.test_damp_pml((33, 70), 33)
     k.test_correct_divE()
     k.test_antenna_helpers()
+    k.test_push_p_after_plane()
     k.test_external_field_jit()
 
 
@@ -274,3 +275,9 @@ def test_bench_flow(fake, monkeypatch, capsys):
     assert d['e2e']['value'] > 0 and 'error' not in d['e2e']
     n = d['config']['particles_total']
     assert 8 * 8 * n / 3 < d['e2e']['h2d_bytes_per_step'] < 14 * 8 * n / 3       # 8 particle arrays + the grids
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('tag', ['lab', 'boost'])
+def test_bunch_injection_plane_flow(fake, tag, fused):
+    test_gpu_w3_bunch.test_bunch_injection_plane_vs_reference_golden(tag, fused)

@@ -131,3 +131,31 @@ def test_emu_correct_divE(emu):
                          ctypes.c_double(1. / epsilon_0), Nz, Nr)
     for got, w, name in zip((Ep, Em, Ez), want, ('Ep', 'Em', 'Ez')):
         assert_close(got, w, 1e-14, name)
+
+
+def test_emu_push_p_after_plane(emu):
+    """push/numba_methods.py push_p_after_plane_numba: the Vay push where z > z_plane, untouched momenta elsewhere."""
+    from oracle import oracle as orc
+    from scipy.constants import e, m_e
+    rng = np.random.default_rng(21)
+    n = 900
+    z = rng.uniform(-1., 1., n)
+    z[:3] = 0.2                                                  # exactly on the plane: not pushed (strict >)
+    u0 = [rng.normal(size=n) * 3. for _ in range(3)]
+    ig0 = 1. / np.sqrt(1. + u0[0]**2 + u0[1]**2 + u0[2]**2)
+    E = [rng.normal(size=n) * 1.e11 for _ in range(3)]
+    B = [rng.normal(size=n) * 300. for _ in range(3)]
+    q, m, dt = -e, m_e, 3.e-16
+    want = [a.copy() for a in u0] + [ig0.copy()]
+    orc.push_p(*want, *E, *B, q, m, dt)
+    keep = z <= 0.2
+    for w, a in zip(want, u0 + [ig0]):
+        w[keep] = a[keep]
+    got = [a.copy() for a in u0] + [ig0.copy()]
+    emu.emu_push_p_after_plane(ctypes.c_longlong(n), _p(z), ctypes.c_double(0.2), *[_p(a) for a in got],
+                               *[_p(a) for a in E + B], ctypes.c_double(q * dt / (m * c)),
+                               ctypes.c_double(0.5 * q * dt / m))
+    for g, w, a, name in zip(got, want, u0 + [ig0], ('ux', 'uy', 'uz', 'inv_gamma')):
+        assert np.array_equal(g[keep], a[keep]), name
+        assert_close(g, w, 1e-14, name)
+    assert 0 < keep.sum() < n
