@@ -459,6 +459,19 @@ class BoundaryCommunicator(object):
             dist.init_process_group('gloo')
         return dist
 
+    def barrier(self):
+        if self.size > 1:
+            self._host_group().barrier()
+
+    def gather_ptcl_array(self, array, n_rank=None, Ntot=None):
+        """The particle arrays of all ranks, concatenated in rank order (boundary_communicator.py:1132-1168; every
+        rank receives the result)."""
+        if self.size == 1:
+            return array
+        parts = [None] * self.size
+        self._host_group().all_gather_object(parts, np.ascontiguousarray(array))
+        return np.concatenate(parts)
+
     def allreduce_sum(self, values):
         """Sum of a short list of floats over the ranks (mpi_comm.allreduce in the reference)."""
         if self.size == 1:

@@ -105,6 +105,20 @@ int b2_axpy(b2_ctx *ctx, int64_t n, double a, const double *x, double *y, void *
     return 0;
 }
 
+int b2_extract_slice(b2_ctx *ctx, const void *const *fields10, int m, int Nm, int Nz, int Nr, int Nr_out, int iz,
+                     double Sz, double *slice, void *stream) {
+    if (m < 0 || m >= Nm || Nr_out <= 0 || Nr_out > Nr)
+        return b2_fail(-3, "b2_extract_slice: bad mode or radial size", __FILE__, __LINE__);
+    if (iz < 0 || iz + 1 >= Nz) return b2_fail(-3, "b2_extract_slice: slice outside of the grid", __FILE__, __LINE__);
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    b2ext::SliceFields F;
+    for (int k = 0; k < 10; ++k) F.f[k] = (const double2 *)fields10[k];
+    const dim3 grid((unsigned)((Nr_out + 127) / 128), 10);
+    b2ext::k_extract_slice<<<grid, 128, 0, s>>>(F, m, 2 * Nm - 1, Nr, Nr_out, iz, Sz, slice);
+    B2_LAUNCHED();
+    return 0;
+}
+
 }  // extern "C"
 
 // =================================================================================================

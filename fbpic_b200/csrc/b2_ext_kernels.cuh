@@ -201,4 +201,25 @@ __global__ void k_axpy(long long n, double a, const double *__restrict__ x, doub
     y[i] = __dadd_rn(y[i], __dmul_rn(a, x[i]));
 }
 
+// ---- back-transformed (lab-frame) field diagnostics --------------------------------------------
+// extract_slice_cuda (fbpic/openpmd_diag/boosted_field_diag.py:745-820): the 10 grid fields of mode m,
+// interpolated linearly between the rows iz and iz+1 (weights Sz, 1 - Sz), as REAL rows of
+// slice[10][2 Nm - 1][Nr_out]: row 0 = Re(mode 0), rows 2m-1, 2m = 2 Re, 2 Im of mode m > 0.
+// Grid: (ir, field).  Rounded products then a rounded sum, like the NumPy expression of the CPU path (:626-629).
+struct SliceFields { const double2 *f[10]; };
+
+__global__ void k_extract_slice(SliceFields F, int m, int n_rows, int Nr, int Nr_out, int iz, double Sz,
+                                double *__restrict__ slice) {
+    const int ir = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (ir >= Nr_out) return;
+    const double fac = (m > 0) ? 2. : 1.;
+    const double a = fac * Sz, b = fac * (1. - Sz);
+    const double2 lo = F.f[k][(size_t)iz * Nr + ir], hi = F.f[k][(size_t)(iz + 1) * Nr + ir];
+    const int row = (m > 0) ? 2 * m - 1 : 0;
+    double *out = slice + ((size_t)k * n_rows + row) * Nr_out + ir;
+    out[0] = __dadd_rn(__dmul_rn(a, lo.x), __dmul_rn(b, hi.x));
+    if (m > 0) out[Nr_out] = __dadd_rn(__dmul_rn(a, lo.y), __dmul_rn(b, hi.y));
+}
+
 }  // namespace b2ext

@@ -114,9 +114,10 @@ class Simulation(object):
                         self.comm, self.comm.moving_win.v, z_host, self.dt)
         single = (self.comm.size == 1)
         periodic_single = single and self.comm.n_guard == 0
-        # external fields act on the gathered E, B of the particles and diagnostics may output them: both need
-        # the unfused gather
-        fuse_gp = self.fused and move_positions and move_momenta and not self.external_fields and not self.diags
+        # external fields act on the gathered E, B of the particles and particle diagnostics may output them: both
+        # need the unfused gather
+        fuse_gp = self.fused and move_positions and move_momenta and not self.external_fields and \
+            not any(getattr(diag, 'needs_gathered_fields', True) for diag in self.diags)
         fuse_cp = self.fused and correct_currents and single and fld.current_correction == 'curl-free'
 
         for species in ptcl:
@@ -158,6 +159,8 @@ class Simulation(object):
                 species.keep_fields_sorted = True
             gal_shift = self.v_comoving * 0.5 * dt if self.use_galilean else 0.
             if fuse_gp:
+                for diag in self.diags:                   # E, B, rho, x at time n (main.py:474-481)
+                    diag.write(self.iteration)
                 for species in ptcl:
                     if species.ballistic_before_plane:
                         # the fused kernel pushes every particle: this species takes the three-kernel route

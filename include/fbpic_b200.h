@@ -311,6 +311,11 @@ int b2_antenna_particles(b2_ctx *ctx, int64_t n, const double *d_bx, const doubl
                          void *stream);
 /* y += a*x (LaserAntenna.push_x, antenna_injection.py:196-218) */
 int b2_axpy(b2_ctx *ctx, int64_t n, double a, const double *d_x, double *d_y, void *stream);
+/* back-transformed diagnostics: extract_slice_cuda (fbpic/openpmd_diag/boosted_field_diag.py:745-820).
+ * d_fields10: host array of the 10 device grids Er, Et, Ez, Br, Bt, Bz, Jr, Jt, Jz, rho (complex [Nz, Nr]) of
+ * mode m; d_slice: real [10][2 Nm - 1][Nr_out]; rows iz, iz + 1 weighted by Sz, 1 - Sz (x2 for m > 0). */
+int b2_extract_slice(b2_ctx *ctx, const void *const *d_fields10, int m, int Nm, int Nz, int Nr, int Nr_out, int iz,
+                     double Sz, double *d_slice, void *stream);
 /* external fields (ExternalField, fbpic/lpa_utils/external_fields.py:13-215): the reference turns the user's
  * Python function into a GPU kernel with Numba (:134-147); here its body arrives as CUDA C statements over
  * the scalars F, x, y, z, t, amplitude, length_scale that end with `F_[i_] = <expr>;`, is compiled once by

@@ -425,7 +425,77 @@ def gen_bunch_plane(tag, gamma_boost=None, nsteps=8):
     save('bunch_plane_' + tag, **out)
 
 
+def _harvest(write_dir, prefix):
+    """Every shim-h5py file under write_dir/hdf5 as '<prefix>/<file>:<path>' -> dataset, '...@attr' -> attribute."""
+    import h5py
+    out = {}
+    d = os.path.join(write_dir, 'hdf5')
+    for name in sorted(os.listdir(d)):
+        for k, v in h5py.flatten(os.path.join(d, name)).items():
+            if isinstance(v, bytes):
+                v = np.bytes_(v)
+            out['%s/%s:%s' % (prefix, name, k)] = v
+    return out
+
+
+def _diag_namespace():
+    import types
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'tests'))
+    if not hasattr(np, 'string_'):          # gone from NumPy 2; the reference's writers use it for text attributes
+        np.string_ = np.bytes_
+    from fbpic.openpmd_diag import (FieldDiagnostic, ParticleDiagnostic, ParticleChargeDensityDiagnostic,
+                                    BackTransformedFieldDiagnostic, set_periodic_checkpoint)
+    from fbpic.lpa_utils.laser import add_laser_pulse, GaussianLaser
+    from fbpic.lpa_utils.boosted_frame import BoostConverter
+    return types.SimpleNamespace(Simulation=Simulation, FieldDiagnostic=FieldDiagnostic,
+                                 ParticleDiagnostic=ParticleDiagnostic,
+                                 ParticleChargeDensityDiagnostic=ParticleChargeDensityDiagnostic,
+                                 BackTransformedFieldDiagnostic=BackTransformedFieldDiagnostic,
+                                 set_periodic_checkpoint=set_periodic_checkpoint, add_laser_pulse=add_laser_pulse,
+                                 GaussianLaser=GaussianLaser, BoostConverter=BoostConverter)
+
+
+def gen_diags():
+    """The trees written by the reference's FieldDiagnostic, ParticleDiagnostic (with a selection and a tracked
+    species), ParticleChargeDensityDiagnostic and checkpoints (fbpic/openpmd_diag/*.py) for tests/diag_cases.py,
+    through the h5py stand-in of oracle/ref_shim."""
+    import shutil
+    import tempfile
+    ns = _diag_namespace()
+    import diag_cases
+    sim, elec, ions = diag_cases.build_diag_sim(ns, verbose_level=0)
+    tmp = tempfile.mkdtemp()
+    dirs = diag_cases.attach_diags(ns, sim, elec, ions, tmp)
+    np.random.seed(24)
+    sim.step(diag_cases.DIAG_STEPS, show_progress=False)
+    out = dict(nsteps=diag_cases.DIAG_STEPS)
+    for d, tag in zip(dirs, diag_cases.DIAG_DIRS):
+        out.update(_harvest(d, tag))
+    shutil.rmtree(tmp)
+    save('diags_tree', **out)
+
+
+def gen_lab_diags():
+    """Lab-frame snapshots of a boosted-frame run written by the reference's BackTransformedFieldDiagnostic
+    (fbpic/openpmd_diag/boosted_field_diag.py) for tests/diag_cases.py."""
+    import shutil
+    import tempfile
+    ns = _diag_namespace()
+    import diag_cases
+    sim, gamma_boost = diag_cases.build_lab_diag_sim(ns, verbose_level=0)
+    tmp = tempfile.mkdtemp()
+    d = diag_cases.attach_lab_diag(ns, sim, gamma_boost, tmp)
+    np.random.seed(30)
+    sim.step(diag_cases.LAB_DIAG_STEPS, show_progress=False)
+    out = dict(nsteps=diag_cases.LAB_DIAG_STEPS)
+    out.update(_harvest(d, 'lab'))
+    shutil.rmtree(tmp)
+    save('diags_lab_tree', **out)
+
+
 GENERATORS = {
+    'diags_tree': gen_diags,
+    'diags_lab_tree': gen_lab_diags,
     'bunch_plane_lab': lambda: gen_bunch_plane('lab'),
     'bunch_plane_boost': lambda: gen_bunch_plane('boost', gamma_boost=3.),
     'species_mix': gen_species_mix,

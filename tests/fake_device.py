@@ -588,6 +588,13 @@ class FakeLib(object):
         return self.emu.emu_axpy(ctypes.c_longlong(n), ctypes.c_double(a), ctypes.c_void_p(_addr(x)),
                                  ctypes.c_void_p(_addr(y)))
 
+    def b2_extract_slice(self, ctx, fields10, m, Nm, Nz, Nr, Nr_out, iz, Sz, slice_, stream):
+        if not (0 <= m < Nm and 0 < Nr_out <= Nr and 0 <= iz and iz + 1 < Nz):
+            return -3
+        ptrs = (ctypes.c_void_p * 10)(*_ptrs(fields10, 10))
+        return self.emu.emu_extract_slice(ptrs, m, Nm, Nz, Nr, Nr_out, iz, ctypes.c_double(Sz),
+                                          ctypes.c_void_p(_addr(slice_)))
+
 
 HOST_EXT_FIELD_TEMPLATE = r'''
 #include <cmath>

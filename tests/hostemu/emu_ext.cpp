@@ -76,4 +76,13 @@ int emu_axpy(long long n, double a, const double *x, double *y) {
     return 0;
 }
 
+int emu_extract_slice(const void *const *fields10, int m, int Nm, int Nz, int Nr, int Nr_out, int iz, double Sz,
+                      double *slice) {
+    b2ext::SliceFields F;
+    for (int k = 0; k < 10; ++k) F.f[k] = (const double2 *)fields10[k];
+    EMU_LAUNCH(emu_dim3((unsigned)((Nr_out + 127) / 128), 10), emu_dim3(128), b2ext::k_extract_slice, F, m, 2 * Nm - 1,
+               Nr, Nr_out, iz, Sz, slice);
+    return 0;
+}
+
 }  // extern "C"

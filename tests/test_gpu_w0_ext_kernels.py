@@ -192,3 +192,24 @@ def test_push_p_after_plane():
         g = g.get()
         assert np.array_equal(g[keep], a[keep]), name
         assert_close(g, w, 1e-14, name)
+
+
+@pytest.mark.parametrize('Nm', [1, 3])
+def test_extract_slice(Nm):
+    """b2_extract_slice (lab-frame diagnostics) against extract_slice_cpu of the reference, bit for bit; a slice
+    outside of the grid is refused."""
+    from fbpic_b200 import _lib
+    from fbpic_b200._lib import DeviceArray, B200Error
+    from test_hostemu_ext import _slice_reference
+    rng = np.random.default_rng(31)
+    Nz, Nr, Nr_out, iz, Sz = 9, 150, 141, 6, 0.3125
+    grids = [[_cplx(rng, (Nz, Nr)) for _ in range(10)] for _ in range(Nm)]
+    out = DeviceArray(10 * (2 * Nm - 1) * Nr_out, np.float64)
+    for m in range(Nm):
+        d = _dev(*grids[m])
+        _lib.call.b2_extract_slice(_lib.context().handle, _lib.ptr_array(d), m, Nm, Nz, Nr, Nr_out, iz, Sz, out.ptr, None)
+    got = out.get().reshape(10, 2 * Nm - 1, Nr_out)
+    assert np.array_equal(got, _slice_reference(grids, Nr_out, iz, Sz))
+    with pytest.raises(B200Error):
+        _lib.call.b2_extract_slice(_lib.context().handle, _lib.ptr_array(d), 0, Nm, Nz, Nr, Nr_out, Nz - 1, Sz, out.ptr,
+                                   None)

@@ -1,7 +1,9 @@
-"""GPU tests of the diagnostics / checkpoint hooks of `Simulation.step()` (fbpic_b200/diags.py; the reference's
-openpmd_diag writes openPMD/HDF5 through h5py, which is not available here, so these are self-consistency
-tests): a field / particle diagnostic written during a step holds the data the simulation itself reports for
-that iteration, and a run restarted from a checkpoint continues like the uninterrupted one."""
+"""GPU tests of the diagnostics / checkpoint hooks of `Simulation.step()` (fbpic_b200/diags.py): the openPMD trees
+written by the field, particle, charge-density, checkpoint and lab-frame (back-transformed) diagnostics against the
+trees the unmodified reference wrote for the same simulations (tests/golden/diags_tree.npz, diags_lab_tree.npz,
+harvested through the h5py stand-in of oracle/ref_shim); a diagnostic written during a step holds the data the
+simulation itself reports for that iteration; a run restarted from a checkpoint continues like the uninterrupted
+one."""
 import numpy as np
 import pytest
 from scipy.constants import c
@@ -56,8 +58,10 @@ def test_diagnostics_hold_the_state_of_their_iteration(fused, tmp_path):
     part = {k: np.array(getattr(sp, k)) for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'w', 'inv_gamma')}
     zmin_phys, _ = sim.comm.get_zmin_zmax(local=False, with_damp=False, with_guard=False)
     sim.step(1)                                   # iteration 5 is due at the start of this cycle
-    f = np.load(str(tmp_path / 'npz' / 'fields00000005.npz'))
-    assert int(f['meta/iteration']) == 5 and abs(float(f['meta/zmin']) - zmin_phys) < 1e-12
+    from fbpic_b200.diags import read_diag
+    from scipy.constants import m_e
+    f = p = read_diag(str(tmp_path), 5)
+    assert abs(float(f['time']) - 5 * sim.dt) < 1e-25 and abs(f['zmin'] - zmin_phys) < 1e-12
     assert f['fields/E/r'].shape == (3, 12, 32)
     for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz'):
         got = _modes(f['fields/%s/%s' % (k[0], k[1])], 2)
@@ -69,13 +73,13 @@ def test_diagnostics_hold_the_state_of_their_iteration(fused, tmp_path):
     for m in range(2):          # re-deposited after a re-sort: summation order differs
         assert_close(got[m], ref['rho'][m] if m else ref['rho'][m].real, 1e-11, 'diag rho m%d' % m, scale=scale)
     assert np.all(np.isfinite(f['fields/J/z']))
-    p = np.load(str(tmp_path / 'npz' / 'particles00000005.npz'))
     sel = part['uz'] > 0.05
     assert sel.sum() > 0 and len(p['particles/electrons/position/x']) == sel.sum()
     order_ref = np.lexsort((part['z'][sel], part['x'][sel]))
     order_got = np.lexsort((p['particles/electrons/position/z'], p['particles/electrons/position/x']))
-    for key, k in (('position/x', 'x'), ('position/z', 'z'), ('momentum/z', 'uz'), ('weighting', 'w')):
-        assert_close(p['particles/electrons/' + key][order_got], part[k][sel][order_ref], 1e-14, 'diag ' + k)
+    for key, k, unit in (('position/x', 'x', 1.), ('position/z', 'z', 1.), ('momentum/z', 'uz', m_e * c),
+                         ('weighting', 'w', 1.)):
+        assert_close(p['particles/electrons/' + key][order_got] / unit, part[k][sel][order_ref], 1e-14, 'diag ' + k)
     assert_close(p['particles/electrons/gamma'][order_got], 1. / part['inv_gamma'][sel][order_ref], 1e-14, 'gamma')
 
 
@@ -150,3 +154,57 @@ def test_tracked_ids_follow_the_particles(fused):
     o, ro = np.argsort(ids), np.argsort(g['id_out'])
     for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w'):
         assert_close(np.asarray(getattr(sp, k))[o], g['out_' + k][ro], 1e-10, 'tracked ' + k)
+
+
+def _namespace():
+    import types
+    from fbpic_b200 import Simulation
+    from fbpic_b200 import openpmd_diag as d
+    from fbpic_b200.lpa_utils.laser import add_laser_pulse, GaussianLaser
+    from fbpic_b200.lpa_utils.boosted_frame import BoostConverter
+    return types.SimpleNamespace(Simulation=Simulation, FieldDiagnostic=d.FieldDiagnostic,
+                                 ParticleDiagnostic=d.ParticleDiagnostic,
+                                 ParticleChargeDensityDiagnostic=d.ParticleChargeDensityDiagnostic,
+                                 BackTransformedFieldDiagnostic=d.BackTransformedFieldDiagnostic,
+                                 set_periodic_checkpoint=d.set_periodic_checkpoint, add_laser_pulse=add_laser_pulse,
+                                 GaussianLaser=GaussianLaser, BoostConverter=BoostConverter)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+def test_diagnostic_trees_vs_reference_golden(fused, tmp_path):
+    """Field, particle (all records / selection; tracked ids), per-species charge density and checkpoint output of
+    the same 5-cycle run, file by file and path by path against what the reference wrote: same groups, datasets,
+    shapes, dtypes and openPMD attributes; data within 1e-9 of the scale of its record (particles matched by id
+    resp. position)."""
+    import diag_cases
+    from conftest import load_golden
+    g = load_golden('diags_tree')
+    ns = _namespace()
+    sim, elec, ions = diag_cases.build_diag_sim(ns, fused=fused)
+    dirs = diag_cases.attach_diags(ns, sim, elec, ions, str(tmp_path))
+    np.random.seed(24)
+    sim.step(diag_cases.DIAG_STEPS)
+    for d, tag in zip(dirs, diag_cases.DIAG_DIRS):
+        ref, got = diag_cases.golden_files(g, tag), diag_cases.written_files(d)
+        assert sorted(ref) == sorted(got), (tag, sorted(ref), sorted(got))
+        for name in ref:
+            diag_cases.compare_trees(got[name], ref[name], 1e-9, '%s/%s' % (tag, name))
+
+
+@pytest.mark.parametrize('fused', [False, True])
+def test_lab_frame_snapshots_vs_reference_golden(fused, tmp_path):
+    """BackTransformedFieldDiagnostic: 4 lab-frame snapshots of E, B, J, rho collected slice by slice during 40
+    cycles of a boosted-frame run with a moving window (slice extraction on the device, Lorentz transformation and
+    placement in the lab grid on the host), against the files of the reference."""
+    import diag_cases
+    from conftest import load_golden
+    g = load_golden('diags_lab_tree')
+    ns = _namespace()
+    sim, gamma_boost = diag_cases.build_lab_diag_sim(ns, fused=fused)
+    d = diag_cases.attach_lab_diag(ns, sim, gamma_boost, str(tmp_path))
+    np.random.seed(30)
+    sim.step(diag_cases.LAB_DIAG_STEPS)
+    ref, got = diag_cases.golden_files(g, 'lab'), diag_cases.written_files(d)
+    assert sorted(ref) == sorted(got) and len(ref) == 4
+    for name in ref:
+        diag_cases.compare_trees(got[name], ref[name], 1e-8, 'lab/' + name)

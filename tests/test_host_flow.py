@@ -159,6 +159,7 @@ def test_ext_kernel_tests_flow(fake):
     k.test_correct_divE()
     k.test_antenna_helpers()
     k.test_push_p_after_plane()
+    k.test_extract_slice(3)
     k.test_external_field_jit()
 
 
@@ -281,3 +282,35 @@ def test_bench_flow(fake, monkeypatch, capsys):
 @pytest.mark.parametrize('tag', ['lab', 'boost'])
 def test_bunch_injection_plane_flow(fake, tag, fused):
     test_gpu_w3_bunch.test_bunch_injection_plane_vs_reference_golden(tag, fused)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+def test_diagnostic_trees_flow(fake, fused, tmp_path):
+    test_gpu_w8_diags.test_diagnostic_trees_vs_reference_golden(fused, tmp_path)
+
+
+@pytest.mark.parametrize('fused', [False, True])
+def test_lab_frame_snapshots_flow(fake, fused, tmp_path):
+    test_gpu_w8_diags.test_lab_frame_snapshots_vs_reference_golden(fused, tmp_path)
+
+
+@pytest.fixture
+def shim_h5py():
+    """`import h5py` resolves to the API stand-in of oracle/ref_shim for one test: the diagnostics then take their
+    h5py branch (fbpic_b200/openpmd_store.py) and write `.h5` containers."""
+    path = os.path.join(ROOT, 'oracle', 'ref_shim')
+    sys.modules.pop('h5py', None)
+    sys.path.insert(0, path)
+    yield
+    sys.path.remove(path)
+    sys.modules.pop('h5py', None)
+
+
+def test_diagnostics_through_the_h5py_api(fake, shim_h5py, tmp_path):
+    """Same comparisons with the reference's trees, the files written and read back through the h5py calls."""
+    import h5py
+    assert h5py.__version__.endswith('shim')
+    test_gpu_w8_diags.test_diagnostic_trees_vs_reference_golden(True, tmp_path / 'a')
+    assert sorted(os.listdir(str(tmp_path / 'a' / 'all' / 'hdf5'))) == ['data00000000.h5', 'data00000004.h5']
+    test_gpu_w8_diags.test_lab_frame_snapshots_vs_reference_golden(True, tmp_path / 'b')
+    test_gpu_w8_diags.test_restart_from_checkpoint_continues_the_run(True, False, tmp_path / 'c')

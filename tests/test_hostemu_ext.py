@@ -159,3 +159,32 @@ def test_emu_push_p_after_plane(emu):
         assert np.array_equal(g[keep], a[keep]), name
         assert_close(g, w, 1e-14, name)
     assert 0 < keep.sum() < n
+
+
+def _slice_reference(grids, Nr_out, iz, Sz):
+    """extract_slice_cpu + get_dataset (boosted_field_diag.py:604-684): Sz * F[iz] + (1 - Sz) * F[iz + 1], modes m > 0
+    doubled, real and imaginary parts as separate rows"""
+    Nm = len(grids)
+    out = np.empty((10, 2 * Nm - 1, Nr_out))
+    for k in range(10):
+        for m in range(Nm):
+            a = grids[m][k] * (2. if m else 1.)
+            row = Sz * a[iz, :Nr_out] + (1. - Sz) * a[iz + 1, :Nr_out]
+            if m == 0:
+                out[k, 0] = row.real
+            else:
+                out[k, 2 * m - 1], out[k, 2 * m] = row.real, row.imag
+    return out
+
+
+@pytest.mark.parametrize('Nm', [1, 3])
+def test_emu_extract_slice(emu, Nm):
+    rng = np.random.default_rng(31)
+    Nz, Nr, Nr_out, iz, Sz = 9, 150, 141, 6, 0.3125
+    grids = [[_cplx(rng, (Nz, Nr)) for _ in range(10)] for _ in range(Nm)]
+    got = np.full((10, 2 * Nm - 1, Nr_out), np.nan)
+    for m in range(Nm):
+        ptrs = (ctypes.c_void_p * 10)(*[g.ctypes.data for g in grids[m]])
+        emu.emu_extract_slice(ptrs, m, Nm, Nz, Nr, Nr_out, iz, ctypes.c_double(Sz), _p(got))
+    want = _slice_reference(grids, Nr_out, iz, Sz)
+    assert np.array_equal(got, want)

@@ -268,7 +268,7 @@ def run_diag_case(tol):
     """Field / particle diagnostics of a sharded run (gathered over the ranks, written by rank 0) against those of
     the single-domain run: same files (fbpic_b200/diags.py; gathering rules of field_diag.py:192-212)."""
     import tempfile
-    from fbpic_b200.diags import FieldDiagnostic, ParticleDiagnostic
+    from fbpic_b200.diags import FieldDiagnostic, ParticleDiagnostic, BackTransformedFieldDiagnostic
     rank, size = dist.get_rank(), dist.get_world_size()
     nzr = int(os.environ.get('MGPU_NZ_PER_RANK', '96'))
     Nz, Nr, Nm, zmax, rmax, n_e, n_order = nzr * size, 16, 2, 0.2e-6 * nzr * size, 8.e-6, 2.e24, 8
@@ -287,6 +287,13 @@ def run_diag_case(tol):
         sim.diags = [FieldDiagnostic(period=3, fldobject=sim.fld, comm=sim.comm, fieldtypes=['E', 'B', 'rho'], write_dir=d),
                      ParticleDiagnostic(period=3, species={'e': sp}, comm=sim.comm, select={'uz': [0.05, None]},
                                         write_dir=d)]
+        # lab-frame slicing (gamma = 2) of the same data: the plane of snapshot 1 starts 2 cells right of the middle
+        # of the box and moves left by 1.15 cells per cycle, i.e. across the boundary between the slabs of a 2-rank run
+        gamma, beta = 2., np.sqrt(0.75)
+        t_lab = (0.5 * zmax + 2.2 * zmax / Nz) * gamma * beta / c
+        sim.diags.append(BackTransformedFieldDiagnostic(0., 2 * gamma * zmax, 0., t_lab, 2, gamma, 3, sim.fld,
+                                                        comm=sim.comm, fieldtypes=['E', 'B', 'rho'],
+                                                        write_dir=os.path.join(d, 'lab')))
         sim.step(5, correct_currents=False)
         sim.step(1, correct_currents=False)      # a new call starts with a particle exchange: migration happens
 
@@ -315,8 +322,9 @@ def run_diag_case(tol):
         ref = Simulation(Nz, zmax, Nr, rmax, Nm, dt, use_all_mpi_ranks=False, n_guard=sim.comm.n_guard, **kw)
         run(ref, -1., 1.e9, dirs[1])
         for it in (0, 3):
-            a = np.load(os.path.join(dirs[0], 'npz', 'fields%08d.npz' % it))
-            b = np.load(os.path.join(dirs[1], 'npz', 'fields%08d.npz' % it))
+            from fbpic_b200.diags import read_diag
+            a = pa = read_diag(dirs[0], it)
+            b = pb = read_diag(dirs[1], it)
             for grp in ('E', 'B'):
                 scale = max(np.abs(b['fields/%s/%s' % (grp, k)]).max() for k in 'rtz') + 1e-300
                 for k in 'rtz':
@@ -327,8 +335,6 @@ def run_diag_case(tol):
             if not np.abs(a['fields/rho'] - b['fields/rho']).max() <= tol * np.abs(b['fields/rho']).max():
                 ok = False
                 print('DIAG MISMATCH rho', it)
-            pa = np.load(os.path.join(dirs[0], 'npz', 'particles%08d.npz' % it))
-            pb = np.load(os.path.join(dirs[1], 'npz', 'particles%08d.npz' % it))
             # (the two runs wrap / migrate their particles at different iterations: compare modulo the box length)
             za, zb = np.sort(pa['particles/e/position/z'] % zmax), np.sort(pb['particles/e/position/z'] % zmax)
             if za.shape != zb.shape or (len(za) and np.abs(za - zb).max() > 1e-9 * zmax):
@@ -336,6 +342,18 @@ def run_diag_case(tol):
                 print('DIAG MISMATCH particles', it, za.shape, zb.shape, np.abs(za - zb).max() if za.shape == zb.shape else '',
                       za.min(), zb.min(), za.max(), zb.max())
         print('diag: selected particles at iteration 3:', len(za))
+        a, b = read_diag(os.path.join(dirs[0], 'lab'), 1), read_diag(os.path.join(dirs[1], 'lab'), 1)
+        filled = np.flatnonzero(np.abs(b['fields/E/z']).sum(axis=(0, 1)))
+        print('diag: lab-frame snapshot, filled columns', filled)
+        if len(filled) < 3:
+            ok = False
+            print('DIAG MISMATCH: lab-frame snapshot holds %d slices' % len(filled))
+        for key in [k for k in b if k.startswith('fields/') and '@' not in k]:
+            record = key.rsplit('/', 1)[0] if key[-2:] in ('/r', '/t', '/z') else key
+            scale = max(np.abs(b[k]).max() for k in b if '@' not in k and (k == record or k.startswith(record + '/')))
+            if a[key].shape != b[key].shape or not np.abs(a[key] - b[key]).max() <= tol * scale or scale == 0:
+                ok = False
+                print('DIAG MISMATCH lab', key, np.abs(a[key] - b[key]).max(), scale)
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, src=0)
     dist.barrier()
