@@ -14,7 +14,8 @@ from fbpic_b200.lpa_utils.laser import add_laser_pulse
 from fbpic_b200.lpa_utils.laser.laser_profiles import GaussianLaser
 from fbpic_b200.lpa_utils.bunch import add_particle_bunch
 from fbpic_b200.lpa_utils.boosted_frame import BoostConverter
-from fbpic_b200.diags import FieldDiagnostic, ParticleDiagnostic
+from fbpic_b200.openpmd_diag import (FieldDiagnostic, ParticleDiagnostic, BackTransformedFieldDiagnostic,
+                                     BackTransformedParticleDiagnostic)
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--steps', type=int, default=None, help='default: the whole interaction')
@@ -54,9 +55,20 @@ add_laser_pulse(sim, GaussianLaser(2., 50.e-6, 16.e-15, -10.e-6, lambda0=0.8e-6,
 v_window_boosted, = boost.velocity([v_window])
 sim.set_moving_window(v=v_window_boosted)
 T_interact = boost.interaction_time(L_plasma, zmax - zmin, v_window)
-sim.diags = [FieldDiagnostic(dt_period=T_interact / 15, fldobject=sim.fld, comm=sim.comm, write_dir=args.out),
+N_lab_diag = 10 + 1
+dt_lab_diag_period = (L_plasma + (zmax - zmin)) / v_window / (N_lab_diag - 1)
+lab_dir = args.out.rstrip('/') + '_lab'
+sim.diags = [  # in the boosted frame
+             FieldDiagnostic(dt_period=T_interact / 15, fldobject=sim.fld, comm=sim.comm, write_dir=args.out),
              ParticleDiagnostic(dt_period=T_interact / 15, species={'electrons': elec, 'bunch': bunch}, comm=sim.comm,
-                                write_dir=args.out)]
+                                write_dir=args.out),
+             # in the lab frame (back-transformed), written every 50 cycles
+             BackTransformedFieldDiagnostic(zmin, zmax, v_window, dt_lab_diag_period, N_lab_diag, boost.gamma0,
+                                            fieldtypes=['rho', 'E', 'B'], period=50, fldobject=sim.fld, comm=sim.comm,
+                                            write_dir=lab_dir),
+             BackTransformedParticleDiagnostic(zmin, zmax, v_window, dt_lab_diag_period, N_lab_diag, boost.gamma0, 50,
+                                               sim.fld, select={'uz': [0., None]}, species={'bunch': bunch},
+                                               comm=sim.comm, write_dir=lab_dir)]
 N_step = args.steps or int(T_interact / sim.dt)
 sim.step(N_step)
 if sim.comm.rank == 0:

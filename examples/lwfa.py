@@ -11,7 +11,7 @@ from scipy.constants import c, e, m_e
 from fbpic_b200 import Simulation
 from fbpic_b200.lpa_utils.laser import add_laser_pulse
 from fbpic_b200.lpa_utils.laser.laser_profiles import GaussianLaser
-from fbpic_b200.diags import FieldDiagnostic, ParticleDiagnostic, set_periodic_checkpoint
+from fbpic_b200.openpmd_diag import FieldDiagnostic, ParticleDiagnostic, set_periodic_checkpoint
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--steps', type=int, default=None, help='default: one window length + 50 microns of plasma')

@@ -131,6 +131,8 @@ _SIGNATURES = {
     'b2_push_p_after_plane': [P, c_int64, P, c_double, P, P, P, P, P, P, P, P, P, P, c_double, c_double, c_double, P],
     'b2_antenna_particles': [P, c_int64, P, P, P, P, P, P, P, c_double, P, P, P, P, P, P],
     'b2_axpy': [P, c_int64, c_double, P, P, P],
+    'b2_select_crossing': [P, c_int64, P, P, P, c_double, c_double, c_double, c_double, c_int64, P, P,
+                           ctypes.POINTER(c_int64), P],
     'b2_extract_slice': [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_double, P, P],
     'b2_external_field_compile': [ctypes.c_char_p, ctypes.POINTER(P)],
     'b2_external_field_cubin_size': [P, ctypes.POINTER(c_size_t)],

@@ -119,6 +119,24 @@ int b2_extract_slice(b2_ctx *ctx, const void *const *fields10, int m, int Nm, in
     return 0;
 }
 
+int b2_select_crossing(b2_ctx *ctx, int64_t n, const double *z, const double *uz, const double *inv_gamma,
+                       double c_light, double dt, double z_curr, double z_prev, int64_t cap, int64_t *d_idx,
+                       int64_t *d_count, int64_t *h_count, void *stream) {
+    if (!d_count || !h_count || (cap > 0 && !d_idx))
+        return b2_fail(-3, "b2_select_crossing: missing buffer", __FILE__, __LINE__);
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    B2_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), s));
+    if (n > 0) {
+        b2ext::k_select_crossing<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+            (long long)n, z, uz, inv_gamma, c_light, dt, z_curr, z_prev, (long long)cap, (long long *)d_idx,
+            (unsigned long long *)d_count);
+        B2_LAUNCHED();
+    }
+    B2_CUDA(cudaMemcpyAsync(h_count, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 }  // extern "C"
 
 // =================================================================================================

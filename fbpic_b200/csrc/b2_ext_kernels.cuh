@@ -222,4 +222,24 @@ __global__ void k_extract_slice(SliceFields F, int m, int n_rows, int Nr, int Nr
     if (m > 0) out[Nr_out] = __dadd_rn(__dmul_rn(a, lo.y), __dmul_rn(b, hi.y));
 }
 
+// ParticleCatcher.get_particle_slice (fbpic/openpmd_diag/boosted_particle_diag.py:598-629): the particles that
+// crossed the output plane of a lab-frame snapshot during the last cycle.  The plane moved from z_prev to z_curr, a
+// particle from z - uz inv_gamma c dt (rounded like the NumPy expression, left to right) to z.  The indices of the
+// selected particles are appended to idx (any order; the caller sorts them); count keeps counting beyond cap so that
+// the caller can retry with a larger buffer.  The reference downloads a slab of particles found through the cell
+// prefix sums (which needs a sorted species) and selects on the host.
+__global__ void k_select_crossing(long long n, const double *__restrict__ z, const double *__restrict__ uz,
+                                  const double *__restrict__ inv_gamma, double c_light, double dt, double z_curr,
+                                  double z_prev, long long cap, long long *__restrict__ idx,
+                                  unsigned long long *__restrict__ count) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double zc = z[i];
+    const double zp = __dsub_rn(zc, __dmul_rn(__dmul_rn(__dmul_rn(uz[i], inv_gamma[i]), c_light), dt));
+    if ((zc >= z_curr && zp <= z_prev) || (zc <= z_curr && zp >= z_prev)) {
+        const unsigned long long pos = atomicAdd(count, 1ULL);
+        if ((long long)pos < cap) idx[pos] = i;
+    }
+}
+
 }  // namespace b2ext

@@ -569,6 +569,197 @@ class BackTransformedFieldDiagnostic(FieldDiagnostic):
 BoostedFieldDiagnostic = BackTransformedFieldDiagnostic
 
 
+class ParticleCatcher(object):
+    """Particles that crossed the plane of a lab-frame snapshot during the last cycle, moved onto the plane and
+    Lorentz-transformed (boosted_particle_diag.py:431-760).  The crossing test runs on the device over the resident
+    particle arrays (b2_select_crossing); only the selected particles are gathered (b2_permute) and read back.  The
+    reference downloads the whole slab of cells around the plane and selects on the host, which needs a sorted
+    species."""
+    ATTRS = ('x', 'y', 'z', 'ux', 'uy', 'uz', 'w', 'inv_gamma')
+
+    def __init__(self, gamma_boost, beta_boost, fldobject):
+        self.gamma_boost, self.beta_boost, self.fld, self.dt = gamma_boost, beta_boost, fldobject, fldobject.dt
+        self._idx = self._count = self._packed = None
+
+    def extract_slice(self, species, current_z_boost, previous_z_boost, t, select=None):
+        data = self.get_particle_slice(species, current_z_boost, previous_z_boost)
+        data = self.interpolate_particles_to_lab_frame(data, current_z_boost, t)
+        if select is not None:
+            data = self.apply_selection(select, data)
+        if species.m > 0:                          # openPMD: momenta in kg m/s
+            for k in ('ux', 'uy', 'uz'):
+                data[k] = data[k] * (species.m * c)
+        return data
+
+    def get_particle_slice(self, species, z_curr, z_prev):
+        """{'x', ..., 'inv_gamma' (, 'id')} of the particles with z on one side of the plane now and on the other
+        side one cycle ago"""
+        n = species.Ntot
+        if not isinstance(species.z, DeviceArray):            # between step() calls: host arrays
+            z, uz, ig = (np.asarray(getattr(species, k))[:n] for k in ('z', 'uz', 'inv_gamma'))
+            z_old = z - uz * ig * c * self.dt
+            keep = np.flatnonzero(((z >= z_curr) & (z_old <= z_prev)) | ((z <= z_curr) & (z_old >= z_prev)))
+            out = {k: np.take(np.asarray(getattr(species, k))[:n], keep) for k in self.ATTRS}
+            if species.tracker is not None:
+                out['id'] = np.take(np.asarray(species.tracker.id)[:n], keep)
+            return out
+        import ctypes
+        ctx = _lib.context().handle
+        if self._count is None:
+            self._count = DeviceArray(1, np.int64)
+        cap = max(4096, n // 32) if self._idx is None else self._idx.size
+        found = ctypes.c_int64(0)
+        while True:
+            if self._idx is None or self._idx.size < cap:
+                self._idx = DeviceArray(cap, np.int64)
+            call.b2_select_crossing(ctx, n, species.z.ptr, species.uz.ptr, species.inv_gamma.ptr, c, self.dt, z_curr,
+                                    z_prev, self._idx.size, self._idx.ptr, self._count.ptr, ctypes.byref(found), None)
+            if found.value <= self._idx.size:
+                break
+            cap = int(found.value)                 # the buffer was too small: the count is exact, run again
+        k = int(found.value)
+        tracked = species.tracker is not None
+        if k == 0:
+            out = {name: np.zeros(0) for name in self.ATTRS}
+            if tracked:
+                out['id'] = np.zeros(0, dtype=np.uint64)
+            return out
+        idx = self._idx.view((k,))
+        idx.set(np.sort(idx.get()))                # particle-array order, whatever order the atomics produced
+        rows = len(self.ATTRS) + (1 if tracked else 0)
+        if self._packed is None or self._packed.size < rows * k:
+            self._packed = DeviceArray(rows * k, np.float64)
+        src = [getattr(species, name) for name in self.ATTRS] + ([species.tracker.id] if tracked else [])
+        dst = [self._packed.ptr + 8 * k * r for r in range(rows)]
+        call.b2_permute(ctx, k, idx.ptr, rows, _lib.ptr_array(src), _lib.ptr_array(dst), None)
+        packed = self._packed.view((rows, k)).get()
+        out = {name: packed[r] for r, name in enumerate(self.ATTRS)}
+        if tracked:
+            out['id'] = packed[rows - 1].view(np.uint64)
+        return out
+
+    def interpolate_particles_to_lab_frame(self, d, current_z_boost, t):
+        """Move every particle along its straight path to the time it met the plane (which travels at -c / beta in
+        the boosted frame), then z and uz to the lab frame (boosted_particle_diag.py:631-686)."""
+        ig = d.pop('inv_gamma')
+        v_z, v_plane = d['uz'] * ig * c, -c / self.beta_boost
+        t_cross = t - (current_z_boost - d['z']) / (v_plane - v_z)
+        shift = c * (t_cross - t) * ig
+        d['x'] = d['x'] + shift * d['ux']
+        d['y'] = d['y'] + shift * d['uy']
+        z = d['z'] + shift * d['uz']
+        d['z'] = self.gamma_boost * (z + self.beta_boost * c * t_cross)
+        d['uz'] = self.gamma_boost * d['uz'] + (1. / ig) * (self.beta_boost * self.gamma_boost)
+        return d
+
+    @staticmethod
+    def apply_selection(select, d):
+        keep = np.ones(len(d['w']), dtype=bool)
+        for q, (lo, hi) in select.items():
+            if lo is not None:
+                keep &= d[q] > lo
+            if hi is not None:
+                keep &= d[q] < hi
+        return {k: v[keep] for k, v in d.items()}
+
+
+class BackTransformedParticleDiagnostic(ParticleDiagnostic):
+    """Particles *in the lab frame* from a simulation in the boosted frame (boosted_particle_diag.py:26-429): every
+    cycle each snapshot collects the particles that its plane t_lab = const swept over; they are appended to the
+    datasets of the snapshot every `period` cycles.  "E", "B" and "gamma" are not available (as in the reference)."""
+    needs_gathered_fields = False
+
+    def __init__(self, zmin_lab, zmax_lab, v_lab, dt_snapshots_lab, Ntot_snapshots_lab, gamma_boost, period,
+                 fldobject, particle_data=["position", "momentum", "weighting"], select=None, write_dir=None,
+                 species={"electrons": None}, comm=None, t_min_snapshots_lab=0., t_max_snapshots_lab=np.inf):
+        if write_dir is None:
+            write_dir = 'lab_diags'
+        for q in particle_data:
+            if q not in ('position', 'momentum', 'weighting'):
+                raise ValueError("Invalid quantity for particle output: %s" % q)
+        ParticleDiagnostic.__init__(self, period, species, comm, particle_data, select, write_dir)
+        self.needs_gathered_fields = False
+        self.fld = fldobject
+        self.gamma_boost = gamma_boost
+        self.inv_gamma_boost = 1. / gamma_boost
+        self.beta_boost = np.sqrt(1. - self.inv_gamma_boost**2)
+        self.inv_beta_boost = 1. / self.beta_boost
+        self.snapshots = []
+        for i in range(Ntot_snapshots_lab):
+            t_lab = i * dt_snapshots_lab
+            if t_min_snapshots_lab <= t_lab < t_max_snapshots_lab:
+                snap = LabSnapshot(t_lab, zmin_lab + v_lab * t_lab, zmax_lab + v_lab * t_lab, self.write_dir, i,
+                                   fldobject, fldobject.interp[0].Nr)
+                snap.buffered_particles = {name: [] for name in self.species_names_list}
+                self.snapshots.append(snap)
+                self.create_file_empty_slice(snap.stem, i, t_lab, self.dt)
+        self.particle_catcher = ParticleCatcher(self.gamma_boost, self.beta_boost, self.fld)
+
+    def _paths(self, species):
+        """(key of the caught data, dataset path, dtype) of every array written for this species"""
+        out = []
+        for record in self._records(species):
+            for comp in _COMPONENTS[record]:
+                path = record if len(_COMPONENTS[record]) == 1 else '%s/%s' % (record, comp[-1])
+                out.append((comp, path, 'uint64' if comp == 'id' else 'f8'))
+        return out
+
+    def create_file_empty_slice(self, stem, iteration, time, dt):
+        f = self.open_file(stem)
+        if f is None:
+            return
+        self.setup_openpmd_file(f, iteration, time, dt)
+        for name in self.species_names_list:
+            species = self.species_dict[name]
+            grp = f.require_group('/data/%d/particles/%s/' % (iteration, name))
+            self.setup_openpmd_species_group(grp, species)
+            for comp, path, dtype in self._paths(species):
+                self.setup_openpmd_component(grp.require_dataset(path, (0,), maxshape=(None,), dtype=dtype))
+            for record in self._records(species):
+                self.setup_openpmd_species_record(grp[record], record)
+        f.close()
+
+    def write(self, iteration):
+        self.store_snapshot_slices(iteration)
+        if iteration % self.period == 0:
+            self.flush_to_disk()
+
+    def store_snapshot_slices(self, iteration):
+        g0 = self.fld.interp[0]
+        time = iteration * self.dt
+        for snap in self.snapshots:
+            snap.update_current_output_positions(time, self.inv_gamma_boost, self.inv_beta_boost)
+            prev_z_boost = (snap.t_lab * self.inv_gamma_boost - (time - self.dt)) * c * self.inv_beta_boost
+            if (g0.zmin <= snap.current_z_boost < g0.zmax) and (snap.zmin_lab <= snap.current_z_lab < snap.zmax_lab):
+                for name in self.species_names_list:
+                    snap.buffered_particles[name].append(self.particle_catcher.extract_slice(
+                        self.species_dict[name], snap.current_z_boost, prev_z_boost, time, self.select))
+
+    def flush_to_disk(self):
+        multi = self.comm is not None and self.comm.size > 1
+        for snap in self.snapshots:
+            for name in self.species_names_list:
+                species = self.species_dict[name]
+                caught = snap.buffered_particles[name]
+                data = {}
+                for comp, path, dtype in self._paths(species):
+                    a = np.concatenate([d[comp] for d in caught]) if caught else np.zeros(0, dtype=dtype)
+                    data[path] = self.comm.gather_ptcl_array(a) if multi else a
+                if self.rank == 0:
+                    f = self.open_file(snap.stem)
+                    grp = f['/data/%d/particles/%s' % (snap.iteration, name)]
+                    for path, a in data.items():
+                        dset = grp[path]
+                        start = dset.shape[0]
+                        dset.resize(start + len(a), axis=0)
+                        dset[start:] = a
+                    f.close()
+                snap.buffered_particles[name] = []
+
+
+BoostedParticleDiagnostic = BackTransformedParticleDiagnostic
+
+
 # ---------------------------------------------------------------------------
 # reading a diagnostic back
 # ---------------------------------------------------------------------------

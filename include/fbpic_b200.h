@@ -314,6 +314,14 @@ int b2_axpy(b2_ctx *ctx, int64_t n, double a, const double *d_x, double *d_y, vo
 /* back-transformed diagnostics: extract_slice_cuda (fbpic/openpmd_diag/boosted_field_diag.py:745-820).
  * d_fields10: host array of the 10 device grids Er, Et, Ez, Br, Bt, Bz, Jr, Jt, Jz, rho (complex [Nz, Nr]) of
  * mode m; d_slice: real [10][2 Nm - 1][Nr_out]; rows iz, iz + 1 weighted by Sz, 1 - Sz (x2 for m > 0). */
+/* lab-frame particle output: ParticleCatcher.get_particle_slice (fbpic/openpmd_diag/boosted_particle_diag.py:598-629).
+ * Appends to d_idx (capacity cap) the indices of the particles for which
+ *   (z >= z_curr and z_old <= z_prev) or (z <= z_curr and z_old >= z_prev),  z_old = z - uz inv_gamma c dt,
+ * in any order, and returns their number in *h_count (host; the call synchronises the stream).  A count above cap
+ * means that only cap indices were stored: call again with a larger buffer.  d_count: 8 bytes of device scratch. */
+int b2_select_crossing(b2_ctx *ctx, int64_t n, const double *d_z, const double *d_uz, const double *d_inv_gamma,
+                       double c_light, double dt, double z_curr, double z_prev, int64_t cap, int64_t *d_idx,
+                       int64_t *d_count, int64_t *h_count, void *stream);
 int b2_extract_slice(b2_ctx *ctx, const void *const *d_fields10, int m, int Nm, int Nz, int Nr, int Nr_out, int iz,
                      double Sz, double *d_slice, void *stream);
 /* external fields (ExternalField, fbpic/lpa_utils/external_fields.py:13-215): the reference turns the user's

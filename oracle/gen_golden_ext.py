@@ -444,13 +444,15 @@ def _diag_namespace():
     if not hasattr(np, 'string_'):          # gone from NumPy 2; the reference's writers use it for text attributes
         np.string_ = np.bytes_
     from fbpic.openpmd_diag import (FieldDiagnostic, ParticleDiagnostic, ParticleChargeDensityDiagnostic,
-                                    BackTransformedFieldDiagnostic, set_periodic_checkpoint)
+                                    BackTransformedFieldDiagnostic, BackTransformedParticleDiagnostic,
+                                    set_periodic_checkpoint)
     from fbpic.lpa_utils.laser import add_laser_pulse, GaussianLaser
     from fbpic.lpa_utils.boosted_frame import BoostConverter
     return types.SimpleNamespace(Simulation=Simulation, FieldDiagnostic=FieldDiagnostic,
                                  ParticleDiagnostic=ParticleDiagnostic,
                                  ParticleChargeDensityDiagnostic=ParticleChargeDensityDiagnostic,
                                  BackTransformedFieldDiagnostic=BackTransformedFieldDiagnostic,
+                                 BackTransformedParticleDiagnostic=BackTransformedParticleDiagnostic,
                                  set_periodic_checkpoint=set_periodic_checkpoint, add_laser_pulse=add_laser_pulse,
                                  GaussianLaser=GaussianLaser, BoostConverter=BoostConverter)
 
@@ -489,6 +491,7 @@ def gen_lab_diags():
     sim.step(diag_cases.LAB_DIAG_STEPS, show_progress=False)
     out = dict(nsteps=diag_cases.LAB_DIAG_STEPS)
     out.update(_harvest(d, 'lab'))
+    out.update(_harvest(os.path.join(d, 'selected'), 'labsel'))
     shutil.rmtree(tmp)
     save('diags_lab_tree', **out)
 

@@ -56,7 +56,9 @@ def build_lab_diag_sim(ns, **sim_kw):
     sim = ns.Simulation(Nz, zmax, Nr, rmax, Nm, dt_lab, zmin=zmin, n_order=-1, n_guard=12, n_damp={'z': 12, 'r': 4},
                         gamma_boost=gamma_boost, v_comoving=-0.9999 * c, use_galilean=False,
                         boundaries={'z': 'open', 'r': 'reflective'}, **sim_kw)
-    sim.add_new_species(q=-e, m=m_e, n=1.e24, p_zmin=0., p_zmax=400.e-6, p_rmax=10.e-6, p_nz=1, p_nr=2, p_nt=4)
+    elec = sim.add_new_species(q=-e, m=m_e, n=1.e24, p_zmin=-26.e-6, p_zmax=400.e-6, p_rmax=10.e-6, p_nz=1, p_nr=2,
+                               p_nt=4)
+    elec.track(sim.comm)
     ns.add_laser_pulse(sim, ns.GaussianLaser(1.5, 5.e-6, 12.e-15, -14.e-6, lambda0=3.2e-6), gamma_boost=gamma_boost)
     v_window, = boost.velocity([c])
     sim.set_moving_window(v=v_window)
@@ -67,10 +69,18 @@ LAB_DIAG_STEPS = 40
 
 
 def attach_lab_diag(ns, sim, gamma_boost, root):
-    """4 lab-frame snapshots every 20 fs in a window that follows the pulse; all of E, B, J, rho; flushed every 16
-    cycles."""
+    """4 lab-frame snapshots every 20 fs in a window that follows the pulse: all of E, B, J, rho and the electrons,
+    flushed every 16 cycles; a selection of the electrons in a second series, flushed every 8 cycles."""
     sim.diags = [ns.BackTransformedFieldDiagnostic(-32.e-6, 0., c, 20.e-15, 4, gamma_boost, 16, sim.fld, comm=sim.comm,
-                                                   fieldtypes=['E', 'B', 'J', 'rho'], write_dir=root)]
+                                                   fieldtypes=['E', 'B', 'J', 'rho'], write_dir=root),
+                 # the (tracked) plasma electrons in the same snapshot files, and a selection of them in other ones
+                 ns.BackTransformedParticleDiagnostic(-32.e-6, 0., c, 20.e-15, 4, gamma_boost, 16, sim.fld,
+                                                      species={'electrons': sim.ptcl[0]}, comm=sim.comm,
+                                                      write_dir=root),
+                 ns.BackTransformedParticleDiagnostic(-32.e-6, 0., c, 20.e-15, 4, gamma_boost, 8, sim.fld,
+                                                      select={'uz': [0.02, None], 'x': [0., None]},
+                                                      species={'electrons': sim.ptcl[0]}, comm=sim.comm,
+                                                      write_dir=os.path.join(root, 'selected'))]
     return root
 
 

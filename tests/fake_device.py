@@ -187,8 +187,9 @@ class FakeLib(object):
     def b2_permute(self, ctx, n, sorted_idx, n_arrays, src, dst, stream):
         perm = _arr(sorted_idx, n, np.int64) if _addr(sorted_idx) else self._perm
         assert perm is not None and len(perm) == n
+        span = int(perm.max()) + 1 if n else 0        # dst[i] = src[idx[i]]: a gather, the source may be longer
         for s, d in zip(_ptrs(src, n_arrays), _ptrs(dst, n_arrays)):
-            _arr(d, n)[:] = _arr(s, n)[perm]
+            _arr(d, n)[:] = _arr(s, span)[perm]
         return 0
 
     def _grids(self, grids, count, Nz, Nr):
@@ -587,6 +588,16 @@ class FakeLib(object):
     def b2_axpy(self, ctx, n, a, x, y, stream):
         return self.emu.emu_axpy(ctypes.c_longlong(n), ctypes.c_double(a), ctypes.c_void_p(_addr(x)),
                                  ctypes.c_void_p(_addr(y)))
+
+    def b2_select_crossing(self, ctx, n, z, uz, ig, c_light, dt, z_curr, z_prev, cap, idx, d_count, h_count, stream):
+        if not _addr(d_count):
+            return -3
+        D, V = ctypes.c_double, ctypes.c_void_p
+        rc = self.emu.emu_select_crossing(ctypes.c_longlong(n), V(_addr(z)), V(_addr(uz)), V(_addr(ig)), D(c_light),
+                                          D(dt), D(z_curr), D(z_prev), ctypes.c_longlong(cap), V(_addr(idx)),
+                                          V(_addr(d_count)))
+        h_count._obj.value = int(_arr(d_count, 1, np.int64)[0])
+        return rc
 
     def b2_extract_slice(self, ctx, fields10, m, Nm, Nz, Nr, Nr_out, iz, Sz, slice_, stream):
         if not (0 <= m < Nm and 0 < Nr_out <= Nr and 0 <= iz and iz + 1 < Nz):

@@ -24,6 +24,12 @@ static thread_local emu_dim3 blockIdx, threadIdx, blockDim, gridDim;
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
+// launches are sequential loops here: a plain read-modify-write
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
+    const unsigned long long old = *p;
+    *p = old + v;
+    return old;
+}
 
 #define EMU_LAUNCH(grid, block, kernel, ...)                                             \
     do {                                                                                 \

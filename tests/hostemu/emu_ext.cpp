@@ -76,6 +76,16 @@ int emu_axpy(long long n, double a, const double *x, double *y) {
     return 0;
 }
 
+int emu_select_crossing(long long n, const double *z, const double *uz, const double *inv_gamma, double c_light,
+                        double dt, double z_curr, double z_prev, long long cap, long long *idx,
+                        unsigned long long *count) {
+    *count = 0;
+    if (n > 0)
+        EMU_LAUNCH(emu_dim3((unsigned)((n + 255) / 256)), emu_dim3(256), b2ext::k_select_crossing, n, z, uz, inv_gamma,
+                   c_light, dt, z_curr, z_prev, cap, idx, count);
+    return 0;
+}
+
 int emu_extract_slice(const void *const *fields10, int m, int Nm, int Nz, int Nr, int Nr_out, int iz, double Sz,
                       double *slice) {
     b2ext::SliceFields F;

@@ -213,3 +213,32 @@ def test_extract_slice(Nm):
     with pytest.raises(B200Error):
         _lib.call.b2_extract_slice(_lib.context().handle, _lib.ptr_array(d), 0, Nm, Nz, Nr, Nr_out, Nz - 1, Sz, out.ptr,
                                    None)
+
+
+def test_select_crossing():
+    """b2_select_crossing (lab-frame particle diagnostics): the particles of the NumPy selection of the reference, in
+    any order; with a buffer that is too small the returned count is still exact."""
+    from fbpic_b200 import _lib
+    from fbpic_b200._lib import DeviceArray
+    from test_hostemu_ext import _crossing_case
+    n, z, uz, ig, c_light, dt, z_curr, z_prev, want = _crossing_case()
+    dz, duz, dig = _dev(z, uz, ig)
+    count = DeviceArray(1, np.int64)
+    for cap in (n, 7):
+        idx = DeviceArray(cap, np.int64)
+        found = ctypes.c_int64(-1)
+        _lib.call.b2_select_crossing(_lib.context().handle, n, dz.ptr, duz.ptr, dig.ptr, c_light, dt, z_curr, z_prev,
+                                     cap, idx.ptr, count.ptr, ctypes.byref(found), None)
+        assert found.value == len(want)
+        got = idx.get()
+        if cap >= len(want):
+            assert np.array_equal(np.sort(got[:len(want)]), want)
+        else:
+            assert np.all(np.isin(got, want))
+    # the gather of the selected particles: b2_permute with a short index list
+    idx = DeviceArray.from_numpy(want.astype(np.int64))
+    out = DeviceArray(2 * len(want), np.float64)
+    _lib.call.b2_permute(_lib.context().handle, len(want), idx.ptr, 2, _lib.ptr_array([dz, duz]),
+                         _lib.ptr_array([out.ptr, out.ptr + 8 * len(want)]), None)
+    got = out.get().reshape(2, -1)
+    assert np.array_equal(got[0], z[want]) and np.array_equal(got[1], uz[want])

@@ -166,6 +166,7 @@ def _namespace():
                                  ParticleDiagnostic=d.ParticleDiagnostic,
                                  ParticleChargeDensityDiagnostic=d.ParticleChargeDensityDiagnostic,
                                  BackTransformedFieldDiagnostic=d.BackTransformedFieldDiagnostic,
+                                 BackTransformedParticleDiagnostic=d.BackTransformedParticleDiagnostic,
                                  set_periodic_checkpoint=d.set_periodic_checkpoint, add_laser_pulse=add_laser_pulse,
                                  GaussianLaser=GaussianLaser, BoostConverter=BoostConverter)
 
@@ -193,9 +194,11 @@ def test_diagnostic_trees_vs_reference_golden(fused, tmp_path):
 
 @pytest.mark.parametrize('fused', [False, True])
 def test_lab_frame_snapshots_vs_reference_golden(fused, tmp_path):
-    """BackTransformedFieldDiagnostic: 4 lab-frame snapshots of E, B, J, rho collected slice by slice during 40
-    cycles of a boosted-frame run with a moving window (slice extraction on the device, Lorentz transformation and
-    placement in the lab grid on the host), against the files of the reference."""
+    """BackTransformedFieldDiagnostic / BackTransformedParticleDiagnostic: 4 lab-frame snapshots of E, B, J, rho and
+    of the (tracked) electrons, collected during 40 cycles of a boosted-frame run with a moving window -- the grid
+    slice and the particles crossing the plane of each snapshot are extracted on the device, the Lorentz
+    transformation and the placement in the lab-frame files happen on the host -- against the files of the
+    reference; a second particle series with a selection on the lab-frame quantities."""
     import diag_cases
     from conftest import load_golden
     g = load_golden('diags_lab_tree')
@@ -206,5 +209,15 @@ def test_lab_frame_snapshots_vs_reference_golden(fused, tmp_path):
     sim.step(diag_cases.LAB_DIAG_STEPS)
     ref, got = diag_cases.golden_files(g, 'lab'), diag_cases.written_files(d)
     assert sorted(ref) == sorted(got) and len(ref) == 4
+    caught = 0
     for name in ref:
         diag_cases.compare_trees(got[name], ref[name], 1e-8, 'lab/' + name)
+        caught += sum(len(v) for k, v in got[name].items() if k.endswith('/electrons/id'))
+    assert caught > 500
+    ref, got = diag_cases.golden_files(g, 'labsel'), diag_cases.written_files(str(tmp_path / 'selected'))
+    assert sorted(ref) == sorted(got) and len(ref) == 4
+    selected = 0
+    for name in ref:
+        diag_cases.compare_trees(got[name], ref[name], 1e-8, 'labsel/' + name)
+        selected += sum(len(v) for k, v in got[name].items() if k.endswith('/electrons/id'))
+    assert 0 < selected < caught

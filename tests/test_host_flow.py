@@ -160,6 +160,7 @@ def test_ext_kernel_tests_flow(fake):
     k.test_antenna_helpers()
     k.test_push_p_after_plane()
     k.test_extract_slice(3)
+    k.test_select_crossing()
     k.test_external_field_jit()
 
 
@@ -314,3 +315,24 @@ def test_diagnostics_through_the_h5py_api(fake, shim_h5py, tmp_path):
     assert sorted(os.listdir(str(tmp_path / 'a' / 'all' / 'hdf5'))) == ['data00000000.h5', 'data00000004.h5']
     test_gpu_w8_diags.test_lab_frame_snapshots_vs_reference_golden(True, tmp_path / 'b')
     test_gpu_w8_diags.test_restart_from_checkpoint_continues_the_run(True, False, tmp_path / 'c')
+
+
+@pytest.mark.parametrize('script', ['lwfa.py', 'boosted_frame.py'])
+def test_example_scripts_flow(fake, script, tmp_path, monkeypatch, capsys):
+    """The two example scripts (the reference's documented input scripts, full size) run a few cycles end to end --
+    laser set-up, bunch with space charge, antenna, moving window, boosted-frame and lab-frame diagnostics -- and
+    leave readable diagnostics."""
+    import runpy
+    import numpy as np
+    from fbpic_b200.diags import read_diag, list_iterations
+    out = str(tmp_path / 'diags')
+    monkeypatch.setattr(sys, 'argv', [script, '--steps', '3', '--out', out])
+    np.random.seed(0)
+    runpy.run_path(os.path.join(ROOT, 'examples', script), run_name='__main__')
+    assert list_iterations(out) == [0]
+    d = read_diag(out, 0)
+    assert d['fields/E/r'].ndim == 3 and 'particles/electrons/position/x' in d
+    if script == 'boosted_frame.py':
+        assert list_iterations(out + '_lab') == list(range(11))
+        lab = read_diag(out + '_lab', 0)
+        assert lab['fields/E/z'].shape[:2] == (3, 75) and 'particles/bunch/momentum/z' in lab

@@ -188,3 +188,33 @@ def test_emu_extract_slice(emu, Nm):
         emu.emu_extract_slice(ptrs, m, Nm, Nz, Nr, Nr_out, iz, ctypes.c_double(Sz), _p(got))
     want = _slice_reference(grids, Nr_out, iz, Sz)
     assert np.array_equal(got, want)
+
+
+def _crossing_case():
+    rng = np.random.default_rng(41)
+    n = 3000
+    z = rng.uniform(0., 1., n)
+    uz = rng.normal(size=n) * 2.
+    ig = 1. / np.sqrt(1. + uz**2 + rng.uniform(0., 1., n))
+    c_light, dt, z_curr, z_prev = 3., 0.01, 0.48, 0.52
+    z_old = z - uz * ig * c_light * dt
+    want = np.flatnonzero(((z >= z_curr) & (z_old <= z_prev)) | ((z <= z_curr) & (z_old >= z_prev)))
+    return n, z, uz, ig, c_light, dt, z_curr, z_prev, want
+
+
+def test_emu_select_crossing(emu):
+    """get_particle_slice (boosted_particle_diag.py:598-629): same particles as the NumPy selection; the count stays
+    exact when the index buffer is too small."""
+    n, z, uz, ig, c_light, dt, z_curr, z_prev, want = _crossing_case()
+    assert 20 < len(want) < n // 4
+    D = ctypes.c_double
+    for cap in (n, 7):
+        idx = np.full(max(cap, 1), -1, dtype=np.int64)
+        count = np.zeros(1, dtype=np.uint64)
+        emu.emu_select_crossing(ctypes.c_longlong(n), _p(z), _p(uz), _p(ig), D(c_light), D(dt), D(z_curr), D(z_prev),
+                                ctypes.c_longlong(cap), _p(idx), _p(count))
+        assert int(count[0]) == len(want)
+        if cap >= len(want):
+            assert np.array_equal(np.sort(idx[:len(want)]), want)
+        else:
+            assert np.all(np.isin(idx[:cap], want))

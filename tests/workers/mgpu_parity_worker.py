@@ -268,7 +268,8 @@ def run_diag_case(tol):
     """Field / particle diagnostics of a sharded run (gathered over the ranks, written by rank 0) against those of
     the single-domain run: same files (fbpic_b200/diags.py; gathering rules of field_diag.py:192-212)."""
     import tempfile
-    from fbpic_b200.diags import FieldDiagnostic, ParticleDiagnostic, BackTransformedFieldDiagnostic
+    from fbpic_b200.diags import (FieldDiagnostic, ParticleDiagnostic, BackTransformedFieldDiagnostic,
+                                  BackTransformedParticleDiagnostic)
     rank, size = dist.get_rank(), dist.get_world_size()
     nzr = int(os.environ.get('MGPU_NZ_PER_RANK', '96'))
     Nz, Nr, Nm, zmax, rmax, n_e, n_order = nzr * size, 16, 2, 0.2e-6 * nzr * size, 8.e-6, 2.e24, 8
@@ -294,6 +295,9 @@ def run_diag_case(tol):
         sim.diags.append(BackTransformedFieldDiagnostic(0., 2 * gamma * zmax, 0., t_lab, 2, gamma, 3, sim.fld,
                                                         comm=sim.comm, fieldtypes=['E', 'B', 'rho'],
                                                         write_dir=os.path.join(d, 'lab')))
+        sim.diags.append(BackTransformedParticleDiagnostic(0., 2 * gamma * zmax, 0., t_lab, 2, gamma, 3, sim.fld,
+                                                           species={'e': sp}, comm=sim.comm,
+                                                           write_dir=os.path.join(d, 'lab')))
         sim.step(5, correct_currents=False)
         sim.step(1, correct_currents=False)      # a new call starts with a particle exchange: migration happens
 
@@ -348,6 +352,20 @@ def run_diag_case(tol):
         if len(filled) < 3:
             ok = False
             print('DIAG MISMATCH: lab-frame snapshot holds %d slices' % len(filled))
+        # (the ids differ between the runs: rank r hands out r, r + size, ...; x and y do not change in this drift)
+        order = lambda t: np.lexsort((np.round(t['particles/e/position/y'] / 1.e-12),       # noqa: E731
+                                      np.round(t['particles/e/position/x'] / 1.e-12)))
+        ia, ib = order(a), order(b)
+        print('diag: lab-frame snapshot, particles caught', len(ia), len(ib))
+        if len(ib) < 50 or len(ia) != len(ib) or len(np.unique(a['particles/e/id'])) != len(ia):
+            ok = False
+            print('DIAG MISMATCH lab particle number / ids')
+        else:
+            for key, ref_scale in (('position/x', rmax), ('position/z', zmax), ('momentum/z', 9.1e-31 * c), ('weighting', 0.)):
+                va, vb = a['particles/e/' + key][ia], b['particles/e/' + key][ib]
+                if not np.abs(va - vb).max() <= 1e-9 * (ref_scale or np.abs(vb).max()):
+                    ok = False
+                    print('DIAG MISMATCH lab particles', key, np.abs(va - vb).max())
         for key in [k for k in b if k.startswith('fields/') and '@' not in k]:
             record = key.rsplit('/', 1)[0] if key[-2:] in ('/r', '/t', '/z') else key
             scale = max(np.abs(b[k]).max() for k in b if '@' not in k and (k == record or k.startswith(record + '/')))
