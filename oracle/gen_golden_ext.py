@@ -448,7 +448,9 @@ def _diag_namespace():
                                     set_periodic_checkpoint)
     from fbpic.lpa_utils.laser import add_laser_pulse, GaussianLaser
     from fbpic.lpa_utils.boosted_frame import BoostConverter
+    from fbpic.lpa_utils.bunch import add_elec_bunch_gaussian
     return types.SimpleNamespace(Simulation=Simulation, FieldDiagnostic=FieldDiagnostic,
+                                 add_elec_bunch_gaussian=add_elec_bunch_gaussian,
                                  ParticleDiagnostic=ParticleDiagnostic,
                                  ParticleChargeDensityDiagnostic=ParticleChargeDensityDiagnostic,
                                  BackTransformedFieldDiagnostic=BackTransformedFieldDiagnostic,
@@ -477,6 +479,21 @@ def gen_diags():
     save('diags_tree', **out)
 
 
+def gen_cpu_gpu_deposition(shape):
+    """The CPU arm of the reference's tests/test_cpu_gpu_deposition.py: its FieldDiagnostic files of rho and J."""
+    import shutil
+    import tempfile
+    ns = _diag_namespace()
+    import diag_cases
+    tmp = tempfile.mkdtemp()
+    sim = diag_cases.build_cpu_gpu_deposition(ns, shape, tmp, use_cuda=False, verbose_level=0)
+    sim.step(3, show_progress=False)
+    tree = _harvest(tmp, 'cpu')
+    shutil.rmtree(tmp)
+    # the data and the grid attributes are what the test compares; keep the fixture small
+    save('cpu_gpu_deposition_' + shape, **{k: v for k, v in tree.items() if '@' not in k or k.endswith(('@time', '@gridSpacing', '@gridGlobalOffset'))})
+
+
 def gen_lab_diags():
     """Lab-frame snapshots of a boosted-frame run written by the reference's BackTransformedFieldDiagnostic
     (fbpic/openpmd_diag/boosted_field_diag.py) for tests/diag_cases.py."""
@@ -498,6 +515,8 @@ def gen_lab_diags():
 
 GENERATORS = {
     'diags_tree': gen_diags,
+    'cpu_gpu_deposition_linear': lambda: gen_cpu_gpu_deposition('linear'),
+    'cpu_gpu_deposition_cubic': lambda: gen_cpu_gpu_deposition('cubic'),
     'diags_lab_tree': gen_lab_diags,
     'bunch_plane_lab': lambda: gen_bunch_plane('lab'),
     'bunch_plane_boost': lambda: gen_bunch_plane('boost', gamma_boost=3.),

@@ -24,6 +24,20 @@ def build_diag_sim(ns, **sim_kw):
     return sim, elec, ions
 
 
+def build_cpu_gpu_deposition(ns, particle_shape, root, **sim_kw):
+    """The reference's own CPU-vs-GPU parity test, as written (tests/test_cpu_gpu_deposition.py:31-84): a Gaussian
+    electron bunch (N = 2000, seed 0) deposits rho and J for 3 cycles; the comparison goes through the files of a
+    FieldDiagnostic with period 1."""
+    Nz, zmax, zmin, Nr, rmax, Nm = 100, 30.e-6, -10.e-6, 50, 20.e-6, 2
+    dt = (zmax - zmin) / Nz / c
+    sim = ns.Simulation(Nz, zmax, Nr, rmax, Nm, dt, zmin=zmin, particle_shape=particle_shape, **sim_kw)
+    sim.ptcl = []
+    np.random.seed(0)
+    ns.add_elec_bunch_gaussian(sim, 20.e-6, 10.e-6, 10.e-6, 10, 0., 10.e-12, 2000)
+    sim.diags = [ns.FieldDiagnostic(1, sim.fld, fieldtypes=['rho', 'J'], comm=sim.comm, write_dir=root)]
+    return sim
+
+
 DIAG_DIRS = ('all', 'sel', 'dens', 'chk')
 
 

@@ -162,12 +162,14 @@ def _namespace():
     from fbpic_b200 import openpmd_diag as d
     from fbpic_b200.lpa_utils.laser import add_laser_pulse, GaussianLaser
     from fbpic_b200.lpa_utils.boosted_frame import BoostConverter
+    from fbpic_b200.lpa_utils.bunch import add_elec_bunch_gaussian
     return types.SimpleNamespace(Simulation=Simulation, FieldDiagnostic=d.FieldDiagnostic,
                                  ParticleDiagnostic=d.ParticleDiagnostic,
                                  ParticleChargeDensityDiagnostic=d.ParticleChargeDensityDiagnostic,
                                  BackTransformedFieldDiagnostic=d.BackTransformedFieldDiagnostic,
                                  BackTransformedParticleDiagnostic=d.BackTransformedParticleDiagnostic,
                                  set_periodic_checkpoint=d.set_periodic_checkpoint, add_laser_pulse=add_laser_pulse,
+                                 add_elec_bunch_gaussian=add_elec_bunch_gaussian,
                                  GaussianLaser=GaussianLaser, BoostConverter=BoostConverter)
 
 
@@ -221,3 +223,31 @@ def test_lab_frame_snapshots_vs_reference_golden(fused, tmp_path):
         diag_cases.compare_trees(got[name], ref[name], 1e-8, 'labsel/' + name)
         selected += sum(len(v) for k, v in got[name].items() if k.endswith('/electrons/id'))
     assert 0 < selected < caught
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('shape', ['linear', 'cubic'])
+def test_cpu_gpu_deposition_as_written(shape, fused, tmp_path):
+    """The reference's own CPU-vs-GPU parity test (tests/test_cpu_gpu_deposition.py), as written: rho and J of a
+    Gaussian bunch after 0, 1, 2 cycles, compared through the FieldDiagnostic files with the reference's tolerance
+    1e-13 (max|F_cpu| + max|F_gpu|).  The CPU arm is the unmodified reference (fixture), the GPU arm is this
+    library; every thetaMode row of rho, Jr, Jt, Jz is compared (the reference looks at rho, Jx, Jz at theta = 0)."""
+    import diag_cases
+    from conftest import load_golden
+    g = load_golden('cpu_gpu_deposition_' + shape)
+    sim = diag_cases.build_cpu_gpu_deposition(_namespace(), shape, str(tmp_path), fused=fused)
+    sim.step(3)
+    cpu, gpu = diag_cases.golden_files(g, 'cpu'), diag_cases.written_files(str(tmp_path))
+    assert sorted(cpu) == sorted(gpu) == ['data%08d' % i for i in range(3)]
+    for name in cpu:
+        it = int(name[4:])
+        for record, comps in (('rho', ('',)), ('J', ('/r', '/t', '/z'))):
+            keys = ['/data/%d/fields/%s%s' % (it, record, co) for co in comps]
+            tol = 1.e-13 * (max(np.abs(cpu[name][k]).max() for k in keys) + max(np.abs(gpu[name][k]).max() for k in keys))
+            assert tol > 0
+            for k in keys:
+                assert cpu[name][k].shape == gpu[name][k].shape == (3, 50, 100)
+                err = np.abs(cpu[name][k] - gpu[name][k]).max()
+                assert err <= tol, '%s %s: %.3e > %.3e' % (name, k, err, tol)
+        assert np.allclose(gpu[name]['/data/%d/fields/rho@gridGlobalOffset' % it],
+                           cpu[name]['/data/%d/fields/rho@gridGlobalOffset' % it], rtol=1e-12, atol=1e-18)

@@ -336,3 +336,16 @@ def test_example_scripts_flow(fake, script, tmp_path, monkeypatch, capsys):
         assert list_iterations(out + '_lab') == list(range(11))
         lab = read_diag(out + '_lab', 0)
         assert lab['fields/E/z'].shape[:2] == (3, 75) and 'particles/bunch/momentum/z' in lab
+
+
+def test_smoke_entry_flow(fake, capsys):
+    """`__graft_entry__.smoke()` (the driver's round-end check) runs its comparison with the oracle"""
+    import __graft_entry__ as entry
+    entry.smoke()
+    assert 'smoke OK' in capsys.readouterr().out
+
+
+@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('shape', ['linear', 'cubic'])
+def test_cpu_gpu_deposition_flow(fake, shape, fused, tmp_path):
+    test_gpu_w8_diags.test_cpu_gpu_deposition_as_written(shape, fused, tmp_path)
