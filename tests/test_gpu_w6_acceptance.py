@@ -6,7 +6,8 @@ with the reference's own parameters and pass criteria (its test files cannot be 
   * tests/test_boosted.py -- numerical Cherenkov instability of a relativistically flowing plasma: the
     Galilean and comoving PSATD schemes are stable where the standard one is not;
   * tests/test_continuous_injection.py -- moving window + continuous injection reproduce the prescribed
-    density profile (lab frame with / without plasma at t = 0, boosted frame with a Cartesian dens_func).
+    density profile (lab frame with / without plasma at t = 0, boosted frame with a Cartesian dens_func);
+  * tests/test_boosted_particle_output.py -- every particle of a bunch is retrieved in every lab-frame snapshot.
 (tests/test_periodic_plasma_wave.py is restated in test_gpu_plasma_wave.py.)"""
 import numpy as np
 import pytest
@@ -284,3 +285,93 @@ def test_linear_wakefield(Nm):
     Er_an = m_e * c**2 * kp * a0**2 / (4. * e) * tr[np.newaxis, :] * long_r[:, np.newaxis]
     assert np.allclose(Ez_sim, Ez_an, atol=0.08 * abs(Ez_an).max())
     assert np.allclose(Er_sim, Er_an, atol=0.11 * abs(Er_an).max())
+
+
+# ------------------------------------------------------------------ test_boosted_particle_output.py
+def test_boosted_output(tmp_path, gamma_boost=10.):
+    """tests/test_boosted_particle_output.py:26-99 as written: a bunch of 3000 tracked particles in a boosted-frame
+    run (gamma = 10, moving window); every one of them must be found, once, in each of the 3 lab-frame snapshots
+    of the BackTransformedParticleDiagnostic."""
+    from fbpic_b200 import Simulation
+    from fbpic_b200.lpa_utils.boosted_frame import BoostConverter
+    from fbpic_b200.lpa_utils.bunch import add_particle_bunch_gaussian
+    from fbpic_b200.openpmd_diag import BackTransformedParticleDiagnostic
+    from fbpic_b200.diags import read_diag, list_iterations
+    Nz, zmax_lab, zmin_lab, Nr, rmax, Nm = 500, 0.e-6, -20.e-6, 10, 10.e-6, 2
+    N_steps, diag_period = 500, 20
+    dt_lab = (zmax_lab - zmin_lab) / Nz * 1. / c
+    T_sim_lab = N_steps * dt_lab
+    sim = Simulation(Nz, zmax_lab, Nr, rmax, Nm, dt_lab, 0, 0, 0, rmax, 1, 1, 4, n_e=0, zmin=zmin_lab,
+                     initialize_ions=False, gamma_boost=gamma_boost, v_comoving=-0.9999 * c,
+                     boundaries={'z': 'open', 'r': 'reflective'})
+    sim.set_moving_window(v=c)
+    sim.ptcl = []
+    N_particles = 3000
+    np.random.seed(0)
+    add_particle_bunch_gaussian(sim, q=-e, m=m_e, sig_r=1.e-6, sig_z=1.e-6, n_emit=0., gamma0=100, sig_gamma=0.,
+                                n_physical_particles=0., n_macroparticles=N_particles,
+                                zf=0.5 * (zmax_lab + zmin_lab), boost=BoostConverter(gamma_boost),
+                                initialize_self_field=False)
+    sim.ptcl[0].track(sim.comm)
+    out = str(tmp_path / 'lab_diags')
+    sim.diags = [BackTransformedParticleDiagnostic(zmin_lab, zmax_lab, v_lab=c, dt_snapshots_lab=T_sim_lab / 3.,
+                                                   Ntot_snapshots_lab=3, gamma_boost=gamma_boost, period=diag_period,
+                                                   fldobject=sim.fld, species={"bunch": sim.ptcl[0]}, comm=sim.comm,
+                                                   write_dir=out)]
+    sim.step(N_steps)
+    ref_pid = np.sort(sim.ptcl[0].tracker.id)
+    assert list_iterations(out) == [0, 1, 2]
+    for iteration in list_iterations(out):
+        pid = np.sort(read_diag(out, iteration)['particles/bunch/id'])
+        assert len(pid) == N_particles
+        assert np.all(ref_pid == pid)
+
+
+# ------------------------------------------------------------------ test_beam_focusing.py
+def _simulate_beam_focusing(z_injection_plane, write_dir):
+    """tests/test_beam_focusing.py:102-133"""
+    from fbpic_b200 import Simulation
+    from fbpic_b200.lpa_utils.bunch import add_elec_bunch_gaussian
+    from fbpic_b200.lpa_utils.boosted_frame import BoostConverter
+    from fbpic_b200.openpmd_diag import BackTransformedParticleDiagnostic
+    Nz, zmax, zmin, Nr, rmax, Nm = 100, 0.e-6, -20.e-6, 200, 20.e-6, 1
+    dt = (zmax - zmin) / Nz / c
+    gamma_boost, gamma0 = 15., 100.
+    z_focus, z0 = 2000.e-6, -10.e-6
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, zmin=zmin, gamma_boost=gamma_boost,
+                     boundaries={'z': 'open', 'r': 'reflective'}, v_comoving=c * np.sqrt(1. - 1. / gamma0**2))
+    sim.ptcl = []
+    add_elec_bunch_gaussian(sim, 1.e-6, 3.e-6, 0.1e-6, gamma0, 0., 200.e-12, 40000, tf=(z_focus - z0) / c, zf=z_focus,
+                            boost=BoostConverter(gamma_boost), z_injection_plane=z_injection_plane)
+    sim.set_moving_window(v=c)
+    sim.diags = [BackTransformedParticleDiagnostic(zmin, zmax, c, 2 * (z_focus - z0) / c / 20, 21, gamma_boost,
+                                                   period=100, fldobject=sim.fld, species={'bunch': sim.ptcl[0]},
+                                                   comm=sim.comm, write_dir=write_dir)]
+    sim.step(101)
+
+
+def test_beam_focusing(tmp_path):
+    """tests/test_beam_focusing.py:63-100 as written: a Gaussian bunch that should focus to sigma_r = 1 micron at
+    z = 2 mm, simulated in a boosted frame (gamma = 15).  Injected directly, its own space-charge field -- acting over
+    the long boosted-frame distance -- keeps it from focusing (off by more than 0.5 micron); injected through a plane
+    at the focus (ballistic motion before the plane, `z_injection_plane`) it reaches the nominal size within 0.05
+    micron.  The RMS radius is read from the lab-frame snapshots of the BackTransformedParticleDiagnostic."""
+    from fbpic_b200.diags import read_diag, list_iterations
+    np.random.seed(0)
+    _simulate_beam_focusing(None, str(tmp_path / 'direct'))
+    _simulate_beam_focusing(2000.e-6, str(tmp_path / 'through_plane'))
+
+    def rms_radius(d):
+        its = list_iterations(d)
+        t, r = [], []
+        for it in its:
+            f = read_diag(d, it)
+            x, w = f['particles/bunch/position/x'], f['particles/bunch/weighting']
+            t.append(float(f['time']))
+            r.append(np.sqrt(np.average(x**2, weights=w)) if len(x) else np.nan)
+        return np.array(t), np.array(r)
+    t1, r1 = rms_radius(str(tmp_path / 'direct'))
+    t2, r2 = rms_radius(str(tmp_path / 'through_plane'))
+    i = np.argmin(abs(c * t2 - 2000.e-6))
+    assert abs(r2[i] - 1.e-6) < 0.05e-6
+    assert abs(r1[i] - 1.e-6) > 0.5e-6

@@ -349,3 +349,13 @@ def test_smoke_entry_flow(fake, capsys):
 @pytest.mark.parametrize('shape', ['linear', 'cubic'])
 def test_cpu_gpu_deposition_flow(fake, shape, fused, tmp_path):
     test_gpu_w8_diags.test_cpu_gpu_deposition_as_written(shape, fused, tmp_path)
+
+
+def test_boosted_particle_output_flow(fake, tmp_path):
+    """the reference's tests/test_boosted_particle_output.py (500 cycles, 3000 tracked particles)"""
+    test_gpu_w6_acceptance.test_boosted_output(tmp_path)
+
+
+def test_beam_focusing_flow(fake, tmp_path):
+    """the reference's tests/test_beam_focusing.py (2 x 101 cycles, 40000 particles, Nr = 200)"""
+    test_gpu_w6_acceptance.test_beam_focusing(tmp_path)
