@@ -4,6 +4,7 @@ against golden outputs of the unmodified reference's CPU path (oracle/gen_golden
 unfused.  Tolerances as in test_gpu_step.py: fields 1e-9 of the field-group maximum, particles 1e-10."""
 import numpy as np
 import pytest
+from scipy.constants import c
 
 from conftest import load_golden, assert_close, group_scale
 
@@ -101,3 +102,66 @@ def test_cross_deposition_step_vs_reference_golden(tag, fused):
     assert abs(sim.fld.interp[0].zmin - float(g['zmin_end'])) <= 1e-12 * abs(float(g['zmax']))
     _check_particles(sp, g, 'cross ' + tag)
     _check_fields(sim, g, 'cross ' + tag, FIELDS)
+
+
+# ------------------------------------------------------------------ the reference's tests/test_pml.py
+def _pml_script(tmp_path, restart, **options):
+    """tests/unautomated/test_pml.py as written (one domain): a tightly focused pulse (w0 = 1.5 micron) in modes 0
+    and 1 diffracts into the radial PML over 40 microns; diagnostics every quarter, a checkpoint at half way."""
+    from fbpic_b200 import Simulation
+    from fbpic_b200.openpmd_diag import FieldDiagnostic, restart_from_checkpoint, set_periodic_checkpoint
+    from fbpic_b200.lpa_utils.laser import add_laser_pulse, GaussianLaser, LaguerreGaussLaser
+    Nz, zmin, zmax, Nr, Lr, Nm, n_order = 360, -6.e-6, 6.e-6, 50, 4.e-6, 2, 32
+    w0, lambda0, tau, a0, zf, z0, L_prop = 1.5e-6, 0.8e-6, 10.e-15, 1., 0., 0., 40.e-6
+    dt = (zmax - zmin) * 1. / c / Nz
+    sim = Simulation(Nz=Nz, zmax=zmax, Nr=Nr, rmax=Lr, Nm=Nm, dt=dt, n_order=n_order, zmin=zmin, **options)
+    profile0 = LaguerreGaussLaser(0, 1, 0.5 * a0, w0, tau, z0, zf=zf, lambda0=lambda0, theta_pol=0., theta0=0.) \
+        + LaguerreGaussLaser(0, 1, 0.5 * a0, w0, tau, z0, zf=zf, lambda0=lambda0, theta_pol=np.pi / 2,
+                             theta0=np.pi / 2)
+    profile1 = GaussianLaser(a0=a0, waist=w0, tau=tau, lambda0=lambda0, z0=z0, zf=zf)
+    if not restart:
+        add_laser_pulse(sim, profile0)
+        add_laser_pulse(sim, profile1)
+    else:
+        restart_from_checkpoint(sim, checkpoint_dir=str(tmp_path / 'checkpoints'))
+    N_step = int(round(L_prop / (c * dt)))
+    diag_period = int(round(N_step / 4))
+    sim.diags = [FieldDiagnostic(diag_period, sim.fld, fieldtypes=["E"], comm=sim.comm,
+                                 write_dir=str(tmp_path / 'diags'))]
+    set_periodic_checkpoint(sim, N_step // 2, checkpoint_dir=str(tmp_path / 'checkpoints'))
+    sim.step(N_step // 2 + 1)
+    return profile0, profile1
+
+
+@pytest.mark.parametrize('z_boundary,use_galilean', [('periodic', False), ('open', True)])
+def test_pml_laser_as_written(z_boundary, use_galilean, tmp_path):
+    """tests/test_pml.py::test_laser_periodic / test_laser_galilean (run_parallel + check_theory_pml) on one domain:
+    run to half way, restart from the checkpoint, run to the end; at every diagnostic E_x of modes 0 and 1 inside the
+    physical domain equals the analytic diffracting pulse within 9 % / 5 % of its maximum, i.e. nothing comes back
+    from the radial boundary."""
+    from fbpic_b200.diags import read_diag, list_iterations
+    options = dict(boundaries={'z': z_boundary, 'r': 'open'})
+    if use_galilean:
+        options.update(use_galilean=True, v_comoving=0.999 * c)
+    _pml_script(tmp_path, False, **options)
+    assert list_iterations(str(tmp_path / 'diags')) == [0, 300, 600]
+    profile0, profile1 = _pml_script(tmp_path, True, **options)
+    iterations = list_iterations(str(tmp_path / 'diags'))
+    assert iterations == [0, 300, 600, 900, 1200]
+    for iteration in iterations:
+        d = read_diag(str(tmp_path / 'diags'), iteration)
+        Er = d['fields/E/r']
+        t = float(d['time'])
+        r = d['dr'] * (0.5 + np.arange(Er.shape[1]))
+        z = d['zmin'] + d['dz'] * (0.5 + np.arange(Er.shape[2]))
+        rr, zz = np.meshgrid(r, z, indexing='ij')
+        # E_x of one mode in the half plane theta = 0 (what openPMD-viewer's get_field('E', 'x', m=m) returns for r > 0)
+        for m, E_sim, profile, rtol in ((0, Er[0], profile0, 9.e-2), (1, Er[1], profile1, 5.e-2)):
+            if z_boundary == 'periodic':
+                Lz = d['dz'] * Er.shape[2]
+                n_shift = np.floor(c * t / Lz)
+                E_th = profile.E_field(rr, 0, zz + (n_shift + 1) * Lz, t)[0] + profile.E_field(rr, 0, zz + n_shift * Lz, t)[0]
+            else:
+                E_th = profile.E_field(rr, 0, zz, t)[0]
+            relative_error = abs(E_sim - E_th).max() / abs(E_th).max()
+            assert relative_error < rtol, (iteration, m, relative_error)

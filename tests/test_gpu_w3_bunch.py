@@ -81,3 +81,46 @@ def test_bunch_injection_plane_vs_reference_golden(tag, fused):
             sc = group_scale(g, 'out_', 'rho' if k == 'rho' else k[0], Nm)
             assert_close(getattr(sim.fld.interp[m], k), g['out_%s_m%d' % (k, m)], 1e-9,
                          'bunch plane %s %s m%d' % (tag, k, m), scale=sc)
+
+
+def test_bunch_gaussian_as_written(tmp_path):
+    """tests/test_space_charge.py::test_bunch_gaussian with tests/unautomated/test_space_charge_gaussian.py, as
+    written (single domain): a symmetrized Gaussian bunch of 100000 particles (gamma = 15) with its space-charge
+    field, one cycle with moving window and diagnostics; the transverse E and B read from the diagnostics file agree
+    with the high-gamma theory of a Gaussian bunch within 10 % of the maximum, and the symmetrized bunch has zero
+    mean transverse position and momentum."""
+    from fbpic_b200 import Simulation
+    from fbpic_b200.openpmd_diag import FieldDiagnostic, ParticleDiagnostic
+    from fbpic_b200.lpa_utils.bunch import add_elec_bunch_gaussian
+    from fbpic_b200.diags import read_diag
+    from scipy.constants import c, epsilon_0
+    np.random.seed(0)
+    Nz, zmax, zmin, Nr, rmax, Nm, n_order = 400, 0.e-6, -40.e-6, 100, 100.e-6, 2, 32
+    sig_r, sig_z, n_emit, gamma0, sig_gamma, Q, N, tf, zf = 3.e-6, 3.e-6, 1.e-6, 15., 1., 10.e-12, 100000, 0, -20.e-6
+    dt = (zmax - zmin) / Nz / c
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, 0, 0, 0, 0, 2, 2, 4, 0., zmin=zmin, n_order=n_order,
+                     boundaries={'z': 'open', 'r': 'reflective'})
+    sim.set_moving_window(v=c)
+    sim.ptcl = []
+    elec = add_elec_bunch_gaussian(sim, sig_r, sig_z, n_emit, gamma0, sig_gamma, Q, N, tf, zf, symmetrize=True)
+    sim.diags = [FieldDiagnostic(10, sim.fld, comm=sim.comm, write_dir=str(tmp_path)),
+                 ParticleDiagnostic(10, species={'elec': elec}, comm=sim.comm, write_dir=str(tmp_path))]
+    sim.step(1)
+    d = read_diag(str(tmp_path), 0)
+    # E_x, B_y in the plane theta = 0 / pi, as openPMD-viewer's get_field(..., theta=0) assembles them from the
+    # thetaMode rows: x > 0: F_r(0) = m0 + Re m1; x < 0: -F_r(pi) = -(m0 - Re m1) (and B_y = B_t(0) resp. -B_t(pi))
+    Er, Bt = d['fields/E/r'], d['fields/B/t']
+    r = d['dr'] * (0.5 + np.arange(Nr))
+    z = d['zmin'] + d['dz'] * (0.5 + np.arange(Er.shape[2]))
+    rr, zz = np.meshgrid(r, z, indexing='ij')
+    Eth = -Q / (2 * np.pi)**1.5 / sig_z / epsilon_0 / rr * (1 - np.exp(-0.5 * rr**2 / sig_r**2)) * \
+        np.exp(-0.5 * (zz - zf)**2 / sig_z**2)
+    for sign in (1., -1.):
+        Ex = sign * (Er[0] + sign * Er[1])
+        By = sign * (Bt[0] + sign * Bt[1])
+        assert np.allclose(Ex, sign * Eth, atol=0.1 * np.abs(Eth).max())
+        assert np.allclose(By, sign * Eth / c, atol=0.1 * np.abs(Eth).max() / c)
+    assert np.abs(Er[0]).max() > 0.8 * np.abs(Eth).max()
+    for key in ('position/x', 'position/y', 'momentum/x', 'momentum/y'):
+        q = d['particles/elec/' + key]
+        assert len(q) == N and abs(q.mean()) < 1.e-10 * q.std()

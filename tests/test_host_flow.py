@@ -14,6 +14,10 @@ import pytest
 from conftest import ROOT
 
 import fake_device
+
+# flows that take minutes on the CPU stand-in: run once with B2_SLOW_FLOWS=1 (results recorded in DESIGN.md section 9)
+slow_flow = pytest.mark.skipif(os.environ.get('B2_SLOW_FLOWS') != '1',
+                               reason='minutes on the CPU stand-in; set B2_SLOW_FLOWS=1')
 import test_gpu_step
 import test_gpu_w0_ext_kernels
 import test_gpu_w1_pml_cross
@@ -356,6 +360,18 @@ def test_boosted_particle_output_flow(fake, tmp_path):
     test_gpu_w6_acceptance.test_boosted_output(tmp_path)
 
 
+@slow_flow
 def test_beam_focusing_flow(fake, tmp_path):
     """the reference's tests/test_beam_focusing.py (2 x 101 cycles, 40000 particles, Nr = 200)"""
     test_gpu_w6_acceptance.test_beam_focusing(tmp_path)
+
+
+def test_bunch_gaussian_as_written_flow(fake, tmp_path):
+    test_gpu_w3_bunch.test_bunch_gaussian_as_written(tmp_path)
+
+
+@slow_flow
+@pytest.mark.parametrize('z_boundary,use_galilean', [('periodic', False), ('open', True)])
+def test_pml_laser_as_written_flow(fake, z_boundary, use_galilean, tmp_path):
+    """the reference's tests/test_pml.py (2 x 601 cycles, fields only, restart in the middle)"""
+    test_gpu_w1_pml_cross.test_pml_laser_as_written(z_boundary, use_galilean, tmp_path)
