@@ -90,3 +90,117 @@ def test_mirror_vs_reference_golden(tag, fused):
         for k in ('Er', 'Et', 'Ez', 'Br', 'Bt', 'Bz'):
             assert_close(getattr(sim.fld.interp[m], k), g['out_%s_m%d' % (k, m)], 1e-9,
                          'mirror %s %s m%d' % (tag, k, m), scale=group_scale(g, 'out_', k[0], Nm))
+
+
+# ------------------------------------------------------------------ the reference's tests/test_laser_antenna.py
+@pytest.mark.parametrize('case', ['labframe', 'labframe_moving', 'boostedframe'])
+def test_antenna_as_written(case):
+    """tests/test_laser_antenna.py (test_antenna_labframe / _labframe_moving / _boostedframe) as written: a wide
+    Gaussian pulse (w0 = 128 micron, a0 = 1) emitted by the antenna over 420 cycles -- antenna at rest, antenna
+    moving at c emitting backwards, boosted frame (gamma = 10).  For the four transverse mode-1 components: the part
+    that carries no information vanishes (1e-6 of the maximum), the fitted amplitude equals a0 within 5 % and the
+    profile is the analytic Gaussian pulse within 3 % of the maximum."""
+    import numpy as np
+    from scipy.optimize import curve_fit
+    from scipy.constants import c, m_e, e
+    from fbpic_b200 import Simulation
+    from fbpic_b200.lpa_utils.laser import add_laser
+    from fbpic_b200.lpa_utils.boosted_frame import BoostConverter
+    gamma_b, z0_sign, v, forward_propagating = {'labframe': (None, -1., 0., True), 'labframe_moving': (None, 1., c, False),
+                                                'boostedframe': (10., -1., 0., True)}[case]
+    Nz, zmin, zmax, Nr, rmax, Nm = 800, -10.e-6, 10.e-6, 25, 400.e-6, 2
+    dt = (zmax - zmin) / Nz / c
+    w0, ctau, a0, zf, z0_antenna, Lprop = 128.e-6, 5.e-6, 1., 0.e-6, 0.e-6, 10.5e-6
+    z0 = z0_antenna + z0_sign * ctau
+    Ntot_step, N_show = int(Lprop / (c * dt)), 5
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, p_zmin=0, p_zmax=0, p_rmin=0, p_rmax=0, p_nz=2, p_nr=2, p_nt=2, n_e=0.,
+                     zmin=zmin, boundaries={'z': 'open', 'r': 'reflective'}, gamma_boost=gamma_b)
+    sim.ptcl = []
+    add_laser(sim, a0, w0, ctau, z0, zf=zf, method='antenna', z0_antenna=z0_antenna, v_antenna=v, gamma_boost=gamma_b,
+              fw_propagating=forward_propagating)
+    N_step = int(round(Ntot_step / N_show))
+    for it in range(N_show):
+        sim.step(N_step, show_progress=False)
+    sim.step(Ntot_step - N_show * N_step, show_progress=False)
+
+    def gaussian_laser(z, r, a0, z0_phase, z0_prop, ctau, lambda0):
+        k0 = 2 * np.pi / lambda0
+        E0 = a0 * m_e * c**2 * k0 / e
+        return E0 * np.exp(-r**2 / w0**2 - (z - z0_prop)**2 / ctau**2) * np.cos(k0 * (z - z0_phase))
+
+    g1 = sim.fld.interp[1]
+    Nz_half = int(g1.Nz / 2) + 2
+    cut = sim.comm.n_guard + sim.comm.nz_damp + sim.comm.n_inject
+    z, r = g1.z[Nz_half:-cut], g1.r
+    boost = BoostConverter(1. if gamma_b is None else gamma_b)
+    ctau_b, lambda0_b, Lprop_b, z0_b = boost.copropag_length([ctau, 0.8e-6, Lprop, z0])
+    if not forward_propagating:
+        Lprop_b = -Lprop_b
+    for fieldtype, info_in_real_part, factor in (('Er', True, 2.), ('Et', False, 2.), ('Br', False, 2. * c),
+                                                 ('Bt', True, 2. * c)):
+        field = factor * np.asarray(getattr(g1, fieldtype))[Nz_half:-cut]
+        interp1, zero_part = (field.real, field.imag) if info_in_real_part else (field.imag, field.real)
+        assert np.allclose(0., zero_part, atol=1.e-6 * interp1.max()), fieldtype
+
+        def fit_function(z, a0, z0_phase):
+            return gaussian_laser(z, r[0], a0, z0_phase, z0_b + Lprop_b, ctau_b, lambda0_b)
+        (a0_fit, z0_fit), _ = curve_fit(fit_function, z, interp1[:, 0], p0=np.array([a0, z0_b + Lprop_b]))
+        assert abs(abs(a0_fit) - a0) / a0 < 0.05, (fieldtype, a0_fit)
+        r2d, z2d = np.meshgrid(r, z)
+        predicted = gaussian_laser(z2d, r2d, a0_fit, z0_fit, z0_b + Lprop_b, ctau_b, lambda0_b)
+        assert np.allclose(predicted, interp1, atol=3.e-2 * interp1.max()), fieldtype
+
+
+# ------------------------------------------------------------------ tests/test_fewcycle_laser.py, test_flattenedgauss_laser.py
+def test_fewcycle_laser_as_written():
+    """tests/test_fewcycle_laser.py::test_laser_periodic as written: a 3 fs, w0 = 1.5 micron pulse (a0 = 4) put on the
+    grid 30 microns before its focus agrees with the analytic few-cycle profile (5 % of the maximum), and again after
+    ONE step of dt = 30 micron / c, which the spectral solver propagates to the focus."""
+    import numpy as np
+    from scipy.constants import c
+    from fbpic_b200 import Simulation
+    from fbpic_b200.lpa_utils.laser import add_laser_pulse, FewCycleLaser
+    Nz, zmax, zmin, Nr, rmax, Nm = 200, 5.e-6, -5.e-6, 200, 17.e-6, 2
+    zfoc, rtol = 30e-6, 5.e-2
+
+    def compare_fields(grid, t, profile):
+        Er = 2 * np.asarray(grid.Er).real
+        z, r = np.meshgrid(grid.z, grid.r, indexing='ij')
+        Er_th, _ = profile.E_field(r, 0, z + c * t, t)
+        assert np.allclose(Er, Er_th, atol=rtol * Er_th.max())
+
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, zfoc * 1. / c, zmin=zmin, boundaries={'z': 'periodic', 'r': 'reflective'})
+    profile = FewCycleLaser(a0=4., waist=1.5e-6, tau_fwhm=3.e-15, z0=0, zf=zfoc)
+    add_laser_pulse(sim, profile)
+    compare_fields(sim.fld.interp[1], sim.time, profile)
+    sim.step(1)
+    compare_fields(sim.fld.interp[1], sim.time, profile)
+
+
+def test_flattenedgauss_laser_as_written():
+    """tests/test_flattenedgauss_laser.py::test_laser_periodic as written (Nz = 1600, Nr = 600): a flattened Gaussian
+    beam (N = 6) propagated over 2.8 mm -- many Rayleigh lengths -- in ONE step has the analytic far-field transverse
+    profile within 1.5 %."""
+    import numpy as np
+    from scipy.special import factorial
+    from scipy.constants import c
+    from fbpic_b200 import Simulation
+    from fbpic_b200.lpa_utils.laser import add_laser_pulse, FlattenedGaussianLaser
+    Nz, zmin, zmax, Nr, rmax, Nm, n_order = 1600, -40.e-6, 40.e-6, 600, 300.e-6, 2, -1
+    w0, N, ctau, k0, a0, zfoc, Lprop, rtol = 4.e-6, 6, 10.e-6, 2 * np.pi / 0.8e-6, 1., 400.e-6, 2800.e-6, 1.5e-2
+
+    def flat_gauss(x, N):
+        u = np.zeros_like(x)
+        for n in range(N + 1):
+            u += 1. / factorial(n) * ((N + 1) * x**2)**n
+        return u * np.exp(-(N + 1) * x**2)
+
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, Lprop * 1. / c, n_order=n_order, zmin=zmin,
+                     boundaries={'z': 'periodic', 'r': 'reflective'})
+    add_laser_pulse(sim, FlattenedGaussianLaser(a0=a0, w0=w0, N=N, tau=ctau / c, z0=0, zf=zfoc))
+    sim.step(1)
+    g1 = sim.fld.interp[1]
+    trans_profile = np.sqrt(np.average(np.asarray(g1.Er).real**2, axis=0))
+    w_th = w0 * (Lprop - zfoc) / (k0 * w0**2 / 2)
+    th_profile = trans_profile[0] * flat_gauss(g1.r / w_th, N)
+    assert np.allclose(th_profile, trans_profile, atol=rtol * th_profile[0])

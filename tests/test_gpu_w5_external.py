@@ -4,6 +4,7 @@ library and applied on the device; whole steps against golden outputs of the unm
 import math
 import numpy as np
 import pytest
+from scipy.constants import c
 
 from conftest import load_golden, assert_close, group_scale
 
@@ -80,3 +81,49 @@ def test_external_field_string_expression():
     sp.receive_particles_from_gpu()
     want = F0 + 7. * np.exp(-(x * x + y * y) / (3.e-6)**2) * np.sin(z / 3.e-6 + 1e14 * 2.e-15)
     assert_close(sp.Ez, want, 1e-14, 'string expression')
+
+
+# ------------------------------------------------------------------ the reference's tests/test_external_fields.py
+def _laser_func(F, x, y, z, t, amplitude, length_scale):
+    """the user function of the reference's test (tests/test_external_fields.py:140-144), verbatim semantics: a
+    plane wave added to the gathered field; `c` and `np` are module-level names, `math` an imported module"""
+    return (F + amplitude * math.cos(2 * np.pi * (z - c * t) / length_scale))
+
+
+@pytest.mark.parametrize('gamma_boost', [None, 10])
+def test_external_fields_as_written(gamma_boost):
+    """tests/test_external_fields.py (test_external_fields_lab / _boost) as written: particles in an external plane
+    wave (Ex, By through `ExternalField`) follow ux = a0 sin(k0' (z - ct)), uz = -gamma0 beta0 + gamma0 (1 - beta0)
+    ux^2 / 2 over two laser periods (400 calls of step(1)), lab frame and boosted frame (gamma = 10), atol 5e-2."""
+    from scipy.constants import e, m_e
+    from fbpic_b200 import Simulation
+    from fbpic_b200.lpa_utils.boosted_frame import BoostConverter
+    from fbpic_b200.lpa_utils.external_fields import ExternalField
+    Nz, Nr, Nm, zmin, zmax, rmax = 5, 10, 2, 0.e-6, 0.8e-6, 2.e-6
+    a0, lambda0 = 1., 0.8e-6
+    k0 = 2 * np.pi / lambda0
+    dt, N_step = lambda0 / c / 200, 400
+    boost = BoostConverter(gamma0=1.) if gamma_boost is None else BoostConverter(gamma_boost)
+    if gamma_boost is not None:
+        dt = dt * (1. + boost.beta0) / boost.gamma0
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, initialize_ions=False, zmin=zmin,
+                     boundaries={'z': 'periodic', 'r': 'reflective'}, gamma_boost=gamma_boost)
+    sim.ptcl = []
+    sim.add_new_species(-e, m_e, n=1., p_rmax=rmax / Nr, p_nz=1, p_nr=1, p_nt=1)
+    sim.external_fields = [ExternalField(_laser_func, 'Ex', a0 * m_e * c**2 * k0 / e, lambda0, gamma_boost=gamma_boost),
+                           ExternalField(_laser_func, 'By', a0 * m_e * c * k0 / e, lambda0, gamma_boost=gamma_boost)]
+    sp = sim.ptcl[0]
+    Nptcl = sp.Ntot
+    z, ux, uz = (np.zeros((N_step, Nptcl)) for _ in range(3))
+    k0p = k0 * boost.gamma0 * (1. - boost.beta0)
+    sp.ux = a0 * np.sin(k0p * sp.z)
+    sp.uz[:] = -boost.gamma0 * boost.beta0 + boost.gamma0 * (1 - boost.beta0) * 0.5 * sp.ux**2
+    for i in range(N_step):
+        z[i, :], ux[i, :], uz[i, :] = sp.z[:], sp.ux[:], sp.uz[:]
+        sim.step(1)
+    t = sim.dt * np.arange(N_step)
+    ux_analytical = a0 * np.sin(k0p * (z - c * t[:, None]))
+    uz_analytical = -boost.gamma0 * boost.beta0 + boost.gamma0 * (1 - boost.beta0) * 0.5 * ux_analytical**2
+    assert np.allclose(ux, ux_analytical, atol=5.e-2)
+    assert np.allclose(uz, uz_analytical, atol=5.e-2)
+    assert np.abs(ux).max() > 0.9

@@ -375,3 +375,28 @@ def test_bunch_gaussian_as_written_flow(fake, tmp_path):
 def test_pml_laser_as_written_flow(fake, z_boundary, use_galilean, tmp_path):
     """the reference's tests/test_pml.py (2 x 601 cycles, fields only, restart in the middle)"""
     test_gpu_w1_pml_cross.test_pml_laser_as_written(z_boundary, use_galilean, tmp_path)
+
+
+@slow_flow
+@pytest.mark.parametrize('case', ['labframe', 'labframe_moving', 'boostedframe'])
+def test_antenna_as_written_flow(fake, case):
+    """the reference's tests/test_laser_antenna.py (420 cycles, fields + antenna particles)"""
+    test_gpu_w2_laser.test_antenna_as_written(case)
+
+
+@slow_flow
+@pytest.mark.parametrize('gamma_boost', [None, 10])
+def test_external_fields_as_written_flow(fake, gamma_boost):
+    """the reference's tests/test_external_fields.py (400 calls of step(1))"""
+    test_gpu_w5_external.test_external_fields_as_written(gamma_boost)
+
+
+def test_fewcycle_laser_as_written_flow(fake):
+    """the reference's tests/test_fewcycle_laser.py"""
+    test_gpu_w2_laser.test_fewcycle_laser_as_written()
+
+
+@slow_flow
+def test_flattenedgauss_laser_as_written_flow(fake):
+    """the reference's tests/test_flattenedgauss_laser.py (Nz = 1600, Nr = 600)"""
+    test_gpu_w2_laser.test_flattenedgauss_laser_as_written()
