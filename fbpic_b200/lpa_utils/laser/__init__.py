@@ -57,70 +57,144 @@ class SummedLaserProfile(LaserProfile):
         return a[0] + b[0], a[1] + b[1]
 
 
-def _gaussian_chirped_envelope(z, t, direction, z0, k0, tau, cep_phase, phi2_chirp):
-    """Complex longitudinal profile of a (chirped) Gaussian pulse
-    (longitudinal_laser_profiles.py:162-181)."""
-    inv_ctau2 = 1. / (c * tau)**2
-    stretch = 1 - 2j * phi2_chirp * c**2 * inv_ctau2
-    xi = direction * (z - z0) - c * t
-    return np.exp(-1j * cep_phase + 1j * k0 * xi - 1. / stretch * inv_ctau2 * xi**2) / stretch**0.5
+# ---- longitudinal profiles (longitudinal_laser_profiles.py) ----
+class LaserLongitudinalProfile(object):
+    """Complex E(z, t) on the axis; `squared_profile_integral()` = integral of |E|^2 dz
+    (longitudinal_laser_profiles.py:16-91)."""
+
+    def __init__(self, propagation_direction, gpu_capable=False):
+        assert propagation_direction in [-1, 1]
+        self.propag_direction = float(propagation_direction)
+        self.gpu_capable = gpu_capable
+        self.lambda0 = 0.8e-6
+        self.k0 = 2 * np.pi / self.lambda0
+
+    def evaluate(self, z, t):
+        return np.zeros_like(z, dtype='complex')
+
+    def squared_profile_integral(self):
+        return 0
 
 
-class _ParaxialLaser(LaserProfile):
-    """E = Re[ E0 * longitudinal(z, t) * transverse(x, y, z) ], polarised at theta_pol."""
+class GaussianChirpedLongitudinalProfile(LaserLongitudinalProfile):
+    """(Chirped) Gaussian pulse (longitudinal_laser_profiles.py:94-187)."""
 
-    def __init__(self, a0, waist, tau, z0, zf, theta_pol, lambda0, cep_phase, phi2_chirp, propagation_direction):
-        LaserProfile.__init__(self, propagation_direction)
-        self.k0 = 2 * np.pi / lambda0
-        E0 = a0 * m_e * c**2 * self.k0 / e
-        self.E0x, self.E0y = E0 * np.cos(theta_pol), E0 * np.sin(theta_pol)
-        self.w0, self.tau, self.z0 = waist, tau, z0
-        self.zf = z0 if zf is None else zf
+    def __init__(self, tau, z0, lambda0=0.8e-6, cep_phase=0., phi2_chirp=0., propagation_direction=1):
+        LaserLongitudinalProfile.__init__(self, propagation_direction, gpu_capable=True)
+        self.lambda0, self.k0 = lambda0, 2 * np.pi / lambda0
+        self.z0, self.cep_phase, self.phi2_chirp = z0, cep_phase, phi2_chirp
+        self.inv_ctau2 = 1. / (c * tau)**2
+
+    def evaluate(self, z, t):
+        stretch = 1 - 2j * self.phi2_chirp * c**2 * self.inv_ctau2
+        xi = self.propag_direction * (z - self.z0) - c * t
+        return np.exp(-1j * self.cep_phase + 1j * self.k0 * xi - 1. / stretch * self.inv_ctau2 * xi**2) / stretch**0.5
+
+    def squared_profile_integral(self):
+        return (0.5 * np.pi / self.inv_ctau2)**.5
+
+
+class CustomSpectrumLongitudinalProfile(LaserLongitudinalProfile):
+    """Pulse shape computed from a measured spectrum: a tab-separated file with the wavelength (m), the spectral
+    intensity per wavelength and, optionally, the spectral phase (rad); E(z, t) is the Fourier transform of
+    sqrt(I lambda^2) exp(i phi) over omega, normalised to a peak of 1 (longitudinal_laser_profiles.py:190-354)."""
+
+    def __init__(self, z0, spectrum_file, phi2_chirp=0., phi3_chirp=0., phi4_chirp=0., subtract_linear_phase=False,
+                 propagation_direction=1):
+        from scipy.interpolate import interp1d
+        LaserLongitudinalProfile.__init__(self, propagation_direction, gpu_capable=False)
+        trapezoid = getattr(np, 'trapezoid', None) or np.trapz
+        data = np.loadtxt(spectrum_file, delimiter='\t')
+        wavelength, intensity = data[:, 0], data[:, 1]
+        phase = np.zeros_like(wavelength) if data.shape[1] < 3 else data[:, 2].copy()
+        omega = 2 * np.pi * c / wavelength
+        if subtract_linear_phase:
+            phase -= omega * np.polyfit(omega, phase, 4)[-2]
+        self.lambda0 = trapezoid(wavelength * intensity, wavelength) / trapezoid(intensity, wavelength)
+        self.k0 = 2 * np.pi / self.lambda0
+        d_omega = omega - self.k0 * c
+        phase += phi2_chirp / 2. * d_omega**2 + phi3_chirp / 6. * d_omega**3 + phi4_chirp / 24. * d_omega**4
+        intensity_fn = interp1d(omega, intensity * wavelength**2, fill_value=0, bounds_error=False)
+        phase_fn = interp1d(omega, phase, fill_value=0, bounds_error=False)
+        # a time window of lambda0^2 / (c d_lambda) sampled at d_lambda / c, d_lambda = lambda0 / 1000
+        d_lambda = self.lambda0 / 1000
+        dt = d_lambda / c
+        window = self.lambda0 * self.lambda0 / c / d_lambda
+        Nt = int(np.round(window / dt))
+        time = -0.5 * window + dt * np.arange(Nt)
+        w = 2 * np.pi * np.fft.fftfreq(Nt, dt)
+        field = np.fft.fftshift(np.fft.fft(np.sqrt(intensity_fn(w)) * np.exp(1j * phase_fn(w))))
+        field = field / abs(field).max()
+        self.interp_Efield_function = interp1d(self.propag_direction * z0 - c * time, field, fill_value=0,
+                                               bounds_error=False)
+        self.squared_field_integral = trapezoid(abs(field)**2, c * time)
+
+    def get_mean_wavelength(self):
+        return self.lambda0
+
+    def squared_profile_integral(self):
+        return self.squared_field_integral
+
+    def evaluate(self, z, t):
+        return self.interp_Efield_function(self.propag_direction * z - c * t)
+
+
+# ---- transverse profiles (transverse_laser_profiles.py) ----
+class LaserTransverseProfile(object):
+    """Complex E(x, y, z) of a monochromatic paraxial beam; `squared_profile_integral()` = integral of |E|^2 over
+    the transverse plane (transverse_laser_profiles.py:14-88)."""
+
+    def __init__(self, propagation_direction, gpu_capable=False):
+        assert propagation_direction in [-1, 1]
+        self.propag_direction = float(propagation_direction)
+        self.gpu_capable = gpu_capable
+        self.lambda0 = 0.8e-6
+        self.k0 = 2 * np.pi / self.lambda0
+
+    def _focus(self, waist, zf, lambda0):
+        self.lambda0, self.k0 = lambda0, 2 * np.pi / lambda0
+        self.w0, self.zf = waist, zf
         self.inv_zr = 1. / (0.5 * self.k0 * waist**2)
-        self.cep_phase, self.phi2_chirp = cep_phase, phi2_chirp
 
     def _diffract(self, z):
         return 1. + 1j * self.propag_direction * (z - self.zf) * self.inv_zr
 
-    def transverse(self, x, y, z):
-        raise NotImplementedError
+    def evaluate(self, x, y, z):
+        return np.zeros_like(x, dtype='complex')
 
-    def E_field(self, x, y, z, t):
-        prof = _gaussian_chirped_envelope(z, t, self.propag_direction, self.z0, self.k0, self.tau,
-                                          self.cep_phase, self.phi2_chirp) * self.transverse(x, y, z)
-        return (self.E0x * prof).real, (self.E0y * prof).real
+    def squared_profile_integral(self):
+        return 0
 
 
-class GaussianLaser(_ParaxialLaser):
-    """Linearly polarised Gaussian pulse with Gouy phase / wavefront curvature away from focus
-    (laser_profiles.py:179-293, transverse_laser_profiles.py:143-160)."""
+class GaussianTransverseProfile(LaserTransverseProfile):
+    """Gaussian beam with Gouy phase / wavefront curvature away from focus (transverse_laser_profiles.py:91-166)."""
 
-    def __init__(self, a0, waist, tau, z0, zf=None, theta_pol=0., lambda0=0.8e-6, cep_phase=0.,
-                 phi2_chirp=0., propagation_direction=1):
-        _ParaxialLaser.__init__(self, a0, waist, tau, z0, zf, theta_pol, lambda0, cep_phase, phi2_chirp,
-                                propagation_direction)
-        self.gpu_capable = True
+    def __init__(self, waist, zf=0., lambda0=0.8e-6, propagation_direction=1):
+        LaserTransverseProfile.__init__(self, propagation_direction, gpu_capable=True)
+        self._focus(waist, zf, lambda0)
 
-    def transverse(self, x, y, z):
+    def evaluate(self, x, y, z):
         d = self._diffract(z)
         return np.exp(-(x**2 + y**2) / (self.w0**2 * d)) / d
 
+    def squared_profile_integral(self):
+        return 0.5 * np.pi * self.w0**2
 
-class LaguerreGaussLaser(_ParaxialLaser):
-    """Laguerre-Gauss mode (p, m), azimuthal dependence cos(m (theta - theta0)), pulse energy independent of
-    p and m (laser_profiles.py:296-445, transverse_laser_profiles.py:169-310)."""
 
-    def __init__(self, p, m, a0, waist, tau, z0, zf=None, theta_pol=0., lambda0=0.8e-6, cep_phase=0.,
-                 theta0=0., propagation_direction=1):
+class LaguerreGaussTransverseProfile(LaserTransverseProfile):
+    """Laguerre-Gauss mode (p, m), azimuthal dependence cos(m (theta - theta0)), energy independent of p and m
+    (transverse_laser_profiles.py:169-310)."""
+
+    def __init__(self, p, m, waist, zf=0., lambda0=0.8e-6, theta0=0., propagation_direction=1):
         if m < 0 or type(m) is not int:
             raise ValueError("m should be an integer positive number.")
-        _ParaxialLaser.__init__(self, a0, waist, tau, z0, zf, theta_pol, lambda0, cep_phase, 0.,
-                                propagation_direction)
+        LaserTransverseProfile.__init__(self, propagation_direction)
+        self._focus(waist, zf, lambda0)
         self.p, self.m, self.theta0 = p, m, theta0
         self.scaled_amplitude = 1. if m == 0 else np.sqrt(factorial(p) / factorial(m + p)) * 2**.5
         self.laguerre_pm = genlaguerre(p, m)
 
-    def transverse(self, x, y, z):
+    def evaluate(self, x, y, z):
         d = self._diffract(z)
         w = self.w0 * abs(d)
         psi = np.angle(d)
@@ -131,20 +205,22 @@ class LaguerreGaussLaser(_ParaxialLaser):
             * np.sqrt(s2)**self.m * self.laguerre_pm(s2) * np.cos(self.m * (theta - self.theta0))
         return prof * self.scaled_amplitude
 
+    def squared_profile_integral(self):
+        return 0.5 * np.pi * self.w0**2
 
-class DonutLikeLaguerreGaussLaser(_ParaxialLaser):
+
+class DonutLikeLaguerreGaussTransverseProfile(LaserTransverseProfile):
     """Laguerre-Gauss mode (p, m) with the helical phase exp(-i m theta): a donut-like intensity profile
-    (laser_profiles.py:448-584, transverse_laser_profiles.py:312-432)."""
+    (transverse_laser_profiles.py:312-432)."""
 
-    def __init__(self, p, m, a0, waist, tau, z0, zf=None, theta_pol=0., lambda0=0.8e-6, cep_phase=0.,
-                 propagation_direction=1):
-        _ParaxialLaser.__init__(self, a0, waist, tau, z0, zf, theta_pol, lambda0, cep_phase, 0.,
-                                propagation_direction)
+    def __init__(self, p, m, waist, zf=0., lambda0=0.8e-6, propagation_direction=1):
+        LaserTransverseProfile.__init__(self, propagation_direction)
+        self._focus(waist, zf, lambda0)
         self.p, self.m = p, m
         self.scaled_amplitude = np.sqrt(factorial(p) / factorial(abs(m) + p))
         self.laguerre_pm = genlaguerre(p, abs(m))
 
-    def transverse(self, x, y, z):
+    def evaluate(self, x, y, z):
         d = self._diffract(z)
         w = self.w0 * abs(d)
         psi = np.angle(d)
@@ -154,25 +230,25 @@ class DonutLikeLaguerreGaussLaser(_ParaxialLaser):
         arg = -1.j * self.m * theta - r2 / (self.w0**2 * d) - 1.j * (2 * self.p + abs(self.m)) * psi
         return np.exp(arg) / d * np.sqrt(s2)**abs(self.m) * self.laguerre_pm(s2) * self.scaled_amplitude
 
+    def squared_profile_integral(self):
+        return 0.5 * np.pi * self.w0**2
 
-class FlattenedGaussianLaser(_ParaxialLaser):
-    """Flat-top-like intensity far from focus (a Gaussian times a polynomial of order N there), built as a
-    sum of N+1 Laguerre-Gauss modes of waist w0 sqrt(N+1) (laser_profiles.py:587-710,
-    transverse_laser_profiles.py:434-565)."""
 
-    def __init__(self, a0, w0, tau, z0, N=6, zf=None, theta_pol=0., lambda0=0.8e-6, cep_phase=0.,
-                 propagation_direction=1):
+class FlattenedGaussianTransverseProfile(LaserTransverseProfile):
+    """Flat-top-like intensity far from focus (a Gaussian times a polynomial of order N there), built as a sum of
+    N+1 Laguerre-Gauss modes of waist w0 sqrt(N+1) (transverse_laser_profiles.py:434-565)."""
+
+    def __init__(self, w0, N=6, zf=0., lambda0=0.8e-6, propagation_direction=1):
+        LaserTransverseProfile.__init__(self, propagation_direction)
         self.N = int(round(N))
-        w_foc = w0 * (self.N + 1)**.5
-        _ParaxialLaser.__init__(self, a0, w_foc, tau, z0, zf, theta_pol, lambda0, cep_phase, 0.,
-                                propagation_direction)
-        self.w_foc = w_foc
+        self.w_foc = w0 * (self.N + 1)**.5
+        self._focus(self.w_foc, zf, lambda0)
         self.cn = np.empty(self.N + 1)
         for n in range(self.N + 1):
             mv = np.arange(n, self.N + 1)
             self.cn[n] = np.sum((1. / 2)**mv * binom(mv, n)) / (self.N + 1)
 
-    def transverse(self, x, y, z):
+    def evaluate(self, x, y, z):
         d = self._diffract(z)
         w = self.w_foc * np.abs(d)
         psi = np.angle(d)
@@ -187,6 +263,90 @@ class FlattenedGaussianLaser(_ParaxialLaser):
                 L_prev, L = L, (((2 * n - 1) - s2) * L - (n - 1) * L_prev) / n
             total += self.cn[n] * np.exp(-(2j * n) * psi) * L
         return total * np.exp(-r2 / (self.w_foc**2 * d)) / d
+
+    def squared_profile_integral(self):
+        return 0.5 * np.pi * self.w_foc**2 * sum(self.cn**2)
+
+
+# ---- full profiles (laser_profiles.py) ----
+class ParaxialApproximationLaser(LaserProfile):
+    """E = Re[E0 longitudinal(z, t) transverse(x, y, z)], E0 such that the pulse carries the energy E_laser (J)
+    (laser_profiles.py:105-176)."""
+
+    def __init__(self, longitudinal_profile, transverse_profile, E_laser, theta_pol=0.):
+        LaserProfile.__init__(self, 1)
+        self.longitudinal_profile, self.transverse_profile = longitudinal_profile, transverse_profile
+        self.propag_direction = longitudinal_profile.propag_direction
+        assert self.propag_direction == transverse_profile.propag_direction
+        assert longitudinal_profile.k0 == transverse_profile.k0
+        self.k0 = longitudinal_profile.k0
+        self.gpu_capable = longitudinal_profile.gpu_capable and transverse_profile.gpu_capable
+        E0 = np.sqrt(2 * E_laser / (epsilon_0 * longitudinal_profile.squared_profile_integral()
+                                    * transverse_profile.squared_profile_integral()))
+        self.E0x, self.E0y = E0 * np.cos(theta_pol), E0 * np.sin(theta_pol)
+
+    def E_field(self, x, y, z, t):
+        prof = self.longitudinal_profile.evaluate(z, t) * self.transverse_profile.evaluate(x, y, z)
+        return (self.E0x * prof).real, (self.E0y * prof).real
+
+
+class _ParaxialLaser(LaserProfile):
+    """A Gaussian (possibly chirped) pulse times a transverse profile, amplitude given by a0, polarised at
+    theta_pol."""
+
+    def __init__(self, a0, tau, z0, theta_pol, lambda0, cep_phase, phi2_chirp, propagation_direction, transverse):
+        LaserProfile.__init__(self, propagation_direction)
+        self.k0 = 2 * np.pi / lambda0
+        E0 = a0 * m_e * c**2 * self.k0 / e
+        self.E0x, self.E0y = E0 * np.cos(theta_pol), E0 * np.sin(theta_pol)
+        self.longitudinal_profile = GaussianChirpedLongitudinalProfile(tau, z0, lambda0, cep_phase, phi2_chirp,
+                                                                       propagation_direction)
+        self.transverse_profile = transverse
+
+    def E_field(self, x, y, z, t):
+        prof = self.longitudinal_profile.evaluate(z, t) * self.transverse_profile.evaluate(x, y, z)
+        return (self.E0x * prof).real, (self.E0y * prof).real
+
+
+class GaussianLaser(_ParaxialLaser):
+    """Linearly polarised Gaussian pulse (laser_profiles.py:179-293)."""
+
+    def __init__(self, a0, waist, tau, z0, zf=None, theta_pol=0., lambda0=0.8e-6, cep_phase=0.,
+                 phi2_chirp=0., propagation_direction=1):
+        _ParaxialLaser.__init__(self, a0, tau, z0, theta_pol, lambda0, cep_phase, phi2_chirp, propagation_direction,
+                                GaussianTransverseProfile(waist, z0 if zf is None else zf, lambda0,
+                                                          propagation_direction))
+        self.gpu_capable = True
+
+
+class LaguerreGaussLaser(_ParaxialLaser):
+    """Laguerre-Gauss pulse (laser_profiles.py:296-445)."""
+
+    def __init__(self, p, m, a0, waist, tau, z0, zf=None, theta_pol=0., lambda0=0.8e-6, cep_phase=0.,
+                 theta0=0., propagation_direction=1):
+        _ParaxialLaser.__init__(self, a0, tau, z0, theta_pol, lambda0, cep_phase, 0., propagation_direction,
+                                LaguerreGaussTransverseProfile(p, m, waist, z0 if zf is None else zf, lambda0,
+                                                               theta0, propagation_direction))
+
+
+class DonutLikeLaguerreGaussLaser(_ParaxialLaser):
+    """Donut-like Laguerre-Gauss pulse (laser_profiles.py:448-584)."""
+
+    def __init__(self, p, m, a0, waist, tau, z0, zf=None, theta_pol=0., lambda0=0.8e-6, cep_phase=0.,
+                 propagation_direction=1):
+        _ParaxialLaser.__init__(self, a0, tau, z0, theta_pol, lambda0, cep_phase, 0., propagation_direction,
+                                DonutLikeLaguerreGaussTransverseProfile(p, m, waist, z0 if zf is None else zf,
+                                                                        lambda0, propagation_direction))
+
+
+class FlattenedGaussianLaser(_ParaxialLaser):
+    """Flattened Gaussian pulse (laser_profiles.py:587-710)."""
+
+    def __init__(self, a0, w0, tau, z0, N=6, zf=None, theta_pol=0., lambda0=0.8e-6, cep_phase=0.,
+                 propagation_direction=1):
+        _ParaxialLaser.__init__(self, a0, tau, z0, theta_pol, lambda0, cep_phase, 0., propagation_direction,
+                                FlattenedGaussianTransverseProfile(w0, N, z0 if zf is None else zf, lambda0,
+                                                                   propagation_direction))
 
 
 class FewCycleLaser(LaserProfile):

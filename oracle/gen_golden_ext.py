@@ -129,6 +129,33 @@ def gen_laser_profiles():
         out[k + '_Ex'], out[k + '_Ey'] = p.E_field(x, y, z, t)
     s = profs['gauss'] + profs['lg11']
     out['sum_Ex'], out['sum_Ey'] = s.E_field(x, y, z, t)
+    # longitudinal x transverse profiles normalised to a pulse energy (laser_profiles.py:105-176); the measured
+    # spectrum is the reference's own fixture tests/laser_spectrum.csv (copied to tests/golden/); np.trapz is gone
+    # from NumPy 2
+    if not hasattr(np, 'trapz'):
+        np.trapz = np.trapezoid
+    from fbpic.lpa_utils.laser import ParaxialApproximationLaser, GaussianChirpedLongitudinalProfile, \
+        GaussianTransverseProfile, FlattenedGaussianTransverseProfile, DonutLikeLaguerreGaussTransverseProfile, \
+        LaguerreGaussTransverseProfile, CustomSpectrumLongitudinalProfile
+    spectrum = os.path.join(os.path.dirname(HERE), 'tests', 'golden', 'laser_spectrum.csv')
+    custom = CustomSpectrumLongitudinalProfile(z0=4.e-6, spectrum_file=spectrum, phi2_chirp=80.e-30, phi3_chirp=2.e-42,
+                                               subtract_linear_phase=True)
+    out['custom_lambda0'] = custom.get_mean_wavelength()
+    out['custom_integral'] = custom.squared_profile_integral()
+    chirped = GaussianChirpedLongitudinalProfile(tau=17.e-15, z0=6.e-6, cep_phase=0.3, phi2_chirp=200.e-30)
+    parax = {
+        'parax_custom': ParaxialApproximationLaser(custom, GaussianTransverseProfile(
+            waist=6.e-6, zf=25.e-6, lambda0=custom.get_mean_wavelength()), 0.7, theta_pol=0.2),
+        'parax_gauss': ParaxialApproximationLaser(chirped, GaussianTransverseProfile(waist=5.e-6, zf=30.e-6), 1.),
+        'parax_flat': ParaxialApproximationLaser(chirped, FlattenedGaussianTransverseProfile(w0=5.e-6, N=8, zf=50.e-6),
+                                                 0.5, theta_pol=1.),
+        'parax_donut': ParaxialApproximationLaser(chirped, DonutLikeLaguerreGaussTransverseProfile(
+            waist=6.e-6, zf=10.e-6, p=2, m=1), 2.),
+        'parax_lg': ParaxialApproximationLaser(chirped, LaguerreGaussTransverseProfile(1, 2, 6.e-6, zf=-8.e-6,
+                                                                                       theta0=0.4), 1.5),
+    }
+    for k, p in parax.items():
+        out[k + '_Ex'], out[k + '_Ey'] = p.E_field(x, y, z, t)
     save('laser_profiles', **out)
 
 

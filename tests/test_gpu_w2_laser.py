@@ -204,3 +204,63 @@ def test_flattenedgauss_laser_as_written():
     w_th = w0 * (Lprop - zfoc) / (k0 * w0**2 / 2)
     th_profile = trans_profile[0] * flat_gauss(g1.r / w_th, N)
     assert np.allclose(th_profile, trans_profile, atol=rtol * th_profile[0])
+
+
+@pytest.mark.parametrize('case', ['custom', 'gaussian', 'flattened_chirped', 'donut_chirped'])
+def test_parax_approx_laser_as_written(case):
+    """tests/test_parax_approx_laser.py::test_laser_periodic as written (Nz = 800, Nr = 300, Nm = 3): a 1 J pulse
+    built as ParaxialApproximationLaser(longitudinal, transverse) -- measured spectrum (the reference's
+    laser_spectrum.csv), Gaussian, chirped flattened Gaussian, chirped donut mode -- is put on the grid 1.6 mm before
+    focus and propagated to the focus in ONE step; the pulse energy recovered from E_r there is 1 J within 1 %, the
+    Gaussian case also matches GaussianLaser on the grid and reaches a0 = 2.22."""
+    import os
+    import numpy as np
+    from scipy.constants import c, epsilon_0, m_e, e
+    from conftest import GOLDEN
+    from fbpic_b200 import Simulation
+    from fbpic_b200.lpa_utils.laser import add_laser_pulse, ParaxialApproximationLaser, \
+        GaussianChirpedLongitudinalProfile, GaussianTransverseProfile, FlattenedGaussianTransverseProfile, \
+        DonutLikeLaguerreGaussTransverseProfile, CustomSpectrumLongitudinalProfile, GaussianLaser
+    Nz, zmin, zmax, Nr, rmax, Nm, n_order = 800, -20.e-6, 20.e-6, 300, 150.e-6, 3, -1
+    w0, ctau, k0, E_laser = 17.e-6, 5.e-6, 2 * np.pi / 0.8e-6, 1.
+    a0_gauss = 192 * 0.8e-6 / w0 * np.sqrt(E_laser * c / (ctau * 1.e15))
+    phi2_chirp, zfoc, Lprop, rtol = 200.e-30, 1600.e-6, 1600.e-6, 1.e-2
+
+    def retrieve_pulse_energy(Er, r, dr, dz):
+        intensity = c * epsilon_0 * (2 * Er)**2
+        power = np.sum(intensity * 2 * np.pi * r[:, np.newaxis] * dr, axis=0)
+        return np.sum(power * dz / c)
+
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, Lprop * 1. / c, n_order=n_order, zmin=zmin,
+                     boundaries={'z': 'periodic', 'r': 'reflective'})
+    reference_profile = None
+    if case == 'custom':
+        long_prof = CustomSpectrumLongitudinalProfile(z0=0., spectrum_file=os.path.join(GOLDEN, 'laser_spectrum.csv'))
+        trans_prof = GaussianTransverseProfile(waist=w0, zf=zfoc, lambda0=long_prof.get_mean_wavelength())
+        reference_profile = GaussianLaser(a0_gauss, w0, ctau / c, z0=0, zf=zfoc, phi2_chirp=phi2_chirp)
+    elif case == 'gaussian':
+        long_prof = GaussianChirpedLongitudinalProfile(tau=ctau / c, z0=0., phi2_chirp=0.)
+        trans_prof = GaussianTransverseProfile(waist=w0, zf=zfoc)
+        reference_profile = GaussianLaser(a0_gauss, w0, ctau / c, z0=0, zf=zfoc)
+    elif case == 'flattened_chirped':
+        long_prof = GaussianChirpedLongitudinalProfile(tau=ctau / c, z0=0., phi2_chirp=phi2_chirp)
+        trans_prof = FlattenedGaussianTransverseProfile(w0=w0, N=30, zf=zfoc)
+    else:
+        long_prof = GaussianChirpedLongitudinalProfile(tau=ctau / c, z0=0., phi2_chirp=phi2_chirp)
+        trans_prof = DonutLikeLaguerreGaussTransverseProfile(waist=w0, zf=zfoc, p=2, m=1)
+    add_laser_pulse(sim, ParaxialApproximationLaser(long_prof, trans_prof, E_laser))
+    if reference_profile is not None:
+        r_2d, z_2d = np.meshgrid(sim.fld.interp[0].r, sim.fld.interp[0].z, indexing='ij')
+        Ex_reference = reference_profile.E_field(r_2d, 0, z_2d, 0)[0]
+        assert np.allclose(2 * np.asarray(sim.fld.interp[1].Er).real.T, Ex_reference, atol=rtol * Ex_reference.max())
+    sim.step(1)
+    if case == 'donut_chirped':
+        Er = np.asarray(sim.fld.interp[2].Er).real.T.copy() * 2
+    else:
+        Er = np.asarray(sim.fld.interp[1].Er).real.T.copy()
+    g1 = sim.fld.interp[1]
+    E_laser_sim = retrieve_pulse_energy(Er, g1.r, g1.dr, g1.dz)
+    assert np.allclose(E_laser_sim, E_laser, atol=rtol * E_laser)
+    if case == 'gaussian':
+        a0_sim = 2 * Er.max() / (m_e * c**2 * k0 / e)
+        assert np.allclose(a0_sim, 2.22, atol=3 * rtol * 2.22)

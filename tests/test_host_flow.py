@@ -400,3 +400,10 @@ def test_fewcycle_laser_as_written_flow(fake):
 def test_flattenedgauss_laser_as_written_flow(fake):
     """the reference's tests/test_flattenedgauss_laser.py (Nz = 1600, Nr = 600)"""
     test_gpu_w2_laser.test_flattenedgauss_laser_as_written()
+
+
+@slow_flow
+@pytest.mark.parametrize('case', ['custom', 'gaussian', 'flattened_chirped', 'donut_chirped'])
+def test_parax_approx_laser_as_written_flow(fake, case):
+    """the reference's tests/test_parax_approx_laser.py (Nz = 800, Nr = 300, Nm = 3)"""
+    test_gpu_w2_laser.test_parax_approx_laser_as_written(case)

@@ -36,6 +36,40 @@ def test_laser_profiles_vs_reference():
     assert_close(Ey, g['sum_Ey'], 1e-13, 'sum Ey')
 
 
+def test_paraxial_profiles_vs_reference():
+    """ParaxialApproximationLaser (longitudinal x transverse profile, amplitude from the pulse energy) with the
+    Gaussian-chirped and measured-spectrum longitudinal profiles and all transverse profiles, against the reference;
+    the spectrum is the reference's own fixture tests/laser_spectrum.csv."""
+    import os
+    from conftest import GOLDEN
+    from fbpic_b200.lpa_utils.laser import ParaxialApproximationLaser, GaussianChirpedLongitudinalProfile, \
+        GaussianTransverseProfile, FlattenedGaussianTransverseProfile, DonutLikeLaguerreGaussTransverseProfile, \
+        LaguerreGaussTransverseProfile, CustomSpectrumLongitudinalProfile
+    g = load_golden('laser_profiles')
+    x, y, z, t = g['x'], g['y'], g['z'], float(g['t'])
+    custom = CustomSpectrumLongitudinalProfile(z0=4.e-6, spectrum_file=os.path.join(GOLDEN, 'laser_spectrum.csv'),
+                                               phi2_chirp=80.e-30, phi3_chirp=2.e-42, subtract_linear_phase=True)
+    assert abs(custom.get_mean_wavelength() / float(g['custom_lambda0']) - 1) < 1e-13
+    assert abs(custom.squared_profile_integral() / float(g['custom_integral']) - 1) < 1e-12
+    chirped = GaussianChirpedLongitudinalProfile(tau=17.e-15, z0=6.e-6, cep_phase=0.3, phi2_chirp=200.e-30)
+    parax = {
+        'parax_custom': ParaxialApproximationLaser(custom, GaussianTransverseProfile(
+            waist=6.e-6, zf=25.e-6, lambda0=custom.get_mean_wavelength()), 0.7, theta_pol=0.2),
+        'parax_gauss': ParaxialApproximationLaser(chirped, GaussianTransverseProfile(waist=5.e-6, zf=30.e-6), 1.),
+        'parax_flat': ParaxialApproximationLaser(chirped, FlattenedGaussianTransverseProfile(w0=5.e-6, N=8, zf=50.e-6),
+                                                 0.5, theta_pol=1.),
+        'parax_donut': ParaxialApproximationLaser(chirped, DonutLikeLaguerreGaussTransverseProfile(
+            waist=6.e-6, zf=10.e-6, p=2, m=1), 2.),
+        'parax_lg': ParaxialApproximationLaser(chirped, LaguerreGaussTransverseProfile(1, 2, 6.e-6, zf=-8.e-6,
+                                                                                       theta0=0.4), 1.5),
+    }
+    for k, p in parax.items():
+        Ex, Ey = p.E_field(x, y, z, t)
+        tol = 1e-9 if k == 'parax_custom' else 1e-13          # interpolated from a 10^6-point FFT of the spectrum
+        assert_close(Ex, g[k + '_Ex'], tol, k + ' Ex')
+        assert_close(Ey, g[k + '_Ey'], tol, k + ' Ey')
+
+
 def test_boost_converter():
     """Lorentz identities of fbpic/lpa_utils/boosted_frame.py."""
     from fbpic_b200.lpa_utils.boosted_frame import BoostConverter
