@@ -124,3 +124,49 @@ def test_bunch_gaussian_as_written(tmp_path):
     for key in ('position/x', 'position/y', 'momentum/x', 'momentum/y'):
         q = d['particles/elec/' + key]
         assert len(q) == N and abs(q.mean()) < 1.e-10 * q.std()
+
+
+@pytest.mark.parametrize('shape', ['linear', 'cubic'])
+def test_charge_cylinder_as_written(shape):
+    """tests/test_charge_cylinder.py as written: an on-axis cylinder of charge shrunk down to 1 % of a radial cell
+    (Ruyten-corrected shapes + corrected cell volumes near the axis); r E_r outside of it, from the deposited and
+    filtered charge through `get_space_charge_spect`, equals the analytic lambda / (2 pi eps0) within 1e-3 for every
+    radius.  (The reference works on host arrays; here the grid operations run inside `GpuMemoryManager` blocks and
+    the element-wise space-charge solve on the host arrays in between.)"""
+    from fbpic_b200 import Simulation, GpuMemoryManager, BinomialSmoother
+    from fbpic_b200.lpa_utils.bunch import get_space_charge_spect
+    from scipy.constants import c, e, epsilon_0
+    Nz, zmax, zmin, Nr, rmax, Nm = 10, 10.e-6, -10.e-6, 20, 2.e-6, 1
+    p_rmax, n_e = 1.e-6, 4.e18 * 1.e6
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, (zmax - zmin) / Nz / c, -100.e-6, 100.e-6, 0., p_rmax, 1, 8, 1, n_e,
+                     zmin=zmin, boundaries={'z': 'periodic', 'r': 'reflective'}, verbose_level=0,
+                     smoother=BinomialSmoother(1, False), particle_shape=shape)
+    elec = sim.ptcl[0]
+    for scale in [1.0, 0.5, 0.25, 0.1, 0.05, 0.025, 0.01]:
+        elec.x *= scale
+        elec.y *= scale
+        with GpuMemoryManager(sim):
+            sim.fld.erase('rho')
+            sim.fld.erase('E')
+            sim.fld.erase('B')
+            sim.fld.interp2spect('E')
+            sim.fld.interp2spect('B')
+            elec.deposit(sim.fld, 'rho')
+            sim.fld.sum_reduce_deposition_array('rho')
+            sim.fld.divide_by_volume('rho')
+            sim.fld.interp2spect('rho_prev')
+            sim.fld.filter_spect('rho_prev')
+        get_space_charge_spect(sim.fld.spect[0], 1)
+        with GpuMemoryManager(sim):
+            sim.fld.spect2interp('E')
+            sim.fld.spect2interp('B')
+            sim.fld.spect2interp('rho_prev')
+        elec.x /= scale
+        elec.y /= scale
+        r = sim.fld.interp[0].r.copy()
+        Er = sim.fld.interp[0].Er[5, :].real.copy()
+        Er_theory = np.where(r < (p_rmax * scale),
+                             r * n_e * e * np.pi * p_rmax**2 / (2 * np.pi * epsilon_0 * (p_rmax * scale)**2),
+                             n_e * e * np.pi * p_rmax**2 / (2 * np.pi * epsilon_0 * r))
+        assert np.abs(Er).max() > 0
+        assert np.allclose((-Er * r)[-5:], (Er_theory * r)[-5:], 1.e-3), scale

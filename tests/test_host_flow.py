@@ -407,3 +407,9 @@ def test_flattenedgauss_laser_as_written_flow(fake):
 def test_parax_approx_laser_as_written_flow(fake, case):
     """the reference's tests/test_parax_approx_laser.py (Nz = 800, Nr = 300, Nm = 3)"""
     test_gpu_w2_laser.test_parax_approx_laser_as_written(case)
+
+
+@pytest.mark.parametrize('shape', ['linear', 'cubic'])
+def test_charge_cylinder_as_written_flow(fake, shape):
+    """the reference's tests/test_charge_cylinder.py"""
+    test_gpu_w3_bunch.test_charge_cylinder_as_written(shape)
