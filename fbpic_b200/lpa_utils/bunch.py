@@ -7,7 +7,7 @@ Relativistic particle bunches and their initial space-charge field, same entry p
 The bunch charge and current are deposited by the regular deposition kernel; the Poisson-like solve for the
 field of a bunch of Lorentz factor gamma is done in spectral space -- forward and inverse transforms on the
 GPU (cuFFT + DMMA Hankel), the element-wise spectral formula on the host arrays of this one-off set-up (the
-reference runs all of it on the CPU, bunch.py:886-915).  Not built: openPMD input (h5py).
+reference runs all of it on the CPU, bunch.py:886-915).
 """
 import warnings
 import numpy as np
@@ -96,8 +96,58 @@ def add_particle_bunch_file(sim, q, m, filename, n_physical_particles, z_off=0.,
                                           initialize_self_field=initialize_self_field)
 
 
-def add_particle_bunch_openPMD(*args, **kwargs):
-    raise NotImplementedError('openPMD input needs h5py, which is outside this build (SURVEY 8f rank 3)')
+def add_particle_bunch_openPMD(sim, q, m, ts_path, z_off=0., species=None, select=None, iteration=None, boost=None,
+                               z_injection_plane=None, initialize_self_field=True):
+    """Bunch from the particle record of an openPMD series (bunch.py:359-453): positions, momenta (kg m/s in the
+    file, divided by the mass record and c) and weights of `species` at `iteration` (default: the last one),
+    optionally restricted by `select` = {'uz': [lo, hi], ...}; the bunch is re-centred so that its weighted mean z is
+    `z_off`.  `ts_path` is the directory that holds the `data%08d.h5` files -- or the `.npz` archives that
+    fbpic_b200's diagnostics write when h5py is not installed.  The reference reads the series with openPMD-viewer;
+    here the tree is read directly (fbpic_b200/openpmd_store.py)."""
+    import os
+    from scipy.constants import c
+    from ..diags import read_diag, list_iterations
+    write_dir = os.path.dirname(os.path.abspath(ts_path).rstrip('/')) if os.path.basename(
+        os.path.abspath(ts_path).rstrip('/')) == 'hdf5' else ts_path
+    its = list_iterations(write_dir)
+    if not its:
+        raise OSError('No openPMD file (data%%08d.h5 / .npz) found in %s' % ts_path)
+    if iteration is None:
+        iteration = its[-1]
+    d = read_diag(write_dir, iteration)
+    names = sorted({k.split('/')[1].split('@')[0] for k in d if k.startswith('particles/')})
+    if species is None:
+        if len(names) != 1:
+            raise ValueError('Several species in the file (%s): pass `species`.' % ', '.join(names))
+        species = names[0]
+    grp = 'particles/%s/' % species
+    if grp + 'position/x' not in d:
+        raise ValueError('The file holds no species `%s` (available: %s).' % (species, ', '.join(names)))
+    mass = float(d[grp + 'mass@value'])
+    to_u = 1. / (mass * c) if mass > 0 else 1.
+    data = {'x': d[grp + 'position/x'], 'y': d[grp + 'position/y'], 'z': d[grp + 'position/z'],
+            'ux': d[grp + 'momentum/x'] * to_u, 'uy': d[grp + 'momentum/y'] * to_u, 'uz': d[grp + 'momentum/z'] * to_u,
+            'w': d[grp + 'weighting']}
+    if select is not None:
+        keep = np.ones(len(data['w']), dtype=bool)
+        for quantity, (lo, hi) in select.items():
+            v = np.sqrt(1. + data['ux']**2 + data['uy']**2 + data['uz']**2) if quantity == 'gamma' else data[quantity]
+            if lo is not None:
+                keep &= v > lo
+            if hi is not None:
+                keep &= v < hi
+        data = {k: v[keep] for k, v in data.items()}
+    z = data['z'] - np.average(data['z'], weights=data['w']) + z_off
+    return add_particle_bunch_from_arrays(sim, q, m, data['x'], data['y'], z, data['ux'], data['uy'], data['uz'],
+                                          data['w'], boost=boost, z_injection_plane=z_injection_plane,
+                                          initialize_self_field=initialize_self_field)
+
+
+def add_elec_bunch_openPMD(sim, ts_path, z_off=0., species=None, select=None, iteration=None, boost=None,
+                           z_injection_plane=None):
+    """bunch.py:742-793"""
+    return add_particle_bunch_openPMD(sim, -e, m_e, ts_path, z_off=z_off, species=species, select=select,
+                                      iteration=iteration, boost=boost, z_injection_plane=z_injection_plane)
 
 
 def add_particle_bunch_from_arrays(sim, q, m, x, y, z, ux, uy, uz, w, boost=None, direction='forward',

@@ -595,6 +595,15 @@ class Particles(object):
         """No ionization / Compton in this build (out of scope)."""
         return
 
+    def make_ionizable(self, element, target_species, level_start=0, level_max=None):
+        """particles.py:398-468 -- not built: refused, so that a script relying on it cannot run silently without."""
+        raise NotImplementedError('ADK ionization (Particles.make_ionizable) is outside of this build.')
+
+    def activate_compton(self, target_species, laser_energy, laser_wavelength, laser_waist, laser_ctau,
+                         laser_initial_z0, ratio_w_electron_photon, boost=None):
+        """particles.py:376-396 -- not built, refused like `make_ionizable`."""
+        raise NotImplementedError('Compton scattering (Particles.activate_compton) is outside of this build.')
+
     def shift_periodic(self, zmin, zmax):
         """Single periodic domain: wrap z back into the box
         (boundaries/particle_buffer_handling.py:514-560)."""

@@ -170,3 +170,48 @@ def test_charge_cylinder_as_written(shape):
                              n_e * e * np.pi * p_rmax**2 / (2 * np.pi * epsilon_0 * r))
         assert np.abs(Er).max() > 0
         assert np.allclose((-Er * r)[-5:], (Er_theory * r)[-5:], 1.e-3), scale
+
+
+def test_bunch_from_openpmd_series(tmp_path):
+    """add_elec_bunch_openPMD: a bunch written by a ParticleDiagnostic is read back from the openPMD series into a
+    second (boosted-frame) simulation -- same particles and same space-charge field as when the arrays are passed
+    directly (`add_elec_bunch_from_arrays`), including the selection and the re-centring at z_off."""
+    from fbpic_b200 import Simulation
+    from fbpic_b200.openpmd_diag import ParticleDiagnostic
+    from fbpic_b200.lpa_utils.boosted_frame import BoostConverter
+    from fbpic_b200.lpa_utils.bunch import add_elec_bunch_gaussian, add_elec_bunch_openPMD, add_elec_bunch_from_arrays
+    from scipy.constants import c
+    Nz, zmax, zmin, Nr, rmax, Nm = 64, 0., -32.e-6, 24, 24.e-6, 2
+    dt = (zmax - zmin) / Nz / c
+    kw = dict(zmin=zmin, n_order=-1, n_guard=12, n_damp={'z': 12, 'r': 6}, boundaries={'z': 'open', 'r': 'reflective'})
+    np.random.seed(3)
+    a = Simulation(Nz, zmax, Nr, rmax, Nm, dt, **kw)
+    a.ptcl = []
+    src = add_elec_bunch_gaussian(a, 2.e-6, 2.e-6, 1.e-6, 40., 2., 20.e-12, 5000, zf=-16.e-6)
+    a.diags = [ParticleDiagnostic(1, {'beam': src}, a.comm, write_dir=str(tmp_path))]
+    x, y, z, ux, uy, uz, w = (np.array(getattr(src, k)) for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'w'))
+    a.step(1)                                   # writes iteration 0: the bunch as initialised
+    keep = uz > 38.
+    z_off = -20.e-6
+    z_ref = z[keep] - np.average(z[keep], weights=w[keep]) + z_off
+    sims = []
+    for loader in ('openPMD', 'arrays'):
+        b = Simulation(Nz, zmax, Nr, rmax, Nm, dt, gamma_boost=4., **kw)
+        b.ptcl = []
+        if loader == 'openPMD':
+            sp = add_elec_bunch_openPMD(b, str(tmp_path / 'hdf5'), z_off=z_off, species='beam',
+                                        select={'uz': [38., None]}, iteration=0, boost=BoostConverter(4.))
+        else:
+            sp = add_elec_bunch_from_arrays(b, x[keep], y[keep], z_ref, ux[keep], uy[keep], uz[keep], w[keep],
+                                            boost=BoostConverter(4.))
+        sims.append((b, sp))
+    (b1, s1), (b2, s2) = sims
+    assert s1.Ntot == s2.Ntot and 100 < s1.Ntot < 5000
+    for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'w', 'inv_gamma'):
+        assert_close(np.array(getattr(s1, k)), np.array(getattr(s2, k)), 1e-12, 'openPMD bunch ' + k)
+    for m in range(Nm):
+        for k in ('Er', 'Ez', 'Bt'):
+            scale = np.abs(getattr(b2.fld.interp[0], 'Er')).max()
+            assert scale > 0
+            assert_close(getattr(b1.fld.interp[m], k), getattr(b2.fld.interp[m], k), 1e-9, 'openPMD bunch %s m%d' % (k, m),
+                         scale=scale * (1. if k[0] == 'E' else 1. / c))

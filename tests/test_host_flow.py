@@ -413,3 +413,7 @@ def test_parax_approx_laser_as_written_flow(fake, case):
 def test_charge_cylinder_as_written_flow(fake, shape):
     """the reference's tests/test_charge_cylinder.py"""
     test_gpu_w3_bunch.test_charge_cylinder_as_written(shape)
+
+
+def test_bunch_from_openpmd_series_flow(fake, tmp_path):
+    test_gpu_w3_bunch.test_bunch_from_openpmd_series(tmp_path)
