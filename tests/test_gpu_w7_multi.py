@@ -33,3 +33,15 @@ def test_two_gpu_diagnostics_match_one_gpu():
            os.path.join(ROOT, 'tests', 'workers', 'mgpu_parity_worker.py')]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0 and 'MGPU_DIAG_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_two_gpu_checkpoint_restart():
+    """A 2-slab run restarted from its per-rank checkpoints continues like the uninterrupted one."""
+    if _lib.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    env = dict(os.environ, MGPU_EXTRA='3')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', '29647',
+           os.path.join(ROOT, 'tests', 'workers', 'mgpu_parity_worker.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and 'MGPU_RESTART_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

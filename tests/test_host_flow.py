@@ -168,6 +168,16 @@ def test_ext_kernel_tests_flow(fake):
     k.test_external_field_jit()
 
 
+def test_two_rank_restart_flow_gloo():
+    """Per-rank checkpoints of a 2-rank run, restart, same continuation (rank by rank)."""
+    env = dict(os.environ, OMP_NUM_THREADS='2', ORACLE_NUM_THREADS='2', MGPU_NZ_PER_RANK='64', MGPU_EXTRA='3')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', '29657',
+           os.path.join(ROOT, 'tests', 'workers', 'mgpu_parity_worker.py'), '--fake-device']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0 and 'MGPU_RESTART_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
 @pytest.mark.parametrize('fused', [False, True])
 def test_transfer_accounting(fake, fused):
     """Bytes copied by a step() call: the fused step neither uploads nor reads back the 6 gathered-field arrays

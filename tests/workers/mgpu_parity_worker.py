@@ -378,8 +378,68 @@ def run_diag_case(tol):
     return bool(int(flag[0]))
 
 
+def run_restart_case(tol):
+    """Checkpoint / restart of a sharded run (checkpoint_restart.py:22-189): every rank writes and reads its own
+    `proc<rank>` directory; the restarted run continues like the uninterrupted one, rank by rank."""
+    import tempfile
+    from fbpic_b200.diags import set_periodic_checkpoint, restart_from_checkpoint
+    rank, size = dist.get_rank(), dist.get_world_size()
+    nzr = int(os.environ.get('MGPU_NZ_PER_RANK', '96'))
+    Nz, Nr, Nm, zmax, rmax, n_e, n_order = nzr * size, 16, 2, 0.2e-6 * nzr * size, 8.e-6, 2.e24, 8
+    dt = zmax / Nz / c
+    P = global_particles(Nz, Nr, zmax, rmax, n_e)
+    P['uz'] = P['uz'] + 0.3          # particles cross the slab boundaries between the checkpoint and the end
+    P['inv_gamma'] = 1. / np.sqrt(1 + P['ux']**2 + P['uy']**2 + P['uz']**2)
+    kw = dict(n_order=n_order, boundaries={'z': 'periodic', 'r': 'reflective'})
+    d = [tempfile.mkdtemp() if rank == 0 else None]
+    dist.broadcast_object_list(d, src=0)
+    a = Simulation(Nz, zmax, Nr, rmax, Nm, dt, **kw)
+    zlo, zhi = a.comm.get_zmin_zmax(local=True, with_damp=False, with_guard=False, rank=rank)
+    sp = set_species(a, P, zlo, zhi)
+    sp.track(a.comm)
+    set_periodic_checkpoint(a, 4, checkpoint_dir=d[0])
+    a.step(4, correct_currents=False)
+    a.step(3, correct_currents=False)
+    b = Simulation(Nz, zmax, Nr, rmax, Nm, dt, **kw)
+    set_species(b, P, zlo, zhi).track(b.comm)
+    restart_from_checkpoint(b, checkpoint_dir=d[0])
+    ok = b.iteration == 4
+    b.step(3, correct_currents=False)
+    sa, sb = a.ptcl[0], b.ptcl[0]
+    if sa.Ntot != sb.Ntot or not np.array_equal(np.sort(sa.tracker.id), np.sort(sb.tracker.id)):
+        ok = False
+        print('RESTART MISMATCH rank %d: particle number / ids %d %d' % (rank, sa.Ntot, sb.Ntot))
+    else:
+        ia, ib = np.argsort(sa.tracker.id), np.argsort(sb.tracker.id)
+        for k, scale in (('x', rmax), ('z', zmax), ('ux', 1.), ('uz', 1.), ('w', 0.)):
+            va, vb = np.asarray(getattr(sa, k))[ia], np.asarray(getattr(sb, k))[ib]
+            if not np.abs(va - vb).max() <= tol * (scale or np.abs(va).max()):
+                ok = False
+                print('RESTART MISMATCH rank %d particles %s: %.3e' % (rank, k, np.abs(va - vb).max()))
+    for grp in ('E', 'B'):
+        scale = max(np.abs(getattr(a.fld.interp[m], grp + k)).max() for m in range(Nm) for k in 'rtz')
+        for m in range(Nm):
+            for k in 'rtz':
+                err = np.abs(getattr(a.fld.interp[m], grp + k) - getattr(b.fld.interp[m], grp + k)).max()
+                if not err <= tol * scale:
+                    ok = False
+                    print('RESTART MISMATCH rank %d %s%s m%d: %.3e vs %.3e' % (rank, grp, k, m, err, scale))
+    if rank == 0:
+        print('restart: rank 0 holds %d particles, %d of them came from another rank'
+              % (sb.Ntot, int(np.sum(np.asarray(sb.tracker.id) % size != rank))))
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    return bool(int(flag[0]))
+
+
 def main():
     dist.init_process_group('gloo')
+    if os.environ.get('MGPU_EXTRA') == '3':
+        ok = run_restart_case(1e-9)
+        if dist.get_rank() == 0 and ok:
+            print('MGPU_RESTART_OK size=%d' % dist.get_world_size())
+        sys.exit(0 if ok else 1)
     if os.environ.get('MGPU_EXTRA') == '2':
         ok = run_diag_case(1e-9)
         if dist.get_rank() == 0 and ok:
