@@ -44,6 +44,24 @@ def build(variant):
         if variant == 'antenna':
             add_laser_pulse(sim, GaussianLaser(1., 20.e-6, 16.e-15, -10.e-6, zf=0.5 * zmax), method='antenna',
                             z0_antenna=0.1 * zmax)
+    elif variant in ('field_diag', 'lab_diag'):
+        # diagnostics overhead: a field output every 10 cycles resp. 10 lab-frame snapshots (fields + particles)
+        # fed every cycle; files go to a scratch directory
+        import tempfile
+        from fbpic_b200.openpmd_diag import (FieldDiagnostic, BackTransformedFieldDiagnostic,
+                                             BackTransformedParticleDiagnostic)
+        out = tempfile.mkdtemp()
+        if variant == 'field_diag':
+            sim = Simulation(Nz, zmax, Nr, rmax, Nm, dz / c, **kw)
+            sim.diags = [FieldDiagnostic(10, sim.fld, comm=sim.comm, fieldtypes=['E', 'B', 'rho'], write_dir=out)]
+        else:
+            # (the run itself is not boosted: the lab-frame diagnostics only slice it, which is what is timed)
+            sim = Simulation(Nz, zmax, Nr, rmax, Nm, dz / c, **kw)
+            sim.ptcl[0].track(sim.comm)
+            args = (0., 5. * zmax, 0., 0.2 * zmax / c, 10, 5., 20, sim.fld)
+            sim.diags = [BackTransformedFieldDiagnostic(*args, comm=sim.comm, write_dir=out),
+                         BackTransformedParticleDiagnostic(*args, species={'electrons': sim.ptcl[0]}, comm=sim.comm,
+                                                           write_dir=out)]
     else:
         raise ValueError(variant)
     sp = sim.ptcl[0]
@@ -59,7 +77,8 @@ def main():
     ev0, ev1 = ctypes.c_void_p(), ctypes.c_void_p()
     call.b2_event_create(ctypes.byref(ev0))
     call.b2_event_create(ctypes.byref(ev1))
-    for variant in ('default', 'pml', 'cross_deposition', 'external_field', 'open_window', 'antenna'):
+    for variant in ('default', 'pml', 'cross_deposition', 'external_field', 'open_window', 'antenna', 'field_diag',
+                    'lab_diag'):
         try:
             sim = build(variant)
             n = sum(s.Ntot for s in sim.ptcl)
