@@ -199,3 +199,31 @@ def read_tree(filename):
         visit('', f)
         f.visititems(visit)
     return out
+
+
+def npz_to_hdf5(npz_path, h5_path=None):
+    """Rewrite one `.npz` archive of this module as the HDF5 file it stands for (needs h5py): same groups, datasets
+    and attributes, i.e. a regular openPMD file.  `python -m fbpic_b200.openpmd_store <dir or file> ...` converts whole
+    diagnostics directories after a run on a machine without h5py."""
+    import h5py
+    h5_path = h5_path or npz_path[:-4] + '.h5'
+    tree = read_tree(npz_path)
+    with h5py.File(h5_path, 'w') as f:
+        for key in sorted(k for k in tree if '@' not in k):
+            if key.endswith('/'):
+                f.require_group(key)
+            else:
+                f.create_dataset(key, data=tree[key])
+        for key in (k for k in tree if '@' in k):
+            path, attr = key.rsplit('@', 1)
+            (f if path == '/' else f[path]).attrs[attr] = tree[key]
+    return h5_path
+
+
+if __name__ == '__main__':
+    import sys
+    for target in sys.argv[1:]:
+        files = [os.path.join(root, n) for root, _, names in os.walk(target) for n in names if n.endswith('.npz')] \
+            if os.path.isdir(target) else [target]
+        for path in sorted(files):
+            print(npz_to_hdf5(path))

@@ -116,3 +116,13 @@ def test_product_never_reaches_the_checkers():
         assert ('def time_oracle' in ctx) or ('def build_oracle_sim' in ctx) or ("args.impl == 'reference'" in ctx) \
             or ('cpu_baseline = None' in ctx), \
             'bench.py imports the oracle outside the cpu_baseline / reference legs'
+
+
+def test_launch_limits_match_the_sources():
+    """The per-launch limits the host layer chunks its work by are those compiled into the library."""
+    import re
+    from fbpic_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'fbpic_b200.h')).read()
+    dht = open(os.path.join(ROOT, 'fbpic_b200', 'csrc', 'b2_dht.cu')).read()
+    assert int(re.search(r'#define\s+B2_MAX_ARRAYS\s+(\d+)', header).group(1)) == _lib.MAX_ARRAYS
+    assert int(re.search(r'#define\s+DHT_MAX_JOBS\s+(\d+)', dht).group(1)) == _lib.MAX_DHT_JOBS

@@ -321,6 +321,31 @@ def shim_h5py():
     sys.modules.pop('h5py', None)
 
 
+def test_npz_archives_convert_to_hdf5(fake, tmp_path):
+    """A diagnostics directory written without h5py (`.npz` archives) converts to the `.h5` files the h5py branch
+    would have written: same tree, compared with the reference's."""
+    import diag_cases
+    from conftest import load_golden
+    from fbpic_b200 import openpmd_store
+    test_gpu_w8_diags.test_diagnostic_trees_vs_reference_golden(True, tmp_path)
+    path = os.path.join(ROOT, 'oracle', 'ref_shim')
+    sys.modules.pop('h5py', None)
+    sys.path.insert(0, path)
+    try:
+        d = str(tmp_path / 'all' / 'hdf5')
+        for name in sorted(os.listdir(d)):
+            openpmd_store.npz_to_hdf5(os.path.join(d, name))
+            os.remove(os.path.join(d, name))
+        assert sorted(os.listdir(d)) == ['data00000000.h5', 'data00000004.h5']
+        g = load_golden('diags_tree')
+        ref, got = diag_cases.golden_files(g, 'all'), diag_cases.written_files(str(tmp_path / 'all'))
+        for name in ref:
+            diag_cases.compare_trees(got[name], ref[name], 1e-9, 'converted ' + name)
+    finally:
+        sys.path.remove(path)
+        sys.modules.pop('h5py', None)
+
+
 def test_diagnostics_through_the_h5py_api(fake, shim_h5py, tmp_path):
     """Same comparisons with the reference's trees, the files written and read back through the h5py calls."""
     import h5py
