@@ -81,6 +81,8 @@ class Simulation(object):
         self.filter_currents = filter_currents
         self.external_fields, self.diags, self.checkpoints = [], [], []
         self.laser_antennas, self.mirrors = [], []
+        from .printing import print_simulation_setup
+        print_simulation_setup(self, verbose_level=verbose_level)
 
     # ------------------------------------------------------------------ data residency
     def send_data_to_gpu(self):
@@ -144,7 +146,14 @@ class Simulation(object):
         # the per-step exchange_particles + re-deposition of rho_prev (main.py:435-449, needed in
         # the reference only because particles may have been added/removed) is done at i_step==0 only.
         wrap_in_push = self.fused and periodic_single and move_positions and not self.laser_antennas
+        progress_bar = None
+        if show_progress and self.comm.rank == 0:     # main.py:398-399; never synchronises the device
+            from .printing import ProgressBar
+            progress_bar = ProgressBar(N)
         for i_step in range(N):
+            if progress_bar is not None:
+                progress_bar.time(i_step)
+                progress_bar.print_progress()
             exchange_now = (self.iteration % self.comm.exchange_period == 0 or i_step == 0)
             if exchange_now and not (wrap_in_push and i_step > 0):
                 for species in ptcl:
@@ -265,6 +274,8 @@ class Simulation(object):
         # wall-clock split of this call: host->device copy, the N cycles (device-synchronised), device->host copy
         self.last_step_timing = dict(h2d_s=t_sent - t_start, cycles_s=t_done - t_sent,
                                      d2h_s=_time.perf_counter() - t_done)
+        if progress_bar is not None:
+            progress_bar.print_summary()
         # bytes copied host->device / device->host by this call (counted from the arrays actually copied)
         self.last_step_bytes = {k: _lib.TRANSFERRED[k] - bytes0[k] for k in bytes0}
 

@@ -452,3 +452,24 @@ def test_charge_cylinder_as_written_flow(fake, shape):
 
 def test_bunch_from_openpmd_series_flow(fake, tmp_path):
     test_gpu_w3_bunch.test_bunch_from_openpmd_series(tmp_path)
+
+
+def test_console_output_flow(fake, capsys):
+    """`verbose_level` banner and `show_progress` line (fbpic/utils/printing.py), silent by default"""
+    import numpy as np
+    from scipy.constants import c
+    from fbpic_b200 import Simulation
+    zmax, rmax = 16.e-6, 8.e-6
+    kw = dict(p_zmin=0, p_zmax=zmax, p_rmin=0, p_rmax=rmax, p_nz=1, p_nr=1, p_nt=4, n_e=1.e24)
+    np.random.seed(0)
+    Simulation(32, zmax, 12, rmax, 2, zmax / 32 / c, **kw).step(2)
+    assert capsys.readouterr().out == ''
+    sim = Simulation(32, zmax, 12, rmax, 2, zmax / 32 / c, verbose_level=2, n_order=8, gamma_boost=3., n_guard=12,
+                     n_damp={'z': 12, 'r': 6}, boundaries={'z': 'open', 'r': 'open'}, **kw)
+    out = capsys.readouterr().out
+    for text in ('fbpic_b200', 'PSATD stencil order: 8', 'Transverse boundaries: open', 'Boosted frame gamma: 3',
+                 'Guard region size'):
+        assert text in out, (text, out)
+    sim.step(3, show_progress=True)
+    out = capsys.readouterr().out
+    assert '3/3' in out and 'ms/step' in out and 'Total time taken' in out
