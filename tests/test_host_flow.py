@@ -126,12 +126,14 @@ def test_uniform_rho_flow(fake, shape):
     test_gpu_w6_acceptance.test_neutral_plasma_shifted(shape)
 
 
+@slow_flow
 def test_cherenkov_instability_flow(fake):
     test_gpu_w6_acceptance.test_cherenkov_instability()
 
 
-@pytest.mark.parametrize('case', ['labframe_with_preexisting_plasma', 'boosted_with_preexisting_plasma',
-                                  'labframe_without_preexisting_plasma'])
+@pytest.mark.parametrize('case', [pytest.param('labframe_with_preexisting_plasma', marks=slow_flow),
+                                  'boosted_with_preexisting_plasma',
+                                  pytest.param('labframe_without_preexisting_plasma', marks=slow_flow)])
 def test_continuous_injection_flow(fake, case):
     getattr(test_gpu_w6_acceptance, 'test_' + case)()
 
@@ -390,6 +392,7 @@ def test_cpu_gpu_deposition_flow(fake, shape, fused, tmp_path):
     test_gpu_w8_diags.test_cpu_gpu_deposition_as_written(shape, fused, tmp_path)
 
 
+@slow_flow
 def test_boosted_particle_output_flow(fake, tmp_path):
     """the reference's tests/test_boosted_particle_output.py (500 cycles, 3000 tracked particles)"""
     test_gpu_w6_acceptance.test_boosted_output(tmp_path)
