@@ -208,7 +208,7 @@ __global__ void k_axpy(long long n, double a, const double *__restrict__ x, doub
 // Grid: (ir, field).  Rounded products then a rounded sum, like the NumPy expression of the CPU path (:626-629).
 struct SliceFields { const double2 *f[10]; };
 
-__global__ void k_extract_slice(SliceFields F, int m, int n_rows, int Nr, int Nr_out, int iz, double Sz,
+__global__ void k_extract_slice(const __grid_constant__ SliceFields F, int m, int n_rows, int Nr, int Nr_out, int iz, double Sz,
                                 double *__restrict__ slice) {
     const int ir = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
