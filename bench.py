@@ -28,7 +28,7 @@ import threading
 import time
 
 import numpy as np
-from scipy.constants import c, e, m_e, epsilon_0
+from scipy.constants import c, e, m_e
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:

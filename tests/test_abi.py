@@ -4,7 +4,6 @@ product fails loudly (no CPU fallback) when no GPU is present."""
 import os
 import re
 import ctypes
-import numpy as np
 import pytest
 
 from conftest import ROOT
