@@ -3,7 +3,8 @@ Laser initialisation and emission, same entry points as `fbpic.lpa_utils.laser`
 (fbpic/lpa_utils/laser/{laser.py, laser_profiles.py, direct_injection.py, antenna_injection.py}):
 
 * laser profiles (`GaussianLaser`, `LaguerreGaussLaser`, `DonutLikeLaguerreGaussLaser`, `FlattenedGaussianLaser`,
-  `FewCycleLaser`, sums with `+`): analytic E(x, y, z, t), NumPy (`FromLasyFileLaser` needs h5py: not built);
+  `FewCycleLaser`, `ParaxialApproximationLaser` over longitudinal / transverse profile classes, sums with `+`):
+  analytic E(x, y, z, t), NumPy (`FromLasyFileLaser` is refused: not built);
 * `add_laser_pulse(sim, profile, method='direct')`: the profile is sampled on the global grid, Ez and B
   follow from div E = 0 and Faraday's law in spectral space.  The transforms of that one-off set-up run on
   the GPU (cuFFT + DMMA Hankel kernels of the hot path) -- the reference does them on the CPU even in GPU
@@ -347,6 +348,14 @@ class FlattenedGaussianLaser(_ParaxialLaser):
         _ParaxialLaser.__init__(self, a0, tau, z0, theta_pol, lambda0, cep_phase, 0., propagation_direction,
                                 FlattenedGaussianTransverseProfile(w0, N, z0 if zf is None else zf, lambda0,
                                                                    propagation_direction))
+
+
+class FromLasyFileLaser(LaserProfile):
+    """Laser read from a lasy openPMD file (laser_profiles.py:841-1065) -- not built: refused, so that a script that
+    relies on it cannot run without its laser."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError('FromLasyFileLaser (lasy envelope files) is outside of this build.')
 
 
 class FewCycleLaser(LaserProfile):
