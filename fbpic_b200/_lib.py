@@ -131,6 +131,10 @@ _SIGNATURES = {
     'b2_push_p_after_plane': [P, c_int64, P, c_double, P, P, P, P, P, P, P, P, P, P, c_double, c_double, c_double, P],
     'b2_antenna_particles': [P, c_int64, P, P, P, P, P, P, P, c_double, P, P, P, P, P, P],
     'b2_axpy': [P, c_int64, c_double, P, P, P],
+    'b2_push_p_ioniz': [P, c_int64, P, P, P, P, P, P, P, P, P, P, P, c_double, c_double, P],
+    'b2_w_times_level': [P, c_int64, P, P, P, P],
+    'b2_ionize': [P, c_int64, P, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P, ctypes.c_uint64, c_int64, P, P,
+                  ctypes.POINTER(c_int64), P],
     'b2_select_crossing': [P, c_int64, P, P, P, c_double, c_double, c_double, c_double, c_int64, P, P,
                            ctypes.POINTER(c_int64), P],
     'b2_extract_slice': [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_double, P, P],

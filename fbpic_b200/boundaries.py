@@ -365,17 +365,20 @@ class BoundaryCommunicator(object):
             self._shift_z(new['z'], n_recv_l + n_stay, n_recv_r, +Ltot)
         if self.left_proc == self.size - 1 and n_recv_l:
             self._shift_z(new['z'], 0, n_recv_l, -Ltot)
-        if species.tracker is not None:
-            self._exchange_ids(species, N, zlo, zhi, n_new, n_stay, n_send_l, n_send_r, n_recv_l, n_recv_r,
+        for carrier in species.uint_carriers():       # tracked ids, ionization levels
+            self._exchange_ids(species, carrier, N, zlo, zhi, n_new, n_stay, n_send_l, n_send_r, n_recv_l, n_recv_r,
                                injected is not None)
         species.resize_device_arrays(new, n_new)
+        if species.ionizer is not None:
+            species.ionizer.update_weights(species)
 
-    def _exchange_ids(self, species, N, zlo, zhi, n_new, n_stay, n_send_l, n_send_r, n_recv_l, n_recv_r, injected):
-        """The tracked ids take the same 3-way partition as the float attributes (the classification of
+    def _exchange_ids(self, species, t, N, zlo, zhi, n_new, n_stay, n_send_l, n_send_r, n_recv_l, n_recv_r, injected):
+        """An 8-byte integer array `t.id` (tracked ids; ionization levels) takes the same 3-way partition as the float
+        attributes (the classification of
         b2_exchange_classify is still valid: one more b2_exchange_scatter with the id array), travel to the
         neighbours in a message of their own, and new ids are drawn for injected plasma
         (particle_buffer_handling.py:117-167, 409-411; particles.py:367-368)."""
-        ctx, t = _lib.context(), species.tracker
+        ctx = _lib.context()
         cap = max(species._capacity, species._capacity_for(n_new))
         dest = t.spare.view((n_new,)) if t.spare.capacity >= n_new else DeviceArray(cap, np.uint64).view((n_new,))
         id_l = DeviceArray(max(n_send_l, 1), np.uint64)

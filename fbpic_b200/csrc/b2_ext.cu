@@ -105,6 +105,50 @@ int b2_axpy(b2_ctx *ctx, int64_t n, double a, const double *x, double *y, void *
     return 0;
 }
 
+int b2_push_p_ioniz(b2_ctx *ctx, int64_t n, const uint64_t *level, double *ux, double *uy, double *uz,
+                    double *inv_gamma, const double *Ex, const double *Ey, const double *Ez, const double *Bx,
+                    const double *By, const double *Bz, double m, double dt, void *stream) {
+    if (n <= 0) return 0;
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    B2Prof prof_(B2P_PUSH, s);
+    const double e = 1.602176634e-19;
+    b2ext::k_push_p_ioniz<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+        (long long)n, (const unsigned long long *)level, ux, uy, uz, inv_gamma, Ex, Ey, Ez, Bx, By, Bz,
+        e * dt / (m * B2_C_LIGHT), 0.5 * e * dt / m);
+    B2_LAUNCHED();
+    return 0;
+}
+
+int b2_w_times_level(b2_ctx *ctx, int64_t n, const double *w, const uint64_t *level, double *out, void *stream) {
+    if (n <= 0) return 0;
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    b2ext::k_w_times_level<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((long long)n, w,
+                                                                      (const unsigned long long *)level, out);
+    B2_LAUNCHED();
+    return 0;
+}
+
+int b2_ionize(b2_ctx *ctx, int64_t n, uint64_t *level, int level_max, const double *adk_prefactor,
+              const double *adk_power, const double *adk_exp_prefactor, const double *ux, const double *uy,
+              const double *uz, const double *Ex, const double *Ey, const double *Ez, const double *Bx,
+              const double *By, const double *Bz, const double *draws, uint64_t seed, int64_t cap, int64_t *d_events,
+              int64_t *d_count, int64_t *h_count, void *stream) {
+    if (!d_count || !h_count || (cap > 0 && !d_events))
+        return b2_fail(-3, "b2_ionize: missing buffer", __FILE__, __LINE__);
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    B2_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), s));
+    if (n > 0) {
+        b2ext::k_ionize<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+            (long long)n, (unsigned long long *)level, level_max, adk_prefactor, adk_power, adk_exp_prefactor, ux, uy,
+            uz, Ex, Ey, Ez, Bx, By, Bz, B2_C_LIGHT, draws, (unsigned long long)seed, (long long)cap,
+            (long long *)d_events, (unsigned long long *)d_count);
+        B2_LAUNCHED();
+    }
+    B2_CUDA(cudaMemcpyAsync(h_count, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 int b2_extract_slice(b2_ctx *ctx, const void *const *fields10, int m, int Nm, int Nz, int Nr, int Nr_out, int iz,
                      double Sz, double *slice, void *stream) {
     if (m < 0 || m >= Nm || Nr_out <= 0 || Nr_out > Nr)

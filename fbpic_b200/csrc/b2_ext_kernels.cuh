@@ -143,17 +143,13 @@ __global__ void k_correct_divE(double2 *__restrict__ Ep, double2 *__restrict__ E
 }
 
 // ---- momentum push beyond a plane -----------------------------------------------------------------------
-// push_p_after_plane_gpu (fbpic/particles/push/cuda_methods.py:103-132): the Vay push
-// (push/inline_functions.py:11-48) for the particles with z > z_plane; the others keep their momentum (ballistic
-// motion of an injected bunch before it reaches the plasma, injection/ballistic_before_plane.py:10-61).
-__global__ void k_push_p_after_plane(long long n, const double *__restrict__ z, double z_plane,
-                                     double *__restrict__ ux, double *__restrict__ uy, double *__restrict__ uz,
-                                     double *__restrict__ inv_gamma, const double *__restrict__ Ex,
-                                     const double *__restrict__ Ey, const double *__restrict__ Ez,
-                                     const double *__restrict__ Bx, const double *__restrict__ By,
-                                     const double *__restrict__ Bz, double econst, double bconst) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n || !(z[i] > z_plane)) return;
+// Vay push of particle i (push/inline_functions.py:11-48)
+__device__ __forceinline__ void vay_push(long long i, double *__restrict__ ux, double *__restrict__ uy,
+                                         double *__restrict__ uz, double *__restrict__ inv_gamma,
+                                         const double *__restrict__ Ex, const double *__restrict__ Ey,
+                                         const double *__restrict__ Ez, const double *__restrict__ Bx,
+                                         const double *__restrict__ By, const double *__restrict__ Bz, double econst,
+                                         double bconst) {
     const double tx = bconst * Bx[i], ty = bconst * By[i], tz = bconst * Bz[i];
     const double t2 = tx * tx + ty * ty + tz * tz;
     const double ig0 = inv_gamma[i], u0x = ux[i], u0y = uy[i], u0z = uz[i];
@@ -170,6 +166,20 @@ __global__ void k_push_p_after_plane(long long n, const double *__restrict__ z, 
     uy[i] = s * (py + sy * st + pz * sx - px * sz);
     uz[i] = s * (pz + sz * st + px * sy - py * sx);
     inv_gamma[i] = ig;
+}
+
+// push_p_after_plane_gpu (fbpic/particles/push/cuda_methods.py:103-132): the Vay push
+// (push/inline_functions.py:11-48) for the particles with z > z_plane; the others keep their momentum (ballistic
+// motion of an injected bunch before it reaches the plasma, injection/ballistic_before_plane.py:10-61).
+__global__ void k_push_p_after_plane(long long n, const double *__restrict__ z, double z_plane,
+                                     double *__restrict__ ux, double *__restrict__ uy, double *__restrict__ uz,
+                                     double *__restrict__ inv_gamma, const double *__restrict__ Ex,
+                                     const double *__restrict__ Ey, const double *__restrict__ Ez,
+                                     const double *__restrict__ Bx, const double *__restrict__ By,
+                                     const double *__restrict__ Bz, double econst, double bconst) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n || !(z[i] > z_plane)) return;
+    vay_push(i, ux, uy, uz, inv_gamma, Ex, Ey, Ez, Bx, By, Bz, econst, bconst);
 }
 
 // ---- laser antenna: virtual particles -------------------------------------------------------------
@@ -239,6 +249,77 @@ __global__ void k_select_crossing(long long n, const double *__restrict__ z, con
     if ((zc >= z_curr && zp <= z_prev) || (zc <= z_curr && zp >= z_prev)) {
         const unsigned long long pos = atomicAdd(count, 1ULL);
         if ((long long)pos < cap) idx[pos] = i;
+    }
+}
+
+// ---- ADK ionization (fbpic/particles/elementary_process/ionization) ------------------------------------------
+// push_p_ioniz_gpu (push/cuda_methods.py:134-170): the charge of an ionizable macroparticle is level * e; neutral
+// ones are not pushed.  econst1, bconst1: the constants of the Vay push for a charge e.
+__global__ void k_push_p_ioniz(long long n, const unsigned long long *__restrict__ level, double *__restrict__ ux,
+                               double *__restrict__ uy, double *__restrict__ uz, double *__restrict__ inv_gamma,
+                               const double *__restrict__ Ex, const double *__restrict__ Ey,
+                               const double *__restrict__ Ez, const double *__restrict__ Bx,
+                               const double *__restrict__ By, const double *__restrict__ Bz, double econst1,
+                               double bconst1) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n || level[i] == 0) return;
+    const double q = (double)level[i];
+    vay_push(i, ux, uy, uz, inv_gamma, Ex, Ey, Ez, Bx, By, Bz, econst1 * q, bconst1 * q);
+}
+
+// w_times_level = w * level: the effective weight of the ions in the deposition (ionizer.py:108-109, 
+// numba_methods.py:67)
+__global__ void k_w_times_level(long long n, const double *__restrict__ w, const unsigned long long *__restrict__ level,
+                                double *__restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = w[i] * (double)level[i];
+}
+
+// uniform number in [0, 1) from a counter: splitmix64 of (seed, draw index); one independent stream per (cycle, ion)
+__device__ __forceinline__ double uniform01(unsigned long long seed, unsigned long long counter) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (counter + 1ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (double)(z >> 11) * (1. / 9007199254740992.);
+}
+
+// ionize_ions_cuda (ionization/cuda_methods.py:16-71, inline_functions.py:9-45): field amplitude in the rest frame of
+// the ion, ADK probability over the proper time of one cycle, one draw per ion; an ionized ion moves up one level and
+// its index and former level are appended to `events` (2 entries each; any order, the caller sorts).  `draws`: host
+// numbers in [0, 1) (parity tests) or null: counter-based generator.  The reference counts per batch of 10 ions and
+// needs a host cumulative sum plus a second pass to place the electrons; here the short event list is all the host
+// reads back.
+__global__ void k_ionize(long long n, unsigned long long *__restrict__ level, int level_max,
+                         const double *__restrict__ adk_prefactor, const double *__restrict__ adk_power,
+                         const double *__restrict__ adk_exp_prefactor, const double *__restrict__ ux,
+                         const double *__restrict__ uy, const double *__restrict__ uz, const double *__restrict__ Ex,
+                         const double *__restrict__ Ey, const double *__restrict__ Ez, const double *__restrict__ Bx,
+                         const double *__restrict__ By, const double *__restrict__ Bz, double c_light,
+                         const double *__restrict__ draws, unsigned long long seed, long long cap,
+                         long long *__restrict__ events, unsigned long long *__restrict__ count) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long lv = level[i];
+    if (lv >= (unsigned long long)level_max) return;
+    const double vx = ux[i], vy = uy[i], vz = uz[i], ex = Ex[i], ey = Ey[i], ez = Ez[i];
+    const double bx = c_light * Bx[i], by = c_light * By[i], bz = c_light * Bz[i];
+    const double u_dot_E = vx * ex + vy * ey + vz * ez;
+    const double gamma = sqrt(1 + vx * vx + vy * vy + vz * vz);
+    const double a = gamma * ex + vy * bz - vz * by, b = gamma * ey + vz * bx - vx * bz,
+                 d = gamma * ez + vx * by - vy * bx;
+    const double E = sqrt(-u_dot_E * u_dot_E + a * a + b * b + d * d);
+    if (E == 0) return;
+    const double w_dtau = 1. / gamma * adk_prefactor[lv] * pow(E, adk_power[lv]) * exp(adk_exp_prefactor[lv] / E);
+    const double p = 1. - exp(-w_dtau);
+    const double r = draws ? draws[i] : uniform01(seed, (unsigned long long)i);
+    if (r < p) {
+        level[i] = lv + 1;
+        const unsigned long long pos = atomicAdd(count, 1ULL);
+        if ((long long)pos < cap) {
+            events[2 * pos] = i;
+            events[2 * pos + 1] = (long long)lv;
+        }
     }
 }
 

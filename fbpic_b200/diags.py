@@ -266,7 +266,8 @@ class ParticleChargeDensityDiagnostic(FieldDiagnostic):
 
 
 _COMPONENTS = {'position': ('x', 'y', 'z'), 'momentum': ('ux', 'uy', 'uz'), 'weighting': ('w',),
-               'gamma': ('gamma',), 'E': ('Ex', 'Ey', 'Ez'), 'B': ('Bx', 'By', 'Bz'), 'id': ('id',)}
+               'gamma': ('gamma',), 'E': ('Ex', 'Ey', 'Ez'), 'B': ('Bx', 'By', 'Bz'), 'id': ('id',),
+               'charge': ('charge',)}
 
 
 class ParticleDiagnostic(OpenPMDDiagnostic):
@@ -286,14 +287,16 @@ class ParticleDiagnostic(OpenPMDDiagnostic):
             if q not in _COMPONENTS:
                 raise ValueError("Invalid string in particle_data: %s" % q)
         self.species_dict, self.select, self.subsampling_fraction = dict(species), select, subsampling_fraction
-        self.particle_data = [q for q in particle_data if q != 'id']
+        self.particle_data = [q for q in particle_data if q not in ('id', 'charge')]
         # E, B at the particles only exist as arrays after the unfused gather (the fused gather + push keeps them
         # in registers): Simulation.step looks at this flag
         self.needs_gathered_fields = ('E' in self.particle_data) or ('B' in self.particle_data)
 
     def _records(self, species):
-        """tracked species get their ids written as well (particle_diag.py:111-116)"""
-        return self.particle_data + (['id'] if species.tracker is not None else [])
+        """tracked species get their ids written as well, ionizable ones their per-particle charge
+        (particle_diag.py:111-128)"""
+        return self.particle_data + (['id'] if species.tracker is not None else []) \
+            + (['charge'] if species.ionizer is not None else [])
 
     @staticmethod
     def _attr(sp, name):
@@ -301,6 +304,9 @@ class ParticleDiagnostic(OpenPMDDiagnostic):
             return 1. / _host(sp.inv_gamma)
         if name == 'id':
             return _host(sp.tracker.id)
+        if name == 'charge':
+            from scipy.constants import e
+            return e * _host(sp.ionizer.levels.id).astype(np.float64)
         return _host(getattr(sp, name))
 
     def apply_selection(self, species):
@@ -325,6 +331,8 @@ class ParticleDiagnostic(OpenPMDDiagnostic):
             grp.attrs[key] = _text(value)
         one = np.array([1], dtype=np.uint64)
         for record, value in (('mass', species.m), ('charge', species.q)):
+            if record == 'charge' and species.ionizer is not None:
+                continue                      # per-particle record instead (particle_diag.py:124-128)
             node = grp.require_group(record)
             self.setup_openpmd_species_record(node, record)
             self.setup_openpmd_component(node)
@@ -589,6 +597,9 @@ class ParticleCatcher(object):
         if species.m > 0:                          # openPMD: momenta in kg m/s
             for k in ('ux', 'uy', 'uz'):
                 data[k] = data[k] * (species.m * c)
+        if 'charge' in data:                       # ionization level -> charge in C
+            from scipy.constants import e
+            data['charge'] = data['charge'] * e
         return data
 
     def get_particle_slice(self, species, z_curr, z_prev):
@@ -602,6 +613,8 @@ class ParticleCatcher(object):
             out = {k: np.take(np.asarray(getattr(species, k))[:n], keep) for k in self.ATTRS}
             if species.tracker is not None:
                 out['id'] = np.take(np.asarray(species.tracker.id)[:n], keep)
+            if species.ionizer is not None:
+                out['charge'] = np.take(np.asarray(species.ionizer.levels.id)[:n], keep)
             return out
         import ctypes
         ctx = _lib.context().handle
@@ -619,23 +632,24 @@ class ParticleCatcher(object):
             cap = int(found.value)                 # the buffer was too small: the count is exact, run again
         k = int(found.value)
         tracked = species.tracker is not None
+        extra = ([('id', species.tracker.id)] if tracked else []) + \
+            ([('charge', species.ionizer.levels.id)] if species.ionizer is not None else [])
         if k == 0:
             out = {name: np.zeros(0) for name in self.ATTRS}
-            if tracked:
-                out['id'] = np.zeros(0, dtype=np.uint64)
+            out.update({name: np.zeros(0, dtype=np.uint64) for name, _ in extra})
             return out
         idx = self._idx.view((k,))
         idx.set(np.sort(idx.get()))                # particle-array order, whatever order the atomics produced
-        rows = len(self.ATTRS) + (1 if tracked else 0)
+        rows = len(self.ATTRS) + len(extra)
         if self._packed is None or self._packed.size < rows * k:
             self._packed = DeviceArray(rows * k, np.float64)
-        src = [getattr(species, name) for name in self.ATTRS] + ([species.tracker.id] if tracked else [])
+        src = [getattr(species, name) for name in self.ATTRS] + [a for _, a in extra]
         dst = [self._packed.ptr + 8 * k * r for r in range(rows)]
         call.b2_permute(ctx, k, idx.ptr, rows, _lib.ptr_array(src), _lib.ptr_array(dst), None)
         packed = self._packed.view((rows, k)).get()
         out = {name: packed[r] for r, name in enumerate(self.ATTRS)}
-        if tracked:
-            out['id'] = packed[rows - 1].view(np.uint64)
+        for j, (name, _) in enumerate(extra):
+            out[name] = packed[len(self.ATTRS) + j].view(np.uint64)
         return out
 
     def interpolate_particles_to_lab_frame(self, d, current_z_boost, t):

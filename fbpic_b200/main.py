@@ -124,7 +124,8 @@ class Simulation(object):
 
         for species in ptcl:
             if not species.data_is_on_gpu:
-                species.fields_resident_only = bool(fuse_gp) and not species.ballistic_before_plane
+                species.fields_resident_only = bool(fuse_gp) and not species.ballistic_before_plane and \
+                    species.ionizer is None
             elif not fuse_gp:
                 species.fields_resident_only = False      # an unfused gather will write them: read them back
         import time as _time
@@ -171,7 +172,7 @@ class Simulation(object):
                 for diag in self.diags:                   # E, B, rho, x at time n (main.py:474-481)
                     diag.write(self.iteration)
                 for species in ptcl:
-                    if species.ballistic_before_plane:
+                    if species.ballistic_before_plane or species.ionizer is not None:
                         # the fused kernel pushes every particle: this species takes the three-kernel route
                         species.gather(fld.interp, self.comm)
                         species.push_p(self.time + 0.5 * dt)
@@ -200,6 +201,9 @@ class Simulation(object):
                 antenna.push_x(0.5 * dt)
             if self.use_galilean:
                 self.shift_galilean_boundaries(0.5 * dt)
+            # elementary processes at t = (n + 1/2) dt, positions and momenta synchronised (main.py:499-503)
+            for species in ptcl:
+                species.handle_elementary_processes(self.time + 0.5 * dt)
             for species in ptcl:
                 species.keep_fields_sorted = False
 
@@ -211,7 +215,7 @@ class Simulation(object):
             # species deposits and already has sort locality
             fuse_pr = self.fused and move_positions and len(ptcl) > 0 and (not cross) and \
                 all((sp.q != 0) and (not sp.is_tracer) and getattr(sp, '_order_matches_prefix', False)
-                    for sp in ptcl)
+                    and sp.ionizer is None for sp in ptcl)
             for antenna in self.laser_antennas:           # main.py:520-522
                 antenna.push_x(0.5 * dt)
             if fuse_pr:

@@ -187,6 +187,24 @@ class ParticleTracker(object):
             self.id, self.spare = self.id.view((n,)), self.spare.view((n,))
 
 
+class LevelCarrier(ParticleTracker):
+    """The ionization level of every macroparticle of an ionizable species: one more 8-byte array that follows the
+    particles through the cell sort and the particle exchange exactly like the tracked ids (same `id` / `spare` /
+    `swap` plumbing); particles that enter (continuous injection) start at `level_start`
+    (particles.py:370-372; particle_buffer_handling.py:120-172, 413-417)."""
+
+    def __init__(self, level_start, N):
+        self.level_start = int(level_start)
+        self.id = self.generate_new_ids(N)
+        self.spare = None
+
+    def generate_new_ids(self, N):
+        return np.full(N, self.level_start, dtype=np.uint64)
+
+    def overwrite_ids(self, levels, comm=None):
+        self.id = np.array(levels, dtype=np.uint64)
+
+
 class Particles(object):
     """One species.  At the end/start of a PIC cycle the momenta are half a step
     behind the positions (particles.py:62-63)."""
@@ -282,8 +300,10 @@ class Particles(object):
             else:
                 d.set(np.asarray(getattr(self, k), dtype=np.float64))
             setattr(self, k, d)
-        if self.tracker is not None:
-            self.tracker.send_to_gpu(self._capacity)
+        for carrier in self.uint_carriers():
+            carrier.send_to_gpu(self._capacity)
+        if self.ionizer is not None:
+            self.ionizer.send_to_gpu(self)
         self._alloc_sort_arrays()
         self.sorted = False
         self.data_is_on_gpu = True
@@ -298,8 +318,10 @@ class Particles(object):
             # fused gather+push keeps the gathered fields in registers: the device arrays still hold the zeros
             # they were created with, so the host gets zeros without a copy
             setattr(self, k, np.zeros(self.Ntot) if self.fields_resident_only else _lib.to_host(getattr(self, k)))
-        if self.tracker is not None:
-            self.tracker.receive_from_gpu()
+        if self.ionizer is not None:
+            self.ionizer.receive_from_gpu(self)
+        for carrier in self.uint_carriers():
+            carrier.receive_from_gpu()
         self.data_is_on_gpu = False
 
     def resize_device_arrays(self, new_arrays, n_new):
@@ -358,6 +380,14 @@ class Particles(object):
             return
         self._need_gpu()
         ctx = _lib.context()
+        if self.ionizer is not None:                              # particles.py:590-597
+            if isinstance(self.injector, BallisticBeforePlane):
+                raise NotImplementedError('Ballistic injection before a plane is not implemented for ionizable '
+                                          'particles.')
+            call.b2_push_p_ioniz(ctx.handle, self.Ntot, self.ionizer.levels.id.ptr, self.ux.ptr, self.uy.ptr,
+                                 self.uz.ptr, self.inv_gamma.ptr, self.Ex.ptr, self.Ey.ptr, self.Ez.ptr, self.Bx.ptr,
+                                 self.By.ptr, self.Bz.ptr, self.m, self.dt, None)
+            return
         if isinstance(self.injector, BallisticBeforePlane):       # particles.py:577-578, 599-606
             call.b2_push_p_after_plane(ctx.handle, self.Ntot, self.z.ptr, self.injector.get_current_plane_position(t),
                                        self.ux.ptr, self.uy.ptr, self.uz.ptr, self.inv_gamma.ptr,
@@ -470,15 +500,22 @@ class Particles(object):
             self.sorting_buffers[i] = src[i]
         self._permute_ids(self.sorted_idx.ptr)
 
+    def uint_carriers(self):
+        """the 8-byte integer arrays that travel with the particles: tracked ids, ionization levels"""
+        out = [self.tracker] if self.tracker is not None else []
+        if self.ionizer is not None:
+            out.append(self.ionizer.levels)
+        return out
+
     def _permute_ids(self, sorted_idx_ptr):
-        """The tracked ids follow the sort (particles.py:541-542); sorted_idx_ptr None: the permutation of the
-        last b2_sort_cells on this context."""
-        if self.tracker is None:
-            return
-        t = self.tracker
-        call.b2_permute(_lib.context().handle, self.Ntot, sorted_idx_ptr, 1, ptr_array([t.id]), ptr_array([t.spare]),
-                        None)
-        t.swap()
+        """The tracked ids and ionization levels follow the sort (particles.py:541-545); sorted_idx_ptr None: the
+        permutation of the last b2_sort_cells on this context."""
+        for t in self.uint_carriers():
+            call.b2_permute(_lib.context().handle, self.Ntot, sorted_idx_ptr, 1, ptr_array([t.id]),
+                            ptr_array([t.spare]), None)
+            t.swap()
+        if self.ionizer is not None:
+            self.ionizer.update_weights(self)
 
     # ------------------------------------------------------------------ deposition
     def deposit_fused(self, fld, fieldtype, push=None):
@@ -492,6 +529,9 @@ class Particles(object):
         The API-visible `cell_idx` / `sorted_idx` are refreshed only by sort_particles()."""
         if self.q == 0:
             return
+        if self.ionizer is not None:        # per-particle charge: the plain sort + deposit sequence, weight w * level
+            assert push is None
+            return self.deposit(fld, fieldtype)
         assert fieldtype in ('rho', 'J')
         self._need_gpu()
         ctx = _lib.context()
@@ -571,6 +611,8 @@ class Particles(object):
             self.sort_particles(fld=fld)
             self.sorted = True
         ctx = _lib.context()
+        # ionizable species: charge e, weight w * level (particles.py:875-880)
+        weight = self.ionizer.w_times_level if self.ionizer is not None else self.w
         grid = fld.interp
         g0 = grid[0]
         Nm = len(grid)
@@ -579,12 +621,12 @@ class Particles(object):
         r0 = getattr(grid[0], attr)
         rh = getattr(grid[1 if Nm > 1 else 0], attr)
         if fieldtype == 'rho':
-            call.b2_deposit_rho(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr, self.w.ptr, self.q,
+            call.b2_deposit_rho(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr, weight.ptr, self.q,
                                 g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, Nm,
                                 ptr_array([g.rho for g in grid]), self.prefix_sum.ptr, r0.ptr, rh.ptr,
                                 int(cubic), None)
         else:
-            call.b2_deposit_J(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr, self.w.ptr, self.q,
+            call.b2_deposit_J(ctx.handle, self.Ntot, self.x.ptr, self.y.ptr, self.z.ptr, weight.ptr, self.q,
                               self.ux.ptr, self.uy.ptr, self.uz.ptr, self.inv_gamma.ptr,
                               g0.invdz, g0.zmin, g0.Nz, g0.invdr, g0.rmin, g0.Nr, Nm,
                               ptr_array([getattr(g, k) for g in grid for k in ('Jr', 'Jt', 'Jz')]),
@@ -592,12 +634,56 @@ class Particles(object):
 
     # ------------------------------------------------------------------ out of scope hooks
     def handle_elementary_processes(self, t):
-        """No ionization / Compton in this build (out of scope)."""
-        return
+        """Ionization (particles.py:497-509); Compton scattering is not built."""
+        if self.ionizer is not None:
+            self.ionizer.handle_ionization(self)
 
     def make_ionizable(self, element, target_species, level_start=0, level_max=None):
-        """particles.py:398-468 -- not built: refused, so that a script relying on it cannot run silently without."""
-        raise NotImplementedError('ADK ionization (Particles.make_ionizable) is outside of this build.')
+        """ADK ionization of this species; the freed electrons go to `target_species` (a `Particles` object, or
+        {level: Particles}) (particles.py:398-495).  The charge becomes e: the deposition uses w * level as weight."""
+        from .ionization import Ionizer
+        if self.data_is_on_gpu:
+            raise _lib.B200Error('make_ionizable acts on the host copy of the data: call it before step()')
+        from scipy.constants import e
+        self.ionizer = Ionizer(element, self, target_species, level_start, level_max=level_max)
+        self.q = e
+
+    def grow_device_arrays(self, n_new, new_uint=None):
+        """Room for n_new - Ntot more particles at the end of every per-particle device array (the caller fills the
+        8 state arrays of the new ones; their gathered fields are zero until the next gather).  `new_uint`: callable
+        carrier -> values of the new entries of that 8-byte array (default: `carrier.generate_new_ids`)."""
+        old_n = self.Ntot
+        add = n_new - old_n
+        if n_new <= self._capacity:
+            for k in FLOAT_ATTRS + FIELD_ATTRS:
+                setattr(self, k, getattr(self, k).view((n_new,)))
+            self.sorting_buffers = [b.view((n_new,)) for b in self.sorting_buffers]
+            self.cell_idx, self.sorted_idx = self.cell_idx.view((n_new,)), self.sorted_idx.view((n_new,))
+            for t in self.uint_carriers():
+                t.id, t.spare = t.id.view((n_new,)), t.spare.view((n_new,))
+        else:
+            cap = self._capacity_for(n_new)
+            for k in FLOAT_ATTRS + FIELD_ATTRS:
+                d = DeviceArray(cap, np.float64).view((n_new,))
+                d.view((old_n,)).copy_from(getattr(self, k))
+                setattr(self, k, d)
+            for t in self.uint_carriers():
+                d = DeviceArray(cap, np.uint64).view((n_new,))
+                d.view((old_n,)).copy_from(t.id)
+                t.id, t.spare = d, DeviceArray(cap, np.uint64).view((n_new,))
+            self._capacity = cap
+            self.Ntot = n_new
+            self._alloc_sort_arrays()
+        for k in FIELD_ATTRS:
+            call.b2_memset(getattr(self, k).ptr + 8 * old_n, 0, 8 * add, None)
+        for t in self.uint_carriers():
+            values = t.generate_new_ids(add) if new_uint is None else new_uint(t)
+            t.id.view((add,), byte_offset=8 * old_n).set(values)
+        self.Ntot = n_new
+        self._order_matches_prefix = False
+        self._keys_fresh = False
+        self._j_since_sort = 0
+        self.sorted = False
 
     def activate_compton(self, target_species, laser_energy, laser_wavelength, laser_waist, laser_ctau,
                          laser_initial_z0, ratio_w_electron_photon, boost=None):

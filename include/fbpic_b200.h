@@ -314,6 +314,24 @@ int b2_axpy(b2_ctx *ctx, int64_t n, double a, const double *d_x, double *d_y, vo
 /* back-transformed diagnostics: extract_slice_cuda (fbpic/openpmd_diag/boosted_field_diag.py:745-820).
  * d_fields10: host array of the 10 device grids Er, Et, Ez, Br, Bt, Bz, Jr, Jt, Jz, rho (complex [Nz, Nr]) of
  * mode m; d_slice: real [10][2 Nm - 1][Nr_out]; rows iz, iz + 1 weighted by Sz, 1 - Sz (x2 for m > 0). */
+/* ADK ionization (fbpic/particles/elementary_process/ionization/).
+ * b2_push_p_ioniz: push_p_ioniz_gpu (push/cuda_methods.py:134-170), charge = d_level[i] * e, neutral ones skipped.
+ * b2_w_times_level: d_out = d_w * d_level, the deposition weight of the ions (ionizer.py:108-109).
+ * b2_ionize: ionize_ions_cuda (ionization/cuda_methods.py:16-71): one ADK draw per ion below level_max with the
+ *   per-level tables adk_* (ionizer.py:166-183); an ionized ion moves up one level; its index and former level are
+ *   appended to d_events (2 x int64 each, capacity cap events, any order).  *h_count: number of events (exact also
+ *   when it exceeds cap: call again is NOT possible, the levels have changed -- give cap = n).  d_draws: uniform
+ *   numbers in [0, 1), one per ion, or NULL: counter-based generator keyed by (seed, ion index).
+ *   The call synchronises the stream. */
+int b2_push_p_ioniz(b2_ctx *ctx, int64_t n, const uint64_t *d_level, double *d_ux, double *d_uy, double *d_uz,
+                    double *d_inv_gamma, const double *d_Ex, const double *d_Ey, const double *d_Ez,
+                    const double *d_Bx, const double *d_By, const double *d_Bz, double m, double dt, void *stream);
+int b2_w_times_level(b2_ctx *ctx, int64_t n, const double *d_w, const uint64_t *d_level, double *d_out, void *stream);
+int b2_ionize(b2_ctx *ctx, int64_t n, uint64_t *d_level, int level_max, const double *d_adk_prefactor,
+              const double *d_adk_power, const double *d_adk_exp_prefactor, const double *d_ux, const double *d_uy,
+              const double *d_uz, const double *d_Ex, const double *d_Ey, const double *d_Ez, const double *d_Bx,
+              const double *d_By, const double *d_Bz, const double *d_draws, uint64_t seed, int64_t cap,
+              int64_t *d_events, int64_t *d_count, int64_t *h_count, void *stream);
 /* lab-frame particle output: ParticleCatcher.get_particle_slice (fbpic/openpmd_diag/boosted_particle_diag.py:598-629).
  * Appends to d_idx (capacity cap) the indices of the particles for which
  *   (z >= z_curr and z_old <= z_prev) or (z <= z_curr and z_old >= z_prev),  z_old = z - uz inv_gamma c dt,

@@ -540,7 +540,40 @@ def gen_lab_diags():
     save('diags_lab_tree', **out)
 
 
+def gen_ionization():
+    """ADK tables of the reference's Ionizer for a few elements and its per-particle probability on random inputs
+    (ionization/ionizer.py:137-183, inline_functions.py:9-45)."""
+    import types
+    from fbpic.particles.elementary_process.ionization.ionizer import Ionizer
+    from fbpic.particles.elementary_process.ionization.inline_functions import get_E_amplitude, \
+        get_ionization_probability
+    out = dict(dt=1.3e-16)
+    for element in ('H', 'He', 'N', 'Ar', 'Kr'):
+        ion = types.SimpleNamespace(level_max=None)
+        Ionizer.initialize_ADK_parameters(ion, element, 1.3e-16)
+        out[element + '_prefactor'], out[element + '_power'], out[element + '_exp_prefactor'] = \
+            ion.adk_prefactor, ion.adk_power, ion.adk_exp_prefactor
+    rng = np.random.default_rng(51)
+    n = 600
+    u = rng.normal(size=(3, n)) * np.array([0.5, 0.5, 3.])[:, None]
+    E = rng.normal(size=(3, n)) * 4.e12
+    B = rng.normal(size=(3, n)) * 1.e4
+    level = rng.integers(0, 7, n)
+    ion = types.SimpleNamespace(level_max=None)
+    Ionizer.initialize_ADK_parameters(ion, 'N', 1.3e-16)
+    p = np.zeros(n)
+    amp = np.zeros(n)
+    for i in range(n):
+        amp[i], g = get_E_amplitude(u[0, i], u[1, i], u[2, i], E[0, i], E[1, i], E[2, i], c * B[0, i], c * B[1, i],
+                                    c * B[2, i])
+        p[i] = get_ionization_probability(amp[i], g, ion.adk_prefactor[level[i]], ion.adk_power[level[i]],
+                                          ion.adk_exp_prefactor[level[i]])
+    out.update(u=u, E=E, B=B, level=level, amplitude=amp, probability=p)
+    save('ionization', **out)
+
+
 GENERATORS = {
+    'ionization': gen_ionization,
     'diags_tree': gen_diags,
     'cpu_gpu_deposition_linear': lambda: gen_cpu_gpu_deposition('linear'),
     'cpu_gpu_deposition_cubic': lambda: gen_cpu_gpu_deposition('cubic'),

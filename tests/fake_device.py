@@ -589,6 +589,29 @@ class FakeLib(object):
         return self.emu.emu_axpy(ctypes.c_longlong(n), ctypes.c_double(a), ctypes.c_void_p(_addr(x)),
                                  ctypes.c_void_p(_addr(y)))
 
+    def b2_push_p_ioniz(self, ctx, n, level, ux, uy, uz, ig, Ex, Ey, Ez, Bx, By, Bz, m, dt, stream):
+        V, D = ctypes.c_void_p, ctypes.c_double
+        e, c = 1.602176634e-19, 299792458.
+        return self.emu.emu_push_p_ioniz(ctypes.c_longlong(n), V(_addr(level)),
+                                         *[V(_addr(p)) for p in (ux, uy, uz, ig, Ex, Ey, Ez, Bx, By, Bz)],
+                                         D(e * dt / (m * c)), D(0.5 * e * dt / m))
+
+    def b2_w_times_level(self, ctx, n, w, level, out, stream):
+        V = ctypes.c_void_p
+        return self.emu.emu_w_times_level(ctypes.c_longlong(n), V(_addr(w)), V(_addr(level)), V(_addr(out)))
+
+    def b2_ionize(self, ctx, n, level, level_max, pre, pw, ex, ux, uy, uz, Ex, Ey, Ez, Bx, By, Bz, draws, seed, cap,
+                  events, d_count, h_count, stream):
+        if not _addr(d_count):
+            return -3
+        V, D = ctypes.c_void_p, ctypes.c_double
+        rc = self.emu.emu_ionize(ctypes.c_longlong(n), V(_addr(level)), level_max, V(_addr(pre)), V(_addr(pw)),
+                                 V(_addr(ex)), *[V(_addr(p)) for p in (ux, uy, uz, Ex, Ey, Ez, Bx, By, Bz)],
+                                 D(299792458.), V(_addr(draws)), ctypes.c_ulonglong(seed), ctypes.c_longlong(cap),
+                                 V(_addr(events)), V(_addr(d_count)))
+        h_count._obj.value = int(_arr(d_count, 1, np.int64)[0])
+        return rc
+
     def b2_select_crossing(self, ctx, n, z, uz, ig, c_light, dt, z_curr, z_prev, cap, idx, d_count, h_count, stream):
         if not _addr(d_count):
             return -3

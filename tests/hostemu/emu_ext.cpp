@@ -76,6 +76,31 @@ int emu_axpy(long long n, double a, const double *x, double *y) {
     return 0;
 }
 
+int emu_push_p_ioniz(long long n, const unsigned long long *level, double *ux, double *uy, double *uz, double *ig,
+                     const double *Ex, const double *Ey, const double *Ez, const double *Bx, const double *By,
+                     const double *Bz, double econst1, double bconst1) {
+    EMU_LAUNCH(emu_dim3((unsigned)((n + 255) / 256)), emu_dim3(256), b2ext::k_push_p_ioniz, n, level, ux, uy, uz, ig, Ex,
+               Ey, Ez, Bx, By, Bz, econst1, bconst1);
+    return 0;
+}
+
+int emu_w_times_level(long long n, const double *w, const unsigned long long *level, double *out) {
+    EMU_LAUNCH(emu_dim3((unsigned)((n + 255) / 256)), emu_dim3(256), b2ext::k_w_times_level, n, w, level, out);
+    return 0;
+}
+
+int emu_ionize(long long n, unsigned long long *level, int level_max, const double *pre, const double *pw,
+               const double *ex, const double *ux, const double *uy, const double *uz, const double *Ex,
+               const double *Ey, const double *Ez, const double *Bx, const double *By, const double *Bz,
+               double c_light, const double *draws, unsigned long long seed, long long cap, long long *events,
+               unsigned long long *count) {
+    *count = 0;
+    if (n > 0)
+        EMU_LAUNCH(emu_dim3((unsigned)((n + 255) / 256)), emu_dim3(256), b2ext::k_ionize, n, level, level_max, pre, pw,
+                   ex, ux, uy, uz, Ex, Ey, Ez, Bx, By, Bz, c_light, draws, seed, cap, events, count);
+    return 0;
+}
+
 int emu_select_crossing(long long n, const double *z, const double *uz, const double *inv_gamma, double c_light,
                         double dt, double z_curr, double z_prev, long long cap, long long *idx,
                         unsigned long long *count) {

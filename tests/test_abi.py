@@ -78,6 +78,8 @@ def test_ctypes_argument_counts_match_header():
                 ok = t is ctypes.c_double
             elif p.startswith('int64_t'):
                 ok = t is ctypes.c_int64
+            elif p.startswith('uint64_t'):
+                ok = t is ctypes.c_uint64
             elif p.startswith('size_t'):
                 ok = t is ctypes.c_size_t
             else:

@@ -1,0 +1,283 @@
+"""GPU tests of ADK ionization (fbpic_b200/ionization.py; fbpic/particles/elementary_process/ionization/): the
+kernel-level pieces against the formulas of the reference, and the reference's own acceptance test
+(tests/test_ionization.py, Chen et al. JCP 2013 figure 2) as written, lab frame and boosted frame."""
+import math
+import shutil
+import numpy as np
+import pytest
+from scipy.constants import c, m_e, m_p, e
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_ionization(gamma_boost, use_separate_electron_species, tmp_path):
+    """tests/test_ionization.py:27-170: a Gaussian laser pulse (a0 = 1.8, plane wave through ExternalField) crosses
+    a slab of N2+ ions; afterwards about 1/3 of them are N5+."""
+    from fbpic_b200 import Simulation
+    from fbpic_b200.lpa_utils.external_fields import ExternalField
+    from fbpic_b200.lpa_utils.boosted_frame import BoostConverter
+    from fbpic_b200.openpmd_diag import ParticleDiagnostic, BackTransformedParticleDiagnostic
+    from fbpic_b200.diags import read_diag, list_iterations
+    zmax_lab, zmin_lab, Nr, rmax, Nm = 20.e-6, 0.e-6, 3, 10.e-6, 2
+    p_zmin, p_zmax, p_rmin, p_rmax, n_atoms, p_nz, p_nr, p_nt = 5.e-6, 15.e-6, 0., 100.e-6, 0.2, 2, 1, 4
+    boost = BoostConverter(gamma_boost)
+    beta_boost = np.sqrt(1. - 1. / gamma_boost**2)
+    zmin, zmax = boost.static_length([zmin_lab, zmax_lab])
+    p_zmin, p_zmax = boost.static_length([p_zmin, p_zmax])
+    n_atoms, = boost.static_density([n_atoms])
+    if gamma_boost > 1:
+        p_nz = int(2 * gamma_boost * (1 + beta_boost) * p_nz)
+    a0, lambda0_lab = 1.8, 0.8e-6
+    lambda0, = boost.copropag_length([lambda0_lab], beta_object=1.)
+    ctau = 10. * lambda0
+    z0 = -2 * ctau
+    omega = 2 * np.pi * c / lambda0
+    E0 = a0 * m_e * c * omega / e
+    B0 = E0 / c
+
+    def laser_func(F, x, y, z, t, amplitude, length_scale):
+        return (F + amplitude * math.cos(2 * np.pi * (z - c * t) / lambda0)
+                * math.exp(-(z - c * t - z0)**2 / ctau**2))
+
+    dz = lambda0 / 16.
+    dt = dz / c
+    Nz = int((zmax - zmin) / dz) + 1
+    N_step = int((2. * 40. * lambda0 + zmax - zmin) / (dz * (1 + beta_boost))) + 1
+    uz_m, = boost.longitudinal_momentum([0.])
+    v_plasma, = boost.velocity([0.])
+    diag_period = N_step - 1
+    level_start = 2
+    np.random.seed(0)
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, zmin=zmin, v_comoving=v_plasma, use_galilean=False,
+                     boundaries={'z': 'open', 'r': 'reflective'})
+    kw = dict(p_nz=p_nz, p_nr=p_nr, p_nt=p_nt, p_zmin=p_zmin, p_zmax=p_zmax, p_rmin=p_rmin, p_rmax=p_rmax,
+              continuous_injection=False, uz_m=uz_m)
+    elec = sim.add_new_species(q=-e, m=m_e, n=level_start * n_atoms, **kw)
+    ions = sim.add_new_species(q=0, m=14. * m_p, n=n_atoms, **kw)
+    if use_separate_electron_species:
+        level_max = 6
+        target_species = {i_level: sim.add_new_species(q=-e, m=m_e) for i_level in range(level_start, level_max)}
+    else:
+        target_species, level_max = elec, None
+    ions.make_ionizable(element='N', level_start=level_start, level_max=level_max, target_species=target_species)
+    sim.set_moving_window(v=v_plasma)
+    sim.external_fields = [ExternalField(laser_func, 'Ex', E0, 0.), ExternalField(laser_func, 'By', B0, 0.)]
+    sim.diags = [ParticleDiagnostic(diag_period, {"ions": ions},
+                                    particle_data=["position", "gamma", "weighting", "E", "B"],
+                                    write_dir=str(tmp_path / 'diags'), comm=sim.comm)]
+    if gamma_boost > 1:
+        T_sim_lab = (2. * 40. * lambda0_lab + zmax_lab - zmin_lab) / c
+        sim.diags.append(BackTransformedParticleDiagnostic(
+            zmin_lab, zmax_lab, v_lab=0., dt_snapshots_lab=T_sim_lab / 2., Ntot_snapshots_lab=3,
+            gamma_boost=gamma_boost, period=diag_period, fldobject=sim.fld, species={"ions": ions}, comm=sim.comm,
+            write_dir=str(tmp_path / 'lab_diags')))
+    n_elec_before = elec.Ntot
+    sim.step(N_step, use_true_rho=True)
+    w = ions.w
+    ioniz_level = ions.ionizer.ionization_level
+    ntot = w.sum()
+    n_N5 = w[ioniz_level == 5].sum()
+    N5_fraction = n_N5 / ntot
+    assert ((N5_fraction > 0.30) and (N5_fraction < 0.34)), N5_fraction
+    if use_separate_electron_species:
+        # The species of level i holds the electrons freed by ions leaving level i, i.e. by all the ions that are
+        # now above it -- minus those that left the box since (the reference's line, np.allclose(electrons,
+        # w[level == i].sum()) with weights of 1e-16 against the default atol of 1e-8, holds for any numbers).
+        for i_level in range(level_start, level_max):
+            freed, above = target_species[i_level].w.sum(), w[ioniz_level > i_level].sum()
+            assert 0.5 * above < freed <= above * (1 + 1e-12), (i_level, freed, above)
+        assert np.isclose(target_species[level_start].w.sum(), ntot, rtol=1e-12, atol=0)     # every ion left N2+
+    else:
+        assert elec.Ntot > n_elec_before
+    its = list_iterations(str(tmp_path / 'diags'))
+    d = read_diag(str(tmp_path / 'diags'), its[-1])
+    w_file, q_file = d['particles/ions/weighting'], d['particles/ions/charge']
+    n_N5_openpmd = np.sum(w_file[(4.5 * e < q_file) & (q_file < 5.5 * e)])
+    assert np.isclose(n_N5_openpmd, n_N5)
+    if gamma_boost > 1.:
+        its = list_iterations(str(tmp_path / 'lab_diags'))
+        d = read_diag(str(tmp_path / 'lab_diags'), its[-1])
+        w_file, q_file = d['particles/ions/weighting'], d['particles/ions/charge']
+        assert np.isclose(np.sum(w_file[(4.5 * e < q_file) & (q_file < 5.5 * e)]), n_N5)
+
+
+def test_ionization_labframe(tmp_path):
+    _run_ionization(1., True, tmp_path)
+
+
+def test_ionization_boostedframe(tmp_path):
+    _run_ionization(2., False, tmp_path)
+
+
+# ------------------------------------------------------------------ kernel level, through the C ABI
+def _dev(*arrays):
+    from fbpic_b200._lib import DeviceArray
+    return [DeviceArray.from_numpy(np.ascontiguousarray(a)) for a in arrays]
+
+
+def test_ionize_kernel_vs_reference_probabilities():
+    """b2_ionize against get_E_amplitude / get_ionization_probability of the reference on 600 random particles
+    (tests/golden/ionization.npz): with given draws exactly the ions with draw < p move up one level."""
+    import ctypes
+    from fbpic_b200 import _lib
+    from fbpic_b200._lib import DeviceArray
+    from test_hostemu_ext import _ionize_case
+    g, tables = _ionize_case()
+    n, level_max = len(g['level']), 6
+    draws = np.random.default_rng(7).uniform(size=n)
+    p = g['probability']
+    want = np.flatnonzero((draws < p) & (g['level'] < level_max))
+    d_level, = _dev(g['level'].astype(np.uint64))
+    d_tab = _dev(*tables)
+    d_arr = _dev(*g['u'], *g['E'], *g['B'])
+    d_draws, = _dev(draws)
+    events, count, found = DeviceArray(2 * n, np.int64), DeviceArray(1, np.int64), ctypes.c_int64(-1)
+    _lib.call.b2_ionize(_lib.context().handle, n, d_level.ptr, level_max, *[t.ptr for t in d_tab],
+                        *[a.ptr for a in d_arr], d_draws.ptr, 0, n, events.ptr, count.ptr, ctypes.byref(found), None)
+    k = found.value
+    ev = events.get()[:2 * k].reshape(k, 2)
+    ev = ev[np.argsort(ev[:, 0])]
+    assert np.array_equal(ev[:, 0], want) and np.array_equal(ev[:, 1], g['level'][want])
+    expect = g['level'].copy()
+    expect[want] += 1
+    assert np.array_equal(d_level.get(), expect.astype(np.uint64))
+    # the built-in generator: same seed, same events; right number on average
+    counts = []
+    for seed in (11, 11, 12):
+        d_level.set(g['level'].astype(np.uint64))
+        _lib.call.b2_ionize(_lib.context().handle, n, d_level.ptr, level_max, *[t.ptr for t in d_tab],
+                            *[a.ptr for a in d_arr], None, seed, n, events.ptr, count.ptr, ctypes.byref(found), None)
+        counts.append(found.value)
+    mean = np.where(g['level'] < level_max, p, 0.).sum()
+    sigma = np.sqrt(np.where(g['level'] < level_max, p * (1 - p), 0.).sum())
+    assert counts[0] == counts[1] and abs(counts[0] - mean) < 5 * sigma and abs(counts[2] - mean) < 5 * sigma
+
+
+def test_push_p_ioniz_and_weights():
+    """b2_push_p_ioniz (charge = level * e, neutral particles untouched) against the oracle's Vay push;
+    b2_w_times_level."""
+    from oracle import oracle as orc
+    from fbpic_b200 import _lib
+    from fbpic_b200._lib import DeviceArray
+    from conftest import assert_close
+    rng = np.random.default_rng(23)
+    n = 500
+    level = rng.integers(0, 4, n).astype(np.uint64)
+    u0 = [rng.normal(size=n) for _ in range(3)]
+    ig0 = 1. / np.sqrt(1. + u0[0]**2 + u0[1]**2 + u0[2]**2)
+    E = [rng.normal(size=n) * 1.e12 for _ in range(3)]
+    B = [rng.normal(size=n) * 3000. for _ in range(3)]
+    m, dt = 14. * m_p, 2.e-16
+    want = [a.copy() for a in u0] + [ig0.copy()]
+    for lv in range(1, 4):
+        sel = level == lv
+        part = [a[sel].copy() for a in want]
+        orc.push_p(*part, *[a[sel].copy() for a in E + B], lv * e, m, dt)
+        for w_, p_ in zip(want, part):
+            w_[sel] = p_
+    d_level, = _dev(level)
+    d_u = _dev(*u0, ig0)
+    d_f = _dev(*E, *B)
+    _lib.call.b2_push_p_ioniz(_lib.context().handle, n, d_level.ptr, *[a.ptr for a in d_u], *[a.ptr for a in d_f], m, dt,
+                              None)
+    for g_, w_, a, name in zip(d_u, want, u0 + [ig0], ('ux', 'uy', 'uz', 'inv_gamma')):
+        g_ = g_.get()
+        assert np.array_equal(g_[level == 0], a[level == 0]), name
+        assert_close(g_, w_, 1e-14, name)
+    w = rng.uniform(1., 2., n)
+    d_w, = _dev(w)
+    out = DeviceArray(n, np.float64)
+    _lib.call.b2_w_times_level(_lib.context().handle, n, d_w.ptr, d_level.ptr, out.ptr, None)
+    assert np.array_equal(out.get(), w * level)
+
+
+def _standing_field(sim, amplitude):
+    """a static longitudinal field in mode 0, strong enough for gradual ionization of nitrogen (no laser needed)"""
+    g = sim.fld.interp[0]
+    g.Ez[:, :] = amplitude * (1 + 0.3 * np.sin(2 * np.pi * g.z / 12.e-6))[:, None]
+
+
+def test_ionization_events_free_one_electron_each():
+    """Static ions in a field: after every call of step() the electron species has grown by exactly the number of
+    ionization events (sum of the level increases), the new electrons sit on ions and carry their weight, and the
+    deposition weight of the ions is w * level."""
+    from fbpic_b200 import Simulation
+    Nz, Nr, Nm, zmax, rmax = 48, 8, 2, 24.e-6, 8.e-6
+    np.random.seed(2)
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, zmax / Nz / c, zmin=0., n_order=-1, n_guard=12, n_damp={'z': 12, 'r': 4},
+                     boundaries={'z': 'open', 'r': 'reflective'})
+    kw = dict(p_zmin=9.e-6, p_zmax=15.e-6, p_rmax=6.e-6, p_nz=2, p_nr=2, p_nt=4, continuous_injection=False)
+    elec = sim.add_new_species(q=-e, m=m_e)
+    ions = sim.add_new_species(q=0, m=14. * m_p, n=1.e18, **kw)
+    ions.make_ionizable('N', target_species=elec, level_start=0, level_max=5)
+    assert ions.q == e and elec.Ntot == 0
+    _standing_field(sim, 1.5e11)
+    total = 0
+    for _ in range(3):
+        levels_before, n_before = ions.ionizer.ionization_level.sum(), elec.Ntot
+        sim.step(3, correct_currents=False)
+        lv = ions.ionizer.ionization_level
+        new = elec.Ntot - n_before
+        assert new == int(lv.sum() - levels_before) and lv.max() <= 5
+        assert np.array_equal(ions.ionizer.w_times_level, np.array(ions.w) * lv)
+        total += new
+    assert total > 50 and len(np.unique(lv)) > 1
+    assert set(np.round(np.array(elec.w) / ions.w[0], 9)) <= set(np.round(np.array(ions.w) / ions.w[0], 9))
+    assert np.array(elec.z).min() > 4.e-6 and np.array(elec.z).max() < 20.e-6
+
+
+def test_ionizable_species_through_window_sort_and_exchange():
+    """The ionization levels follow the ions through cell sorts, the removal at the left edge of a moving window and
+    the continuous injection at the right edge: an ion never loses charge, injected ions start at level_start, the
+    per-particle arrays keep the length of the species and the deposition weight stays w * level."""
+    from fbpic_b200 import Simulation
+    Nz, Nr, Nm, zmax, rmax = 48, 8, 2, 24.e-6, 8.e-6
+    np.random.seed(2)
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, zmax / Nz / c, zmin=0., n_order=-1, n_guard=12, n_damp={'z': 12, 'r': 4},
+                     boundaries={'z': 'open', 'r': 'reflective'})
+    kw = dict(p_zmin=4.e-6, p_zmax=200.e-6, p_rmax=6.e-6, p_nz=2, p_nr=2, p_nt=4)
+    elec = sim.add_new_species(q=-e, m=m_e, n=1.e18, **kw)
+    ions = sim.add_new_species(q=0, m=14. * m_p, n=1.e18, **kw)
+    ions.make_ionizable('N', target_species=elec, level_start=1)
+    ions.track(sim.comm)
+    sim.set_moving_window(v=c)
+    _standing_field(sim, 2.2e11)
+    seen = {}
+    n_first = ions.Ntot
+    for _ in range(4):
+        sim.step(5, correct_currents=False)
+        ids, lv = ions.tracker.id, ions.ionizer.ionization_level
+        assert len(lv) == ions.Ntot == len(ids) and lv.min() >= 1 and lv.max() <= 7
+        assert np.array_equal(ions.ionizer.w_times_level, np.array(ions.w) * lv)
+        for pid, level in zip(ids.tolist(), lv.tolist()):
+            assert level >= seen.get(pid, 1)
+            seen[pid] = level
+    assert len(seen) > n_first, 'no ion was injected'          # the window brought new ions in (and dropped others)
+    assert max(seen.values()) > 1, 'nothing was ionized'
+
+
+def test_grow_device_arrays_beyond_capacity():
+    """`Particles.grow_device_arrays` (room for freed electrons): within the allocated head room the arrays are
+    re-viewed, beyond it they are reallocated; the existing particles, their ids and fields are kept either way."""
+    from fbpic_b200 import Simulation, GpuMemoryManager
+    np.random.seed(1)
+    zmax, rmax = 8.e-6, 4.e-6
+    sim = Simulation(16, zmax, 8, rmax, 2, zmax / 16 / c, p_zmin=0, p_zmax=zmax, p_rmin=0, p_rmax=rmax, p_nz=1, p_nr=1,
+                     p_nt=4, n_e=1.e20)
+    sp = sim.ptcl[0]
+    sp.track(sim.comm)
+    n0 = sp.Ntot
+    x0, ids0 = np.array(sp.x), np.array(sp.tracker.id)
+    with GpuMemoryManager(sim):
+        cap0 = sp._capacity
+        sp.grow_device_arrays(n0 + 10)                       # fits
+        assert sp._capacity == cap0 and sp.Ntot == n0 + 10
+        sp.x.view((10,), byte_offset=8 * n0).set(np.arange(10.))
+        sp.grow_device_arrays(cap0 + 1000)                   # does not fit
+        assert sp._capacity > cap0 and sp.Ntot == cap0 + 1000 and sp.cell_idx.size == sp.Ntot
+        for k in ('y', 'z', 'ux', 'uy', 'uz', 'inv_gamma', 'w'):          # fill the rest: the data goes back to the host
+            getattr(sp, k).view((sp.Ntot - n0,), byte_offset=8 * n0).fill(0)
+        sp.x.view((sp.Ntot - n0 - 10,), byte_offset=8 * (n0 + 10)).fill(0)
+    assert np.array_equal(np.array(sp.x)[:n0], x0) and np.array_equal(np.array(sp.x)[n0:n0 + 10], np.arange(10.))
+    ids = np.array(sp.tracker.id)
+    assert np.array_equal(ids[:n0], ids0) and len(np.unique(ids)) == sp.Ntot == len(sp.Ex)

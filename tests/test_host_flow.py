@@ -28,6 +28,7 @@ import test_gpu_w4_scripts
 import test_gpu_w6_acceptance
 import test_gpu_w8_diags
 import test_gpu_w9_step_options
+import test_gpu_w9b_ionization
 
 
 @pytest.fixture
@@ -476,3 +477,17 @@ def test_console_output_flow(fake, capsys):
     sim.step(3, show_progress=True)
     out = capsys.readouterr().out
     assert '3/3' in out and 'ms/step' in out and 'Total time taken' in out
+
+
+@pytest.mark.parametrize('frame', ['labframe', 'boostedframe'])
+def test_ionization_as_written_flow(fake, frame, tmp_path):
+    """the reference's tests/test_ionization.py (N5+ fraction after a laser pulse, Chen et al. 2013)"""
+    getattr(test_gpu_w9b_ionization, 'test_ionization_' + frame)(tmp_path)
+
+
+def test_ionization_kernels_and_plumbing_flow(fake):
+    test_gpu_w9b_ionization.test_ionize_kernel_vs_reference_probabilities()
+    test_gpu_w9b_ionization.test_push_p_ioniz_and_weights()
+    test_gpu_w9b_ionization.test_grow_device_arrays_beyond_capacity()
+    test_gpu_w9b_ionization.test_ionization_events_free_one_electron_each()
+    test_gpu_w9b_ionization.test_ionizable_species_through_window_sort_and_exchange()

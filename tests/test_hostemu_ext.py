@@ -218,3 +218,90 @@ def test_emu_select_crossing(emu):
             assert np.array_equal(np.sort(idx[:len(want)]), want)
         else:
             assert np.all(np.isin(idx[:cap], want))
+
+
+def _ionize_case():
+    """inputs and probabilities of the reference's ADK functions for nitrogen (tests/golden/ionization.npz)"""
+    from conftest import load_golden
+    from fbpic_b200.ionization import Ionizer
+    import types
+    g = load_golden('ionization')
+    ion = types.SimpleNamespace(level_max=None)
+    Ionizer.initialize_ADK_parameters(ion, 'N', float(g['dt']))
+    tables = [np.ascontiguousarray(a) for a in (ion.adk_prefactor, ion.adk_power, ion.adk_exp_prefactor)]
+    return g, tables
+
+
+def test_emu_ionize(emu):
+    """k_ionize against get_E_amplitude / get_ionization_probability of the reference (inline_functions.py:9-45):
+    with given draws, exactly the ions with draw < p (and level < level_max) move up one level and are reported with
+    their former level; with the built-in generator the ionized fraction matches the mean probability."""
+    g, tables = _ionize_case()
+    n, level_max = len(g['level']), 6
+    rng = np.random.default_rng(7)
+    draws = rng.uniform(size=n)
+    p = g['probability']
+    clear = np.abs(draws - p) > 1e-9                      # away from the rounding of p
+    assert clear.all()
+    want = np.flatnonzero((draws < p) & (g['level'] < level_max))
+    assert 30 < len(want) < n - 30
+    arrs = [np.ascontiguousarray(a) for a in (*g['u'], *g['E'], *g['B'])]
+    D = ctypes.c_double
+    level = g['level'].astype(np.uint64)
+    events = np.full(2 * n, -1, dtype=np.int64)
+    count = np.zeros(1, dtype=np.uint64)
+    emu.emu_ionize(ctypes.c_longlong(n), _p(level), level_max, *[_p(t) for t in tables], *[_p(a) for a in arrs],
+                   D(c), _p(draws), ctypes.c_ulonglong(0), ctypes.c_longlong(n), _p(events), _p(count))
+    k = int(count[0])
+    ev = events[:2 * k].reshape(k, 2)
+    ev = ev[np.argsort(ev[:, 0])]
+    assert np.array_equal(ev[:, 0], want) and np.array_equal(ev[:, 1], g['level'][want])
+    expect = g['level'].copy()
+    expect[want] += 1
+    assert np.array_equal(level, expect.astype(np.uint64))
+    # built-in counter-based generator: deterministic for a seed, different between seeds, right on average
+    big = 200
+    tiled = [np.tile(a, big) for a in arrs]
+    fractions = []
+    for seed in (11, 11, 12):
+        level = np.tile(g['level'], big).astype(np.uint64)
+        events = np.zeros(2 * n * big, dtype=np.int64)
+        emu.emu_ionize(ctypes.c_longlong(n * big), _p(level), level_max, *[_p(t) for t in tables], *[_p(a) for a in tiled],
+                       D(c), None, ctypes.c_ulonglong(seed), ctypes.c_longlong(n * big), _p(events), _p(count))
+        fractions.append(int(count[0]))
+    mean = np.where(g['level'] < level_max, p, 0.).sum() * big
+    sigma = np.sqrt(np.where(g['level'] < level_max, p * (1 - p), 0.).sum() * big)
+    assert fractions[0] == fractions[1] != fractions[2]
+    assert abs(fractions[0] - mean) < 5 * sigma and abs(fractions[2] - mean) < 5 * sigma
+
+
+def test_emu_push_p_ioniz_and_weights(emu):
+    """k_push_p_ioniz: Vay push with the charge level * e, neutral particles untouched (push_p_ioniz_numba);
+    k_w_times_level."""
+    from oracle import oracle as orc
+    from scipy.constants import e, m_p
+    rng = np.random.default_rng(23)
+    n = 500
+    level = rng.integers(0, 4, n).astype(np.uint64)
+    u0 = [rng.normal(size=n) for _ in range(3)]
+    ig0 = 1. / np.sqrt(1. + u0[0]**2 + u0[1]**2 + u0[2]**2)
+    E = [rng.normal(size=n) * 1.e12 for _ in range(3)]
+    B = [rng.normal(size=n) * 3000. for _ in range(3)]
+    m, dt = 14. * m_p, 2.e-16
+    want = [a.copy() for a in u0] + [ig0.copy()]
+    for lv in range(1, 4):
+        sel = level == lv
+        part = [a[sel].copy() for a in want]
+        orc.push_p(*part, *[a[sel].copy() for a in E + B], lv * e, m, dt)
+        for w_, p_ in zip(want, part):
+            w_[sel] = p_
+    got = [a.copy() for a in u0] + [ig0.copy()]
+    emu.emu_push_p_ioniz(ctypes.c_longlong(n), _p(level), *[_p(a) for a in got], *[_p(a) for a in E + B],
+                         ctypes.c_double(e * dt / (m * c)), ctypes.c_double(0.5 * e * dt / m))
+    for g_, w_, a, name in zip(got, want, u0 + [ig0], ('ux', 'uy', 'uz', 'inv_gamma')):
+        assert np.array_equal(g_[level == 0], a[level == 0]), name
+        assert_close(g_, w_, 1e-14, name)
+    w = rng.uniform(1., 2., n)
+    out = np.zeros(n)
+    emu.emu_w_times_level(ctypes.c_longlong(n), _p(w), _p(level), _p(out))
+    assert np.array_equal(out, w * level)

@@ -123,3 +123,19 @@ def test_host_tables_option_variants_bit_exact():
             assert np.array_equal(gr.invvol, g['%s_invvol_m%d' % (tag, m)]), (tag, m)
             assert np.array_equal(gr.ruyten_linear_coef, g['%s_lin_m%d' % (tag, m)]), (tag, m)
             assert np.array_equal(gr.ruyten_cubic_coef, g['%s_cub_m%d' % (tag, m)]), (tag, m)
+
+
+def test_adk_tables_vs_reference():
+    """Per-level ADK tables (prefactor, power, exponential prefactor) of `Ionizer.initialize_ADK_parameters` for H,
+    He, N, Ar, Kr against the reference's (ionizer.py:137-183), which also pins the ionization energies."""
+    import types
+    from fbpic_b200.ionization import Ionizer, get_ionization_energies
+    g = load_golden('ionization')
+    for element in ('H', 'He', 'N', 'Ar', 'Kr'):
+        ion = types.SimpleNamespace(level_max=None)
+        Ionizer.initialize_ADK_parameters(ion, element, float(g['dt']))
+        for name, got in (('prefactor', ion.adk_prefactor), ('power', ion.adk_power),
+                          ('exp_prefactor', ion.adk_exp_prefactor)):
+            ref = g['%s_%s' % (element, name)]
+            assert got.shape == ref.shape and np.allclose(got, ref, rtol=1e-12, atol=0), (element, name)
+    assert get_ionization_energies('Xx') is None and len(get_ionization_energies('Ar')) == 18
