@@ -897,6 +897,10 @@ def restart_from_checkpoint(sim, iteration=None, checkpoint_dir='./checkpoints')
                 sp.track(comm)
             sp.tracker.overwrite_ids(d[grp + 'id'], comm)
         sp.inv_gamma = 1. / np.sqrt(1 + sp.ux**2 + sp.uy**2 + sp.uz**2)
+        if sp.ionizer is not None:            # checkpoint_restart.py:317-323
+            from scipy.constants import e
+            sp.ionizer.levels.overwrite_ids(np.uint64(np.round(d[grp + 'charge'] / e)))
+            sp.ionizer.w_times_level = sp.w * sp.ionizer.levels.id
         for k in FIELD_ATTRS:
             setattr(sp, k, np.zeros(sp.Ntot))
         if hasattr(sp.injector, 'reset_injection_positions'):

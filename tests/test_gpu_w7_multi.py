@@ -45,3 +45,15 @@ def test_two_gpu_checkpoint_restart():
            os.path.join(ROOT, 'tests', 'workers', 'mgpu_parity_worker.py')]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0 and 'MGPU_RESTART_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_two_gpu_ionization_levels_migrate():
+    """Ionization levels travel with the ions across the slab boundaries; one electron per event over all ranks."""
+    if _lib.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    env = dict(os.environ, MGPU_EXTRA='4')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', '29649',
+           os.path.join(ROOT, 'tests', 'workers', 'mgpu_parity_worker.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and 'MGPU_IONIZATION_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -281,3 +281,34 @@ def test_grow_device_arrays_beyond_capacity():
     assert np.array_equal(np.array(sp.x)[:n0], x0) and np.array_equal(np.array(sp.x)[n0:n0 + 10], np.arange(10.))
     ids = np.array(sp.tracker.id)
     assert np.array_equal(ids[:n0], ids0) and len(np.unique(ids)) == sp.Ntot == len(sp.Ex)
+
+
+def test_restart_keeps_the_ionization_levels(tmp_path):
+    """A checkpoint stores the per-particle charge of an ionizable species; after `restart_from_checkpoint` the ions
+    have their levels (and deposition weights) back (checkpoint_restart.py:317-323)."""
+    from fbpic_b200 import Simulation
+    from fbpic_b200.openpmd_diag import set_periodic_checkpoint, restart_from_checkpoint
+
+    def build():
+        Nz, Nr, Nm, zmax, rmax = 48, 8, 2, 24.e-6, 8.e-6
+        np.random.seed(2)
+        sim = Simulation(Nz, zmax, Nr, rmax, Nm, zmax / Nz / c, zmin=0., n_order=-1, n_guard=12,
+                         n_damp={'z': 12, 'r': 4}, boundaries={'z': 'open', 'r': 'reflective'})
+        kw = dict(p_zmin=9.e-6, p_zmax=15.e-6, p_rmax=6.e-6, p_nz=2, p_nr=2, p_nt=4, continuous_injection=False)
+        elec = sim.add_new_species(q=-e, m=m_e)
+        ions = sim.add_new_species(q=0, m=14. * m_p, n=1.e18, **kw)
+        ions.make_ionizable('N', target_species=elec, level_start=0, level_max=5)
+        return sim, elec, ions
+    a, elec_a, ions_a = build()
+    _standing_field(a, 1.5e11)
+    set_periodic_checkpoint(a, 6, checkpoint_dir=str(tmp_path))
+    a.step(6, correct_currents=False)
+    b, elec_b, ions_b = build()
+    restart_from_checkpoint(b, checkpoint_dir=str(tmp_path))
+    assert b.iteration == 6 and elec_b.Ntot == elec_a.Ntot > 0 and ions_b.Ntot == ions_a.Ntot
+    oa, ob = np.lexsort((ions_a.x, ions_a.z)), np.lexsort((ions_b.x, ions_b.z))
+    la, lb = ions_a.ionizer.ionization_level[oa], ions_b.ionizer.ionization_level[ob]
+    assert np.array_equal(la, lb) and la.max() > 0
+    assert np.allclose(ions_b.ionizer.w_times_level[ob], ions_a.ionizer.w_times_level[oa], rtol=1e-14, atol=0)
+    b.step(2, correct_currents=False)                      # and the restarted run goes on ionizing
+    assert ions_b.ionizer.ionization_level.sum() >= lb.sum()

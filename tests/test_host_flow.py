@@ -171,6 +171,16 @@ def test_ext_kernel_tests_flow(fake):
     k.test_external_field_jit()
 
 
+def test_two_rank_ionization_flow_gloo():
+    """Ionization levels migrate with the ions between 2 ranks; electrons = events over all ranks."""
+    env = dict(os.environ, OMP_NUM_THREADS='2', ORACLE_NUM_THREADS='2', MGPU_NZ_PER_RANK='64', MGPU_EXTRA='4')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', '29655',
+           os.path.join(ROOT, 'tests', 'workers', 'mgpu_parity_worker.py'), '--fake-device']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0 and 'MGPU_IONIZATION_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
 def test_two_rank_restart_flow_gloo():
     """Per-rank checkpoints of a 2-rank run, restart, same continuation (rank by rank)."""
     env = dict(os.environ, OMP_NUM_THREADS='2', ORACLE_NUM_THREADS='2', MGPU_NZ_PER_RANK='64', MGPU_EXTRA='3')
@@ -483,6 +493,10 @@ def test_console_output_flow(fake, capsys):
 def test_ionization_as_written_flow(fake, frame, tmp_path):
     """the reference's tests/test_ionization.py (N5+ fraction after a laser pulse, Chen et al. 2013)"""
     getattr(test_gpu_w9b_ionization, 'test_ionization_' + frame)(tmp_path)
+
+
+def test_ionization_restart_flow(fake, tmp_path):
+    test_gpu_w9b_ionization.test_restart_keeps_the_ionization_levels(tmp_path)
 
 
 def test_ionization_kernels_and_plumbing_flow(fake):

@@ -433,8 +433,74 @@ def run_restart_case(tol):
     return bool(int(flag[0]))
 
 
+def run_ionization_case():
+    """Ionizable species on 2 slabs (particles/elementary_process/ionization; particle_buffer_handling.py:120-172,
+    413-417): drifting nitrogen ions in a static field cross the slab boundaries and the ring closure; their
+    ionization levels travel with them (an ion never loses charge, identified by its tracked id), the deposition weight
+    stays w * level on every rank, and over all ranks one electron appears per ionization event."""
+    from scipy.constants import m_p
+    rank, size = dist.get_rank(), dist.get_world_size()
+    nzr = int(os.environ.get('MGPU_NZ_PER_RANK', '96'))
+    Nz, Nr, Nm, zmax, rmax, n_order = nzr * size, 8, 2, 0.25e-6 * nzr * size, 6.e-6, 8
+    dt = zmax / Nz / c
+    np.random.seed(5)
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, n_order=n_order, boundaries={'z': 'periodic', 'r': 'reflective'})
+    kw = dict(p_zmin=0., p_zmax=zmax, p_rmin=0., p_rmax=5.e-6, p_nz=1, p_nr=2, p_nt=4, continuous_injection=False)
+    elec = sim.add_new_species(q=-e, m=m_e)
+    ions = sim.add_new_species(q=0, m=14. * m_p, n=1.e18, uz_m=0.5, **kw)
+    ions.make_ionizable('N', target_species=elec, level_start=1, level_max=5)
+    ions.track(sim.comm)
+    for m in range(Nm):
+        if m == 0:
+            sim.fld.interp[0].Ez[:, :] = 1.8e11
+    ok = True
+    seen = {}
+    start = [None] * size
+    dist.all_gather_object(start, (np.array(ions.tracker.id), ions.ionizer.ionization_level.copy()))
+    for ids, lv in start:
+        seen.update(zip(ids.tolist(), lv.tolist()))
+    n_e0 = torch.tensor([elec.Ntot]); dist.all_reduce(n_e0)
+    lev0 = sum(seen.values())
+    for _ in range(3):
+        sim.step(8, correct_currents=False, move_momenta=False)      # rigid drift: nobody leaves radially
+        lv = ions.ionizer.ionization_level
+        if len(lv) != ions.Ntot or not np.array_equal(ions.ionizer.w_times_level, np.array(ions.w) * lv):
+            ok = False
+            print('IONIZATION MISMATCH rank %d: weights / lengths' % rank)
+        now = [None] * size
+        dist.all_gather_object(now, (np.array(ions.tracker.id), lv.copy()))
+        allids = np.concatenate([a for a, _ in now])
+        if len(np.unique(allids)) != len(allids) or len(allids) != len(seen):
+            ok = False
+            print('IONIZATION MISMATCH: ids', len(allids), len(seen))
+        for ids, levels in now:
+            for pid, level in zip(ids.tolist(), levels.tolist()):
+                if level < seen[pid]:
+                    ok = False
+                seen[pid] = level
+    n_e = torch.tensor([elec.Ntot]); dist.all_reduce(n_e)
+    moved = int(np.sum(np.array(ions.tracker.id) % size != rank))
+    if int(n_e[0] - n_e0[0]) != sum(seen.values()) - lev0 or sum(seen.values()) == lev0:
+        ok = False
+        print('IONIZATION MISMATCH: electrons %d vs events %d' % (int(n_e[0] - n_e0[0]), sum(seen.values()) - lev0))
+    if rank == 0:
+        print('ionization: %d events, %d electrons, %d ions on rank 0 came from another rank'
+              % (sum(seen.values()) - lev0, int(n_e[0] - n_e0[0]), moved))
+        if moved == 0:
+            ok = False
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    return bool(int(flag[0]))
+
+
 def main():
     dist.init_process_group('gloo')
+    if os.environ.get('MGPU_EXTRA') == '4':
+        ok = run_ionization_case()
+        if dist.get_rank() == 0 and ok:
+            print('MGPU_IONIZATION_OK size=%d' % dist.get_world_size())
+        sys.exit(0 if ok else 1)
     if os.environ.get('MGPU_EXTRA') == '3':
         ok = run_restart_case(1e-9)
         if dist.get_rank() == 0 and ok:
