@@ -489,6 +489,7 @@ def test_console_output_flow(fake, capsys):
     assert '3/3' in out and 'ms/step' in out and 'Total time taken' in out
 
 
+@slow_flow
 @pytest.mark.parametrize('frame', ['labframe', 'boostedframe'])
 def test_ionization_as_written_flow(fake, frame, tmp_path):
     """the reference's tests/test_ionization.py (N5+ fraction after a laser pulse, Chen et al. 2013)"""
