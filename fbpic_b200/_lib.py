@@ -135,6 +135,8 @@ _SIGNATURES = {
     'b2_w_times_level': [P, c_int64, P, P, P, P],
     'b2_ionize': [P, c_int64, P, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P, ctypes.c_uint64, c_int64, P, P,
                   ctypes.POINTER(c_int64), P],
+    'b2_compton_count': [P, c_int64, P, P, P, P, P, P, P, P, ctypes.c_uint64, P, P, ctypes.POINTER(c_int64), P],
+    'b2_compton_scatter': [P, c_int64, P, P, P, P, P, P, P, P, P, P, ctypes.c_uint64, P, P, P],
     'b2_select_crossing': [P, c_int64, P, P, P, c_double, c_double, c_double, c_double, c_int64, P, P,
                            ctypes.POINTER(c_int64), P],
     'b2_extract_slice': [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_double, P, P],

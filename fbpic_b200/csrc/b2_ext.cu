@@ -149,6 +149,52 @@ int b2_ionize(b2_ctx *ctx, int64_t n, uint64_t *level, int level_max, const doub
     return 0;
 }
 
+static b2ext::ComptonParams compton_params(const double *p20, uint64_t seed) {
+    b2ext::ComptonParams P;
+    P.ct = p20[0]; P.photon_n_lab_peak = p20[1]; P.inv_laser_waist2 = p20[2]; P.inv_laser_ctau2 = p20[3];
+    P.laser_initial_z0 = p20[4]; P.gamma_boost = p20[5]; P.beta_boost = p20[6];
+    P.photon_p = p20[7]; P.photon_px = p20[8]; P.photon_py = p20[9]; P.photon_pz = p20[10];
+    P.photon_beta_x = p20[11]; P.photon_beta_y = p20[12]; P.photon_beta_z = p20[13];
+    P.dt = p20[14]; P.ratio_w_electron_photon = p20[15]; P.inv_ratio_w_elec_photon = p20[16];
+    P.pi_re2 = p20[17]; P.inv_mc = p20[18]; P.c_light = p20[19];
+    P.seed = seed;
+    return P;
+}
+
+int b2_compton_count(b2_ctx *ctx, int64_t n, const double *x, const double *y, const double *z, const double *ux,
+                     const double *uy, const double *uz, const double *inv_gamma, const double *params20,
+                     uint64_t seed, int32_t *d_nscatter, int64_t *d_total, int64_t *h_total, void *stream) {
+    if (!params20 || !d_total || !h_total || (n > 0 && !d_nscatter))
+        return b2_fail(-3, "b2_compton_count: missing buffer", __FILE__, __LINE__);
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    B2_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int64_t), s));
+    if (n > 0) {
+        b2ext::k_compton_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+            (long long)n, x, y, z, ux, uy, uz, inv_gamma, compton_params(params20, seed), d_nscatter,
+            (unsigned long long *)d_total);
+        B2_LAUNCHED();
+    }
+    B2_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int b2_compton_scatter(b2_ctx *ctx, int64_t n, const int32_t *d_nscatter, const double *x, const double *y,
+                       const double *z, double *ux, double *uy, double *uz, const double *inv_gamma, const double *w,
+                       const double *params20, uint64_t seed, double *const *photon8, int64_t *d_cursor,
+                       void *stream) {
+    if (n <= 0) return 0;
+    if (!params20 || !photon8 || !d_cursor) return b2_fail(-3, "b2_compton_scatter: missing buffer", __FILE__, __LINE__);
+    cudaStream_t s = b2_stream_of(ctx, stream);
+    B2_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(int64_t), s));
+    b2ext::k_compton_scatter<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+        (long long)n, d_nscatter, x, y, z, ux, uy, uz, inv_gamma, w, compton_params(params20, seed), photon8[0],
+        photon8[1], photon8[2], photon8[3], photon8[4], photon8[5], photon8[6], photon8[7],
+        (unsigned long long *)d_cursor);
+    B2_LAUNCHED();
+    return 0;
+}
+
 int b2_extract_slice(b2_ctx *ctx, const void *const *fields10, int m, int Nm, int Nz, int Nr, int Nr_out, int iz,
                      double Sz, double *slice, void *stream) {
     if (m < 0 || m >= Nm || Nr_out <= 0 || Nr_out > Nr)

@@ -323,4 +323,128 @@ __global__ void k_ionize(long long n, unsigned long long *__restrict__ level, in
     }
 }
 
+// ---- Compton scattering (fbpic/particles/elementary_process/compton) --------------------------------------------
+struct ComptonParams {
+    double ct;                  // c * time of the simulation frame
+    double photon_n_lab_peak, inv_laser_waist2, inv_laser_ctau2, laser_initial_z0, gamma_boost, beta_boost;
+    double photon_p, photon_px, photon_py, photon_pz, photon_beta_x, photon_beta_y, photon_beta_z;   // incoming flux
+    double dt, ratio_w_electron_photon, inv_ratio_w_elec_photon;
+    double pi_re2, inv_mc, c_light;
+    unsigned long long seed;
+};
+
+// boost of the 4-momentum (p, px, py, pz) by (gamma, beta) along the unit vector n (compton/inline_functions.py:16-37)
+__device__ __forceinline__ void lorentz4(double p, double px, double py, double pz, double gamma, double beta,
+                                         double nx, double ny, double nz, double &po, double &pxo, double &pyo,
+                                         double &pzo) {
+    const double par = nx * px + ny * py + nz * pz;
+    po = gamma * (p - beta * par);
+    const double par_out = gamma * (par - beta * p);
+    pxo = px + nx * (par_out - par);
+    pyo = py + ny * (par_out - par);
+    pzo = pz + nz * (par_out - par);
+}
+
+// Number of photon macroparticles each electron emits during this cycle: photon density of the Gaussian pulse at the
+// electron (get_photon_density_gaussian, inline_functions.py:78-112), integrated Klein-Nishina cross-section in the
+// rest frame of the electron (get_scattering_probability, :39-76), nscatter = int(p ratio + u) (numba_methods.py:73-88).
+// total: sum of nscatter (the host sizes the photon arrays with it).
+__global__ void k_compton_count(long long n, const double *__restrict__ x, const double *__restrict__ y,
+                                const double *__restrict__ z, const double *__restrict__ ux,
+                                const double *__restrict__ uy, const double *__restrict__ uz,
+                                const double *__restrict__ inv_gamma, const __grid_constant__ ComptonParams P,
+                                int *__restrict__ nscatter, unsigned long long *__restrict__ total) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double zlab = P.gamma_boost * (z[i] + P.beta_boost * P.ct);
+    const double ctlab = P.gamma_boost * (P.ct + P.beta_boost * z[i]);
+    const double d = zlab - P.laser_initial_z0 + ctlab;
+    const double n_lab = P.photon_n_lab_peak *
+        exp(-2 * P.inv_laser_waist2 * (x[i] * x[i] + y[i] * y[i]) - 2 * P.inv_laser_ctau2 * d * d);
+    const double photon_n = P.gamma_boost * n_lab * (1 + P.beta_boost);
+    const double ig = inv_gamma[i];
+    const double tf = 1. / ig - ux[i] * P.photon_beta_x - uy[i] * P.photon_beta_y - uz[i] * P.photon_beta_z;
+    const double k = P.photon_p * tf * P.inv_mc;
+    const double f1 = 2 * (2 + k * (1 + k) * (8 + k)) / (k * k * (1 + 2 * k) * (1 + 2 * k));
+    const double f2 = (2 + k * (2 - k)) * log(1 + 2 * k) / (k * k * k);
+    const double sigma = P.pi_re2 * (f1 - f2);
+    const double p = 1 - exp(-sigma * photon_n * tf * P.c_light * P.dt * ig);
+    const int ns = (int)(p * P.ratio_w_electron_photon + uniform01(P.seed, (unsigned long long)i * 65536ULL));
+    nscatter[i] = ns;
+    if (ns > 0) atomicAdd(total, (unsigned long long)ns);
+}
+
+// The scattered photons (scatter_photons_electrons_numba, numba_methods.py:90-264): incoming photon boosted to the
+// rest frame of the electron, scattering angle from the Klein-Nishina distribution by rejection sampling, back to
+// the simulation frame; the photon starts at the electron; the electron recoils with probability 1 / ratio.  Each
+// electron reserves its nscatter slots at the end of the photon arrays with one atomic (ph_* point at the first free
+// slot); the draws are counter-based per (electron, draw), so the result does not depend on the order of the atomics.
+__global__ void k_compton_scatter(long long n, const int *__restrict__ nscatter, const double *__restrict__ x,
+                                  const double *__restrict__ y, const double *__restrict__ z,
+                                  double *__restrict__ ux, double *__restrict__ uy, double *__restrict__ uz,
+                                  const double *__restrict__ inv_gamma, const double *__restrict__ w,
+                                  const __grid_constant__ ComptonParams P, double *__restrict__ ph_x,
+                                  double *__restrict__ ph_y, double *__restrict__ ph_z, double *__restrict__ ph_ux,
+                                  double *__restrict__ ph_uy, double *__restrict__ ph_uz,
+                                  double *__restrict__ ph_inv_gamma, double *__restrict__ ph_w,
+                                  unsigned long long *__restrict__ cursor) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int ns = nscatter[i];
+    if (ns <= 0) return;
+    unsigned long long draw = (unsigned long long)i * 65536ULL + 1ULL;
+    unsigned long long slot = atomicAdd(cursor, (unsigned long long)ns);
+    const double e_ux = ux[i], e_uy = uy[i], e_uz = uz[i], ig = inv_gamma[i];
+    const double gamma = 1. / ig;
+    const double u = sqrt(e_ux * e_ux + e_uy * e_uy + e_uz * e_uz);
+    const double beta = u * ig;
+    double nx = 0., ny = 0., nz = 1.;
+    if (u != 0) { nx = e_ux / u; ny = e_uy / u; nz = e_uz / u; }
+    double rp, rpx, rpy, rpz;
+    lorentz4(P.photon_p, P.photon_px, P.photon_py, P.photon_pz, gamma, beta, nx, ny, nz, rp, rpx, rpy, rpz);
+    const double cos_t = rpz / rp;
+    double sin_t = 0., cos_f = 1., sin_f = 0.;
+    if (cos_t * cos_t < 1) {
+        sin_t = sqrt(1 - cos_t * cos_t);
+        const double inv_pxy = 1. / (sin_t * rp);
+        cos_f = rpx * inv_pxy;
+        sin_f = rpy * inv_pxy;
+    }
+    double npx = 0., npy = 0., npz = 0.;
+    for (int s = 0; s < ns; ++s) {
+        const double k = rp * P.inv_mc;
+        const double c0 = 2. * (2. * k * k + 2. * k + 1.) / ((2. * k + 1.) * (2. * k + 1.) * (2. * k + 1.));
+        const double b = (2. + c0) / (2. - c0), a = 2. * b - 1.;
+        double xs;
+        while (true) {
+            const double r1 = uniform01(P.seed, draw++);
+            xs = b - (b + 1.) * pow(0.5 * c0, r1);
+            const double h = a / (b - xs);
+            const double fac = 1 + k * (1 - xs);
+            const double f = ((1 + xs * xs) * fac + k * k * (1 - xs) * (1 - xs)) / (fac * fac * fac);
+            if (uniform01(P.seed, draw++) < f / h) break;
+        }
+        const double new_p = rp / (1 + k * (1 - xs));
+        const double sin_s = sqrt(1 - xs * xs);
+        const double phi = 2 * 3.141592653589793 * uniform01(P.seed, draw++);
+        const double pX = new_p * sin_s * cos(phi), pY = new_p * sin_s * sin(phi), pZ = new_p * xs;
+        const double qx = sin_t * cos_f * pZ + cos_t * cos_f * pX - sin_f * pY;
+        const double qy = sin_t * sin_f * pZ + cos_t * sin_f * pX + cos_f * pY;
+        const double qz = cos_t * pZ - sin_t * pX;
+        double np_;
+        lorentz4(new_p, qx, qy, qz, gamma, beta, -nx, -ny, -nz, np_, npx, npy, npz);
+        ph_x[slot] = x[i]; ph_y[slot] = y[i]; ph_z[slot] = z[i];
+        ph_w[slot] = w[i] * P.inv_ratio_w_elec_photon;
+        ph_ux[slot] = npx; ph_uy[slot] = npy; ph_uz[slot] = npz;
+        ph_inv_gamma[slot] = 1. / np_;
+        ++slot;
+    }
+    // recoil from the last photon, with probability 1 / ratio (numba_methods.py:257-263)
+    if (uniform01(P.seed, draw++) < P.inv_ratio_w_elec_photon) {
+        ux[i] = e_ux + P.inv_mc * (P.photon_px - npx);
+        uy[i] = e_uy + P.inv_mc * (P.photon_py - npy);
+        uz[i] = e_uz + P.inv_mc * (P.photon_pz - npz);
+    }
+}
+
 }  // namespace b2ext

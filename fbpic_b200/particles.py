@@ -634,9 +634,11 @@ class Particles(object):
 
     # ------------------------------------------------------------------ out of scope hooks
     def handle_elementary_processes(self, t):
-        """Ionization (particles.py:497-509); Compton scattering is not built."""
+        """Ionization, Compton scattering (particles.py:497-509)"""
         if self.ionizer is not None:
             self.ionizer.handle_ionization(self)
+        if self.compton_scatterer is not None:
+            self.compton_scatterer.handle_scattering(self, t)
 
     def make_ionizable(self, element, target_species, level_start=0, level_max=None):
         """ADK ionization of this species; the freed electrons go to `target_species` (a `Particles` object, or
@@ -687,8 +689,11 @@ class Particles(object):
 
     def activate_compton(self, target_species, laser_energy, laser_wavelength, laser_waist, laser_ctau,
                          laser_initial_z0, ratio_w_electron_photon, boost=None):
-        """particles.py:376-396 -- not built, refused like `make_ionizable`."""
-        raise NotImplementedError('Compton scattering (Particles.activate_compton) is outside of this build.')
+        """Compton scattering of a counter-propagating Gaussian laser pulse off this (electron) species; the photons
+        go to `target_species` (q = 0, m = 0) (particles.py:376-396)."""
+        from .compton import ComptonScatterer
+        self.compton_scatterer = ComptonScatterer(self, target_species, laser_energy, laser_wavelength, laser_waist,
+                                                  laser_ctau, laser_initial_z0, ratio_w_electron_photon, boost)
 
     def shift_periodic(self, zmin, zmax):
         """Single periodic domain: wrap z back into the box

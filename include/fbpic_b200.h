@@ -332,6 +332,24 @@ int b2_ionize(b2_ctx *ctx, int64_t n, uint64_t *d_level, int level_max, const do
               const double *d_uz, const double *d_Ex, const double *d_Ey, const double *d_Ez, const double *d_Bx,
               const double *d_By, const double *d_Bz, const double *d_draws, uint64_t seed, int64_t cap,
               int64_t *d_events, int64_t *d_count, int64_t *h_count, void *stream);
+/* Compton scattering of a counter-propagating Gaussian laser pulse off an electron species
+ * (fbpic/particles/elementary_process/compton/).  params20 (host): ct, photon_n_lab_peak, inv_laser_waist2,
+ * inv_laser_ctau2, laser_initial_z0, gamma_boost, beta_boost, photon_p, photon_px, photon_py, photon_pz,
+ * photon_beta_x, photon_beta_y, photon_beta_z, dt, ratio_w_electron_photon, 1/ratio, pi r_e^2, 1/(m_e c), c.
+ * b2_compton_count: determine_scatterings_* (numba_methods.py:50-88 with get_photon_density_gaussian and
+ *   get_scattering_probability): d_nscatter[i] photons for electron i, their sum in *h_total (synchronises).
+ * b2_compton_scatter: scatter_photons_electrons_* (numba_methods.py:90-264): writes the sum(d_nscatter) photons
+ *   (x, y, z, ux, uy, uz = momentum in kg m/s, inv_gamma = 1/|p|, w) from the first free slot photon8[k] on
+ *   (host array of 8 device pointers in the order x y z ux uy uz inv_gamma w) and applies the electron recoil.
+ *   Same seed in both calls; draws are counter-based per (electron, draw). */
+int b2_compton_count(b2_ctx *ctx, int64_t n, const double *d_x, const double *d_y, const double *d_z,
+                     const double *d_ux, const double *d_uy, const double *d_uz, const double *d_inv_gamma,
+                     const double *params20, uint64_t seed, int32_t *d_nscatter, int64_t *d_total, int64_t *h_total,
+                     void *stream);
+int b2_compton_scatter(b2_ctx *ctx, int64_t n, const int32_t *d_nscatter, const double *d_x, const double *d_y,
+                       const double *d_z, double *d_ux, double *d_uy, double *d_uz, const double *d_inv_gamma,
+                       const double *d_w, const double *params20, uint64_t seed, double *const *photon8,
+                       int64_t *d_cursor, void *stream);
 /* lab-frame particle output: ParticleCatcher.get_particle_slice (fbpic/openpmd_diag/boosted_particle_diag.py:598-629).
  * Appends to d_idx (capacity cap) the indices of the particles for which
  *   (z >= z_curr and z_old <= z_prev) or (z <= z_curr and z_old >= z_prev),  z_old = z - uz inv_gamma c dt,

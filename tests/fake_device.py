@@ -612,6 +612,21 @@ class FakeLib(object):
         h_count._obj.value = int(_arr(d_count, 1, np.int64)[0])
         return rc
 
+    def b2_compton_count(self, ctx, n, x, y, z, ux, uy, uz, ig, params20, seed, nscatter, d_total, h_total, stream):
+        V = ctypes.c_void_p
+        rc = self.emu.emu_compton_count(ctypes.c_longlong(n), *[V(_addr(p)) for p in (x, y, z, ux, uy, uz, ig)],
+                                        V(_addr(params20)), ctypes.c_ulonglong(seed), V(_addr(nscatter)),
+                                        V(_addr(d_total)))
+        h_total._obj.value = int(_arr(d_total, 1, np.int64)[0])
+        return rc
+
+    def b2_compton_scatter(self, ctx, n, nscatter, x, y, z, ux, uy, uz, ig, w, params20, seed, photon8, cursor, stream):
+        V = ctypes.c_void_p
+        ptrs = (ctypes.c_void_p * 8)(*_ptrs(photon8, 8))
+        return self.emu.emu_compton_scatter(ctypes.c_longlong(n), V(_addr(nscatter)),
+                                            *[V(_addr(p)) for p in (x, y, z, ux, uy, uz, ig, w)], V(_addr(params20)),
+                                            ctypes.c_ulonglong(seed), ptrs, V(_addr(cursor)))
+
     def b2_select_crossing(self, ctx, n, z, uz, ig, c_light, dt, z_curr, z_prev, cap, idx, d_count, h_count, stream):
         if not _addr(d_count):
             return -3

@@ -101,6 +101,39 @@ int emu_ionize(long long n, unsigned long long *level, int level_max, const doub
     return 0;
 }
 
+static b2ext::ComptonParams emu_compton_params(const double *p20, unsigned long long seed) {
+    b2ext::ComptonParams P;
+    P.ct = p20[0]; P.photon_n_lab_peak = p20[1]; P.inv_laser_waist2 = p20[2]; P.inv_laser_ctau2 = p20[3];
+    P.laser_initial_z0 = p20[4]; P.gamma_boost = p20[5]; P.beta_boost = p20[6];
+    P.photon_p = p20[7]; P.photon_px = p20[8]; P.photon_py = p20[9]; P.photon_pz = p20[10];
+    P.photon_beta_x = p20[11]; P.photon_beta_y = p20[12]; P.photon_beta_z = p20[13];
+    P.dt = p20[14]; P.ratio_w_electron_photon = p20[15]; P.inv_ratio_w_elec_photon = p20[16];
+    P.pi_re2 = p20[17]; P.inv_mc = p20[18]; P.c_light = p20[19];
+    P.seed = seed;
+    return P;
+}
+
+int emu_compton_count(long long n, const double *x, const double *y, const double *z, const double *ux,
+                      const double *uy, const double *uz, const double *ig, const double *p20,
+                      unsigned long long seed, int *nscatter, unsigned long long *total) {
+    *total = 0;
+    if (n > 0)
+        EMU_LAUNCH(emu_dim3((unsigned)((n + 255) / 256)), emu_dim3(256), b2ext::k_compton_count, n, x, y, z, ux, uy, uz,
+                   ig, emu_compton_params(p20, seed), nscatter, total);
+    return 0;
+}
+
+int emu_compton_scatter(long long n, const int *nscatter, const double *x, const double *y, const double *z,
+                        double *ux, double *uy, double *uz, const double *ig, const double *w, const double *p20,
+                        unsigned long long seed, double *const *ph, unsigned long long *cursor) {
+    *cursor = 0;
+    if (n > 0)
+        EMU_LAUNCH(emu_dim3((unsigned)((n + 255) / 256)), emu_dim3(256), b2ext::k_compton_scatter, n, nscatter, x, y, z,
+                   ux, uy, uz, ig, w, emu_compton_params(p20, seed), ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6],
+                   ph[7], cursor);
+    return 0;
+}
+
 int emu_select_crossing(long long n, const double *z, const double *uz, const double *inv_gamma, double c_light,
                         double dt, double z_curr, double z_prev, long long cap, long long *idx,
                         unsigned long long *count) {

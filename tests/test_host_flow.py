@@ -29,6 +29,7 @@ import test_gpu_w6_acceptance
 import test_gpu_w8_diags
 import test_gpu_w9_step_options
 import test_gpu_w9b_ionization
+import test_gpu_w9c_compton
 
 
 @pytest.fixture
@@ -506,3 +507,15 @@ def test_ionization_kernels_and_plumbing_flow(fake):
     test_gpu_w9b_ionization.test_grow_device_arrays_beyond_capacity()
     test_gpu_w9b_ionization.test_ionization_events_free_one_electron_each()
     test_gpu_w9b_ionization.test_ionizable_species_through_window_sort_and_exchange()
+
+
+@slow_flow
+@pytest.mark.parametrize('gamma_boost', [1., 10.])
+def test_compton_as_written_flow(fake, gamma_boost):
+    """the reference's tests/test_compton.py (300000 electrons, 101 cycles of push + scattering)"""
+    test_gpu_w9c_compton.test_compton_as_written(gamma_boost)
+
+
+@pytest.mark.parametrize('gamma_boost', [1., 10.])
+def test_compton_momentum_conservation_flow(fake, gamma_boost):
+    test_gpu_w9c_compton.test_compton_momentum_conservation(gamma_boost)
