@@ -62,6 +62,14 @@ def build(variant):
             sim.diags = [BackTransformedFieldDiagnostic(*args, comm=sim.comm, write_dir=out),
                          BackTransformedParticleDiagnostic(*args, species={'electrons': sim.ptcl[0]}, comm=sim.comm,
                                                            write_dir=out)]
+    elif variant == 'ionization':
+        # a second, ionizable species (nitrogen, same sampling) that feeds the electrons: the ADK pass, the
+        # per-particle-charge push and the unfused route of that species (the electrons keep the fused kernels)
+        from scipy.constants import e, m_p
+        sim = Simulation(Nz, zmax, Nr, rmax, Nm, dz / c, **kw)
+        ions = sim.add_new_species(q=0, m=14. * m_p, n=4.e24, p_zmin=0, p_zmax=zmax, p_rmin=0, p_rmax=rmax, p_nz=2,
+                                   p_nr=2, p_nt=4)
+        ions.make_ionizable('N', target_species=sim.ptcl[0], level_start=1)
     else:
         raise ValueError(variant)
     sp = sim.ptcl[0]
@@ -78,7 +86,7 @@ def main():
     call.b2_event_create(ctypes.byref(ev0))
     call.b2_event_create(ctypes.byref(ev1))
     for variant in ('default', 'pml', 'cross_deposition', 'external_field', 'open_window', 'antenna', 'field_diag',
-                    'lab_diag'):
+                    'lab_diag', 'ionization'):
         try:
             sim = build(variant)
             n = sum(s.Ntot for s in sim.ptcl)
