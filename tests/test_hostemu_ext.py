@@ -305,3 +305,62 @@ def test_emu_push_p_ioniz_and_weights(emu):
     out = np.zeros(n)
     emu.emu_w_times_level(ctypes.c_longlong(n), _p(w), _p(level), _p(out))
     assert np.array_equal(out, w * level)
+
+
+def test_emu_compton_count_and_scatter(emu):
+    """k_compton_count against the NumPy statement of get_photon_density_gaussian / get_scattering_probability
+    (compton/inline_functions.py:39-112): the number of photons per electron is p x ratio on average and reproducible
+    for a seed; k_compton_scatter fills exactly that many photon slots, each with |p| = 1 / inv_gamma, at the position
+    of an emitting electron, with a weight w / ratio."""
+    from scipy.constants import h, m_e, physical_constants
+    r_e = physical_constants['classical electron radius'][0]
+    rng = np.random.default_rng(61)
+    n = 40000
+    x, y = rng.normal(size=n) * 5.e-6, rng.normal(size=n) * 5.e-6
+    z = rng.normal(size=n) * 2.e-6
+    ux, uy = rng.normal(size=n) * 0.1, rng.normal(size=n) * 0.1
+    uz = 30. + rng.normal(size=n)
+    ig = 1. / np.sqrt(1 + ux**2 + uy**2 + uz**2)
+    w = rng.uniform(1., 2., n)
+    lam, waist, ctau, z0, ratio, dt = h * c / 1.602176634e-19, 30.e-6, 6.e-4, 0., 40., 4.e-13
+    p_ph = h / lam
+    # peak photon density such that an electron at the centre emits about one photon macroparticle in 40 cycles
+    n_peak = (1. / 40. / ratio) / (8. / 3 * np.pi * r_e**2 * 2. * c * dt)
+    ct = 1.e-6
+    P = np.array([ct, n_peak, 1. / waist**2, 1. / ctau**2, z0, 1., 0., p_ph, 0., 0., -p_ph, 0., 0., -1., dt, ratio,
+                  1. / ratio, np.pi * r_e**2, 1. / (m_e * c), c])
+    # NumPy statement of the reference formulas (lab frame: gamma_boost = 1)
+    n_ph = n_peak * np.exp(-2 * (x**2 + y**2) / waist**2 - 2 * (z - z0 + ct)**2 / ctau**2)
+    tf = 1. / ig + uz
+    k = p_ph * tf / (m_e * c)
+    sigma = np.pi * r_e**2 * (2 * (2 + k * (1 + k) * (8 + k)) / (k**2 * (1 + 2 * k)**2)
+                              - (2 + k * (2 - k)) * np.log(1 + 2 * k) / k**3)
+    prob = 1 - np.exp(-sigma * n_ph * tf * c * dt * ig)
+    assert 0.005 < prob.mean() * ratio < 5.
+    ns = [np.zeros(n, dtype=np.int32) for _ in range(3)]
+    total = np.zeros(1, dtype=np.uint64)
+    totals = []
+    for seed, out in zip((5, 5, 6), ns):
+        emu.emu_compton_count(ctypes.c_longlong(n), *[_p(a) for a in (x, y, z, ux, uy, uz, ig)], _p(P),
+                              ctypes.c_ulonglong(seed), _p(out), _p(total))
+        totals.append(int(total[0]))
+        assert totals[-1] == out.sum()
+    assert np.array_equal(ns[0], ns[1]) and not np.array_equal(ns[0], ns[2])
+    mean, sig = (prob * ratio).sum(), np.sqrt(n / 12. + 1.)        # int(p r + u): uniform rounding noise
+    assert abs(totals[0] - mean) < 6 * sig and abs(totals[2] - mean) < 6 * sig
+    # the photons
+    N = totals[0]
+    ph = [np.full(N, np.nan) for _ in range(8)]
+    ptrs = (ctypes.c_void_p * 8)(*[a.ctypes.data for a in ph])
+    e_u = [ux.copy(), uy.copy(), uz.copy()]
+    cursor = np.zeros(1, dtype=np.uint64)
+    emu.emu_compton_scatter(ctypes.c_longlong(n), _p(ns[0]), _p(x), _p(y), _p(z), *[_p(a) for a in e_u], _p(ig), _p(w),
+                            _p(P), ctypes.c_ulonglong(5), ptrs, _p(cursor))
+    assert int(cursor[0]) == N and not np.isnan(np.stack(ph)).any()
+    px, py, pz, inv_p = ph[3], ph[4], ph[5], ph[6]
+    assert np.allclose(np.sqrt(px**2 + py**2 + pz**2) * inv_p, 1., rtol=1e-12)
+    assert np.all(np.isin(ph[0], x[ns[0] > 0])) and np.all(np.isin(np.round(ph[7] * ratio, 9), np.round(w, 9)))
+    # up-shifted by up to 4 gamma^2 and beamed forward; electrons that recoiled lost longitudinal momentum
+    assert np.mean(pz > 0) > 0.99 and (1. / inv_p).max() < 4 * 35.**2 * p_ph
+    changed = e_u[2] != uz
+    assert 0 < changed.sum() <= (ns[0] > 0).sum() and np.all(e_u[2][changed] < uz[changed])
