@@ -4,7 +4,7 @@ Laser initialisation and emission, same entry points as `fbpic.lpa_utils.laser`
 
 * laser profiles (`GaussianLaser`, `LaguerreGaussLaser`, `DonutLikeLaguerreGaussLaser`, `FlattenedGaussianLaser`,
   `FewCycleLaser`, `ParaxialApproximationLaser` over longitudinal / transverse profile classes, sums with `+`):
-  analytic E(x, y, z, t), NumPy (`FromLasyFileLaser` is refused: not built);
+  analytic E(x, y, z, t), NumPy; `FromLasyFileLaser`: envelope interpolated from a lasy file;
 * `add_laser_pulse(sim, profile, method='direct')`: the profile is sampled on the global grid, Ez and B
   follow from div E = 0 and Faraday's law in spectral space.  The transforms of that one-off set-up run on
   the GPU (cuFFT + DMMA Hankel kernels of the hot path) -- the reference does them on the CPU even in GPU
@@ -351,11 +351,86 @@ class FlattenedGaussianLaser(_ParaxialLaser):
 
 
 class FromLasyFileLaser(LaserProfile):
-    """Laser read from a lasy openPMD file (laser_profiles.py:841-1065) -- not built: refused, so that a script that
-    relies on it cannot run without its laser."""
+    """Laser whose envelope E(x, y, t) in the emission plane comes from a `lasy` file (openPMD `laserEnvelope` mesh,
+    `thetaMode` or `cartesian` geometry; laser_profiles.py:841-1065): multilinear interpolation of the envelope times
+    exp(-i omega t), along the polarisation vector of the file.  The time axis of the file starts at `t_start`
+    (its own offset is ignored, as in the reference).  Only for `method='antenna'`.  The file is read with the tree
+    reader of the diagnostics (`.h5` through h5py, or an `.npz` archive of the same tree)."""
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError('FromLasyFileLaser (lasy envelope files) is outside of this build.')
+    def __init__(self, filename, t_start=0.):
+        from ...openpmd_store import read_tree
+        LaserProfile.__init__(self, propagation_direction=1, gpu_capable=False)
+        self.t_start = t_start
+        tree = read_tree(filename)
+
+        def text(v):
+            v = v[()] if isinstance(v, np.ndarray) and v.ndim == 0 else v
+            return v.decode() if isinstance(v, bytes) else str(v)
+        valid = False
+        if '/@software' in tree and '/@softwareVersion' in tree:
+            version = tuple(int(n) for n in text(tree['/@softwareVersion']).split('.'))
+            valid = (text(tree['/@software']) == 'lasy') and version >= (0, 3, 0)
+        if not valid:
+            raise RuntimeError("The `lasy` version that was used to create the file %s is obsolete and not supported "
+                               "by FBPIC.\nPlease upgrade your lasy version to at least 0.3.0 (e.g. with `pip install "
+                               "--upgrade lasy`) and re-create the file %s." % (filename, filename))
+        key = '/data/0/meshes/laserEnvelope'
+        self.env_data = np.asarray(tree[key])
+        self.omega = float(tree[key + '@angularFrequency'])
+        self.pol = np.asarray(tree[key + '@polarization'])
+        offset = np.asarray(tree[key + '@gridGlobalOffset'], dtype=np.float64)
+        spacing = np.asarray(tree[key + '@gridSpacing'], dtype=np.float64) * float(tree[key + '@gridUnitSI'])
+        self.t_min_lasy = offset[0]
+        self.geometry = text(tree[key + '@geometry'])
+        if self.geometry == 'thetaMode':
+            self.inv_dt, self.inv_dr = 1. / spacing[0], 1. / spacing[1]
+        elif self.geometry == 'cartesian':
+            self.inv_dt, self.inv_dy, self.inv_dx = 1. / spacing[0], 1. / spacing[1], 1. / spacing[2]
+            self.y_min, self.x_min = offset[1], offset[2]
+        else:
+            raise RuntimeError("Unknown geometry for lasy file %s: %s" % (filename, self.geometry))
+
+    @staticmethod
+    def _cell(pos, n):
+        """lower index, weight of the upper node, inside-the-table flag of a linear interpolation on n nodes"""
+        i = np.floor(pos).astype(np.int64)
+        inside = (i >= 0) & (i + 1 <= n - 1)
+        return np.where(inside, i, 0), pos - i, inside
+
+    def envelope(self, x, y, t):
+        x, y, t = np.broadcast_arrays(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64),
+                                      np.asarray(t, dtype=np.float64))
+        d = self.env_data
+        if self.geometry == 'thetaMode':
+            _, nt, nr = d.shape
+            r = (x**2 + y**2)**.5
+            ir, Sr, ok_r = self._cell(r * self.inv_dr, nr)
+            it, St, ok_t = self._cell(t * self.inv_dt, nt)
+
+            def interp(a):
+                return (1 - Sr) * (1 - St) * a[it, ir] + Sr * (1 - St) * a[it, ir + 1] \
+                    + (1 - Sr) * St * a[it + 1, ir] + Sr * St * a[it + 1, ir + 1]
+            env = interp(d[0]).astype(np.complex128)
+            with np.errstate(invalid='ignore', divide='ignore'):
+                phase = (x + 1.j * y) / r
+            for m in range(1, d.shape[0] // 2 + 1):
+                e_m = phase**m
+                env = env + interp(d[2 * m - 1]) * e_m.real + interp(d[2 * m]) * e_m.imag
+            return np.where(ok_r & ok_t, env, 0.)
+        nt, ny, nx = d.shape
+        ix, Sx, ok_x = self._cell((x - self.x_min) * self.inv_dx, nx)
+        iy, Sy, ok_y = self._cell((y - self.y_min) * self.inv_dy, ny)
+        it, St, ok_t = self._cell(t * self.inv_dt, nt)
+        env = 0.
+        for jt, wt in ((it, 1 - St), (it + 1, St)):
+            for jy, wy in ((iy, 1 - Sy), (iy + 1, Sy)):
+                for jx, wx in ((ix, 1 - Sx), (ix + 1, Sx)):
+                    env = env + wx * wy * wt * d[jt, jy, jx]
+        return np.where(ok_x & ok_y & ok_t, env, 0.)
+
+    def E_field(self, x, y, z, t):
+        E = self.envelope(x, y, t - self.t_start) * np.exp(-1.j * self.omega * (t - self.t_start + self.t_min_lasy))
+        return (E * self.pol[0]).real, (E * self.pol[1]).real
 
 
 class FewCycleLaser(LaserProfile):

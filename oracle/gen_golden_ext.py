@@ -572,7 +572,52 @@ def gen_ionization():
     save('ionization', **out)
 
 
+def gen_lasy_laser():
+    """The reference's FromLasyFileLaser (laser_profiles.py:841-1065) on two synthetic lasy files (thetaMode with
+    modes 0 and 1, and cartesian), written through the h5py stand-in; the fixture keeps the file contents so that the
+    tests can rebuild the files."""
+    import tempfile
+    import h5py
+    from fbpic.lpa_utils.laser import FromLasyFileLaser
+    rng = np.random.default_rng(71)
+    omega = 2 * np.pi * c / 0.8e-6
+    pol = np.array([np.cos(0.3), np.sin(0.3) * np.exp(0.5j)])
+    out = dict(omega=omega, pol=pol)
+    tmp = tempfile.mkdtemp()
+
+    def write(name, data, geometry, spacing, offset):
+        path = os.path.join(tmp, name)
+        with h5py.File(path, 'w') as f:
+            f.attrs['software'], f.attrs['softwareVersion'] = np.bytes_('lasy'), np.bytes_('0.4.0')
+            d = f.create_dataset('/data/0/meshes/laserEnvelope', data=data)
+            d.attrs['angularFrequency'], d.attrs['polarization'] = omega, pol
+            d.attrs['geometry'] = np.bytes_(geometry)
+            d.attrs['gridSpacing'], d.attrs['gridGlobalOffset'], d.attrs['gridUnitSI'] = spacing, offset, 1.
+        return path
+    # thetaMode: [2 Nm - 1, nt, nr]
+    nt, nr, dt_, dr_ = 60, 40, 1.e-15, 1.e-6
+    tt, rr = np.meshgrid(dt_ * np.arange(nt), dr_ * np.arange(nr), indexing='ij')
+    g = np.exp(-(tt - 30.e-15)**2 / (10.e-15)**2 - rr**2 / (12.e-6)**2) * np.exp(1.j * 2.e13 * tt)
+    rt = 1.e12 * np.stack([g, 0.2 * g * rr / 12.e-6, 0.1j * g * rr / 12.e-6])
+    p1 = write('theta.h5', rt, 'thetaMode', np.array([dt_, dr_]), np.array([-25.e-15, 0.]))
+    # cartesian: [nt, ny, nx]
+    ny, nx, dy_, dx_ = 24, 28, 2.e-6, 1.5e-6
+    t3, y3, x3 = np.meshgrid(dt_ * np.arange(nt), -23.e-6 + dy_ * np.arange(ny), -20.e-6 + dx_ * np.arange(nx),
+                             indexing='ij')
+    xyz = 1.e12 * np.exp(-(t3 - 30.e-15)**2 / (10.e-15)**2 - (x3**2 + 1.5 * y3**2) / (12.e-6)**2 + 1.j * x3 / 5.e-6)
+    p2 = write('cart.h5', xyz, 'cartesian', np.array([dt_, dy_, dx_]), np.array([-25.e-15, -23.e-6, -20.e-6]))
+    n = 500
+    x, y = rng.uniform(-22.e-6, 22.e-6, n), rng.uniform(-26.e-6, 26.e-6, n)
+    t = rng.uniform(-5.e-15, 70.e-15, n)
+    out.update(x=x, y=y, t=t, theta_data=rt, cart_data=xyz)
+    for tag, path in (('theta', p1), ('cart', p2)):
+        prof = FromLasyFileLaser(path, t_start=4.e-15)
+        out[tag + '_Ex'], out[tag + '_Ey'] = prof.E_field(x, y, 0. * x, t)
+    save('lasy_laser', **out)
+
+
 GENERATORS = {
+    'lasy_laser': gen_lasy_laser,
     'ionization': gen_ionization,
     'diags_tree': gen_diags,
     'cpu_gpu_deposition_linear': lambda: gen_cpu_gpu_deposition('linear'),

@@ -139,3 +139,38 @@ def test_adk_tables_vs_reference():
             ref = g['%s_%s' % (element, name)]
             assert got.shape == ref.shape and np.allclose(got, ref, rtol=1e-12, atol=0), (element, name)
     assert get_ionization_energies('Xx') is None and len(get_ionization_energies('Ar')) == 18
+
+
+def _write_lasy_like(path, data, geometry, spacing, offset, omega, pol, version='0.4.0'):
+    """a file with the layout `lasy` writes (openPMD `laserEnvelope` mesh), through fbpic_b200's own container"""
+    from fbpic_b200.openpmd_store import File
+    f = File(path, 'w')
+    f.attrs['software'], f.attrs['softwareVersion'] = np.bytes_('lasy'), np.bytes_(version)
+    d = f.create_dataset('/data/0/meshes/laserEnvelope', data=data)
+    d.attrs['angularFrequency'], d.attrs['polarization'], d.attrs['geometry'] = omega, pol, np.bytes_(geometry)
+    d.attrs['gridSpacing'], d.attrs['gridGlobalOffset'], d.attrs['gridUnitSI'] = spacing, offset, 1.
+    f.close()
+
+
+def test_lasy_file_laser_vs_reference(tmp_path):
+    """FromLasyFileLaser on a thetaMode (modes 0, 1) and a cartesian envelope file against the reference's class on
+    the same files (points inside and outside of the tables, in space and time); obsolete files are refused."""
+    import pytest
+    from fbpic_b200.lpa_utils.laser import FromLasyFileLaser
+    g = load_golden('lasy_laser')
+    omega, pol = float(g['omega']), g['pol']
+    x, y, t = g['x'], g['y'], g['t']
+    cases = {'theta': (g['theta_data'], 'thetaMode', np.array([1.e-15, 1.e-6]), np.array([-25.e-15, 0.])),
+             'cart': (g['cart_data'], 'cartesian', np.array([1.e-15, 2.e-6, 1.5e-6]),
+                      np.array([-25.e-15, -23.e-6, -20.e-6]))}
+    for tag, (data, geometry, spacing, offset) in cases.items():
+        path = str(tmp_path / (tag + '.npz'))
+        _write_lasy_like(path, data, geometry, spacing, offset, omega, pol)
+        Ex, Ey = FromLasyFileLaser(path, t_start=4.e-15).E_field(x, y, 0. * x, t)
+        assert np.count_nonzero(g[tag + '_Ex']) > 100 and np.count_nonzero(g[tag + '_Ex'] == 0) > 20
+        assert_close(Ex, g[tag + '_Ex'], 1e-13, tag + ' Ex')
+        assert_close(Ey, g[tag + '_Ey'], 1e-13, tag + ' Ey')
+    old = str(tmp_path / 'old.npz')
+    _write_lasy_like(old, *cases['theta'], omega, pol, version='0.2.1')
+    with pytest.raises(RuntimeError):
+        FromLasyFileLaser(old)
