@@ -12,3 +12,12 @@ from .particles import Particles                  # noqa: F401
 from .fields import Fields, BinomialSmoother      # noqa: F401
 from .boundaries import BoundaryCommunicator      # noqa: F401
 from ._lib import DeviceArray, cuda_available, B200Error   # noqa: F401
+
+
+def set_random_seed(random_seed):
+    """Fix the seeds of the Monte-Carlo parts (plasma loading, bunches, ionization, Compton scattering): rank r uses
+    random_seed + r (fbpic/utils/random_seed.py).  The device generators of the elementary processes take their seeds
+    from `np.random` when `make_ionizable` / `activate_compton` are called, so call this first."""
+    import os
+    import numpy as np
+    np.random.seed(random_seed + int(os.environ.get('RANK', '0')))

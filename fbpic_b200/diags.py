@@ -265,6 +265,41 @@ class ParticleChargeDensityDiagnostic(FieldDiagnostic):
                 f.close()
 
 
+class InputScriptDiagnostic(OpenPMDDiagnostic):
+    """Saves the text of the running input script (the first `*.py` among the command-line arguments) and optional
+    extra attributes (`param_dict`, camelCase keys) into the file attributes of every dump
+    (inputscript_diag.py:13-120)."""
+    needs_gathered_fields = False
+
+    def __init__(self, period=None, comm=None, param_dict=None, write_dir=None, iteration_min=0, iteration_max=np.inf,
+                 dt_period=None, dt_sim=None):
+        import sys
+        OpenPMDDiagnostic.__init__(self, period, comm, write_dir, iteration_min, iteration_max, dt_period=dt_period,
+                                   dt_sim=dt_sim)
+        self.param_dict = param_dict
+        self._input_script = None
+        scripts = [a for a in sys.argv if '.py' in a]
+        if scripts and os.path.isfile(scripts[0]):
+            with open(scripts[0], 'r') as f:
+                self._input_script = f.read()
+
+    def write_hdf5(self, iteration):
+        if self._input_script is None:
+            return
+        f = self.open_file(self.file_stem(iteration))
+        if f is None:
+            return
+        f.attrs['inputScript'] = _text(self._input_script)
+        for key, val in (self.param_dict or {}).items():
+            if isinstance(val, str):
+                f.attrs[key] = _text(val)
+            elif isinstance(val, (list, tuple)):
+                f.attrs[key] = np.array(val)
+            else:
+                f.attrs[key] = val
+        f.close()
+
+
 _COMPONENTS = {'position': ('x', 'y', 'z'), 'momentum': ('ux', 'uy', 'uz'), 'weighting': ('w',),
                'gamma': ('gamma',), 'E': ('Ex', 'Ey', 'Ez'), 'B': ('Bx', 'By', 'Bz'), 'id': ('id',),
                'charge': ('charge',)}

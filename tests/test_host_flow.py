@@ -519,3 +519,31 @@ def test_compton_as_written_flow(fake, gamma_boost):
 @pytest.mark.parametrize('gamma_boost', [1., 10.])
 def test_compton_momentum_conservation_flow(fake, gamma_boost):
     test_gpu_w9c_compton.test_compton_momentum_conservation(gamma_boost)
+
+
+def test_input_script_diagnostic_flow(fake, tmp_path, monkeypatch):
+    """InputScriptDiagnostic: the text of the running script and the extra attributes land in the file attributes"""
+    import numpy as np
+    from scipy.constants import c
+    from fbpic_b200 import Simulation, set_random_seed
+    from fbpic_b200.openpmd_diag import InputScriptDiagnostic, FieldDiagnostic
+    from fbpic_b200.openpmd_store import read_tree, existing_file
+    script = tmp_path / 'my_run.py'
+    script.write_text('# the input deck\nNz = 32\n')
+    monkeypatch.setattr(sys, 'argv', ['python', str(script)])
+    set_random_seed(4)
+    first = np.random.rand()
+    set_random_seed(4)
+    assert np.random.rand() == first
+    zmax, rmax = 16.e-6, 8.e-6
+    sim = Simulation(32, zmax, 12, rmax, 2, zmax / 32 / c, p_zmin=0, p_zmax=zmax, p_rmin=0, p_rmax=rmax, p_nz=1, p_nr=1,
+                     p_nt=4, n_e=1.e24)
+    out = str(tmp_path / 'diags')
+    sim.diags = [FieldDiagnostic(2, sim.fld, comm=sim.comm, fieldtypes=['E'], write_dir=out),
+                 InputScriptDiagnostic(2, sim.comm, param_dict={'runLabel': 'scan 7', 'a0': 2.5, 'box': [1, 2]},
+                                       write_dir=out)]
+    sim.step(3)
+    tree = read_tree(existing_file(os.path.join(out, 'hdf5', 'data00000002')))
+    assert bytes(tree['/@inputScript']).decode() == script.read_text()
+    assert bytes(tree['/@runLabel']).decode() == 'scan 7' and float(tree['/@a0']) == 2.5
+    assert list(tree['/@box']) == [1, 2] and '/data/2/fields/E/r' in tree
