@@ -370,7 +370,7 @@ def test_diagnostics_through_the_h5py_api(fake, shim_h5py, tmp_path):
     test_gpu_w8_diags.test_restart_from_checkpoint_continues_the_run(True, False, tmp_path / 'c')
 
 
-@pytest.mark.parametrize('script', ['lwfa.py', 'boosted_frame.py'])
+@pytest.mark.parametrize('script', ['lwfa.py', 'boosted_frame.py', 'ionization_injection.py'])
 def test_example_scripts_flow(fake, script, tmp_path, monkeypatch, capsys):
     """The two example scripts (the reference's documented input scripts, full size) run a few cycles end to end --
     laser set-up, bunch with space charge, antenna, moving window, boosted-frame and lab-frame diagnostics -- and
@@ -385,6 +385,8 @@ def test_example_scripts_flow(fake, script, tmp_path, monkeypatch, capsys):
     assert list_iterations(out) == [0]
     d = read_diag(out, 0)
     assert d['fields/E/r'].ndim == 3 and 'particles/electrons/position/x' in d
+    if script == 'ionization_injection.py':
+        assert 'fields/rho_electrons' in d and 'particles/electrons from N/weighting' in d
     if script == 'boosted_frame.py':
         assert list_iterations(out + '_lab') == list(range(11))
         lab = read_diag(out + '_lab', 0)
