@@ -2,7 +2,6 @@
 kernel-level pieces against the formulas of the reference, and the reference's own acceptance test
 (tests/test_ionization.py, Chen et al. JCP 2013 figure 2) as written, lab frame and boosted frame."""
 import math
-import shutil
 import numpy as np
 import pytest
 from scipy.constants import c, m_e, m_p, e

@@ -65,7 +65,7 @@ def build(variant):
     elif variant == 'ionization':
         # a second, ionizable species (nitrogen, same sampling) that feeds the electrons: the ADK pass, the
         # per-particle-charge push and the unfused route of that species (the electrons keep the fused kernels)
-        from scipy.constants import e, m_p
+        from scipy.constants import m_p
         sim = Simulation(Nz, zmax, Nr, rmax, Nm, dz / c, **kw)
         ions = sim.add_new_species(q=0, m=14. * m_p, n=4.e24, p_zmin=0, p_zmax=zmax, p_rmin=0, p_rmax=rmax, p_nz=2,
                                    p_nr=2, p_nt=4)
