@@ -37,4 +37,6 @@ def assert_close(a, b, rel, what='', scale=None):
 
 # Test files are collected in alphabetical order and the driver runs `pytest -x`: the hardware-proven GPU tests
 # (test_gpu_kernels / multi / plasma_wave / step) therefore come first, the tests of the SURVEY 8f widening
-# (test_gpu_w1 .. w7, ordered from kernel-level goldens to whole-script and analytic acceptance runs) after them.
+# (test_gpu_w0 .. w9c, ordered from kernel-level goldens to whole-script and analytic acceptance runs, then the
+# full-size property tests test_gpu_x_*) after them; the external-field tests, whose kernels are compiled at run time
+# by NVRTC and loaded through the CUDA library API, come last (test_gpu_y_external).

@@ -1,6 +1,7 @@
 """GPU parity tests of `ExternalField` (fbpic/lpa_utils/external_fields.py; SURVEY 2: user-defined fields applied
 after the gather): the user's Python function is translated to CUDA C, JIT-compiled by NVRTC inside the
 library and applied on the device; whole steps against golden outputs of the unmodified reference."""
+import ctypes
 import math
 import numpy as np
 import pytest
@@ -22,6 +23,30 @@ def focusing_field(F, x, y, z, t, amplitude, length_scale):
     else:
         g = 0.
     return F - amplitude * k * x * g * math.sin(k * (z - 299792458. * t))
+
+
+def _dev(*arrays):
+    from fbpic_b200._lib import DeviceArray
+    return [DeviceArray.from_numpy(np.ascontiguousarray(a)) for a in arrays]
+
+
+def test_external_field_jit():
+    """NVRTC -> cubin -> cudaLibraryLoadData -> launch, lab frame and boosted (z, t) arguments."""
+    from fbpic_b200 import _lib
+    rng = np.random.default_rng(7)
+    n = 1000
+    F, x, y, z = rng.normal(size=n), rng.normal(size=n) * 1e-6, rng.normal(size=n) * 1e-6, rng.uniform(0, 2e-5, n)
+    h = ctypes.c_void_p()
+    _lib.call.b2_external_field_compile(b'    F_[i_] = F + amplitude * cos(z / length_scale) * x - t * 1.e9 * y;',
+                                        ctypes.byref(h))
+    for g, b in ((1., 0.), (3., np.sqrt(1 - 1 / 9.))):
+        d = _dev(F, x, y, z)
+        t, amp, L = 5.e-15, 2.5, 3.e-6
+        _lib.call.b2_external_field_apply(_lib.context().handle, h, n, d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, t, amp, L,
+                                          g, b, None)
+        zl, tl = g * (z + b * c * t), g * (t + b * (1. / c) * z)
+        assert_close(d[0].get(), F + amp * np.cos(zl / L) * x - tl * 1.e9 * y, 1e-14, 'external field g=%g' % g)
+    _lib.call.b2_external_field_free(h)
 
 
 @pytest.mark.parametrize('fused', [False, True])

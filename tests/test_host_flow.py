@@ -22,7 +22,7 @@ import test_gpu_step
 import test_gpu_w0_ext_kernels
 import test_gpu_w1_pml_cross
 import test_gpu_w2_laser
-import test_gpu_w5_external
+import test_gpu_y_external
 import test_gpu_w3_bunch
 import test_gpu_w4_scripts
 import test_gpu_w6_acceptance
@@ -78,11 +78,11 @@ def test_laser_antenna_flow(fake, tag, fused):
 @pytest.mark.parametrize('fused', [False, True])
 @pytest.mark.parametrize('tag', ['lab', 'boost'])
 def test_external_fields_flow(fake, tag, fused):
-    test_gpu_w5_external.test_external_fields_step_vs_reference_golden(tag, fused)
+    test_gpu_y_external.test_external_fields_step_vs_reference_golden(tag, fused)
 
 
 def test_external_field_string_flow(fake):
-    test_gpu_w5_external.test_external_field_string_expression()
+    test_gpu_y_external.test_external_field_string_expression()
 
 
 @pytest.mark.parametrize('tag', ['uniform', 'gaussian', 'gaussian_boost'])
@@ -169,7 +169,7 @@ def test_ext_kernel_tests_flow(fake):
     k.test_push_p_after_plane()
     k.test_extract_slice(3)
     k.test_select_crossing()
-    k.test_external_field_jit()
+    test_gpu_y_external.test_external_field_jit()
 
 
 def test_two_rank_ionization_flow_gloo():
@@ -440,7 +440,7 @@ def test_antenna_as_written_flow(fake, case):
 @pytest.mark.parametrize('gamma_boost', [None, 10])
 def test_external_fields_as_written_flow(fake, gamma_boost):
     """the reference's tests/test_external_fields.py (400 calls of step(1))"""
-    test_gpu_w5_external.test_external_fields_as_written(gamma_boost)
+    test_gpu_y_external.test_external_fields_as_written(gamma_boost)
 
 
 def test_fewcycle_laser_as_written_flow(fake):
