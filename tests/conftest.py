@@ -39,4 +39,4 @@ def assert_close(a, b, rel, what='', scale=None):
 # (test_gpu_kernels / multi / plasma_wave / step) therefore come first, the tests of the SURVEY 8f widening
 # (test_gpu_w0 .. w9c, ordered from kernel-level goldens to whole-script and analytic acceptance runs, then the
 # full-size property tests test_gpu_x_*) after them; the external-field tests, whose kernels are compiled at run time
-# by NVRTC and loaded through the CUDA library API, come last (test_gpu_y_external).
+# by NVRTC and loaded through the CUDA library API, come last (test_gpu_y_external, test_gpu_y2_ionization_laser).

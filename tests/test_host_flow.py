@@ -29,6 +29,7 @@ import test_gpu_w6_acceptance
 import test_gpu_w8_diags
 import test_gpu_w9_step_options
 import test_gpu_w9b_ionization
+import test_gpu_y2_ionization_laser
 import test_gpu_w9c_compton
 
 
@@ -496,7 +497,7 @@ def test_console_output_flow(fake, capsys):
 @pytest.mark.parametrize('frame', ['labframe', 'boostedframe'])
 def test_ionization_as_written_flow(fake, frame, tmp_path):
     """the reference's tests/test_ionization.py (N5+ fraction after a laser pulse, Chen et al. 2013)"""
-    getattr(test_gpu_w9b_ionization, 'test_ionization_' + frame)(tmp_path)
+    getattr(test_gpu_y2_ionization_laser, 'test_ionization_' + frame)(tmp_path)
 
 
 def test_ionization_restart_flow(fake, tmp_path):
