@@ -632,7 +632,7 @@ class Particles(object):
                               ptr_array([getattr(g, k) for g in grid for k in ('Jr', 'Jt', 'Jz')]),
                               self.prefix_sum.ptr, r0.ptr, rh.ptr, int(cubic), None)
 
-    # ------------------------------------------------------------------ out of scope hooks
+    # ------------------------------------------------------------------ elementary processes
     def handle_elementary_processes(self, t):
         """Ionization, Compton scattering (particles.py:497-509)"""
         if self.ionizer is not None:

@@ -2,8 +2,8 @@
 (docs/source/example_input/lwfa_script.py and boosted_frame_script.py), written ONCE against a namespace `ns`
 that provides `Simulation`, `add_laser_pulse`, `GaussianLaser`, `add_particle_bunch`, `BoostConverter`:
 oracle/gen_golden_ext.py runs them with the unmodified reference's objects, the tests with fbpic_b200's -- the
-same user code on both sides of the drop-in boundary.  (Diagnostics are left out: openPMD output is outside
-this build.)"""
+same user code on both sides of the drop-in boundary.  (The diagnostics of the scripts are exercised separately:
+tests/diag_cases.py, examples/.)"""
 import numpy as np
 from scipy.constants import c, e, m_e, m_p
 
