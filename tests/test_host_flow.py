@@ -550,3 +550,30 @@ def test_input_script_diagnostic_flow(fake, tmp_path, monkeypatch):
     assert bytes(tree['/@inputScript']).decode() == script.read_text()
     assert bytes(tree['/@runLabel']).decode() == 'scan 7' and float(tree['/@a0']) == 2.5
     assert list(tree['/@box']) == [1, 2] and '/data/2/fields/E/r' in tree
+
+
+def test_lasy_file_laser_through_the_antenna_flow(fake, tmp_path):
+    """A laser read from a (synthetic) lasy file is emitted by the antenna: after 60 cycles the pulse is on the grid
+    with the polarisation of the file."""
+    import numpy as np
+    from scipy.constants import c
+    from fbpic_b200 import Simulation
+    from fbpic_b200.lpa_utils.laser import add_laser_pulse, FromLasyFileLaser
+    from test_lpa_utils_host import _write_lasy_like
+    nt, nr, dt_, dr_ = 80, 40, 1.e-15, 1.e-6
+    tt, rr = np.meshgrid(dt_ * np.arange(nt), dr_ * np.arange(nr), indexing='ij')
+    env = 2.e12 * np.exp(-(tt - 30.e-15)**2 / (8.e-15)**2 - rr**2 / (10.e-6)**2)[None].astype(np.complex128)
+    path = str(tmp_path / 'lasy_laser_00000.npz')
+    _write_lasy_like(path, env, 'thetaMode', np.array([dt_, dr_]), np.array([0., 0.]), 2 * np.pi * c / 0.8e-6,
+                     np.array([1. + 0.j, 0.j]))
+    Nz, Nr, Nm, zmax, rmax = 160, 24, 2, 16.e-6, 24.e-6
+    sim = Simulation(Nz, zmax, Nr, rmax, Nm, zmax / Nz / c, zmin=0., n_order=-1, n_guard=12, n_damp={'z': 12, 'r': 6},
+                     boundaries={'z': 'open', 'r': 'reflective'})
+    add_laser_pulse(sim, FromLasyFileLaser(path), method='antenna', z0_antenna=2.e-6)
+    sim.step(120)
+    g1 = sim.fld.interp[1]
+    Er, Et = np.abs(g1.Er).max(), np.abs(g1.Et).max()
+    assert 0.2e12 < 2 * Er < 2.4e12 and abs(Er - Et) < 1e-3 * Er          # x-polarised: |Er| = |Et| in mode 1
+    assert np.abs(sim.fld.interp[0].Er).max() < 1e-6 * Er
+    iz = np.unravel_index(np.abs(g1.Er).argmax(), g1.Er.shape)[0]
+    assert 4.e-6 < g1.z[iz] < 14.e-6                                       # the pulse left the antenna towards +z
