@@ -574,6 +574,6 @@ def test_lasy_file_laser_through_the_antenna_flow(fake, tmp_path):
     g1 = sim.fld.interp[1]
     Er, Et = np.abs(g1.Er).max(), np.abs(g1.Et).max()
     assert 0.2e12 < 2 * Er < 2.4e12 and abs(Er - Et) < 1e-3 * Er          # x-polarised: |Er| = |Et| in mode 1
-    assert np.abs(sim.fld.interp[0].Er).max() < 1e-6 * Er
+    assert np.abs(sim.fld.interp[0].Er).max() < 1e-4 * Er
     iz = np.unravel_index(np.abs(g1.Er).argmax(), g1.Er.shape)[0]
     assert 4.e-6 < g1.z[iz] < 14.e-6                                       # the pulse left the antenna towards +z
