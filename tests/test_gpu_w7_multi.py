@@ -41,7 +41,7 @@ def test_two_gpu_checkpoint_restart():
         pytest.skip('needs 2 GPUs')
     env = dict(os.environ, MGPU_EXTRA='3')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
-           '--master-addr', '127.0.0.1', '--master-port', '29647',
+           '--master-addr', '127.0.0.1', '--master-port', '29651',
            os.path.join(ROOT, 'tests', 'workers', 'mgpu_parity_worker.py')]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0 and 'MGPU_RESTART_OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
