@@ -102,7 +102,7 @@ class FakeLib(object):
         return self.launches
 
     def b2_malloc(self, p, nbytes):
-        buf = np.zeros(int(nbytes) + 64, dtype=np.uint8)
+        buf = np.zeros(int(nbytes) + int(os.environ.get('B2_FAKE_PAD', '64')), dtype=np.uint8)
         a = buf.ctypes.data
         self._mem[a] = buf
         p._obj.value = a
