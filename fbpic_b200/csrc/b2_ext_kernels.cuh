@@ -415,8 +415,9 @@ __global__ void k_compton_scatter(long long n, const int *__restrict__ nscatter,
         const double k = rp * P.inv_mc;
         const double c0 = 2. * (2. * k * k + 2. * k + 1.) / ((2. * k + 1.) * (2. * k + 1.) * (2. * k + 1.));
         const double b = (2. + c0) / (2. - c0), a = 2. * b - 1.;
-        double xs;
-        while (true) {
+        double xs = 1.;
+        // (acceptance is above 1/2 for every k; the bound only keeps a NaN input from spinning forever)
+        for (int attempt = 0; attempt < 4096; ++attempt) {
             const double r1 = uniform01(P.seed, draw++);
             xs = b - (b + 1.) * pow(0.5 * c0, r1);
             const double h = a / (b - xs);

@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: test needs a CUDA device (B200)')
 
 
+def pytest_collection_modifyitems(config, items):
+    """A GPU test that hangs would take the whole box with it: every `-m gpu` test gets a time limit when the
+    pytest-timeout plugin is there (the slowest one takes well under a minute on a B200)."""
+    if not config.pluginmanager.hasplugin('timeout'):
+        return
+    import pytest
+    for item in items:
+        if item.get_closest_marker('gpu') is not None and item.get_closest_marker('timeout') is None:
+            item.add_marker(pytest.mark.timeout(900))
+
+
 def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN, name + '.npz')))
 
