@@ -20,7 +20,7 @@ def pytest_collection_modifyitems(config, items):
     import pytest
     for item in items:
         if item.get_closest_marker('gpu') is not None and item.get_closest_marker('timeout') is None:
-            item.add_marker(pytest.mark.timeout(900))
+            item.add_marker(pytest.mark.timeout(900, method='thread'))     # a hang inside a CUDA call ignores signals
 
 
 def load_golden(name):
