@@ -92,7 +92,6 @@ def build_b200_sim(cfg, n_gpus, fused=True, seed=0, sort_period=1, full_slab=Fal
 
 def build_oracle_sim(cfg, Nz, nthreads, seed=0):
     from oracle import oracle as orc
-    from fbpic_b200.particles import generate_evenly_spaced
     np.random.seed(seed)
     zmax = Nz * cfg['dz']
     dt = cfg['dz'] / c
@@ -100,8 +99,15 @@ def build_oracle_sim(cfg, Nz, nthreads, seed=0):
     sim = orc.OracleSim(Nz, zmax, cfg['Nr'], cfg['rmax'], cfg['Nm'], dt, nthreads=nthreads)
     # particles exactly as Simulation.add_new_species would create them (last two r cells empty)
     Npz, Npr = Nz * p_nz, cfg['Nr'] * p_nr
-    Ntot, x, y, z, ux, uy, uz, ig, w = generate_evenly_spaced(
-        Npz, 0., zmax, Npr, 0., cfg['rmax'], p_nt, cfg['n_e'], None, 0., 0., 0., 0., 0., 0.)
+    # (the port's own statement of the lattice of continuous_injection.py:203-275: cold, uniform density)
+    ddz, ddr, dth = zmax / Npz, cfg['rmax'] / Npr, 2 * np.pi / p_nt
+    zp, rp, tp = np.meshgrid(ddz * (np.arange(Npz) + 0.5), ddr * (np.arange(Npr) + 0.5), dth * np.arange(p_nt),
+                             copy=True, indexing='ij')
+    tp += (2 * np.pi * np.random.rand(Npz, Npr))[:, :, None]
+    r, th, z = rp.ravel(), tp.ravel(), zp.ravel()
+    x, y, w = r * np.cos(th), r * np.sin(th), cfg['n_e'] * r * dth * ddr * ddz
+    Ntot = z.size
+    ux, uy, uz, ig = np.zeros(Ntot), np.zeros(Ntot), np.zeros(Ntot), np.ones(Ntot)
     sim.add_species(-e, m_e, x, y, z, ux, uy, uz, ig, w)
     zz = (0.5 + np.arange(Nz)) * cfg['dz']
     rr = (0.5 + np.arange(cfg['Nr'])) * (cfg['rmax'] / cfg['Nr'])
@@ -227,6 +233,34 @@ def time_oracle(cfg, Nz, steps, warmup, nthreads):
     return Ntot * steps / dt, dt / steps * 1e3, Ntot
 
 
+def cpu_model():
+    try:
+        for ln in open('/proc/cpuinfo'):
+            if ln.startswith('model name'):
+                return ln.split(':', 1)[1].strip()
+    except Exception:
+        pass
+    return 'unknown CPU'
+
+
+def time_reference(cfg, Nz, steps, warmup, threads, budget_s=0.):
+    """FBPIC's own CPU path (oracle/_ref, installed by oracle/make_ref.sh) in a subprocess with the thread
+    environment of SURVEY 8d; returns the dict printed by oracle/ref_bench.py."""
+    if not os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'fbpic', 'main.py')):
+        raise RuntimeError('oracle/_ref not installed (bash oracle/make_ref.sh)')
+    job = {'cfg': {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}, 'Nz': Nz, 'steps': steps,
+           'warmup': warmup, 'threads': threads, 'budget_s': budget_s}
+    env = dict(os.environ)
+    for k in ('OMP_WAIT_POLICY', 'OPENBLAS_NUM_THREADS'):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'oracle', 'ref_bench.py'), json.dumps(job)],
+                       capture_output=True, text=True, env=env, timeout=float(os.environ.get('REF_TIMEOUT_S', 900.)))
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError('reference run failed: ' + (r.stderr or r.stdout)[-300:])
+    return json.loads(lines[-1])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -257,27 +291,48 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        from oracle import oracle as orc
-        orc.build()
-        Nz_s = min(cfg['Nz'], 1024)          # bounded sample: a z-slab of the same workload
-        steps = max(1, min(args.steps, 10))
-        nthreads = int(os.environ.get('ORACLE_NUM_THREADS', min(ncores, 32)))
-        val, ms, Ntot = time_oracle(cfg, Nz_s, steps, min(args.warmup, 2), nthreads)
-        sample = 'z-slab Nz=%d of the workload (%d particles), %d steps, oracle port (C+OpenMP particle ' \
-                 'kernels, scipy.fft, OpenBLAS dgemm), %d threads' % (Nz_s, Ntot, steps, nthreads)
-        print(json.dumps({
+        # FBPIC's own numba CPU path (unmodified, oracle/_ref) on THIS workload at full size, all host threads
+        # this process may use; the C/OpenMP oracle port is timed next to it as a second, labelled number.
+        threads = int(os.environ.get('REF_NUM_THREADS', len(os.sched_getaffinity(0))))
+        warm = max(1, min(args.warmup, 5))
+        try:
+            ref = time_reference(cfg, cfg['Nz'], args.steps, warm, threads,
+                                 budget_s=float(os.environ.get('REF_BUDGET_S', 200.)))
+            kind, val, ms, steps, Ntot = 'reference', ref['value'], ref['ms_per_step'], ref['steps'], ref['Ntot']
+            sample = 'the whole workload (Nz=%d, %d particles), %d steps after %d warm-up steps: unmodified FBPIC %s ' \
+                     'Simulation(use_cuda=False).step(), numba %s threading layer %s, NUMBA_NUM_THREADS=%d of %d ' \
+                     'logical cores (%s), OPENBLAS_NUM_THREADS=1, FFT = scipy.fft through the pyfftw shim' % (
+                         cfg['Nz'], Ntot, steps, warm, ref['fbpic'], ref['numba'], ref['threading_layer'],
+                         threads, ncores, cpu_model())
+            extra = {'reference_detail': ref}
+        except Exception as exc:            # oracle/_ref missing or numba unusable on this box: the port, labelled
+            from oracle import oracle as orc
+            orc.build()
+            Nz_s, steps = min(cfg['Nz'], 1024), max(1, min(args.steps, 10))
+            val, ms, Ntot = time_oracle(cfg, Nz_s, steps, min(args.warmup, 2), min(threads, 32))
+            kind = 'port'
+            sample = 'z-slab Nz=%d of the workload (%d particles), %d steps, oracle port (C+OpenMP particle ' \
+                     'kernels, scipy.fft, OpenBLAS dgemm), %d threads; FBPIC itself failed: %s' % (
+                         Nz_s, Ntot, steps, min(threads, 32), repr(exc)[:200])
+            extra = {}
+        line = {
             'impl': 'reference', 'metric': metric, 'value': val, 'unit': 'particle-updates/s',
-            'n_gpus': 0, 'steps': steps, 'warmup': min(args.warmup, 2), 'ms_per_step': ms,
+            'n_gpus': 0, 'steps': steps, 'warmup': warm, 'ms_per_step': ms,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'config': {'workload': workload, 'sample': sample},
-            'cpu_baseline': {'value': val, 'unit': 'particle-updates/s', 'cores': nthreads, 'kind': 'port',
-                             'sample': sample},
+            'cpu_baseline': {'value': val, 'unit': 'particle-updates/s', 'cores': threads, 'kind': kind,
+                             'sample': sample, 'cpu': cpu_model()},
             'e2e': {'value': val, 'unit': 'particle-updates/s', 'h2d_bytes_per_step': 0,
-                    'd2h_bytes_per_step': 0}}))
+                    'd2h_bytes_per_step': 0}}
+        line.update(extra)
+        print(json.dumps(line))
         return
 
     # ------------------------------------------------------------------ B200 arm
-    os.environ['NCCL_DEBUG'] = os.environ.get('B2_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
+    # NCCL's own report of the communicator (rank count, transport) goes to stderr: stdout stays the one JSON line
+    os.environ.setdefault('NCCL_DEBUG', os.environ.get('B2_NCCL_DEBUG', 'INFO'))
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+    os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
     from fbpic_b200 import _lib
     from fbpic_b200._lib import call
     dist = None
@@ -417,18 +472,26 @@ def main():
         kernels[k] = d
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
-        from oracle import oracle as orc
-        orc.build()
-        Nz_s = min(cfg['Nz'], 512)
-        best = None
-        for nt in sorted({min(ncores, t) for t in (16, 32, 64)}):
-            val, ms_cpu, n_cpu = time_oracle(cfg, Nz_s, 2, 1, nt)
-            if best is None or val > best[0]:
-                best = (val, nt, n_cpu)
-        cpu_baseline = {'value': best[0], 'unit': 'particle-updates/s', 'cores': best[1], 'kind': 'port',
-                        'sample': 'z-slab Nz=%d of the workload (%d particles), 2 steps after 1 warm-up, oracle '
-                                  'port, best of 16/32/64 threads on %d logical cores' % (Nz_s, best[2], ncores)}
+    if not args.no_cpu_baseline and n_gpus == 1:
+        # bounded sample on this box's host cores: FBPIC's own numba path (oracle/_ref) on a z-slab of the
+        # workload; the C/OpenMP oracle port only if the reference cannot run here (labelled)
+        threads = len(os.sched_getaffinity(0))
+        Nz_s = min(cfg['Nz'], 1024)
+        try:
+            ref = time_reference(cfg, Nz_s, 4, 1, threads, budget_s=25.)
+            cpu_baseline = {'value': ref['value'], 'unit': 'particle-updates/s', 'cores': threads,
+                            'kind': 'reference', 'cpu': cpu_model(),
+                            'sample': 'z-slab Nz=%d of the workload (%d particles), %d steps after 1 warm-up: unmodified '
+                                      'FBPIC %s numba CPU path, %d threads (`--impl reference` times the whole workload)'
+                                      % (Nz_s, ref['Ntot'], ref['steps'], ref['fbpic'], threads)}
+        except Exception as exc:
+            from oracle import oracle as orc
+            orc.build()
+            Nz_s = min(cfg['Nz'], 512)
+            val, ms_cpu, n_cpu = time_oracle(cfg, Nz_s, 2, 1, min(threads, 32))
+            cpu_baseline = {'value': val, 'unit': 'particle-updates/s', 'cores': min(threads, 32), 'kind': 'port',
+                            'sample': 'z-slab Nz=%d of the workload (%d particles), 2 steps after 1 warm-up, oracle '
+                                      'port; FBPIC itself failed: %s' % (Nz_s, n_cpu, repr(exc)[:160])}
     out = {
         'metric': metric, 'value': value, 'unit': 'particle-updates/s', 'n_gpus': n_gpus,
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': t_ms / args.steps,

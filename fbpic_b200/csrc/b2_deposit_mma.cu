@@ -375,6 +375,7 @@ int b2_deposit_permute(b2_ctx *ctx, int what, int64_t n, const double *const *sr
                        void *const *grids, const int32_t *prefix, const double *r0, const double *rh, int cubic,
                        void *stream) {
     (void)prefix;
+    if (n <= 0) return 0;     // empty species: nothing to permute or deposit
     if (!ctx->last_idx32 || ctx->last_sort_n != n)
         return b2_fail(-4, "b2_deposit_permute: no matching b2_sort_cells result in this context", __FILE__, __LINE__);
     return b2_deposit_mma(ctx, what != 0, n, src8, dst8, ctx->last_idx32, nullptr, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm,

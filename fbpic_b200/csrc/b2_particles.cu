@@ -345,9 +345,9 @@ k_gather_push_tiled(int64_t n, double *__restrict__ x, double *__restrict__ y, d
     }
     __syncthreads();
     const int z0 = s_box[0], r0 = s_box[2];
-    const int nrow = s_box[1] - z0 + 1, ncol = s_box[3] - r0 + 1;
-    const bool tile_ok = (s_box[1] >= z0) && nrow > 0 && ncol > 0 && (nrow * ncol <= GP_TILE_CELLS)
-                         && z0 >= -1 && s_box[1] <= Nz;
+    const bool box_ok = (s_box[1] >= s_box[0]) && (s_box[3] >= s_box[2]);   // some particle is near
+    const int nrow = box_ok ? s_box[1] - z0 + 1 : 0, ncol = box_ok ? s_box[3] - r0 + 1 : 0;
+    const bool tile_ok = box_ok && (nrow * ncol <= GP_TILE_CELLS) && z0 >= -1 && s_box[1] <= Nz;
     const bool use_tile = tile_ok && near;          // per thread
     if (tile_ok && tid < nrow * ncol) {
         // one thread per tile cell (GP_TILE_CELLS <= GP_TPB), 6*NM coalesced 16-byte loads each
@@ -543,7 +543,10 @@ int b2_sort_cells(b2_ctx *ctx, int64_t n, int32_t *cell_idx, int64_t *sorted_idx
     cudaStream_t s = b2_stream_of(ctx, stream);
     const int ncells = Nz * (Nr + 1);
     if (n <= 0) {
+        // an empty species still counts as sorted (cuda_sorting.py:106,181 skip the launches, the
+        // prefix sum stays all-zero): record it so that a following permute / deposit_permute matches
         B2_CUDA(cudaMemsetAsync(prefix_sum, 0, sizeof(int32_t) * (size_t)ncells, s));
+        ctx->last_sort_n = 0;
         return 0;
     }
     // 32-bit particle indices (CUB num_items, the idx32 permutation, the int32 prefix sums): one species on one
