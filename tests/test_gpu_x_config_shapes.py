@@ -63,8 +63,13 @@ def _run_case(Nz, Nr, Nm, p_nt, fused, v_comoving=None, ions=False, n_order=-1, 
         got = np.stack([getattr(sp, k) for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'w')])
         want = np.stack([r[k] for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'w')])
         go, wo = np.lexsort((got[2], got[1], got[0], got[6])), np.lexsort((want[2], want[1], want[0], want[6]))
+        # one scale per vector: a component that stays at rounding level (uy of a plasma driven in x, z) is
+        # compared on the scale of the momentum, not of its own noise
+        s_x = 2 * max(np.abs(want[j]).max() for j in (0, 1))
+        s_u = 2 * max(np.abs(want[j]).max() for j in (3, 4, 5))
         for j, k in enumerate(('x', 'y', 'z', 'ux', 'uy', 'uz')):
-            assert_close(got[j][go], want[j][wo], 1e-10, 'species %d %s' % (i, k))
+            assert_close(got[j][go], want[j][wo], 1e-10, 'species %d %s' % (i, k),
+                         scale=(s_x if j < 2 else None if j == 2 else s_u))
 
 
 @pytest.mark.parametrize('fused', [False, True])
