@@ -35,7 +35,7 @@ class DhtJob(ctypes.Structure):
 
 
 DHT_SCALAR, DHT_RT_TO_PM, DHT_PM_TO_RT = 0, 1, 2
-MAX_DHT_JOBS = 12           # DHT_MAX_JOBS (csrc/b2_dht.cu): products carried by one batched Hankel launch
+MAX_DHT_JOBS = 16           # DHT_MAX_JOBS (csrc/b2_dht.cu): jobs (of any kind) carried by one batched Hankel launch
 MAX_ARRAYS = 32             # B2_MAX_ARRAYS (include/fbpic_b200.h): pointers carried by one multi-array launch
 
 

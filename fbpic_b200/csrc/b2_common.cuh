@@ -56,6 +56,8 @@ static inline cudaStream_t b2_stream_of(b2_ctx *ctx, void *stream) {
 }
 
 int b2_scratch(b2_ctx *ctx, int slot, size_t nbytes, void **ptr);
+// b2_dht_tma.cu: drop the cached packed Hankel matrix / tensor maps of a buffer that is freed or overwritten
+void b2_dht_forget(const void *p);
 
 // ---- optional per-kernel-family device timing (CUDA events on the launching stream) ----
 enum B2ProfSlot {

@@ -25,7 +25,7 @@
 #define DHT_AP (DHT_BK + 4)   // A row pitch in complex elements: 20 -> conflict-free LDS.128
 #define DHT_BP (DHT_BN + 4)   // B row pitch in doubles: 132 -> conflict-free LDS.64
 #define DHT_THREADS 256
-#define DHT_MAX_JOBS 12
+#define DHT_MAX_JOBS 16
 
 struct DhtJob {
     const double2 *in1, *in2;   // NPROD=1: A = c1*in1 + c2*in2 (in2 may be null); NPROD=2: p, m
@@ -214,24 +214,44 @@ static int launch_dht(b2_ctx *ctx, const DhtJobs &jobs, int njobs, int Nz, int N
     return 0;
 }
 
+// b2_dht_tma.cu: TMA-fed persistent kernel, one launch for a mixed job list; returns 1 when that path is
+// unavailable (B2_DHT_IMPL=legacy, a driver without cuTensorMapEncodeTiled, more than DHT_MAX_JOBS jobs) and the
+// LDG-staged k_dht above runs instead
+int b2_dht_tma_run(b2_ctx *ctx, const b2_dht_job *jobs, int njobs, int Nz, int Nr, cudaStream_t s);
+
+static int run_tma(b2_ctx *ctx, const b2_dht_job *jobs, int njobs, int Nz, int Nr, cudaStream_t s) {
+    B2Prof prof_(B2P_DHT, s);
+    int rc = b2_dht_tma_run(ctx, jobs, njobs, Nz, Nr, s);
+    if (rc == 0)
+        for (int k = 0; k < njobs; ++k)
+            g_dht_flops += (jobs[k].kind == B2_DHT_SCALAR ? 1. : 2.) * 4. * Nz * (double)Nr * Nr;
+    return rc;
+}
+
 extern "C" {
 
 double b2_dht_flops(void) { return g_dht_flops; }
 
-// Batched transforms: one launch per kernel flavour for the whole list (all modes / components).
+// Batched transforms: the whole list (all modes / components, any mix of kinds) in one launch.
 int b2_dht_batch(b2_ctx *ctx, int njobs, const b2_dht_job *jobs, int Nz, int Nr, void *stream) {
+    {   // TMA path: the whole list in one launch
+        int rc = run_tma(ctx, jobs, njobs, Nz, Nr, b2_stream_of(ctx, stream));
+        if (rc != 1) return rc;          // done (0) or failed (<0 / CUDA code); 1 = path unavailable
+    }
+    // LDG-staged kernels: one launch per flavour, flushed whenever a list is full
     DhtJobs j1, j2;
     int n1 = 0, n2 = 0;
+    cudaStream_t s = b2_stream_of(ctx, stream);
     for (int k = 0; k < njobs; ++k) {
         const b2_dht_job &u = jobs[k];
         if (u.kind == B2_DHT_SCALAR) {
-            if (n1 >= DHT_MAX_JOBS) return b2_fail(-3, "b2_dht_batch: too many jobs", __FILE__, __LINE__);
+            if (n1 >= DHT_MAX_JOBS) { int rc = launch_dht<1>(ctx, j1, n1, Nz, Nr, s); if (rc) return rc; n1 = 0; }
             DhtJob &j = j1.j[n1++];
             j.in1 = (const double2 *)u.in1; j.in2 = nullptr; j.out1 = (double2 *)u.out1; j.out2 = nullptr;
             j.M1 = u.M1; j.M2 = nullptr; j.rowscale = u.rowscale;
             j.c1 = make_double2(1., 0.); j.c2 = make_double2(0., 0.);
         } else if (u.kind == B2_DHT_RT_TO_PM) {
-            if (n1 + 2 > DHT_MAX_JOBS) return b2_fail(-3, "b2_dht_batch: too many jobs", __FILE__, __LINE__);
+            if (n1 + 2 > DHT_MAX_JOBS) { int rc = launch_dht<1>(ctx, j1, n1, Nz, Nr, s); if (rc) return rc; n1 = 0; }
             for (int h = 0; h < 2; ++h) {
                 DhtJob &j = j1.j[n1++];
                 j.in1 = (const double2 *)u.in1; j.in2 = (const double2 *)u.in2;
@@ -240,7 +260,7 @@ int b2_dht_batch(b2_ctx *ctx, int njobs, const b2_dht_job *jobs, int Nz, int Nr,
                 j.c1 = make_double2(0.5, 0.); j.c2 = make_double2(0., h == 0 ? -0.5 : 0.5);
             }
         } else if (u.kind == B2_DHT_PM_TO_RT) {
-            if (n2 >= DHT_MAX_JOBS) return b2_fail(-3, "b2_dht_batch: too many jobs", __FILE__, __LINE__);
+            if (n2 >= DHT_MAX_JOBS) { int rc = launch_dht<2>(ctx, j2, n2, Nz, Nr, s); if (rc) return rc; n2 = 0; }
             DhtJob &j = j2.j[n2++];
             j.in1 = (const double2 *)u.in1; j.in2 = (const double2 *)u.in2;
             j.out1 = (double2 *)u.out1; j.out2 = (double2 *)u.out2;
@@ -250,7 +270,6 @@ int b2_dht_batch(b2_ctx *ctx, int njobs, const b2_dht_job *jobs, int Nz, int Nr,
             return b2_fail(-3, "b2_dht_batch: unknown job kind", __FILE__, __LINE__);
         }
     }
-    cudaStream_t s = b2_stream_of(ctx, stream);
     if (n1) { int rc = launch_dht<1>(ctx, j1, n1, Nz, Nr, s); if (rc) return rc; }
     if (n2) { int rc = launch_dht<2>(ctx, j2, n2, Nz, Nr, s); if (rc) return rc; }
     return 0;
@@ -258,6 +277,11 @@ int b2_dht_batch(b2_ctx *ctx, int njobs, const b2_dht_job *jobs, int Nz, int Nr,
 
 int b2_dht(b2_ctx *ctx, const void *in, void *out, const double *M, const double *rowscale, int Nz, int Nr,
            void *stream) {
+    {
+        b2_dht_job u = {in, nullptr, out, nullptr, M, nullptr, rowscale, B2_DHT_SCALAR};
+        int rc = run_tma(ctx, &u, 1, Nz, Nr, b2_stream_of(ctx, stream));
+        if (rc != 1) return rc;
+    }
     DhtJobs jobs;
     DhtJob &j = jobs.j[0];
     j.in1 = (const double2 *)in; j.in2 = nullptr; j.out1 = (double2 *)out; j.out2 = nullptr;
@@ -268,6 +292,11 @@ int b2_dht(b2_ctx *ctx, const void *in, void *out, const double *M, const double
 
 int b2_dht_rt_to_pm(b2_ctx *ctx, const void *r, const void *t, void *out_p, void *out_m, const double *Mp,
                     const double *Mm, const double *rowscale, int Nz, int Nr, void *stream) {
+    {
+        b2_dht_job u = {r, t, out_p, out_m, Mp, Mm, rowscale, B2_DHT_RT_TO_PM};
+        int rc = run_tma(ctx, &u, 1, Nz, Nr, b2_stream_of(ctx, stream));
+        if (rc != 1) return rc;
+    }
     DhtJobs jobs;
     for (int k = 0; k < 2; ++k) {
         DhtJob &j = jobs.j[k];
@@ -282,6 +311,11 @@ int b2_dht_rt_to_pm(b2_ctx *ctx, const void *r, const void *t, void *out_p, void
 
 int b2_dht_pm_to_rt(b2_ctx *ctx, const void *p, const void *m, void *out_r, void *out_t, const double *iMp,
                     const double *iMm, const double *rowscale, int Nz, int Nr, void *stream) {
+    {
+        b2_dht_job u = {p, m, out_r, out_t, iMp, iMm, rowscale, B2_DHT_PM_TO_RT};
+        int rc = run_tma(ctx, &u, 1, Nz, Nr, b2_stream_of(ctx, stream));
+        if (rc != 1) return rc;
+    }
     DhtJobs jobs;
     DhtJob &j = jobs.j[0];
     j.in1 = (const double2 *)p; j.in2 = (const double2 *)m;

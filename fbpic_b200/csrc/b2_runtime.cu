@@ -104,17 +104,20 @@ int b2_ctx_destroy(b2_ctx *ctx) {
 void *b2_ctx_stream(b2_ctx *ctx) { return (void *)ctx->stream; }
 
 int b2_malloc(void **p, size_t n) { B2_CUDA(cudaMalloc(p, n ? n : 16)); return 0; }
-int b2_free(void *p) { B2_CUDA(cudaFree(p)); return 0; }
+int b2_free(void *p) { b2_dht_forget(p); B2_CUDA(cudaFree(p)); return 0; }
 int b2_host_alloc(void **p, size_t n) { B2_CUDA(cudaMallocHost(p, n ? n : 16)); return 0; }
 int b2_host_free(void *p) { B2_CUDA(cudaFreeHost(p)); return 0; }
 int b2_memcpy_h2d(void *d, const void *h, size_t n, void *s) {
+    b2_dht_forget(d);
     B2_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, (cudaStream_t)s)); return 0; }
 int b2_memcpy_d2h(void *h, const void *d, size_t n, void *s) {
     B2_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, (cudaStream_t)s)); return 0; }
 int b2_memcpy_d2d(void *dst, const void *src, size_t n, void *s) {
+    b2_dht_forget(dst);
     B2_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)s));
     g_b2_launches.fetch_add(1); return 0; }
 int b2_memset(void *p, int v, size_t n, void *s) {
+    b2_dht_forget(p);
     B2_CUDA(cudaMemsetAsync(p, v, n, (cudaStream_t)s)); g_b2_launches.fetch_add(1); return 0; }
 int b2_stream_sync(void *s) { B2_CUDA(cudaStreamSynchronize((cudaStream_t)s)); return 0; }
 int b2_device_sync(void) { B2_CUDA(cudaDeviceSynchronize()); return 0; }

@@ -535,28 +535,37 @@ class Fields(object):
         return out
 
     def fused_deposit2spect(self, fieldtype, filter_currents=True):
-        """divide_by_volume + interp2spect + filter_spect of a freshly deposited source
-        (main.py:640,657,666-668) as 1 (rho) or 3 (J) FFTs per mode + ONE batched Hankel launch."""
+        """divide_by_volume + interp2spect + filter_spect of freshly deposited sources
+        (main.py:640,657,666-668) as 1 (rho) or 3 (J) FFTs per mode + ONE batched Hankel launch.
+        `fieldtype` may be a list (e.g. ['J', 'rho_next']: the current deposited at the half step is
+        transformed together with the charge deposited at the end of the step -- nothing reads the
+        spectral current in between), all of it in one FFT call and one Hankel launch."""
+        fieldtypes = [fieldtype] if isinstance(fieldtype, str) else list(fieldtype)
         T = self._fused_tables(filter_currents)
         ctx = _lib.context()
         jobs, ffts = [], []
         for m in range(self.Nm):
             g, s, t = self.interp[m], self.spect[m], T[m]
             fz = t['fz'].ptr if t['fz'] is not None else None
-            if fieldtype == 'J':
-                ffts += [(g.Jz, t['buf'][0]), (g.Jr, t['buf'][1]), (g.Jt, t['buf'][2])]
-                jobs.append(DhtJob(t['buf'][0].ptr, None, s.Jz.ptr, None, t['F0'].ptr, None, fz, _lib.DHT_SCALAR))
-                jobs.append(DhtJob(t['buf'][1].ptr, t['buf'][2].ptr, s.Jp.ptr, s.Jm.ptr, t['Fp'].ptr, t['Fm'].ptr,
-                                   fz, _lib.DHT_RT_TO_PM))
-            elif fieldtype in RHO_TYPES:
-                ffts.append((g.rho, t['buf'][0]))
-                jobs.append(DhtJob(t['buf'][0].ptr, None, getattr(s, fieldtype).ptr, None, t['F0'].ptr, None,
-                                   fz, _lib.DHT_SCALAR))
-            else:
-                raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
+            nbuf = 0
+            for ft in fieldtypes:
+                if ft == 'J':
+                    bz, br, bt = t['buf'][nbuf:nbuf + 3]
+                    nbuf += 3
+                    ffts += [(g.Jz, bz), (g.Jr, br), (g.Jt, bt)]
+                    jobs.append(DhtJob(bz.ptr, None, s.Jz.ptr, None, t['F0'].ptr, None, fz, _lib.DHT_SCALAR))
+                    jobs.append(DhtJob(br.ptr, bt.ptr, s.Jp.ptr, s.Jm.ptr, t['Fp'].ptr, t['Fm'].ptr,
+                                       fz, _lib.DHT_RT_TO_PM))
+                elif ft in RHO_TYPES:
+                    b = t['buf'][nbuf]
+                    nbuf += 1
+                    ffts.append((g.rho, b))
+                    jobs.append(DhtJob(b.ptr, None, getattr(s, ft).ptr, None, t['F0'].ptr, None,
+                                       fz, _lib.DHT_SCALAR))
+                else:
+                    raise ValueError('Invalid string for fieldtype: %s' % ft)
         self._fft_many(ffts, 0)
-        arr = (DhtJob * len(jobs))(*jobs)
-        call.b2_dht_batch(ctx.handle, len(jobs), arr, self.Nz, self.Nr, None)
+        self._dht_batch(jobs)
 
     def fused_spect2interp_EB(self):
         """spect2interp('E') + spect2interp('B') (main.py:768-769): batched inverse Hankel
@@ -573,8 +582,7 @@ class Fields(object):
                 jobs.append(DhtJob(getattr(s, f + 'p').ptr, getattr(s, f + 'm').ptr, br.ptr, bt.ptr,
                                    t['Ip'].ptr, t['Im'].ptr, None, _lib.DHT_PM_TO_RT))
                 ffts += [(bz, getattr(g, f + 'z')), (br, getattr(g, f + 'r')), (bt, getattr(g, f + 't'))]
-        arr = (DhtJob * len(jobs))(*jobs)
-        call.b2_dht_batch(ctx.handle, len(jobs), arr, self.Nz, self.Nr, None)
+        self._dht_batch(jobs)
         self._fft_many(ffts, 2)
 
     def fused_partial2interp_EB(self):
@@ -599,30 +607,16 @@ class Fields(object):
                 old = getattr(g, name)
                 setattr(g, name, t['buf'][o])        # pointer swap: the result becomes the field array
                 t['buf'][o] = old
-        arr = (DhtJob * len(jobs))(*jobs)
-        call.b2_dht_batch(ctx.handle, len(jobs), arr, self.Nz, self.Nr, None)
+        self._dht_batch(jobs)
 
     def _dht_batch(self, jobs):
-        """b2_dht_batch on a job list of any length: one launch per kernel flavour carries at most MAX_DHT_JOBS
-        products (a scalar job is 1, an (r,t)->(p,m) job 2 products of the single-product kernel; a (p,m)->(r,t)
-        job is 1 product pair of the other kernel), longer lists are split."""
+        """b2_dht_batch on a job list of any length: one launch carries at most MAX_DHT_JOBS jobs (of any
+        mix of kinds), longer lists are split."""
         ctx = _lib.context()
-        chunk, n1, n2 = [], 0, 0
-
-        def flush():
-            if chunk:
-                arr = (DhtJob * len(chunk))(*chunk)
-                call.b2_dht_batch(ctx.handle, len(chunk), arr, self.Nz, self.Nr, None)
-
-        for j in jobs:
-            c1 = {_lib.DHT_SCALAR: 1, _lib.DHT_RT_TO_PM: 2}.get(j.kind, 0)
-            c2 = 1 if j.kind == _lib.DHT_PM_TO_RT else 0
-            if n1 + c1 > _lib.MAX_DHT_JOBS or n2 + c2 > _lib.MAX_DHT_JOBS:
-                flush()
-                chunk, n1, n2 = [], 0, 0
-            chunk.append(j)
-            n1, n2 = n1 + c1, n2 + c2
-        flush()
+        for i in range(0, len(jobs), _lib.MAX_DHT_JOBS):
+            chunk = jobs[i:i + _lib.MAX_DHT_JOBS]
+            arr = (DhtJob * len(chunk))(*chunk)
+            call.b2_dht_batch(ctx.handle, len(chunk), arr, self.Nz, self.Nr, None)
 
     def _pml_buffers(self):
         if getattr(self, '_pml_buf', None) is None:

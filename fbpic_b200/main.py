@@ -207,8 +207,12 @@ class Simulation(object):
             for species in ptcl:
                 species.keep_fields_sorted = False
 
-            self.deposit('J', exchange=(correct_currents is False))
             cross = correct_currents and fld.current_correction == 'cross-deposition'
+            # fused mode: nothing reads the spectral current before correct_currents, so its FFTs and Hankel
+            # transforms wait for the charge deposited at the end of the step and share its launches
+            defer_J = self.fused and not cross and not self.use_pml and \
+                not (self.comm.size > 1 and ((correct_currents is False) or (use_true_rho is True)))
+            self.deposit('J', exchange=(correct_currents is False), defer_spectral=defer_J)
             if cross:                                 # main.py:512-514
                 self.cross_deposit(move_positions)
             # fused mode: the second half push rides inside the rho deposition kernel when every
@@ -283,8 +287,10 @@ class Simulation(object):
         # bytes copied host->device / device->host by this call (counted from the arrays actually copied)
         self.last_step_bytes = {k: _lib.TRANSFERRED[k] - bytes0[k] for k in bytes0}
 
-    def deposit(self, fieldtype, exchange=False, update_spectral=True, species_list=None, push=None):
-        """fbpic/main.py:588-670"""
+    def deposit(self, fieldtype, exchange=False, update_spectral=True, species_list=None, push=None,
+                defer_spectral=False):
+        """fbpic/main.py:588-670.  `defer_spectral` (fused mode): the transforms of this source are batched
+        with those of the next fused deposit."""
         fld = self.fld
         if species_list is None:            # everything deposits (main.py:618-624)
             species_list = [s for s in self.ptcl if not s.is_tracer]
@@ -308,9 +314,15 @@ class Simulation(object):
         fld.sum_reduce_deposition_array(grid_type)
         if self.fused and update_spectral and not (exchange and self.comm.size > 1):
             # divide_by_volume, the transforms and the filter as FFTs + one batched Hankel launch
-            fld.fused_deposit2spect(fieldtype, self.filter_currents)
+            pending = getattr(self, '_pending_spect', [])
+            if defer_spectral:
+                self._pending_spect = pending + [fieldtype]
+            else:
+                self._pending_spect = []
+                fld.fused_deposit2spect(pending + [fieldtype], self.filter_currents)
             fld.exchanged_source[fieldtype] = exchange
             return
+        assert not getattr(self, '_pending_spect', []), 'a deferred transform must be followed by a fused deposit'
         fld.divide_by_volume(grid_type)
         if exchange and self.comm.size > 1:
             self.comm.exchange_fields(fld.interp, grid_type, 'add')

@@ -240,3 +240,49 @@ def test_fused_deposition_paths_vs_oracle(shape, Nm):
     raw = oracle_dep('rho', Q)
     for m in range(Nm):
         assert_close(sim.fld.interp[m].rho.get(), raw[0, m], 1e-13, 'displaced/fused rho m%d' % m)
+
+
+@pytest.mark.parametrize('Nz,Nr', [(1000, 200), (2304, 72), (90, 16)])
+def test_dht_batch_all_kinds_vs_numpy(Nz, Nr):
+    """b2_dht_batch with a mixed job list (scalar, (r,t)->(p,m), (p,m)->(r,t), with and without a row scale) at
+    sizes whose 16-row units do not divide evenly among the persistent CTAs of the TMA-fed kernel (partial
+    tiles, several column strips, zero-padded K and N of the packed matrices); out = rowscale * (A @ M)."""
+    import ctypes
+    from fbpic_b200 import _lib
+    from fbpic_b200._lib import DeviceArray, DhtJob, call
+    rng = np.random.default_rng(Nz * 7 + Nr)
+    cplx = lambda: rng.normal(size=(Nz, Nr)) + 1.j * rng.normal(size=(Nz, Nr))
+    mats = [rng.normal(size=(Nr, Nr)) for _ in range(4)]
+    d_mats = [DeviceArray.from_numpy(M) for M in mats]
+    rs = rng.uniform(0.5, 1.5, size=Nz)
+    d_rs = DeviceArray.from_numpy(rs)
+    ins = [cplx() for _ in range(8)]
+    d_ins = [DeviceArray.from_numpy(a) for a in ins]
+    d_outs = [DeviceArray((Nz, Nr), np.complex128) for _ in range(10)]
+    jobs, want = [], []
+    # 3 scalar jobs (one with row scale)
+    for k, (mi, scale) in enumerate([(0, None), (1, d_rs), (2, None)]):
+        jobs.append(DhtJob(d_ins[k].ptr, None, d_outs[k].ptr, None, d_mats[mi].ptr, None,
+                           scale.ptr if scale is not None else None, _lib.DHT_SCALAR))
+        want.append((k, (ins[k] @ mats[mi]) * (rs[:, None] if scale is not None else 1.)))
+    # forward vector job with row scale: p = (r - i t)/2 @ M0, m = (r + i t)/2 @ M3
+    jobs.append(DhtJob(d_ins[3].ptr, d_ins[4].ptr, d_outs[3].ptr, d_outs[4].ptr, d_mats[0].ptr, d_mats[3].ptr,
+                       d_rs.ptr, _lib.DHT_RT_TO_PM))
+    want.append((3, (0.5 * (ins[3] - 1.j * ins[4]) @ mats[0]) * rs[:, None]))
+    want.append((4, (0.5 * (ins[3] + 1.j * ins[4]) @ mats[3]) * rs[:, None]))
+    # two inverse vector jobs: r = P + Q, t = i (P - Q)
+    for a, b, o, (m1, m2) in ((5, 6, 5, (1, 2)), (6, 7, 7, (3, 0))):
+        jobs.append(DhtJob(d_ins[a].ptr, d_ins[b].ptr, d_outs[o].ptr, d_outs[o + 1].ptr, d_mats[m1].ptr,
+                           d_mats[m2].ptr, None, _lib.DHT_PM_TO_RT))
+        P, Q = ins[a] @ mats[m1], ins[b] @ mats[m2]
+        want.append((o, P + Q))
+        want.append((o + 1, 1.j * (P - Q)))
+    arr = (DhtJob * len(jobs))(*jobs)
+    call.b2_dht_batch(_lib.context().handle, len(jobs), arr, Nz, Nr, None)
+    for o, ref in want:
+        assert_close(d_outs[o].get(), ref, 1e-13, 'output %d' % o)
+    # a matrix buffer that is overwritten must not be served from the packed-matrix cache
+    M_new = rng.normal(size=(Nr, Nr))
+    d_mats[0].set(M_new)
+    call.b2_dht(_lib.context().handle, d_ins[0].ptr, d_outs[9].ptr, d_mats[0].ptr, None, Nz, Nr, None)
+    assert_close(d_outs[9].get(), ins[0] @ M_new, 1e-13, 'after matrix update')
