@@ -39,6 +39,13 @@ CONFIGS = {
     'C2': dict(Nz=4096, Nr=256, Nm=2, ppc=(2, 2, 4), dz=0.05e-6, rmax=20.e-6 * 256 / 50, n_e=4.e24),
     'C1': dict(Nz=256, Nr=64, Nm=2, ppc=(2, 2, 4), dz=0.2e-6, rmax=20.e-6, n_e=2.e24),
     'C4': dict(Nz=2048, Nr=512, Nm=4, ppc=(2, 2, 16), dz=0.05e-6, rmax=40.e-6, n_e=4.e24),
+    # C4 with the minimum azimuthal sampling main.py:817-821 allows for the default of p_nt (transform-dominated)
+    'C4t': dict(Nz=2048, Nr=512, Nm=4, ppc=(2, 2, 4), dz=0.05e-6, rmax=40.e-6, n_e=4.e24),
+    # C2 as the script runs it: open z (damping + injection cells: 4416 local cells) and a moving window at c
+    'C2w': dict(Nz=4096, Nr=256, Nm=2, ppc=(2, 2, 4), dz=0.05e-6, rmax=20.e-6 * 256 / 50, n_e=4.e24, window=True),
+    # C5: boosted frame, Galilean PSATD, gamma = 10, electrons + ions, 8 per cell in theta; Nz per GPU (named on 4)
+    'C5': dict(Nz=2048, Nr=256, Nm=2, ppc=(2, 2, 8), dz=0.05e-6 * 10, rmax=20.e-6 * 256 / 50, n_e=4.e24 * 10,
+               gamma_boost=10., ions=True),
     'tiny': dict(Nz=128, Nr=32, Nm=2, ppc=(2, 2, 4), dz=0.1e-6, rmax=10.e-6, n_e=4.e24),
 }
 
@@ -59,7 +66,7 @@ def laser_fields(z, r, a0=4., w0=5.e-6, ctau=16.e-15 * c, z0=None, lambda0=0.8e-
     return Er1, Et1, Br1, Bt1
 
 
-def build_b200_sim(cfg, n_gpus, fused=True, seed=0, sort_period=1, full_slab=False):
+def build_b200_sim(cfg, n_gpus, fused=True, seed=0, sort_period=1, full_slab=True):
     from fbpic_b200 import Simulation
     np.random.seed(seed + int(os.environ.get('RANK', '0')))
     dt = cfg['dz'] / c
@@ -68,24 +75,51 @@ def build_b200_sim(cfg, n_gpus, fused=True, seed=0, sort_period=1, full_slab=Fal
     n_guard = None
     nz_phys = cfg['Nz']
     if n_gpus > 1:
-        # z-slabs: every rank works on a LOCAL periodic box = physical cells + 2*n_guard guard cells and
-        # FFTs that length.  Guard width = stencil reach of n_order=32 (boundary_communicator.py:243-250),
-        # rounded up to a multiple of 8.  Default: the local box keeps the single-GPU length cfg['Nz']
-        # (4096 = one-kernel cuFFT; 4096 physical + 2*64 = 4224 costs 2.5x per transform), i.e. each
-        # GPU owns cfg['Nz'] - 2*n_guard physical cells; --full-slab keeps cfg['Nz'] physical cells.
+        # z-slabs: every rank works on a LOCAL periodic box = physical cells + 2*n_guard guard cells and FFTs
+        # that length.  Guard width >= stencil reach of n_order=32 (boundary_communicator.py:243-250).
+        # Default (`full_slab`): cfg['Nz'] PHYSICAL cells per GPU as BASELINE names C3 / C5; the guard is widened
+        # from the minimum (64) until the local length has only the factors 2, 3, 5 (4096 + 2*112 = 4320 =
+        # 2^5 3^3 5: cuFFT runs that length in one kernel, 4224 = 2^7 3 11 costs 2.5x per transform).
+        # --compact-slab: the local box keeps the single-GPU length (cfg['Nz'] - 2*n_guard physical cells).
         from fbpic_b200.host_tables import stencil_reach
         n_guard = stencil_reach(cfg['Nz'] * n_gpus, cfg['dz'], cfg['dz'], n_order, None, False) + 1
         n_guard = (n_guard + 7) // 8 * 8
-        if not full_slab:
+        if full_slab:
+            def smooth(n):
+                for f in (2, 3, 5):
+                    while n % f == 0:
+                        n //= f
+                return n == 1
+            while not smooth(cfg['Nz'] + 2 * n_guard):
+                n_guard += 8
+        else:
             nz_phys = cfg['Nz'] - 2 * n_guard
     Nz_g = nz_phys * n_gpus
     zmax = Nz_g * cfg['dz']
+    kw = {}
+    uz_m = 0.
+    if cfg.get('gamma_boost'):
+        gb = cfg['gamma_boost']
+        kw.update(v_comoving=-c * np.sqrt(1. - 1. / gb**2), use_galilean=True, initialize_ions=cfg.get('ions', False))
+        uz_m = -np.sqrt(gb**2 - 1.)
+        if n_gpus == 1:
+            n_order = 32
+    window = bool(cfg.get('window')) and n_gpus == 1
+    bz = 'open' if window else 'periodic'
     sim = Simulation(Nz_g, zmax, cfg['Nr'], cfg['rmax'], cfg['Nm'], dt, p_zmin=0., p_zmax=zmax,
                      p_rmin=0., p_rmax=cfg['rmax'], p_nz=p_nz, p_nr=p_nr, p_nt=p_nt, n_e=cfg['n_e'],
-                     n_order=n_order, n_guard=n_guard, boundaries={'z': 'periodic', 'r': 'reflective'},
-                     fused=fused, sort_period=sort_period)
+                     n_order=n_order, n_guard=n_guard, boundaries={'z': bz, 'r': 'reflective'},
+                     fused=fused, sort_period=sort_period, **kw)
+    if uz_m != 0.:
+        for sp in sim.ptcl:                 # the plasma flows backwards at gamma in the boosted frame (main.py:909-936)
+            sp.uz = np.full(sp.Ntot, uz_m)
+            sp.inv_gamma = np.full(sp.Ntot, 1. / np.sqrt(1. + uz_m**2))
+    if window:
+        sim.set_moving_window(v=c)
     g1 = sim.fld.interp[1]
-    Er1, Et1, Br1, Bt1 = laser_fields(g1.z, g1.r, z0=0.5 * zmax if n_gpus == 1 else 0.5 * nz_phys * cfg['dz'])
+    lam = 0.8e-6 * (cfg['dz'] / 0.05e-6)
+    Er1, Et1, Br1, Bt1 = laser_fields(g1.z, g1.r, lambda0=lam,
+                                      z0=0.5 * zmax if n_gpus == 1 else 0.5 * nz_phys * cfg['dz'])
     g1.Er[:, :], g1.Et[:, :], g1.Br[:, :], g1.Bt[:, :] = Er1, Et1, Br1, Bt1
     return sim
 
@@ -205,6 +239,17 @@ def bind_to_gpu_numa(device_index):
     return None
 
 
+def csrc_hash():
+    """sha256 over the CUDA sources of the library (ties an ncu traffic figure to the build it was captured from)"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, 'fbpic_b200', 'csrc')
+    for f in sorted(os.listdir(d)):
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), 'rb').read())
+    return h.hexdigest()
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -273,9 +318,10 @@ def main():
     ap.add_argument('--sort-period', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--full-slab', action='store_true',
-                    help='N>1: Nz physical cells per GPU plus guards (local FFT length Nz+2*n_guard) instead '
-                         'of a local box of Nz cells including the guards')
+    ap.add_argument('--compact-slab', action='store_true',
+                    help='N>1: local box of Nz cells INCLUDING the guards (Nz - 2*n_guard physical cells per GPU) '
+                         'instead of Nz physical cells per GPU plus guards')
+    ap.add_argument('--no-parity', action='store_true', help='N>1: skip the untimed N-rank vs 1-rank parity check')
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get('RANK', '0'))
@@ -342,7 +388,7 @@ def main():
     ctx = _lib.context()
     affinity = bind_to_gpu_numa(ctx.device)
     sim = build_b200_sim(cfg, n_gpus, fused=not args.no_fused, sort_period=args.sort_period,
-                         full_slab=args.full_slab)
+                         full_slab=not args.compact_slab)
     nz_local = sim.fld.interp[0].Nz
     if n_gpus > 1:
         workload += ' | z-slabs: %d physical + 2x%d guard = %d local cells per GPU, n_order=32' % (
@@ -421,6 +467,23 @@ def main():
         except Exception as exc:      # the device-timed line above must survive a failure of this leg
             e2e = {'value': None, 'unit': 'particle-updates/s', 'error': repr(exc)[:300]}
 
+    # ---- N > 1: the sharded loop against the same problem on one GPU (untimed; small periodic box, all ranks)
+    mgpu_parity = None
+    if dist is not None and not args.no_parity:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, 'tools'))
+            from mgpu_parity import periodic_case
+            cases = []
+            for correct, tol in ((False, 1e-9), (True, 5e-4)):
+                ok, err, counts = periodic_case(dist, correct, tol, nsteps=24, nzr=96, verbose=False)
+                cases.append({'correct_currents': correct, 'ok': ok, 'max_err_rel_to_field_max': err, 'tol': tol,
+                              'particles_per_rank': counts})
+            mgpu_parity = {'ranks': world, 'ok': all(cse['ok'] for cse in cases), 'cases': cases,
+                           'what': 'E, B, J, rho of %d z-slabs (96 physical cells each, NCCL halo + particle migration, '
+                                   '24 steps) vs the same box on one GPU (tools/mgpu_parity.py)' % world}
+        except Exception as exc:
+            mgpu_parity = {'ranks': world, 'ok': False, 'error': repr(exc)[:300]}
+
     if rank != 0:
         return
     # ---- roofline of the dominant kernel family (device time from CUDA events inside the timed region)
@@ -428,47 +491,60 @@ def main():
     hbm_peak = (peaks or {}).get('hbm_gbs', 6650.)
     peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback'
     cells = nz_local * cfg['Nr'] * 16
-    alg = {   # algorithmic bytes per launch
+    Nm = cfg['Nm']
+    exchange_path = (n_gpus > 1) or bool(cfg.get('window'))      # guard exchange / damping between iFFT and FFT
+    # algorithmic bytes PER STEP of each kernel family, whatever the number of launches:
+    alg = {
         # J: + (4+64+64-64) B/particle on the steps where the SoA permutation rides along;
         # rho: the second position push is fused in (reads 64, writes 24 B/particle)
-        'deposit_J': (64 + 68 / max(args.sort_period, 1)) * Ntot_local + 3 * cfg['Nm'] * cells,
-        'deposit_rho': 88 * Ntot_local + cfg['Nm'] * cells,
-        'gather_push': 112 * Ntot_local + 6 * cfg['Nm'] * cells,
-        'permute': (8 + 128) * Ntot_local,
-        'sort': (4 + 12 + 4) * Ntot_local,
-        'fft': 2 * cells,
-        'spectral': (11 + 8) * cells + 5 * cells // 2,
+        'deposit_J': (64 + 68 / max(args.sort_period, 1)) * Ntot_local + 3 * Nm * cells,
+        'deposit_rho': 88 * Ntot_local + Nm * cells,
+        'gather_push': 112 * Ntot_local + 6 * Nm * cells,
+        'sort': (4 + 12 + 4) * Ntot_local / max(args.sort_period, 1),
+        # z-FFTs: J (3) + rho (1) forward and E, B (6) inverse per mode; the exchange path adds the
+        # iFFT -> exchange -> FFT round trips of J (3 + 3) and of E, B (6 more forward)
+        'fft': (22 if exchange_path else 10) * Nm * 2 * cells,
+        # fused correct + push (+ push_rho): reads 11, writes 8 arrays, coefficients 2.5 arrays-worth per mode;
+        # as separate correct / push / push_rho launches: 27 arrays
+        'spectral': Nm * ((27 if exchange_path else 19) * cells + 5 * cells // 2),
     }
     top = max(prof.items(), key=lambda kv: kv[1]['ms'])[0] if prof else None
     roofline = None
     shares = {k: v['ms'] / t_ms for k, v in prof.items()}
     if top == 'dht':
-        # flops counted by the library for the launches of the timed region (4*Nz*Nr^2 per array)
-        flop_step = dht_flops / args.steps
-        ach = flop_step * args.steps / (prof['dht']['ms'] * 1e-3) / 1e12
-        roofline = {'kernel': 'k_dht (Hankel GEMM, fp64 DMMA)', 'bound': 'tensor', 'achieved': ach,
+        # flops counted by the library for the launches of the timed region (4*Nz*Nr^2 per transformed array)
+        ach = dht_flops / (prof['dht']['ms'] * 1e-3) / 1e12
+        roofline = {'kernel': 'k_dht_tma (Hankel GEMM, TMA-fed fp64 DMMA)', 'bound': 'tensor', 'achieved': ach,
                     'peak': 37.1, 'unit': 'TFLOP/s', 'frac': ach / 37.1, 'traffic': None,
-                    'peak_source': 'measured DMMA.8x8x4 issue peak on B200 (profiles/r01_microbench.txt); '
-                                   'MEASURED_PEAKS.json has no fp64 entry'}
+                    'peak_source': 'measured DMMA.8x8x4 issue peak on B200 (profiles/r01_microbench.txt, '
+                                   'profiles/r02_microbench_dmma_operands.txt); MEASURED_PEAKS.json has no fp64 entry'}
     elif top in alg:
-        per_launch_ms = prof[top]['ms'] / prof[top]['launches']
-        ach = alg[top] / (per_launch_ms * 1e-3) / 1e9
+        ach = alg[top] * args.steps / (prof[top]['ms'] * 1e-3) / 1e9
         roofline = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
                     'frac': ach / hbm_peak, 'traffic': None, 'peak_source': peak_src}
-    try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
-    except Exception:
-        traffic = {}
-    if roofline is not None and args.config == 'C2' and n_gpus == 1:
-        roofline['traffic'] = (traffic.get(top) or {}).get('bytes_per_launch')
-        roofline['traffic_source'] = 'ncu --set full capture of this kernel (profiles/r01_ncu_final.txt), per launch'
+    # DRAM traffic per launch of the dominant kernel: from the ncu --set full capture of THIS build
+    # (profiles/r02_traffic.json records the hash of csrc/ it was taken from; null if the sources changed since)
+    if roofline is not None:
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
+        except Exception:
+            traffic = {}
+        ent = (traffic.get('kernels') or {}).get('%s:%s' % (args.config, top))
+        if ent and n_gpus == 1 and traffic.get('csrc_sha256') == csrc_hash():
+            roofline['traffic'] = ent['dram_bytes_per_launch']
+            roofline['traffic_source'] = ent['source']
+        else:
+            roofline['traffic_source'] = 'no ncu --set full capture of this kernel for this build and config'
     kernels = {}
     for k, v in prof.items():
         d = dict(ms_per_step=v['ms'] / args.steps, launches_per_step=v['launches'] / args.steps,
                  share=shares[k])
         if k in alg:
-            d['GBps'] = alg[k] / (v['ms'] / v['launches'] * 1e-3) / 1e9
+            d['GBps'] = alg[k] * args.steps / (v['ms'] * 1e-3) / 1e9
             d['hbm_frac'] = d['GBps'] / hbm_peak
+        if k == 'dht':
+            d['TFLOPs'] = dht_flops / (v['ms'] * 1e-3) / 1e12
+            d['tensor_frac'] = d['TFLOPs'] / 37.1
         kernels[k] = d
 
     cpu_baseline = None
@@ -503,6 +579,8 @@ def main():
         'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline,
         'cpu_baseline': cpu_baseline, 'kernels': kernels,
     }
+    if mgpu_parity is not None:
+        out['mgpu_parity'] = mgpu_parity
     print(json.dumps(out))
 
 

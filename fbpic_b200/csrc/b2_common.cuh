@@ -101,3 +101,41 @@ __device__ __forceinline__ B2Cyl b2_cyl(double xj, double yj, double zj,
     c.z_cell = __dadd_rn(__dmul_rn(invdz, __dsub_rn(zj, zmin)), -0.5);
     return c;
 }
+
+// cell key (cuda_sorting.py:55-88)
+__device__ __forceinline__ int b2_cell_of(const B2Cyl &c, int Nz, int Nr) {
+    int ir_upper = (int)ceil(c.r_cell);
+    int iz_upper = (int)ceil(c.z_cell);
+    if (ir_upper > Nr) ir_upper = Nr;
+    if (iz_upper < 0) iz_upper += Nz;
+    else if (iz_upper > Nz - 1) iz_upper -= Nz;
+    return ir_upper + iz_upper * (Nr + 1);
+}
+
+
+// Vay pusher (push/inline_functions.py:11-48)
+__device__ __forceinline__ void b2_vay(double &ux, double &uy, double &uz, double &inv_gamma,
+                                       const double F[6], double econst, double bconst) {
+    const double taux = bconst * F[3], tauy = bconst * F[4], tauz = bconst * F[5];
+    const double tau2 = taux * taux + tauy * tauy + tauz * tauz;
+    const double uxp = ux + econst * F[0] + inv_gamma * (uy * tauz - uz * tauy);
+    const double uyp = uy + econst * F[1] + inv_gamma * (uz * taux - ux * tauz);
+    const double uzp = uz + econst * F[2] + inv_gamma * (ux * tauy - uy * taux);
+    const double sigma = 1 + uxp * uxp + uyp * uyp + uzp * uzp - tau2;
+    const double utau = uxp * taux + uyp * tauy + uzp * tauz;
+    const double igf = sqrt(2. / (sigma + sqrt(sigma * sigma + 4 * (tau2 + utau * utau))));
+    const double tx = igf * taux, ty = igf * tauy, tz = igf * tauz, ut = igf * utau;
+    const double s = 1. / (1 + tau2 * igf * igf);
+    ux = s * (uxp + tx * ut + uyp * tz - uzp * ty);
+    uy = s * (uyp + ty * ut + uzp * tx - uxp * tz);
+    uz = s * (uzp + tz * ut + uxp * ty - uyp * tx);
+    inv_gamma = igf;
+}
+
+
+// b2_gather_pipe.cu: persistent gather + push kernel with TMA-staged field tiles (linear shapes).  Processes the
+// first *done particles (a multiple of 128, possibly 0 when the path is unavailable); rc != 0 is an error.
+int b2_gather_push_pipe(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, double *ux, double *uy, double *uz,
+                        double *inv_gamma, double rmax_gather, double invdz, double zmin, int Nz, double invdr,
+                        double rmin, int Nr, int Nm, const void *const *grids, double econst, double bconst, double chdt,
+                        int32_t *cell_idx, double key_zmin, cudaStream_t s, int64_t *done);

@@ -442,9 +442,14 @@ static std::mutex g_dt_mutex;
 struct DtPacked { double *ptr; int Nr; };
 static std::map<const void *, DtPacked> g_dt_packed;                 // keyed by the row-major matrix pointer
 struct DtMapKey {
-    const void *p; int Nz, Nr;
+    const void *p; int Nz, Nr, box_d, box_rows, swz;
     bool operator<(const DtMapKey &o) const {
-        return p != o.p ? p < o.p : (Nz != o.Nz ? Nz < o.Nz : Nr < o.Nr);
+        if (p != o.p) return p < o.p;
+        if (Nz != o.Nz) return Nz < o.Nz;
+        if (Nr != o.Nr) return Nr < o.Nr;
+        if (box_d != o.box_d) return box_d < o.box_d;
+        if (box_rows != o.box_rows) return box_rows < o.box_rows;
+        return swz < o.swz;
     }
 };
 static std::map<DtMapKey, CUtensorMap> g_dt_maps;
@@ -493,23 +498,31 @@ static int dt_packed_matrix(const double *M, int Nr, cudaStream_t s, const doubl
     return 0;
 }
 
-static int dt_tensor_map(const void *A, int Nz, int Nr, CUtensorMap *out) {
-    const DtMapKey key{A, Nz, Nr};
+// Tensor map of a complex [Nz,Nr] field array seen as doubles [Nz][2*Nr]: boxes of box_rows rows x box_d doubles
+// (cached per array / shape / box).  Shared with b2_gather_pipe.cu.  rc 1: the TMA descriptor API is unavailable.
+int b2_tma_field_map(const void *A, int Nz, int Nr, int box_d, int box_rows, int swizzle128, CUtensorMap *out) {
+    if (dt_resolve() < 0) return 1;
+    const DtMapKey key{A, Nz, Nr, box_d, box_rows, swizzle128};
     auto it = g_dt_maps.find(key);
     if (it != g_dt_maps.end()) { *out = it->second; return 0; }
     if (g_dt_maps.size() > 4096) g_dt_maps.clear();
     CUtensorMap m;
     const cuuint64_t dims[2] = {(cuuint64_t)2 * Nr, (cuuint64_t)Nz};       // doubles per row, rows
     const cuuint64_t strides[1] = {(cuuint64_t)Nr * 16};                   // bytes between rows
-    const cuuint32_t box[2] = {16, DT_BM};                                 // 8 complex x 64 rows
+    const cuuint32_t box[2] = {(cuuint32_t)box_d, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = g_dt_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(A), dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return b2_fail((int)r, "cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
     g_dt_maps[key] = m;
     *out = m;
     return 0;
+}
+std::mutex &b2_tma_mutex() { return g_dt_mutex; }
+static int dt_tensor_map(const void *A, int Nz, int Nr, CUtensorMap *out) {
+    return b2_tma_field_map(A, Nz, Nr, 16, DT_BM, 1, out);       // 8 complex x 64 rows, SWIZZLE_128B
 }
 
 struct DtHostJob {           // one job in terms of raw pointers

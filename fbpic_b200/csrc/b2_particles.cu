@@ -10,15 +10,6 @@ static inline unsigned grid1d(int64_t n, int tpb) { return (unsigned)((n + tpb -
 // =====================================================================================
 // cell key (cuda_sorting.py:55-88)
 // =====================================================================================
-__device__ __forceinline__ int b2_cell_of(const B2Cyl &c, int Nz, int Nr) {
-    int ir_upper = (int)ceil(c.r_cell);
-    int iz_upper = (int)ceil(c.z_cell);
-    if (ir_upper > Nr) ir_upper = Nr;
-    if (iz_upper < 0) iz_upper += Nz;
-    else if (iz_upper > Nz - 1) iz_upper -= Nz;
-    return ir_upper + iz_upper * (Nr + 1);
-}
-
 __global__ void k_cell_index(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
                              const double *__restrict__ z, double invdz, double zmin, int Nz,
                              double invdr, double rmin, int Nr, int32_t *__restrict__ cell_idx) {
@@ -222,24 +213,6 @@ k_gather(int64_t n, const double *__restrict__ x, const double *__restrict__ y, 
 // =====================================================================================
 // Vay pusher (push/inline_functions.py:11-48) and position push (push/cuda_methods.py:17-52)
 // =====================================================================================
-__device__ __forceinline__ void b2_vay(double &ux, double &uy, double &uz, double &inv_gamma,
-                                       const double F[6], double econst, double bconst) {
-    const double taux = bconst * F[3], tauy = bconst * F[4], tauz = bconst * F[5];
-    const double tau2 = taux * taux + tauy * tauy + tauz * tauz;
-    const double uxp = ux + econst * F[0] + inv_gamma * (uy * tauz - uz * tauy);
-    const double uyp = uy + econst * F[1] + inv_gamma * (uz * taux - ux * tauz);
-    const double uzp = uz + econst * F[2] + inv_gamma * (ux * tauy - uy * taux);
-    const double sigma = 1 + uxp * uxp + uyp * uyp + uzp * uzp - tau2;
-    const double utau = uxp * taux + uyp * tauy + uzp * tauz;
-    const double igf = sqrt(2. / (sigma + sqrt(sigma * sigma + 4 * (tau2 + utau * utau))));
-    const double tx = igf * taux, ty = igf * tauy, tz = igf * tauz, ut = igf * utau;
-    const double s = 1. / (1 + tau2 * igf * igf);
-    ux = s * (uxp + tx * ut + uyp * tz - uzp * ty);
-    uy = s * (uyp + ty * ut + uzp * tx - uxp * tz);
-    uz = s * (uzp + tz * ut + uxp * ty - uyp * tx);
-    inv_gamma = igf;
-}
-
 __global__ void k_push_p(int64_t n, double *__restrict__ ux, double *__restrict__ uy, double *__restrict__ uz,
                          double *__restrict__ inv_gamma, const double *__restrict__ Ex,
                          const double *__restrict__ Ey, const double *__restrict__ Ez,
@@ -656,8 +629,21 @@ int b2_gather_push(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, doub
     B2Grids G;
     for (int k = 0; k < 6 * Nm; ++k) G.g[k] = (const double2 *)grids[k];
     cudaStream_t s = b2_stream_of(ctx, stream);
-    unsigned g = grid1d(n, 256);
     const double ec = q * dt_p / (m * B2_C_LIGHT), bc = 0.5 * q * dt_p / m, chdt = B2_C_LIGHT * dt_x;
+    if (!cubic) {
+        // linear shapes: the persistent kernel with TMA-staged field tiles (b2_gather_pipe.cu) takes the full
+        // 128-particle chunks; what is left (n % 128 particles, or everything when that path is unavailable)
+        // goes to the kernels of this file
+        int64_t done = 0;
+        int rc = b2_gather_push_pipe(ctx, n, x, y, z, ux, uy, uz, inv_gamma, rmax_gather, invdz, zmin, Nz, invdr, rmin,
+                                     Nr, Nm, grids, ec, bc, chdt, cell_idx, key_zmin, s, &done);
+        if (rc) return rc;
+        if (done >= n) return 0;
+        x += done; y += done; z += done; ux += done; uy += done; uz += done; inv_gamma += done;
+        if (cell_idx) cell_idx += done;
+        n -= done;
+    }
+    unsigned g = grid1d(n, 256);
 #define B2_ARGS cubic != 0, g, s, n, x, y, z, ux, uy, uz, inv_gamma, rmax_gather, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt, cell_idx, key_zmin
     switch (Nm) {
         case 1: launch_gather_push<1>(B2_ARGS); break;

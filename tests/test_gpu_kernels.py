@@ -4,6 +4,7 @@ C ABI, against (a) the golden vectors generated from the unmodified FBPIC refere
 1e-13*(max|a|+max|b|) for deposition (the reference's own CPU/GPU tolerance,
 tests/test_cpu_gpu_deposition.py:96-98), 1e-13 for gather / push."""
 import ctypes
+import os
 import numpy as np
 import pytest
 from scipy.constants import c
@@ -286,3 +287,15 @@ def test_dht_batch_all_kinds_vs_numpy(Nz, Nr):
     d_mats[0].set(M_new)
     call.b2_dht(_lib.context().handle, d_ins[0].ptr, d_outs[9].ptr, d_mats[0].ptr, None, Nz, Nr, None)
     assert_close(d_outs[9].get(), ins[0] @ M_new, 1e-13, 'after matrix update')
+
+
+def test_gather_push_pipe_variant_matches_golden():
+    """The persistent TMA-staged gather+push kernel (opt-in, B2_GATHER_IMPL=pipe) against the same goldens and
+    oracle cases as the default kernel: the switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    env = dict(os.environ, B2_GATHER_IMPL='pipe')
+    out = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-m', 'gpu', '-q', '-x',
+                          '-p', 'no:cacheprovider', '-k', 'golden and not pipe or gather_vs_oracle'],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]

@@ -1,11 +1,8 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "transforms or dht" -p no:cacheprovider 2>&1 | tail -3
-export DHT_BENCH_REPS=20
-B2_DHT_IMPL=tma timeout 300 python tools/dht_bench.py --one 2>&1 | grep -v "C1" | cut -c1-150 | tee gpurun_out/r02_dht_bench_e.jsonl
-timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_step.py tests/test_gpu_plasma_wave.py tests/test_gpu_x_config_shapes.py tests/test_gpu_w4_scripts.py tests/test_gpu_w1_pml_cross.py -m gpu -q -p no:cacheprovider 2>&1 | tail -8
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>gpurun_out/bench_default.err | grep '^{' > gpurun_out/r02_b_bench_default.json; python - <<'PY'
-import json
-d=json.load(open('gpurun_out/r02_b_bench_default.json'))
-print(d['value'], d['ms_per_step'], d['roofline'], d['e2e']['value'])
-for k,v in d['kernels'].items(): print('   ',k, {a:round(b,4) for a,b in v.items()})
-PY
+timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "pipe or golden" -p no:cacheprovider 2>&1 | tail -3
+# ncu --set full of the hot kernels inside the bench command (steady state: skip the set-up launches)
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_dht_tma|k_gather_push|k_deposit_mma" --launch-skip 60 -c 10 -o gpurun_out/r02_hot -f python bench.py --steps 4 --warmup 3 --preroll 8 --no-e2e --no-cpu-baseline > gpurun_out/ncu_hot.log 2>&1; tail -2 gpurun_out/ncu_hot.log
+B2_GATHER_IMPL=pipe timeout 600 ncu --set full --import-source on --clock-control none -k regex:"k_gather_push" --launch-skip 10 -c 2 -o gpurun_out/r02_gather_pipe -f python bench.py --steps 4 --warmup 3 --preroll 8 --no-e2e --no-cpu-baseline > gpurun_out/ncu_gp.log 2>&1; tail -2 gpurun_out/ncu_gp.log
+# launch list of the bench command (per-launch durations, cold-cache / serialised)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 3 --preroll 2 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; tail -1 gpurun_out/ncu_launches.log | cut -c1-200
+ls -la gpurun_out/*.ncu-rep
