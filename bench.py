@@ -77,21 +77,20 @@ def build_b200_sim(cfg, n_gpus, fused=True, seed=0, sort_period=1, full_slab=Tru
     if n_gpus > 1:
         # z-slabs: every rank works on a LOCAL periodic box = physical cells + 2*n_guard guard cells and FFTs
         # that length.  Guard width >= stencil reach of n_order=32 (boundary_communicator.py:243-250).
-        # Default (`full_slab`): cfg['Nz'] PHYSICAL cells per GPU as BASELINE names C3 / C5; the guard is widened
-        # from the minimum (64) until the local length has only the factors 2, 3, 5 (4096 + 2*112 = 4320 =
-        # 2^5 3^3 5: cuFFT runs that length in one kernel, 4224 = 2^7 3 11 costs 2.5x per transform).
+        # Default (`full_slab`): cfg['Nz'] PHYSICAL cells per GPU as BASELINE names C3 / C5, local length
+        # cfg['Nz'] + 2*n_guard (4096 + 2*64 = 4224 = 64*66: the two-pass z-FFT of b2_fft.cu runs that length at
+        # 17 us per array, cuFFT needs 36 us -- profiles/r02_fft_group.txt).
         # --compact-slab: the local box keeps the single-GPU length (cfg['Nz'] - 2*n_guard physical cells).
         from fbpic_b200.host_tables import stencil_reach
         n_guard = stencil_reach(cfg['Nz'] * n_gpus, cfg['dz'], cfg['dz'], n_order, None, False) + 1
         n_guard = (n_guard + 7) // 8 * 8
         if full_slab:
-            def smooth(n):
-                for f in (2, 3, 5):
-                    while n % f == 0:
-                        n //= f
-                return n == 1
-            while not smooth(cfg['Nz'] + 2 * n_guard):
-                n_guard += 8
+            # widen the guard (steps of 8 cells) until the local length has a two-pass FFT plan with small radices
+            from fbpic_b200 import _lib as _l
+            for extra in range(0, 129, 8):
+                if _l.load().b2_fft_has_plan(cfg['Nz'] + 2 * (n_guard + extra), 13):
+                    n_guard += extra
+                    break
         else:
             nz_phys = cfg['Nz'] - 2 * n_guard
     Nz_g = nz_phys * n_gpus

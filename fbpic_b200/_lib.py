@@ -104,6 +104,7 @@ _SIGNATURES = {
     'b2_dht_pm_to_rt': [P, P, P, P, P, P, P, P, c_int, c_int, P],
     'b2_dht_batch': [P, c_int, ctypes.POINTER(DhtJob), c_int, c_int, P],
     'b2_dht_flops': [],
+    'b2_fft_has_plan': [c_int, c_int],
     'b2_rt_to_pm': [P, P, P, c_int, c_int, P],
     'b2_pm_to_rt': [P, P, P, c_int, c_int, P],
     'b2_filter': [P, c_int, P, P, P, c_int, c_int, P],

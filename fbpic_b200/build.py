@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'libfbpic_b200.so')
-SOURCES = ['b2_runtime.cu', 'b2_particles.cu', 'b2_gather_pipe.cu', 'b2_deposit_mma.cu', 'b2_fields.cu', 'b2_dht.cu', 'b2_dht_tma.cu', 'b2_comm.cu',
+SOURCES = ['b2_runtime.cu', 'b2_particles.cu', 'b2_gather_pipe.cu', 'b2_deposit_mma.cu', 'b2_fields.cu', 'b2_fft.cu', 'b2_dht.cu', 'b2_dht_tma.cu', 'b2_comm.cu',
            'b2_ext.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

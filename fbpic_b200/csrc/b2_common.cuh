@@ -56,6 +56,9 @@ static inline cudaStream_t b2_stream_of(b2_ctx *ctx, void *stream) {
 }
 
 int b2_scratch(b2_ctx *ctx, int slot, size_t nbytes, void **ptr);
+// b2_fft.cu: two-pass z-FFT; rc 1 = no plan for this length (cuFFT takes it)
+int b2_fft_own(b2_ctx *ctx, int na, const void *const *in, void *const *out, int Nz, int Nr, int inverse,
+               cudaStream_t s);
 // b2_dht_tma.cu: drop the cached packed Hankel matrix / tensor maps of a buffer that is freed or overwritten
 void b2_dht_forget(const void *p);
 

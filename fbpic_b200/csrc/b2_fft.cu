@@ -1,0 +1,270 @@
+// b2_fft.cu -- z-FFT of the [Nz][Nr] field arrays as a two-pass (four-step) transform, every access coalesced
+// along r.
+//
+// Replaces FFT.transform / inverse_transform (fbpic/fields/spectral_transform/fourier.py:104-168: cuFFT Z2Z plan
+// (Nz, batch Nr) + two transpose kernels + a scale pass).  cuFFT's strided plan on the native layout (b2_fields.cu)
+// needs no transposes, but runs at 1.8 TB/s for Nz = 4096 and at 0.8 TB/s as soon as Nz is not a power of two
+// (profiles/r02_fft_sizes.txt: 43 us for the 4224 cells of a z-slab with its guard cells, 18.6 us for 4096) --
+// and every local grid with guard, damping or injection cells has such a length.  Here Nz = n1 * n2:
+//   pass 1, line j2 < n2 : n1-point DFT over the rows j1*n2 + j2, times the twiddle w_N^(j2*k1) -> scratch row k1*n2 + j2
+//   pass 2, line k1 < n1 : n2-point DFT over the scratch rows k1*n2 + j2 (contiguous)         -> out row k1 + n1*k2
+// A CTA owns one line x 16 columns (256-byte row segments); its n = RA*RB points are transformed in two register
+// stages (radix RA: butterflies for 2, 4, 8, direct sums for the odd and composite radices a grid length with
+// guard cells brings: 3, 5, 6, 7, 9, 10, 11, 12, 13, 23) with one exchange through shared memory.  The scratch array
+// of a group of arrays stays in the 126 MB L2 between the passes, so DRAM sees one read and one write per array.
+// Sizes without an (n1, n2) plan fall back to cuFFT.
+#include "b2_common.cuh"
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#define FF_C 16                 // columns per CTA
+#define FF_GROUP 8              // max arrays per launch pair (B2_FFT_GROUP, default 6: the scratch of a group stays L2-resident)
+
+struct FfArgs {
+    const double2 *in[FF_GROUP];
+    double2 *out[FF_GROUP];
+    const double2 *Wn;          // w_n^k, k < n (forward sign)
+    const double2 *WN;          // w_N^k, k < N, or null (no inter-pass twiddle)
+    long long line_stride_in, elem_stride_in, line_stride_out, elem_stride_out;   // in rows
+    int Nr, inverse;
+    double scale;
+};
+
+__device__ __forceinline__ double2 ff_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 ff_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 ff_mul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// multiplication by -i (forward, s = +1) or +i (inverse, s = -1)
+__device__ __forceinline__ double2 ff_rot(double2 a, double s) { return make_double2(s * a.y, -s * a.x); }
+
+// R-point DFT in registers, natural order in and out.  w[j] = w_R^j with the direction's sign already applied.
+template <int R> struct FfDft {
+    static __device__ __forceinline__ void run(double2 (&x)[R], const double2 (&w)[R], double) {
+        double2 y[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            double2 acc = x[0];
+#pragma unroll
+            for (int j = 1; j < R; ++j) {
+                const double2 t = w[(j * q) % R];
+                acc.x += x[j].x * t.x - x[j].y * t.y;
+                acc.y += x[j].x * t.y + x[j].y * t.x;
+            }
+            y[q] = acc;
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = y[q];
+    }
+};
+template <> struct FfDft<2> {
+    static __device__ __forceinline__ void run(double2 (&x)[2], const double2 (&)[2], double) {
+        const double2 a = x[0], b = x[1];
+        x[0] = ff_add(a, b); x[1] = ff_sub(a, b);
+    }
+};
+template <> struct FfDft<4> {
+    static __device__ __forceinline__ void run(double2 (&x)[4], const double2 (&)[4], double s) {
+        const double2 t0 = ff_add(x[0], x[2]), t1 = ff_sub(x[0], x[2]);
+        const double2 t2 = ff_add(x[1], x[3]), t3 = ff_rot(ff_sub(x[1], x[3]), s);
+        x[0] = ff_add(t0, t2); x[2] = ff_sub(t0, t2);
+        x[1] = ff_add(t1, t3); x[3] = ff_sub(t1, t3);
+    }
+};
+template <> struct FfDft<8> {
+    static __device__ __forceinline__ void run(double2 (&x)[8], const double2 (&)[8], double s) {
+        const double c = 0.70710678118654752440;
+        double2 a[4], b[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a[k] = ff_add(x[k], x[k + 4]); b[k] = ff_sub(x[k], x[k + 4]); }
+        // b[k] *= w_8^k : 1, (1 - i s)/sqrt2, -i s, (-1 - i s)/sqrt2
+        b[1] = make_double2(c * (b[1].x + s * b[1].y), c * (b[1].y - s * b[1].x));
+        b[2] = ff_rot(b[2], s);
+        b[3] = make_double2(c * (-b[3].x + s * b[3].y), c * (-b[3].y - s * b[3].x));
+        const double2 dummy[4] = {};
+        FfDft<4>::run(a, dummy, s);
+        FfDft<4>::run(b, dummy, s);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { x[2 * m] = a[m]; x[2 * m + 1] = b[m]; }
+    }
+};
+
+template <int RA, int RB>
+__global__ void __launch_bounds__((RA > RB ? RA : RB) * FF_C)
+k_fft_pass(const FfArgs A) {
+    constexpr int n = RA * RB;
+    __shared__ double2 sW[n];
+    __shared__ double2 sS[n][FF_C];
+    const int tid = threadIdx.x, u = tid / FF_C, col = tid % FF_C;
+    const long long line = blockIdx.x;
+    const int c = blockIdx.y * FF_C + col;
+    const double2 *in = A.in[blockIdx.z];
+    double2 *out = A.out[blockIdx.z];
+    const double s = A.inverse ? -1. : 1.;
+    for (int k = tid; k < n; k += blockDim.x) {
+        double2 w = __ldg(A.Wn + k);
+        if (A.inverse) w.y = -w.y;
+        sW[k] = w;
+    }
+    __syncthreads();
+    const bool live = c < A.Nr;
+    // ---- stage 1: thread (eb = u, column): RA-point DFT over the elements ea*RB + eb, twiddle w_n^(eb*qa)
+    if (u < RB && live) {
+        double2 x[RA], w[RA];
+#pragma unroll
+        for (int ea = 0; ea < RA; ++ea)
+            x[ea] = __ldg(in + (size_t)(line * A.line_stride_in + (long long)(ea * RB + u) * A.elem_stride_in) * A.Nr + c);
+#pragma unroll
+        for (int j = 0; j < RA; ++j) w[j] = sW[j * RB];
+        FfDft<RA>::run(x, w, s);
+#pragma unroll
+        for (int qa = 0; qa < RA; ++qa) sS[qa * RB + u][col] = ff_mul(x[qa], sW[u * qa]);
+    }
+    __syncthreads();
+    // ---- stage 2: thread (qa = u, column): RB-point DFT over eb, output element q = qa + RA*qb
+    if (u < RA && live) {
+        double2 y[RB], w[RB];
+#pragma unroll
+        for (int eb = 0; eb < RB; ++eb) y[eb] = sS[u * RB + eb][col];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) w[j] = sW[j * RA];
+        FfDft<RB>::run(y, w, s);
+#pragma unroll
+        for (int qb = 0; qb < RB; ++qb) {
+            const int q = u + RA * qb;
+            double2 v = y[qb];
+            if (A.WN) {
+                double2 t = __ldg(A.WN + line * q);
+                if (A.inverse) t.y = -t.y;
+                v = ff_mul(v, t);
+            }
+            v.x *= A.scale; v.y *= A.scale;
+            out[(size_t)(line * A.line_stride_out + (long long)q * A.elem_stride_out) * A.Nr + c] = v;
+        }
+    }
+}
+
+// ---- host side: plans ---------------------------------------------------------------------------------
+typedef void (*ff_kernel_t)(const FfArgs);
+struct FfPair { int ra, rb; ff_kernel_t fn; };
+#define FF_PAIR(a, b) {a, b, k_fft_pass<a, b>}
+static const FfPair g_ff_pairs[] = {
+    FF_PAIR(2, 2), FF_PAIR(2, 4), FF_PAIR(4, 4), FF_PAIR(4, 8), FF_PAIR(8, 8),        // 4, 8, 16, 32, 64
+    FF_PAIR(3, 4), FF_PAIR(4, 5), FF_PAIR(4, 6), FF_PAIR(4, 7), FF_PAIR(4, 9), FF_PAIR(4, 10),   // 12 .. 40
+    FF_PAIR(3, 8), FF_PAIR(5, 8), FF_PAIR(6, 8), FF_PAIR(7, 8), FF_PAIR(8, 9), FF_PAIR(8, 10),   // 24 .. 80
+    FF_PAIR(8, 11), FF_PAIR(8, 12), FF_PAIR(8, 13), FF_PAIR(8, 16),                   // 88, 96, 104, 128
+    FF_PAIR(3, 11), FF_PAIR(5, 7), FF_PAIR(6, 6), FF_PAIR(5, 9), FF_PAIR(5, 10), FF_PAIR(6, 9),  // 33 .. 54
+    FF_PAIR(6, 10), FF_PAIR(5, 13), FF_PAIR(6, 11), FF_PAIR(3, 23), FF_PAIR(7, 10), FF_PAIR(6, 12),   // 60 .. 72
+    FF_PAIR(7, 11), FF_PAIR(6, 13), FF_PAIR(9, 9), FF_PAIR(7, 12), FF_PAIR(9, 10), FF_PAIR(7, 13),    // 77 .. 91
+    FF_PAIR(9, 11), FF_PAIR(10, 10), FF_PAIR(9, 12), FF_PAIR(10, 11), FF_PAIR(10, 12), FF_PAIR(11, 11),
+    FF_PAIR(10, 13), FF_PAIR(11, 12), FF_PAIR(12, 12),
+};
+static const int g_ff_npairs = (int)(sizeof(g_ff_pairs) / sizeof(g_ff_pairs[0]));
+
+struct FfPlan {
+    int N, p1, p2;              // indices into g_ff_pairs: n1 = size(p1) (pass 1), n2 = size(p2) (pass 2)
+    double2 *Wn1, *Wn2, *WN;    // device tables
+};
+static std::map<int, FfPlan> g_ff_plans;        // by N; p1 < 0: no plan (cuFFT)
+static std::mutex g_ff_mutex;
+
+static double ff_cost(int r) { return (r == 2 || r == 4 || r == 8) ? 1.5 * std::log2((double)r) : (double)r; }
+
+static int ff_upload_table(int n, double2 **out) {
+    std::vector<double2> h(n);
+    for (int k = 0; k < n; ++k) {
+        // exact octant symmetries are not needed at the 1e-13 tolerance; long double keeps the table at 1 ulp
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+        h[k] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+    B2_CUDA(cudaMalloc(out, sizeof(double2) * n));
+    B2_CUDA(cudaMemcpy(*out, h.data(), sizeof(double2) * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int ff_get_plan(int N, const FfPlan **plan) {
+    auto it = g_ff_plans.find(N);
+    if (it == g_ff_plans.end()) {
+        FfPlan P;
+        P.N = N; P.p1 = P.p2 = -1; P.Wn1 = P.Wn2 = P.WN = nullptr;
+        double best = 1e300;
+        for (int a = 0; a < g_ff_npairs; ++a)
+            for (int b = 0; b < g_ff_npairs; ++b) {
+                const int n1 = g_ff_pairs[a].ra * g_ff_pairs[a].rb, n2 = g_ff_pairs[b].ra * g_ff_pairs[b].rb;
+                if ((long long)n1 * n2 != N) continue;
+                const double cst = ff_cost(g_ff_pairs[a].ra) + ff_cost(g_ff_pairs[a].rb) + ff_cost(g_ff_pairs[b].ra)
+                                   + ff_cost(g_ff_pairs[b].rb);
+                if (cst < best) { best = cst; P.p1 = a; P.p2 = b; }
+            }
+        if (P.p1 >= 0) {
+            const int n1 = g_ff_pairs[P.p1].ra * g_ff_pairs[P.p1].rb, n2 = g_ff_pairs[P.p2].ra * g_ff_pairs[P.p2].rb;
+            int rc = ff_upload_table(n1, &P.Wn1); if (rc) return rc;
+            rc = ff_upload_table(n2, &P.Wn2); if (rc) return rc;
+            rc = ff_upload_table(N, &P.WN); if (rc) return rc;
+        }
+        it = g_ff_plans.emplace(N, P).first;
+    }
+    *plan = &it->second;
+    return 0;
+}
+
+// na transforms of length Nz down the columns of row-major [Nz][Nr] arrays.  inverse: 0 forward, 1 inverse scaled
+// by 1/Nz, 2 inverse unscaled.  rc 1: no plan for this length (the caller uses cuFFT).
+int b2_fft_own(b2_ctx *ctx, int na, const void *const *in, void *const *out, int Nz, int Nr, int inverse,
+               cudaStream_t s) {
+    static const bool off = []() { const char *e = getenv("B2_FFT_IMPL"); return e && !strcmp(e, "cufft"); }();
+    if (off || Nz < 16) return 1;
+    std::lock_guard<std::mutex> lk(g_ff_mutex);
+    const FfPlan *P;
+    int rc = ff_get_plan(Nz, &P);
+    if (rc) return rc;
+    if (P->p1 < 0) return 1;
+    const FfPair &k1 = g_ff_pairs[P->p1], &k2 = g_ff_pairs[P->p2];
+    const int n1 = k1.ra * k1.rb, n2 = k2.ra * k2.rb;
+    static const int group_env = []() { const char *e = getenv("B2_FFT_GROUP"); int g = e ? atoi(e) : 6;
+                                        return g < 1 ? 1 : (g > FF_GROUP ? FF_GROUP : g); }();
+    const int group = group_env;
+    void *scratch;
+    rc = b2_scratch(ctx, 2, sizeof(double2) * (size_t)group * Nz * Nr, &scratch);
+    if (rc) return rc;
+    const unsigned ncol = (unsigned)((Nr + FF_C - 1) / FF_C);
+    for (int g0 = 0; g0 < na; g0 += group) {
+        const int ng = (na - g0 < group) ? na - g0 : group;
+        FfArgs A1, A2;
+        memset(&A1, 0, sizeof(A1)); memset(&A2, 0, sizeof(A2));
+        for (int k = 0; k < ng; ++k) {
+            double2 *T = (double2 *)scratch + (size_t)k * Nz * Nr;
+            A1.in[k] = (const double2 *)in[g0 + k]; A1.out[k] = T;
+            A2.in[k] = T; A2.out[k] = (double2 *)out[g0 + k];
+        }
+        // pass 1: line j2, elements j1 (rows j1*n2 + j2) -> rows k1*n2 + j2, twiddle w_N^(j2*k1)
+        A1.Wn = P->Wn1; A1.WN = P->WN; A1.line_stride_in = 1; A1.elem_stride_in = n2;
+        A1.line_stride_out = 1; A1.elem_stride_out = n2; A1.Nr = Nr; A1.inverse = inverse ? 1 : 0; A1.scale = 1.;
+        // pass 2: line k1, elements j2 (rows k1*n2 + j2) -> rows k1 + n1*k2
+        A2.Wn = P->Wn2; A2.WN = nullptr; A2.line_stride_in = n2; A2.elem_stride_in = 1;
+        A2.line_stride_out = 1; A2.elem_stride_out = n1; A2.Nr = Nr; A2.inverse = inverse ? 1 : 0;
+        A2.scale = (inverse == 1) ? 1. / Nz : 1.;
+        const int t1 = (k1.ra > k1.rb ? k1.ra : k1.rb) * FF_C, t2 = (k2.ra > k2.rb ? k2.ra : k2.rb) * FF_C;
+        k1.fn<<<dim3((unsigned)n2, ncol, (unsigned)ng), t1, 0, s>>>(A1);
+        B2_LAUNCHED();
+        k2.fn<<<dim3((unsigned)n1, ncol, (unsigned)ng), t2, 0, s>>>(A2);
+        B2_LAUNCHED();
+    }
+    return 0;
+}
+
+// 1 if the two-pass transform has a plan for this length whose radices are all <= max_radix (grid planners pick a
+// guard width that gives such a local length), 0 otherwise (cuFFT would take it)
+extern "C" int b2_fft_has_plan(int Nz, int max_radix) {
+    std::lock_guard<std::mutex> lk(g_ff_mutex);
+    for (int a = 0; a < g_ff_npairs; ++a)
+        for (int b = 0; b < g_ff_npairs; ++b) {
+            const FfPair &p = g_ff_pairs[a], &q = g_ff_pairs[b];
+            if ((long long)p.ra * p.rb * q.ra * q.rb != Nz) continue;
+            if (p.ra <= max_radix && p.rb <= max_radix && q.ra <= max_radix && q.rb <= max_radix) return 1;
+        }
+    return 0;
+}

@@ -321,6 +321,10 @@ int b2_pm_to_rt(b2_ctx *ctx, void *p, void *m, int Nz, int Nr, void *stream) {
 int b2_fft_z(b2_ctx *ctx, const void *in, void *out, int Nz, int Nr, int inverse, void *stream) {
     cudaStream_t s = b2_stream_of(ctx, stream);
     B2Prof prof_(B2P_FFT, s);
+    const void *ins[1] = {in};
+    void *outs[1] = {out};
+    int rc = b2_fft_own(ctx, 1, ins, outs, Nz, Nr, inverse, s);      // b2_fft.cu; 1: no plan for this length
+    if (rc != 1) return rc;
     return fft_exec(ctx, 0, s, in, out, Nz, Nr, inverse);
 }
 
@@ -330,10 +334,13 @@ int b2_fft_z(b2_ctx *ctx, const void *in, void *out, int Nz, int Nr, int inverse
 int b2_fft_z_multi(b2_ctx *ctx, int na, const void *const *in, void *const *out, int Nz, int Nr, int inverse,
                    void *stream) {
     if (na <= 0) return 0;
-    int rc = fft_lanes_init(ctx);
-    if (rc) return rc;
     cudaStream_t s = b2_stream_of(ctx, stream);
     B2Prof prof_(B2P_FFT, s);
+    int rc = b2_fft_own(ctx, na, in, out, Nz, Nr, inverse, s);       // two-pass transform of b2_fft.cu
+    if (rc != 1) return rc;
+    // no (n1, n2) plan for this length: cuFFT, the independent transforms spread over concurrent lanes
+    rc = fft_lanes_init(ctx);
+    if (rc) return rc;
     const int lanes = ctx->fft_lanes < na ? ctx->fft_lanes : na;
     if (lanes > 1) {
         B2_CUDA(cudaEventRecord(ctx->fft_fork, s));

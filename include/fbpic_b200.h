@@ -195,6 +195,9 @@ int b2_fft_z(b2_ctx *ctx, const void *d_in, void *d_out, int Nz, int Nr, int inv
 /* batched: n_arrays independent [Nz,Nr] arrays */
 int b2_fft_z_multi(b2_ctx *ctx, int n_arrays, const void *const *d_in, void *const *d_out,
                    int Nz, int Nr, int inverse, void *stream);
+/* 1 if the library's own two-pass z-FFT (csrc/b2_fft.cu) covers this length with radices <= max_radix, 0 if cuFFT
+ * would take it (host-side query, no device work): lets a grid planner pick a guard width with a fast length */
+int b2_fft_has_plan(int Nz, int max_radix);
 /* out[iz,:] = rowscale[iz] * (in[iz,:] @ M)   (rowscale may be NULL); fp64 DMMA */
 int b2_dht(b2_ctx *ctx, const void *d_in, void *d_out, const double *d_M, const double *d_rowscale,
            int Nz, int Nr, void *stream);

@@ -299,3 +299,28 @@ def test_gather_push_pipe_variant_matches_golden():
                           '-p', 'no:cacheprovider', '-k', 'golden and not pipe or gather_vs_oracle'],
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize('Nz,Nr', [(4096, 256), (4224, 64), (4320, 32), (4416, 20), (2048, 50), (200, 64),
+                                   (1000, 33), (64, 48), (37, 50)])
+def test_fft_z_vs_numpy(Nz, Nr):
+    """z-FFT (two-pass transform of b2_fft.cu for the lengths it has a plan for -- powers of two and the
+    guard-cell lengths 4224 = 64*66, 4320 = 60*72, 4416 = 64*69 -- cuFFT otherwise) against numpy.fft: forward,
+    inverse scaled by 1/Nz, inverse unscaled; single call and a multi-array call with an odd number of arrays."""
+    from fbpic_b200 import _lib
+    from fbpic_b200._lib import DeviceArray, call, ptr_array
+    rng = np.random.default_rng(Nz + 3 * Nr)
+    ctx = _lib.context()
+    arrs = [rng.normal(size=(Nz, Nr)) + 1.j * rng.normal(size=(Nz, Nr)) for _ in range(5)]
+    d_in = [DeviceArray.from_numpy(a) for a in arrs]
+    d_out = [DeviceArray((Nz, Nr), np.complex128) for _ in range(5)]
+    for inverse, ref in ((0, lambda a: np.fft.fft(a, axis=0)), (1, lambda a: np.fft.ifft(a, axis=0)),
+                         (2, lambda a: np.fft.ifft(a, axis=0) * Nz)):
+        call.b2_fft_z(ctx.handle, d_in[0].ptr, d_out[0].ptr, Nz, Nr, inverse, None)
+        assert_close(d_out[0].get(), ref(arrs[0]), 1e-13, 'single, inverse=%d' % inverse)
+        call.b2_fft_z_multi(ctx.handle, 5, ptr_array(d_in), ptr_array(d_out), Nz, Nr, inverse, None)
+        for k in range(5):
+            assert_close(d_out[k].get(), ref(arrs[k]), 1e-13, 'multi %d, inverse=%d' % (k, inverse))
+    # in place
+    call.b2_fft_z(ctx.handle, d_in[1].ptr, d_in[1].ptr, Nz, Nr, 0, None)
+    assert_close(d_in[1].get(), np.fft.fft(arrs[1], axis=0), 1e-13, 'in place')

@@ -9,7 +9,8 @@ ctx = _lib.context()
 Nr = 256
 ev0, ev1 = ctypes.c_void_p(), ctypes.c_void_p()
 call.b2_event_create(ctypes.byref(ev0)); call.b2_event_create(ctypes.byref(ev1))
-for Nz in (4096, 4222, 4224, 4256, 4290, 4312, 4320, 4352, 4400, 4410, 4480):
+print('impl', os.environ.get('B2_FFT_IMPL', 'own (two-pass) where planned'))
+for Nz in (4096, 4224, 4320, 2048, 256):
     a = DeviceArray.zeros((Nz, Nr), np.complex128)
     b = DeviceArray.zeros((Nz, Nr), np.complex128)
     for _ in range(3):
@@ -20,5 +21,20 @@ for Nz in (4096, 4222, 4224, 4256, 4290, 4312, 4320, 4352, 4400, 4410, 4480):
     call.b2_event_record(ev1, ctx.stream)
     ms = ctypes.c_float(0.)
     call.b2_event_elapsed_ms(ev0, ev1, ctypes.byref(ms))
-    print('Nz=%d  n_guard=%d  %.1f us/FFT  %.0f GB/s' % (Nz, (Nz - 4096) // 2, ms.value / 20 * 1e3,
-                                                       2 * Nz * Nr * 16 / (ms.value / 20 * 1e-3) / 1e9))
+    t1 = ms.value / 20 * 1e3
+    # the batched call of the PIC step: 12 independent arrays (E, B of two modes)
+    from fbpic_b200._lib import ptr_array
+    A = [DeviceArray.zeros((Nz, Nr), np.complex128) for _ in range(12)]
+    B = [DeviceArray.zeros((Nz, Nr), np.complex128) for _ in range(12)]
+    pa, pb = ptr_array(A), ptr_array(B)
+    for _ in range(3):
+        call.b2_fft_z_multi(ctx.handle, 12, pa, pb, Nz, Nr, 2, None)
+    call.b2_event_record(ev0, ctx.stream)
+    for _ in range(10):
+        call.b2_fft_z_multi(ctx.handle, 12, pa, pb, Nz, Nr, 2, None)
+    call.b2_event_record(ev1, ctx.stream)
+    call.b2_event_elapsed_ms(ev0, ev1, ctypes.byref(ms))
+    t12 = ms.value / 120 * 1e3
+    print('Nz=%d  single call %.1f us/FFT (%.0f GB/s)   batch of 12: %.1f us/FFT (%.0f GB/s)' % (
+        Nz, t1, 2 * Nz * Nr * 16 / (t1 * 1e-6) / 1e9, t12, 2 * Nz * Nr * 16 / (t12 * 1e-6) / 1e9))
+    del A, B
