@@ -49,6 +49,7 @@ struct DtParams {
     int KT;                      // K stages = ceil(Nr / 16)
     int units_per_strip;         // ceil(Nz / 16)
     int total_units, producer_sleep;
+    unsigned stagger_ns, pad3_;
     long long *dbg;              // -DDT_DEBUG builds: per consumer warp [t_total, t_kloop, t_epilogue, tiles] (cycles)
 };
 
@@ -390,6 +391,12 @@ k_dht_tma(const __grid_constant__ DtParams P) {
 
     // =============================================================== consumer warps (2 warpgroups)
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // the two consumer warpgroups (rows 0-31 / 32-63 of every tile) run about one ring stage out of step: while one
+    // group is blocked issuing its epilogue stores (128 KB per tile through the SM's store path) the other still has
+    // K stages to multiply, so the DMMA pipe does not drain at tile boundaries.  The offset is set once here; the
+    // ring (empty barriers need both groups) bounds it, and it is self-restoring: a group alone on the pipe runs
+    // at twice the speed.
+    if (P.stagger_ns > 0 && warp >= DT_CONSUMER_WARPS / 2) __nanosleep(P.stagger_ns);
     DtWalk walk(P);
     int job, strip, m0, cnt;
     uint32_t s = 0, ph = 0;
@@ -576,6 +583,8 @@ static int dt_launch(b2_ctx *ctx, const DtHostJob *jobs, int njobs, int Nz, int 
     P.dbg = nullptr;
     static const int psleep = getenv("B2_DHT_PSLEEP") ? atoi(getenv("B2_DHT_PSLEEP")) : 1;
     P.producer_sleep = psleep;
+    static const int stagger = getenv("B2_DHT_STAGGER_NS") ? atoi(getenv("B2_DHT_STAGGER_NS")) : 0;   // measured: no gain (profiles/README)
+    P.stagger_ns = (unsigned)(stagger > 0 ? stagger : 0);
     if (debug) {
         B2_CUDA(cudaMalloc(&P.dbg, sizeof(long long) * grid * DT_CONSUMER_WARPS * 4));
         B2_CUDA(cudaMemsetAsync(P.dbg, 0, sizeof(long long) * grid * DT_CONSUMER_WARPS * 4, s));

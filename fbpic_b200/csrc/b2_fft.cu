@@ -42,9 +42,11 @@ __device__ __forceinline__ double2 ff_mul(double2 a, double2 b) {
 __device__ __forceinline__ double2 ff_rot(double2 a, double s) { return make_double2(s * a.y, -s * a.x); }
 
 // R-point DFT in registers, natural order in and out.  w[j] = w_R^j with the direction's sign already applied.
+// Output q is handed to `emit(q, value)` as soon as it is formed: the direct sums of the odd radices never hold
+// a second array of R values (radix 23 would not fit the register file otherwise).
 template <int R> struct FfDft {
-    static __device__ __forceinline__ void run(double2 (&x)[R], const double2 (&w)[R], double) {
-        double2 y[R];
+    template <class Emit>
+    static __device__ __forceinline__ void run(double2 (&x)[R], const double2 (&w)[R], double, Emit emit) {
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             double2 acc = x[0];
@@ -54,28 +56,33 @@ template <int R> struct FfDft {
                 acc.x += x[j].x * t.x - x[j].y * t.y;
                 acc.y += x[j].x * t.y + x[j].y * t.x;
             }
-            y[q] = acc;
+            emit(q, acc);
         }
-#pragma unroll
-        for (int q = 0; q < R; ++q) x[q] = y[q];
     }
 };
 template <> struct FfDft<2> {
-    static __device__ __forceinline__ void run(double2 (&x)[2], const double2 (&)[2], double) {
-        const double2 a = x[0], b = x[1];
-        x[0] = ff_add(a, b); x[1] = ff_sub(a, b);
+    template <class Emit>
+    static __device__ __forceinline__ void run(double2 (&x)[2], const double2 (&)[2], double, Emit emit) {
+        emit(0, ff_add(x[0], x[1])); emit(1, ff_sub(x[0], x[1]));
     }
 };
 template <> struct FfDft<4> {
-    static __device__ __forceinline__ void run(double2 (&x)[4], const double2 (&)[4], double s) {
+    static __device__ __forceinline__ void inplace(double2 (&x)[4], double s) {
         const double2 t0 = ff_add(x[0], x[2]), t1 = ff_sub(x[0], x[2]);
         const double2 t2 = ff_add(x[1], x[3]), t3 = ff_rot(ff_sub(x[1], x[3]), s);
         x[0] = ff_add(t0, t2); x[2] = ff_sub(t0, t2);
         x[1] = ff_add(t1, t3); x[3] = ff_sub(t1, t3);
     }
+    template <class Emit>
+    static __device__ __forceinline__ void run(double2 (&x)[4], const double2 (&)[4], double s, Emit emit) {
+        inplace(x, s);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) emit(q, x[q]);
+    }
 };
 template <> struct FfDft<8> {
-    static __device__ __forceinline__ void run(double2 (&x)[8], const double2 (&)[8], double s) {
+    template <class Emit>
+    static __device__ __forceinline__ void run(double2 (&x)[8], const double2 (&)[8], double s, Emit emit) {
         const double c = 0.70710678118654752440;
         double2 a[4], b[4];
 #pragma unroll
@@ -84,11 +91,10 @@ template <> struct FfDft<8> {
         b[1] = make_double2(c * (b[1].x + s * b[1].y), c * (b[1].y - s * b[1].x));
         b[2] = ff_rot(b[2], s);
         b[3] = make_double2(c * (-b[3].x + s * b[3].y), c * (-b[3].y - s * b[3].x));
-        const double2 dummy[4] = {};
-        FfDft<4>::run(a, dummy, s);
-        FfDft<4>::run(b, dummy, s);
+        FfDft<4>::inplace(a, s);
+        FfDft<4>::inplace(b, s);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) { x[2 * m] = a[m]; x[2 * m + 1] = b[m]; }
+        for (int m = 0; m < 4; ++m) { emit(2 * m, a[m]); emit(2 * m + 1, b[m]); }
     }
 };
 
@@ -119,9 +125,7 @@ k_fft_pass(const FfArgs A) {
             x[ea] = __ldg(in + (size_t)(line * A.line_stride_in + (long long)(ea * RB + u) * A.elem_stride_in) * A.Nr + c);
 #pragma unroll
         for (int j = 0; j < RA; ++j) w[j] = sW[j * RB];
-        FfDft<RA>::run(x, w, s);
-#pragma unroll
-        for (int qa = 0; qa < RA; ++qa) sS[qa * RB + u][col] = ff_mul(x[qa], sW[u * qa]);
+        FfDft<RA>::run(x, w, s, [&](int qa, double2 v) { sS[qa * RB + u][col] = ff_mul(v, sW[u * qa]); });
     }
     __syncthreads();
     // ---- stage 2: thread (qa = u, column): RB-point DFT over eb, output element q = qa + RA*qb
@@ -131,11 +135,8 @@ k_fft_pass(const FfArgs A) {
         for (int eb = 0; eb < RB; ++eb) y[eb] = sS[u * RB + eb][col];
 #pragma unroll
         for (int j = 0; j < RB; ++j) w[j] = sW[j * RA];
-        FfDft<RB>::run(y, w, s);
-#pragma unroll
-        for (int qb = 0; qb < RB; ++qb) {
+        FfDft<RB>::run(y, w, s, [&](int qb, double2 v) {
             const int q = u + RA * qb;
-            double2 v = y[qb];
             if (A.WN) {
                 double2 t = __ldg(A.WN + line * q);
                 if (A.inverse) t.y = -t.y;
@@ -143,7 +144,7 @@ k_fft_pass(const FfArgs A) {
             }
             v.x *= A.scale; v.y *= A.scale;
             out[(size_t)(line * A.line_stride_out + (long long)q * A.elem_stride_out) * A.Nr + c] = v;
-        }
+        });
     }
 }
 
@@ -158,6 +159,7 @@ static const FfPair g_ff_pairs[] = {
     FF_PAIR(8, 11), FF_PAIR(8, 12), FF_PAIR(8, 13), FF_PAIR(8, 16),                   // 88, 96, 104, 128
     FF_PAIR(3, 11), FF_PAIR(5, 7), FF_PAIR(6, 6), FF_PAIR(5, 9), FF_PAIR(5, 10), FF_PAIR(6, 9),  // 33 .. 54
     FF_PAIR(6, 10), FF_PAIR(5, 13), FF_PAIR(6, 11), FF_PAIR(3, 23), FF_PAIR(7, 10), FF_PAIR(6, 12),   // 60 .. 72
+    FF_PAIR(2, 17), FF_PAIR(4, 17), FF_PAIR(2, 23), FF_PAIR(4, 23),                   // 34, 68, 46, 92
     FF_PAIR(7, 11), FF_PAIR(6, 13), FF_PAIR(9, 9), FF_PAIR(7, 12), FF_PAIR(9, 10), FF_PAIR(7, 13),    // 77 .. 91
     FF_PAIR(9, 11), FF_PAIR(10, 10), FF_PAIR(9, 12), FF_PAIR(10, 11), FF_PAIR(10, 12), FF_PAIR(11, 11),
     FF_PAIR(10, 13), FF_PAIR(11, 12), FF_PAIR(12, 12),

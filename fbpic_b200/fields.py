@@ -89,9 +89,16 @@ class InterpolationGrid(object):
     def r(self):
         return self.rmin + (0.5 + np.arange(self.Nr)) * self.dr
 
-    def send_fields_to_gpu(self):
+    def send_fields_to_gpu(self, sources_recomputed=False):
+        """`sources_recomputed` (set by Simulation.step): J and rho are erased and deposited afresh before
+        anything reads them (main.py:446-454), so their host copies are not uploaded -- the device arrays start
+        as zeros."""
         for k in self._fields:
-            setattr(self, k, _lib.to_device(getattr(self, k)))
+            a = getattr(self, k)
+            if sources_recomputed and k in ('Jr', 'Jt', 'Jz', 'rho') and not isinstance(a, DeviceArray):
+                setattr(self, k, DeviceArray.zeros(a.shape, np.complex128))
+            else:
+                setattr(self, k, _lib.to_device(a))
         if self.d_invvol is None:
             self.d_invvol = DeviceArray.from_numpy(self.invvol)
             self.d_ruyten_linear_coef = DeviceArray.from_numpy(self.ruyten_linear_coef)
@@ -269,9 +276,15 @@ class SpectralGrid(object):
         self.use_cuda = True
         self.d_kz = self.d_kr = self.d_inv_k2 = self.d_filter_array_z = self.d_filter_array_r = None
 
-    def send_fields_to_gpu(self):
+    def send_fields_to_gpu(self, recomputed=False):
+        """`recomputed` (set by Simulation.step): every spectral array is rebuilt from the interpolation grid or
+        from a fresh deposition before it is read (main.py:408-415, 446-454), so nothing is uploaded."""
         for k in self._fields:
-            setattr(self, k, _lib.to_device(getattr(self, k)))
+            a = getattr(self, k)
+            if recomputed and not isinstance(a, DeviceArray):
+                setattr(self, k, DeviceArray.zeros(a.shape, np.complex128))
+            else:
+                setattr(self, k, _lib.to_device(a))
         if self.d_kz is None:
             self.d_kz = DeviceArray.from_numpy(self.kz_1d)
             self.d_kr = DeviceArray.from_numpy(self.kr_1d)
@@ -400,10 +413,12 @@ class Fields(object):
         self.exchanged_source = {'J': False, 'rho_prev': False, 'rho_new': False,
                                  'rho_next_xy': False, 'rho_next_z': False}
 
-    def send_fields_to_gpu(self):
+    def send_fields_to_gpu(self, step_entry=False):
+        """fields.py:221-232.  `step_entry`: called by Simulation.step(N >= 1), which recomputes the sources and
+        all spectral arrays before their first use -- only E and B of the interpolation grid cross the bus."""
         for m in range(self.Nm):
-            self.interp[m].send_fields_to_gpu()
-            self.spect[m].send_fields_to_gpu()
+            self.interp[m].send_fields_to_gpu(sources_recomputed=step_entry)
+            self.spect[m].send_fields_to_gpu(recomputed=step_entry)
         self.data_is_on_gpu = True
 
     def receive_fields_from_gpu(self):

@@ -85,9 +85,9 @@ class Simulation(object):
         print_simulation_setup(self, verbose_level=verbose_level)
 
     # ------------------------------------------------------------------ data residency
-    def send_data_to_gpu(self):
+    def send_data_to_gpu(self, step_entry=False):
         """fbpic/utils/cuda.py:101-118"""
-        self.fld.send_fields_to_gpu()
+        self.fld.send_fields_to_gpu(step_entry=step_entry)
         for species in self.ptcl:
             species.send_particles_to_gpu()
 
@@ -131,7 +131,9 @@ class Simulation(object):
         import time as _time
         bytes0 = dict(_lib.TRANSFERRED)
         t_start = _time.perf_counter()
-        self.send_data_to_gpu()
+        # (J, rho and every spectral array are recomputed before their first use when at least one cycle runs:
+        #  their host copies stay where they are)
+        self.send_data_to_gpu(step_entry=(N >= 1))
         t_sent = _time.perf_counter()
         self.comm.exchange_fields(fld.interp, 'E', 'replace')
         self.comm.exchange_fields(fld.interp, 'B', 'replace')
