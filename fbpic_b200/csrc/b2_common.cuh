@@ -136,6 +136,43 @@ __device__ __forceinline__ void b2_vay(double &ux, double &uy, double &uz, doubl
 }
 
 
+// stencil sum of one particle from a shared-memory tile of all 6*NM mode arrays (row pitch PITCH cells); AXIS: with
+// the two guard-cell terms of a particle within half a cell of the axis (gathering/cuda_methods.py:126-160)
+template <int NM, bool AXIS, int PITCH>
+__device__ __forceinline__ void b2_tile_sum(const double2 (*tile)[PITCH], int t_ll, int t_lu, int t_ul, int t_uu,
+                                            int t_l0, int t_u0, double S_ll, double S_lu, double S_ul, double S_uu,
+                                            double S_lg, double S_ug, bool on_axis, double cs, double sn,
+                                            double (&Fc)[2][3]) {
+    double e_re = 1., e_im = 0.;
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+        const double flip = (m & 1) ? -1. : 1.;
+        const double factor = (m == 0) ? 1. : 2.;
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int a = 6 * m + 3 * f + k;
+                const double2 v_ll = tile[a][t_ll], v_lu = tile[a][t_lu], v_ul = tile[a][t_ul], v_uu = tile[a][t_uu];
+                double re = 0., im = 0.;
+                re += S_ll * v_ll.x; im += S_ll * v_ll.y;
+                re += S_lu * v_lu.x; im += S_lu * v_lu.y;
+                re += S_ul * v_ul.x; im += S_ul * v_ul.y;
+                re += S_uu * v_uu.x; im += S_uu * v_uu.y;
+                if (AXIS && on_axis) {
+                    const double sgn = (k == 2) ? flip : -flip;
+                    const double2 v_l0 = tile[a][t_l0], v_u0 = tile[a][t_u0];
+                    re += sgn * S_lg * v_l0.x; im += sgn * S_lg * v_l0.y;
+                    re += sgn * S_ug * v_u0.x; im += sgn * S_ug * v_u0.y;
+                }
+                Fc[f][k] += factor * (re * e_re - im * e_im);
+            }
+        }
+        const double nr = e_re * cs + e_im * sn, ni = e_im * cs - e_re * sn;
+        e_re = nr; e_im = ni;
+    }
+}
+
 // b2_gather_pipe.cu: persistent gather + push kernel with TMA-staged field tiles (linear shapes).  Processes the
 // first *done particles (a multiple of 128, possibly 0 when the path is unavailable); rc != 0 is an error.
 int b2_gather_push_pipe(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, double *ux, double *uy, double *uz,

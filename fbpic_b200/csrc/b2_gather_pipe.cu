@@ -192,57 +192,71 @@ k_gather_push_pipe(const __grid_constant__ GqParams<NM> P) {
         const bool use_tile = tile_ok && active && iz_l0 >= z0 && iz_l0 + 1 < z0 + GQ_ROWS && ir_l >= r0
                               && ir_u < r0 + GQ_COLS;
         double Fc[2][3] = {{0., 0., 0.}, {0., 0., 0.}};
+        // tile-only copy of the stencil sum when every gathering lane of the warp reads the tile (no dead
+        // predicated LDG and address arithmetic), mixed copy otherwise
+        const bool warp_on_tile = __all_sync(0xffffffffu, use_tile || !active);
+        // (guard-cell terms near the axis: skipped as a whole by the warps that hold no such particle)
+        const bool warp_near_axis = __any_sync(0xffffffffu, active && ir_l == 0 && ir_u == 0);
         if (active) {
-            int iz_l = iz_l0, iz_u = iz_l0 + 1;
-            if (iz_l < 0) iz_l += P.Nz;
-            if (iz_u < 0) iz_u += P.Nz;
-            if (iz_l > P.Nz - 1) iz_l -= P.Nz;
-            if (iz_u > P.Nz - 1) iz_u -= P.Nz;
             const double S_ll = Sz_l * Sr_l, S_lu = Sz_l * Sr_u, S_ul = Sz_u * Sr_l, S_uu = Sz_u * Sr_u;
             const double S_lg = Sz_l * Sr_g, S_ug = Sz_u * Sr_g;
             const bool on_axis = (ir_l == 0 && ir_u == 0);
             const int t_ll = (iz_l0 - z0) * GQ_COLS + (ir_l - r0), t_lu = (iz_l0 - z0) * GQ_COLS + (ir_u - r0);
             const int t_ul = t_ll + GQ_COLS, t_uu = t_lu + GQ_COLS;
             const int t_l0 = (iz_l0 - z0) * GQ_COLS - r0, t_u0 = t_l0 + GQ_COLS;   // column 0 (on_axis: r0 == 0)
-            const size_t o_ll = (size_t)iz_l * P.Nr + ir_l, o_lu = (size_t)iz_l * P.Nr + ir_u;
-            const size_t o_ul = (size_t)iz_u * P.Nr + ir_l, o_uu = (size_t)iz_u * P.Nr + ir_u;
-            const size_t o_l0 = (size_t)iz_l * P.Nr, o_u0 = (size_t)iz_u * P.Nr;
             double e_re = 1., e_im = 0.;
+            if (warp_on_tile) {
+                if (warp_near_axis)
+                    b2_tile_sum<NM, true, GQ_ROWS * GQ_COLS>(S.tile[ts], t_ll, t_lu, t_ul, t_uu, t_l0, t_u0, S_ll, S_lu,
+                                                              S_ul, S_uu, S_lg, S_ug, on_axis, cs, sn, Fc);
+                else
+                    b2_tile_sum<NM, false, GQ_ROWS * GQ_COLS>(S.tile[ts], t_ll, t_lu, t_ul, t_uu, t_l0, t_u0, S_ll, S_lu,
+                                                               S_ul, S_uu, S_lg, S_ug, false, cs, sn, Fc);
+            } else {
+                int iz_l = iz_l0, iz_u = iz_l0 + 1;
+                if (iz_l < 0) iz_l += P.Nz;
+                if (iz_u < 0) iz_u += P.Nz;
+                if (iz_l > P.Nz - 1) iz_l -= P.Nz;
+                if (iz_u > P.Nz - 1) iz_u -= P.Nz;
+                const size_t o_ll = (size_t)iz_l * P.Nr + ir_l, o_lu = (size_t)iz_l * P.Nr + ir_u;
+                const size_t o_ul = (size_t)iz_u * P.Nr + ir_l, o_uu = (size_t)iz_u * P.Nr + ir_u;
+                const size_t o_l0 = (size_t)iz_l * P.Nr, o_u0 = (size_t)iz_u * P.Nr;
 #pragma unroll
-            for (int m = 0; m < NM; ++m) {
-                const double flip = (m & 1) ? -1. : 1.;
-                const double factor = (m == 0) ? 1. : 2.;
+                for (int m = 0; m < NM; ++m) {
+                    const double flip = (m & 1) ? -1. : 1.;
+                    const double factor = (m == 0) ? 1. : 2.;
 #pragma unroll
-                for (int f = 0; f < 2; ++f) {
+                    for (int f = 0; f < 2; ++f) {
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const int a = 6 * m + 3 * f + q;
-                        double2 v_ll, v_lu, v_ul, v_uu;
-                        if (use_tile) {
-                            const double2 *T = S.tile[ts][a];
-                            v_ll = T[t_ll]; v_lu = T[t_lu]; v_ul = T[t_ul]; v_uu = T[t_uu];
-                        } else {
-                            const double2 *g = P.g[a];
-                            v_ll = __ldg(g + o_ll); v_lu = __ldg(g + o_lu); v_ul = __ldg(g + o_ul); v_uu = __ldg(g + o_uu);
+                        for (int q = 0; q < 3; ++q) {
+                            const int a = 6 * m + 3 * f + q;
+                            double2 v_ll, v_lu, v_ul, v_uu;
+                            if (use_tile) {
+                                const double2 *T = S.tile[ts][a];
+                                v_ll = T[t_ll]; v_lu = T[t_lu]; v_ul = T[t_ul]; v_uu = T[t_uu];
+                            } else {
+                                const double2 *g = P.g[a];
+                                v_ll = __ldg(g + o_ll); v_lu = __ldg(g + o_lu); v_ul = __ldg(g + o_ul); v_uu = __ldg(g + o_uu);
+                            }
+                            double re = 0., im = 0.;
+                            re += S_ll * v_ll.x; im += S_ll * v_ll.y;
+                            re += S_lu * v_lu.x; im += S_lu * v_lu.y;
+                            re += S_ul * v_ul.x; im += S_ul * v_ul.y;
+                            re += S_uu * v_uu.x; im += S_uu * v_uu.y;
+                            if (on_axis) {
+                                const double sgn = (q == 2) ? flip : -flip;
+                                double2 v_l0, v_u0;
+                                if (use_tile) { v_l0 = S.tile[ts][a][t_l0]; v_u0 = S.tile[ts][a][t_u0]; }
+                                else { v_l0 = __ldg(P.g[a] + o_l0); v_u0 = __ldg(P.g[a] + o_u0); }
+                                re += sgn * S_lg * v_l0.x; im += sgn * S_lg * v_l0.y;
+                                re += sgn * S_ug * v_u0.x; im += sgn * S_ug * v_u0.y;
+                            }
+                            Fc[f][q] += factor * (re * e_re - im * e_im);
                         }
-                        double re = 0., im = 0.;
-                        re += S_ll * v_ll.x; im += S_ll * v_ll.y;
-                        re += S_lu * v_lu.x; im += S_lu * v_lu.y;
-                        re += S_ul * v_ul.x; im += S_ul * v_ul.y;
-                        re += S_uu * v_uu.x; im += S_uu * v_uu.y;
-                        if (on_axis) {
-                            const double sgn = (q == 2) ? flip : -flip;
-                            double2 v_l0, v_u0;
-                            if (use_tile) { v_l0 = S.tile[ts][a][t_l0]; v_u0 = S.tile[ts][a][t_u0]; }
-                            else { v_l0 = __ldg(P.g[a] + o_l0); v_u0 = __ldg(P.g[a] + o_u0); }
-                            re += sgn * S_lg * v_l0.x; im += sgn * S_lg * v_l0.y;
-                            re += sgn * S_ug * v_u0.x; im += sgn * S_ug * v_u0.y;
-                        }
-                        Fc[f][q] += factor * (re * e_re - im * e_im);
                     }
+                    const double nr = e_re * cs + e_im * sn, ni = e_im * cs - e_re * sn;
+                    e_re = nr; e_im = ni;
                 }
-                const double nr = e_re * cs + e_im * sn, ni = e_im * cs - e_re * sn;
-                e_re = nr; e_im = ni;
             }
         }
         double F[6];

@@ -336,57 +336,79 @@ k_gather_push_tiled(int64_t n, double *__restrict__ x, double *__restrict__ y, d
     if (!in_range) return;
 
     double Fc[2][3] = {{0., 0., 0.}, {0., 0., 0.}};
+    // Two copies of the stencil sum: when every gathering lane of the warp reads the tile (the usual case) the
+    // warp runs the copy that has no global loads and none of their address arithmetic; a predicated
+    // `tile ? LDS : LDG` select would issue both for every warp (48 dead LDG + ~100 address instructions per
+    // warp, a fifth of the kernel -- profiles/r02_gather_pipe_vs_tiled.md).
+    const unsigned live = __activemask();
+    const bool warp_on_tile = __all_sync(live, use_tile || !active);
+    // (the two guard-cell terms of a particle within half a cell of the axis: skipped as a whole by the warps --
+    //  all but one in Nr -- that hold no such particle, instead of 24 predicated-off loads and 48 fp64 operations)
+    const bool warp_near_axis = __any_sync(live, active && ir_l == 0 && ir_u == 0);
     if (active) {
-        int iz_l = iz_l0, iz_u = iz_l0 + 1;
-        if (iz_l < 0) iz_l += Nz;
-        if (iz_u < 0) iz_u += Nz;
-        if (iz_l > Nz - 1) iz_l -= Nz;
-        if (iz_u > Nz - 1) iz_u -= Nz;
         const double S_ll = Sz_l * Sr_l, S_lu = Sz_l * Sr_u, S_ul = Sz_u * Sr_l, S_uu = Sz_u * Sr_u;
         const double S_lg = Sz_l * Sr_g, S_ug = Sz_u * Sr_g;
         const bool on_axis = (ir_l == 0 && ir_u == 0);
-        // tile-relative cell offsets (used when use_tile) and global offsets (fallback)
-        const int t_ll = (iz_l0 - z0) * ncol + (ir_l - r0), t_lu = (iz_l0 - z0) * ncol + (ir_u - r0);
-        const int t_ul = t_ll + ncol, t_uu = t_lu + ncol;
-        const int t_l0 = (iz_l0 - z0) * ncol - r0, t_u0 = t_l0 + ncol;    // column 0 (only if on_axis: r0 == 0)
-        const size_t o_ll = (size_t)iz_l * Nr + ir_l, o_lu = (size_t)iz_l * Nr + ir_u;
-        const size_t o_ul = (size_t)iz_u * Nr + ir_l, o_uu = (size_t)iz_u * Nr + ir_u;
-        const size_t o_l0 = (size_t)iz_l * Nr, o_u0 = (size_t)iz_u * Nr;
-        double e_re = 1., e_im = 0.;
+        if (warp_on_tile) {
+            const int t_ll = (iz_l0 - z0) * ncol + (ir_l - r0), t_lu = (iz_l0 - z0) * ncol + (ir_u - r0);
+            const int t_ul = t_ll + ncol, t_uu = t_lu + ncol;
+            const int t_l0 = (iz_l0 - z0) * ncol - r0, t_u0 = t_l0 + ncol;    // column 0 (only if on_axis: r0 == 0)
+            // (warp-uniform choice: only the warps that hold a particle next to the axis carry the guard terms)
+            if (warp_near_axis)
+                b2_tile_sum<NM, true, GP_TILE_CELLS>(tile, t_ll, t_lu, t_ul, t_uu, t_l0, t_u0, S_ll, S_lu, S_ul, S_uu,
+                                                      S_lg, S_ug, on_axis, c.cs, c.sn, Fc);
+            else
+                b2_tile_sum<NM, false, GP_TILE_CELLS>(tile, t_ll, t_lu, t_ul, t_uu, t_l0, t_u0, S_ll, S_lu, S_ul, S_uu,
+                                                       S_lg, S_ug, false, c.cs, c.sn, Fc);
+        } else {
+            int iz_l = iz_l0, iz_u = iz_l0 + 1;
+            if (iz_l < 0) iz_l += Nz;
+            if (iz_u < 0) iz_u += Nz;
+            if (iz_l > Nz - 1) iz_l -= Nz;
+            if (iz_u > Nz - 1) iz_u -= Nz;
+            // tile-relative cell offsets (used when use_tile) and global offsets (fallback)
+            const int t_ll = (iz_l0 - z0) * ncol + (ir_l - r0), t_lu = (iz_l0 - z0) * ncol + (ir_u - r0);
+            const int t_ul = t_ll + ncol, t_uu = t_lu + ncol;
+            const int t_l0 = (iz_l0 - z0) * ncol - r0, t_u0 = t_l0 + ncol;
+            const size_t o_ll = (size_t)iz_l * Nr + ir_l, o_lu = (size_t)iz_l * Nr + ir_u;
+            const size_t o_ul = (size_t)iz_u * Nr + ir_l, o_uu = (size_t)iz_u * Nr + ir_u;
+            const size_t o_l0 = (size_t)iz_l * Nr, o_u0 = (size_t)iz_u * Nr;
+            double e_re = 1., e_im = 0.;
 #pragma unroll
-        for (int m = 0; m < NM; ++m) {
-            const double flip = (m & 1) ? -1. : 1.;
-            const double factor = (m == 0) ? 1. : 2.;
+            for (int m = 0; m < NM; ++m) {
+                const double flip = (m & 1) ? -1. : 1.;
+                const double factor = (m == 0) ? 1. : 2.;
 #pragma unroll
-            for (int f = 0; f < 2; ++f) {
+                for (int f = 0; f < 2; ++f) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int a = 6 * m + 3 * f + k;
-                    double2 v_ll, v_lu, v_ul, v_uu;
-                    if (use_tile) {
-                        v_ll = tile[a][t_ll]; v_lu = tile[a][t_lu]; v_ul = tile[a][t_ul]; v_uu = tile[a][t_uu];
-                    } else {
-                        const double2 *g = G.g[a];
-                        v_ll = __ldg(g + o_ll); v_lu = __ldg(g + o_lu); v_ul = __ldg(g + o_ul); v_uu = __ldg(g + o_uu);
+                    for (int k = 0; k < 3; ++k) {
+                        const int a = 6 * m + 3 * f + k;
+                        double2 v_ll, v_lu, v_ul, v_uu;
+                        if (use_tile) {
+                            v_ll = tile[a][t_ll]; v_lu = tile[a][t_lu]; v_ul = tile[a][t_ul]; v_uu = tile[a][t_uu];
+                        } else {
+                            const double2 *g = G.g[a];
+                            v_ll = __ldg(g + o_ll); v_lu = __ldg(g + o_lu); v_ul = __ldg(g + o_ul); v_uu = __ldg(g + o_uu);
+                        }
+                        double re = 0., im = 0.;
+                        re += S_ll * v_ll.x; im += S_ll * v_ll.y;
+                        re += S_lu * v_lu.x; im += S_lu * v_lu.y;
+                        re += S_ul * v_ul.x; im += S_ul * v_ul.y;
+                        re += S_uu * v_uu.x; im += S_uu * v_uu.y;
+                        if (on_axis) {
+                            const double sgn = (k == 2) ? flip : -flip;
+                            double2 v_l0, v_u0;
+                            if (use_tile) { v_l0 = tile[a][t_l0]; v_u0 = tile[a][t_u0]; }
+                            else { v_l0 = __ldg(G.g[a] + o_l0); v_u0 = __ldg(G.g[a] + o_u0); }
+                            re += sgn * S_lg * v_l0.x; im += sgn * S_lg * v_l0.y;
+                            re += sgn * S_ug * v_u0.x; im += sgn * S_ug * v_u0.y;
+                        }
+                        Fc[f][k] += factor * (re * e_re - im * e_im);
                     }
-                    double re = 0., im = 0.;
-                    re += S_ll * v_ll.x; im += S_ll * v_ll.y;
-                    re += S_lu * v_lu.x; im += S_lu * v_lu.y;
-                    re += S_ul * v_ul.x; im += S_ul * v_ul.y;
-                    re += S_uu * v_uu.x; im += S_uu * v_uu.y;
-                    if (on_axis) {
-                        const double sgn = (k == 2) ? flip : -flip;
-                        double2 v_l0, v_u0;
-                        if (use_tile) { v_l0 = tile[a][t_l0]; v_u0 = tile[a][t_u0]; }
-                        else { v_l0 = __ldg(G.g[a] + o_l0); v_u0 = __ldg(G.g[a] + o_u0); }
-                        re += sgn * S_lg * v_l0.x; im += sgn * S_lg * v_l0.y;
-                        re += sgn * S_ug * v_u0.x; im += sgn * S_ug * v_u0.y;
-                    }
-                    Fc[f][k] += factor * (re * e_re - im * e_im);
                 }
+                const double nr = e_re * c.cs + e_im * c.sn, ni = e_im * c.cs - e_re * c.sn;
+                e_re = nr; e_im = ni;
             }
-            const double nr = e_re * c.cs + e_im * c.sn, ni = e_im * c.cs - e_re * c.sn;
-            e_re = nr; e_im = ni;
         }
     }
     double F[6];
