@@ -374,10 +374,17 @@ def main():
         return
 
     # ------------------------------------------------------------------ B200 arm
-    # NCCL's own report of the communicator (rank count, transport) goes to stderr: stdout stays the one JSON line
-    os.environ.setdefault('NCCL_DEBUG', os.environ.get('B2_NCCL_DEBUG', 'INFO'))
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-    os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
+    # NCCL's own report of the communicator (rank count, transport; NCCL_DEBUG=INFO prints to stdout) must reach
+    # stderr while stdout stays the one JSON line: file descriptor 1 is pointed at stderr for the whole run and the
+    # JSON line is written to the saved descriptor at the end.
+    json_fd = 1
+    if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() not in ('INFO', 'TRACE'):
+            os.environ['NCCL_DEBUG'] = os.environ.get('B2_NCCL_DEBUG', 'INFO')
+        os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
     from fbpic_b200 import _lib
     from fbpic_b200._lib import call
     dist = None
@@ -580,7 +587,8 @@ def main():
     }
     if mgpu_parity is not None:
         out['mgpu_parity'] = mgpu_parity
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(out) + '\n').encode())
 
 
 if __name__ == '__main__':

@@ -105,8 +105,10 @@ k_fft_pass(const FfArgs A) {
     __shared__ double2 sW[n];
     __shared__ double2 sS[n][FF_C];
     const int tid = threadIdx.x, u = tid / FF_C, col = tid % FF_C;
-    const long long line = blockIdx.x;
-    const int c = blockIdx.y * FF_C + col;
+    // column tile fastest: the CTAs in flight together cover whole 4 KB rows (adjacent 256-byte segments of the
+    // same DRAM pages) instead of the same segment of 64 rows that lie n2 rows apart
+    const long long line = blockIdx.y;
+    const int c = blockIdx.x * FF_C + col;
     const double2 *in = A.in[blockIdx.z];
     double2 *out = A.out[blockIdx.z];
     const double s = A.inverse ? -1. : 1.;
@@ -254,9 +256,9 @@ int b2_fft_own(b2_ctx *ctx, int na, const void *const *in, void *const *out, int
         A2.line_stride_out = 1; A2.elem_stride_out = n1; A2.Nr = Nr; A2.inverse = inverse ? 1 : 0;
         A2.scale = (inverse == 1) ? 1. / Nz : 1.;
         const int t1 = (k1.ra > k1.rb ? k1.ra : k1.rb) * FF_C, t2 = (k2.ra > k2.rb ? k2.ra : k2.rb) * FF_C;
-        k1.fn<<<dim3((unsigned)n2, ncol, (unsigned)ng), t1, 0, s>>>(A1);
+        k1.fn<<<dim3(ncol, (unsigned)n2, (unsigned)ng), t1, 0, s>>>(A1);
         B2_LAUNCHED();
-        k2.fn<<<dim3((unsigned)n1, ncol, (unsigned)ng), t2, 0, s>>>(A2);
+        k2.fn<<<dim3(ncol, (unsigned)n1, (unsigned)ng), t2, 0, s>>>(A2);
         B2_LAUNCHED();
     }
     return 0;
