@@ -512,7 +512,7 @@ def main():
         'fft': (22 if exchange_path else 10) * Nm * 2 * cells,
         # fused correct + push (+ push_rho): reads 11, writes 8 arrays, coefficients 2.5 arrays-worth per mode;
         # as separate correct / push / push_rho launches: 27 arrays
-        'spectral': Nm * ((27 if exchange_path else 19) * cells + 5 * cells // 2),
+        'spectral': Nm * ((27 if n_gpus > 1 else 19) * cells + 5 * cells // 2),
     }
     top = max(prof.items(), key=lambda kv: kv[1]['ms'])[0] if prof else None
     roofline = None

@@ -47,7 +47,7 @@ struct DtParams {
     DtJob job[DT_MAX_JOBS];
     int njobs, Nz, Nr, Np;       // Np: padded matrix width (multiple of 128)
     int KT;                      // K stages = ceil(Nr / 16)
-    int units_per_strip;         // ceil(Nz / 16)
+    int blocks64;                // ceil(Nz / 64): 64-row blocks per column strip
     int total_units, producer_sleep;
     unsigned stagger_ns, pad3_;
     long long *dbg;              // -DDT_DEBUG builds: per consumer warp [t_total, t_kloop, t_epilogue, tiles] (cycles)
@@ -123,25 +123,30 @@ struct DtWalk {
         // each) at four different phases of the tile period instead of all at once
         first = (u_end - u >= 8) ? 1 + (int)(b & 3) : DT_BM / 16;
     }
-    // next tile: job, column strip, first row, number of 16-row units (1..4); false when done
+    // next tile: job, column strip, first row, number of 16-row units (1..4); false when done.
+    // Unit order inside a job: (64-row block, column strip, 16-row unit of the block) -- the strips of one row
+    // block follow each other in the walk, so the A rows a CTA has just streamed for strip s are still in L2
+    // (mostly in flight on the same SM) when strip s+1 asks for them: DRAM reads every field array once
+    // (strip-major order re-read it once per strip: 2.1x the algorithmic bytes in the r02 capture).
     __device__ __forceinline__ bool next(const DtParams &P, int &job, int &strip, int &m0, int &cnt) {
-        if (u >= u_end) return false;
-        int j = 0;
-        while (j + 1 < P.njobs && P.job[j + 1].unit_begin <= u) ++j;
-        const int v = u - P.job[j].unit_begin;
-        const int s = v / P.units_per_strip;
-        const int mu = v - s * P.units_per_strip;
-        job = j;
-        strip = s;
-        int c = P.units_per_strip - mu;
-        if (c > DT_BM / 16) c = DT_BM / 16;
-        if (c > first) c = first;
-        first = DT_BM / 16;
-        if (c > u_end - u) c = u_end - u;
-        cnt = c;
-        m0 = mu * 16;
-        u += c;
-        return true;
+        while (u < u_end) {
+            int j = 0;
+            while (j + 1 < P.njobs && P.job[j + 1].unit_begin <= u) ++j;
+            const int v = u - P.job[j].unit_begin;
+            const int sub = v & 3, q = v >> 2;
+            const int ns = P.job[j].n_strips;
+            const int mb = q / ns;
+            int c = DT_BM / 16 - sub;
+            if (c > first) c = first;
+            first = DT_BM / 16;
+            if (c > u_end - u) c = u_end - u;
+            u += c;
+            const int row0 = mb * DT_BM + sub * 16;
+            if (row0 >= P.Nz) continue;               // padding units of the last row block
+            job = j; strip = q - mb * ns; m0 = row0; cnt = c;
+            return true;
+        }
+        return false;
     }
 };
 
@@ -551,7 +556,7 @@ static int dt_launch(b2_ctx *ctx, const DtHostJob *jobs, int njobs, int Nz, int 
     P.njobs = njobs; P.Nz = Nz; P.Nr = Nr;
     P.Np = dt_round_up(Nr, 128);
     P.KT = dt_round_up(Nr, DT_BK) / DT_BK;
-    P.units_per_strip = (Nz + 15) / 16;
+    P.blocks64 = (Nz + DT_BM - 1) / DT_BM;
     long long units = 0;
     double products = 0.;
     for (int k = 0; k < njobs; ++k) {
@@ -568,7 +573,7 @@ static int dt_launch(b2_ctx *ctx, const DtHostJob *jobs, int njobs, int Nz, int 
         const int bn = 128 / nprod;
         P.job[k].n_strips = (Nr + bn - 1) / bn;
         P.job[k].unit_begin = (int)units;
-        units += (long long)P.job[k].n_strips * P.units_per_strip;
+        units += (long long)P.job[k].n_strips * P.blocks64 * (DT_BM / 16);
         if (units > 0x7fffffffLL) return b2_fail(-3, "b2_dht: grid too large", __FILE__, __LINE__);
         products += nprod;
     }
