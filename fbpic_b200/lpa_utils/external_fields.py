@@ -88,8 +88,17 @@ class _Translator(object):
                 return self.number(float(self.outer[n.id]))        # captured numeric constant
             self.fail(n, 'name `%s`' % n.id)
         if isinstance(n, ast.Attribute):
-            if isinstance(n.value, ast.Name) and n.attr in _CONSTS:
-                return self.number(_CONSTS[n.attr])
+            # `mod.name`: evaluated on the object the function really captured (scipy.constants.e is the elementary
+            # charge, math.e is Euler's number); the bare spelling math.pi / np.pi of an un-captured module keeps working
+            if isinstance(n.value, ast.Name):
+                base = self.outer.get(n.value.id)
+                if base is not None:
+                    val = getattr(base, n.attr, None)
+                    if isinstance(val, (int, float, np.floating, np.integer)) and not isinstance(val, bool):
+                        return self.number(float(val))
+                    self.fail(n, 'attribute `%s.%s`' % (n.value.id, n.attr))
+                if n.value.id in ('math', 'np', 'numpy') and n.attr in _CONSTS:
+                    return self.number(_CONSTS[n.attr])
             self.fail(n, 'attribute `%s`' % n.attr)
         if isinstance(n, ast.UnaryOp):
             if isinstance(n.op, ast.USub):

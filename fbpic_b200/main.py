@@ -8,8 +8,9 @@ current correction + PSATD push, z guard-cell exchange and particle migration.
 Widened per SURVEY 8f: moving window with continuous injection (rank 1), laser antennas
 (rank 2), radial PML (`boundaries['r']='open'`) and the cross-deposition current correction
 (rank 4); plus mirrors, external fields and the boosted-frame conversion of the set-up
-(`gamma_boost`), and the `sim.diags` / `sim.checkpoints` hooks (fbpic_b200/diags.py).  Out of scope
-and therefore rejected loudly: ionization, Compton scattering.
+(`gamma_boost`), the `sim.diags` / `sim.checkpoints` hooks (fbpic_b200/diags.py), ADK ionization and
+Compton scattering (fbpic_b200/ionization.py, compton.py).  `step(show_progress=...)` defaults to False here
+(reference: True; INTEGRATION.md).
 """
 import numpy as np
 from scipy.constants import m_e, m_p, e, c

@@ -6,7 +6,8 @@ rearrange_particle_arrays, send/receive_particles_*): same method names,
 argument meaning and attribute names (`x..w`, `Ex..Bz`, `cell_idx`,
 `sorted_idx`, `prefix_sum`, `sorted`, `Ntot`, `q`, `m`).
 
-Out of scope here: ionization, Compton scattering, tracking.
+Beyond SURVEY section 8 (2g/2f), hooked in here: ionization (`make_ionizable`), Compton scattering
+(`activate_compton`), tracking (`track`)  -- fbpic_b200/ionization.py, compton.py.
 """
 import inspect
 import warnings
@@ -677,7 +678,7 @@ class Particles(object):
             self.Ntot = n_new
             self._alloc_sort_arrays()
         for k in FIELD_ATTRS:
-            call.b2_memset(getattr(self, k).ptr + 8 * old_n, 0, 8 * add, None)
+            call.b2_memset(getattr(self, k).ptr + 8 * old_n, 0, 8 * add, _lib.context().stream)
         for t in self.uint_carriers():
             values = t.generate_new_ids(add) if new_uint is None else new_uint(t)
             t.id.view((add,), byte_offset=8 * old_n).set(values)

@@ -101,3 +101,17 @@ def test_boosted_frame_amplitudes():
     assert (f1, f2) == ('By', 'Ex') and abs(a1 - g * 2.) < 1e-14 and abs(a2 + g * b * c * 2.) < 1e-6
     e = ExternalField(f_undulator, 'Ez', 2., 1.e-2, gamma_boost=g)
     assert e.fieldtypes_and_amplitudes == (('Ez', 2.),)
+
+
+def test_module_attribute_constants_are_resolved_on_the_captured_object():
+    """`const.e` of `import scipy.constants as const` is the elementary charge, `math.e` Euler's number: an attribute
+    is evaluated on the module the function captured, never matched by its bare name."""
+    import math
+    import scipy.constants as const
+    from fbpic_b200.lpa_utils.external_fields import python_to_cuda
+
+    def field(F, x, y, z, t, amplitude, length_scale):
+        return F + amplitude * const.e * math.cos(2 * math.pi * z / length_scale) + math.e
+
+    src = python_to_cuda(field)
+    assert '1.602176634e-19' in src and '2.718281828459045' in src
