@@ -27,6 +27,7 @@ struct b2_ctx {
     const int32_t *last_idx32;
     const int32_t *last_keys_sorted;
     int64_t last_sort_n;
+    const void *last_sort_prefix;   // prefix_sum array of that sort: identifies the species it belongs to
     int64_t part_n;            // size of the last b2_exchange_classify (scratch slot 1)
     void *nccl_comm;
     int nccl_rank, nccl_size;

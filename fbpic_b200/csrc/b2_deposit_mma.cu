@@ -374,9 +374,9 @@ int b2_deposit_permute(b2_ctx *ctx, int what, int64_t n, const double *const *sr
                        double q, double invdz, double zmin, int Nz, double invdr, double rmin, int Nr, int Nm,
                        void *const *grids, const int32_t *prefix, const double *r0, const double *rh, int cubic,
                        void *stream) {
-    (void)prefix;
     if (n <= 0) return 0;     // empty species: nothing to permute or deposit
-    if (!ctx->last_idx32 || ctx->last_sort_n != n)
+    // the cached permutation must be the one of THIS species: same length and same prefix-sum array as the last sort
+    if (!ctx->last_idx32 || ctx->last_sort_n != n || (prefix && ctx->last_sort_prefix != (const void *)prefix))
         return b2_fail(-4, "b2_deposit_permute: no matching b2_sort_cells result in this context", __FILE__, __LINE__);
     return b2_deposit_mma(ctx, what != 0, n, src8, dst8, ctx->last_idx32, nullptr, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm,
                           grids, r0, rh, cubic, stream);

@@ -542,6 +542,7 @@ int b2_sort_cells(b2_ctx *ctx, int64_t n, int32_t *cell_idx, int64_t *sorted_idx
         // prefix sum stays all-zero): record it so that a following permute / deposit_permute matches
         B2_CUDA(cudaMemsetAsync(prefix_sum, 0, sizeof(int32_t) * (size_t)ncells, s));
         ctx->last_sort_n = 0;
+        ctx->last_sort_prefix = prefix_sum;
         return 0;
     }
     // 32-bit particle indices (CUB num_items, the idx32 permutation, the int32 prefix sums): one species on one
@@ -568,6 +569,7 @@ int b2_sort_cells(b2_ctx *ctx, int64_t n, int32_t *cell_idx, int64_t *sorted_idx
                                             (const int32_t *)idx_in, idx_sorted, (int)n, 0, end_bit, s));
     g_b2_launches.fetch_add(4);
     ctx->last_idx32 = idx_sorted; ctx->last_keys_sorted = keys_sorted; ctx->last_sort_n = n;
+    ctx->last_sort_prefix = prefix_sum;
     if (sorted_idx) {     // materialise the API-visible int64 permutation and the sorted keys
         k_finish_sort<<<grid1d(n, 256), 256, 0, s>>>(n, keys_sorted, idx_sorted, cell_idx, sorted_idx);
         B2_LAUNCHED();

@@ -76,7 +76,7 @@ int b2_ctx_create(int device, b2_ctx **out) {
     ctx->device = device;
     ctx->stream = stream;
     for (int i = 0; i < 4; ++i) { ctx->scratch[i] = nullptr; ctx->scratch_bytes[i] = 0; }
-    ctx->last_idx32 = nullptr; ctx->last_keys_sorted = nullptr; ctx->last_sort_n = -1; ctx->part_n = -1;
+    ctx->last_idx32 = nullptr; ctx->last_keys_sorted = nullptr; ctx->last_sort_n = -1; ctx->part_n = -1; ctx->last_sort_prefix = nullptr;
     ctx->nccl_comm = nullptr;
     ctx->nccl_rank = 0;
     ctx->nccl_size = 1;

@@ -178,6 +178,7 @@ class FakeLib(object):
         perm, prefix = orc.sort_contract(keys, Nz, Nr) if n else (np.zeros(0, np.int64),
                                                                   np.zeros(Nz * (Nr + 1), np.int32))
         self._perm = perm.copy()
+        self._perm_prefix = _addr(prefix_sum)          # as the library: the cached permutation belongs to this array
         if _addr(sorted_idx):
             _arr(sorted_idx, n, np.int64)[:] = perm
             keys[:] = keys[perm]
@@ -293,7 +294,10 @@ class FakeLib(object):
 
     def b2_deposit_permute(self, ctx, what, n, src8, dst8, q, invdz, zmin, Nz, invdr, rmin, Nr, Nm, grids,
                            prefix, r0, rh, cubic, stream):
-        assert self._perm is not None and len(self._perm) == n
+        if n <= 0:
+            return 0
+        assert self._perm is not None and len(self._perm) == n and _addr(prefix) == self._perm_prefix, \
+            'b2_deposit_permute: no matching b2_sort_cells result'
         s, d = _ptrs(src8, 8), _ptrs(dst8, 8)
         for a, b in zip(s, d):
             _arr(b, n)[:] = _arr(a, n)[self._perm]
