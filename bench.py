@@ -587,8 +587,11 @@ def main():
     }
     if mgpu_parity is not None:
         out['mgpu_parity'] = mgpu_parity
-    sys.stdout.flush()
-    os.write(json_fd, (json.dumps(out) + '\n').encode())
+    if json_fd == 1:
+        print(json.dumps(out))
+    else:
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + '\n').encode())
 
 
 if __name__ == '__main__':
