@@ -10,7 +10,8 @@
 //   pass 2, line k1 < n1 : n2-point DFT over the scratch rows k1*n2 + j2 (contiguous)         -> out row k1 + n1*k2
 // A CTA owns one line x 16 columns (256-byte row segments); its n = RA*RB points are transformed in two register
 // stages (radix RA: butterflies for 2, 4, 8, direct sums for the odd and composite radices a grid length with
-// guard cells brings: 3, 5, 6, 7, 9, 10, 11, 12, 13, 23) with one exchange through shared memory.  The scratch array
+// guard cells brings: 3, 5, 6, 7, 9, 10, 11, 12, 13, 17, 23; the sums of a radix above 13 are spread over several
+// threads) with one exchange through shared memory.  The scratch array
 // of a group of arrays stays in the 126 MB L2 between the passes, so DRAM sees one read and one write per array.
 // Sizes without an (n1, n2) plan fall back to cuFFT.
 #include "b2_common.cuh"
@@ -98,8 +99,11 @@ template <> struct FfDft<8> {
     }
 };
 
-template <int RA, int RB>
-__global__ void __launch_bounds__((RA > RB ? RA : RB) * FF_C)
+// P2 > 1 (pairs with a big direct radix RB, written (small, big)): P2 threads share the RB-point sums of one
+// (qa, column) -- thread `part` forms the outputs qb = part, part + P2, ... -- so that the second stage has as many
+// busy threads as the first (RA threads with 23^2 complex products each left the rest of the CTA idle).
+template <int RA, int RB, int P2>
+__global__ void __launch_bounds__((RA * P2 > RB ? RA * P2 : (RA > RB ? RA : RB)) * FF_C)
 k_fft_pass(const FfArgs A) {
     constexpr int n = RA * RB;
     __shared__ double2 sW[n];
@@ -131,6 +135,35 @@ k_fft_pass(const FfArgs A) {
     }
     __syncthreads();
     // ---- stage 2: thread (qa = u, column): RB-point DFT over eb, output element q = qa + RA*qb
+    if (P2 > 1) {
+        if (u < RA * P2 && live) {
+            const int qa = u % RA, part = u / RA;
+            double2 y[RB];
+#pragma unroll
+            for (int eb = 0; eb < RB; ++eb) y[eb] = sS[qa * RB + eb][col];
+            for (int qb = part; qb < RB; qb += P2) {
+                double2 acc = y[0];
+                int idx = 0;                                  // (j * qb) mod RB, advanced with j
+#pragma unroll
+                for (int j = 1; j < RB; ++j) {
+                    idx += qb;
+                    if (idx >= RB) idx -= RB;
+                    const double2 t = sW[idx * RA];           // w_RB^(j*qb)
+                    acc.x += y[j].x * t.x - y[j].y * t.y;
+                    acc.y += y[j].x * t.y + y[j].y * t.x;
+                }
+                const int q = qa + RA * qb;
+                if (A.WN) {
+                    double2 t = __ldg(A.WN + line * q);
+                    if (A.inverse) t.y = -t.y;
+                    acc = ff_mul(acc, t);
+                }
+                acc.x *= A.scale; acc.y *= A.scale;
+                out[(size_t)(line * A.line_stride_out + (long long)q * A.elem_stride_out) * A.Nr + c] = acc;
+            }
+        }
+        return;
+    }
     if (u < RA && live) {
         double2 y[RB], w[RB];
 #pragma unroll
@@ -152,13 +185,13 @@ k_fft_pass(const FfArgs A) {
 
 // ---- host side: plans ---------------------------------------------------------------------------------
 typedef void (*ff_kernel_t)(const FfArgs);
-struct FfPair { int ra, rb; ff_kernel_t fn; };
-#define FF_PAIR(a, b) {a, b, k_fft_pass<a, b>}
+struct FfPair { int ra, rb, p2; ff_kernel_t fn; };
+#define FF_PAIR(a, b) {a, b, ((b) > 13 ? (b) / (a) : 1), k_fft_pass<a, b, ((b) > 13 ? (b) / (a) : 1)>}
 static const FfPair g_ff_pairs[] = {
     FF_PAIR(2, 2), FF_PAIR(2, 4), FF_PAIR(4, 4), FF_PAIR(4, 8), FF_PAIR(8, 8),        // 4, 8, 16, 32, 64
     FF_PAIR(3, 4), FF_PAIR(4, 5), FF_PAIR(4, 6), FF_PAIR(4, 7), FF_PAIR(4, 9), FF_PAIR(4, 10),   // 12 .. 40
     FF_PAIR(3, 8), FF_PAIR(5, 8), FF_PAIR(6, 8), FF_PAIR(7, 8), FF_PAIR(8, 9), FF_PAIR(8, 10),   // 24 .. 80
-    FF_PAIR(8, 11), FF_PAIR(8, 12), FF_PAIR(8, 13), FF_PAIR(8, 16),                   // 88, 96, 104, 128
+    FF_PAIR(8, 11), FF_PAIR(8, 12), FF_PAIR(8, 13),                                   // 88, 96, 104
     FF_PAIR(3, 11), FF_PAIR(5, 7), FF_PAIR(6, 6), FF_PAIR(5, 9), FF_PAIR(5, 10), FF_PAIR(6, 9),  // 33 .. 54
     FF_PAIR(6, 10), FF_PAIR(5, 13), FF_PAIR(6, 11), FF_PAIR(3, 23), FF_PAIR(7, 10), FF_PAIR(6, 12),   // 60 .. 72
     FF_PAIR(2, 17), FF_PAIR(4, 17), FF_PAIR(2, 23), FF_PAIR(4, 23),                   // 34, 68, 46, 92
@@ -199,10 +232,6 @@ static int ff_get_plan(int N, const FfPlan **plan) {
             for (int b = 0; b < g_ff_npairs; ++b) {
                 const int n1 = g_ff_pairs[a].ra * g_ff_pairs[a].rb, n2 = g_ff_pairs[b].ra * g_ff_pairs[b].rb;
                 if ((long long)n1 * n2 != N) continue;
-                // a direct radix above 13 is computed by too few threads of the CTA to pay (measured: 76 us at
-                // 4416 = 64 * 3 * 23 against 53 us of cuFFT): such lengths stay with cuFFT
-                if (g_ff_pairs[a].ra > 13 || g_ff_pairs[a].rb > 13 || g_ff_pairs[b].ra > 13 || g_ff_pairs[b].rb > 13)
-                    continue;
                 const double cst = ff_cost(g_ff_pairs[a].ra) + ff_cost(g_ff_pairs[a].rb) + ff_cost(g_ff_pairs[b].ra)
                                    + ff_cost(g_ff_pairs[b].rb);
                 if (cst < best) { best = cst; P.p1 = a; P.p2 = b; }
@@ -255,7 +284,8 @@ int b2_fft_own(b2_ctx *ctx, int na, const void *const *in, void *const *out, int
         A2.Wn = P->Wn2; A2.WN = nullptr; A2.line_stride_in = n2; A2.elem_stride_in = 1;
         A2.line_stride_out = 1; A2.elem_stride_out = n1; A2.Nr = Nr; A2.inverse = inverse ? 1 : 0;
         A2.scale = (inverse == 1) ? 1. / Nz : 1.;
-        const int t1 = (k1.ra > k1.rb ? k1.ra : k1.rb) * FF_C, t2 = (k2.ra > k2.rb ? k2.ra : k2.rb) * FF_C;
+        auto nthreads = [](const FfPair &k) { int m = k.ra > k.rb ? k.ra : k.rb; if (k.ra * k.p2 > m) m = k.ra * k.p2; return m * FF_C; };
+        const int t1 = nthreads(k1), t2 = nthreads(k2);
         k1.fn<<<dim3(ncol, (unsigned)n2, (unsigned)ng), t1, 0, s>>>(A1);
         B2_LAUNCHED();
         k2.fn<<<dim3(ncol, (unsigned)n1, (unsigned)ng), t2, 0, s>>>(A2);

@@ -19,7 +19,7 @@ def _n(v):
     return max(int(round(v * SCALE)), 8)
 
 
-def _run_case(Nz, Nr, Nm, p_nt, fused, v_comoving=None, ions=False, n_order=-1, nsteps=3):
+def _run_case(Nz, Nr, Nm, p_nt, fused, v_comoving=None, ions=False, n_order=-1, nsteps=3, sort_period=1):
     from fbpic_b200 import Simulation
     from oracle import oracle as orc
     np.random.seed(2)
@@ -28,7 +28,8 @@ def _run_case(Nz, Nr, Nm, p_nt, fused, v_comoving=None, ions=False, n_order=-1, 
     dt = dz / c
     sim = Simulation(Nz, zmax, Nr, rmax, Nm, dt, p_zmin=0, p_zmax=zmax, p_rmin=0, p_rmax=rmax, p_nz=2, p_nr=2,
                      p_nt=p_nt, n_e=4.e24, n_order=n_order, n_guard=(None if n_order == -1 else 16),
-                     v_comoving=v_comoving, use_galilean=(v_comoving is not None), initialize_ions=ions, fused=fused)
+                     v_comoving=v_comoving, use_galilean=(v_comoving is not None), initialize_ions=ions, fused=fused,
+                     sort_period=sort_period)
     w0 = 0.2 * rmax
     k0 = 2 * np.pi / zmax * 3
     for sp in sim.ptcl:
@@ -75,6 +76,12 @@ def _run_case(Nz, Nr, Nm, p_nt, fused, v_comoving=None, ions=False, n_order=-1, 
 @pytest.mark.parametrize('fused', [False, True])
 def test_c2_shape(fused):
     _run_case(_n(256), _n(256), 2, 4, fused)
+
+
+def test_c2_shape_as_benched():
+    """C2 shape with the bench's own settings: fused step, sort_period = 4, 9 cycles (two re-sorts, the cycles in
+    between deposit and gather on particles that have moved since their last sort)."""
+    _run_case(_n(256), _n(256), 2, 4, True, nsteps=9, sort_period=4)
 
 
 @pytest.mark.parametrize('fused', [False, True])

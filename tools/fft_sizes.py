@@ -10,7 +10,7 @@ Nr = 256
 ev0, ev1 = ctypes.c_void_p(), ctypes.c_void_p()
 call.b2_event_create(ctypes.byref(ev0)); call.b2_event_create(ctypes.byref(ev1))
 print('impl', os.environ.get('B2_FFT_IMPL', 'own (two-pass) where planned'))
-for Nz in (4096, 4224, 2048, 2240, 256):
+for Nz in (4096, 4224, 4416, 2176, 2208):
     a = DeviceArray.zeros((Nz, Nr), np.complex128)
     b = DeviceArray.zeros((Nz, Nr), np.complex128)
     for _ in range(3):
