@@ -319,13 +319,11 @@ int b2_gather_push_pipe(b2_ctx *ctx, int64_t n, double *x, double *y, double *z,
                         double rmin, int Nr, int Nm, const void *const *grids, double econst, double bconst, double chdt,
                         int32_t *cell_idx, double key_zmin, cudaStream_t s, int64_t *done) {
     *done = 0;
-    // default for linear shapes with Nm <= 2; B2_GATHER_IMPL=tiled selects k_gather_push_tiled (b2_particles.cu)
-    // for everything, =pipe this kernel for every Nm.  Measured on a B200 (profiles/r02_gather_pipe_vs_tiled.md):
-    // C2 (Nm=2) 0.613 ms here, 0.618 ms tiled; C4 (Nm=4, 36 KB of tile per slot: 3 CTAs per SM) 4.5 ms here, 4.3 tiled.
-    static const int mode = []() { const char *e = getenv("B2_GATHER_IMPL");
-                                   if (e && (!strcmp(e, "tiled") || !strcmp(e, "legacy"))) return 0;
-                                   return (e && !strcmp(e, "pipe")) ? 2 : 1; }();
-    const bool off = (mode == 0) || (mode == 1 && Nm > 2);
+    // opt-in: B2_GATHER_IMPL=pipe (every Nm).  Measured on a B200 (profiles/r02_gather_pipe_vs_tiled.md): at C2
+    // 0.620 ms here against 0.596 ms of k_gather_push_tiled, at C4 (Nm = 4, 36 KB of tile per slot: 3 CTAs per SM)
+    // 4.5 against 4.0 ms -- the tiled kernel is the default.
+    static const bool on = []() { const char *e = getenv("B2_GATHER_IMPL"); return e && !strcmp(e, "pipe"); }();
+    const bool off = !on;
     const int64_t nchunks = n / GQ_TPB;
     if (off || nchunks == 0 || Nz < GQ_ROWS || Nr < GQ_COLS) return 0;
     // cp.async.bulk needs 16-byte aligned sources: chunk starts are multiples of 1 KB from the array base

@@ -274,11 +274,14 @@ k_gather_push(int64_t n, double *__restrict__ x, double *__restrict__ y, double 
 // z-row boundary of the sorted order) falls back to global loads; results are identical either way.
 #define GP_TPB 128
 #define GP_TILE_CELLS 96
+#ifndef GP_MIN_CTAS
+#define GP_MIN_CTAS 8
+#endif
 
 // (Measured alternatives that lost: loading the momenta together with the positions -- 80 registers,
 // 6 CTAs/SM, 0.79 vs 0.72 ms at C2 -- and prefetch.global.L2 of the momenta, 0.77 ms.)
 template <int NM>
-__global__ void __launch_bounds__(GP_TPB, 8)
+__global__ void __launch_bounds__(GP_TPB, GP_MIN_CTAS)
 k_gather_push_tiled(int64_t n, double *__restrict__ x, double *__restrict__ y, double *__restrict__ z,
                     double *__restrict__ ux, double *__restrict__ uy, double *__restrict__ uz,
                     double *__restrict__ inv_gamma, double rmax_gather, double invdz, double zmin, int Nz,

@@ -289,13 +289,13 @@ def test_dht_batch_all_kinds_vs_numpy(Nz, Nr):
     assert_close(d_outs[9].get(), ins[0] @ M_new, 1e-13, 'after matrix update')
 
 
-def test_gather_push_tiled_variant_matches_golden():
-    """The tiled gather+push kernel (B2_GATHER_IMPL=tiled; the default is the persistent TMA-staged kernel, which
-    also hands it the last n % 128 particles) against the same goldens and oracle cases: the switch is read once
-    per process, hence the subprocess."""
+def test_gather_push_pipe_variant_matches_golden():
+    """The persistent TMA-staged gather+push kernel (opt-in, B2_GATHER_IMPL=pipe; it hands the last n % 128 particles
+    to the tiled kernel) against the same goldens and oracle cases as the default: the switch is read once per
+    process, hence the subprocess."""
     import subprocess
     import sys
-    env = dict(os.environ, B2_GATHER_IMPL='tiled')
+    env = dict(os.environ, B2_GATHER_IMPL='pipe')
     out = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-m', 'gpu', '-q', '-x',
                           '-p', 'no:cacheprovider', '-k', 'golden and not variant or gather_vs_oracle'],
                          capture_output=True, text=True, env=env, timeout=600)
