@@ -302,6 +302,29 @@ def test_gather_push_pipe_variant_matches_golden():
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
 
 
+@pytest.mark.parametrize('Nz,Nr,na', [(4224, 256, 13), (2240, 512, 3), (4096, 300, 2), (256, 16, 2), (4416, 130, 2)])
+def test_fft_many_arrays_vs_numpy(Nz, Nr, na):
+    """The batched z-FFT call against numpy.fft at the lengths of the bench configurations (4224 = z-slab of C3 with
+    its guards, 2240 = C5, 4416 = C2 with damping cells, radix 23): more arrays than one launch group carries, a
+    ragged last column tile (Nr = 300, 130), back-to-back calls on the same scratch, in-place round trip."""
+    from fbpic_b200 import _lib
+    from fbpic_b200._lib import DeviceArray, call, ptr_array
+    rng = np.random.default_rng(Nz + 7 * Nr)
+    ctx = _lib.context()
+    arrs = [rng.normal(size=(Nz, Nr)) + 1.j * rng.normal(size=(Nz, Nr)) for _ in range(na)]
+    d_in = [DeviceArray.from_numpy(a) for a in arrs]
+    d_out = [DeviceArray((Nz, Nr), np.complex128) for _ in range(na)]
+    for rep in range(2):
+        for inverse, ref in ((0, lambda a: np.fft.fft(a, axis=0)), (2, lambda a: np.fft.ifft(a, axis=0) * Nz)):
+            call.b2_fft_z_multi(ctx.handle, na, ptr_array(d_in), ptr_array(d_out), Nz, Nr, inverse, None)
+            for k in range(na):
+                assert_close(d_out[k].get(), ref(arrs[k]), 1e-13, 'rep %d array %d, inverse=%d' % (rep, k, inverse))
+    call.b2_fft_z_multi(ctx.handle, na, ptr_array(d_in), ptr_array(d_in), Nz, Nr, 0, None)
+    call.b2_fft_z_multi(ctx.handle, na, ptr_array(d_in), ptr_array(d_in), Nz, Nr, 1, None)
+    for k in range(na):
+        assert_close(d_in[k].get(), arrs[k], 1e-13, 'in place round trip, array %d' % k)
+
+
 @pytest.mark.parametrize('Nz,Nr', [(4096, 256), (4224, 64), (4320, 32), (4416, 20), (2048, 50), (200, 64),
                                    (1000, 33), (64, 48), (37, 50)])
 def test_fft_z_vs_numpy(Nz, Nr):
