@@ -74,6 +74,8 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush
     double *sV = sW + MT * 8 * DM_PITCH;               // [NVT][DM_PITCH]: only the rows that carry a value
     // [DM_TPB] run identity = packed upper cell indices (iz_u << DM_IR_BITS | ir_u), -1: no particle
     int *sK = (int *)(sV + NVT * DM_PITCH);
+    double **sG = (double **)(sK + DM_TPB);            // [NT*8] flush table: destination of an accumulator column
+    int *sF = (int *)(sG + NT * 8);                    // [NT*8] its flags
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q0 = blockIdx.x * (int64_t)DM_TPB;
@@ -81,15 +83,15 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush
 
     // ------------------------------------------------------------------ phase A
     {
-        int key = -1;
+        // (a thread beyond the end of the array works on a copy of the last particle with zero weight and marks
+        //  its slot with key -1: no zero-filled packet registers, no divergent tail)
+        const bool live = i < n;
+        int key;
         double S[NROW];
         double V[NT * 8];
-#pragma unroll
-        for (int r = 0; r < NROW; ++r) S[r] = 0.;
-#pragma unroll
-        for (int v = 0; v < NT * 8; ++v) V[v] = 0.;
-        if (i < n) {
-            const size_t j = PERMUTE ? (size_t)__ldg(idx32 + i) : (size_t)i;
+        {
+            const int64_t ii = live ? i : n - 1;
+            const size_t j = PERMUTE ? (size_t)__ldg(idx32 + ii) : (size_t)ii;
             double at[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) at[k] = (PERMUTE || IS_J || PUSH || k < 4) ? __ldg(P.src[k] + j) : 0.;
@@ -103,19 +105,20 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush
                     while (at[2] >= push.wrap_zmax) at[2] -= l_box;
                     while (at[2] < push.wrap_zmin) at[2] += l_box;
                 }
-                if (!PERMUTE) {
+                if (!PERMUTE && live) {
                     P.dst[0][i] = at[0]; P.dst[1][i] = at[1]; P.dst[2][i] = at[2];
                 }
             }
-            if (PERMUTE) {
+            if (PERMUTE && live) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) P.dst[k][i] = at[k];
             }
+            if (!live) at[3] = 0.;
             const B2Cyl c = b2_cyl(at[0], at[1], at[2], invdz, zmin, invdr, rmin);
             int iru = (int)ceil(c.r_cell), izu = (int)ceil(c.z_cell);
             if (iru > Nr) iru = Nr;
             if (izu < 0) izu += Nz; else if (izu > Nz - 1) izu -= Nz;
-            key = (izu << DM_IR_BITS) | iru;
+            key = live ? ((izu << DM_IR_BITS) | iru) : -1;
             const double beta0 = __ldg(ruyten0 + iru), beta_hi = __ldg(ruyten_hi + iru);
             // shape factors (particle_shapes.py:17-80); the flip sign is applied at flush time
             double sz[NPT], sr0[NPT], sr1[NPT];
@@ -178,15 +181,31 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush
         for (int r = 0; r < MT * 8; ++r) sW[r * DM_PITCH + tid] = S[r];
 #pragma unroll
         for (int v = 0; v < NVT; ++v) sV[v * DM_PITCH + tid] = V[v];
+        // flush tables, one entry per accumulator column: grid (+ re / im part) the column's value goes to, and
+        // flags -- 1: value of a mode m >= 1 (weight class 1), 2: changes sign when folded below the axis
+        if (tid < NT * 8) {
+            const int col = tid;
+            int comp = col, m = 0, part = 0;
+            if (col >= NCOMP) {
+                const int d = col - NCOMP, km = d >> 1;
+                part = d & 1;
+                comp = km / (NM > 1 ? NM - 1 : 1);
+                m = km - comp * (NM > 1 ? NM - 1 : 1) + 1;
+            }
+            bool neg = (m & 1) != 0;
+            if (IS_J && comp < 2) neg = !neg;
+            sG[col] = (col < NVT) ? ((double *)G.g[IS_J ? (3 * m + comp) : m] + part) : nullptr;
+            sF[col] = (m > 0 ? 1 : 0) | (neg ? 2 : 0);
+        }
     }
     __syncthreads();
 
     // ------------------------------------------------------------------ phase B
     const int g = lane >> 2, t = lane & 3;
-    // lane constants of the flush: this lane holds C[row = mt*8+g][col = nt*8 + 2t + h]
+    // lane constants of the flush: this lane holds C[row = mt*8+g][col = nt*8 + 2t + h]; bit (mt*NT + nt)*2 + h
+    // of ok_mask: the entry carries a value of the row's weight class, of neg_mask: its sign flips below the axis
+    unsigned ok_mask = 0, neg_mask = 0;
     int f_a[MT], f_b[MT];                     // stencil offsets of the row's point
-    double *f_ptr[MT][NT][2];                 // grid base (+re/im part) of the column's value, null: unused
-    double f_flip[MT][NT][2];                 // sign applied when the point lies below the axis
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         const int row = mt * 8 + g;
@@ -197,48 +216,43 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int col = nt * 8 + 2 * t + h;
-                int comp = 0, m = 0, part = 0;
-                bool ok = col < NVT;
-                if (col >= NCOMP) {
-                    const int d = col - NCOMP;
-                    part = d & 1;
-                    const int km = d >> 1;
-                    comp = km / (NM > 1 ? NM - 1 : 1);
-                    m = km - comp * (NM > 1 ? NM - 1 : 1) + 1;
-                } else {
-                    comp = col;
-                }
-                ok = ok && ((m > 0) == (cls == 1));        // weight class of this value
-                double sgn = (m & 1) ? -1. : 1.;
-                if (IS_J && comp < 2) sgn = -sgn;
-                f_flip[mt][nt][h] = sgn;
-                f_ptr[mt][nt][h] = ok ? ((double *)G.g[IS_J ? (3 * m + comp) : m] + part) : nullptr;
+                const int col = nt * 8 + 2 * t + h, fl = sF[col];
+                if (col < NVT && (fl & 1) == cls) ok_mask |= 1u << ((mt * NT + nt) * 2 + h);
+                if (fl & 2) neg_mask |= 1u << ((mt * NT + nt) * 2 + h);
             }
     }
-    const int lo_w = warp * 32, hi_w = lo_w + 32;            // this warp's particles (CTA-local)
-    int pos = lo_w;
-    while (pos < hi_w) {
-        const int key = sK[pos];
+    double *const *const sGl = sG + 2 * t;     // entry (nt, h) at sGl[nt * 8 + h]
+    // fragment rows of this lane; value rows beyond NVT do not exist: their columns are never flushed, any
+    // finite operand will do
+    const double *a_row[MT], *b_row[NT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) a_row[mt] = sW + (mt * 8 + g) * DM_PITCH;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) b_row[nt] = sV + (nt * 8 + g < NVT ? nt * 8 + g : NVT - 1) * DM_PITCH;
+    const int lo_w = warp * 32;                              // this warp's particles (CTA-local)
+    const int my_key = sK[lo_w + lane];
+    int pos = 0;                                             // warp-local
+    while (pos < 32) {
+        const int key = __shfl_sync(0xffffffffu, my_key, pos);
         // end of the run of equal keys starting at pos (within the warp's slice)
-        const int kk = (lo_w + lane >= pos) ? sK[lo_w + lane] : key;
-        const unsigned diff = __ballot_sync(0xffffffffu, kk != key);
-        const int end = diff ? (lo_w + __ffs(diff) - 1) : hi_w;
+        const unsigned diff = __ballot_sync(0xffffffffu, lane >= pos && my_key != key);
+        const int end = diff ? (__ffs(diff) - 1) : 32;
         if (key >= 0) {
             double acc[MT][NT][2];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.;
+            // K = 4 particles per step; a particle outside the run is masked in the weights only (its values
+            // are finite numbers of this warp's slice, times zero)
             for (int k0 = pos & ~3; k0 < end; k0 += 4) {
                 const int p = k0 + t;
-                const bool in = (p >= pos) && (p < end);
+                const bool in = (unsigned)(p - pos) < (unsigned)(end - pos);
                 double a[MT], b[NT];
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) a[mt] = in ? sW[(mt * 8 + g) * DM_PITCH + p] : 0.;
+                for (int mt = 0; mt < MT; ++mt) { const double v = a_row[mt][lo_w + p]; a[mt] = in ? v : 0.; }
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
-                    b[nt] = (in && nt * 8 + g < NVT) ? sV[(nt * 8 + g) * DM_PITCH + p] : 0.;
+                for (int nt = 0; nt < NT; ++nt) b[nt] = b_row[nt][lo_w + p];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -253,16 +267,25 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush
                 if (iz > Nz - 1) iz -= Nz;
                 int ir = ir_u + f_b[mt];
                 const bool below = ir < 0;
-                if (below) ir = -(1 + ir);
+                if (below) ir = ~ir;                          // -(1 + ir)
                 if (ir > Nr - 1) ir = Nr - 1;
-                const size_t o = 2 * ((size_t)iz * Nr + ir);
+                const unsigned o = (unsigned)(iz * Nr + ir);  // < 2^31 (checked by the launcher)
+                const unsigned flip = below ? neg_mask : 0u;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const double v = acc[mt][nt][h];
-                        if (f_ptr[mt][nt][h] != nullptr && v != 0.)
-                            atomicAdd(f_ptr[mt][nt][h] + o, below ? f_flip[mt][nt][h] * v : v);
+                        const int bit = (mt * NT + nt) * 2 + h;
+                        if ((ok_mask >> bit) & 1u) {
+                            // sign flip = the flag bit moved onto the sign bit of the high word
+                            const double v = acc[mt][nt][h];
+                            const int hi = __double2hiint(v) ^ (int)((flip << (31 - bit)) & 0x80000000u);
+                            // (the pointer comes out of shared memory: a plain atomicAdd would take the generic
+                            //  path with its address-space checks)
+                            asm volatile("red.global.add.f64 [%0], %1;"
+                                         ::"l"((char *)sGl[nt * 8 + h] + (size_t)o * 16),
+                                           "d"(__hiloint2double(hi, __double2loint(v))) : "memory");
+                        }
                     }
             }
         }
@@ -286,8 +309,8 @@ struct DmArgs {
 template <int NM, bool IS_J, int NPT, bool PERMUTE, bool PUSH>
 static int launch_dm(cudaStream_t s, const DmArgs &A) {
     constexpr int NCOMP = IS_J ? 3 : 1;
-    constexpr int MT = 2 * NPT * NPT / 8, NVT = NCOMP * (2 * NM - 1);
-    const size_t smem = sizeof(double) * DM_PITCH * (8 * MT + NVT) + sizeof(int) * DM_TPB;
+    constexpr int MT = 2 * NPT * NPT / 8, NVT = NCOMP * (2 * NM - 1), NT = (NVT + 7) / 8;
+    const size_t smem = sizeof(double) * DM_PITCH * (8 * MT + NVT) + sizeof(int) * DM_TPB + (sizeof(double *) + sizeof(int)) * NT * 8;
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
         B2_CUDA(cudaFuncSetAttribute(k_deposit_mma<NM, IS_J, NPT, PERMUTE, PUSH>,

@@ -1,5 +1,7 @@
-timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -p no:cacheprovider -k "fft or transforms" 2>&1 | tail -5
-python tools/fft_sizes.py 2>&1 | tail -6
-for v in "B2_FFT_LAG=2 B2_FFT_RING=6" "B2_FFT_LAG=4 B2_FFT_RING=8" "B2_FFT_GC=16 B2_FFT_LAG=2 B2_FFT_RING=5"; do
-  env $v FFT_SIZES=4096,4224 python tools/fft_sizes.py 2>&1 | tail -3
-done
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_step.py tests/test_gpu_x_fullsize_properties.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -5
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e 2>/dev/null | grep '^{' | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('C2', d['value'], d['ms_per_step']); print({k:round(v['ms_per_step'],4) for k,v in d['kernels'].items()})"
+python bench.py --config C4 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | grep '^{' | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('C4', d['value'], d['ms_per_step']); print({k:round(v['ms_per_step'],3) for k,v in d['kernels'].items()})"
