@@ -181,6 +181,10 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush
         for (int r = 0; r < MT * 8; ++r) sW[r * DM_PITCH + tid] = S[r];
 #pragma unroll
         for (int v = 0; v < NVT; ++v) sV[v * DM_PITCH + tid] = V[v];
+        if (tid < DM_PITCH - DM_TPB) {
+#pragma unroll
+            for (int v = 0; v < NVT; ++v) sV[v * DM_PITCH + DM_TPB + tid] = 0.;
+        }
         // flush tables, one entry per accumulator column: grid (+ re / im part) the column's value goes to, and
         // flags -- 1: value of a mode m >= 1 (weight class 1), 2: changes sign when folded below the axis
         if (tid < NT * 8) {
@@ -263,9 +267,12 @@ k_deposit_mma(int64_t n, B2DmPtrs P, const int32_t *__restrict__ idx32, B2DmPush
                 for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.;
             // K = 4 particles per step; a particle outside the run is masked in the weights only (its values
             // are finite numbers of this CTA's packets, times zero)
-            for (int k0 = pos & ~3; k0 < end; k0 += 4) {
+            // (steps start at the run's first slot, not at a multiple of 4: ceil(len / 4) steps instead of 4.75 on
+            //  average for 16 particles; the last step may read up to 3 slots past the run -- of the next run, or of
+            //  the zero-filled pad columns behind slot 255)
+            for (int k0 = pos; k0 < end; k0 += 4) {
                 const int p = k0 + t;
-                const bool in = (unsigned)(p - pos) < (unsigned)(end - pos);
+                const bool in = p < end;
                 double a[MT], b[NT];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) { const double v = a_row[mt][p]; a[mt] = in ? v : 0.; }
