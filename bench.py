@@ -8,9 +8,10 @@ Workload (BASELINE.json configs[1], SURVEY 8d "C2"): Nz=4096 per GPU, Nr=256, Nm
 shapes, uniform electrons 2x2x4 per cell (16.8 M macro-particles per GPU) filling the box,
 a0=4 / w0=5um / 16fs Gaussian laser pulse initialised analytically on the grid, z periodic
 (Nz stays 4096: isolates the hot loop).  N>1: weak scaling over z-slabs (n_order=32, NCCL guard-cell
-exchange + particle migration): every GPU works on a local periodic box of 4096 cells = 3968 physical
-cells + 2x64 guard cells, so the local z-FFT keeps the single-GPU length (`--full-slab`: 4096 physical
-cells + guards = 4224 local cells per GPU); the particle count in `value` is the real one.
+exchange + particle migration), C3 as named: 4096 physical cells + 2x64 guard cells = 4224 local cells per GPU
+(`--compact-slab`: the guards inside a local box of 4096 cells); the particle count in `value` is the real one.
+The timed region holds the K steps and nothing else; the per-kernel-family device times (`kernels`, `roofline`) come
+from a second pass of K steps with CUDA events around every launch (`ms_per_step_instrumented`).
 One "step" = one full PIC cycle (Simulation.step(1)); metric = particle-updates/s =
 (sum over ranks of macro-particles) * K / (max over ranks of the device time of K steps).
 Prints ONE JSON line (rank 0).
@@ -415,23 +416,33 @@ def main():
     call.b2_event_create(ctypes.byref(ev0))
     call.b2_event_create(ctypes.byref(ev1))
     sampler = ClockSampler(ctx.device) if rank == 0 else None
-    call.b2_profile_reset()
-    call.b2_profile_enable(1)
     launches0 = _lib.load().b2_launch_count()
     flops0 = _lib.load().b2_dht_flops()
     barrier()
     if sampler:
         sampler.start()
+    # the timed region: K steps, nothing else on the stream (the per-launch events of the kernel table cost
+    # ~2 us of stream time per launch: they are recorded in a second pass of K steps below)
     call.b2_event_record(ev0, ctx.stream)
     sim.step(args.steps, keep_on_gpu=True)
     call.b2_event_record(ev1, ctx.stream)
+    host_enqueue_ms = sim.last_enqueue_s * 1e3 / args.steps
     barrier()
     ms = ctypes.c_float(0.)
     call.b2_event_elapsed_ms(ev0, ev1, ctypes.byref(ms))
     clocks = sampler.stop() if sampler else None
     launches = _lib.load().b2_launch_count() - launches0
     dht_flops = _lib.load().b2_dht_flops() - flops0
+    # second pass, same K steps, with CUDA events around every launch: per-kernel-family device time (roofline)
+    call.b2_profile_reset()
+    call.b2_profile_enable(1)
+    call.b2_event_record(ev0, ctx.stream)
+    sim.step(args.steps, keep_on_gpu=True)
+    call.b2_event_record(ev1, ctx.stream)
+    barrier()
     call.b2_profile_enable(0)
+    ms_prof = ctypes.c_float(0.)
+    call.b2_event_elapsed_ms(ev0, ev1, ctypes.byref(ms_prof))
     prof = profile_table()
     t_ms, n_tot = ms.value, float(Ntot_local)
     if dist is not None:
@@ -582,7 +593,8 @@ def main():
         'config': {'workload': workload, 'particles_total': n_tot, 'host_affinity': affinity, 'fused': not args.no_fused,
                    'n_order': -1 if n_gpus == 1 else 32, 'n_guard': sim.comm.n_guard, 'preroll_steps': args.preroll, 'sort_period': args.sort_period,
                    'l2': 'inputs larger than L2 (particle state %.1f GB per GPU)' % (Ntot_local * 64 / 1e9)},
-        'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline,
+        'gpu_launches': int(launches), 'host_enqueue_ms_per_step': round(host_enqueue_ms, 4),
+        'ms_per_step_instrumented': round(ms_prof.value / args.steps, 4), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline,
         'cpu_baseline': cpu_baseline, 'kernels': kernels,
     }
     if mgpu_parity is not None:

@@ -278,6 +278,7 @@ class Simulation(object):
         fld.spect2interp('rho_prev')
         if (not fld.exchanged_source['rho_prev']) and (self.comm.size > 1):
             self.comm.exchange_fields(self.fld.interp, 'rho', 'add')
+        t_enqueued = _time.perf_counter()
         _lib.context().sync()
         t_done = _time.perf_counter()
         if not keep_on_gpu:
@@ -285,6 +286,8 @@ class Simulation(object):
         # wall-clock split of this call: host->device copy, the N cycles (device-synchronised), device->host copy
         self.last_step_timing = dict(h2d_s=t_sent - t_start, cycles_s=t_done - t_sent,
                                      d2h_s=_time.perf_counter() - t_done)
+        # host time spent issuing the launches of the N cycles (the device runs behind it, asynchronously)
+        self.last_enqueue_s = t_enqueued - t_sent
         if progress_bar is not None:
             progress_bar.print_summary()
         # bytes copied host->device / device->host by this call (counted from the arrays actually copied)
