@@ -43,21 +43,44 @@ __device__ __forceinline__ double2 ff_mul(double2 a, double2 b) {
 __device__ __forceinline__ double2 ff_rot(double2 a, double s) { return make_double2(s * a.y, -s * a.x); }
 
 // R-point DFT in registers, natural order in and out.  w[j] = w_R^j with the direction's sign already applied.
-// Output q is handed to `emit(q, value)` as soon as it is formed: the direct sums of the odd radices never hold
-// a second array of R values (radix 23 would not fit the register file otherwise).
+// Output q is handed to `emit(q, value)` as soon as it is formed.  The direct sums of the odd and composite radices
+// use the conjugate symmetry of the twiddles, w^{(R-j)q} = conj(w^{jq}):  with a_j = x_j + x_{R-j} and
+// b_j = x_j - x_{R-j},  X[q] = P + iQ and X[R-q] = P - iQ  where  P = x_0 + sum_j Re(w^{jq}) a_j (+ (-1)^q x_{R/2}),
+// Q = sum_j Im(w^{jq}) b_j -- 4 real multiply-adds per (pair of outputs, pair of inputs) instead of 16: the
+// 11-point sums of the 4224-cell slab transform cost 130 operations instead of 440.
 template <int R> struct FfDft {
     template <class Emit>
     static __device__ __forceinline__ void run(double2 (&x)[R], const double2 (&w)[R], double, Emit emit) {
+        constexpr int H = (R - 1) / 2;
+        constexpr bool EVEN = (R % 2 == 0);
+        double2 a[H], b[H];
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
+        for (int j = 1; j <= H; ++j) { a[j - 1] = ff_add(x[j], x[R - j]); b[j - 1] = ff_sub(x[j], x[R - j]); }
+        {
             double2 acc = x[0];
 #pragma unroll
-            for (int j = 1; j < R; ++j) {
+            for (int j = 0; j < H; ++j) acc = ff_add(acc, a[j]);
+            if (EVEN) acc = ff_add(acc, x[R / 2]);
+            emit(0, acc);
+        }
+        if (EVEN) {     // q = R/2: every twiddle is +-1
+            double2 acc = ((R / 2) & 1) ? ff_sub(x[0], x[R / 2]) : ff_add(x[0], x[R / 2]);
+#pragma unroll
+            for (int j = 1; j <= H; ++j) acc = (j & 1) ? ff_sub(acc, a[j - 1]) : ff_add(acc, a[j - 1]);
+            emit(R / 2, acc);
+        }
+#pragma unroll
+        for (int q = 1; q <= H; ++q) {
+            double2 P = x[0], Q = make_double2(0., 0.);
+            if (EVEN) P = (q & 1) ? ff_sub(P, x[R / 2]) : ff_add(P, x[R / 2]);
+#pragma unroll
+            for (int j = 1; j <= H; ++j) {
                 const double2 t = w[(j * q) % R];
-                acc.x += x[j].x * t.x - x[j].y * t.y;
-                acc.y += x[j].x * t.y + x[j].y * t.x;
+                P.x += t.x * a[j - 1].x; P.y += t.x * a[j - 1].y;
+                Q.x += t.y * b[j - 1].x; Q.y += t.y * b[j - 1].y;
             }
-            emit(q, acc);
+            emit(q, make_double2(P.x - Q.y, P.y + Q.x));
+            emit(R - q, make_double2(P.x + Q.y, P.y - Q.x));
         }
     }
 };
@@ -102,8 +125,14 @@ template <> struct FfDft<8> {
 // P2 > 1 (pairs with a big direct radix RB, written (small, big)): P2 threads share the RB-point sums of one
 // (qa, column) -- thread `part` forms the outputs qb = part, part + P2, ... -- so that the second stage has as many
 // busy threads as the first (RA threads with 23^2 complex products each left the rest of the CTA idle).
+// resident CTAs the register allocation has to leave room for (the symmetric sums give ptxas many independent
+// outputs to keep in flight: unbounded, the 11-point pass takes 132 registers and 2 CTAs per SM instead of 3)
+constexpr int ff_pass_min_ctas(int rmax, int p2) {
+    return p2 > 1 ? 2 : 65536 / ((rmax == 7 ? 80 : rmax <= 8 ? 64 : rmax <= 11 ? 104 : 128) * rmax * FF_C);
+}
 template <int RA, int RB, int P2>
-__global__ void __launch_bounds__((RA * P2 > RB ? RA * P2 : (RA > RB ? RA : RB)) * FF_C)
+__global__ void __launch_bounds__((RA * P2 > RB ? RA * P2 : (RA > RB ? RA : RB)) * FF_C,
+                                  ff_pass_min_ctas(RA > RB ? RA : RB, P2))
 k_fft_pass(const FfArgs A) {
     constexpr int n = RA * RB;
     __shared__ double2 sW[n];
@@ -135,23 +164,36 @@ k_fft_pass(const FfArgs A) {
     }
     __syncthreads();
     // ---- stage 2: thread (qa = u, column): RB-point DFT over eb, output element q = qa + RA*qb
-    if (P2 > 1) {
+    if constexpr (P2 > 1) {
         if (u < RA * P2 && live) {
             const int qa = u % RA, part = u / RA;
-            double2 y[RB];
+            // the same symmetric sums as FfDft<R>, the (RB + 1) / 2 units -- output 0, then the output pairs
+            // (q, RB - q) -- dealt out to the P2 threads
+            constexpr int H = (RB - 1) / 2;
+            static_assert(RB % 2 == 1, "the split second stage is written for odd radices");
+            // (every y_j is read once and feeds all the units of the thread: the sums stay in 4 registers per unit
+            //  -- held in registers, a_j and b_j cost 88 registers for radix 23 and one CTA per SM)
+            constexpr int NU = (H + 1 + P2 - 1) / P2;         // units per thread
+            const double2 y0 = sS[qa * RB][col];
+            double2 P[NU], Q[NU];
+            int idx[NU];
 #pragma unroll
-            for (int eb = 0; eb < RB; ++eb) y[eb] = sS[qa * RB + eb][col];
-            for (int qb = part; qb < RB; qb += P2) {
-                double2 acc = y[0];
-                int idx = 0;                                  // (j * qb) mod RB, advanced with j
+            for (int k = 0; k < NU; ++k) { P[k] = y0; Q[k] = make_double2(0., 0.); idx[k] = 0; }
 #pragma unroll
-                for (int j = 1; j < RB; ++j) {
-                    idx += qb;
-                    if (idx >= RB) idx -= RB;
-                    const double2 t = sW[idx * RA];           // w_RB^(j*qb)
-                    acc.x += y[j].x * t.x - y[j].y * t.y;
-                    acc.y += y[j].x * t.y + y[j].y * t.x;
+            for (int j = 1; j <= H; ++j) {
+                const double2 yj = sS[qa * RB + j][col], yr = sS[qa * RB + RB - j][col];
+                const double2 a = ff_add(yj, yr), b = ff_sub(yj, yr);
+#pragma unroll
+                for (int k = 0; k < NU; ++k) {
+                    const int unit = part + k * P2;           // (a unit beyond H computes a copy of output 0: unused)
+                    idx[k] += (unit <= H) ? unit : 0;         // (j * unit) mod RB, advanced with j
+                    if (idx[k] >= RB) idx[k] -= RB;
+                    const double2 t = sW[idx[k] * RA];        // w_RB^(j*unit)
+                    P[k].x += t.x * a.x; P[k].y += t.x * a.y;
+                    Q[k].x += t.y * b.x; Q[k].y += t.y * b.y;
                 }
+            }
+            auto put = [&](int qb, double2 acc) {
                 const int q = qa + RA * qb;
                 if (A.WN) {
                     double2 t = __ldg(A.WN + line * q);
@@ -160,6 +202,13 @@ k_fft_pass(const FfArgs A) {
                 }
                 acc.x *= A.scale; acc.y *= A.scale;
                 out[(size_t)(line * A.line_stride_out + (long long)q * A.elem_stride_out) * A.Nr + c] = acc;
+            };
+#pragma unroll
+            for (int k = 0; k < NU; ++k) {
+                const int unit = part + k * P2;
+                if (unit > H) break;
+                put(unit, make_double2(P[k].x - Q[k].y, P[k].y + Q[k].x));
+                if (unit > 0) put(RB - unit, make_double2(P[k].x + Q[k].y, P[k].y - Q[k].x));
             }
         }
         return;

@@ -1,1 +1,2 @@
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:"k_gather_push_tiled" --launch-skip 5 -c 1 -o gpurun_out/r02_gp4 -f python bench.py --steps 4 --warmup 3 --preroll 4 --no-e2e --no-cpu-baseline > gpurun_out/ncu_gp4.log 2>&1; tail -2 gpurun_out/ncu_gp4.log
+timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -p no:cacheprovider -k "fft or transforms" 2>&1 | tail -3
+FFT_SIZES=4224,4416,4352,2176 python tools/fft_sizes.py 2>&1 | tail -5

@@ -9,7 +9,7 @@ ctx = _lib.context()
 Nr = 256
 ev0, ev1 = ctypes.c_void_p(), ctypes.c_void_p()
 call.b2_event_create(ctypes.byref(ev0)); call.b2_event_create(ctypes.byref(ev1))
-print('impl', os.environ.get('B2_FFT_IMPL', 'own (fused launch where the first pass is 8 x 8)'), {k: v for k, v in os.environ.items() if k.startswith('B2_FFT_')})
+print('impl', os.environ.get('B2_FFT_IMPL', 'own (two-pass) where planned'), {k: v for k, v in os.environ.items() if k.startswith('B2_FFT_')})
 for Nz in [int(v) for v in os.environ.get('FFT_SIZES', '4096,4224,4416,2240,2048').split(',')]:
     a = DeviceArray.zeros((Nz, Nr), np.complex128)
     b = DeviceArray.zeros((Nz, Nr), np.complex128)
