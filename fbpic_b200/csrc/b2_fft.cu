@@ -135,7 +135,7 @@ __global__ void __launch_bounds__((RA * P2 > RB ? RA * P2 : (RA > RB ? RA : RB))
                                   ff_pass_min_ctas(RA > RB ? RA : RB, P2))
 k_fft_pass(const FfArgs A) {
     constexpr int n = RA * RB;
-    __shared__ double2 sW[n];
+    __shared__ double2 sW[n], sT[n];
     __shared__ double2 sS[n][FF_C];
     const int tid = threadIdx.x, u = tid / FF_C, col = tid % FF_C;
     // column tile fastest: the CTAs in flight together cover whole 4 KB rows (adjacent 256-byte segments of the
@@ -145,19 +145,31 @@ k_fft_pass(const FfArgs A) {
     const double2 *in = A.in[blockIdx.z];
     double2 *out = A.out[blockIdx.z];
     const double s = A.inverse ? -1. : 1.;
+    const bool live = c < A.Nr;
+    // the element loads go out first; the tables -- w_n^k and, in the first pass, this line's n inter-pass twiddles
+    // w_N^(line*q) -- are fetched behind them and parked in shared memory (ncu: with a __ldg at the point of use,
+    // the wait for the inter-pass twiddle was as long as the wait for the elements themselves)
+    const bool act1 = u < RB && live;
+    double2 x[RA];
+    if (act1) {
+#pragma unroll
+        for (int ea = 0; ea < RA; ++ea)
+            x[ea] = __ldg(in + (size_t)(line * A.line_stride_in + (long long)(ea * RB + u) * A.elem_stride_in) * A.Nr + c);
+    }
     for (int k = tid; k < n; k += blockDim.x) {
         double2 w = __ldg(A.Wn + k);
         if (A.inverse) w.y = -w.y;
         sW[k] = w;
+        if (A.WN) {
+            double2 t = __ldg(A.WN + line * k);
+            if (A.inverse) t.y = -t.y;
+            sT[k] = t;
+        }
     }
     __syncthreads();
-    const bool live = c < A.Nr;
     // ---- stage 1: thread (eb = u, column): RA-point DFT over the elements ea*RB + eb, twiddle w_n^(eb*qa)
-    if (u < RB && live) {
-        double2 x[RA], w[RA];
-#pragma unroll
-        for (int ea = 0; ea < RA; ++ea)
-            x[ea] = __ldg(in + (size_t)(line * A.line_stride_in + (long long)(ea * RB + u) * A.elem_stride_in) * A.Nr + c);
+    if (act1) {
+        double2 w[RA];
 #pragma unroll
         for (int j = 0; j < RA; ++j) w[j] = sW[j * RB];
         FfDft<RA>::run(x, w, s, [&](int qa, double2 v) { sS[qa * RB + u][col] = ff_mul(v, sW[u * qa]); });
@@ -195,11 +207,7 @@ k_fft_pass(const FfArgs A) {
             }
             auto put = [&](int qb, double2 acc) {
                 const int q = qa + RA * qb;
-                if (A.WN) {
-                    double2 t = __ldg(A.WN + line * q);
-                    if (A.inverse) t.y = -t.y;
-                    acc = ff_mul(acc, t);
-                }
+                if (A.WN) acc = ff_mul(acc, sT[q]);
                 acc.x *= A.scale; acc.y *= A.scale;
                 out[(size_t)(line * A.line_stride_out + (long long)q * A.elem_stride_out) * A.Nr + c] = acc;
             };
@@ -221,11 +229,7 @@ k_fft_pass(const FfArgs A) {
         for (int j = 0; j < RB; ++j) w[j] = sW[j * RA];
         FfDft<RB>::run(y, w, s, [&](int qb, double2 v) {
             const int q = u + RA * qb;
-            if (A.WN) {
-                double2 t = __ldg(A.WN + line * q);
-                if (A.inverse) t.y = -t.y;
-                v = ff_mul(v, t);
-            }
+            if (A.WN) v = ff_mul(v, sT[q]);
             v.x *= A.scale; v.y *= A.scale;
             out[(size_t)(line * A.line_stride_out + (long long)q * A.elem_stride_out) * A.Nr + c] = v;
         });
