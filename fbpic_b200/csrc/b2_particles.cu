@@ -288,8 +288,7 @@ k_gather_push_tiled(int64_t n, double *__restrict__ x, double *__restrict__ y, d
                     double invdr, double rmin, int Nr, B2Grids G, double econst, double bconst, double chdt,
                     int32_t *__restrict__ cell_idx, double key_zmin) {
     __shared__ double2 tile[6 * NM][GP_TILE_CELLS];
-    __shared__ int s_box[4];     // min iz_l (unwrapped), max iz_u (unwrapped), min ir, max ir (clamped)
-    __shared__ int s_anchor[2];
+    __shared__ int4 s_boxw[GP_TPB / 32];     // per warp: min iz_l (unwrapped), max iz_u (unwrapped), min ir, max ir (clamped)
     const int tid = threadIdx.x;
     const int64_t i = blockIdx.x * (int64_t)GP_TPB + tid;
     const bool in_range = i < n;
@@ -306,24 +305,32 @@ k_gather_push_tiled(int64_t n, double *__restrict__ x, double *__restrict__ y, d
     if (ir_l < 0) { Sr_g = Sr_l; Sr_l = 0.; ir_l = 0; }
     if (ir_l > Nr - 1) ir_l = Nr - 1;
     if (ir_u > Nr - 1) ir_u = Nr - 1;
-    // bounding box of the stencils of the particles that lie NEAR the CTA's first particle (sorted
-    // particles all do); a stray particle (moved far since the last sort) gathers from global memory
-    // on its own instead of blowing up the tile for the whole CTA
-    if (tid == 0) {
-        s_box[0] = INT_MAX; s_box[1] = INT_MIN; s_box[2] = INT_MAX; s_box[3] = INT_MIN;
-        s_anchor[0] = iz_l0; s_anchor[1] = ir_l;
+    // bounding box of the stencils of the particles that lie NEAR their warp's first particle (sorted particles all
+    // do); a stray particle (moved far since the last sort) gathers from global memory on its own instead of blowing
+    // up the tile for the whole CTA.  Warp-level integer reductions, one shared-memory slot per warp and one barrier:
+    // the 4 x 128 shared atomics on four addresses plus the barrier for the CTA-wide anchor took as long as the
+    // particle loads (ncu: barrier stall 4.7 cycles per issue).
+    const int lane = tid & 31, warp_id = tid >> 5;
+    const int a_z = __shfl_sync(0xffffffffu, iz_l0, 0), a_r = __shfl_sync(0xffffffffu, ir_l, 0);
+    const bool near = active && abs(iz_l0 - a_z) <= 2 && ir_l >= a_r - 8 && ir_u <= a_r + 40;
+    {
+        const int b0 = __reduce_min_sync(0xffffffffu, near ? iz_l0 : INT_MAX);
+        const int b1 = __reduce_max_sync(0xffffffffu, near ? iz_l0 + 1 : INT_MIN);
+        const int b2 = __reduce_min_sync(0xffffffffu, near ? ir_l : INT_MAX);
+        const int b3 = __reduce_max_sync(0xffffffffu, near ? ir_u : INT_MIN);
+        if (lane == 0) s_boxw[warp_id] = make_int4(b0, b1, b2, b3);
     }
     __syncthreads();
-    const bool near = active && abs(iz_l0 - s_anchor[0]) <= 2 && ir_l >= s_anchor[1] - 8 && ir_u <= s_anchor[1] + 40;
-    if (near) {
-        atomicMin(&s_box[0], iz_l0); atomicMax(&s_box[1], iz_l0 + 1);
-        atomicMin(&s_box[2], ir_l);  atomicMax(&s_box[3], ir_u);
+    int4 box = s_boxw[0];
+#pragma unroll
+    for (int w = 1; w < GP_TPB / 32; ++w) {
+        const int4 o = s_boxw[w];
+        box.x = min(box.x, o.x); box.y = max(box.y, o.y); box.z = min(box.z, o.z); box.w = max(box.w, o.w);
     }
-    __syncthreads();
-    const int z0 = s_box[0], r0 = s_box[2];
-    const bool box_ok = (s_box[1] >= s_box[0]) && (s_box[3] >= s_box[2]);   // some particle is near
-    const int nrow = box_ok ? s_box[1] - z0 + 1 : 0, ncol = box_ok ? s_box[3] - r0 + 1 : 0;
-    const bool tile_ok = box_ok && (nrow * ncol <= GP_TILE_CELLS) && z0 >= -1 && s_box[1] <= Nz;
+    const int z0 = box.x, r0 = box.z;
+    const bool box_ok = (box.y >= box.x) && (box.w >= box.z);   // some particle is near
+    const int nrow = box_ok ? box.y - z0 + 1 : 0, ncol = box_ok ? box.w - r0 + 1 : 0;
+    const bool tile_ok = box_ok && (nrow * ncol <= GP_TILE_CELLS) && z0 >= -1 && box.y <= Nz;
     const bool use_tile = tile_ok && near;          // per thread
     if (tile_ok && tid < nrow * ncol) {
         // one thread per tile cell (GP_TILE_CELLS <= GP_TPB), 6*NM coalesced 16-byte loads each
