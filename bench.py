@@ -38,6 +38,8 @@ if ROOT not in sys.path:
 CONFIGS = {
     # name: Nz (per GPU), Nr, Nm, (p_nz, p_nr, p_nt), dz [m], rmax [m], n_e
     'C2': dict(Nz=4096, Nr=256, Nm=2, ppc=(2, 2, 4), dz=0.05e-6, rmax=20.e-6 * 256 / 50, n_e=4.e24),
+    # C2 with cubic particle shapes (the 4 x 4 stencil kernels)
+    'C2c': dict(Nz=4096, Nr=256, Nm=2, ppc=(2, 2, 4), dz=0.05e-6, rmax=20.e-6 * 256 / 50, n_e=4.e24, shape='cubic'),
     'C1': dict(Nz=256, Nr=64, Nm=2, ppc=(2, 2, 4), dz=0.2e-6, rmax=20.e-6, n_e=2.e24),
     'C4': dict(Nz=2048, Nr=512, Nm=4, ppc=(2, 2, 16), dz=0.05e-6, rmax=40.e-6, n_e=4.e24),
     # C4 with the minimum azimuthal sampling main.py:817-821 allows for the default of p_nt (transform-dominated)
@@ -109,7 +111,7 @@ def build_b200_sim(cfg, n_gpus, fused=True, seed=0, sort_period=1, full_slab=Tru
     sim = Simulation(Nz_g, zmax, cfg['Nr'], cfg['rmax'], cfg['Nm'], dt, p_zmin=0., p_zmax=zmax,
                      p_rmin=0., p_rmax=cfg['rmax'], p_nz=p_nz, p_nr=p_nr, p_nt=p_nt, n_e=cfg['n_e'],
                      n_order=n_order, n_guard=n_guard, boundaries={'z': bz, 'r': 'reflective'},
-                     fused=fused, sort_period=sort_period, **kw)
+                     fused=fused, sort_period=sort_period, particle_shape=cfg.get('shape', 'linear'), **kw)
     if uz_m != 0.:
         for sp in sim.ptcl:                 # the plasma flows backwards at gamma in the boosted frame (main.py:909-936)
             sp.uz = np.full(sp.Ntot, uz_m)
@@ -328,8 +330,8 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     n_gpus = max(args.gpus, world)
     metric = 'particle-updates/s (PIC hot loop: gather+push+deposit+sort+spectral solve)'
-    workload = '%s periodic plasma + laser: Nz=%d/GPU Nr=%d Nm=%d ppc=%dx%dx%d linear' % (
-        (args.config, cfg['Nz'], cfg['Nr'], cfg['Nm']) + cfg['ppc'])
+    workload = '%s periodic plasma + laser: Nz=%d/GPU Nr=%d Nm=%d ppc=%dx%dx%d %s' % (
+        (args.config, cfg['Nz'], cfg['Nr'], cfg['Nm']) + cfg['ppc'] + (cfg.get('shape', 'linear'),))
     ncores = os.cpu_count() or 1
     nthreads = int(os.environ.get('ORACLE_NUM_THREADS', min(ncores, 64)))
 

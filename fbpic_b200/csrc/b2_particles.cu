@@ -515,6 +515,144 @@ __global__ void k_partition_scatter(int64_t n, const int32_t *__restrict__ p_sta
 // C ABI
 // =====================================================================================
 
+// ---- cubic shapes: the same tiling for the 4 x 4 stencil -------------------------------------------------------
+// (gather_field_gpu_cubic, gathering/cuda_methods.py:209-354: the reference walks the 16 points of every mode array
+//  in global memory per particle.)  One CTA = 128 consecutive (sorted) particles; the bounding box of their stencils
+//  -- rows iz_lowest .. iz_lowest + 3 unwrapped, columns after the reflection at the axis and the clamp at Nr - 1 --
+//  goes to shared memory once, every mode array; a CTA whose box does not fit GPC_TILE_CELLS cells (it straddles a
+//  z-row boundary of the sorted order) or a stray particle walks global memory like b2_gather_one.
+template <int NM>
+__global__ void __launch_bounds__(GP_TPB, 4)
+k_gather_push_tiled_cubic(int64_t n, double *__restrict__ x, double *__restrict__ y, double *__restrict__ z,
+                          double *__restrict__ ux, double *__restrict__ uy, double *__restrict__ uz,
+                          double *__restrict__ inv_gamma, double rmax_gather, double invdz, double zmin, int Nz,
+                          double invdr, double rmin, int Nr, B2Grids G, double econst, double bconst, double chdt,
+                          int32_t *__restrict__ cell_idx, double key_zmin) {
+    constexpr int GPC_TILE_CELLS = NM <= 3 ? 128 : 120;       // (48 KB of static shared memory at Nm = 4)
+    static_assert(GPC_TILE_CELLS <= GP_TPB, "one thread loads one tile cell");
+    __shared__ double2 tile[6 * NM][GPC_TILE_CELLS];
+    __shared__ int4 s_boxw[GP_TPB / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp_id = tid >> 5;
+    const int64_t i = blockIdx.x * (int64_t)GP_TPB + tid;
+    const bool in_range = i < n;
+    double xj = 0., yj = 0., zj = 0.;
+    if (in_range) { xj = x[i]; yj = y[i]; zj = z[i]; }
+    const B2Cyl c = b2_cyl(xj, yj, zj, invdz, zmin, invdr, rmin);
+    const bool active = in_range && (c.r < rmax_gather);
+    const int ir_lowest = (int)floor(c.r_cell) - 1, iz_lowest = (int)floor(c.z_cell) - 1;
+    int irs[4];
+    bool neg[4];
+    int ir_min = INT_MAX, ir_max = INT_MIN;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        int ir = ir_lowest + b;
+        neg[b] = (ir < 0);
+        if (ir < 0) ir = -ir - 1;
+        else if (ir > Nr - 1) ir = Nr - 1;
+        irs[b] = ir;
+        ir_min = min(ir_min, ir); ir_max = max(ir_max, ir);
+    }
+    const int a_z = __shfl_sync(0xffffffffu, iz_lowest, 0), a_r = __shfl_sync(0xffffffffu, ir_min, 0);
+    const bool near = active && abs(iz_lowest - a_z) <= 2 && ir_min >= a_r - 8 && ir_max <= a_r + 40;
+    {
+        const int b0 = __reduce_min_sync(0xffffffffu, near ? iz_lowest : INT_MAX);
+        const int b1 = __reduce_max_sync(0xffffffffu, near ? iz_lowest + 3 : INT_MIN);
+        const int b2 = __reduce_min_sync(0xffffffffu, near ? ir_min : INT_MAX);
+        const int b3 = __reduce_max_sync(0xffffffffu, near ? ir_max : INT_MIN);
+        if (lane == 0) s_boxw[warp_id] = make_int4(b0, b1, b2, b3);
+    }
+    __syncthreads();
+    int4 box = s_boxw[0];
+#pragma unroll
+    for (int w = 1; w < GP_TPB / 32; ++w) {
+        const int4 o = s_boxw[w];
+        box.x = min(box.x, o.x); box.y = max(box.y, o.y); box.z = min(box.z, o.z); box.w = max(box.w, o.w);
+    }
+    const int z0 = box.x, r0 = box.z;
+    const bool box_ok = (box.y >= box.x) && (box.w >= box.z);
+    const int nrow = box_ok ? box.y - z0 + 1 : 0, ncol = box_ok ? box.w - r0 + 1 : 0;
+    // (rows may hang over either end of the periodic box by the stencil reach: wrapped once by the loader)
+    const bool tile_ok = box_ok && (nrow * ncol <= GPC_TILE_CELLS) && z0 >= -Nz && box.y < 2 * Nz;
+    const bool use_tile = tile_ok && near;
+    if (tile_ok && tid < nrow * ncol) {
+        const int row = tid / ncol, col = tid - row * ncol;
+        int iz = z0 + row;
+        if (iz < 0) iz += Nz;
+        if (iz > Nz - 1) iz -= Nz;
+        const size_t o = (size_t)iz * Nr + r0 + col;
+#pragma unroll
+        for (int a = 0; a < 6 * NM; ++a) tile[a][tid] = __ldg(G.g[a] + o);
+    }
+    __syncthreads();
+    if (!in_range) return;
+    double F[6];
+    const unsigned live = __activemask();
+    const bool warp_on_tile = __all_sync(live, use_tile || !active);
+    if (warp_on_tile) {
+        double Fc[2][3] = {{0., 0., 0.}, {0., 0., 0.}};
+        if (active) {
+            double Sr[4], Sz[4];
+            const double rl = c.r_cell - ir_lowest;
+            Sr[0] = -1. / 6. * ((rl - 2.) * (rl - 2.) * (rl - 2.));
+            Sr[1] = 1. / 6. * (3. * ((rl - 1.) * (rl - 1.) * (rl - 1.)) - 6. * ((rl - 1.) * (rl - 1.)) + 4.);
+            Sr[2] = 1. / 6. * (3. * ((2. - rl) * (2. - rl) * (2. - rl)) - 6. * ((2. - rl) * (2. - rl)) + 4.);
+            Sr[3] = -1. / 6. * ((1. - rl) * (1. - rl) * (1. - rl));
+            const double zl = c.z_cell - iz_lowest;
+            Sz[0] = -1. / 6. * ((zl - 2.) * (zl - 2.) * (zl - 2.));
+            Sz[1] = 1. / 6. * (3. * ((zl - 1.) * (zl - 1.) * (zl - 1.)) - 6. * ((zl - 1.) * (zl - 1.)) + 4.);
+            Sz[2] = 1. / 6. * (3. * ((2. - zl) * (2. - zl) * (2. - zl)) - 6. * ((2. - zl) * (2. - zl)) + 4.);
+            Sz[3] = -1. / 6. * ((1. - zl) * (1. - zl) * (1. - zl));
+            const int t0 = (iz_lowest - z0) * ncol - r0;       // tile index of (row a, column ir) = t0 + a*ncol + ir
+            double e_re = 1., e_im = 0.;
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                const double flip = (m & 1) ? -1. : 1.;
+                const double factor = (m == 0) ? 1. : 2.;
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    double acc[3][2] = {{0., 0.}, {0., 0.}, {0., 0.}};
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const double sr_long = neg[b] ? Sr[b] * flip : Sr[b];
+                        const double sr_perp = neg[b] ? -Sr[b] * flip : Sr[b];
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            const int t = t0 + a * ncol + irs[b];
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                const double w = Sz[a] * ((k == 2) ? sr_long : sr_perp);
+                                const double2 v = tile[6 * m + 3 * f + k][t];
+                                acc[k][0] += w * v.x;
+                                acc[k][1] += w * v.y;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) Fc[f][k] += factor * (acc[k][0] * e_re - acc[k][1] * e_im);
+                }
+                const double nr = e_re * c.cs + e_im * c.sn, ni = e_im * c.cs - e_re * c.sn;
+                e_re = nr; e_im = ni;
+            }
+        }
+        F[0] = c.cs * Fc[0][0] - c.sn * Fc[0][1];
+        F[1] = c.sn * Fc[0][0] + c.cs * Fc[0][1];
+        F[2] = Fc[0][2];
+        F[3] = c.cs * Fc[1][0] - c.sn * Fc[1][1];
+        F[4] = c.sn * Fc[1][0] + c.cs * Fc[1][1];
+        F[5] = Fc[1][2];
+    } else {
+        b2_gather_one<NM, true>(c, G, rmax_gather, Nz, Nr, F);
+    }
+    double a = ux[i], b = uy[i], cz = uz[i], g = inv_gamma[i];
+    b2_vay(a, b, cz, g, F, econst, bconst);
+    ux[i] = a; uy[i] = b; uz[i] = cz; inv_gamma[i] = g;
+    const double xn = xj + chdt * g * 1. * a;
+    const double yn = yj + chdt * g * 1. * b;
+    const double zn = zj + chdt * g * 1. * cz;
+    x[i] = xn; y[i] = yn; z[i] = zn;
+    if (cell_idx) cell_idx[i] = b2_cell_of(b2_cyl(xn, yn, zn, invdz, key_zmin, invdr, rmin), Nz, Nr);
+}
+
 template <int NM>
 static void launch_gather(bool cubic, unsigned g, cudaStream_t s, int64_t n, const double *x, const double *y,
                           const double *z, double rg, double invdz, double zmin, int Nz, double invdr, double rmin,
@@ -528,7 +666,10 @@ static void launch_gather_push(bool cubic, unsigned g, cudaStream_t s, int64_t n
                                double *ux, double *uy, double *uz, double *ig, double rg, double invdz, double zmin,
                                int Nz, double invdr, double rmin, int Nr, const B2Grids &G, double ec, double bc,
                                double chdt, int32_t *cell_idx, double key_zmin) {
-    if (cubic) k_gather_push<NM, true><<<g, 256, 0, s>>>(n, x, y, z, ux, uy, uz, ig, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt, cell_idx, key_zmin);
+    // cubic shapes: tiled as well (B2_GATHER_CUBIC=plain: the thread-per-particle walk through global memory)
+    static const bool plain = []() { const char *e = getenv("B2_GATHER_CUBIC"); return e && !strcmp(e, "plain"); }();
+    if (cubic && plain) k_gather_push<NM, true><<<g, 256, 0, s>>>(n, x, y, z, ux, uy, uz, ig, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt, cell_idx, key_zmin);
+    else if (cubic) k_gather_push_tiled_cubic<NM><<<grid1d(n, GP_TPB), GP_TPB, 0, s>>>(n, x, y, z, ux, uy, uz, ig, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt, cell_idx, key_zmin);
     else k_gather_push_tiled<NM><<<grid1d(n, GP_TPB), GP_TPB, 0, s>>>(n, x, y, z, ux, uy, uz, ig, rg, invdz, zmin, Nz, invdr, rmin, Nr, G, ec, bc, chdt, cell_idx, key_zmin);
 }
 

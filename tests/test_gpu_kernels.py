@@ -147,6 +147,15 @@ def test_deposit_gather_vs_oracle_large(shape, Nm):
                F['Ex'], F['Ey'], F['Ez'], F['Bx'], F['By'], F['Bz'])
     for k in F:
         assert_close(getattr(sp, k).get(), F[k], 1e-13, 'gather ' + k)
+    # fused gather + push on the SORTED particles (the tiled kernels, linear and cubic: field tiles in shared memory)
+    # against the oracle's push with the oracle's gathered fields
+    Pu = {k: getattr(sp, k).get() for k in ('x', 'y', 'z', 'ux', 'uy', 'uz', 'inv_gamma')}
+    sp.gather_and_push(sim.fld.interp, sim.comm, 0.5 * dt)
+    orc.push_p(Pu['ux'], Pu['uy'], Pu['uz'], Pu['inv_gamma'], F['Ex'], F['Ey'], F['Ez'], F['Bx'], F['By'], F['Bz'],
+               sp.q, sp.m, dt)
+    orc.push_x(Pu['x'], Pu['y'], Pu['z'], Pu['ux'], Pu['uy'], Pu['uz'], Pu['inv_gamma'], 0.5 * dt)
+    for k in ('ux', 'uy', 'uz', 'inv_gamma', 'x', 'y', 'z'):
+        assert_close(getattr(sp, k).get(), Pu[k], 1e-13, 'fused gather+push ' + k)
 
 
 @pytest.mark.parametrize('Nz,Nr', [(64, 48), (200, 64), (37, 50), (128, 256)])
