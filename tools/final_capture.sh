@@ -11,7 +11,7 @@ python bench.py --impl reference --steps 20 --warmup 5 2>gpurun_out/bench_ref.er
 cut -c1-300 gpurun_out/${R}_bench_reference_arm.json
 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench_default.err | grep '^{' > gpurun_out/${R}_bench_default.json
 cut -c1-300 gpurun_out/${R}_bench_default.json
-for c in C1 C4 C4t C2w; do
+for c in C1 C4 C4t C2w C2c; do
   python bench.py --config $c --steps 20 --warmup 5 --no-cpu-baseline 2>gpurun_out/bench_$c.err | grep '^{' > gpurun_out/${R}_bench_$c.json
   cut -c1-200 gpurun_out/${R}_bench_$c.json
 done
