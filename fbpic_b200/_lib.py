@@ -279,7 +279,13 @@ def pinned_empty(shape, dtype):
     blocks are recycled through a size-keyed free list."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
-    cap = max(4096, 1 << (max(n, 1) - 1).bit_length()) if n < (1 << 20) else ((n + (1 << 20) - 1) >> 20) << 20
+    # (sizes above 1 MB are rounded up to 1/8 of their power of two: a species whose particle count drifts from call
+    #  to call -- moving window, injection -- still finds its buffers in the free list)
+    if n < (1 << 20):
+        cap = max(4096, 1 << (max(n, 1) - 1).bit_length())
+    else:
+        g = 1 << max(20, n.bit_length() - 4)
+        cap = (n + g - 1) // g * g
     free = _PINNED_FREE.get(cap)
     if free:
         ptr = free.pop()

@@ -1,7 +1,10 @@
 // b2_runtime.cu -- context, memory, streams, events, CUDA graphs (host side of the C ABI).
 // Replaces the cupy array/pool plumbing of the reference GPU path (fbpic/utils/cuda.py:101-182).
 #include "b2_common.cuh"
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 std::atomic<uint64_t> g_b2_launches{0};
 thread_local char g_b2_err[512] = "no error";
@@ -103,8 +106,65 @@ int b2_ctx_destroy(b2_ctx *ctx) {
 
 void *b2_ctx_stream(b2_ctx *ctx) { return (void *)ctx->stream; }
 
-int b2_malloc(void **p, size_t n) { B2_CUDA(cudaMalloc(p, n ? n : 16)); return 0; }
-int b2_free(void *p) { b2_dht_forget(p); B2_CUDA(cudaFree(p)); return 0; }
+// Device blocks are recycled through a size-keyed free list (the reference leans on cupy's memory pool for the
+// same reason, fbpic/utils/cuda.py): Simulation.step() drops and re-creates every state array at its entry / exit,
+// and cudaMalloc / cudaFree (a device-wide synchronisation each) of ~40 blocks of 16-134 MB took as long as the
+// PCIe copies themselves.  Reuse is safe in stream order: everything this library launches is ordered on the
+// context stream (the FFT lanes and NCCL join back into it).  B2_POOL_MB caps the parked bytes (default 65536);
+// when cudaMalloc runs out of memory the parked blocks are released and the call is retried.
+static std::mutex g_pool_mutex;
+static std::multimap<size_t, void *> g_pool_free;        // parked blocks by size
+static std::map<void *, size_t> g_pool_size;             // size of every block handed out or parked
+static size_t g_pool_bytes = 0;
+static size_t pool_round(size_t n) {
+    if (n < 16) n = 16;
+    if (n < (1u << 20)) return (n + 255) & ~(size_t)255;
+    // above 1 MB: multiples of 1/16 of the power of two below n, so that arrays whose length drifts from call to call
+    // (moving window, injection) find their blocks again
+    size_t g = (size_t)1 << 20;
+    while ((g << 5) <= n) g <<= 1;
+    return (n + g - 1) / g * g;
+}
+static void pool_release_all() {
+    for (auto &kv : g_pool_free) { g_pool_size.erase(kv.second); cudaFree(kv.second); }
+    g_pool_free.clear();
+    g_pool_bytes = 0;
+}
+int b2_malloc(void **p, size_t n) {
+    const size_t cap = pool_round(n);
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    auto it = g_pool_free.find(cap);
+    if (it != g_pool_free.end()) {
+        *p = it->second;
+        g_pool_bytes -= cap;
+        g_pool_free.erase(it);
+        return 0;
+    }
+    cudaError_t err = cudaMalloc(p, cap);
+    if (err == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        pool_release_all();
+        err = cudaMalloc(p, cap);
+    }
+    B2_CUDA(err);
+    g_pool_size[*p] = cap;
+    return 0;
+}
+int b2_free(void *p) {
+    if (!p) return 0;
+    b2_dht_forget(p);
+    static const size_t limit = []() { const char *e = getenv("B2_POOL_MB"); return (size_t)(e ? atoll(e) : 65536) << 20; }();
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    auto it = g_pool_size.find(p);
+    if (it != g_pool_size.end() && g_pool_bytes + it->second <= limit) {
+        g_pool_free.emplace(it->second, p);
+        g_pool_bytes += it->second;
+        return 0;
+    }
+    if (it != g_pool_size.end()) g_pool_size.erase(it);
+    B2_CUDA(cudaFree(p));
+    return 0;
+}
 int b2_host_alloc(void **p, size_t n) { B2_CUDA(cudaMallocHost(p, n ? n : 16)); return 0; }
 int b2_host_free(void *p) { B2_CUDA(cudaFreeHost(p)); return 0; }
 int b2_memcpy_h2d(void *d, const void *h, size_t n, void *s) {

@@ -41,6 +41,7 @@ int b2_ctx_destroy(b2_ctx *ctx);
 void *b2_ctx_stream(b2_ctx *ctx);
 const char *b2_error_string(void);
 const char *b2_version(void);
+/* device blocks are recycled through a size-keyed free list (B2_POOL_MB caps the parked bytes, default 65536) */
 int b2_malloc(void **d_ptr, size_t nbytes);
 int b2_free(void *d_ptr);
 int b2_host_alloc(void **h_ptr, size_t nbytes);       /* pinned host memory */
