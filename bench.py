@@ -435,7 +435,12 @@ def main():
     clocks = sampler.stop() if sampler else None
     launches = _lib.load().b2_launch_count() - launches0
     dht_flops = _lib.load().b2_dht_flops() - flops0
-    # second pass, same K steps, with CUDA events around every launch: per-kernel-family device time (roofline)
+    # second pass, same K steps, with CUDA events around every launch: per-kernel-family device time (roofline).
+    # The second-stream overlap of the post-exchange z-FFTs is off in this pass: events around a launch that shares
+    # the device with another stream would time the sharing, not the kernel.
+    overlap_eb = bool(sim.fld.side_allowed()) and (n_gpus > 1 or bool(cfg.get('window')))
+    sim.fld.join_side()
+    sim.fld._side_ok = False
     call.b2_profile_reset()
     call.b2_profile_enable(1)
     call.b2_event_record(ev0, ctx.stream)
@@ -443,6 +448,7 @@ def main():
     call.b2_event_record(ev1, ctx.stream)
     barrier()
     call.b2_profile_enable(0)
+    sim.fld._side_ok = None          # (re-evaluated at the next use)
     ms_prof = ctypes.c_float(0.)
     call.b2_event_elapsed_ms(ev0, ev1, ctypes.byref(ms_prof))
     prof = profile_table()
@@ -596,7 +602,7 @@ def main():
                    'n_order': -1 if n_gpus == 1 else 32, 'n_guard': sim.comm.n_guard, 'preroll_steps': args.preroll, 'sort_period': args.sort_period,
                    'l2': 'inputs larger than L2 (particle state %.1f GB per GPU)' % (Ntot_local * 64 / 1e9)},
         'gpu_launches': int(launches), 'host_enqueue_ms_per_step': round(host_enqueue_ms, 4),
-        'ms_per_step_instrumented': round(ms_prof.value / args.steps, 4), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline,
+        'ms_per_step_instrumented': round(ms_prof.value / args.steps, 4), 'overlap_eb_ffts': overlap_eb, 'clocks': clocks, 'e2e': e2e, 'roofline': roofline,
         'cpu_baseline': cpu_baseline, 'kernels': kernels,
     }
     if mgpu_parity is not None:

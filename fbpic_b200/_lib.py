@@ -56,6 +56,9 @@ _SIGNATURES = {
     'b2_memcpy_d2d': [P, P, c_size_t, P],
     'b2_memset': [P, c_int, c_size_t, P],
     'b2_stream_sync': [P],
+    'b2_stream_create': [ctypes.POINTER(P)],
+    'b2_stream_destroy': [P],
+    'b2_stream_wait_event': [P, P],
     'b2_device_sync': [],
     'b2_event_create': [ctypes.POINTER(P)],
     'b2_event_destroy': [P],

@@ -318,7 +318,9 @@ int b2_fft_own(b2_ctx *ctx, int na, const void *const *in, void *const *out, int
                                         return g < 1 ? 1 : (g > FF_GROUP ? FF_GROUP : g); }();
     const int group = group_env;
     void *scratch;
-    rc = b2_scratch(ctx, 2, sizeof(double2) * (size_t)group * Nz * Nr, &scratch);
+    // (a transform issued on another stream than the context's runs beside the context stream's own transforms:
+    //  private scratch)
+    rc = b2_scratch(ctx, s == ctx->stream ? 2 : 3, sizeof(double2) * (size_t)group * Nz * Nr, &scratch);
     if (rc) return rc;
     const unsigned ncol = (unsigned)((Nr + FF_C - 1) / FF_C);
     for (int g0 = 0; g0 < na; g0 += group) {

@@ -181,6 +181,9 @@ int b2_memset(void *p, int v, size_t n, void *s) {
     B2_CUDA(cudaMemsetAsync(p, v, n, (cudaStream_t)s)); g_b2_launches.fetch_add(1); return 0; }
 int b2_stream_sync(void *s) { B2_CUDA(cudaStreamSynchronize((cudaStream_t)s)); return 0; }
 int b2_device_sync(void) { B2_CUDA(cudaDeviceSynchronize()); return 0; }
+int b2_stream_create(void **s) { cudaStream_t st; B2_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); *s = (void *)st; return 0; }
+int b2_stream_destroy(void *s) { B2_CUDA(cudaStreamDestroy((cudaStream_t)s)); return 0; }
+int b2_stream_wait_event(void *s, void *e) { B2_CUDA(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)e, 0)); return 0; }
 int b2_event_create(void **e) { cudaEvent_t ev; B2_CUDA(cudaEventCreate(&ev)); *e = (void *)ev; return 0; }
 int b2_event_destroy(void *e) { B2_CUDA(cudaEventDestroy((cudaEvent_t)e)); return 0; }
 int b2_event_record(void *e, void *s) { B2_CUDA(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s)); return 0; }

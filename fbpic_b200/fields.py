@@ -13,6 +13,7 @@ Radial PML split fields (`use_pml`) and the cross-deposition current correction
  are built, and so is correct_divE (NumPy-only in the reference, a device kernel here).
 """
 import ctypes
+import os
 import numpy as np
 from scipy.constants import mu_0, epsilon_0
 
@@ -422,6 +423,7 @@ class Fields(object):
         self.data_is_on_gpu = True
 
     def receive_fields_from_gpu(self):
+        self.join_side()
         for m in range(self.Nm):
             self.interp[m].receive_fields_from_gpu()
             self.spect[m].receive_fields_from_gpu()
@@ -434,6 +436,7 @@ class Fields(object):
             if use_true_rho:
                 assert self.exchanged_source['rho_prev'] is True
                 assert self.exchanged_source['rho_next'] is True
+        self.join_side()       # the spectral E, B may still be on their way (partial_interp2spect(side=True))
         for m in range(self.Nm):
             self.spect[m].push_eb_with(self.psatd[m], use_true_rho)
             self.spect[m].push_rho()
@@ -451,11 +454,13 @@ class Fields(object):
 
     def correct_divE(self):
         """fields.py:298-311 (the reference runs this one with NumPy; here it is a device kernel)"""
+        self.join_side()
         for m in range(self.Nm):
             self.spect[m].correct_divE(self.psatd[m])
 
     def correct_currents_and_push(self, use_true_rho=False):
         """Fused Fields.correct_currents() + Fields.push() (single-domain fast path)."""
+        self.join_side()
         for m in range(self.Nm):
             self.spect[m].correct_and_push(self.psatd[m], use_true_rho)
             self.spect[m].push_rho()
@@ -465,6 +470,7 @@ class Fields(object):
         return fieldtype in ('E', 'B', 'J')
 
     def interp2spect(self, fieldtype):
+        self.join_side()
         for m in range(self.Nm):
             g, s, tr = self.interp[m], self.spect[m], self.trans[m]
             if self._vec(fieldtype):
@@ -482,6 +488,7 @@ class Fields(object):
                 raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
 
     def spect2interp(self, fieldtype):
+        self.join_side()
         for m in range(self.Nm):
             g, s, tr = self.interp[m], self.spect[m], self.trans[m]
             if self._vec(fieldtype):
@@ -510,6 +517,40 @@ class Fields(object):
             return [(getattr(s, fieldtype), g.rho)]
         raise ValueError('Invalid string for fieldtype: %s' % fieldtype)
 
+    # ---- second stream: transforms off the critical path of the step ----
+    def side_allowed(self):
+        """The z-FFTs that follow the guard-cell exchange of E and B rebuild the SPECTRAL arrays, which nothing reads
+        before the next field push: they may run on a second stream, under the particle kernels of the next step
+        (which leave half of the DRAM bandwidth idle).  Only with the library's own transform (a cuFFT plan must
+        not serve two streams at once); B2_OVERLAP_EB=0 switches it off."""
+        if getattr(self, '_side_ok', None) is None:
+            self._side_ok = os.environ.get('B2_OVERLAP_EB', '1') != '0' and \
+                bool(_lib.load().b2_fft_has_plan(self.Nz, 23))
+        return self._side_ok
+
+    def _fft_many_side(self, pairs, inverse):
+        """`_fft_many` on the second stream, ordered after everything issued so far on the context stream;
+        `join_side()` orders the context stream after it."""
+        ctx = _lib.context()
+        if getattr(self, '_side_stream', None) is None:
+            p, e0, e1 = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+            call.b2_stream_create(ctypes.byref(p))
+            call.b2_event_create(ctypes.byref(e0))
+            call.b2_event_create(ctypes.byref(e1))
+            self._side_stream, self._side_fork, self._side_join = p, e0, e1
+        call.b2_event_record(self._side_fork, ctx.stream)
+        call.b2_stream_wait_event(self._side_stream, self._side_fork)
+        call.b2_fft_z_multi(ctx.handle, len(pairs), ptr_array([a for a, _ in pairs]),
+                            ptr_array([b for _, b in pairs]), self.Nz, self.Nr, inverse, self._side_stream)
+        call.b2_event_record(self._side_join, self._side_stream)
+        self._side_pending = True
+
+    def join_side(self):
+        """Order the context stream after the transforms issued on the second stream (no host wait)."""
+        if getattr(self, '_side_pending', False):
+            call.b2_stream_wait_event(_lib.context().stream, self._side_join)
+            self._side_pending = False
+
     def _fft_many(self, pairs, inverse):
         """z-FFTs of independent arrays in one call (spread over concurrent lanes by the library)."""
         if not pairs:
@@ -519,11 +560,21 @@ class Fields(object):
 
     def spect2partial_interp(self, fieldtype):
         """iFFT along z only (fields.py:431-485)."""
+        if fieldtype != 'J':
+            self.join_side()
         self._fft_many([(sp, it) for m in range(self.Nm) for sp, it in self._partial_pairs(m, fieldtype)], 1)
 
-    def partial_interp2spect(self, fieldtype):
-        """FFT along z only (fields.py:487-537)."""
-        self._fft_many([(it, sp) for m in range(self.Nm) for sp, it in self._partial_pairs(m, fieldtype)], 0)
+    def partial_interp2spect(self, fieldtype, side=False):
+        """FFT along z only (fields.py:487-537).  `side`: on the second stream (see side_allowed); the caller
+        must not touch the spectral arrays of `fieldtype` before join_side()."""
+        pairs = [(it, sp) for m in range(self.Nm) for sp, it in self._partial_pairs(m, fieldtype)]
+        if side and pairs and self.side_allowed():
+            self.join_side()
+            self._fft_many_side(pairs, 0)
+            return
+        if fieldtype != 'J':
+            self.join_side()
+        self._fft_many(pairs, 0)
 
     # ---- fused transforms (single-domain fast path of Simulation.step) ----
     def _fused_tables(self, filter_currents):
@@ -585,6 +636,7 @@ class Fields(object):
     def fused_spect2interp_EB(self):
         """spect2interp('E') + spect2interp('B') (main.py:768-769): batched inverse Hankel
         transforms of all modes (1/Nz folded in), then the 6*Nm unscaled inverse FFTs."""
+        self.join_side()
         T = self._fused_tables(getattr(self, '_fused_key', True))
         ctx = _lib.context()
         jobs, ffts = [], []
@@ -641,6 +693,7 @@ class Fields(object):
     def fused_spect2interp_EB_pml(self):
         """spect2interp of 'E', 'B', 'E_pml', 'B_pml' (main.py:732-737) as batched inverse Hankel launches of all modes
         (1/Nz folded into the matrices) followed by one multi-lane call of unscaled inverse FFTs."""
+        self.join_side()
         T = self._fused_tables(getattr(self, '_fused_key', True))
         P = self._pml_buffers()
         jobs, ffts = [], []
@@ -662,6 +715,7 @@ class Fields(object):
     def fused_interp2spect_EB_pml(self):
         """interp2spect of 'E', 'B', 'E_pml', 'B_pml' (main.py:757-761): one multi-lane call of forward FFTs, then
         batched forward Hankel launches with the (r,t)->(p,m) combination in their prologue."""
+        self.join_side()
         T = self._fused_tables(getattr(self, '_fused_key', True))
         P = self._pml_buffers()
         jobs, ffts = [], []
@@ -691,6 +745,7 @@ class Fields(object):
         return
 
     def filter_spect(self, fieldtype):
+        self.join_side()
         for m in range(self.Nm):
             self.spect[m].filter(fieldtype)
 

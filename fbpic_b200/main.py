@@ -371,7 +371,9 @@ class Simulation(object):
                 self.comm.damp_EB_open_boundary(fld.interp)
                 for mirror in self.mirrors:           # main.py:751-753 (rows in z: valid in (z, kr) space)
                     mirror.set_fields_to_zero(fld.interp, self.comm, self.time)
-                fld.partial_interp2spect('EB')
+                # (the spectral arrays are next read by the field push of the following cycle: these 6*Nm forward
+                #  transforms go to the second stream and run under that cycle's particle kernels)
+                fld.partial_interp2spect('EB', side=True)
                 # the exchanged (z, kr) arrays go straight to real space: inverse Hankel only
                 fld.fused_partial2interp_EB()
                 return

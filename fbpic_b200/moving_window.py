@@ -26,6 +26,7 @@ class MovingWindow(object):
 
     def move_grids(self, fld, ptcl, comm, time):
         """moving_window.py:60-132"""
+        fld.join_side()        # the shift touches the spectral E, B
         dz = comm.dz
         if comm.rank == 0:
             self.zmin += self.v * (time - self.t_last_move)

@@ -51,6 +51,12 @@ int b2_memcpy_d2h(void *h_dst, const void *d_src, size_t nbytes, void *stream);
 int b2_memcpy_d2d(void *d_dst, const void *d_src, size_t nbytes, void *stream);
 int b2_memset(void *d_ptr, int value, size_t nbytes, void *stream);
 int b2_stream_sync(void *stream);
+/* a second stream for work that is off the critical path of the step (the z-FFTs that follow the guard-cell exchange
+ * of E and B, boundary_communicator.py / main.py:741-766, are needed only by the next field push); a transform issued
+ * on it uses its own scratch.  Order against the context stream with events. */
+int b2_stream_create(void **stream);
+int b2_stream_destroy(void *stream);
+int b2_stream_wait_event(void *stream, void *event);
 int b2_device_sync(void);
 int b2_event_create(void **event);
 int b2_event_destroy(void *event);

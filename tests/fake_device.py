@@ -130,6 +130,20 @@ class FakeLib(object):
     def b2_stream_sync(self, stream):
         return 0
 
+    def b2_fft_has_plan(self, Nz, max_radix):
+        return 1
+
+    # a second stream: the stand-in executes every call at once, in program order
+    def b2_stream_create(self, p):
+        p._obj.value = 0x5717
+        return 0
+
+    def b2_stream_destroy(self, stream):
+        return 0
+
+    def b2_stream_wait_event(self, stream, e):
+        return 0
+
     # events and the per-kernel profiler: host clock, no per-kernel records
     def b2_event_create(self, p):
         p._obj.value = len(self.calls) + 1
