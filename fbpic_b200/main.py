@@ -112,7 +112,11 @@ class Simulation(object):
         if self.comm.moving_win is not None:          # main.py:390-395
             for species in self.ptcl:
                 if species.continuous_injection and species.injector is not None:
-                    z_host = species.z.get() if species.data_is_on_gpu else species.z
+                    # (the positions are read only by the first call on the last rank, to find the end of the
+                    #  plasma: no 8-byte-per-particle download at the entry of every later step() call)
+                    need_z = species.injector.z_inject is None and self.comm.rank == self.comm.size - 1
+                    z_host = np.empty(0) if not need_z else \
+                        (species.z.get() if species.data_is_on_gpu else species.z)
                     species.injector.initialize_injection_positions(
                         self.comm, self.comm.moving_win.v, z_host, self.dt)
         single = (self.comm.size == 1)
