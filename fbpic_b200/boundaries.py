@@ -307,6 +307,12 @@ class BoundaryCommunicator(object):
         zlo = g0.zmin + ng * g0.dz
         zhi = g0.zmax - ng * g0.dz
         N = species.Ntot
+        # new plasma entering through the right edge (boundary_communicator.py:803-810): generated on the host FIRST
+        # -- it does not depend on the classification, whose call returns counts and therefore waits for every cycle
+        # still queued on the device; the 4 ms of NumPy work per exchange now run under those cycles
+        injected = None
+        if (self.moving_win is not None) and (self.rank == self.size - 1) and species.continuous_injection:
+            injected = species.generate_continuously_injected_particles(time)
         counts = (ctypes.c_int64 * 3)()
         call.b2_exchange_classify(ctx.handle, N, species.z.ptr, zlo, zhi, counts, None)
         n_stay, n_left, n_right = int(counts[0]), int(counts[1]), int(counts[2])
@@ -327,10 +333,7 @@ class BoundaryCommunicator(object):
             call.b2_nccl_group_end()
             h = cnt.get()
             n_recv_l, n_recv_r = int(h[2]), int(h[3])
-        injected = None
-        if (self.moving_win is not None) and (self.rank == self.size - 1) and species.continuous_injection:
-            # new plasma entering through the right edge (boundary_communicator.py:803-810)
-            injected = species.generate_continuously_injected_particles(time)
+        if injected is not None:
             n_recv_r = injected.shape[1]
         n_new = n_recv_l + n_stay + n_recv_r
         new = species.exchange_buffers(n_new)       # spare sort buffers: no allocation in steady state
