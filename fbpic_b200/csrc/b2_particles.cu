@@ -806,9 +806,9 @@ int b2_gather_push(b2_ctx *ctx, int64_t n, double *x, double *y, double *z, doub
     cudaStream_t s = b2_stream_of(ctx, stream);
     const double ec = q * dt_p / (m * B2_C_LIGHT), bc = 0.5 * q * dt_p / m, chdt = B2_C_LIGHT * dt_x;
     if (!cubic) {
-        // linear shapes: the persistent kernel with TMA-staged field tiles (b2_gather_pipe.cu) takes the full
-        // 128-particle chunks; what is left (n % 128 particles, or everything when that path is unavailable)
-        // goes to the kernels of this file
+        // linear shapes, B2_GATHER_IMPL=pipe only: the persistent kernel with TMA-staged field tiles
+        // (b2_gather_pipe.cu) takes the full 128-particle chunks and reports how many it did; what is left (n % 128
+        // particles -- or everything, by default) goes to the tiled kernels of this file
         int64_t done = 0;
         int rc = b2_gather_push_pipe(ctx, n, x, y, z, ux, uy, uz, inv_gamma, rmax_gather, invdz, zmin, Nz, invdr, rmin,
                                      Nr, Nm, grids, ec, bc, chdt, cell_idx, key_zmin, s, &done);

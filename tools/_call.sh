@@ -1,4 +1,2 @@
-timeout 300 python -m pytest tests/test_gpu_step.py tests/test_gpu_w4_scripts.py tests/test_gpu_w6_acceptance.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -2
-python bench.py --config C2w --steps 20 --warmup 5 --no-cpu-baseline 2>gpurun_out/bench_C2w.err | grep "^{" > gpurun_out/r02_bench_C2w.json; python -c "
-import json
-d=json.load(open('gpurun_out/r02_bench_C2w.json')); print('C2w', d['value'], d['ms_per_step'], d['host_enqueue_ms_per_step'], d['e2e']['value'])"
+python __graft_entry__.py --smoke 2>&1 | tail -1
+timeout 400 ncu --set full --import-source on --clock-control none -k regex:"k_dht_tma|k_gather_push|k_deposit_mma|k_fft_pass|k_spectral" --launch-skip 110 -c 16 -o gpurun_out/r02_hot -f python bench.py --steps 4 --warmup 3 --preroll 8 --no-e2e --no-cpu-baseline > gpurun_out/ncu_hot.log 2>&1; tail -1 gpurun_out/ncu_hot.log
