@@ -200,12 +200,18 @@ class FakeLib(object):
         return 0
 
     def b2_permute(self, ctx, n, sorted_idx, n_arrays, src, dst, stream):
+        self._check_na(n_arrays)
         perm = _arr(sorted_idx, n, np.int64) if _addr(sorted_idx) else self._perm
         assert perm is not None and len(perm) == n
         span = int(perm.max()) + 1 if n else 0        # dst[i] = src[idx[i]]: a gather, the source may be longer
         for s, d in zip(_ptrs(src, n_arrays), _ptrs(dst, n_arrays)):
             _arr(d, n)[:] = _arr(s, span)[perm]
         return 0
+
+    @staticmethod
+    def _check_na(na):
+        # the real library refuses more pointers than one multi-array launch carries (B2_MAX_ARRAYS, fbpic_b200.h)
+        assert na <= 32, 'too many arrays (B2_MAX_ARRAYS = 32)'
 
     def _grids(self, grids, count, Nz, Nr):
         return [_grid(p, Nz, Nr) for p in _ptrs(grids, count)]
@@ -265,6 +271,7 @@ class FakeLib(object):
         return 0
 
     def b2_exchange_scatter(self, ctx, n, z, zlo, zhi, n_arrays, src, stay, left, right, stream):
+        self._check_na(n_arrays)
         assert self._part is not None and self._part[0] == n
         _, l, r = self._part
         s = ~(l | r)
@@ -333,12 +340,14 @@ class FakeLib(object):
 
     # ---------------------------------------------------------------- grids
     def b2_scale_rows_by_r(self, ctx, na, arrays, v, Nz, Nr, stream):
+        self._check_na(na)
         s = _arr(v, Nr)
         for a in self._grids(arrays, na, Nz, Nr):
             a *= s[None, :]
         return 0
 
     def b2_filter(self, ctx, na, arrays, fz, fr, Nz, Nr, stream):
+        self._check_na(na)
         f = _arr(fz, Nz)[:, None] * _arr(fr, Nr)[None, :]
         for a in self._grids(arrays, na, Nz, Nr):
             a *= f
@@ -436,6 +445,7 @@ class FakeLib(object):
         return self._spectral(mode, comoving, dt, V, use_true_rho, Nz, Nr, True, True)
 
     def b2_damp_z(self, ctx, na, arrays, damp, nd, left, right, Nz, Nr, stream):
+        self._check_na(na)
         d = _arr(damp, nd)
         for a in self._grids(arrays, na, Nz, Nr):
             if left:
@@ -445,6 +455,7 @@ class FakeLib(object):
         return 0
 
     def b2_shift_spect(self, ctx, na, arrays, shift, n_move, Nz, Nr, stream):
+        self._check_na(na)
         sft = _arr(shift, Nz, np.complex128)
         pw = np.ones(Nz, dtype=np.complex128)
         for _ in range(abs(n_move)):
@@ -461,6 +472,7 @@ class FakeLib(object):
 
     # ---------------------------------------------------------------- z-slab exchange: gloo stands in for NCCL
     def b2_halo_stage(self, ctx, mode, na, arrays, row0, nrow, Nr, packed, stream):
+        self._check_na(na)
         if na <= 0 or nrow <= 0:
             return 0
         pk = _arr(packed, na * nrow * Nr, np.complex128).reshape(na, nrow, Nr)
